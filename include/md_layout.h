@@ -1,0 +1,234 @@
+/* md_layout.h — array layouts (column indices) of the batched MetaDrive step.
+ *
+ * DATA LAYOUT ONLY: no algorithm lives here.  The same flat arrays are consumed by the CUDA library
+ * (metadrive_ped_b200/csrc), by the CPU oracle (oracle/md_oracle.c) and are produced by the Python
+ * scene builder (metadrive_ped_b200/scene.py), so all three agree on what a column means.
+ *
+ * All float arrays are float32 row-major, all int arrays int32 row-major.
+ * "NV" = n_envs * slots_per_env vehicle slots (agents first in every env), "NO" = n_envs * objs_per_env.
+ */
+#ifndef MD_LAYOUT_H
+#define MD_LAYOUT_H
+
+/* ---- map tables (one set per distinct map, concatenated; MAPD_* gives offsets) ---------------- */
+/* lane_f [Ltot, 16]  (reference: component/lane/straight_lane.py:12-47, circular_lane.py:12-51) */
+#define LANE_F 16
+#define LF_TYPE 0    /* 0 straight, 1 circular */
+#define LF_WIDTH 1
+#define LF_LENGTH 2
+#define LF_P0 3      /* straight: sx sy ex ey dirx diry heading ; circular: cx cy radius start_phase end_phase direction angle */
+#define LF_SX 10     /* lane.start */
+#define LF_SY 11
+#define LF_EX 12     /* lane.end */
+#define LF_EY 13
+#define LF_HULL_LONG 14 /* straight lanes: last polygon sample longitude (hull = [0, this] x [-w/2, w/2]) */
+#define LF_SPARE 15
+/* lane_i [Ltot, 8] */
+#define LANE_I 8
+#define LI_ROAD 0    /* road id local to the map */
+#define LI_IDX 1     /* lane index inside the road, 0 = left-most */
+#define LI_FROM 2    /* node ids local to the map */
+#define LI_TO 3
+#define LI_HULL_OFF 4 /* offset into hull_xy (local to the map), convex CCW polygon */
+#define LI_HULL_N 5
+#define LI_LINE_L 6  /* line type of the left / right border (0 none 1 broken 2 continuous 3 side 4 guardrail) */
+#define LI_LINE_R 7
+/* lane_bb [Ltot, 4]: hull AABB xmin ymin xmax ymax */
+/* road_i [Rtot, 6] */
+#define ROAD_I 6
+#define RI_FROM 0
+#define RI_TO 1
+#define RI_FIRST 2   /* first lane id (local to the map) */
+#define RI_N 3
+#define RI_NEG 4     /* Road.is_negative_road() */
+#define RI_BLOCK 5   /* ord(block id char) */
+/* line_f [Stot, 6]: static-world lane-line boxes (component/block/base_block.py:468-519) */
+#define LINE_F 6
+#define LN_CX 0
+#define LN_CY 1
+#define LN_UX 2      /* unit direction */
+#define LN_UY 3
+#define LN_HALF 4    /* half length; half width is 0.0375 */
+#define LN_KIND 5    /* 0 white solid, 1 yellow solid, 2 white broken, 3 yellow broken */
+/* quad_f [Qtot, 8]: sidewalk strip quads, 4 corners CCW (component/pgblock/pg_block.py:294-332) */
+#define QUAD_F 8
+/* map_desc [M, 16] int32 */
+#define MAPD 16
+#define MD_LANE_OFF 0
+#define MD_N_LANES 1
+#define MD_ROAD_OFF 2
+#define MD_N_ROADS 3
+#define MD_HULL_OFF 4
+#define MD_LINE_OFF 5
+#define MD_N_LINES 6
+#define MD_QUAD_OFF 7
+#define MD_N_QUADS 8
+#define MD_GRID_OFF 9   /* offset into grid_start (cells+1 entries per map) */
+#define MD_GRID_NX 10
+#define MD_GRID_NY 11
+#define MD_ITEM_OFF 12  /* offset into grid_items */
+#define MD_MAX_LANE_NUM 13 /* lane_num of the map config (navigation normalisation) */
+/* map_descf [M, 4] float: grid origin x, y, cell size, spare */
+#define MAPDF 4
+
+/* ---- per-vehicle-slot arrays ------------------------------------------------------------------ */
+/* veh_p [NV, 16]: static parameters (component/vehicle/vehicle_type.py, component/pg_space.py:226-272) */
+#define VEH_P 16
+#define VP_TYPE 0
+#define VP_LENGTH 1
+#define VP_WIDTH 2
+#define VP_HEIGHT 3
+#define VP_MASS 4
+#define VP_TIRE_R 5
+#define VP_LATERAL 6
+#define VP_FRONT_WB 7
+#define VP_REAR_WB 8
+#define VP_CHASSIS_AXIS 9
+#define VP_ENGINE 10
+#define VP_BRAKE 11
+#define VP_MAX_STEER 12   /* degrees */
+#define VP_FRICTION 13
+#define VP_MAX_SPEED 14   /* km/h */
+#define VP_REVERSE 15
+/* veh_s [NV, 16]: rigid-body state */
+#define VEH_S 16
+#define VS_POS 0     /* 3 */
+#define VS_QUAT 3    /* 4: w x y z */
+#define VS_VEL 7     /* 3 */
+#define VS_ANGVEL 10 /* 3 */
+#define VS_STEER 13  /* last applied steering action in [-1,1] */
+#define VS_THROTTLE 14
+#define VS_SPARE 15
+/* veh_c [NV, 16]: per-step latches + episode accumulators (component/vehicle/base_vehicle.py:211-232) */
+#define VEH_C 16
+#define VC_LAST_X 0
+#define VC_LAST_Y 1
+#define VC_LAST_HX 2     /* last_heading_dir */
+#define VC_LAST_HY 3
+#define VC_PREV_A0 4     /* last_current_action[0] */
+#define VC_PREV_A1 5
+#define VC_CUR_A0 6      /* last_current_action[1] */
+#define VC_CUR_A1 7
+#define VC_DIST_L 8
+#define VC_DIST_R 9
+#define VC_ENERGY 10
+#define VC_EP_REWARD 11
+#define VC_STEP_ENERGY 12
+#define VC_TOTAL_COST 13
+/* veh_i [NV, 16] */
+#define VEH_I 16
+#define VI_KIND 0        /* 0 empty, 1 agent, 2 traffic */
+#define VI_ALIVE 1       /* body is in the world (visible to lidar / collisions) */
+#define VI_ACTIVE 2      /* acts and is localised this step */
+#define VI_TRIGGER 3     /* block index whose trigger activates this traffic vehicle, -1 = always */
+#define VI_LANE 4        /* current lane id (local to the map), -1 unknown */
+#define VI_CKPT0 5
+#define VI_CKPT1 6
+#define VI_ROUTE_LEN 7
+#define VI_FLAGS 8
+#define VI_ROUTING_LANE 9 /* IDM routing_target_lane, -1 = None */
+#define VI_STATIC 10
+#define VI_EP_LEN 11
+#define VI_DONE 12       /* agent finished (auto-reset pending) */
+#define VI_SPAWN_LANE 13
+/* veh_route [NV, 24]: checkpoint node ids, -1 padded */
+#define ROUTE_MAX 24
+/* veh_idm [NV, 8] (policy/idm_policy.py:224-233) */
+#define VEH_IDM 8
+#define VD_TIMER 0
+#define VD_TARGET_SPEED 1
+#define VD_H_PERR 2
+#define VD_H_IERR 3
+#define VD_L_PERR 4
+#define VD_L_IERR 5
+#define VD_RNG 6         /* counter of the build-defined hash RNG that replaces np_random.randint */
+/* veh_navi [NV, 10]: navigation info (node_network_navigation.py:243-292) */
+#define NAVI_DIM 10
+
+/* flag bits in VI_FLAGS (component/vehicle/base_vehicle.py:36-62) */
+#define FL_CRASH_VEHICLE 0x001
+#define FL_CRASH_OBJECT 0x002
+#define FL_CRASH_BUILDING 0x004
+#define FL_CRASH_HUMAN 0x008
+#define FL_CRASH_SIDEWALK 0x010
+#define FL_ON_WHITE 0x020
+#define FL_ON_YELLOW 0x040
+#define FL_ON_BROKEN 0x080
+#define FL_ON_LANE 0x100
+#define FL_OUT_OF_ROUTE 0x200
+/* extra bits only in the info word returned by md_step */
+#define FL_OUT_OF_ROAD 0x400
+#define FL_ARRIVE 0x800
+#define FL_MAX_STEP 0x1000
+
+/* ---- per-object arrays: obj_f [NO, 12] --------------------------------------------------------- */
+#define OBJ_F 12
+#define OB_KIND 0    /* -1 empty, 0 cone, 1 warning, 2 barrier, 3 pedestrian */
+#define OB_X 1
+#define OB_Y 2
+#define OB_HEADING 3
+#define OB_A 4       /* radius (cylinders) or half length along heading (barrier) */
+#define OB_B 5       /* half width (barrier) */
+#define OB_HEIGHT 6
+#define OB_ZC 7      /* z of the shape centre */
+#define OB_LANE 8    /* lane id as float, -1 none */
+#define OB_CRASHED 9 /* COST_ONCE latch (static_object/traffic_object.py:27) */
+#define OB_VX 10     /* pedestrians: planar velocity */
+#define OB_VY 11
+
+/* ---- per-env ints: env_i [E, 8] ------------------------------------------------------------------ */
+#define ENV_I 8
+#define EI_MAP 0
+#define EI_NEXT_TRIGGER 1  /* index of the next block whose vehicles are still waiting; 0 = none left */
+#define EI_STEP 2          /* engine.episode_step */
+#define EI_N_BLOCKS 3
+#define EI_SEED 4
+/* env_trigger [E, 8]: trigger road id (local to map) per block index */
+#define TRIGGER_MAX 8
+
+/* ---- observation row (obs/state_obs.py:64-151, 185-232), N = 240, num_others = 0 ---------------- */
+#define OBS_EGO 9
+#define OBS_NAVI 10
+#define OBS_STATE (OBS_EGO + OBS_NAVI)
+
+/* ---- configuration passed by value through the C ABI ------------------------------------------- */
+typedef struct MdConfig {
+    int n_envs, slots_per_env, agents_per_env, objs_per_env;
+    int n_lasers, horizon, decision_repeat, traffic_mode; /* 0 trigger, 1 respawn, 2 hybrid */
+    float dt, lidar_dist;
+    float success_reward, out_of_road_penalty, crash_vehicle_penalty, crash_object_penalty;
+    float driving_reward, speed_reward;
+    float crash_vehicle_cost, crash_object_cost, out_of_road_cost;
+    int use_lateral_reward, out_of_route_done, on_continuous_line_done;
+    int crash_vehicle_done, crash_object_done, crash_human_done, truncate_as_terminate;
+    int enable_idm_lane_change, is_multi_agent, delay_done, spare0;
+} MdConfig;
+
+/* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */
+typedef struct MdArrays {
+    /* maps */
+    const int* map_desc;      /* [M, MAPD] */
+    const float* map_descf;   /* [M, MAPDF] */
+    const float* lane_f;      /* [Ltot, LANE_F] */
+    const int* lane_i;        /* [Ltot, LANE_I] */
+    const float* lane_bb;     /* [Ltot, 4] */
+    const int* road_i;        /* [Rtot, ROAD_I] */
+    const float* hull_xy;     /* [Htot, 2] */
+    const float* line_f;      /* [Stot, LINE_F] */
+    const float* quad_f;      /* [Qtot, QUAD_F] */
+    const int* grid_start;    /* per map: nx*ny+1 */
+    const int* grid_items;    /* item < n_lines: line id ; else quad id + n_lines (ids local to the map) */
+    /* scenario / state */
+    int* env_i;               /* [E, ENV_I] */
+    const int* env_trigger;   /* [E, TRIGGER_MAX] */
+    const float* veh_p;       /* [NV, VEH_P] */
+    float* veh_s;             /* [NV, VEH_S] */
+    float* veh_c;             /* [NV, VEH_C] */
+    int* veh_i;               /* [NV, VEH_I] */
+    const int* veh_route;     /* [NV, ROUTE_MAX] */
+    float* veh_idm;           /* [NV, VEH_IDM] */
+    float* veh_navi;          /* [NV, NAVI_DIM] */
+    float* obj_f;             /* [NO, OBJ_F] */
+} MdArrays;
+
+#endif

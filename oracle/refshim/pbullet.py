@@ -537,8 +537,13 @@ class BulletWorld:
 
     def remove(self, obj):
         if isinstance(obj, BulletVehicle):
+            # panda3d BulletWorld::do_remove_vehicle also removes the chassis body
+            # (the reference relies on it: base_class/base_object.py:90-93 breaks after the vehicle)
             if obj in self.vehicles:
                 self.vehicles.remove(obj)
+            if obj.chassis in self.bodies:
+                self.bodies.remove(obj.chassis)
+                obj.chassis.world = None
         elif obj in self.bodies:
             self.bodies.remove(obj)
             obj.world = None
