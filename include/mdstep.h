@@ -1,0 +1,93 @@
+/* mdstep.h — C ABI of libmdstep.so, the B200-native batched MetaDrive step.
+ *
+ * The reference (zhuhaozh/metadrive_ped = MetaDrive v0.4.2.2) exposes this path as a Python class surface, not
+ * an FFI; the arithmetic lives behind panda3d.bullet.  Each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/metadrive).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions: plain pointers and sizes only; all `*_dev` buffers are caller-owned CUDA device memory (e.g.
+ * torch tensors' data_ptr()), contiguous, float32 / int32 / uint8; `stream` is a cudaStream_t passed as void*.
+ * Calls enqueue kernels on `stream` and return without synchronising (except the *_host variants and
+ * md_get_state / md_set_state, which are synchronous).  One handle per device; a handle is not thread-safe.
+ * Return value: 0 on success, negative on error (md_last_error gives the text).
+ */
+#ifndef MDSTEP_H
+#define MDSTEP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "md_layout.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct md_sim md_sim;
+
+#define MD_ABI_VERSION 1
+int md_abi_version(void);
+
+/* engine construction: replaces initialize_engine / BaseEngine.__init__ + PhysicsWorld
+ * (engine/engine_utils.py:8-15, engine/base_engine.py:51-96, engine/core/physics_world.py:9-17) */
+int md_create(const MdConfig* cfg, int device, md_sim** out);
+void md_destroy(md_sim* sim);
+const char* md_last_error(const md_sim* sim);
+
+/* scene upload: replaces PGMap/BaseBlock.create_in_world + manager.reset() spawning bodies into the Bullet worlds
+ * (component/pgblock/pg_block.py:248-256, component/block/base_block.py:431-519, manager/traffic_manager.py:51-72,
+ * manager/object_manager.py:40-91).  `host` holds HOST pointers in the md_layout.h layouts; `rows[i]` is the row
+ * count of the i-th array in MdArrays field order.  The library copies everything and keeps a device snapshot of the
+ * mutable arrays as the reset state.  Caller keeps ownership of the host buffers. */
+int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* rows);
+
+/* env.reset(): replaces BaseEnv.reset -> engine.reset + _get_reset_return (envs/base_env.py:502-584).
+ * Restores the snapshot of every env whose mask byte is non-zero (all envs if env_mask_dev == NULL), runs the
+ * reset-time after_step and writes the first observation of their agents into obs_dev [A, 19 + n_lasers]. */
+int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev, void* stream);
+
+/* env.step(): replaces BaseEnv.step = _step_simulator + _get_step_return (envs/base_env.py:426-463, 586-623):
+ * engine.before_step (agent actuation, trigger, IDM), decision_repeat x doPhysics + contact callback,
+ * engine.after_step (localisation, state check), reward / cost / done, LidarStateObservation.observe.
+ * actions_dev [A,2]; obs_dev [A, 19+n_lasers]; reward/cost [A] f32; terminated/truncated [A] u8;
+ * info_flags [A] i32 (FL_* bits); info_f [A,8] f32 = velocity, steering, acceleration, step_energy, episode_energy,
+ * step_reward, episode_reward, episode_length. */
+int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
+            uint8_t* terminated_dev, uint8_t* truncated_dev, int32_t* info_flags_dev, float* info_f_dev, void* stream);
+
+/* batched auto-reset on device: every env whose agents are all terminated or truncated is restored to its snapshot
+ * and its agents' observation rows are overwritten with the reset observation (the user-side loop
+ * `if done: env.reset()` of examples/profile_metadrive.py:26-29, without a host round trip). */
+int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, void* stream);
+
+/* the same step through HOST buffers: pinned staging, H2D of actions and D2H of all outputs on the sim's own stream,
+ * synchronous.  This is the call the Gymnasium-surface classes make. */
+int md_step_host(md_sim* sim, const float* actions, float* obs, float* reward, float* cost, uint8_t* terminated,
+                 uint8_t* truncated, int32_t* info_flags, float* info_f, int autoreset);
+int md_reset_host(md_sim* sim, const uint8_t* env_mask, float* obs);
+
+/* isolated stages, for parity tests and per-kernel ncu captures */
+/* Lidar.perceive (component/sensors/lidar.py:49-73; sensors/distance_detector.py:27-85): frac_dev [A,n_lasers] in
+ * [0,1]; hit_dev [A,n_lasers] = hit vehicle slot, slots_per_env + object index, or -1 */
+int md_lidar(md_sim* sim, float* frac_dev, int32_t* hit_dev, void* stream);
+/* n_sub x BulletWorld.doPhysics(dt,1,dt) for every vehicle with given actuation act3_dev [NV,3] = steering rad,
+ * engine force, brake (component/vehicle/base_vehicle.py:447-484; engine/core/engine_core.py:350-352) */
+int md_dynamics(md_sim* sim, const float* act3_dev, int n_sub, void* stream);
+/* BaseVehicle.after_step for every active vehicle (component/vehicle/base_vehicle.py:234-253, 700-792) */
+int md_after_step(md_sim* sim, void* stream);
+/* IDMPolicy.act for every active traffic vehicle (policy/idm_policy.py:235-267): out_dev [NV,2] */
+int md_idm(md_sim* sim, float* out_actions_dev, void* stream);
+
+/* snapshots: BaseObject.get_state / set_state (base_class/base_object.py:435-452).  `name` is an MdArrays field
+ * name ("veh_s", "veh_i", "obj_f", ...); synchronous host <-> device copy of the whole array. */
+int md_get_state(md_sim* sim, const char* name, void* host_dst, size_t bytes);
+int md_set_state(md_sim* sim, const char* name, const void* host_src, size_t bytes);
+/* make the current device state the snapshot md_reset restores */
+int md_snapshot(md_sim* sim);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t md_launch_count(const md_sim* sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,44 @@
+"""ctypes mirror of include/md_layout.h (MdConfig, MdArrays). Data definitions only."""
+import ctypes as C
+
+from .scene import ARRAY_ORDER
+
+
+class MdConfig(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int), ("slots_per_env", C.c_int), ("agents_per_env", C.c_int), ("objs_per_env", C.c_int),
+        ("n_lasers", C.c_int), ("horizon", C.c_int), ("decision_repeat", C.c_int), ("traffic_mode", C.c_int),
+        ("dt", C.c_float), ("lidar_dist", C.c_float),
+        ("success_reward", C.c_float), ("out_of_road_penalty", C.c_float), ("crash_vehicle_penalty", C.c_float),
+        ("crash_object_penalty", C.c_float), ("driving_reward", C.c_float), ("speed_reward", C.c_float),
+        ("crash_vehicle_cost", C.c_float), ("crash_object_cost", C.c_float), ("out_of_road_cost", C.c_float),
+        ("use_lateral_reward", C.c_int), ("out_of_route_done", C.c_int), ("on_continuous_line_done", C.c_int),
+        ("crash_vehicle_done", C.c_int), ("crash_object_done", C.c_int), ("crash_human_done", C.c_int),
+        ("truncate_as_terminate", C.c_int), ("enable_idm_lane_change", C.c_int), ("is_multi_agent", C.c_int),
+        ("delay_done", C.c_int), ("spare0", C.c_int),
+    ]
+
+
+TRAFFIC_MODES = {"trigger": 0, "respawn": 1, "hybrid": 2}
+
+
+def make_config(n_envs, slots_per_env, agents_per_env=1, objs_per_env=0, **kw):
+    """MdConfig with the reference's defaults (envs/metadrive_env.py:16-89, envs/base_env.py:32-266)."""
+    d = dict(
+        n_lasers=240, horizon=0, decision_repeat=5, traffic_mode=0, dt=0.02, lidar_dist=50.0,
+        success_reward=10.0, out_of_road_penalty=5.0, crash_vehicle_penalty=5.0, crash_object_penalty=5.0,
+        driving_reward=1.0, speed_reward=0.1, crash_vehicle_cost=1.0, crash_object_cost=1.0, out_of_road_cost=1.0,
+        use_lateral_reward=0, out_of_route_done=0, on_continuous_line_done=1, crash_vehicle_done=1,
+        crash_object_done=1, crash_human_done=1, truncate_as_terminate=0, enable_idm_lane_change=1,
+        is_multi_agent=0, delay_done=0, spare0=0,
+    )
+    for k, v in kw.items():
+        if k not in d:
+            raise KeyError(k)
+        d[k] = v
+    return MdConfig(n_envs=n_envs, slots_per_env=slots_per_env, agents_per_env=agents_per_env,
+                    objs_per_env=objs_per_env, **d)
+
+
+class MdArrays(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in ARRAY_ORDER]

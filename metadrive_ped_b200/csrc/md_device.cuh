@@ -1,0 +1,478 @@
+// md_device.cuh — device-side arithmetic of the batched MetaDrive step (sm_100a).
+//
+// Every function cites the reference file:line (relative to /root/reference/metadrive) whose behaviour it
+// implements; Bullet-level pieces follow the published btRaycastVehicle / btTransformUtil algorithms.
+// float32 throughout; this translation unit is compiled with -fmad=false so that a*b+c rounds twice exactly like
+// the CPU oracle built with -ffp-contract=off (index / flag outputs are compared bit-exactly).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/md_layout.h"
+
+#define MD_PI 3.14159265358979323846f
+#define MD_TWO_PI 6.28318530717958647692f
+#define SUSP_REST 0.4f             // panda3d bulletVehicle.cxx create_wheel default
+#define MAX_SUSP_FORCE 6000.0f     // btRaycastVehicle::btVehicleTuning default
+#define GRAVITY_Z (-9.81f)         // engine/core/physics_world.py:14
+#define SUSP_STIFFNESS 40.0f       // component/vehicle/base_vehicle.py:97
+#define SUSP_TRAVEL_CM 15.0f       // :96
+#define DAMP_RELAX 4.8f            // :666
+#define DAMP_COMP 1.2f             // :667
+#define ROLL_INFLUENCE 0.5f        // :670
+#define SIDE_DAMPING 0.2f          // btRaycastVehicle resolveSingleBilateral contactDamping
+#define LIDAR_HEIGHT 1.2f          // component/sensors/lidar.py:19
+#define LINE_HALF_W 0.0375f        // LANE_LINE_WIDTH / 4, component/block/base_block.py:503
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ F3 cross(F3 a, F3 b) {
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+struct M3 { float m[3][3]; };  // world = m * local
+__device__ __forceinline__ M3 quat_to_m3(float w, float x, float y, float z) {
+    float n = w * w + x * x + y * y + z * z;
+    float s = n > 0.0f ? 2.0f / n : 0.0f;
+    M3 r;
+    r.m[0][0] = 1.0f - s * (y * y + z * z); r.m[0][1] = s * (x * y - w * z); r.m[0][2] = s * (x * z + w * y);
+    r.m[1][0] = s * (x * y + w * z); r.m[1][1] = 1.0f - s * (x * x + z * z); r.m[1][2] = s * (y * z - w * x);
+    r.m[2][0] = s * (x * z - w * y); r.m[2][1] = s * (y * z + w * x); r.m[2][2] = 1.0f - s * (x * x + y * y);
+    return r;
+}
+__device__ __forceinline__ F3 col(const M3& r, int c) { return f3(r.m[0][c], r.m[1][c], r.m[2][c]); }
+__device__ __forceinline__ F3 mul(const M3& r, F3 a) {
+    return f3(r.m[0][0] * a.x + r.m[0][1] * a.y + r.m[0][2] * a.z, r.m[1][0] * a.x + r.m[1][1] * a.y + r.m[1][2] * a.z,
+              r.m[2][0] * a.x + r.m[2][1] * a.y + r.m[2][2] * a.z);
+}
+__device__ __forceinline__ F3 tmul(const M3& r, F3 a) {
+    return f3(r.m[0][0] * a.x + r.m[1][0] * a.y + r.m[2][0] * a.z, r.m[0][1] * a.x + r.m[1][1] * a.y + r.m[2][1] * a.z,
+              r.m[0][2] * a.x + r.m[1][2] * a.y + r.m[2][2] * a.z);
+}
+__device__ __forceinline__ float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
+// utils/math.py:29-42
+__device__ __forceinline__ float wrap_to_pi(float x) {
+    float a = fmodf(x, MD_TWO_PI);
+    if (a < 0.0f) a += MD_TWO_PI;
+    if (a > MD_PI) a -= MD_TWO_PI;
+    return a;
+}
+// base_vehicle.py:990-992 + base_object.py:390-398: heading = normalised xy projection of the chassis +Y axis
+__device__ __forceinline__ void heading_vec(const M3& R, float& hx, float& hy) {
+    float fx = R.m[0][1], fy = R.m[1][1];
+    float n = sqrtf(fx * fx + fy * fy);
+    hx = fx / n;
+    hy = fy / n;
+}
+
+// ------------------------------------------------------------------------------------------------ lanes
+// component/lane/straight_lane.py:60-74, circular_lane.py:57-121, abs_lane.py:76-90
+__device__ __forceinline__ void lane_position(const float* __restrict__ L, float lon, float lat, float& x, float& y) {
+    if (L[LF_TYPE] == 0.0f) {
+        float dx = L[LF_P0 + 4], dy = L[LF_P0 + 5];
+        x = L[LF_P0 + 0] + lon * dx + lat * dy;
+        y = L[LF_P0 + 1] + lon * dy + lat * (-dx);
+    } else {
+        float r = L[LF_P0 + 2], dir = L[LF_P0 + 5];
+        float phi = dir * lon / r + L[LF_P0 + 3];
+        float rr = r + lat * dir;
+        x = L[LF_P0 + 0] + rr * cosf(phi);
+        y = L[LF_P0 + 1] + rr * sinf(phi);
+    }
+}
+__device__ __forceinline__ float lane_heading_at(const float* __restrict__ L, float lon) {
+    if (L[LF_TYPE] == 0.0f) return L[LF_P0 + 6];
+    float dir = L[LF_P0 + 5];
+    float phi = dir * lon / L[LF_P0 + 2] + L[LF_P0 + 3];
+    return phi + (MD_PI / 2.0f) * dir;
+}
+__device__ __forceinline__ void lane_local(const float* __restrict__ L, float px, float py, float& lon, float& lat) {
+    float ddx = px - L[LF_P0 + 0], ddy = py - L[LF_P0 + 1];
+    if (L[LF_TYPE] == 0.0f) {
+        float dx = L[LF_P0 + 4], dy = L[LF_P0 + 5];
+        lon = ddx * dx + ddy * dy;
+        lat = ddx * dy + ddy * (-dx);
+    } else {
+        float r = L[LF_P0 + 2], sp = L[LF_P0 + 3], ep = L[LF_P0 + 4], dir = L[LF_P0 + 5];
+        float abs_phase = wrap_to_pi(atan2f(ddy, ddx));
+        float sp_w = wrap_to_pi(sp), ep_w = wrap_to_pi(ep);
+        float d_s = fabsf(wrap_to_pi(abs_phase - sp_w));
+        float d_e = fabsf(wrap_to_pi(abs_phase - ep_w));
+        bool clockwise = dir < 0.0f;
+        if (d_s > d_e) {
+            float diff = clockwise ? (ep - abs_phase) : (abs_phase - ep);
+            lon = wrap_to_pi(diff) * r + L[LF_LENGTH];
+        } else {
+            float diff = clockwise ? (sp - abs_phase) : (abs_phase - sp);
+            lon = wrap_to_pi(diff) * r;
+        }
+        lat = dir * (sqrtf(ddx * ddx + ddy * ddy) - r);
+    }
+}
+__device__ __forceinline__ float lane_distance(const float* __restrict__ L, float px, float py) {
+    float s, r;
+    lane_local(L, px, py, s, r);
+    float a = s - L[LF_LENGTH], b = 0.0f - s;
+    return fabsf(r) + (a > 0.0f ? a : 0.0f) + (b > 0.0f ? b : 0.0f);
+}
+__device__ __forceinline__ bool lane_is_previous_of(const float* __restrict__ A, const float* __restrict__ B) {
+    float dx = A[LF_EX] - B[LF_SX], dy = A[LF_EY] - B[LF_SY];
+    return sqrtf(dx * dx + dy * dy) < 0.1f;
+}
+// component/block/base_block.py:459-466: lane body = convex hull of lane.polygon
+__device__ __forceinline__ bool point_in_hull(const float* __restrict__ hull, int n, float px, float py) {
+    for (int i = 0; i < n; i++) {
+        int j = i + 1 == n ? 0 : i + 1;
+        float ax = hull[2 * i], ay = hull[2 * i + 1], bx = hull[2 * j], by = hull[2 * j + 1];
+        float c = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
+        if (c < 0.0f) return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ overlaps
+struct Rect { float cx, cy, ux, uy, hu, hv; };
+
+__device__ __forceinline__ bool rect_rect(const Rect& a, const Rect& b) {
+    float dx = b.cx - a.cx, dy = b.cy - a.cy;
+    float c = a.ux * b.ux + a.uy * b.uy;
+    float s = a.ux * b.uy - a.uy * b.ux;
+    float ac = fabsf(c), as = fabsf(s);
+    if (fabsf(dx * a.ux + dy * a.uy) > a.hu + (b.hu * ac + b.hv * as)) return false;
+    if (fabsf(-dx * a.uy + dy * a.ux) > a.hv + (b.hu * as + b.hv * ac)) return false;
+    if (fabsf(dx * b.ux + dy * b.uy) > b.hu + (a.hu * ac + a.hv * as)) return false;
+    if (fabsf(-dx * b.uy + dy * b.ux) > b.hv + (a.hu * as + a.hv * ac)) return false;
+    return true;
+}
+__device__ __forceinline__ bool rect_circle(const Rect& a, float px, float py, float r) {
+    float dx = px - a.cx, dy = py - a.cy;
+    float lx = dx * a.ux + dy * a.uy;
+    float ly = -dx * a.uy + dy * a.ux;
+    float qx = clipf(lx, -a.hu, a.hu), qy = clipf(ly, -a.hv, a.hv);
+    float ex = lx - qx, ey = ly - qy;
+    return ex * ex + ey * ey <= r * r;
+}
+__device__ __forceinline__ bool rect_quad(const Rect& a, const float* __restrict__ q) {
+    float rx[4], ry[4];
+    float vx = -a.uy, vy = a.ux;
+    rx[0] = a.cx + a.ux * a.hu + vx * a.hv; ry[0] = a.cy + a.uy * a.hu + vy * a.hv;
+    rx[1] = a.cx - a.ux * a.hu + vx * a.hv; ry[1] = a.cy - a.uy * a.hu + vy * a.hv;
+    rx[2] = a.cx - a.ux * a.hu - vx * a.hv; ry[2] = a.cy - a.uy * a.hu - vy * a.hv;
+    rx[3] = a.cx + a.ux * a.hu - vx * a.hv; ry[3] = a.cy + a.uy * a.hu - vy * a.hv;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        float ax = k == 0 ? a.ux : vx, ay = k == 0 ? a.uy : vy;
+        float h = k == 0 ? a.hu : a.hv;
+        float c0 = a.cx * ax + a.cy * ay;
+        float lo = 1e30f, hi = -1e30f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float p = q[2 * i] * ax + q[2 * i + 1] * ay;
+            lo = fminf(lo, p); hi = fmaxf(hi, p);
+        }
+        if (lo > c0 + h || hi < c0 - h) return false;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) & 3;
+        float ex = q[2 * j] - q[2 * i], ey = q[2 * j + 1] - q[2 * i + 1];
+        float nx = ey, ny = -ex;
+        float qmax = q[2 * i] * nx + q[2 * i + 1] * ny;
+        float rmin = 1e30f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) rmin = fminf(rmin, rx[k] * nx + ry[k] * ny);
+        if (rmin > qmax) return false;
+    }
+    return true;
+}
+// chassis footprint: box (W/2, L/2, H/2) offset +H/2 above the body origin (base_vehicle.py:588-590)
+__device__ __forceinline__ Rect vehicle_rect(const float* __restrict__ P, const float* S) {
+    M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
+    float hx, hy;
+    heading_vec(R, hx, hy);
+    float hh = 0.5f * P[VP_HEIGHT];
+    Rect r;
+    r.cx = S[VS_POS + 0] + R.m[0][2] * hh;
+    r.cy = S[VS_POS + 1] + R.m[1][2] * hh;
+    r.ux = hx; r.uy = hy;
+    r.hu = 0.5f * P[VP_LENGTH];
+    r.hv = 0.5f * P[VP_WIDTH];
+    return r;
+}
+// TrafficBarrier: BulletBoxShape((WIDTH/2, LENGTH/2, h/2)) (static_object/traffic_object.py:143)
+__device__ __forceinline__ Rect object_rect(const float* O) {
+    Rect r;
+    r.cx = O[OB_X]; r.cy = O[OB_Y];
+    r.ux = cosf(O[OB_HEADING]); r.uy = sinf(O[OB_HEADING]);
+    r.hu = O[OB_B]; r.hv = O[OB_A];
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ ray casts
+// sensors/distance_detector.py:27-85 (rayTestClosest); t in [0,1], 2 = miss, 0 if the origin is inside
+__device__ __forceinline__ float ray_obb(F3 o, F3 d, F3 c, const M3& R, F3 h) {
+    F3 ol = tmul(R, o - c);
+    F3 dl = tmul(R, d);
+    float t0 = 0.0f, t1 = 1.0f;
+    const float olv[3] = {ol.x, ol.y, ol.z}, dlv[3] = {dl.x, dl.y, dl.z}, hv[3] = {h.x, h.y, h.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (fabsf(dlv[k]) < 1e-12f) {
+            if (fabsf(olv[k]) > hv[k]) return 2.0f;
+        } else {
+            float inv = 1.0f / dlv[k];
+            float ta = (-hv[k] - olv[k]) * inv, tb = (hv[k] - olv[k]) * inv;
+            if (ta > tb) { float t = ta; ta = tb; tb = t; }
+            t0 = fmaxf(t0, ta);
+            t1 = fminf(t1, tb);
+            if (t0 > t1) return 2.0f;
+        }
+    }
+    return t0;
+}
+__device__ __forceinline__ float ray_zcyl(F3 o, F3 d, float cx, float cy, float zc, float r, float hh) {
+    if (fabsf(o.z - zc) > hh) return 2.0f;
+    float ox = o.x - cx, oy = o.y - cy;
+    float a = d.x * d.x + d.y * d.y;
+    float b = ox * d.x + oy * d.y;
+    float cc = ox * ox + oy * oy - r * r;
+    float disc = b * b - a * cc;
+    if (disc < 0.0f) return 2.0f;
+    float sq = sqrtf(disc);
+    float ta = (-b - sq) / a, tb = (-b + sq) / a;
+    float t0 = fmaxf(0.0f, ta), t1 = fminf(1.0f, tb);
+    if (t0 > t1) return 2.0f;
+    return t0;
+}
+
+// ------------------------------------------------------------------------------------------------ dynamics
+struct Actuation { float steer_rad, engine, brake; };
+
+// btTransformUtil::integrateTransform (rotation part); q = w x y z
+__device__ __forceinline__ void quat_integrate(float* q, F3 w, float dt) {
+    float ang = sqrtf(dot(w, w));
+    if (ang * dt > 0.25f * MD_PI) ang = 0.25f * MD_PI / dt;
+    F3 axis;
+    if (ang < 0.001f) axis = w * (0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang);
+    else axis = w * (sinf(0.5f * ang * dt) / ang);
+    float aw = cosf(ang * dt * 0.5f), ax = axis.x, ay = axis.y, az = axis.z;
+    float bw = q[0], bx = q[1], by = q[2], bz = q[3];
+    float rw = aw * bw - ax * bx - ay * by - az * bz;
+    float rx = aw * bx + ax * bw + ay * bz - az * by;
+    float ry = aw * by - ax * bz + ay * bw + az * bx;
+    float rz = aw * bz + ax * by - ay * bx + az * bw;
+    float n = sqrtf(rw * rw + rx * rx + ry * ry + rz * rz);
+    q[0] = rw / n; q[1] = rx / n; q[2] = ry / n; q[3] = rz / n;
+}
+
+struct Body {  // rigid-body state kept in registers across the sub-steps
+    F3 pos, v, w;
+    float q[4];
+};
+
+__device__ __forceinline__ F3 apply_inv_inertia(const M3& R, F3 t, float Ix, float Iy, float Iz) {
+    F3 tl = tmul(R, t);
+    tl = f3(tl.x / Ix, tl.y / Iy, tl.z / Iz);
+    return mul(R, tl);
+}
+
+// one doPhysics(dt, 1, dt) sub-step of a chassis on four ray-cast wheels over the plane z = 0
+// (base_vehicle.py:577-598,632-671; engine_core.py:350-352; btRaycastVehicle::updateVehicle / updateFriction)
+__device__ void vehicle_substep(const float* __restrict__ P, Body& B, Actuation act, float dt) {
+    const float mass = P[VP_MASS], inv_m = 1.0f / mass;
+    const float lx = P[VP_WIDTH], ly = P[VP_LENGTH], lz = P[VP_HEIGHT];
+    const float Ix = mass / 12.0f * (ly * ly + lz * lz), Iy = mass / 12.0f * (lx * lx + lz * lz),
+                Iz = mass / 12.0f * (lx * lx + ly * ly);
+    F3 pos = B.pos, v = B.v, w = B.w;
+    v.z += GRAVITY_Z * dt;
+    float wl = sqrtf(dot(w, w));
+    if (wl * dt > 0.5f * MD_PI) w = w * ((0.5f * MD_PI / dt) / wl);
+    pos = pos + v * dt;
+    quat_integrate(B.q, w, dt);
+    M3 R = quat_to_m3(B.q[0], B.q[1], B.q[2], B.q[3]);
+    {   // chassis box vs ground plane: inelastic clamp of the lowest bottom corner (DESIGN.md "Dynamics")
+        float hw = 0.5f * lx, hl = 0.5f * ly;
+        float lowest = 0.0f;
+#pragma unroll
+        for (int sx = -1; sx <= 1; sx += 2)
+#pragma unroll
+            for (int sy = -1; sy <= 1; sy += 2)
+                lowest = fminf(lowest, pos.z + R.m[2][0] * (float)sx * hw + R.m[2][1] * (float)sy * hl);
+        if (lowest < 0.0f) {
+            pos.z -= lowest;
+            if (v.z < 0.0f) v.z = 0.0f;
+        }
+    }
+    F3 up = col(R, 2), right = col(R, 0);
+    F3 normal = f3(0.0f, 0.0f, 1.0f);
+    const float conn_z = P[VP_TIRE_R] - P[VP_CHASSIS_AXIS];
+    bool on[4];
+    F3 cp[4];
+    float fs[4];
+    int n_ground = 0;
+    const float raylen = SUSP_REST + P[VP_TIRE_R];
+    F3 dir = up * -1.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float cxw = (i & 1) ? -P[VP_LATERAL] : P[VP_LATERAL];
+        float cyw = i < 2 ? P[VP_FRONT_WB] : -P[VP_REAR_WB];
+        F3 hard = pos + mul(R, f3(cxw, cyw, conn_z));
+        on[i] = false; fs[i] = 0.0f; cp[i] = f3(0, 0, 0);
+        if (!(dir.z < 0.0f && hard.z > 0.0f)) continue;
+        float t = hard.z / (-dir.z * raylen);
+        if (t > 1.0f) continue;
+        on[i] = true; n_ground++;
+        cp[i] = hard + dir * (raylen * t);
+        float slen = t * raylen - P[VP_TIRE_R];
+        slen = clipf(slen, SUSP_REST - SUSP_TRAVEL_CM * 0.01f, SUSP_REST + SUSP_TRAVEL_CM * 0.01f);
+        float denom = dot(normal, dir);
+        F3 rel = cp[i] - pos;
+        float proj_vel = dot(normal, v + cross(w, rel));
+        float rel_vel, clipped_inv;
+        if (denom >= -0.1f) { rel_vel = 0.0f; clipped_inv = 10.0f; }
+        else { float inv = -1.0f / denom; rel_vel = proj_vel * inv; clipped_inv = inv; }
+        float force = SUSP_STIFFNESS * (SUSP_REST - slen) * clipped_inv;
+        force -= (rel_vel < 0.0f ? DAMP_COMP : DAMP_RELAX) * rel_vel;
+        fs[i] = fmaxf(force * mass, 0.0f);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (!on[i]) continue;
+        float f = fminf(fs[i], MAX_SUSP_FORCE);
+        F3 imp = normal * (f * dt);
+        F3 rel = cp[i] - pos;
+        v = v + imp * inv_m;
+        w = w + apply_inv_inertia(R, cross(rel, imp), Ix, Iy, Iz);
+    }
+    if (n_ground > 0) {
+        F3 axle[4], fwd[4];
+        float side[4] = {0, 0, 0, 0}, fimp[4] = {0, 0, 0, 0}, skid[4] = {1, 1, 1, 1};
+        bool sliding = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            axle[i] = f3(0, 0, 0); fwd[i] = f3(0, 0, 0);
+            if (!on[i]) continue;
+            float st = i < 2 ? act.steer_rad : 0.0f;
+            float cs = cosf(st), sn = sinf(st);
+            F3 a = (right * cs + cross(up, right) * sn) + up * (dot(up, right) * (1.0f - cs));
+            a = a - normal * dot(a, normal);
+            a = a * (1.0f / sqrtf(dot(a, a)));
+            F3 f = cross(normal, a);
+            f = f * (1.0f / sqrtf(dot(f, f)));
+            axle[i] = a; fwd[i] = f;
+            F3 rel = cp[i] - pos;
+            F3 aj = tmul(R, cross(rel, a));
+            float jac = inv_m + (aj.x * aj.x / Ix + aj.y * aj.y / Iy + aj.z * aj.z / Iz);
+            float rel_vel = dot(a, v + cross(w, rel));
+            side[i] = -SIDE_DAMPING * rel_vel / jac;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!on[i]) continue;
+            float rolling;
+            if (act.engine != 0.0f) rolling = act.engine * dt;
+            else {
+                float max_imp = act.brake;
+                F3 rel = cp[i] - pos;
+                F3 c0 = cross(rel, fwd[i]);
+                F3 iw = apply_inv_inertia(R, c0, Ix, Iy, Iz);
+                float denom0 = inv_m + dot(fwd[i], cross(iw, rel));
+                float vrel = dot(fwd[i], v + cross(w, rel));
+                float j1 = -vrel / denom0 / (float)n_ground;
+                rolling = clipf(j1, -max_imp, max_imp);
+            }
+            fimp[i] = rolling;
+            float maximp = fs[i] * dt * P[VP_FRICTION];
+            float x = fimp[i] * 0.5f, y = side[i];
+            float imp2 = x * x + y * y;
+            if (imp2 > maximp * maximp) { sliding = true; skid[i] *= maximp / sqrtf(imp2); }
+        }
+        if (sliding) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (side[i] != 0.0f && skid[i] < 1.0f) { fimp[i] *= skid[i]; side[i] *= skid[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!on[i]) continue;
+            F3 rel = cp[i] - pos;
+            if (fimp[i] != 0.0f) {
+                F3 imp = fwd[i] * fimp[i];
+                v = v + imp * inv_m;
+                w = w + apply_inv_inertia(R, cross(rel, imp), Ix, Iy, Iz);
+            }
+            if (side[i] != 0.0f) {
+                F3 imp = axle[i] * side[i];
+                F3 rel2 = rel - up * (dot(up, rel) * (1.0f - ROLL_INFLUENCE));
+                v = v + imp * inv_m;
+                w = w + apply_inv_inertia(R, cross(rel2, imp), Ix, Iy, Iz);
+            }
+        }
+    }
+    B.pos = pos; B.v = v; B.w = w;
+}
+
+// BaseVehicle._preprocess_action + _set_action + _apply_throttle_brake (base_vehicle.py:204-209, 447-484)
+__device__ __forceinline__ float scrub(float a) {  // utils/math.py:16-26
+    if (isnan(a)) return 0.0f;
+    return clipf(a, -1.0f, 1.0f);
+}
+__device__ __forceinline__ Actuation actuate(const float* __restrict__ P, float* S, float* C, float a0, float a1) {
+    a0 = scrub(a0); a1 = scrub(a1);
+    C[VC_PREV_A0] = C[VC_CUR_A0]; C[VC_PREV_A1] = C[VC_CUR_A1];
+    C[VC_CUR_A0] = a0; C[VC_CUR_A1] = a1;
+    S[VS_STEER] = a0; S[VS_THROTTLE] = a1;
+    Actuation act;
+    act.steer_rad = a0 * P[VP_MAX_STEER] * (MD_PI / 180.0f);
+    float speed_kmh = sqrtf(S[VS_VEL] * S[VS_VEL] + S[VS_VEL + 1] * S[VS_VEL + 1]) * 3.6f;
+    if (a1 >= 0.0f) {
+        act.brake = 2.0f;
+        act.engine = speed_kmh > P[VP_MAX_SPEED] ? 0.0f : P[VP_ENGINE] * a1;
+    } else if (P[VP_REVERSE] != 0.0f) {
+        act.engine = P[VP_ENGINE] * a1; act.brake = 0.0f;
+    } else {
+        act.engine = 0.0f; act.brake = fabsf(a1) * P[VP_BRAKE];
+    }
+    return act;
+}
+// BaseVehicle.before_step latches (base_vehicle.py:211-232)
+__device__ __forceinline__ void latch_before_step(const float* S, float* C, int* I) {
+    I[VI_FLAGS] = FL_ON_LANE;
+    C[VC_LAST_X] = S[VS_POS]; C[VC_LAST_Y] = S[VS_POS + 1];
+    M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
+    heading_vec(R, C[VC_LAST_HX], C[VC_LAST_HY]);
+}
+
+// ------------------------------------------------------------------------------------------------ map views
+struct MapView {
+    const float* lane_f; const int* lane_i; const float* lane_bb; const int* road_i; const float* hull;
+    const float* lines; const float* quads; const int* gs; const int* gi;
+    int n_lanes, n_roads, n_lines, nx, ny;
+    float gx0, gy0, cell;
+};
+__device__ __forceinline__ MapView map_view(const MdArrays& A, int map) {
+    const int* d = A.map_desc + (size_t)map * MAPD;
+    const float* df = A.map_descf + (size_t)map * MAPDF;
+    MapView m;
+    m.lane_f = A.lane_f + (size_t)d[MD_LANE_OFF] * LANE_F;
+    m.lane_i = A.lane_i + (size_t)d[MD_LANE_OFF] * LANE_I;
+    m.lane_bb = A.lane_bb + (size_t)d[MD_LANE_OFF] * 4;
+    m.road_i = A.road_i + (size_t)d[MD_ROAD_OFF] * ROAD_I;
+    m.hull = A.hull_xy + (size_t)d[MD_HULL_OFF] * 2;
+    m.lines = A.line_f + (size_t)d[MD_LINE_OFF] * LINE_F;
+    m.quads = A.quad_f + (size_t)d[MD_QUAD_OFF] * QUAD_F;
+    m.gs = A.grid_start + d[MD_GRID_OFF];
+    m.gi = A.grid_items + d[MD_ITEM_OFF];
+    m.n_lanes = d[MD_N_LANES]; m.n_roads = d[MD_N_ROADS]; m.n_lines = d[MD_N_LINES];
+    m.nx = d[MD_GRID_NX]; m.ny = d[MD_GRID_NY];
+    m.gx0 = df[0]; m.gy0 = df[1]; m.cell = df[2];
+    return m;
+}
+__device__ __forceinline__ int find_road(const MapView& m, int from, int to) {
+    for (int r = 0; r < m.n_roads; r++)
+        if (m.road_i[r * ROAD_I + RI_FROM] == from && m.road_i[r * ROAD_I + RI_TO] == to) return r;
+    return -1;
+}

@@ -1,0 +1,101 @@
+"""ctypes binding of the CPU oracle (oracle/md_oracle.c). TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from metadrive_ped_b200.abi import MdArrays, MdConfig
+from metadrive_ped_b200.scene import ARRAY_ORDER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libmd_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "md_oracle.c")
+    hdr = os.path.join(_HERE, "..", "include", "md_layout.h")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src),
+                                                                                   os.path.getmtime(hdr)):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleSim:
+    """Holds numpy copies of the flat arrays and steps them with the C oracle."""
+    def __init__(self, arrays: dict, cfg: MdConfig):
+        self.cfg = cfg
+        self.a = {k: np.ascontiguousarray(arrays[k]).copy() for k in ARRAY_ORDER}
+        self.init = {k: self.a[k].copy() for k in ("env_i", "veh_s", "veh_c", "veh_i", "veh_idm", "veh_navi", "obj_f")}
+        self.A = MdArrays(**{k: _p(self.a[k]) for k in ARRAY_ORDER})
+        self.n_agents = cfg.n_envs * cfg.agents_per_env
+        self.obs_dim = 19 + cfg.n_lasers
+        self.ray_cs = np.zeros((cfg.n_lasers, 2), np.float32)
+        lib().mdo_make_ray_table(cfg.n_lasers, _p(self.ray_cs))
+        na = self.n_agents
+        self.obs = np.zeros((na, self.obs_dim), np.float32)
+        self.reward = np.zeros(na, np.float32)
+        self.cost = np.zeros(na, np.float32)
+        self.term = np.zeros(na, np.uint8)
+        self.trunc = np.zeros(na, np.uint8)
+        self.info_flags = np.zeros(na, np.int32)
+        self.info_f = np.zeros((na, 8), np.float32)
+        self.hit = np.zeros((na, cfg.n_lasers), np.int32)
+
+    def reset_observe(self):
+        lib().mdo_reset_observe(C.byref(self.cfg), C.byref(self.A), _p(self.ray_cs), _p(self.obs), _p(self.hit))
+        return self.obs
+
+    def step(self, actions, env_begin=0, env_end=None):
+        actions = np.ascontiguousarray(actions, np.float32).reshape(self.n_agents, 2)
+        if env_end is None:
+            env_end = self.cfg.n_envs
+        lib().mdo_step(C.byref(self.cfg), C.byref(self.A), _p(self.ray_cs), _p(actions), _p(self.obs), _p(self.reward),
+                       _p(self.cost), _p(self.term), _p(self.trunc), _p(self.info_flags), _p(self.info_f),
+                       _p(self.hit), C.c_int(env_begin), C.c_int(env_end))
+        return self.obs, self.reward, self.term, self.trunc
+
+    def reset_envs(self, mask):
+        """Restore the initial snapshot of the masked envs (what the product's md_reset does on device)."""
+        S, O = self.cfg.slots_per_env, self.cfg.objs_per_env
+        for e in np.nonzero(np.asarray(mask))[0]:
+            for k in ("veh_s", "veh_c", "veh_i", "veh_idm", "veh_navi"):
+                self.a[k][e * S:(e + 1) * S] = self.init[k][e * S:(e + 1) * S]
+            self.a["env_i"][e] = self.init["env_i"][e]
+            if O:
+                self.a["obj_f"][e * O:(e + 1) * O] = self.init["obj_f"][e * O:(e + 1) * O]
+
+    def lidar(self):
+        frac = np.zeros((self.n_agents, self.cfg.n_lasers), np.float32)
+        hit = np.zeros((self.n_agents, self.cfg.n_lasers), np.int32)
+        lib().mdo_lidar(C.byref(self.cfg), C.byref(self.A), _p(self.ray_cs), _p(frac), _p(hit))
+        return frac, hit
+
+    def dynamics(self, act3, n_sub):
+        act3 = np.ascontiguousarray(act3, np.float32)
+        lib().mdo_dynamics(C.byref(self.cfg), C.byref(self.A), _p(act3), C.c_int(n_sub))
+
+    def after_step(self):
+        lib().mdo_after_step(C.byref(self.cfg), C.byref(self.A))
+
+    def idm(self):
+        out = np.zeros((self.cfg.n_envs * self.cfg.slots_per_env, 2), np.float32)
+        lib().mdo_idm(C.byref(self.cfg), C.byref(self.A), _p(out))
+        return out

@@ -721,6 +721,8 @@ class BulletWorld:
             q = mat_to_quat(c.mat)
             pos, q, v, w = ph.vehicle_substep_pre(body, c.pos, q, c.mat, c.lin_vel, c.ang_vel, dt)
             R = quat_to_mat(q)
+            box = c.shapes[0][0]
+            pos, v = ph.chassis_ground_clamp(box.half[0], box.half[1], pos, R, v)
             v, w = ph.update_vehicle(body, pos, R, v, w, dt)
             c.pos, c.mat, c.lin_vel, c.ang_vel = pos, R, v, w
             c._geom_cache = None

@@ -585,9 +585,15 @@ class _Task:
     done = 0
 
 
+class _TaskChainMgr:
+    def getNumTaskChains(self):
+        return 0
+
+
 class _TaskMgr:
     def __init__(self):
         self.globalClock = _mk("clock")()
+        self.mgr = _TaskChainMgr()
 
     def add(self, *a, **k):
         return None

@@ -88,6 +88,24 @@ def vehicle_substep_pre(body, pos, q, R, v, w, dt):
     return pos, q, v, w
 
 
+def chassis_ground_clamp(body_half_w, body_half_l, pos, R, v):
+    """Chassis-box vs ground-plane contact, restated as an inelastic clamp (Bullet resolves this contact with
+    its sequential-impulse solver, restitution 0): the lowest bottom corner of the box (bottom face = body
+    origin plane, base_vehicle.py:588-590) is lifted to z = 0 and the downward velocity is removed."""
+    lowest = 0.0
+    for sx in (-1.0, 1.0):
+        for sy in (-1.0, 1.0):
+            z = pos[2] + R[2, 0] * sx * body_half_w + R[2, 1] * sy * body_half_l
+            lowest = min(lowest, z)
+    if lowest < 0.0:
+        pos = pos.copy()
+        pos[2] -= lowest
+        if v[2] < 0.0:
+            v = v.copy()
+            v[2] = 0.0
+    return pos, v
+
+
 def update_vehicle(body, pos, R, v, w, dt):
     """btRaycastVehicle::updateVehicle on the plane z = 0 (normal +z, `engine/core/terrain.py:157-175`)."""
     n_w = len(body.wheels)
