@@ -1,0 +1,1240 @@
+// md_kernels.cu — kernels + C ABI of libmdstep.so (sm_100a).  See include/mdstep.h for the boundary and
+// DESIGN.md for the data layout, the launch structure and the roofline of each kernel.
+//
+// Launch structure of one env.step:
+//   k_step_vehicles  thread per vehicle slot, a CTA owns whole envs: before_step (actuation, trigger, IDM),
+//                    decision_repeat sub-steps with the state in registers and the env's footprints in shared
+//                    memory for the contact pass, after_step (localisation, state check), reward / cost / done and
+//                    the 19 state floats of the observation; publishes one 64-byte "body row" per vehicle.
+//   k_lidar          warp per agent: the env's body rows + object rows are staged into shared memory with one
+//                    cp.async.bulk (TMA 1-D bulk copy) per table completing on an mbarrier; 240 rays, 7.5 per lane,
+//                    nearest hit kept in registers; coalesced store of the 240 lidar floats.
+//   k_done_mask / k_reset_vehicles / k_lidar(masked)   batched auto-reset, still without a host round trip.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mdstep.h"
+#include "md_device.cuh"
+
+#define STEP_THREADS 128
+#define LIDAR_WARPS 8
+#define MAX_LASERS 512
+
+__constant__ float c_ray_cs[2 * MAX_LASERS];
+
+enum {
+    MODE_AGENT_PRE = 1, MODE_TRIGGER = 2, MODE_IDM = 4, MODE_DYN = 8, MODE_CONTACTS = 16, MODE_POST = 32,
+    MODE_OUT = 64, MODE_EXT_ACT = 128, MODE_IDM_OUT = 256, MODE_RESET = 512, MODE_REMOVE = 1024, MODE_CLEAR_FLAGS = 2048,
+    MODE_FULL = MODE_AGENT_PRE | MODE_TRIGGER | MODE_IDM | MODE_DYN | MODE_CONTACTS | MODE_POST | MODE_OUT | MODE_REMOVE
+};
+
+struct StepOut {
+    float* obs; float* reward; float* cost; uint8_t* term; uint8_t* trunc; int* info_flags; float* info_f;
+};
+struct Snapshot {
+    const int* env_i; const float* veh_s; const float* veh_c; const int* veh_i; const float* veh_idm;
+    const float* veh_navi; const float* obj_f;
+};
+
+// neighbour record of one vehicle slot, shared by the threads of its env
+struct __align__(16) Nb {
+    float x, y, vx, vy;
+    Rect r;
+    int lane, alive, active, kind;
+};
+
+struct FrontBack { int fobj[3], bobj[3]; float fdist[3], bdist[3]; bool exists[3]; };
+#define OBJ_NONE (-1)
+
+// unified view of "the k-th surrounding object" for the IDM: vehicles first (by slot), then objects
+struct NbrView {
+    const Nb* nb; const float* obj; int S, O, self; float px, py;
+    __device__ __forceinline__ int count() const { return S + O; }
+    __device__ __forceinline__ bool valid(int k) const {
+        if (k < S) {
+            if (k == self || !nb[k].alive) return false;
+            return rect_circle(nb[k].r, px, py, 50.0f);
+        }
+        const float* Ob = obj + (k - S) * OBJ_F;
+        if (Ob[OB_KIND] < 0.0f) return false;
+        if (Ob[OB_KIND] == 2.0f) { Rect r = object_rect(Ob); return rect_circle(r, px, py, 50.0f); }
+        float dx = Ob[OB_X] - px, dy = Ob[OB_Y] - py, rr = 50.0f + Ob[OB_A];
+        return dx * dx + dy * dy <= rr * rr;
+    }
+    __device__ __forceinline__ void get(int k, float& x, float& y, float& vx, float& vy, int& lane, bool& ped) const {
+        if (k < S) { x = nb[k].x; y = nb[k].y; vx = nb[k].vx; vy = nb[k].vy; lane = nb[k].lane; ped = false; }
+        else {
+            const float* Ob = obj + (k - S) * OBJ_F;
+            x = Ob[OB_X]; y = Ob[OB_Y]; vx = Ob[OB_VX]; vy = Ob[OB_VY]; lane = (int)Ob[OB_LANE]; ped = Ob[OB_KIND] == 3.0f;
+        }
+    }
+};
+
+// FrontBackObjects.get_find_front_back_objs (policy/idm_policy.py:82-132)
+__device__ void find_front_back(const MapView& m, const NbrView& nv, unsigned long long valid_lo, unsigned long long valid_hi,
+                                int lane, float px, float py, float max_d, bool use_ref, int ref_first, int ref_n,
+                                FrontBack& out) {
+    int lanes[3] = {-1, lane, -1};
+    if (use_ref) {
+        int idx = m.lane_i[lane * LANE_I + LI_IDX];
+        if (idx > 0) lanes[0] = ref_first + idx - 1;
+        if (idx + 1 < ref_n) lanes[2] = ref_first + idx + 1;
+    }
+    for (int i = 0; i < 3; i++) {
+        out.fobj[i] = out.bobj[i] = OBJ_NONE;
+        out.exists[i] = lanes[i] >= 0;
+        out.fdist[i] = out.bdist[i] = max_d;
+        if (lanes[i] < 0) continue;
+        const float* Li = m.lane_f + lanes[i] * LANE_F;
+        float cur_long, lat;
+        lane_local(Li, px, py, cur_long, lat);
+        float left_long = Li[LF_LENGTH] - cur_long;
+        bool ffound = false, bfound = false;
+        const int n = nv.count();
+        for (int k = 0; k < n; k++) {
+            bool ok = k < 64 ? ((valid_lo >> k) & 1ull) : ((valid_hi >> (k - 64)) & 1ull);
+            if (!ok) continue;
+            float ox, oy, ovx, ovy; int olane; bool ped;
+            nv.get(k, ox, oy, ovx, ovy, olane, ped);
+            if (olane < 0) continue;
+            const float* Lo = m.lane_f + olane * LANE_F;
+            float lon, lt;
+            if (olane == lanes[i]) {
+                lane_local(Li, ox, oy, lon, lt);
+                lon -= cur_long;
+                if (out.fdist[i] > lon && lon > 0.0f) { out.fdist[i] = lon; out.fobj[i] = k; ffound = true; }
+                if (lon < 0.0f && fabsf(lon) < out.bdist[i]) { out.bdist[i] = fabsf(lon); out.bobj[i] = k; bfound = true; }
+            } else if (!ffound && lane_is_previous_of(Li, Lo)) {
+                lane_local(Lo, ox, oy, lon, lt);
+                lon += left_long;
+                if (out.fdist[i] > lon && lon > 0.0f) { out.fdist[i] = lon; out.fobj[i] = k; }
+            } else if (!bfound && lane_is_previous_of(Lo, Li)) {
+                lane_local(Lo, ox, oy, lon, lt);
+                lon = Lo[LF_LENGTH] - lon + cur_long;
+                if (out.bdist[i] > lon) { out.bdist[i] = lon; out.bobj[i] = k; }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float pid(float kp, float ki, float kd, float& p_err, float& i_err, float err) {
+    i_err += err;
+    float d = err - p_err;
+    p_err = err;
+    return -kp * p_err - ki * i_err - kd * d;
+}
+// build-defined replacement of np_random.randint(0, n) (policy/idm_policy.py:288)
+__device__ __forceinline__ int hash_randint(uint32_t slot, uint32_t counter, int n) {
+    uint32_t x = slot * 0x9E3779B9u + counter * 0x85EBCA6Bu + 0x165667B1u;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return (int)(x % (uint32_t)n);
+}
+
+// IDMPolicy.act (policy/idm_policy.py:235-402) for one traffic vehicle; S/I/D are this thread's register copies
+__device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv, int g, const float* S, int* I, float* D,
+                        const int* __restrict__ route, float& out_a0, float& out_a1) {
+    float px = S[VS_POS], py = S[VS_POS + 1];
+    M3 Rg = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
+    float hx, hy;
+    heading_vec(Rg, hx, hy);
+    float speed_kmh = sqrtf(S[VS_VEL] * S[VS_VEL] + S[VS_VEL + 1] * S[VS_VEL + 1]) * 3.6f;
+    int c0 = I[VI_CKPT0], c1 = I[VI_CKPT1];
+    int cur_road = find_road(m, route[c0], route[c0 + 1]);
+    int next_road = c1 != c0 ? find_road(m, route[c1], route[c1 + 1]) : -1;
+    int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+    int veh_lane = I[VI_LANE];
+#define IN_CUR(l) ((l) >= cur_first && (l) < cur_first + cur_n)
+    bool success;
+    int rt = I[VI_ROUTING_LANE];
+    if (rt < 0) {
+        rt = veh_lane;
+        success = IN_CUR(rt);
+    } else if (!IN_CUR(rt)) {
+        success = false;
+        for (int l = cur_first; l < cur_first + cur_n; l++) {
+            bool conn = lane_is_previous_of(m.lane_f + rt * LANE_F, m.lane_f + l * LANE_F) ||
+                        find_road(m, m.lane_i[rt * LANE_I + LI_TO], m.lane_i[l * LANE_I + LI_TO]) >= 0;
+            if (conn) { rt = l; success = true; break; }
+        }
+    } else if (IN_CUR(veh_lane) && rt != veh_lane) {
+        rt = veh_lane;
+        uint32_t ctr = (uint32_t)D[VD_RNG];
+        D[VD_TIMER] = (float)hash_randint((uint32_t)g, ctr, 25);
+        D[VD_RNG] = (float)(ctr + 1);
+        success = true;
+    } else success = true;
+    I[VI_ROUTING_LANE] = rt;
+
+    // Lidar.get_surrounding_objects(r = 50) (component/sensors/lidar.py:170-186): membership bitmask
+    unsigned long long vlo = 0ull, vhi = 0ull;
+    bool has_ped = false;
+    const int n = nv.count();
+    for (int k = 0; k < n; k++) {
+        if (!nv.valid(k)) continue;
+        if (k < 64) vlo |= 1ull << k; else vhi |= 1ull << (k - 64);
+        if (k >= nv.S) {
+            const float* Ob = nv.obj + (k - nv.S) * OBJ_F;
+            if (Ob[OB_KIND] == 3.0f || Ob[OB_LANE] < 0.0f) has_ped = true;  // no `.lane` -> except path (:254-259)
+        }
+    }
+    int front = OBJ_NONE;
+    float front_dist = 0.0f;
+    int steer_lane = rt;
+    FrontBack fb;
+    if (has_ped) {
+        front = OBJ_NONE; front_dist = 5.0f; steer_lane = rt;
+    } else if (success && cfg.enable_idm_lane_change) {
+        find_front_back(m, nv, vlo, vhi, rt, px, py, 30.0f, true, cur_first, cur_n, fb);
+        int next_n = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_N] : 0;
+        int next_first = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_FIRST] : -1;
+        int diff = next_road >= 0 ? cur_n - next_n : 0;
+        int lo = 0, hi = cur_n - 1;
+        int rt_idx = m.lane_i[rt * LANE_I + LI_IDX];
+        bool decided = false;
+        front = fb.fobj[1]; front_dist = fb.fdist[1]; steer_lane = rt;
+        if (diff > 0) {
+            if (lane_is_previous_of(m.lane_f + cur_first * LANE_F, m.lane_f + next_first * LANE_F)) { lo = 0; hi = next_n - 1; }
+            else { lo = diff; hi = cur_n - 1; }
+            if (rt_idx < lo || rt_idx > hi) {
+                decided = true;
+                if (rt_idx > hi) {
+                    if (fb.bdist[0] < 15.0f || fb.fdist[0] < 5.0f) { D[VD_TARGET_SPEED] = 5.0f; }
+                    else { D[VD_TARGET_SPEED] = 30.0f; front = fb.fobj[0]; front_dist = fb.fdist[0]; steer_lane = cur_first + rt_idx - 1; }
+                } else {
+                    if (fb.bdist[2] < 15.0f || fb.fdist[2] < 5.0f) { D[VD_TARGET_SPEED] = 5.0f; }
+                    else { D[VD_TARGET_SPEED] = 30.0f; front = fb.fobj[2]; front_dist = fb.fdist[2]; steer_lane = cur_first + rt_idx + 1; }
+                }
+            }
+        }
+        if (!decided) {
+            bool overtake = false;
+            float fsp = 0.0f;
+            if (fb.fobj[1] != OBJ_NONE) {
+                float ox, oy, ovx, ovy; int ol; bool pd;
+                nv.get(fb.fobj[1], ox, oy, ovx, ovy, ol, pd);
+                fsp = sqrtf(ovx * ovx + ovy * ovy) * 3.6f;
+            }
+            if (fabsf(speed_kmh - 30.0f) > 3.0f && fb.fobj[1] != OBJ_NONE && fabsf(fsp - 30.0f) > 3.0f && D[VD_TIMER] > 50.0f) {
+                bool has_r = false, has_l = false;
+                float rs = 0.0f, ls = 0.0f;
+                float ox, oy, ovx, ovy; int ol; bool pd;
+                if (fb.fobj[2] != OBJ_NONE) { has_r = true; nv.get(fb.fobj[2], ox, oy, ovx, ovy, ol, pd); rs = sqrtf(ovx * ovx + ovy * ovy) * 3.6f; }
+                else if (fb.exists[2] && fb.fdist[2] > 15.0f && fb.bdist[2] > 15.0f) { has_r = true; rs = 100.0f; }
+                if (fb.fobj[0] != OBJ_NONE) { has_l = true; nv.get(fb.fobj[0], ox, oy, ovx, ovy, ol, pd); ls = sqrtf(ovx * ovx + ovy * ovy) * 3.6f; }
+                else if (fb.exists[0] && fb.fdist[0] > 15.0f && fb.bdist[0] > 15.0f) { has_l = true; ls = 100.0f; }
+                if (has_l && ls - fsp > 10.0f) {
+                    int e = rt_idx - 1;
+                    if (e >= lo && e <= hi) { front = fb.fobj[0]; front_dist = fb.fdist[0]; steer_lane = cur_first + e; overtake = true; }
+                }
+                if (!overtake && has_r && rs - fsp > 10.0f) {
+                    int e = rt_idx + 1;
+                    if (e >= lo && e <= hi) { front = fb.fobj[2]; front_dist = fb.fdist[2]; steer_lane = cur_first + e; overtake = true; }
+                }
+            }
+            if (!overtake) {
+                D[VD_TARGET_SPEED] = 30.0f;
+                D[VD_TIMER] += 1.0f;
+                front = fb.fobj[1]; front_dist = fb.fdist[1]; steer_lane = rt;
+            }
+        }
+    } else {
+        find_front_back(m, nv, vlo, vhi, rt, px, py, 30.0f, false, 0, 0, fb);
+        front = fb.fobj[1]; front_dist = fb.fdist[1]; steer_lane = rt;
+    }
+    // steering_control (:293-301)
+    const float* Ls = m.lane_f + steer_lane * LANE_F;
+    float lon, lat;
+    lane_local(Ls, px, py, lon, lat);
+    float lane_heading = lane_heading_at(Ls, lon + 1.0f);
+    float v_heading = atan2f(hy, hx);
+    float steering = pid(1.7f, 0.01f, 3.5f, D[VD_H_PERR], D[VD_H_IERR], -wrap_to_pi(lane_heading - v_heading));
+    steering += pid(0.3f, 0.002f, 0.05f, D[VD_L_PERR], D[VD_L_IERR], -lat);
+    // acceleration (:303-320), km/h units
+    float target = D[VD_TARGET_SPEED];
+    float ratio = fmaxf(speed_kmh, 0.0f) / target;
+    float r2 = ratio * ratio, r4 = r2 * r2, r8 = r4 * r4;
+    float acc = 1.0f - r8 * r2;
+    if (front != OBJ_NONE) {
+        float ox, oy, ovx, ovy; int ol; bool pd;
+        nv.get(front, ox, oy, ovx, ovy, ol, pd);
+        float d = front_dist;
+        float dvx = S[VS_VEL] * 3.6f - ovx * 3.6f, dvy = S[VS_VEL + 1] * 3.6f - ovy * 3.6f;
+        float dv = dvx * hx + dvy * hy;
+        float d_star = 10.0f + speed_kmh * 1.5f + speed_kmh * dv / (2.0f * sqrtf(5.0f));
+        float nz = fabsf(d) > 1e-2f ? d : (d > 0.0f ? 1e-2f : -1e-2f);
+        float sd = d_star / nz;
+        acc -= sd * sd;
+    }
+    out_a0 = steering;
+    out_a1 = acc;
+#undef IN_CUR
+}
+
+// NodeNetworkNavigation.update_localization (component/navigation_module/node_network_navigation.py:130-304) with
+// ray_localization (utils/pg/utils.py:151-203) answered by AABB -> point-in-convex-hull over the map's lane table
+__device__ void localise(const MapView& m, const float* S, int* I, const int* __restrict__ route, float* navi) {
+    float px = S[VS_POS], py = S[VS_POS + 1];
+    M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
+    float hx, hy;
+    heading_vec(R, hx, hy);
+    int c0 = I[VI_CKPT0], c1 = I[VI_CKPT1], n_ck = I[VI_ROUTE_LEN];
+    int cur_road = find_road(m, route[c0], route[c0 + 1]);
+    int next_road = c1 != c0 ? find_road(m, route[c1], route[c1 + 1]) : -1;
+    int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+    int nx_first = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_FIRST] : -1;
+    int nx_n = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_N] : 0;
+    bool on_lane = false;
+    int best_any = -1, best_cur = -1, best_next = -1;
+    float d_any = 1e30f, d_cur = 1e30f, d_next = 1e30f;
+    const float4* bb4 = reinterpret_cast<const float4*>(m.lane_bb);
+    for (int l = 0; l < m.n_lanes; l++) {
+        float4 bb = __ldg(bb4 + l);
+        if (px < bb.x || py < bb.y || px > bb.z || py > bb.w) continue;
+        if (!point_in_hull(m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], px, py)) continue;
+        on_lane = true;
+        const float* Ll = m.lane_f + l * LANE_F;
+        float lon, lat;
+        lane_local(Ll, px, py, lon, lat);
+        float lh = lane_heading_at(Ll, lon);
+        float cosang = cosf(lh) * hx + sinf(lh) * hy;
+        if (!(cosang > 0.0f)) continue;
+        float dist = lane_distance(Ll, px, py);
+        if (dist < d_any) { d_any = dist; best_any = l; }
+        if (l >= cur_first && l < cur_first + cur_n && dist < d_cur) { d_cur = dist; best_cur = l; }
+        if (next_road >= 0 && l >= nx_first && l < nx_first + nx_n && dist < d_next) { d_next = dist; best_next = l; }
+    }
+    int lane = best_cur >= 0 ? best_cur : (next_road < 0 ? best_any : (best_next >= 0 ? best_next : best_any));
+    if (on_lane) I[VI_FLAGS] |= FL_ON_LANE; else I[VI_FLAGS] &= ~FL_ON_LANE;
+    if (lane < 0) lane = I[VI_LANE];
+    I[VI_LANE] = lane;
+    const float* Lc = m.lane_f + lane * LANE_F;
+    float lon, lat;
+    lane_local(Lc, px, py, lon, lat);
+    if (c0 != c1) {  // _update_target_checkpoints (:181-201)
+        int start = m.lane_i[lane * LANE_I + LI_FROM];
+        bool in_tail = false;
+        int idx = -1;
+        for (int k = c1; k < n_ck; k++) if (route[k] == start) { in_tail = true; break; }
+        if (in_tail && lon < 5.0f) {
+            for (int k = c1; k < n_ck - 1; k++) if (route[k] == start) { idx = k; break; }
+            if (idx >= 0) {
+                c0 = idx;
+                c1 = (idx + 1 == n_ck - 1) ? idx : idx + 1;
+                I[VI_CKPT0] = c0; I[VI_CKPT1] = c1;
+                cur_road = find_road(m, route[c0], route[c0 + 1]);
+                next_road = c1 != c0 ? find_road(m, route[c1], route[c1 + 1]) : -1;
+                cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST]; cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+                nx_first = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_FIRST] : -1;
+            }
+        }
+    }
+    float lane_w = Lc[LF_WIDTH];
+    float later_middle = ((float)cur_n / 2.0f - 0.5f) * lane_w;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {  // _get_info_for_checkpoint (:243-292)
+        int ref = k == 0 ? cur_first : (next_road >= 0 ? nx_first : cur_first);
+        const float* Lr = m.lane_f + ref * LANE_F;
+        float ckx, cky;
+        lane_position(Lr, Lr[LF_LENGTH], later_middle, ckx, cky);
+        float dx = ckx - px, dy = cky - py;
+        float dn = sqrtf(dx * dx + dy * dy);
+        if (dn > 50.0f) { dx = dx / dn * 50.0f; dy = dy / dn * 50.0f; }
+        float in_heading = dx * R.m[0][1] + dy * R.m[1][1];      // base_vehicle.py:983-988
+        float in_rhs = -(dx * R.m[0][0] + dy * R.m[1][0]);
+        float* o = navi + 5 * k;
+        o[0] = clipf((in_heading / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+        o[1] = clipf((in_rhs / 50.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+        float bend = 0.0f, dirv = 0.0f, angle = 0.0f;
+        if (Lr[LF_TYPE] != 0.0f) {
+            bend = Lr[LF_P0 + 2] / (60.0f + (float)cur_n * lane_w);
+            dirv = -Lr[LF_P0 + 5];
+            angle = Lr[LF_P0 + 6];
+        }
+        o[2] = clipf(bend, 0.0f, 1.0f);
+        o[3] = clipf((dirv + 1.0f) / 2.0f, 0.0f, 1.0f);
+        o[4] = clipf((angle * (180.0f / MD_PI) / 135.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    }
+}
+
+// BaseVehicle._state_check, static world part + sidewalk sweep (component/vehicle/base_vehicle.py:700-792),
+// broad phase = the map's uniform grid
+__device__ void state_check_static(const MapView& m, const Rect& r, int& flags) {
+    float rad = sqrtf(r.hu * r.hu + r.hv * r.hv);
+    int x0 = (int)floorf((r.cx - rad - m.gx0) / m.cell), x1 = (int)floorf((r.cx + rad - m.gx0) / m.cell);
+    int y0 = (int)floorf((r.cy - rad - m.gy0) / m.cell), y1 = (int)floorf((r.cy + rad - m.gy0) / m.cell);
+    x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, m.nx - 1); y1 = min(y1, m.ny - 1);
+    for (int cy = y0; cy <= y1; cy++)
+        for (int cx = x0; cx <= x1; cx++) {
+            int c = cy * m.nx + cx;
+            int k1 = m.gs[c + 1];
+            for (int k = m.gs[c]; k < k1; k++) {
+                int it = m.gi[k];
+                if (it < m.n_lines) {
+                    const float* Ln = m.lines + it * LINE_F;
+                    int kind = (int)Ln[LN_KIND];
+                    int bit = kind == 0 ? FL_ON_WHITE : (kind == 1 ? FL_ON_YELLOW : FL_ON_BROKEN);
+                    if (flags & bit) continue;
+                    Rect lr;
+                    lr.cx = Ln[LN_CX]; lr.cy = Ln[LN_CY]; lr.ux = Ln[LN_UX]; lr.uy = Ln[LN_UY]; lr.hu = Ln[LN_HALF]; lr.hv = LINE_HALF_W;
+                    if (rect_rect(r, lr)) flags |= bit;
+                } else {
+                    if (flags & FL_CRASH_SIDEWALK) continue;
+                    if (rect_quad(r, m.quads + (it - m.n_lines) * QUAD_F)) flags |= FL_CRASH_SIDEWALK;
+                }
+            }
+        }
+}
+
+// contact pairs of vehicle `slot` against the env's other bodies (engine/core/collision_callback.py:5-42 when
+// latch, component/vehicle/base_vehicle.py:735-742 otherwise)
+__device__ __forceinline__ int dynamic_contacts(const Nb* nb, float* obj, int S, int O, int slot, const Rect& r, bool latch,
+                                                int* obj_first, bool claim_pass) {
+    int flags = 0;
+    for (int k = 0; k < S; k++) {
+        if (k == slot || !nb[k].alive) continue;
+        if (rect_rect(r, nb[k].r)) flags |= FL_CRASH_VEHICLE;
+    }
+    for (int k = 0; k < O; k++) {
+        const float* Ob = obj + k * OBJ_F;
+        if (Ob[OB_KIND] < 0.0f) continue;
+        bool hit;
+        if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
+        else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
+        if (!hit) continue;
+        if (Ob[OB_KIND] == 3.0f) flags |= FL_CRASH_HUMAN;
+        else if (latch) {
+            if (Ob[OB_CRASHED] == 0.0f) {
+                if (claim_pass) atomicMin(&obj_first[k], slot);          // COST_ONCE: lowest slot takes the flag
+                else if (obj_first[k] == slot) flags |= FL_CRASH_OBJECT;
+            }
+        } else flags |= FL_CRASH_OBJECT;
+    }
+    return flags;
+}
+
+// reward / cost / done + the 19 state floats of the observation for one agent
+// (envs/metadrive_env.py:128-279, envs/base_env.py:586-623, obs/state_obs.py:64-151)
+__device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_step, const float* P, const float* S, float* C,
+                              int* I, const int* __restrict__ route, const float* navi, size_t a, const StepOut& out,
+                              bool write_scalars) {
+    float px = S[VS_POS], py = S[VS_POS + 1];
+    M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
+    float hx, hy;
+    heading_vec(R, hx, hy);
+    float speed_kmh = sqrtf(S[VS_VEL] * S[VS_VEL] + S[VS_VEL + 1] * S[VS_VEL + 1]) * 3.6f;
+    int flags = I[VI_FLAGS];
+    int c0 = I[VI_CKPT0], n_ck = I[VI_ROUTE_LEN];
+    int cur_road = find_road(m, route[c0], route[c0 + 1]);
+    int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+    int lane = I[VI_LANE];
+    float lane_w = m.lane_f[lane * LANE_F + LF_WIDTH];
+    if (write_scalars) {
+        I[VI_EP_LEN] += 1;
+        int rl = lane;
+        float positive = 1.0f;
+        if (!(lane >= cur_first && lane < cur_first + cur_n)) {
+            rl = cur_first;
+            positive = m.road_i[cur_road * ROAD_I + RI_NEG] ? -1.0f : 1.0f;
+        }
+        float long_last, long_now, lat_now, tmp;
+        lane_local(m.lane_f + rl * LANE_F, C[VC_LAST_X], C[VC_LAST_Y], long_last, tmp);
+        lane_local(m.lane_f + rl * LANE_F, px, py, long_now, lat_now);
+        float lateral_factor = cfg.use_lateral_reward ? clipf(1.0f - 2.0f * fabsf(lat_now) / lane_w, 0.0f, 1.0f) : 1.0f;
+        float rew = 0.0f;
+        rew += cfg.driving_reward * (long_now - long_last) * lateral_factor * positive;
+        rew += cfg.speed_reward * (speed_kmh / P[VP_MAX_SPEED]) * positive;
+        float step_reward = rew;
+        int final_road = find_road(m, route[n_ck - 2], route[n_ck - 1]);
+        int final_lane = m.road_i[final_road * ROAD_I + RI_FIRST] + m.road_i[final_road * ROAD_I + RI_N] - 1;
+        float fl_long, fl_lat;
+        lane_local(m.lane_f + final_lane * LANE_F, px, py, fl_long, fl_lat);
+        float fl_len = m.lane_f[final_lane * LANE_F + LF_LENGTH];
+        bool arrive = (fl_len - 5.0f < fl_long && fl_long < fl_len + 5.0f) &&
+                      (lane_w / 2.0f >= fl_lat && fl_lat >= (0.5f - (float)cur_n) * lane_w);
+        bool outr = !(flags & FL_ON_LANE);
+        if (cfg.out_of_route_done) outr = outr || (flags & FL_OUT_OF_ROUTE);
+        else if (cfg.on_continuous_line_done) outr = outr || (flags & (FL_ON_YELLOW | FL_ON_WHITE | FL_CRASH_SIDEWALK));
+        if (arrive) rew = cfg.success_reward;
+        else if (outr) rew = -cfg.out_of_road_penalty;
+        else if (flags & FL_CRASH_VEHICLE) rew = -cfg.crash_vehicle_penalty;
+        else if (flags & FL_CRASH_OBJECT) rew = -cfg.crash_object_penalty;
+        C[VC_EP_REWARD] += rew;
+        bool max_step = cfg.horizon > 0 && I[VI_EP_LEN] >= cfg.horizon;
+        bool done = false;
+        if (arrive) done = true;
+        if (outr) done = true;
+        if ((flags & FL_CRASH_VEHICLE) && cfg.crash_vehicle_done) done = true;
+        if ((flags & FL_CRASH_OBJECT) && cfg.crash_object_done) done = true;
+        if (flags & FL_CRASH_BUILDING) done = true;
+        if ((flags & FL_CRASH_HUMAN) && cfg.crash_human_done) done = true;
+        if (max_step && cfg.truncate_as_terminate) done = true;
+        float c = 0.0f;
+        if (outr) c = cfg.out_of_road_cost;
+        else if (flags & FL_CRASH_VEHICLE) c = cfg.crash_vehicle_cost;
+        else if (flags & FL_CRASH_OBJECT) c = cfg.crash_object_cost;
+        C[VC_TOTAL_COST] += c;
+        bool trunc = max_step;
+        if (cfg.horizon > 0 && env_step > 5 * cfg.horizon) {
+            trunc = true;
+            if (cfg.truncate_as_terminate) done = true;
+        }
+        if (done) I[VI_DONE] = 1;
+        out.reward[a] = rew; out.cost[a] = c;
+        out.term[a] = (uint8_t)(I[VI_DONE] != 0); out.trunc[a] = (uint8_t)trunc;
+        out.info_flags[a] = flags | (outr ? FL_OUT_OF_ROAD : 0) | (arrive ? FL_ARRIVE : 0) | (max_step ? FL_MAX_STEP : 0);
+        float4* inf = reinterpret_cast<float4*>(out.info_f + a * 8);
+        inf[0] = make_float4(sqrtf(S[VS_VEL] * S[VS_VEL] + S[VS_VEL + 1] * S[VS_VEL + 1]), S[VS_STEER], S[VS_THROTTLE], C[VC_STEP_ENERGY]);
+        inf[1] = make_float4(C[VC_ENERGY], step_reward, C[VC_EP_REWARD], (float)I[VI_EP_LEN]);
+    }
+    float* o = out.obs + a * (size_t)(OBS_STATE + cfg.n_lasers);
+    o[0] = clipf(C[VC_DIST_L] / 18.0f, 0.0f, 1.0f);
+    o[1] = clipf(C[VC_DIST_R] / 18.0f, 0.0f, 1.0f);
+    {
+        const float* Lr = m.lane_f + (cur_first + cur_n - 1) * LANE_F;
+        float lx, ly;
+        if (Lr[LF_TYPE] == 0.0f) {
+            float ex = Lr[LF_P0 + 2] - Lr[LF_P0 + 0], ey = Lr[LF_P0 + 3] - Lr[LF_P0 + 1];
+            float ln = sqrtf(ex * ex + ey * ey);
+            lx = ey / ln; ly = -ex / ln;
+        } else if (Lr[LF_P0 + 5] > 0.0f) { lx = px - Lr[LF_P0 + 0]; ly = py - Lr[LF_P0 + 1]; }
+        else { lx = Lr[LF_P0 + 0] - px; ly = Lr[LF_P0 + 1] - py; }
+        float ln = sqrtf(lx * lx + ly * ly), fn = sqrtf(hx * hx + hy * hy);
+        float hd = 0.0f;
+        if (ln * fn != 0.0f) hd = clipf((hx * lx + hy * ly) / (ln * fn), -1.0f, 1.0f) / 2.0f + 0.5f;
+        o[2] = hd;
+    }
+    o[3] = clipf((speed_kmh + 1.0f) / (P[VP_MAX_SPEED] + 1.0f), 0.0f, 1.0f);
+    o[4] = clipf((S[VS_STEER] / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o[5] = clipf((C[VC_CUR_A0] + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o[6] = clipf((C[VC_CUR_A1] + 1.0f) / 2.0f, 0.0f, 1.0f);
+    {
+        float lhx = C[VC_LAST_HX], lhy = C[VC_LAST_HY];
+        float dotp = hx * lhx + hy * lhy, crs = hx * lhy - hy * lhx;
+        float beta = dotp <= 0.0f ? 0.5f * MD_PI : atan2f(fabsf(crs), dotp);
+        o[7] = clipf(beta / 0.1f, 0.0f, 1.0f);
+    }
+    {
+        float lon, lat;
+        lane_local(m.lane_f + lane * LANE_F, px, py, lon, lat);
+        o[8] = clipf((lat * 2.0f / 4.5f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < NAVI_DIM; k++) o[OBS_EGO + k] = navi[k];
+}
+
+__device__ __forceinline__ void load16(float* dst, const float* src) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { float4 v = s4[k]; dst[4 * k] = v.x; dst[4 * k + 1] = v.y; dst[4 * k + 2] = v.z; dst[4 * k + 3] = v.w; }
+}
+__device__ __forceinline__ void store16(float* dst, const float* src) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int k = 0; k < 4; k++) d4[k] = make_float4(src[4 * k], src[4 * k + 1], src[4 * k + 2], src[4 * k + 3]);
+}
+__device__ __forceinline__ void load16i(int* dst, const int* src) {
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { int4 v = s4[k]; dst[4 * k] = v.x; dst[4 * k + 1] = v.y; dst[4 * k + 2] = v.z; dst[4 * k + 3] = v.w; }
+}
+__device__ __forceinline__ void store16i(int* dst, const int* src) {
+    int4* d4 = reinterpret_cast<int4*>(dst);
+#pragma unroll
+    for (int k = 0; k < 4; k++) d4[k] = make_int4(src[4 * k], src[4 * k + 1], src[4 * k + 2], src[4 * k + 3]);
+}
+
+__device__ __forceinline__ void fill_nb(Nb& n, const float* P, const float* S, const int* I) {
+    n.x = S[VS_POS]; n.y = S[VS_POS + 1]; n.vx = S[VS_VEL]; n.vy = S[VS_VEL + 1];
+    n.r = vehicle_rect(P, S);
+    n.lane = I[VI_LANE]; n.alive = I[VI_ALIVE]; n.active = I[VI_ACTIVE]; n.kind = I[VI_KIND];
+}
+
+// body row for the lidar kernel (BODY_ROW floats): centre(3) half(3) R(9) alive | origin x y, spare(2)
+#define BODY_ROW 20
+__device__ __forceinline__ void write_body_row(float* row, const float* P, const float* S, int alive) {
+    M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
+    float hh = 0.5f * P[VP_HEIGHT];
+    F3 cen = f3(S[VS_POS], S[VS_POS + 1], S[VS_POS + 2]) + col(R, 2) * hh;
+    float4* r4 = reinterpret_cast<float4*>(row);
+    r4[0] = make_float4(cen.x, cen.y, cen.z, 0.5f * P[VP_WIDTH]);
+    r4[1] = make_float4(0.5f * P[VP_LENGTH], hh, R.m[0][0], R.m[0][1]);
+    r4[2] = make_float4(R.m[0][2], R.m[1][0], R.m[1][1], R.m[1][2]);
+    r4[3] = make_float4(R.m[2][0], R.m[2][1], R.m[2][2], alive ? 1.0f : 0.0f);
+    r4[4] = make_float4(S[VS_POS], S[VS_POS + 1], 0.0f, 0.0f);
+}
+
+// ================================================================================================ k_step_vehicles
+// dynamic shared memory: per env of the CTA  Nb[S] | obj rows [O*OBJ_F] | obj_first[O]
+__global__ void __launch_bounds__(STEP_THREADS)
+k_step_vehicles(MdConfig cfg, MdArrays A, int mode, int envs_per_block, const float* __restrict__ actions,
+                const float* __restrict__ ext_act3, int n_sub, float* __restrict__ idm_out, StepOut out,
+                float* __restrict__ body_tab, const uint8_t* __restrict__ env_mask, Snapshot snap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
+    const int le = threadIdx.x / S, slot = threadIdx.x - le * S;
+    const int env = blockIdx.x * envs_per_block + le;
+    const bool in_range = le < envs_per_block && env < cfg.n_envs;
+    const size_t per_env = sizeof(Nb) * S + sizeof(float) * OBJ_F * O + sizeof(int) * ((O + 3) & ~3);
+    unsigned char* my = smem_raw + per_env * (in_range ? le : 0);
+    Nb* nb = reinterpret_cast<Nb*>(my);
+    float* sobj = reinterpret_cast<float*>(my + sizeof(Nb) * S);
+    int* obj_first = reinterpret_cast<int*>(my + sizeof(Nb) * S + sizeof(float) * OBJ_F * O);
+
+    bool masked_off = in_range && env_mask != nullptr && env_mask[env] == 0;
+    const bool work = in_range && !masked_off;
+    const int g = env * S + slot;
+    float P[VEH_P], St[VEH_S], C[VEH_C], D[VEH_IDM], navi[NAVI_DIM];
+    int I[VEH_I];
+    int env_step = 0, map = 0;
+    const int* route = nullptr;
+    if (work) {
+        if (mode & MODE_RESET) {  // restore the snapshot rows of this slot (env.reset)
+            load16(St, snap.veh_s + (size_t)g * VEH_S);
+            load16(C, snap.veh_c + (size_t)g * VEH_C);
+            load16i(I, snap.veh_i + (size_t)g * VEH_I);
+#pragma unroll
+            for (int k = 0; k < VEH_IDM; k++) D[k] = snap.veh_idm[(size_t)g * VEH_IDM + k];
+#pragma unroll
+            for (int k = 0; k < NAVI_DIM; k++) navi[k] = snap.veh_navi[(size_t)g * NAVI_DIM + k];
+            for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = snap.obj_f[(size_t)env * O * OBJ_F + k];
+            if (slot == 0)
+                for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = snap.env_i[env * ENV_I + k];
+        } else {
+            load16(St, A.veh_s + (size_t)g * VEH_S);
+            load16(C, A.veh_c + (size_t)g * VEH_C);
+            load16i(I, A.veh_i + (size_t)g * VEH_I);
+#pragma unroll
+            for (int k = 0; k < VEH_IDM; k++) D[k] = A.veh_idm[(size_t)g * VEH_IDM + k];
+#pragma unroll
+            for (int k = 0; k < NAVI_DIM; k++) navi[k] = A.veh_navi[(size_t)g * NAVI_DIM + k];
+        }
+        load16(P, A.veh_p + (size_t)g * VEH_P);
+        route = A.veh_route + (size_t)g * ROUTE_MAX;
+    }
+    __syncthreads();  // RESET wrote env_i / obj_f through global memory
+    if (work) {
+        map = (mode & MODE_RESET) ? snap.env_i[env * ENV_I + EI_MAP] : A.env_i[env * ENV_I + EI_MAP];
+        env_step = ((mode & MODE_RESET) ? snap.env_i[env * ENV_I + EI_STEP] : A.env_i[env * ENV_I + EI_STEP]) + ((mode & MODE_AGENT_PRE) ? 1 : 0);
+        fill_nb(nb[slot], P, St, I);
+        const float* og = (mode & MODE_RESET) ? snap.obj_f : A.obj_f;
+        for (int k = slot; k < O * OBJ_F; k += S) sobj[k] = og[(size_t)env * O * OBJ_F + k];
+    }
+    MapView m;
+    if (work) m = map_view(A, map);
+    Actuation act;
+    act.steer_rad = 0.0f; act.engine = 0.0f; act.brake = 2.0f;  // what vehicle.reset() leaves (base_vehicle.py:376)
+    const bool is_agent = work && I[VI_KIND] == 1;
+    const bool is_traffic = work && I[VI_KIND] == 2;
+
+    if (mode & MODE_RESET) {
+        if (work && I[VI_ALIVE] && (is_agent || is_traffic)) latch_before_step(St, C, I);
+    }
+    // ---- agent_manager.before_step (manager/agent_manager.py:164-202)
+    if ((mode & MODE_AGENT_PRE) && is_agent && I[VI_ACTIVE]) {
+        latch_before_step(St, C, I);
+        const float* a = actions + ((size_t)env * NA + slot) * 2;
+        act = actuate(P, St, C, a[0], a[1]);
+    }
+    __syncthreads();
+    // ---- PGTrafficManager.before_step: trigger (manager/traffic_manager.py:74-88), one thread per env
+    if ((mode & MODE_TRIGGER) && work && slot == 0 && cfg.traffic_mode != 1) {
+        int nt = A.env_i[env * ENV_I + EI_NEXT_TRIGGER];
+        const int n_blocks = A.env_i[env * ENV_I + EI_N_BLOCKS];
+        for (int s = 0; s < NA && nt > 0; s++) {
+            if (!nb[s].active || nb[s].kind != 1) continue;
+            int road = m.lane_i[nb[s].lane * LANE_I + LI_ROAD];
+            if (road == A.env_trigger[env * TRIGGER_MAX + nt]) {
+                for (int k = 0; k < S; k++)
+                    if (nb[k].kind == 2 && nb[k].alive && A.veh_i[(size_t)(env * S + k) * VEH_I + VI_TRIGGER] == nt) nb[k].active = 1;
+                nt = nt + 1 < n_blocks ? nt + 1 : 0;
+            }
+        }
+        A.env_i[env * ENV_I + EI_NEXT_TRIGGER] = nt;
+    }
+    if (work && slot == 0 && (mode & MODE_AGENT_PRE)) A.env_i[env * ENV_I + EI_STEP] = env_step;
+    __syncthreads();
+    if (work) I[VI_ACTIVE] = nb[slot].active;
+    // ---- IDM decisions against the pre-step world (policy/idm_policy.py:235-267)
+    if ((mode & (MODE_IDM | MODE_IDM_OUT)) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE]) {
+        NbrView nv;
+        nv.nb = nb; nv.obj = sobj; nv.S = S; nv.O = O; nv.self = slot; nv.px = St[VS_POS]; nv.py = St[VS_POS + 1];
+        float a0, a1;
+        idm_act(cfg, m, nv, g, St, I, D, route, a0, a1);
+        if (mode & MODE_IDM_OUT) { idm_out[2 * (size_t)g] = a0; idm_out[2 * (size_t)g + 1] = a1; }
+        if (mode & MODE_IDM) {
+            latch_before_step(St, C, I);
+            act = actuate(P, St, C, a0, a1);
+        }
+    }
+    if ((mode & MODE_EXT_ACT) && work) {
+        act.steer_rad = ext_act3[3 * (size_t)g]; act.engine = ext_act3[3 * (size_t)g + 1]; act.brake = ext_act3[3 * (size_t)g + 2];
+    }
+    // ---- engine.step: n_sub x doPhysics + contact-added callback (engine/base_engine.py:417-445)
+    if (mode & MODE_DYN) {
+        Body B;
+        if (work) {
+            B.pos = f3(St[VS_POS], St[VS_POS + 1], St[VS_POS + 2]);
+            B.q[0] = St[VS_QUAT]; B.q[1] = St[VS_QUAT + 1]; B.q[2] = St[VS_QUAT + 2]; B.q[3] = St[VS_QUAT + 3];
+            B.v = f3(St[VS_VEL], St[VS_VEL + 1], St[VS_VEL + 2]);
+            B.w = f3(St[VS_ANGVEL], St[VS_ANGVEL + 1], St[VS_ANGVEL + 2]);
+        }
+        const bool moves = work && I[VI_ALIVE] && !I[VI_STATIC];
+        for (int rep = 0; rep < n_sub; rep++) {
+            if (moves) {
+                vehicle_substep(P, B, act, cfg.dt);
+                St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y; St[VS_POS + 2] = B.pos.z;
+                St[VS_QUAT] = B.q[0]; St[VS_QUAT + 1] = B.q[1]; St[VS_QUAT + 2] = B.q[2]; St[VS_QUAT + 3] = B.q[3];
+                St[VS_VEL] = B.v.x; St[VS_VEL + 1] = B.v.y; St[VS_VEL + 2] = B.v.z;
+                St[VS_ANGVEL] = B.w.x; St[VS_ANGVEL + 1] = B.w.y; St[VS_ANGVEL + 2] = B.w.z;
+            }
+            if (mode & MODE_CONTACTS) {
+                __syncthreads();  // everyone finished reading the previous footprints
+                if (work) {
+                    nb[slot].r = vehicle_rect(P, St);
+                    nb[slot].x = St[VS_POS]; nb[slot].y = St[VS_POS + 1]; nb[slot].vx = St[VS_VEL]; nb[slot].vy = St[VS_VEL + 1];
+                    for (int k = slot; k < O; k += S) {  // kinematic movers (traffic_participants/pedestrian.py:67-95)
+                        obj_first[k] = 0x7fffffff;
+                        float* Ob = sobj + k * OBJ_F;
+                        if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
+                    }
+                }
+                __syncthreads();
+                if (work && I[VI_ALIVE]) I[VI_FLAGS] |= dynamic_contacts(nb, sobj, S, O, slot, nb[slot].r, true, obj_first, true);
+                __syncthreads();
+                if (work && I[VI_ALIVE]) I[VI_FLAGS] |= dynamic_contacts(nb, sobj, S, O, slot, nb[slot].r, true, obj_first, false);
+                __syncthreads();
+                if (work)
+                    for (int k = slot; k < O; k += S)
+                        if (obj_first[k] != 0x7fffffff) sobj[k * OBJ_F + OB_CRASHED] = 1.0f;
+            }
+        }
+    }
+    // ---- engine.after_step (component/vehicle/base_vehicle.py:234-271)
+    if (mode & (MODE_POST | MODE_RESET)) {
+        __syncthreads();
+        if (work) { nb[slot].r = vehicle_rect(P, St); nb[slot].alive = I[VI_ALIVE]; }
+        __syncthreads();
+        const bool do_post = work && I[VI_ALIVE] && ((mode & MODE_RESET) ? (is_agent || is_traffic) : (I[VI_ACTIVE] != 0));
+        if (do_post) {
+            if (mode & MODE_CLEAR_FLAGS) I[VI_FLAGS] = FL_ON_LANE;
+            localise(m, St, I, route, navi);
+            Rect r = nb[slot].r;
+            int flags = I[VI_FLAGS];
+            state_check_static(m, r, flags);
+            flags |= dynamic_contacts(nb, sobj, S, O, slot, r, false, obj_first, false);
+            I[VI_FLAGS] = flags;
+            int c0 = I[VI_CKPT0];
+            int cur_road = find_road(m, route[c0], route[c0 + 1]);
+            int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+            float lon, lat;
+            lane_local(m.lane_f + cur_first * LANE_F, St[VS_POS], St[VS_POS + 1], lon, lat);
+            float lane_w = m.lane_f[I[VI_LANE] * LANE_F + LF_WIDTH];
+            float to_left = lat + lane_w / 2.0f;
+            float to_right = lane_w * (float)cur_n - to_left;
+            C[VC_DIST_L] = to_left; C[VC_DIST_R] = to_right;
+            if (to_right < 0.0f || to_left < 0.0f) I[VI_FLAGS] |= FL_OUT_OF_ROUTE;
+            float dx = C[VC_LAST_X] - St[VS_POS], dy = C[VC_LAST_Y] - St[VS_POS + 1];
+            float dist_km = sqrtf(dx * dx + dy * dy) / 1000.0f;
+            float speed_kmh = sqrtf(St[VS_VEL] * St[VS_VEL] + St[VS_VEL + 1] * St[VS_VEL + 1]) * 3.6f;
+            float step_energy = 3.25f * expf(0.01f * speed_kmh) * dist_km / 100.0f * 1000.0f;
+            C[VC_STEP_ENERGY] = step_energy;
+            C[VC_ENERGY] += step_energy;
+            if ((mode & MODE_RESET) && !I[VI_ACTIVE]) I[VI_FLAGS] = FL_ON_LANE;  // reset() ends with _init_step_info
+        }
+        // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111)
+        if ((mode & MODE_REMOVE) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE] && !(I[VI_FLAGS] & FL_ON_LANE)) {
+            I[VI_ALIVE] = 0; I[VI_ACTIVE] = 0;
+        }
+    }
+    // ---- _get_step_return (envs/base_env.py:586-623)
+    if ((mode & (MODE_OUT | MODE_RESET)) && is_agent && I[VI_ACTIVE] && slot < NA) {
+        size_t a = (size_t)env * NA + slot;
+        agent_outputs(cfg, m, env_step, P, St, C, I, route, navi, a, out, (mode & MODE_OUT) != 0);
+    }
+    // ---- write back
+    if (work) {
+        store16(A.veh_s + (size_t)g * VEH_S, St);
+        store16(A.veh_c + (size_t)g * VEH_C, C);
+        store16i(A.veh_i + (size_t)g * VEH_I, I);
+#pragma unroll
+        for (int k = 0; k < VEH_IDM; k++) A.veh_idm[(size_t)g * VEH_IDM + k] = D[k];
+#pragma unroll
+        for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = navi[k];
+        write_body_row(body_tab + (size_t)g * BODY_ROW, P, St, I[VI_ALIVE]);
+    }
+    if (mode & (MODE_CONTACTS | MODE_RESET)) {
+        __syncthreads();
+        if (work && (mode & MODE_CONTACTS))
+            for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = sobj[k];
+    }
+}
+
+// ================================================================================================ k_lidar
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__host__ __device__ inline size_t lidar_smem_per_warp(int S, int O) {
+    size_t b = (size_t)S * BODY_ROW * 4 + (size_t)O * OBJ_F * 4 + sizeof(float) * (size_t)(S + O);
+    return ((b + 15) & ~(size_t)15) + 16;
+}
+
+// Lidar.perceive (component/sensors/lidar.py:49-73 -> sensors/distance_detector.py:27-85), one warp per agent.
+// The reference's angular mask (lidar.py:140-168) only skips rays that provably miss; here every ray is cast and a
+// conservative bounding-circle test prunes the (ray, body) pairs instead.
+__global__ void __launch_bounds__(LIDAR_WARPS * 32)
+k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restrict__ obj_f, const int* __restrict__ veh_i,
+        float* __restrict__ out, int out_stride, int out_off, int* __restrict__ hit_out, const uint8_t* __restrict__ env_mask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env, N = cfg.n_lasers;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t body_bytes = (size_t)S * BODY_ROW * 4, obj_bytes = (size_t)O * OBJ_F * 4;
+    const size_t per_warp = lidar_smem_per_warp(S, O);
+    unsigned char* my = smem_raw + per_warp * warp;
+    float* sbody = reinterpret_cast<float*>(my);
+    float* sobj = reinterpret_cast<float*>(my + body_bytes);
+    float* srad = reinterpret_cast<float*>(my + body_bytes + obj_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(my + per_warp - 16);
+
+    const long long a = (long long)blockIdx.x * LIDAR_WARPS + warp;
+    if (a >= (long long)cfg.n_envs * NA) return;
+    const int env = (int)(a / NA), slot = (int)(a - (long long)env * NA);
+    if (env_mask != nullptr && env_mask[env] == 0) return;
+    if (!veh_i[(size_t)(env * S + slot) * VEH_I + VI_ACTIVE]) return;
+
+    // stage the env's body rows and object rows: one bulk async copy (TMA 1-D) each, completing on the warp's mbarrier
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(body_bytes + obj_bytes));
+        bulk_g2s(sbody, body_tab + (size_t)env * S * BODY_ROW, (uint32_t)body_bytes, bar);
+        if (obj_bytes) bulk_g2s(sobj, obj_f + (size_t)env * O * OBJ_F, (uint32_t)obj_bytes, bar);
+    }
+    mbar_wait(bar, 0);
+
+    // bounding radii for the conservative prune (+0.1 % + 1 mm slack); < 0 marks "skip"
+    for (int k = lane; k < S; k += 32) {
+        const float* b = sbody + BODY_ROW * k;
+        srad[k] = (b[15] != 0.0f && k != slot) ? sqrtf(b[3] * b[3] + b[4] * b[4] + b[5] * b[5]) * 1.001f + 1e-3f : -1.0f;
+    }
+    for (int k = lane; k < O; k += 32) {
+        const float* ob = sobj + OBJ_F * k;
+        float r = ob[OB_KIND] == 2.0f ? sqrtf(ob[OB_A] * ob[OB_A] + ob[OB_B] * ob[OB_B]) : ob[OB_A];
+        srad[S + k] = ob[OB_KIND] >= 0.0f ? r * 1.001f + 1e-3f : -1.0f;
+    }
+    __syncwarp();
+
+    const float* eb = sbody + BODY_ROW * slot;
+    const float D = cfg.lidar_dist;
+    float hx, hy;
+    {
+        float fx = eb[7], fy = eb[10];  // R[0][1], R[1][1]: the chassis +Y axis
+        float n = sqrtf(fx * fx + fy * fy);
+        hx = fx / n; hy = fy / n;
+    }
+    const F3 o = f3(eb[16], eb[17], LIDAR_HEIGHT);
+    float* orow = out + (size_t)a * out_stride + out_off;
+    int* hrow = hit_out ? hit_out + (size_t)a * N : nullptr;
+    for (int i = lane; i < N; i += 32) {
+        const float c = c_ray_cs[2 * i], s = c_ray_cs[2 * i + 1];
+        const float ux = hx * c - hy * s, uy = hy * c + hx * s;   // unit direction (distance_detector.py:177-180)
+        const F3 d = f3(ux * D, uy * D, 0.0f);
+        float best = 2.0f;
+        int hit = -1;
+        for (int k = 0; k < S; k++) {
+            const float rb = srad[k];
+            if (rb < 0.0f) continue;
+            const float* b = sbody + BODY_ROW * k;
+            const float rx = b[0] - o.x, ry = b[1] - o.y;
+            const float proj = rx * ux + ry * uy;
+            const float perp2 = (rx * rx + ry * ry) - proj * proj;
+            if (perp2 > rb * rb + 1e-3f || proj < -rb || proj > D + rb) continue;
+            M3 R;
+            R.m[0][0] = b[6]; R.m[0][1] = b[7]; R.m[0][2] = b[8];
+            R.m[1][0] = b[9]; R.m[1][1] = b[10]; R.m[1][2] = b[11];
+            R.m[2][0] = b[12]; R.m[2][1] = b[13]; R.m[2][2] = b[14];
+            float t = ray_obb(o, d, f3(b[0], b[1], b[2]), R, f3(b[3], b[4], b[5]));
+            if (t < best) { best = t; hit = k; }
+        }
+        for (int k = 0; k < O; k++) {
+            const float rb = srad[S + k];
+            if (rb < 0.0f) continue;
+            const float* ob = sobj + OBJ_F * k;
+            const float rx = ob[OB_X] - o.x, ry = ob[OB_Y] - o.y;
+            const float proj = rx * ux + ry * uy;
+            const float perp2 = (rx * rx + ry * ry) - proj * proj;
+            if (perp2 > rb * rb + 1e-3f || proj < -rb || proj > D + rb) continue;
+            float t;
+            if (ob[OB_KIND] == 2.0f) {
+                float ch = cosf(ob[OB_HEADING]), sh = sinf(ob[OB_HEADING]);
+                M3 R;
+                R.m[0][0] = ch; R.m[0][1] = -sh; R.m[0][2] = 0.0f; R.m[1][0] = sh; R.m[1][1] = ch; R.m[1][2] = 0.0f;
+                R.m[2][0] = 0.0f; R.m[2][1] = 0.0f; R.m[2][2] = 1.0f;
+                t = ray_obb(o, d, f3(ob[OB_X], ob[OB_Y], ob[OB_ZC]), R, f3(ob[OB_B], ob[OB_A], 0.5f * ob[OB_HEIGHT]));
+            } else {
+                t = ray_zcyl(o, d, ob[OB_X], ob[OB_Y], ob[OB_ZC], ob[OB_A], 0.5f * ob[OB_HEIGHT]);
+            }
+            if (t < best) { best = t; hit = S + k; }
+        }
+        orow[i] = best <= 1.0f ? best : 1.0f;
+        if (hrow) hrow[i] = best <= 1.0f ? hit : -1;
+    }
+}
+
+// env finished <=> none of its active agents is still running (single-agent: the agent terminated or truncated)
+__global__ void k_done_mask(MdConfig cfg, const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc,
+                            uint8_t* __restrict__ mask) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cfg.n_envs) return;
+    bool any_running = false;
+    for (int s = 0; s < cfg.agents_per_env; s++) {
+        size_t a = (size_t)e * cfg.agents_per_env + s;
+        if (!(term[a] || trunc[a])) any_running = true;
+    }
+    mask[e] = any_running ? 0 : 1;
+}
+
+// ================================================================================================ host side / C ABI
+struct md_sim {
+    MdConfig cfg;
+    int device;
+    std::string err;
+    MdArrays dev;           // device pointers
+    int64_t rows[21];
+    size_t bytes[21];
+    Snapshot snap;
+    void* snap_bufs[7];
+    float* body_tab;
+    uint8_t* mask;
+    cudaStream_t stream;    // own stream for the *_host entry points
+    // pinned host staging + device mirrors for the *_host entry points
+    float *h_actions, *h_obs, *h_reward, *h_cost, *h_info_f;
+    uint8_t *h_term, *h_trunc, *h_mask;
+    int32_t* h_info_flags;
+    float *d_actions, *d_obs, *d_reward, *d_cost, *d_info_f;
+    uint8_t *d_term, *d_trunc, *d_mask_in;
+    int32_t* d_info_flags;
+    int64_t launches;
+    bool loaded;
+};
+
+static const char* kNames[21] = {"map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f",
+                                 "quad_f", "grid_start", "grid_items", "env_i", "env_trigger", "veh_p", "veh_s", "veh_c",
+                                 "veh_i", "veh_route", "veh_idm", "veh_navi", "obj_f"};
+static const int kRowBytes[21] = {MAPD * 4, MAPDF * 4, LANE_F * 4, LANE_I * 4, 16, ROAD_I * 4, 8, LINE_F * 4, QUAD_F * 4, 4, 4,
+                                  ENV_I * 4, TRIGGER_MAX * 4, VEH_P * 4, VEH_S * 4, VEH_C * 4, VEH_I * 4, ROUTE_MAX * 4,
+                                  VEH_IDM * 4, NAVI_DIM * 4, OBJ_F * 4};
+static const int kSnapIdx[7] = {11, 14, 15, 16, 18, 19, 20};  // env_i veh_s veh_c veh_i veh_idm veh_navi obj_f
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            sim->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return -1;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+static void** arr_slot(MdArrays* a, int i) { return reinterpret_cast<void**>(a) + i; }
+
+extern "C" int md_abi_version(void) { return MD_ABI_VERSION; }
+
+extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
+    if (!cfg || !out) return -2;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        fprintf(stderr, "libmdstep: no usable CUDA device %d (count %d) - there is no CPU fallback\n", device, n);
+        return -3;
+    }
+    md_sim* sim = new md_sim();
+    sim->cfg = *cfg;
+    sim->device = device;
+    sim->loaded = false;
+    sim->launches = 0;
+    memset(&sim->dev, 0, sizeof(sim->dev));
+    *out = sim;
+    if (cfg->n_lasers > MAX_LASERS || cfg->slots_per_env > STEP_THREADS || cfg->slots_per_env < 1 ||
+        cfg->agents_per_env > cfg->slots_per_env || cfg->slots_per_env + cfg->objs_per_env > 128) {
+        sim->err = "unsupported sizes: n_lasers <= 512, slots_per_env <= 128, slots + objects per env <= 128";
+        return -4;
+    }
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
+    std::vector<float> tab(2 * MAX_LASERS, 0.0f);
+    for (int i = 0; i < cfg->n_lasers; i++) {
+        double a = (double)i * (2.0 * 3.14159265358979323846 / (double)cfg->n_lasers);
+        tab[2 * i] = (float)cos(a);
+        tab[2 * i + 1] = (float)sin(a);
+    }
+    CK(cudaMemcpyToSymbol(c_ray_cs, tab.data(), sizeof(float) * 2 * MAX_LASERS));
+    return 0;
+}
+
+extern "C" const char* md_last_error(const md_sim* sim) { return sim ? sim->err.c_str() : "null handle"; }
+extern "C" int64_t md_launch_count(const md_sim* sim) { return sim ? sim->launches : 0; }
+
+extern "C" void md_destroy(md_sim* sim) {
+    if (!sim) return;
+    cudaSetDevice(sim->device);
+    if (sim->loaded) {
+        for (int i = 0; i < 21; i++) cudaFree(*arr_slot(&sim->dev, i));
+        for (int i = 0; i < 7; i++) cudaFree(sim->snap_bufs[i]);
+        cudaFree(sim->body_tab); cudaFree(sim->mask);
+        cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_reward); cudaFreeHost(sim->h_cost);
+        cudaFreeHost(sim->h_info_f); cudaFreeHost(sim->h_term); cudaFreeHost(sim->h_trunc); cudaFreeHost(sim->h_mask);
+        cudaFreeHost(sim->h_info_flags);
+        cudaFree(sim->d_actions); cudaFree(sim->d_obs); cudaFree(sim->d_reward); cudaFree(sim->d_cost); cudaFree(sim->d_info_f);
+        cudaFree(sim->d_term); cudaFree(sim->d_trunc); cudaFree(sim->d_mask_in); cudaFree(sim->d_info_flags);
+    }
+    cudaStreamDestroy(sim->stream);
+    delete sim;
+}
+
+static int set_snapshot_ptrs(md_sim* sim) {
+    sim->snap.env_i = (const int*)sim->snap_bufs[0];
+    sim->snap.veh_s = (const float*)sim->snap_bufs[1];
+    sim->snap.veh_c = (const float*)sim->snap_bufs[2];
+    sim->snap.veh_i = (const int*)sim->snap_bufs[3];
+    sim->snap.veh_idm = (const float*)sim->snap_bufs[4];
+    sim->snap.veh_navi = (const float*)sim->snap_bufs[5];
+    sim->snap.obj_f = (const float*)sim->snap_bufs[6];
+    return 0;
+}
+
+extern "C" int md_snapshot(md_sim* sim) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    for (int k = 0; k < 7; k++)
+        CK(cudaMemcpy(sim->snap_bufs[k], *arr_slot(&sim->dev, kSnapIdx[k]), sim->bytes[kSnapIdx[k]], cudaMemcpyDeviceToDevice));
+    return 0;
+}
+
+extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* rows) {
+    if (!sim || !host || !rows) return -2;
+    if (sim->loaded) { sim->err = "scene already loaded; create a new handle"; return -5; }
+    CK(cudaSetDevice(sim->device));
+    const MdConfig& c = sim->cfg;
+    const int64_t NV = (int64_t)c.n_envs * c.slots_per_env;
+    if (rows[13] != NV || rows[14] != NV || rows[16] != NV || rows[11] != c.n_envs) {
+        sim->err = "row counts do not match the configuration";
+        return -6;
+    }
+    for (int i = 0; i < 21; i++) {
+        sim->rows[i] = rows[i];
+        sim->bytes[i] = (size_t)rows[i] * kRowBytes[i];
+        void* d = nullptr;
+        CK(cudaMalloc(&d, sim->bytes[i] ? sim->bytes[i] : 16));
+        const void* h = *arr_slot(const_cast<MdArrays*>(host), i);
+        if (sim->bytes[i]) CK(cudaMemcpy(d, h, sim->bytes[i], cudaMemcpyHostToDevice));
+        *arr_slot(&sim->dev, i) = d;
+    }
+    for (int k = 0; k < 7; k++) CK(cudaMalloc(&sim->snap_bufs[k], sim->bytes[kSnapIdx[k]] ? sim->bytes[kSnapIdx[k]] : 16));
+    set_snapshot_ptrs(sim);
+    CK(cudaMalloc(&sim->body_tab, (size_t)NV * BODY_ROW * 4));
+    CK(cudaMemset(sim->body_tab, 0, (size_t)NV * BODY_ROW * 4));
+    CK(cudaMalloc(&sim->mask, (size_t)c.n_envs));
+    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_STATE + c.n_lasers;
+    CK(cudaMallocHost(&sim->h_actions, NA * 2 * 4)); CK(cudaMallocHost(&sim->h_obs, NA * od * 4));
+    CK(cudaMallocHost(&sim->h_reward, NA * 4)); CK(cudaMallocHost(&sim->h_cost, NA * 4));
+    CK(cudaMallocHost(&sim->h_info_f, NA * 8 * 4)); CK(cudaMallocHost(&sim->h_term, NA)); CK(cudaMallocHost(&sim->h_trunc, NA));
+    CK(cudaMallocHost(&sim->h_mask, (size_t)c.n_envs)); CK(cudaMallocHost(&sim->h_info_flags, NA * 4));
+    CK(cudaMalloc(&sim->d_actions, NA * 2 * 4)); CK(cudaMalloc(&sim->d_obs, NA * od * 4));
+    CK(cudaMalloc(&sim->d_reward, NA * 4)); CK(cudaMalloc(&sim->d_cost, NA * 4)); CK(cudaMalloc(&sim->d_info_f, NA * 8 * 4));
+    CK(cudaMalloc(&sim->d_term, NA)); CK(cudaMalloc(&sim->d_trunc, NA)); CK(cudaMalloc(&sim->d_mask_in, (size_t)c.n_envs));
+    CK(cudaMalloc(&sim->d_info_flags, NA * 4));
+    sim->loaded = true;
+    return md_snapshot(sim);
+}
+
+static int find_name(const char* name) {
+    for (int i = 0; i < 21; i++)
+        if (strcmp(name, kNames[i]) == 0) return i;
+    return -1;
+}
+extern "C" int md_get_state(md_sim* sim, const char* name, void* host_dst, size_t bytes) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    if (strcmp(name, "body_tab") == 0) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(host_dst, sim->body_tab, bytes, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    int i = find_name(name);
+    if (i < 0 || bytes != sim->bytes[i]) { sim->err = std::string("md_get_state: bad name or size for ") + name; return -7; }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host_dst, *arr_slot(&sim->dev, i), bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int md_set_state(md_sim* sim, const char* name, const void* host_src, size_t bytes) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    int i = find_name(name);
+    if (i < 0 || bytes != sim->bytes[i]) { sim->err = std::string("md_set_state: bad name or size for ") + name; return -7; }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(*arr_slot(&sim->dev, i), host_src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int launch_step(md_sim* sim, int mode, const float* actions, const float* ext_act3, int n_sub, float* idm_out,
+                       StepOut out, const uint8_t* mask, cudaStream_t st) {
+    const MdConfig& c = sim->cfg;
+    int epb = STEP_THREADS / c.slots_per_env;
+    if (epb < 1) epb = 1;
+    int threads = epb * c.slots_per_env;
+    threads = (threads + 31) & ~31;
+    int blocks = (c.n_envs + epb - 1) / epb;
+    size_t per_env = sizeof(Nb) * c.slots_per_env + sizeof(float) * OBJ_F * c.objs_per_env + sizeof(int) * ((c.objs_per_env + 3) & ~3);
+    size_t smem = per_env * epb;
+    k_step_vehicles<<<blocks, threads, smem, st>>>(c, sim->dev, mode, epb, actions, ext_act3, n_sub, idm_out, out, sim->body_tab,
+                                                  mask, sim->snap);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* hit, const uint8_t* mask, cudaStream_t st) {
+    const MdConfig& c = sim->cfg;
+    long long na = (long long)c.n_envs * c.agents_per_env;
+    int blocks = (int)((na + LIDAR_WARPS - 1) / LIDAR_WARPS);
+    size_t smem = lidar_smem_per_warp(c.slots_per_env, c.objs_per_env) * LIDAR_WARPS;
+    k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, out, stride, off, hit, mask);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev, void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    StepOut out = {obs_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (launch_step(sim, MODE_RESET, nullptr, nullptr, 0, nullptr, out, env_mask_dev, st)) return -1;
+    return launch_lidar(sim, obs_dev, OBS_STATE + sim->cfg.n_lasers, OBS_STATE, nullptr, env_mask_dev, st);
+}
+
+extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
+                       uint8_t* terminated_dev, uint8_t* truncated_dev, int32_t* info_flags_dev, float* info_f_dev, void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    StepOut out = {obs_dev, reward_dev, cost_dev, terminated_dev, truncated_dev, info_flags_dev, info_f_dev};
+    if (launch_step(sim, MODE_FULL, actions_dev, nullptr, sim->cfg.decision_repeat, nullptr, out, nullptr, st)) return -1;
+    return launch_lidar(sim, obs_dev, OBS_STATE + sim->cfg.n_lasers, OBS_STATE, nullptr, nullptr, st);
+}
+
+extern "C" int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    k_done_mask<<<(sim->cfg.n_envs + 255) / 256, 256, 0, st>>>(sim->cfg, terminated_dev, truncated_dev, sim->mask);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return md_reset(sim, sim->mask, obs_dev, stream);
+}
+
+extern "C" int md_lidar(md_sim* sim, float* frac_dev, int32_t* hit_dev, void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // refresh the body rows from the current state without moving anything
+    StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (launch_step(sim, 0, nullptr, nullptr, 0, nullptr, out, nullptr, st)) return -1;
+    return launch_lidar(sim, frac_dev, sim->cfg.n_lasers, 0, hit_dev, nullptr, st);
+}
+extern "C" int md_dynamics(md_sim* sim, const float* act3_dev, int n_sub, void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    return launch_step(sim, MODE_DYN | MODE_EXT_ACT, nullptr, act3_dev, n_sub, nullptr, out, nullptr, (cudaStream_t)stream);
+}
+extern "C" int md_after_step(md_sim* sim, void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    return launch_step(sim, MODE_POST | MODE_CLEAR_FLAGS, nullptr, nullptr, 0, nullptr, out, nullptr, (cudaStream_t)stream);
+}
+extern "C" int md_idm(md_sim* sim, float* out_actions_dev, void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    return launch_step(sim, MODE_IDM_OUT, nullptr, nullptr, 0, out_actions_dev, out, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int md_reset_host(md_sim* sim, const uint8_t* env_mask, float* obs) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    const MdConfig& c = sim->cfg;
+    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_STATE + c.n_lasers;
+    const uint8_t* dm = nullptr;
+    if (env_mask) {
+        memcpy(sim->h_mask, env_mask, (size_t)c.n_envs);
+        CK(cudaMemcpyAsync(sim->d_mask_in, sim->h_mask, (size_t)c.n_envs, cudaMemcpyHostToDevice, sim->stream));
+        dm = sim->d_mask_in;
+    }
+    if (md_reset(sim, dm, sim->d_obs, sim->stream)) return -1;
+    CK(cudaMemcpyAsync(sim->h_obs, sim->d_obs, NA * od * 4, cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    memcpy(obs, sim->h_obs, NA * od * 4);
+    return 0;
+}
+
+extern "C" int md_step_host(md_sim* sim, const float* actions, float* obs, float* reward, float* cost, uint8_t* terminated,
+                            uint8_t* truncated, int32_t* info_flags, float* info_f, int autoreset) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    const MdConfig& c = sim->cfg;
+    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_STATE + c.n_lasers;
+    memcpy(sim->h_actions, actions, NA * 2 * 4);
+    CK(cudaMemcpyAsync(sim->d_actions, sim->h_actions, NA * 2 * 4, cudaMemcpyHostToDevice, sim->stream));
+    if (md_step(sim, sim->d_actions, sim->d_obs, sim->d_reward, sim->d_cost, sim->d_term, sim->d_trunc, sim->d_info_flags,
+                sim->d_info_f, sim->stream))
+        return -1;
+    // scalars are read before the optional auto-reset overwrites the observation rows of finished envs
+    CK(cudaMemcpyAsync(sim->h_reward, sim->d_reward, NA * 4, cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_cost, sim->d_cost, NA * 4, cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_term, sim->d_term, NA, cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_trunc, sim->d_trunc, NA, cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_info_flags, sim->d_info_flags, NA * 4, cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_info_f, sim->d_info_f, NA * 8 * 4, cudaMemcpyDeviceToHost, sim->stream));
+    if (autoreset && md_autoreset(sim, sim->d_term, sim->d_trunc, sim->d_obs, sim->stream)) return -1;
+    CK(cudaMemcpyAsync(sim->h_obs, sim->d_obs, NA * od * 4, cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    memcpy(obs, sim->h_obs, NA * od * 4);
+    memcpy(reward, sim->h_reward, NA * 4);
+    memcpy(cost, sim->h_cost, NA * 4);
+    memcpy(terminated, sim->h_term, NA);
+    memcpy(truncated, sim->h_trunc, NA);
+    memcpy(info_flags, sim->h_info_flags, NA * 4);
+    memcpy(info_f, sim->h_info_f, NA * 8 * 4);
+    return 0;
+}

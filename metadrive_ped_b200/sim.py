@@ -1,0 +1,150 @@
+"""BatchedSim: one handle of libmdstep.so on one GPU, with torch tensors as caller-owned device buffers.
+
+Mirrors the step surface of the reference engine for E environments at once:
+  reset()  ~ BaseEnv.reset   (envs/base_env.py:502-537)          -> obs [A, 19 + n_lasers]
+  step(a)  ~ BaseEnv.step    (envs/base_env.py:426-431, 586-623) -> obs, reward, cost, terminated, truncated, info
+PyTorch is used for device memory and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _libmod
+from .abi import MdArrays, MdConfig
+from .scene import ARRAY_ORDER
+
+INFO_F_NAMES = ["velocity", "steering", "acceleration", "step_energy", "episode_energy", "step_reward",
+                "episode_reward", "episode_length"]
+
+
+class BatchedSim:
+    def __init__(self, arrays: dict, cfg: MdConfig, device: int = 0):
+        import torch
+        if not torch.cuda.is_available():
+            raise _libmod.MdStepError("BatchedSim needs a CUDA device; this package has no CPU fallback")
+        self.torch = torch
+        self.lib = _libmod.load()
+        self.cfg = cfg
+        self.device = device
+        self.tdev = torch.device("cuda", device)
+        self.h = C.c_void_p()
+        rc = self.lib.md_create(C.byref(cfg), device, C.byref(self.h))
+        self._check(rc)
+        self._host = {k: np.ascontiguousarray(arrays[k]) for k in ARRAY_ORDER}
+        rows = (C.c_int64 * len(ARRAY_ORDER))(*[self._host[k].shape[0] for k in ARRAY_ORDER])
+        ha = MdArrays(**{k: self._host[k].ctypes.data_as(C.c_void_p) for k in ARRAY_ORDER})
+        self._check(self.lib.md_load_scene(self.h, C.byref(ha), rows))
+        self.n_agents = cfg.n_envs * cfg.agents_per_env
+        self.obs_dim = 19 + cfg.n_lasers
+        na = self.n_agents
+        kw = dict(device=self.tdev)
+        self.obs = torch.zeros((na, self.obs_dim), dtype=torch.float32, **kw)
+        self.reward = torch.zeros(na, dtype=torch.float32, **kw)
+        self.cost = torch.zeros(na, dtype=torch.float32, **kw)
+        self.terminated = torch.zeros(na, dtype=torch.uint8, **kw)
+        self.truncated = torch.zeros(na, dtype=torch.uint8, **kw)
+        self.info_flags = torch.zeros(na, dtype=torch.int32, **kw)
+        self.info_f = torch.zeros((na, 8), dtype=torch.float32, **kw)
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.md_last_error(self.h) if self.h else b""
+            raise _libmod.MdStepError("libmdstep call failed (%d): %s" % (rc, (msg or b"").decode()))
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+    # ------------------------------------------------------------------ device-resident API (tensors in, tensors out)
+    def reset(self, env_mask=None):
+        self._check(self.lib.md_reset(self.h, self._ptr(env_mask), self._ptr(self.obs), self._stream()))
+        return self.obs
+
+    def step(self, actions, autoreset=False):
+        assert actions.is_cuda and actions.dtype == self.torch.float32 and actions.is_contiguous()
+        assert actions.numel() == self.n_agents * 2
+        self._check(self.lib.md_step(self.h, self._ptr(actions), self._ptr(self.obs), self._ptr(self.reward),
+                                     self._ptr(self.cost), self._ptr(self.terminated), self._ptr(self.truncated),
+                                     self._ptr(self.info_flags), self._ptr(self.info_f), self._stream()))
+        if autoreset:
+            self._check(self.lib.md_autoreset(self.h, self._ptr(self.terminated), self._ptr(self.truncated),
+                                              self._ptr(self.obs), self._stream()))
+        return self.obs, self.reward, self.cost, self.terminated, self.truncated
+
+    # ------------------------------------------------------------------ host-buffer API (numpy in, numpy out)
+    def step_host(self, actions: np.ndarray, autoreset=False):
+        na = self.n_agents
+        a = np.ascontiguousarray(actions, np.float32).reshape(na, 2)
+        if not hasattr(self, "_hb"):
+            self._hb = dict(obs=np.zeros((na, self.obs_dim), np.float32), reward=np.zeros(na, np.float32),
+                            cost=np.zeros(na, np.float32), term=np.zeros(na, np.uint8), trunc=np.zeros(na, np.uint8),
+                            flags=np.zeros(na, np.int32), info_f=np.zeros((na, 8), np.float32))
+        b = self._hb
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.md_step_host(self.h, p(a), p(b["obs"]), p(b["reward"]), p(b["cost"]), p(b["term"]),
+                                          p(b["trunc"]), p(b["flags"]), p(b["info_f"]), int(bool(autoreset))))
+        return b["obs"], b["reward"], b["cost"], b["term"], b["trunc"], b["flags"], b["info_f"]
+
+    def reset_host(self, env_mask=None):
+        na = self.n_agents
+        obs = np.zeros((na, self.obs_dim), np.float32)
+        m = None if env_mask is None else np.ascontiguousarray(env_mask, np.uint8)
+        self._check(self.lib.md_reset_host(self.h, m.ctypes.data_as(C.c_void_p) if m is not None else None,
+                                           obs.ctypes.data_as(C.c_void_p)))
+        return obs
+
+    # ------------------------------------------------------------------ isolated stages
+    def lidar(self):
+        t = self.torch
+        frac = t.zeros((self.n_agents, self.cfg.n_lasers), dtype=t.float32, device=self.tdev)
+        hit = t.zeros((self.n_agents, self.cfg.n_lasers), dtype=t.int32, device=self.tdev)
+        self._check(self.lib.md_lidar(self.h, self._ptr(frac), self._ptr(hit), self._stream()))
+        return frac, hit
+
+    def dynamics(self, act3, n_sub):
+        self._check(self.lib.md_dynamics(self.h, self._ptr(act3), int(n_sub), self._stream()))
+
+    def after_step(self):
+        self._check(self.lib.md_after_step(self.h, self._stream()))
+
+    def idm(self):
+        t = self.torch
+        out = t.zeros((self.cfg.n_envs * self.cfg.slots_per_env, 2), dtype=t.float32, device=self.tdev)
+        self._check(self.lib.md_idm(self.h, self._ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ state snapshots
+    def get_state(self, name):
+        ref = self._host[name]
+        out = np.empty_like(ref)
+        self.torch.cuda.synchronize(self.tdev)
+        self._check(self.lib.md_get_state(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def set_state(self, name, value):
+        v = np.ascontiguousarray(value, self._host[name].dtype)
+        assert v.shape == self._host[name].shape, (v.shape, self._host[name].shape)
+        self.torch.cuda.synchronize(self.tdev)
+        self._check(self.lib.md_set_state(self.h, name.encode(), v.ctypes.data_as(C.c_void_p), v.nbytes))
+
+    def snapshot(self):
+        self._check(self.lib.md_snapshot(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.md_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.md_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,81 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on identical inputs, and against the
+golden traces of the reference.  Index / flag outputs bit-exact, floats within the north-star tolerances:
+lidar fractions 1e-4 relative, poses 1e-2 m / 1e-3 rad over 100 steps."""
+import numpy as np
+import pytest
+
+from tests.golden_util import golden_world, list_golden, load_golden
+
+pytestmark = pytest.mark.gpu
+
+STATE_FLAG_MASK = 0x3ff
+
+
+def _make(tag, replicas):
+    import torch
+    from metadrive_ped_b200.sim import BatchedSim
+    from oracle.oracle import OracleSim
+    g = load_golden(tag)
+    arrays, cfg, geo = golden_world(g, replicas=replicas)
+    return g, cfg, BatchedSim(arrays, cfg), OracleSim(arrays, cfg), torch
+
+
+@pytest.mark.parametrize("tag", list_golden())
+def test_step_matches_oracle_and_golden(tag, oracle_lib):
+    g, cfg, sim, orc, torch = _make(tag, replicas=3)
+    n = g["veh_f"].shape[1]
+    S = cfg.slots_per_env
+    obs_g = sim.reset().cpu().numpy()
+    obs_o = orc.reset_observe().copy()
+    np.testing.assert_allclose(obs_g, obs_o, atol=1e-5, rtol=0)
+    np.testing.assert_allclose(obs_g[0], g["obs"][0], atol=2e-4, rtol=0)
+    T = len(g["reward"])
+    for t in range(T):
+        a = np.tile(g["actions"][t].astype(np.float32), (cfg.n_envs, 1))
+        sim.step(torch.from_numpy(a).cuda())
+        orc.step(a)
+        vi_g, vi_o = sim.get_state("veh_i"), orc.a["veh_i"]
+        vs_g, vs_o = sim.get_state("veh_s"), orc.a["veh_s"]
+        # integer state: bit-exact against the oracle
+        np.testing.assert_array_equal(vi_g, vi_o, err_msg="veh_i at step %d" % t)
+        np.testing.assert_array_equal(sim.info_flags.cpu().numpy(), orc.info_flags)
+        np.testing.assert_array_equal(sim.terminated.cpu().numpy(), orc.term)
+        np.testing.assert_array_equal(sim.truncated.cpu().numpy(), orc.trunc)
+        # poses: 1e-2 m / 1e-3 rad is the bar; the two float32 paths stay far inside it
+        np.testing.assert_allclose(vs_g[:, 0:3], vs_o[:, 0:3], atol=2e-3, rtol=0)
+        np.testing.assert_allclose(vs_g[:, 3:7], vs_o[:, 3:7], atol=5e-4, rtol=0)
+        np.testing.assert_allclose(sim.reward.cpu().numpy(), orc.reward, atol=1e-4, rtol=0)
+        np.testing.assert_allclose(sim.cost.cpu().numpy(), orc.cost, atol=0, rtol=0)
+        og = sim.obs.cpu().numpy()
+        np.testing.assert_allclose(og[:, :19], orc.obs[:, :19], atol=2e-4, rtol=0)
+        np.testing.assert_allclose(og[:, 19:], orc.obs[:, 19:], atol=2e-4, rtol=1e-4)
+        # against the reference's own trace (ego): reward, done, observation
+        assert abs(float(sim.reward[0]) - g["reward"][t]) < 2e-3
+        assert bool(sim.terminated[0]) == bool(g["terminated"][t])
+        np.testing.assert_allclose(og[0, :19], g["obs"][t + 1][:19], atol=2e-3, rtol=0)
+    sim.close()
+
+
+@pytest.mark.parametrize("tag", ["cfg2_pg3_seed11_dense", "cfg2_SCO_nolimit", "cfg4_safe_seed5"])
+def test_lidar_kernel_bit_exact_hits(tag, oracle_lib):
+    """md_lidar in isolation on perturbed poses: hit ids bit-exact, fractions 1e-4 relative."""
+    g, cfg, sim, orc, torch = _make(tag, replicas=16)
+    rng = np.random.RandomState(1)
+    vs = orc.a["veh_s"].copy()
+    S = cfg.slots_per_env
+    # scatter every env's ego over the traffic, with random headings and small tilts
+    for e in range(cfg.n_envs):
+        k = rng.randint(1, max(2, g["veh_f"].shape[1]))
+        ego, other = e * S, e * S + k
+        vs[ego, 0:2] = vs[other, 0:2] + rng.uniform(-15, 15, 2)
+        ang = rng.uniform(-np.pi, np.pi)
+        q = np.array([np.cos(ang / 2), rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01), np.sin(ang / 2)])
+        vs[ego, 3:7] = q / np.linalg.norm(q)
+    orc.a["veh_s"][:] = vs
+    sim.set_state("veh_s", vs)
+    frac_o, hit_o = orc.lidar()
+    frac_g, hit_g = sim.lidar()
+    np.testing.assert_array_equal(hit_g.cpu().numpy(), hit_o)
+    np.testing.assert_allclose(frac_g.cpu().numpy(), frac_o, rtol=1e-4, atol=1e-6)
+    assert (hit_o >= 0).sum() > 50, "test scene must actually hit things"
+    sim.close()
