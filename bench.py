@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the batched MetaDrive step with 240-beam lidar observations (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (for N>1 launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU arm, rank 0 only
+
+Workload (configs[1] of BASELINE.json): `MetaDriveEnv(map=3, traffic_density=0.1, num_scenarios=1000)` — 3-block PG
+maps with IDM traffic, 8192 environments per GPU cycling through the 1000 reference scenarios of the shipped
+library, reference profiling protocol (examples/profile_metadrive.py:16-29): action [0, 1], finished envs reset
+in place (on device).  A step = one env.step of every env: before_step (actuation, trigger, IDM), 5 physics
+sub-steps with contacts, after_step, reward/cost/done, 259-float observation, plus the auto-reset of finished envs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 8192
+LIBRARY = "pg3_density0.1.npz"
+# SURVEY.md 8(d) algorithmic bytes per unit of work
+B_EGO = 1684.0
+B_TRAFFIC = 560.0
+B_LIDAR_SHARE = 256.0 + 960.0  # neighbour footprints read + the 240 lidar floats written (k_lidar's part of B_EGO)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=3)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_world(n_envs, rank):
+    from metadrive_ped_b200.library import ScenarioLibrary
+    lib = ScenarioLibrary(LIBRARY)
+    idx = [(rank * n_envs + e) % len(lib) for e in range(n_envs)]
+    arrays, cfg = lib.build_world(idx, slots_per_env=None)
+    return lib, arrays, cfg
+
+
+def workload_name():
+    return "MetaDriveEnv PG 3-block maps, IDM traffic density 0.1, 1000 reference scenarios, 240-beam lidar"
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle port of the reference's path on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle.oracle import OracleSim
+    sample = 1024
+    lib, arrays, cfg = build_world(sample, 0)
+    orc = OracleSim(arrays, cfg)
+    orc.reset_observe()
+    a = np.tile(np.array([0.0, 1.0], np.float32), (sample, 1))
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        orc.step(a)
+        orc.reset_envs(orc.term | orc.trunc)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.step(a)
+        done = (orc.term | orc.trunc).astype(bool)
+        if done.any():
+            orc.reset_envs(done)
+            # reset observation of the restored envs: the oracle recomputes it with the next step's observe
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "agent_steps_per_sec_240beam_lidar", "value": v, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "envs_per_step": sample, "actions": "[0,1] (profile_metadrive.py)"},
+        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d envs x %d steps, OpenMP over envs" % (sample, args.steps)},
+        "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "lidar_rays_per_sec": v * 240,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--actions", default="profile", choices=["profile", "random"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours) needs a GPU: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from metadrive_ped_b200.sim import BatchedSim
+    E = args.envs_per_gpu
+    t_build = time.time()
+    lib, arrays, cfg = build_world(E, rank)
+    sim = BatchedSim(arrays, cfg, device=local_rank)
+    t_build = time.time() - t_build
+    A = sim.n_agents
+    kind = arrays["veh_i"][:, 0].reshape(E, cfg.slots_per_env)
+    traffic_per_env = float((kind == 2).sum(1).mean())
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    if args.actions == "profile":
+        act_dev = torch.tensor([0.0, 1.0], device=dev).repeat(A, 1).contiguous()
+    else:
+        act_dev = (torch.rand((A, 2), generator=g, device=dev) * 2 - 1).contiguous()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sim.reset()
+    for _ in range(args.warmup):
+        sim.step(act_dev, autoreset=True)
+    barrier()
+
+    # ---------------- timed region: device-resident inputs, CUDA events on the launch stream, L2 flushed between steps
+    K = args.steps
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches0 = sim.launch_count
+    sim.profile_begin(K)
+    done_count = torch.zeros((), dtype=torch.int64, device=dev)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        for k in range(K):
+            flush.zero_()
+            ev0[k].record()
+            sim.step(act_dev, autoreset=True)
+            ev1[k].record()
+            done_count += (sim.terminated | sim.truncated).sum()
+        barrier()
+    step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(K)])
+    k_step_ms, k_lidar_ms = sim.profile_end()
+    launches = sim.launch_count - launches0
+    total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) / 1e3
+    value = world * A * K / total_s
+
+    # ---------------- e2e: the host-buffer call (pinned staging, H2D actions + D2H outputs inside), wall clock
+    a_host = act_dev.cpu().numpy()
+    for _ in range(3):
+        sim.step_host(a_host, autoreset=True)
+    barrier()
+    Ke = max(10, min(K, 100))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        sim.step_host(a_host, autoreset=True)
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * A * Ke / float(e2e_s.item())
+    h2d = A * 2 * 4
+    d2h = A * (sim.obs_dim * 4 + 4 + 4 + 1 + 1 + 4 + 8 * 4)
+
+    # ---------------- episode statistics: the only cross-GPU exchange of this path (one tiny all-reduce)
+    stats = torch.tensor([float(done_count.item()), float(A * K)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        dom = "k_step_vehicles" if k_step_ms.mean() >= k_lidar_ms.mean() else "k_lidar"
+        if dom == "k_lidar":
+            bytes_per_launch = A * B_LIDAR_SHARE
+            dur_ms = float(k_lidar_ms.mean())
+        else:
+            bytes_per_launch = E * ((B_EGO - B_LIDAR_SHARE) + B_TRAFFIC * traffic_per_env)
+            dur_ms = float(k_step_ms.mean())
+        achieved = bytes_per_launch / (dur_ms * 1e-3) / 1e9
+        line = {
+            "metric": "agent_steps_per_sec_240beam_lidar", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+            "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(), "envs_per_gpu": E, "agents_per_env": 1,
+                       "slots_per_env": cfg.slots_per_env, "traffic_per_env_mean": traffic_per_env,
+                       "distinct_scenarios": min(len(lib), E * world), "actions": args.actions,
+                       "autoreset": "on device, inside the timed region", "l2": "flushed between steps (256 MiB memset, untimed)",
+                       "scene_build_s": round(t_build, 1)},
+            "lidar_rays_per_sec": value * cfg.n_lasers,
+            "gpu_launches": int(launches),
+            "kernel_ms": {"k_step_vehicles": float(k_step_ms.mean()), "k_lidar": float(k_lidar_ms.mean()),
+                          "step_total_incl_autoreset": float(step_ms.mean())},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch},
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke},
+            "clocks": clocks.summary(),
+            "episodes_finished_frac": float(stats[0].item() / max(stats[1].item(), 1.0)),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(lib)
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(lib):
+    """The oracle port on the box's host cores over a bounded sample (about 10-20 s of CPU work)."""
+    from oracle.oracle import OracleSim
+    sample = 512
+    arrays, cfg = lib.build_world(list(range(sample)))
+    orc = OracleSim(arrays, cfg)
+    orc.reset_observe()
+    a = np.tile(np.array([0.0, 1.0], np.float32), (sample, 1))
+    t0 = time.perf_counter()
+    orc.step(a)
+    one = max(time.perf_counter() - t0, 1e-4)
+    steps = int(max(5, min(400, 12.0 / one)))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.step(a)
+        done = (orc.term | orc.trunc).astype(bool)
+        if done.any():
+            orc.reset_envs(done)
+    dt = time.perf_counter() - t0
+    return {"value": sample * steps / dt, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "%d envs x %d steps of the same workload, OpenMP over envs" % (sample, steps)}
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,11 @@ int md_get_state(md_sim* sim, const char* name, void* host_dst, size_t bytes);
 int md_set_state(md_sim* sim, const char* name, const void* host_src, size_t bytes);
 /* make the current device state the snapshot md_reset restores */
 int md_snapshot(md_sim* sim);
+/* per-kernel device timing of the next max_steps md_step calls: three cudaEvents per call recorded on the launch
+ * stream (no synchronisation added).  md_profile_end (after the caller synchronised) fills the milliseconds of
+ * k_step_vehicles and k_lidar per recorded step and returns how many were recorded. */
+int md_profile_begin(md_sim* sim, int max_steps);
+int md_profile_end(md_sim* sim, float* step_ms, float* lidar_ms, int cap);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t md_launch_count(const md_sim* sim);
 

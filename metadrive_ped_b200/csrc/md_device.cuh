@@ -128,7 +128,7 @@ __device__ __forceinline__ bool point_in_hull(const float* __restrict__ hull, in
         int j = i + 1 == n ? 0 : i + 1;
         float ax = hull[2 * i], ay = hull[2 * i + 1], bx = hull[2 * j], by = hull[2 * j + 1];
         float c = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
-        if (c < 0.0f) return false;
+        if (c < -1e-3f) return false;  // edge counts as inside; Bullet's hull has a 0.04 m margin
     }
     return true;
 }

@@ -947,6 +947,9 @@ struct md_sim {
     int32_t* d_info_flags;
     int64_t launches;
     bool loaded;
+    // optional per-kernel timing: 3 events per md_step on the launch stream (bench.py's roofline leg)
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_cap, prof_n;
 };
 
 static const char* kNames[21] = {"map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f",
@@ -982,6 +985,8 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     sim->device = device;
     sim->loaded = false;
     sim->launches = 0;
+    sim->prof_cap = 0;
+    sim->prof_n = 0;
     memset(&sim->dev, 0, sizeof(sim->dev));
     *out = sim;
     if (cfg->n_lasers > MAX_LASERS || cfg->slots_per_env > STEP_THREADS || cfg->slots_per_env < 1 ||
@@ -1148,8 +1153,41 @@ extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, fl
     CK(cudaSetDevice(sim->device));
     cudaStream_t st = (cudaStream_t)stream;
     StepOut out = {obs_dev, reward_dev, cost_dev, terminated_dev, truncated_dev, info_flags_dev, info_f_dev};
+    const bool prof = sim->prof_n < sim->prof_cap;
+    if (prof) CK(cudaEventRecord(sim->prof_ev[3 * sim->prof_n], st));
     if (launch_step(sim, MODE_FULL, actions_dev, nullptr, sim->cfg.decision_repeat, nullptr, out, nullptr, st)) return -1;
-    return launch_lidar(sim, obs_dev, OBS_STATE + sim->cfg.n_lasers, OBS_STATE, nullptr, nullptr, st);
+    if (prof) CK(cudaEventRecord(sim->prof_ev[3 * sim->prof_n + 1], st));
+    if (launch_lidar(sim, obs_dev, OBS_STATE + sim->cfg.n_lasers, OBS_STATE, nullptr, nullptr, st)) return -1;
+    if (prof) { CK(cudaEventRecord(sim->prof_ev[3 * sim->prof_n + 2], st)); sim->prof_n++; }
+    return 0;
+}
+
+// per-kernel device timing of the next `max_steps` md_step calls (events on the launch stream, no sync added)
+extern "C" int md_profile_begin(md_sim* sim, int max_steps) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    while ((int)sim->prof_ev.size() < 3 * max_steps) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        sim->prof_ev.push_back(e);
+    }
+    sim->prof_cap = max_steps;
+    sim->prof_n = 0;
+    return 0;
+}
+// after the caller synchronised: ms of k_step_vehicles and k_lidar for each recorded step; returns the count
+extern "C" int md_profile_end(md_sim* sim, float* step_ms, float* lidar_ms, int cap) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    int n = sim->prof_n < cap ? sim->prof_n : cap;
+    for (int i = 0; i < n; i++) {
+        CK(cudaEventSynchronize(sim->prof_ev[3 * i + 2]));
+        CK(cudaEventElapsedTime(&step_ms[i], sim->prof_ev[3 * i], sim->prof_ev[3 * i + 1]));
+        CK(cudaEventElapsedTime(&lidar_ms[i], sim->prof_ev[3 * i + 1], sim->prof_ev[3 * i + 2]));
+    }
+    sim->prof_cap = 0;
+    sim->prof_n = 0;
+    return n;
 }
 
 extern "C" int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, void* stream) {

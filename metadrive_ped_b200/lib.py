@@ -13,7 +13,7 @@ _lib = None
 EXPORTS = [
     "md_abi_version", "md_create", "md_destroy", "md_last_error", "md_load_scene", "md_reset", "md_step",
     "md_autoreset", "md_step_host", "md_reset_host", "md_lidar", "md_dynamics", "md_after_step", "md_idm",
-    "md_get_state", "md_set_state", "md_snapshot", "md_launch_count",
+    "md_get_state", "md_set_state", "md_snapshot", "md_launch_count", "md_profile_begin", "md_profile_end",
 ]
 
 
@@ -62,6 +62,8 @@ def load():
     lib.md_get_state.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.md_set_state.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.md_snapshot.argtypes = [vp]
+    lib.md_profile_begin.argtypes = [vp, ip]
+    lib.md_profile_end.argtypes = [vp, vp, vp, ip]
     lib.md_launch_count.argtypes = [vp]
     lib.md_launch_count.restype = C.c_int64
     for name in EXPORTS:

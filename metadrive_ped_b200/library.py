@@ -1,0 +1,99 @@
+"""Scenario library: maps + reset-time rosters exported once from the reference (oracle/gen_assets.py) and shipped
+as compressed arrays, so that reset() on a box without the reference still produces the reference's scenes.
+
+A library entry i corresponds to `env.reset(seed=seeds[i])` of the reference env the library was generated from
+(envs/base_env.py:502-537): the PG map (component/algorithm/BIG.py) and what the managers spawned
+(manager/traffic_manager.py:211-277, manager/object_manager.py:40-151, manager/agent_manager.py:88-113).
+"""
+import json
+import os
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+from . import scene as sc
+from .abi import make_config
+
+ASSET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+
+def _build_geo(args):
+    lane_f, lane_i, road_i, meta, lane_num = args
+    return sc.build_map_geometry(sc.MapTable(lane_f, lane_i, road_i, meta, lane_num))
+
+
+class ScenarioLibrary:
+    def __init__(self, path):
+        if not os.path.isabs(path) and not os.path.exists(path):
+            path = os.path.join(ASSET_DIR, path)
+        d = np.load(path, allow_pickle=False)
+        self.path = path
+        self.seeds = d["seeds"]
+        self.map_off, self.veh_off, self.obj_off = d["map_off"], d["veh_off"], d["obj_off"]
+        self.meta = d["meta"]
+        self.env_kind = str(d["env"])
+        self.config = json.loads(str(d["config"]))
+        self._a = {k: d[k] for k in ("lane_f", "lane_i", "road_i", "veh_static", "veh_dyn", "routes", "veh_int", "idm",
+                                      "objects")}
+        self._geo = {}
+
+    def __len__(self):
+        return len(self.seeds)
+
+    def index_of_seed(self, seed):
+        idx = np.nonzero(self.seeds == seed)[0]
+        if len(idx) == 0:
+            raise KeyError("scenario seed %d is not in library %s" % (seed, os.path.basename(self.path)))
+        return int(idx[0])
+
+    def _map_args(self, i):
+        lo, nl, ro, nr, lane_num = (int(x) for x in self.map_off[i])
+        return (np.asarray(self._a["lane_f"][lo:lo + nl], np.float64), np.asarray(self._a["lane_i"][lo:lo + nl], np.int32),
+                np.asarray(self._a["road_i"][ro:ro + nr], np.int32), json.loads(str(self.meta[i])), lane_num)
+
+    def geometries(self, indices, workers=None):
+        """MapGeometry for every library index in `indices` (cached; built in parallel)."""
+        todo = [i for i in dict.fromkeys(indices) if i not in self._geo]
+        if todo:
+            workers = workers or min(len(todo), os.cpu_count() or 1)
+            if workers > 1 and len(todo) > 4:
+                with ProcessPoolExecutor(workers) as ex:
+                    for i, g in zip(todo, ex.map(_build_geo, [self._map_args(i) for i in todo], chunksize=8)):
+                        self._geo[i] = g
+            else:
+                for i in todo:
+                    self._geo[i] = _build_geo(self._map_args(i))
+        return [self._geo[i] for i in indices]
+
+    def scenario(self, i, map_id):
+        vo, nv = (int(x) for x in self.veh_off[i])
+        oo, no = (int(x) for x in self.obj_off[i])
+        a = self._a
+        return sc.Scenario(map_id, np.asarray(a["veh_static"][vo:vo + nv], np.float32),
+                           np.asarray(a["veh_dyn"][vo:vo + nv], np.float64), np.asarray(a["routes"][vo:vo + nv], np.int32),
+                           np.asarray(a["veh_int"][vo:vo + nv], np.int32), np.asarray(a["idm"][vo:vo + nv], np.float32),
+                           np.asarray(a["objects"][oo:oo + no], np.float64).reshape(-1, 8), int(self.seeds[i]))
+
+    def max_vehicles(self):
+        return int(self.veh_off[:, 1].max())
+
+    def max_objects(self):
+        return int(self.obj_off[:, 1].max())
+
+    def build_world(self, indices, slots_per_env=None, objs_per_env=None, **cfg_kw):
+        """(arrays, cfg) for one env per entry of `indices` (library indices, repeats allowed)."""
+        indices = [int(i) for i in indices]
+        uniq = list(dict.fromkeys(indices))
+        geos = self.geometries(uniq)
+        map_id = {i: k for k, i in enumerate(uniq)}
+        scen_cache = {i: self.scenario(i, map_id[i]) for i in uniq}
+        scenarios = [scen_cache[i] for i in indices]
+        S = slots_per_env or max(4, -(-max(len(s.veh_static) for s in scenarios) // 4) * 4)
+        O = objs_per_env if objs_per_env is not None else max(len(s.objects) for s in scenarios)
+        arrays = sc.pack(geos, scenarios, S, 1, O)
+        kw = {}
+        if self.env_kind == "safe":  # envs/safe_metadrive_env.py:10-19
+            kw.update(crash_vehicle_done=0, crash_object_done=0)
+        kw.update(cfg_kw)
+        cfg = make_config(len(indices), S, 1, O, **kw)
+        return arrays, cfg

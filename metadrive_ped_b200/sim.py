@@ -134,6 +134,20 @@ class BatchedSim:
     def snapshot(self):
         self._check(self.lib.md_snapshot(self.h))
 
+    def profile_begin(self, max_steps):
+        self._check(self.lib.md_profile_begin(self.h, int(max_steps)))
+        self._prof_cap = int(max_steps)
+
+    def profile_end(self):
+        """(k_step_vehicles ms, k_lidar ms) arrays for the md_step calls since profile_begin (synchronises)."""
+        self.torch.cuda.synchronize(self.tdev)
+        a = np.zeros(self._prof_cap, np.float32)
+        b = np.zeros(self._prof_cap, np.float32)
+        n = self.lib.md_profile_end(self.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), self._prof_cap)
+        if n < 0:
+            self._check(n)
+        return a[:n], b[:n]
+
     @property
     def launch_count(self):
         return int(self.lib.md_launch_count(self.h))

@@ -295,14 +295,17 @@ def ray_zcyl(o, d, c, r, half_h):
     return t0
 
 
+HULL_TOL = 1e-3  # m^2 on the edge cross product (sub-millimetre); Bullet's own hull carries a 0.04 m margin
+
+
 def point_in_convex(poly, p):
-    """poly: (n,2) CCW convex hull vertices."""
+    """poly: (n,2) CCW convex hull vertices. Points on an edge count as inside (see HULL_TOL)."""
     x, y = p
     n = len(poly)
     for i in range(n):
         ax, ay = poly[i]
         bx, by = poly[(i + 1) % n]
-        if (bx - ax) * (y - ay) - (by - ay) * (x - ax) < 0:
+        if (bx - ax) * (y - ay) - (by - ay) * (x - ax) < -HULL_TOL:
             return False
     return True
 
