@@ -1,0 +1,7 @@
+"""metadrive_ped_b200 — a B200-native batched MetaDrive step behind the reference's Gymnasium surface.
+
+Only the step path lives here (include/mdstep.h is the boundary): hand-written sm_100a kernels in csrc/, the ctypes
+binding (lib, sim), host-side scene tables (scene, library) and the drop-in env classes (envs)."""
+from .envs import BatchedMetaDriveEnv, MetaDriveEnv, SafeMetaDriveEnv  # noqa: F401
+
+__version__ = "0.1.0"

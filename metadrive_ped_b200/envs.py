@@ -1,0 +1,269 @@
+"""Gymnasium-surface drop-ins for the step path: MetaDriveEnv / SafeMetaDriveEnv (single env, reference return
+shapes and info keys) and BatchedMetaDriveEnv (E envs per call, tensors in / tensors out).
+
+Surface mirrored (paths relative to /root/reference/metadrive):
+  Env(config)                         envs/base_env.py:278-313     unknown key -> KeyError (utils/config.py:136-147)
+  reset(seed) -> (obs, info)          envs/base_env.py:502-537     seed outside [start_seed, start_seed+num_scenarios) -> AssertionError (:886-891)
+  step(action) -> (obs, r, term, trunc, info)   envs/base_env.py:426-431, 586-623
+  observation_space / action_space    obs/state_obs.py:172-183; policy/env_input_policy.py:50-68
+  info keys                           component/vehicle/base_vehicle.py:243-252; envs/metadrive_env.py:132-152, 204, 269;
+                                      envs/base_env.py:614-616; envs/safe_metadrive_env.py:31-35
+Scenes come from the shipped scenario library (maps + reset-time rosters exported from the reference); a config the
+library does not cover raises, it is never silently approximated.  Rendering / image observation / manual control
+keys raise NotImplementedError.
+"""
+import numpy as np
+
+from .abi import TRAFFIC_MODES
+from .library import ScenarioLibrary
+
+DEFAULT_AGENT = "default_agent"
+
+# the keys of BASE_DEFAULT_CONFIG + METADRIVE_DEFAULT_CONFIG that touch the step path, with the reference defaults
+# (envs/base_env.py:32-266, envs/metadrive_env.py:16-89)
+STEP_DEFAULTS = dict(
+    start_seed=0, num_scenarios=1, map=3, traffic_density=0.1, traffic_mode="trigger", need_inverse_traffic=False,
+    random_traffic=False, accident_prob=0.0, static_traffic_object=True, random_spawn_lane_index=True, horizon=None,
+    truncate_as_terminate=False, decision_repeat=5, physics_world_step_size=2e-2, discrete_action=False,
+    success_reward=10.0, out_of_road_penalty=5.0, crash_vehicle_penalty=5.0, crash_object_penalty=5.0,
+    driving_reward=1.0, speed_reward=0.1, use_lateral_reward=False, crash_vehicle_cost=1.0, crash_object_cost=1.0,
+    out_of_road_cost=1.0, out_of_route_done=False, on_continuous_line_done=True, crash_vehicle_done=True,
+    crash_object_done=True, crash_human_done=True, cost_to_reward=False, enable_idm_lane_change=True,
+    use_render=False, image_observation=False, manual_control=False, log_level=20, random_agent_model=False,
+    vehicle_config=dict(lidar=dict(num_lasers=240, distance=50, num_others=0, gaussian_noise=0.0, dropout_prob=0.0,
+                                   add_others_navi=False),
+                        side_detector=dict(num_lasers=0, distance=50), lane_line_detector=dict(num_lasers=0, distance=20),
+                        enable_reverse=False, vehicle_model="default"),
+    # extension of this build: which device hosts the simulation
+    device=0,
+)
+UNSUPPORTED_TRUE = ("use_render", "image_observation", "manual_control", "discrete_action", "random_agent_model",
+                    "need_inverse_traffic", "random_traffic")
+
+
+class Box:
+    """Minimal gymnasium.spaces.Box stand-in used when gymnasium is not installed (same fields / contains)."""
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low = np.full(shape, low, dtype)
+        self.high = np.full(shape, high, dtype)
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low)) and bool(np.all(x <= self.high))
+
+    __contains__ = contains
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+
+def _box(low, high, shape):
+    try:
+        import gymnasium
+        return gymnasium.spaces.Box(low, high, shape=shape, dtype=np.float32)
+    except Exception:
+        return Box(low, high, shape)
+
+
+def _merge(default, user, path=""):
+    out = dict(default)
+    for k, v in (user or {}).items():
+        if k not in default:
+            raise KeyError("'{}' does not exist in existing config. Please use config.update(...) to update the "
+                           "config. Existing keys: {}.".format(path + k, sorted(default.keys())))
+        out[k] = _merge(default[k], v, path + k + ".") if isinstance(default[k], dict) and isinstance(v, dict) else v
+    return out
+
+
+class _Agent:
+    """Read-only view of the ego for the attributes the reference's tests poke at (env.agent.position, ...)."""
+    def __init__(self, env):
+        self._env = env
+
+    def _row(self, name):
+        return self._env._sim.get_state(name)[0]
+
+    @property
+    def position(self):
+        return self._row("veh_s")[0:2].astype(np.float64)
+
+    @property
+    def heading_theta(self):
+        w, x, y, z = self._row("veh_s")[3:7].astype(np.float64)
+        fx, fy = 2 * (x * y - w * z), 1 - 2 * (x * x + z * z)
+        return float(np.arctan2(fy, fx))
+
+    @property
+    def speed_km_h(self):
+        v = self._row("veh_s")[7:9].astype(np.float64)
+        return float(np.hypot(*v) * 3.6)
+
+    def _flag(self, bit):
+        return bool(int(self._row("veh_i")[8]) & bit)
+
+    crash_vehicle = property(lambda s: s._flag(0x1))
+    crash_object = property(lambda s: s._flag(0x2))
+    crash_building = property(lambda s: s._flag(0x4))
+    crash_human = property(lambda s: s._flag(0x8))
+    crash_sidewalk = property(lambda s: s._flag(0x10))
+    on_white_continuous_line = property(lambda s: s._flag(0x20))
+    on_yellow_continuous_line = property(lambda s: s._flag(0x40))
+    on_broken_line = property(lambda s: s._flag(0x80))
+    on_lane = property(lambda s: s._flag(0x100))
+
+
+class MetaDriveEnv:
+    LIBRARY = "pg3_density0.1.npz"
+    EXTRA_DEFAULTS = {}
+
+    @classmethod
+    def default_config(cls):
+        d = dict(STEP_DEFAULTS)
+        d.update(cls.EXTRA_DEFAULTS)
+        return d
+
+    def __init__(self, config=None):
+        self.config = _merge(self.default_config(), config)
+        for k in UNSUPPORTED_TRUE:
+            if self.config[k]:
+                raise NotImplementedError("config['%s'] is outside the step path this build covers" % k)
+        lid = self.config["vehicle_config"]["lidar"]
+        if lid["num_others"] != 0 or lid["gaussian_noise"] != 0 or lid["dropout_prob"] != 0:
+            raise NotImplementedError("lidar num_others / noise are not covered yet")
+        self.start_seed = self.start_index = self.config["start_seed"]
+        self.num_scenarios = self.env_num = self.config["num_scenarios"]
+        self._lib = None
+        self._sims = {}
+        self._sim = None
+        self.current_seed = None
+        self.agent = _Agent(self)
+        self.episode_cost = 0.0
+        n = lid["num_lasers"]
+        self.observation_space = _box(-0.0, 1.0, (19 + n, ))
+        self.action_space = _box(-1.0, 1.0, (2, ))
+
+    # -- scenes
+    def _library(self):
+        if self._lib is None:
+            lib = ScenarioLibrary(self.LIBRARY)
+            lc = lib.config
+            want = dict(map=self.config["map"], traffic_density=self.config["traffic_density"])
+            have = dict(map=lc.get("map"), traffic_density=lc.get("traffic_density", self.default_config()["traffic_density"]))
+            if want != have or self.config["traffic_mode"] != "trigger":
+                raise NotImplementedError(
+                    "no shipped scenario library for %s (have %s); generate one with oracle/gen_assets.py" % (want, have))
+            self._lib = lib
+        return self._lib
+
+    def _cfg_kw(self):
+        c = self.config
+        return dict(
+            n_lasers=c["vehicle_config"]["lidar"]["num_lasers"], lidar_dist=float(c["vehicle_config"]["lidar"]["distance"]),
+            horizon=int(c["horizon"] or 0), decision_repeat=c["decision_repeat"], dt=c["physics_world_step_size"],
+            traffic_mode=TRAFFIC_MODES[c["traffic_mode"]], success_reward=c["success_reward"],
+            out_of_road_penalty=c["out_of_road_penalty"], crash_vehicle_penalty=c["crash_vehicle_penalty"],
+            crash_object_penalty=c["crash_object_penalty"], driving_reward=c["driving_reward"], speed_reward=c["speed_reward"],
+            crash_vehicle_cost=c["crash_vehicle_cost"], crash_object_cost=c["crash_object_cost"],
+            out_of_road_cost=c["out_of_road_cost"], use_lateral_reward=int(c["use_lateral_reward"]),
+            out_of_route_done=int(c["out_of_route_done"]), on_continuous_line_done=int(c["on_continuous_line_done"]),
+            crash_vehicle_done=int(c["crash_vehicle_done"]), crash_object_done=int(c["crash_object_done"]),
+            crash_human_done=int(c["crash_human_done"]), truncate_as_terminate=int(c["truncate_as_terminate"]),
+            enable_idm_lane_change=int(c["enable_idm_lane_change"]),
+        )
+
+    # -- gym surface
+    def reset(self, seed=None):
+        from .sim import BatchedSim
+        if seed is None:
+            seed = self.start_seed if self.current_seed is None else \
+                self.start_seed + (self.current_seed + 1 - self.start_seed) % self.num_scenarios
+        assert self.start_seed <= seed < self.start_seed + self.num_scenarios, \
+            "scenario_index (seed) should be in [{}:{})".format(self.start_seed, self.start_seed + self.num_scenarios)
+        lib = self._library()
+        if seed not in self._sims:
+            arrays, cfg = lib.build_world([lib.index_of_seed(seed)], **self._cfg_kw())
+            self._sims[seed] = BatchedSim(arrays, cfg, device=self.config["device"])
+        self._sim = self._sims[seed]
+        self.current_seed = seed
+        self.episode_cost = 0.0
+        obs = self._sim.reset_host()[0].copy()
+        return obs, self._info(None)
+
+    def step(self, action):
+        assert self._sim is not None, "call reset() first"
+        a = np.asarray(action, np.float32).reshape(1, 2)
+        obs, rew, cost, term, trunc, flags, info_f = self._sim.step_host(a, autoreset=False)
+        self.episode_cost += float(cost[0])
+        info = self._info((a[0], float(cost[0]), int(flags[0]), info_f[0]))
+        r = float(rew[0])
+        if self.config["cost_to_reward"]:
+            r -= float(cost[0])
+        return obs[0].copy(), r, bool(term[0]), bool(trunc[0]), info
+
+    def _info(self, step):
+        if step is None:
+            a, cost, flags, f = np.zeros(2, np.float32), 0.0, 0x100, np.zeros(8, np.float32)
+        else:
+            a, cost, flags, f = step
+        crash = bool(flags & 0x1f)
+        info = {
+            "velocity": float(f[0]), "steering": float(f[1]), "acceleration": float(f[2]), "step_energy": float(f[3]),
+            "episode_energy": float(f[4]), "policy": "EnvInputPolicy", "overtake_vehicle_num": 0,
+            "action": (float(a[0]), float(a[1])), "raw_action": (float(a[0]), float(a[1])),
+            "crash_vehicle": bool(flags & 0x1), "crash_object": bool(flags & 0x2), "crash_building": bool(flags & 0x4),
+            "crash_human": bool(flags & 0x8), "crash_sidewalk": bool(flags & 0x10), "out_of_road": bool(flags & 0x400),
+            "arrive_dest": bool(flags & 0x800), "max_step": bool(flags & 0x1000), "env_seed": self.current_seed,
+            "crash": crash, "cost": cost, "step_reward": float(f[5]), "episode_reward": float(f[6]),
+            "episode_length": int(f[7]),
+        }
+        return info
+
+    def close(self):
+        for s in self._sims.values():
+            s.close()
+        self._sims = {}
+        self._sim = None
+
+    @property
+    def agents(self):
+        return {DEFAULT_AGENT: self.agent}
+
+
+class SafeMetaDriveEnv(MetaDriveEnv):
+    """envs/safe_metadrive_env.py:7-35"""
+    LIBRARY = "safe_pg3.npz"
+    EXTRA_DEFAULTS = dict(num_scenarios=100, accident_prob=0.8, traffic_density=0.05, crash_vehicle_done=False,
+                          crash_object_done=False, cost_to_reward=False)
+
+    def _info(self, step):
+        info = super()._info(step)
+        info["total_cost"] = self.episode_cost
+        return info
+
+
+class BatchedMetaDriveEnv:
+    """E independent MetaDriveEnv instances stepped per call, device tensors in and out (the fast path the Gym dict
+    surface cannot offer at 10^6+ steps/s).  Finished envs reset in place on device."""
+    def __init__(self, num_envs, config=None, env_cls=MetaDriveEnv, rank=0):
+        from .shard import shard_scenarios
+        from .sim import BatchedSim
+        proto = env_cls(config)
+        lib = proto._library()
+        first = lib.index_of_seed(proto.start_seed)
+        n = min(proto.num_scenarios, len(lib) - first)
+        idx = [first + i for i in shard_scenarios(n, num_envs, rank)]
+        arrays, cfg = lib.build_world(idx, **proto._cfg_kw())
+        self.sim = BatchedSim(arrays, cfg, device=proto.config["device"])
+        self.num_envs = num_envs
+        self.observation_space, self.action_space = proto.observation_space, proto.action_space
+
+    def reset(self):
+        return self.sim.reset()
+
+    def step(self, actions):
+        obs, r, c, te, tr = self.sim.step(actions, autoreset=True)
+        return obs, r, te, tr, dict(cost=c, flags=self.sim.info_flags, scalars=self.sim.info_f)
+
+    def close(self):
+        self.sim.close()
