@@ -68,6 +68,9 @@
 #define MD_GRID_NY 11
 #define MD_ITEM_OFF 12  /* offset into grid_items */
 #define MD_MAX_LANE_NUM 13 /* lane_num of the map config (navigation normalisation) */
+#define MD_LGRID_OFF 14    /* offset into lgrid_start: same cells as the static grid, items = lane ids whose hull AABB
+                              touches the cell (broad phase of the lane localisation) */
+#define MD_LITEM_OFF 15
 /* map_descf [M, 4] float: grid origin x, y, cell size, spare */
 #define MAPDF 4
 
@@ -229,6 +232,10 @@ typedef struct MdArrays {
     float* veh_idm;           /* [NV, VEH_IDM] */
     float* veh_navi;          /* [NV, NAVI_DIM] */
     float* obj_f;             /* [NO, OBJ_F] */
+    /* derived acceleration tables (the CPU oracle ignores them and scans instead) */
+    const int* lgrid_start;   /* per map: nx*ny+1 */
+    const int* lgrid_items;   /* lane ids local to the map */
+    const int* veh_rroad;     /* [NV, ROUTE_MAX]: road id of route segment k = (route[k] -> route[k+1]), -1 padded */
 } MdArrays;
 
 #endif

@@ -37,7 +37,7 @@ const char* md_last_error(const md_sim* sim);
 /* scene upload: replaces PGMap/BaseBlock.create_in_world + manager.reset() spawning bodies into the Bullet worlds
  * (component/pgblock/pg_block.py:248-256, component/block/base_block.py:431-519, manager/traffic_manager.py:51-72,
  * manager/object_manager.py:40-91).  `host` holds HOST pointers in the md_layout.h layouts; `rows[i]` is the row
- * count of the i-th array in MdArrays field order.  The library copies everything and keeps a device snapshot of the
+ * count of the i-th array in MdArrays field order (24 arrays).  The library copies everything and keeps a device snapshot of the
  * mutable arrays as the reset state.  Caller keeps ownership of the host buffers. */
 int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* rows);
 
@@ -84,11 +84,11 @@ int md_get_state(md_sim* sim, const char* name, void* host_dst, size_t bytes);
 int md_set_state(md_sim* sim, const char* name, const void* host_src, size_t bytes);
 /* make the current device state the snapshot md_reset restores */
 int md_snapshot(md_sim* sim);
-/* per-kernel device timing of the next max_steps md_step calls: three cudaEvents per call recorded on the launch
- * stream (no synchronisation added).  md_profile_end (after the caller synchronised) fills the milliseconds of
- * k_step_vehicles and k_lidar per recorded step and returns how many were recorded. */
+/* per-kernel device timing of the next max_steps md_step calls: five cudaEvents per call recorded on the launch
+ * stream (no synchronisation added).  md_profile_end (after the caller synchronised) fills ms[4*i + k] with the
+ * milliseconds of kernel k (0 k_pre, 1 k_dyn, 2 k_post, 3 k_lidar) of recorded step i and returns how many steps. */
 int md_profile_begin(md_sim* sim, int max_steps);
-int md_profile_end(md_sim* sim, float* step_ms, float* lidar_ms, int cap);
+int md_profile_end(md_sim* sim, float* ms, int cap);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t md_launch_count(const md_sim* sim);
 

@@ -55,7 +55,15 @@ __device__ __forceinline__ F3 tmul(const M3& r, F3 a) {
 __device__ __forceinline__ float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
 // utils/math.py:29-42
 __device__ __forceinline__ float wrap_to_pi(float x) {
-    float a = fmodf(x, MD_TWO_PI);
+    float a;
+    if (fabsf(x) <= 2.0f * MD_TWO_PI) {
+        // |x| <= 4*pi: the conditional +-2*pi below are exact float operations (Sterbenz), hence identical to fmodf
+        a = x;
+        if (a >= MD_TWO_PI) a -= MD_TWO_PI;
+        if (a <= -MD_TWO_PI) a += MD_TWO_PI;
+    } else {
+        a = fmodf(x, MD_TWO_PI);
+    }
     if (a < 0.0f) a += MD_TWO_PI;
     if (a > MD_PI) a -= MD_TWO_PI;
     return a;
@@ -131,6 +139,28 @@ __device__ __forceinline__ bool point_in_hull(const float* __restrict__ hull, in
         if (c < -1e-3f) return false;  // edge counts as inside; Bullet's hull has a 0.04 m margin
     }
     return true;
+}
+
+// Conservative shortcuts around point_in_hull, given the point's lane coordinates: +1 certainly inside, -1 certainly
+// outside, 0 undecided (run the exact edge loop).  Both shortcuts are implied by the exact test with a >= 1 cm margin
+// (float error and the 1e-3 edge tolerance are orders of magnitude smaller), so results stay bit-identical.
+__device__ __forceinline__ int hull_shortcut(const float* __restrict__ L, float px, float py, float lon, float lat) {
+    const float hw = 0.5f * L[LF_WIDTH];
+    if (L[LF_TYPE] == 0.0f) {
+        const float lmax = L[LF_HULL_LONG];
+        if (lon >= 0.02f && lon <= lmax - 0.02f && fabsf(lat) <= hw - 0.02f) return 1;
+        if (lon < -0.02f || lon > lmax + 0.02f || fabsf(lat) > hw + 0.02f) return -1;
+        return 0;
+    }
+    // arc strip: the hull's outer boundary are the chords of the 1 m samples (at most 1.3 cm inside the true arc for
+    // R >= 10 m); its corners reach sqrt((R + w/2)^2 + 1) because of the 1 m tangent extensions at both ends
+    const float r = L[LF_P0 + 2];
+    const float ro = r + hw;
+    const float sag = ro / (8.0f * r * r) * 1.25f + 0.02f;  // chord sagitta of the outer 1 m samples, with slack
+    if (lon >= 0.02f && lon <= L[LF_LENGTH] - 0.02f && fabsf(lat) <= hw - sag) return 1;
+    const float ddx = px - L[LF_P0 + 0], ddy = py - L[LF_P0 + 1];
+    if (ddx * ddx + ddy * ddy > ro * ro + 1.0f + 0.5f * ro) return -1;  // >= 25 cm beyond the farthest hull corner
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ overlaps
@@ -449,7 +479,7 @@ __device__ __forceinline__ void latch_before_step(const float* S, float* C, int*
 // ------------------------------------------------------------------------------------------------ map views
 struct MapView {
     const float* lane_f; const int* lane_i; const float* lane_bb; const int* road_i; const float* hull;
-    const float* lines; const float* quads; const int* gs; const int* gi;
+    const float* lines; const float* quads; const int* gs; const int* gi; const int* lgs; const int* lgi;
     int n_lanes, n_roads, n_lines, nx, ny;
     float gx0, gy0, cell;
 };
@@ -466,6 +496,8 @@ __device__ __forceinline__ MapView map_view(const MdArrays& A, int map) {
     m.quads = A.quad_f + (size_t)d[MD_QUAD_OFF] * QUAD_F;
     m.gs = A.grid_start + d[MD_GRID_OFF];
     m.gi = A.grid_items + d[MD_ITEM_OFF];
+    m.lgs = A.lgrid_start + d[MD_LGRID_OFF];
+    m.lgi = A.lgrid_items + d[MD_LITEM_OFF];
     m.n_lanes = d[MD_N_LANES]; m.n_roads = d[MD_N_ROADS]; m.n_lines = d[MD_N_LINES];
     m.nx = d[MD_GRID_NX]; m.ny = d[MD_GRID_NY];
     m.gx0 = df[0]; m.gy0 = df[1]; m.cell = df[2];

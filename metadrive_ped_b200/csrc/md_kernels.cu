@@ -138,15 +138,15 @@ __device__ __forceinline__ int hash_randint(uint32_t slot, uint32_t counter, int
 
 // IDMPolicy.act (policy/idm_policy.py:235-402) for one traffic vehicle; S/I/D are this thread's register copies
 __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv, int g, const float* S, int* I, float* D,
-                        const int* __restrict__ route, float& out_a0, float& out_a1) {
+                        const int* __restrict__ rroad, float& out_a0, float& out_a1) {
     float px = S[VS_POS], py = S[VS_POS + 1];
     M3 Rg = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
     float hx, hy;
     heading_vec(Rg, hx, hy);
     float speed_kmh = sqrtf(S[VS_VEL] * S[VS_VEL] + S[VS_VEL + 1] * S[VS_VEL + 1]) * 3.6f;
     int c0 = I[VI_CKPT0], c1 = I[VI_CKPT1];
-    int cur_road = find_road(m, route[c0], route[c0 + 1]);
-    int next_road = c1 != c0 ? find_road(m, route[c1], route[c1 + 1]) : -1;
+    int cur_road = rroad[c0];
+    int next_road = c1 != c0 ? rroad[c1] : -1;
     int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
     int veh_lane = I[VI_LANE];
 #define IN_CUR(l) ((l) >= cur_first && (l) < cur_first + cur_n)
@@ -278,14 +278,15 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
 
 // NodeNetworkNavigation.update_localization (component/navigation_module/node_network_navigation.py:130-304) with
 // ray_localization (utils/pg/utils.py:151-203) answered by AABB -> point-in-convex-hull over the map's lane table
-__device__ void localise(const MapView& m, const float* S, int* I, const int* __restrict__ route, float* navi) {
+__device__ void localise(const MapView& m, const float* S, int* I, const int* __restrict__ route,
+                         const int* __restrict__ rroad, float* navi) {
     float px = S[VS_POS], py = S[VS_POS + 1];
     M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
     float hx, hy;
     heading_vec(R, hx, hy);
     int c0 = I[VI_CKPT0], c1 = I[VI_CKPT1], n_ck = I[VI_ROUTE_LEN];
-    int cur_road = find_road(m, route[c0], route[c0 + 1]);
-    int next_road = c1 != c0 ? find_road(m, route[c1], route[c1 + 1]) : -1;
+    int cur_road = rroad[c0];
+    int next_road = c1 != c0 ? rroad[c1] : -1;
     int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
     int nx_first = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_FIRST] : -1;
     int nx_n = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_N] : 0;
@@ -293,14 +294,24 @@ __device__ void localise(const MapView& m, const float* S, int* I, const int* __
     int best_any = -1, best_cur = -1, best_next = -1;
     float d_any = 1e30f, d_cur = 1e30f, d_next = 1e30f;
     const float4* bb4 = reinterpret_cast<const float4*>(m.lane_bb);
-    for (int l = 0; l < m.n_lanes; l++) {
+    // broad phase: only the lanes binned into the grid cell under the vehicle (ascending lane id, like a full scan)
+    int k0 = 0, k1 = 0;
+    {
+        int cx = (int)floorf((px - m.gx0) / m.cell), cy = (int)floorf((py - m.gy0) / m.cell);
+        if (cx >= 0 && cy >= 0 && cx < m.nx && cy < m.ny) { k0 = m.lgs[cy * m.nx + cx]; k1 = m.lgs[cy * m.nx + cx + 1]; }
+    }
+    for (int kk = k0; kk < k1; kk++) {
+        const int l = m.lgi[kk];
         float4 bb = __ldg(bb4 + l);
         if (px < bb.x || py < bb.y || px > bb.z || py > bb.w) continue;
-        if (!point_in_hull(m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], px, py)) continue;
-        on_lane = true;
         const float* Ll = m.lane_f + l * LANE_F;
         float lon, lat;
         lane_local(Ll, px, py, lon, lat);
+        const int sc = hull_shortcut(Ll, px, py, lon, lat);
+        if (sc < 0) continue;
+        if (sc == 0 &&
+            !point_in_hull(m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], px, py)) continue;
+        on_lane = true;
         float lh = lane_heading_at(Ll, lon);
         float cosang = cosf(lh) * hx + sinf(lh) * hy;
         if (!(cosang > 0.0f)) continue;
@@ -327,8 +338,8 @@ __device__ void localise(const MapView& m, const float* S, int* I, const int* __
                 c0 = idx;
                 c1 = (idx + 1 == n_ck - 1) ? idx : idx + 1;
                 I[VI_CKPT0] = c0; I[VI_CKPT1] = c1;
-                cur_road = find_road(m, route[c0], route[c0 + 1]);
-                next_road = c1 != c0 ? find_road(m, route[c1], route[c1 + 1]) : -1;
+                cur_road = rroad[c0];
+                next_road = c1 != c0 ? rroad[c1] : -1;
                 cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST]; cur_n = m.road_i[cur_road * ROAD_I + RI_N];
                 nx_first = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_FIRST] : -1;
             }
@@ -421,7 +432,7 @@ __device__ __forceinline__ int dynamic_contacts(const Nb* nb, float* obj, int S,
 // reward / cost / done + the 19 state floats of the observation for one agent
 // (envs/metadrive_env.py:128-279, envs/base_env.py:586-623, obs/state_obs.py:64-151)
 __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_step, const float* P, const float* S, float* C,
-                              int* I, const int* __restrict__ route, const float* navi, size_t a, const StepOut& out,
+                              int* I, const int* __restrict__ rroad, const float* navi, size_t a, const StepOut& out,
                               bool write_scalars) {
     float px = S[VS_POS], py = S[VS_POS + 1];
     M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
@@ -430,7 +441,7 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
     float speed_kmh = sqrtf(S[VS_VEL] * S[VS_VEL] + S[VS_VEL + 1] * S[VS_VEL + 1]) * 3.6f;
     int flags = I[VI_FLAGS];
     int c0 = I[VI_CKPT0], n_ck = I[VI_ROUTE_LEN];
-    int cur_road = find_road(m, route[c0], route[c0 + 1]);
+    int cur_road = rroad[c0];
     int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
     int lane = I[VI_LANE];
     float lane_w = m.lane_f[lane * LANE_F + LF_WIDTH];
@@ -450,7 +461,7 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         rew += cfg.driving_reward * (long_now - long_last) * lateral_factor * positive;
         rew += cfg.speed_reward * (speed_kmh / P[VP_MAX_SPEED]) * positive;
         float step_reward = rew;
-        int final_road = find_road(m, route[n_ck - 2], route[n_ck - 1]);
+        int final_road = rroad[n_ck - 2];
         int final_lane = m.road_i[final_road * ROAD_I + RI_FIRST] + m.road_i[final_road * ROAD_I + RI_N] - 1;
         float fl_long, fl_lat;
         lane_local(m.lane_f + final_lane * LANE_F, px, py, fl_long, fl_lat);
@@ -569,210 +580,289 @@ __device__ __forceinline__ void write_body_row(float* row, const float* P, const
     r4[4] = make_float4(S[VS_POS], S[VS_POS + 1], 0.0f, 0.0f);
 }
 
-// ================================================================================================ k_step_vehicles
-// dynamic shared memory: per env of the CTA  Nb[S] | obj rows [O*OBJ_F] | obj_first[O]
-__global__ void __launch_bounds__(STEP_THREADS)
-k_step_vehicles(MdConfig cfg, MdArrays A, int mode, int envs_per_block, const float* __restrict__ actions,
-                const float* __restrict__ ext_act3, int n_sub, float* __restrict__ idm_out, StepOut out,
-                float* __restrict__ body_tab, const uint8_t* __restrict__ env_mask, Snapshot snap) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
-    const int le = threadIdx.x / S, slot = threadIdx.x - le * S;
-    const int env = blockIdx.x * envs_per_block + le;
-    const bool in_range = le < envs_per_block && env < cfg.n_envs;
-    const size_t per_env = sizeof(Nb) * S + sizeof(float) * OBJ_F * O + sizeof(int) * ((O + 3) & ~3);
-    unsigned char* my = smem_raw + per_env * (in_range ? le : 0);
-    Nb* nb = reinterpret_cast<Nb*>(my);
-    float* sobj = reinterpret_cast<float*>(my + sizeof(Nb) * S);
-    int* obj_first = reinterpret_cast<int*>(my + sizeof(Nb) * S + sizeof(float) * OBJ_F * O);
+// ================================================================================================ step kernels
+// Thread mapping shared by k_pre / k_dyn / k_post: a CTA owns EPB consecutive envs; thread t handles vehicle
+// (env_local = t % EPB, slot = t / EPB).  With EPB = 32 a warp is "slot s of 32 different envs": every lane of a
+// warp plays the same role (slot 0 = the agent, the alive traffic is a prefix of the remaining slots), which is
+// what keeps the SIMT lanes converged; warps of empty slots retire immediately.
+// Shared memory per CTA: Nb[EPB*S] (env-major, so an env's records are contiguous) | object rows | COST_ONCE claims.
+struct StepGeom {
+    int S, O, NA, epb, le, slot, env, g;
+    bool work;
+    Nb* nb; float* sobj; int* obj_first;
+};
+__device__ __forceinline__ StepGeom step_geom(const MdConfig& cfg, int epb, unsigned char* smem_raw) {
+    StepGeom G;
+    G.S = cfg.slots_per_env; G.O = cfg.objs_per_env; G.NA = cfg.agents_per_env; G.epb = epb;
+    G.le = threadIdx.x % epb; G.slot = threadIdx.x / epb;
+    G.env = blockIdx.x * epb + G.le;
+    G.work = G.slot < G.S && G.env < cfg.n_envs;
+    G.g = G.env * G.S + G.slot;
+    const int ofs = (G.O + 3) & ~3;
+    Nb* nb_all = reinterpret_cast<Nb*>(smem_raw);
+    float* obj_all = reinterpret_cast<float*>(smem_raw + sizeof(Nb) * (size_t)epb * G.S);
+    int* first_all = reinterpret_cast<int*>(smem_raw + sizeof(Nb) * (size_t)epb * G.S + sizeof(float) * OBJ_F * (size_t)G.O * epb);
+    G.nb = nb_all + (size_t)G.le * G.S;
+    G.sobj = obj_all + (size_t)G.le * G.O * OBJ_F;
+    G.obj_first = first_all + (size_t)G.le * ofs;
+    return G;
+}
+__host__ __device__ inline size_t step_smem_bytes(int S, int O, int epb) {
+    return (sizeof(Nb) * (size_t)S + sizeof(float) * OBJ_F * (size_t)O + sizeof(int) * (size_t)((O + 3) & ~3)) * epb;
+}
+// stage the env's object rows: the threads of one env (its S slots) stride over the O*OBJ_F floats
+__device__ __forceinline__ void stage_objects(const StepGeom& G, const float* __restrict__ obj_f) {
+    if (G.work)
+        for (int k = G.slot; k < G.O * OBJ_F; k += G.S) G.sobj[k] = obj_f[(size_t)G.env * G.O * OBJ_F + k];
+}
 
-    bool masked_off = in_range && env_mask != nullptr && env_mask[env] == 0;
-    const bool work = in_range && !masked_off;
-    const int g = env * S + slot;
-    float P[VEH_P], St[VEH_S], C[VEH_C], D[VEH_IDM], navi[NAVI_DIM];
+// ---- k_pre: engine.before_step (agent actuation, traffic trigger, IDM decisions) ------------------------------
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ actions, float* __restrict__ idm_out,
+      float4* __restrict__ veh_act) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const StepGeom G = step_geom(cfg, epb, smem_raw);
+    const int S = G.S, slot = G.slot, env = G.env, g = G.g;
+    float P[VEH_P], St[VEH_S], C[VEH_C], D[VEH_IDM];
     int I[VEH_I];
-    int env_step = 0, map = 0;
-    const int* route = nullptr;
-    if (work) {
-        if (mode & MODE_RESET) {  // restore the snapshot rows of this slot (env.reset)
-            load16(St, snap.veh_s + (size_t)g * VEH_S);
-            load16(C, snap.veh_c + (size_t)g * VEH_C);
-            load16i(I, snap.veh_i + (size_t)g * VEH_I);
-#pragma unroll
-            for (int k = 0; k < VEH_IDM; k++) D[k] = snap.veh_idm[(size_t)g * VEH_IDM + k];
-#pragma unroll
-            for (int k = 0; k < NAVI_DIM; k++) navi[k] = snap.veh_navi[(size_t)g * NAVI_DIM + k];
-            for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = snap.obj_f[(size_t)env * O * OBJ_F + k];
-            if (slot == 0)
-                for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = snap.env_i[env * ENV_I + k];
-        } else {
-            load16(St, A.veh_s + (size_t)g * VEH_S);
-            load16(C, A.veh_c + (size_t)g * VEH_C);
-            load16i(I, A.veh_i + (size_t)g * VEH_I);
-#pragma unroll
-            for (int k = 0; k < VEH_IDM; k++) D[k] = A.veh_idm[(size_t)g * VEH_IDM + k];
-#pragma unroll
-            for (int k = 0; k < NAVI_DIM; k++) navi[k] = A.veh_navi[(size_t)g * NAVI_DIM + k];
-        }
+    if (G.work) {
         load16(P, A.veh_p + (size_t)g * VEH_P);
-        route = A.veh_route + (size_t)g * ROUTE_MAX;
+        load16(St, A.veh_s + (size_t)g * VEH_S);
+        load16(C, A.veh_c + (size_t)g * VEH_C);
+        load16i(I, A.veh_i + (size_t)g * VEH_I);
+        const float4* d4 = reinterpret_cast<const float4*>(A.veh_idm + (size_t)g * VEH_IDM);
+        float4 d0 = d4[0], d1 = d4[1];
+        D[0] = d0.x; D[1] = d0.y; D[2] = d0.z; D[3] = d0.w; D[4] = d1.x; D[5] = d1.y; D[6] = d1.z; D[7] = d1.w;
+        fill_nb(G.nb[slot], P, St, I);
     }
-    __syncthreads();  // RESET wrote env_i / obj_f through global memory
-    if (work) {
-        map = (mode & MODE_RESET) ? snap.env_i[env * ENV_I + EI_MAP] : A.env_i[env * ENV_I + EI_MAP];
-        env_step = ((mode & MODE_RESET) ? snap.env_i[env * ENV_I + EI_STEP] : A.env_i[env * ENV_I + EI_STEP]) + ((mode & MODE_AGENT_PRE) ? 1 : 0);
-        fill_nb(nb[slot], P, St, I);
-        const float* og = (mode & MODE_RESET) ? snap.obj_f : A.obj_f;
-        for (int k = slot; k < O * OBJ_F; k += S) sobj[k] = og[(size_t)env * O * OBJ_F + k];
-    }
-    MapView m;
-    if (work) m = map_view(A, map);
+    stage_objects(G, A.obj_f);
     Actuation act;
     act.steer_rad = 0.0f; act.engine = 0.0f; act.brake = 2.0f;  // what vehicle.reset() leaves (base_vehicle.py:376)
-    const bool is_agent = work && I[VI_KIND] == 1;
-    const bool is_traffic = work && I[VI_KIND] == 2;
-
-    if (mode & MODE_RESET) {
-        if (work && I[VI_ALIVE] && (is_agent || is_traffic)) latch_before_step(St, C, I);
-    }
-    // ---- agent_manager.before_step (manager/agent_manager.py:164-202)
+    const bool is_agent = G.work && I[VI_KIND] == 1;
+    const bool is_traffic = G.work && I[VI_KIND] == 2;
+    // agent_manager.before_step (manager/agent_manager.py:164-202)
     if ((mode & MODE_AGENT_PRE) && is_agent && I[VI_ACTIVE]) {
         latch_before_step(St, C, I);
-        const float* a = actions + ((size_t)env * NA + slot) * 2;
+        const float* a = actions + ((size_t)env * G.NA + slot) * 2;
         act = actuate(P, St, C, a[0], a[1]);
     }
     __syncthreads();
-    // ---- PGTrafficManager.before_step: trigger (manager/traffic_manager.py:74-88), one thread per env
-    if ((mode & MODE_TRIGGER) && work && slot == 0 && cfg.traffic_mode != 1) {
+    MapView m;
+    if (G.work) m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+    // PGTrafficManager.before_step: trigger (manager/traffic_manager.py:74-88), one thread per env
+    if ((mode & MODE_TRIGGER) && G.work && slot == 0 && cfg.traffic_mode != 1) {
         int nt = A.env_i[env * ENV_I + EI_NEXT_TRIGGER];
         const int n_blocks = A.env_i[env * ENV_I + EI_N_BLOCKS];
-        for (int s = 0; s < NA && nt > 0; s++) {
-            if (!nb[s].active || nb[s].kind != 1) continue;
-            int road = m.lane_i[nb[s].lane * LANE_I + LI_ROAD];
+        for (int s = 0; s < G.NA && nt > 0; s++) {
+            if (!G.nb[s].active || G.nb[s].kind != 1) continue;
+            int road = m.lane_i[G.nb[s].lane * LANE_I + LI_ROAD];
             if (road == A.env_trigger[env * TRIGGER_MAX + nt]) {
                 for (int k = 0; k < S; k++)
-                    if (nb[k].kind == 2 && nb[k].alive && A.veh_i[(size_t)(env * S + k) * VEH_I + VI_TRIGGER] == nt) nb[k].active = 1;
+                    if (G.nb[k].kind == 2 && G.nb[k].alive && A.veh_i[(size_t)(env * S + k) * VEH_I + VI_TRIGGER] == nt) G.nb[k].active = 1;
                 nt = nt + 1 < n_blocks ? nt + 1 : 0;
             }
         }
         A.env_i[env * ENV_I + EI_NEXT_TRIGGER] = nt;
     }
-    if (work && slot == 0 && (mode & MODE_AGENT_PRE)) A.env_i[env * ENV_I + EI_STEP] = env_step;
+    if (G.work && slot == 0 && (mode & MODE_AGENT_PRE)) A.env_i[env * ENV_I + EI_STEP] += 1;
     __syncthreads();
-    if (work) I[VI_ACTIVE] = nb[slot].active;
-    // ---- IDM decisions against the pre-step world (policy/idm_policy.py:235-267)
+    if (G.work) I[VI_ACTIVE] = G.nb[slot].active;
+    // IDM decisions against the pre-step world (policy/idm_policy.py:235-267)
     if ((mode & (MODE_IDM | MODE_IDM_OUT)) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE]) {
         NbrView nv;
-        nv.nb = nb; nv.obj = sobj; nv.S = S; nv.O = O; nv.self = slot; nv.px = St[VS_POS]; nv.py = St[VS_POS + 1];
+        nv.nb = G.nb; nv.obj = G.sobj; nv.S = S; nv.O = G.O; nv.self = slot; nv.px = St[VS_POS]; nv.py = St[VS_POS + 1];
         float a0, a1;
-        idm_act(cfg, m, nv, g, St, I, D, route, a0, a1);
+        idm_act(cfg, m, nv, g, St, I, D, A.veh_rroad + (size_t)g * ROUTE_MAX, a0, a1);
         if (mode & MODE_IDM_OUT) { idm_out[2 * (size_t)g] = a0; idm_out[2 * (size_t)g + 1] = a1; }
         if (mode & MODE_IDM) {
             latch_before_step(St, C, I);
             act = actuate(P, St, C, a0, a1);
         }
     }
-    if ((mode & MODE_EXT_ACT) && work) {
-        act.steer_rad = ext_act3[3 * (size_t)g]; act.engine = ext_act3[3 * (size_t)g + 1]; act.brake = ext_act3[3 * (size_t)g + 2];
-    }
-    // ---- engine.step: n_sub x doPhysics + contact-added callback (engine/base_engine.py:417-445)
-    if (mode & MODE_DYN) {
-        Body B;
-        if (work) {
-            B.pos = f3(St[VS_POS], St[VS_POS + 1], St[VS_POS + 2]);
-            B.q[0] = St[VS_QUAT]; B.q[1] = St[VS_QUAT + 1]; B.q[2] = St[VS_QUAT + 2]; B.q[3] = St[VS_QUAT + 3];
-            B.v = f3(St[VS_VEL], St[VS_VEL + 1], St[VS_VEL + 2]);
-            B.w = f3(St[VS_ANGVEL], St[VS_ANGVEL + 1], St[VS_ANGVEL + 2]);
-        }
-        const bool moves = work && I[VI_ALIVE] && !I[VI_STATIC];
-        for (int rep = 0; rep < n_sub; rep++) {
-            if (moves) {
-                vehicle_substep(P, B, act, cfg.dt);
-                St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y; St[VS_POS + 2] = B.pos.z;
-                St[VS_QUAT] = B.q[0]; St[VS_QUAT + 1] = B.q[1]; St[VS_QUAT + 2] = B.q[2]; St[VS_QUAT + 3] = B.q[3];
-                St[VS_VEL] = B.v.x; St[VS_VEL + 1] = B.v.y; St[VS_VEL + 2] = B.v.z;
-                St[VS_ANGVEL] = B.w.x; St[VS_ANGVEL + 1] = B.w.y; St[VS_ANGVEL + 2] = B.w.z;
-            }
-            if (mode & MODE_CONTACTS) {
-                __syncthreads();  // everyone finished reading the previous footprints
-                if (work) {
-                    nb[slot].r = vehicle_rect(P, St);
-                    nb[slot].x = St[VS_POS]; nb[slot].y = St[VS_POS + 1]; nb[slot].vx = St[VS_VEL]; nb[slot].vy = St[VS_VEL + 1];
-                    for (int k = slot; k < O; k += S) {  // kinematic movers (traffic_participants/pedestrian.py:67-95)
-                        obj_first[k] = 0x7fffffff;
-                        float* Ob = sobj + k * OBJ_F;
-                        if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
-                    }
-                }
-                __syncthreads();
-                if (work && I[VI_ALIVE]) I[VI_FLAGS] |= dynamic_contacts(nb, sobj, S, O, slot, nb[slot].r, true, obj_first, true);
-                __syncthreads();
-                if (work && I[VI_ALIVE]) I[VI_FLAGS] |= dynamic_contacts(nb, sobj, S, O, slot, nb[slot].r, true, obj_first, false);
-                __syncthreads();
-                if (work)
-                    for (int k = slot; k < O; k += S)
-                        if (obj_first[k] != 0x7fffffff) sobj[k * OBJ_F + OB_CRASHED] = 1.0f;
-            }
-        }
-    }
-    // ---- engine.after_step (component/vehicle/base_vehicle.py:234-271)
-    if (mode & (MODE_POST | MODE_RESET)) {
-        __syncthreads();
-        if (work) { nb[slot].r = vehicle_rect(P, St); nb[slot].alive = I[VI_ALIVE]; }
-        __syncthreads();
-        const bool do_post = work && I[VI_ALIVE] && ((mode & MODE_RESET) ? (is_agent || is_traffic) : (I[VI_ACTIVE] != 0));
-        if (do_post) {
-            if (mode & MODE_CLEAR_FLAGS) I[VI_FLAGS] = FL_ON_LANE;
-            localise(m, St, I, route, navi);
-            Rect r = nb[slot].r;
-            int flags = I[VI_FLAGS];
-            state_check_static(m, r, flags);
-            flags |= dynamic_contacts(nb, sobj, S, O, slot, r, false, obj_first, false);
-            I[VI_FLAGS] = flags;
-            int c0 = I[VI_CKPT0];
-            int cur_road = find_road(m, route[c0], route[c0 + 1]);
-            int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
-            float lon, lat;
-            lane_local(m.lane_f + cur_first * LANE_F, St[VS_POS], St[VS_POS + 1], lon, lat);
-            float lane_w = m.lane_f[I[VI_LANE] * LANE_F + LF_WIDTH];
-            float to_left = lat + lane_w / 2.0f;
-            float to_right = lane_w * (float)cur_n - to_left;
-            C[VC_DIST_L] = to_left; C[VC_DIST_R] = to_right;
-            if (to_right < 0.0f || to_left < 0.0f) I[VI_FLAGS] |= FL_OUT_OF_ROUTE;
-            float dx = C[VC_LAST_X] - St[VS_POS], dy = C[VC_LAST_Y] - St[VS_POS + 1];
-            float dist_km = sqrtf(dx * dx + dy * dy) / 1000.0f;
-            float speed_kmh = sqrtf(St[VS_VEL] * St[VS_VEL] + St[VS_VEL + 1] * St[VS_VEL + 1]) * 3.6f;
-            float step_energy = 3.25f * expf(0.01f * speed_kmh) * dist_km / 100.0f * 1000.0f;
-            C[VC_STEP_ENERGY] = step_energy;
-            C[VC_ENERGY] += step_energy;
-            if ((mode & MODE_RESET) && !I[VI_ACTIVE]) I[VI_FLAGS] = FL_ON_LANE;  // reset() ends with _init_step_info
-        }
-        // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111)
-        if ((mode & MODE_REMOVE) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE] && !(I[VI_FLAGS] & FL_ON_LANE)) {
-            I[VI_ALIVE] = 0; I[VI_ACTIVE] = 0;
-        }
-    }
-    // ---- _get_step_return (envs/base_env.py:586-623)
-    if ((mode & (MODE_OUT | MODE_RESET)) && is_agent && I[VI_ACTIVE] && slot < NA) {
-        size_t a = (size_t)env * NA + slot;
-        agent_outputs(cfg, m, env_step, P, St, C, I, route, navi, a, out, (mode & MODE_OUT) != 0);
-    }
-    // ---- write back
-    if (work) {
+    if (G.work) {
+        veh_act[g] = make_float4(act.steer_rad, act.engine, act.brake, 0.0f);
         store16(A.veh_s + (size_t)g * VEH_S, St);
         store16(A.veh_c + (size_t)g * VEH_C, C);
         store16i(A.veh_i + (size_t)g * VEH_I, I);
+        float4* d4 = reinterpret_cast<float4*>(A.veh_idm + (size_t)g * VEH_IDM);
+        d4[0] = make_float4(D[0], D[1], D[2], D[3]);
+        d4[1] = make_float4(D[4], D[5], D[6], D[7]);
+    }
+}
+
+// ---- k_dyn: engine.step = n_sub x doPhysics + contact-added callback (engine/base_engine.py:417-445) --------------
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ veh_act, const float* __restrict__ ext_act3,
+      int n_sub) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const StepGeom G = step_geom(cfg, epb, smem_raw);
+    const int S = G.S, O = G.O, slot = G.slot, env = G.env, g = G.g;
+    float P[VEH_P], St[VEH_S];
+    int alive = 0, is_static = 1, flags = 0;
+    Actuation act;
+    act.steer_rad = 0.0f; act.engine = 0.0f; act.brake = 2.0f;
+    if (G.work) {
+        load16(P, A.veh_p + (size_t)g * VEH_P);
+        load16(St, A.veh_s + (size_t)g * VEH_S);
+        const int* I = A.veh_i + (size_t)g * VEH_I;
+        alive = I[VI_ALIVE]; is_static = I[VI_STATIC]; flags = I[VI_FLAGS];
+        if (mode & MODE_EXT_ACT) {
+            act.steer_rad = ext_act3[3 * (size_t)g]; act.engine = ext_act3[3 * (size_t)g + 1]; act.brake = ext_act3[3 * (size_t)g + 2];
+        } else {
+            float4 a = veh_act[g];
+            act.steer_rad = a.x; act.engine = a.y; act.brake = a.z;
+        }
+        G.nb[slot].alive = alive;
+    }
+    const bool contacts = (mode & MODE_CONTACTS) != 0;
+    if (contacts) stage_objects(G, A.obj_f);
+    Body B;
+    B.pos = f3(St[VS_POS], St[VS_POS + 1], St[VS_POS + 2]);
+    B.q[0] = St[VS_QUAT]; B.q[1] = St[VS_QUAT + 1]; B.q[2] = St[VS_QUAT + 2]; B.q[3] = St[VS_QUAT + 3];
+    B.v = f3(St[VS_VEL], St[VS_VEL + 1], St[VS_VEL + 2]);
+    B.w = f3(St[VS_ANGVEL], St[VS_ANGVEL + 1], St[VS_ANGVEL + 2]);
+    const bool moves = G.work && alive && !is_static;
+    for (int rep = 0; rep < n_sub; rep++) {
+        if (moves) {
+            vehicle_substep(P, B, act, cfg.dt);
+            St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y; St[VS_POS + 2] = B.pos.z;
+            St[VS_QUAT] = B.q[0]; St[VS_QUAT + 1] = B.q[1]; St[VS_QUAT + 2] = B.q[2]; St[VS_QUAT + 3] = B.q[3];
+        }
+        if (contacts) {
+            __syncthreads();  // everyone finished reading the previous footprints
+            if (G.work) {
+                G.nb[slot].r = vehicle_rect(P, St);
+                for (int k = slot; k < O; k += S) {  // kinematic movers (traffic_participants/pedestrian.py:67-95)
+                    G.obj_first[k] = 0x7fffffff;
+                    float* Ob = G.sobj + k * OBJ_F;
+                    if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
+                }
+            }
+            __syncthreads();
+            if (G.work && alive) flags |= dynamic_contacts(G.nb, G.sobj, S, O, slot, G.nb[slot].r, true, G.obj_first, true);
+            if (O > 0) {  // COST_ONCE needs the claims of every vehicle before anyone reads them
+                __syncthreads();
+                if (G.work && alive) flags |= dynamic_contacts(G.nb, G.sobj, 0, O, slot, G.nb[slot].r, true, G.obj_first, false);
+                __syncthreads();
+                if (G.work)
+                    for (int k = slot; k < O; k += S)
+                        if (G.obj_first[k] != 0x7fffffff) G.sobj[k * OBJ_F + OB_CRASHED] = 1.0f;
+            }
+        }
+    }
+    if (G.work) {
+        St[VS_VEL] = B.v.x; St[VS_VEL + 1] = B.v.y; St[VS_VEL + 2] = B.v.z;
+        St[VS_ANGVEL] = B.w.x; St[VS_ANGVEL + 1] = B.w.y; St[VS_ANGVEL + 2] = B.w.z;
+        store16(A.veh_s + (size_t)g * VEH_S, St);
+        A.veh_i[(size_t)g * VEH_I + VI_FLAGS] = flags;
+    }
+    if (contacts && O > 0) {
+        __syncthreads();
+        if (G.work)
+            for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = G.sobj[k];
+    }
+}
+
+// ---- k_post: engine.after_step + _get_step_return (base_vehicle.py:234-271; envs/base_env.py:586-623) -----------
+// MODE_RESET: the reset-time variant (envs/base_env.py:560-584) for the envs selected by env_mask
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restrict__ body_tab,
+       const uint8_t* __restrict__ env_mask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepGeom G = step_geom(cfg, epb, smem_raw);
+    if (G.work && env_mask != nullptr && env_mask[G.env] == 0) G.work = false;
+    const int S = G.S, slot = G.slot, env = G.env, g = G.g;
+    float P[VEH_P], St[VEH_S], C[VEH_C], navi[NAVI_DIM];
+    int I[VEH_I];
+    if (G.work) {
+        load16(P, A.veh_p + (size_t)g * VEH_P);
+        load16(St, A.veh_s + (size_t)g * VEH_S);
+        load16(C, A.veh_c + (size_t)g * VEH_C);
+        load16i(I, A.veh_i + (size_t)g * VEH_I);
 #pragma unroll
-        for (int k = 0; k < VEH_IDM; k++) A.veh_idm[(size_t)g * VEH_IDM + k] = D[k];
+        for (int k = 0; k < NAVI_DIM; k++) navi[k] = A.veh_navi[(size_t)g * NAVI_DIM + k];
+        G.nb[slot].r = vehicle_rect(P, St);
+        G.nb[slot].alive = I[VI_ALIVE];
+    }
+    stage_objects(G, A.obj_f);
+    const bool is_agent = G.work && I[VI_KIND] == 1;
+    const bool is_traffic = G.work && I[VI_KIND] == 2;
+    if ((mode & MODE_RESET) && G.work && I[VI_ALIVE] && (is_agent || is_traffic)) latch_before_step(St, C, I);
+    __syncthreads();
+    MapView m;
+    int env_step = 0;
+    if (G.work) { m = map_view(A, A.env_i[env * ENV_I + EI_MAP]); env_step = A.env_i[env * ENV_I + EI_STEP]; }
+    const int* rroad = A.veh_rroad + (size_t)g * ROUTE_MAX;
+    const bool do_post = G.work && I[VI_ALIVE] && ((mode & MODE_RESET) ? (is_agent || is_traffic) : (I[VI_ACTIVE] != 0));
+    if (do_post) {
+        if (mode & MODE_CLEAR_FLAGS) I[VI_FLAGS] = FL_ON_LANE;
+        localise(m, St, I, A.veh_route + (size_t)g * ROUTE_MAX, rroad, navi);
+        Rect r = G.nb[slot].r;
+        int flags = I[VI_FLAGS];
+        state_check_static(m, r, flags);
+        flags |= dynamic_contacts(G.nb, G.sobj, S, G.O, slot, r, false, G.obj_first, false);
+        I[VI_FLAGS] = flags;
+        int cur_road = rroad[I[VI_CKPT0]];
+        int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+        float lon, lat;
+        lane_local(m.lane_f + cur_first * LANE_F, St[VS_POS], St[VS_POS + 1], lon, lat);
+        float lane_w = m.lane_f[I[VI_LANE] * LANE_F + LF_WIDTH];
+        float to_left = lat + lane_w / 2.0f;
+        float to_right = lane_w * (float)cur_n - to_left;
+        C[VC_DIST_L] = to_left; C[VC_DIST_R] = to_right;
+        if (to_right < 0.0f || to_left < 0.0f) I[VI_FLAGS] |= FL_OUT_OF_ROUTE;
+        float dx = C[VC_LAST_X] - St[VS_POS], dy = C[VC_LAST_Y] - St[VS_POS + 1];
+        float dist_km = sqrtf(dx * dx + dy * dy) / 1000.0f;
+        float speed_kmh = sqrtf(St[VS_VEL] * St[VS_VEL] + St[VS_VEL + 1] * St[VS_VEL + 1]) * 3.6f;
+        float step_energy = 3.25f * expf(0.01f * speed_kmh) * dist_km / 100.0f * 1000.0f;
+        C[VC_STEP_ENERGY] = step_energy;
+        C[VC_ENERGY] += step_energy;
+        if ((mode & MODE_RESET) && !I[VI_ACTIVE]) I[VI_FLAGS] = FL_ON_LANE;  // reset() ends with _init_step_info
+    }
+    // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111)
+    if ((mode & MODE_REMOVE) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE] && !(I[VI_FLAGS] & FL_ON_LANE)) {
+        I[VI_ALIVE] = 0; I[VI_ACTIVE] = 0;
+    }
+    if ((mode & (MODE_OUT | MODE_RESET)) && is_agent && I[VI_ACTIVE] && slot < G.NA) {
+        size_t a = (size_t)env * G.NA + slot;
+        agent_outputs(cfg, m, env_step, P, St, C, I, rroad, navi, a, out, (mode & MODE_OUT) != 0);
+    }
+    if (G.work) {
+        store16(A.veh_c + (size_t)g * VEH_C, C);
+        store16i(A.veh_i + (size_t)g * VEH_I, I);
+        if (do_post) {
 #pragma unroll
-        for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = navi[k];
+            for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = navi[k];
+        }
         write_body_row(body_tab + (size_t)g * BODY_ROW, P, St, I[VI_ALIVE]);
     }
-    if (mode & (MODE_CONTACTS | MODE_RESET)) {
-        __syncthreads();
-        if (work && (mode & MODE_CONTACTS))
-            for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = sobj[k];
-    }
+}
+
+// ---- k_restore: env.reset state restore for the masked envs (snapshot -> live arrays), thread per slot row ------
+__global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t* __restrict__ env_mask) {
+    const int S = cfg.slots_per_env, O = cfg.objs_per_env;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)cfg.n_envs * S) return;
+    const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
+    if (env_mask != nullptr && env_mask[env] == 0) return;
+    const float4* s4 = reinterpret_cast<const float4*>(snap.veh_s + (size_t)g * VEH_S);
+    const float4* c4 = reinterpret_cast<const float4*>(snap.veh_c + (size_t)g * VEH_C);
+    const int4* i4 = reinterpret_cast<const int4*>(snap.veh_i + (size_t)g * VEH_I);
+    float4* ds = reinterpret_cast<float4*>(A.veh_s + (size_t)g * VEH_S);
+    float4* dc = reinterpret_cast<float4*>(A.veh_c + (size_t)g * VEH_C);
+    int4* di = reinterpret_cast<int4*>(A.veh_i + (size_t)g * VEH_I);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { ds[k] = s4[k]; dc[k] = c4[k]; di[k] = i4[k]; }
+    const float4* d4 = reinterpret_cast<const float4*>(snap.veh_idm + (size_t)g * VEH_IDM);
+    float4* dd = reinterpret_cast<float4*>(A.veh_idm + (size_t)g * VEH_IDM);
+    dd[0] = d4[0]; dd[1] = d4[1];
+    for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = snap.veh_navi[(size_t)g * NAVI_DIM + k];
+    for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = snap.obj_f[(size_t)env * O * OBJ_F + k];
+    if (slot == 0)
+        for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = snap.env_i[env * ENV_I + k];
 }
 
 // ================================================================================================ k_lidar
@@ -931,11 +1021,12 @@ struct md_sim {
     int device;
     std::string err;
     MdArrays dev;           // device pointers
-    int64_t rows[21];
-    size_t bytes[21];
+    int64_t rows[24];
+    size_t bytes[24];
     Snapshot snap;
     void* snap_bufs[7];
     float* body_tab;
+    float4* veh_act;        // [NV] steering rad, engine force, brake: k_pre -> k_dyn
     uint8_t* mask;
     cudaStream_t stream;    // own stream for the *_host entry points
     // pinned host staging + device mirrors for the *_host entry points
@@ -952,12 +1043,14 @@ struct md_sim {
     int prof_cap, prof_n;
 };
 
-static const char* kNames[21] = {"map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f",
-                                 "quad_f", "grid_start", "grid_items", "env_i", "env_trigger", "veh_p", "veh_s", "veh_c",
-                                 "veh_i", "veh_route", "veh_idm", "veh_navi", "obj_f"};
-static const int kRowBytes[21] = {MAPD * 4, MAPDF * 4, LANE_F * 4, LANE_I * 4, 16, ROAD_I * 4, 8, LINE_F * 4, QUAD_F * 4, 4, 4,
-                                  ENV_I * 4, TRIGGER_MAX * 4, VEH_P * 4, VEH_S * 4, VEH_C * 4, VEH_I * 4, ROUTE_MAX * 4,
-                                  VEH_IDM * 4, NAVI_DIM * 4, OBJ_F * 4};
+#define N_ARR 24
+static const char* kNames[N_ARR] = {"map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f",
+                                    "quad_f", "grid_start", "grid_items", "env_i", "env_trigger", "veh_p", "veh_s", "veh_c",
+                                    "veh_i", "veh_route", "veh_idm", "veh_navi", "obj_f", "lgrid_start", "lgrid_items",
+                                    "veh_rroad"};
+static const int kRowBytes[N_ARR] = {MAPD * 4, MAPDF * 4, LANE_F * 4, LANE_I * 4, 16, ROAD_I * 4, 8, LINE_F * 4, QUAD_F * 4, 4, 4,
+                                     ENV_I * 4, TRIGGER_MAX * 4, VEH_P * 4, VEH_S * 4, VEH_C * 4, VEH_I * 4, ROUTE_MAX * 4,
+                                     VEH_IDM * 4, NAVI_DIM * 4, OBJ_F * 4, 4, 4, ROUTE_MAX * 4};
 static const int kSnapIdx[7] = {11, 14, 15, 16, 18, 19, 20};  // env_i veh_s veh_c veh_i veh_idm veh_navi obj_f
 
 #define CK(call)                                                                                   \
@@ -969,6 +1062,7 @@ static const int kSnapIdx[7] = {11, 14, 15, 16, 18, 19, 20};  // env_i veh_s veh
         }                                                                                          \
     } while (0)
 
+static int opt_in_smem(md_sim* sim);
 static void** arr_slot(MdArrays* a, int i) { return reinterpret_cast<void**>(a) + i; }
 
 extern "C" int md_abi_version(void) { return MD_ABI_VERSION; }
@@ -1013,9 +1107,9 @@ extern "C" void md_destroy(md_sim* sim) {
     if (!sim) return;
     cudaSetDevice(sim->device);
     if (sim->loaded) {
-        for (int i = 0; i < 21; i++) cudaFree(*arr_slot(&sim->dev, i));
+        for (int i = 0; i < N_ARR; i++) cudaFree(*arr_slot(&sim->dev, i));
         for (int i = 0; i < 7; i++) cudaFree(sim->snap_bufs[i]);
-        cudaFree(sim->body_tab); cudaFree(sim->mask);
+        cudaFree(sim->body_tab); cudaFree(sim->veh_act); cudaFree(sim->mask);
         cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_reward); cudaFreeHost(sim->h_cost);
         cudaFreeHost(sim->h_info_f); cudaFreeHost(sim->h_term); cudaFreeHost(sim->h_trunc); cudaFreeHost(sim->h_mask);
         cudaFreeHost(sim->h_info_flags);
@@ -1055,7 +1149,7 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
         sim->err = "row counts do not match the configuration";
         return -6;
     }
-    for (int i = 0; i < 21; i++) {
+    for (int i = 0; i < N_ARR; i++) {
         sim->rows[i] = rows[i];
         sim->bytes[i] = (size_t)rows[i] * kRowBytes[i];
         void* d = nullptr;
@@ -1068,6 +1162,8 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
     set_snapshot_ptrs(sim);
     CK(cudaMalloc(&sim->body_tab, (size_t)NV * BODY_ROW * 4));
     CK(cudaMemset(sim->body_tab, 0, (size_t)NV * BODY_ROW * 4));
+    CK(cudaMalloc(&sim->veh_act, (size_t)NV * sizeof(float4)));
+    CK(cudaMemset(sim->veh_act, 0, (size_t)NV * sizeof(float4)));
     CK(cudaMalloc(&sim->mask, (size_t)c.n_envs));
     const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_STATE + c.n_lasers;
     CK(cudaMallocHost(&sim->h_actions, NA * 2 * 4)); CK(cudaMallocHost(&sim->h_obs, NA * od * 4));
@@ -1079,11 +1175,12 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
     CK(cudaMalloc(&sim->d_term, NA)); CK(cudaMalloc(&sim->d_trunc, NA)); CK(cudaMalloc(&sim->d_mask_in, (size_t)c.n_envs));
     CK(cudaMalloc(&sim->d_info_flags, NA * 4));
     sim->loaded = true;
+    if (opt_in_smem(sim)) return -4;
     return md_snapshot(sim);
 }
 
 static int find_name(const char* name) {
-    for (int i = 0; i < 21; i++)
+    for (int i = 0; i < N_ARR; i++)
         if (strcmp(name, kNames[i]) == 0) return i;
     return -1;
 }
@@ -1111,18 +1208,74 @@ extern "C" int md_set_state(md_sim* sim, const char* name, const void* host_src,
     return 0;
 }
 
-static int launch_step(md_sim* sim, int mode, const float* actions, const float* ext_act3, int n_sub, float* idm_out,
-                       StepOut out, const uint8_t* mask, cudaStream_t st) {
-    const MdConfig& c = sim->cfg;
-    int epb = STEP_THREADS / c.slots_per_env;
-    if (epb < 1) epb = 1;
-    int threads = epb * c.slots_per_env;
-    threads = (threads + 31) & ~31;
-    int blocks = (c.n_envs + epb - 1) / epb;
-    size_t per_env = sizeof(Nb) * c.slots_per_env + sizeof(float) * OBJ_F * c.objs_per_env + sizeof(int) * ((c.objs_per_env + 3) & ~3);
-    size_t smem = per_env * epb;
-    k_step_vehicles<<<blocks, threads, smem, st>>>(c, sim->dev, mode, epb, actions, ext_act3, n_sub, idm_out, out, sim->body_tab,
-                                                  mask, sim->snap);
+// CTA geometry shared by k_pre / k_dyn / k_post: EPB envs per CTA, EPB * S threads, launch bound MAXT >= threads
+struct StepLaunch { int epb, threads, blocks, maxt; size_t smem; };
+static StepLaunch step_launch(const MdConfig& c) {
+    StepLaunch L;
+    L.epb = 32;
+    while (L.epb > 1 && L.epb * c.slots_per_env > 1024) L.epb >>= 1;
+    L.threads = (L.epb * c.slots_per_env + 31) & ~31;
+    L.blocks = (c.n_envs + L.epb - 1) / L.epb;
+    L.maxt = L.threads <= 256 ? 256 : (L.threads <= 512 ? 512 : (L.threads <= 640 ? 640 : (L.threads <= 768 ? 768 : 1024)));
+    L.smem = step_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb);
+    return L;
+}
+#define DISPATCH_MAXT(L, KERNEL, ...)                                                                                 \
+    do {                                                                                                              \
+        switch ((L).maxt) {                                                                                           \
+            case 256: KERNEL<256><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
+            case 512: KERNEL<512><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
+            case 640: KERNEL<640><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
+            case 768: KERNEL<768><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
+            default: KERNEL<1024><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
+        }                                                                                                             \
+    } while (0)
+
+template <typename K>
+static cudaError_t allow_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+// dynamic shared memory above the 48 KB default needs an opt-in per kernel instantiation
+static int opt_in_smem(md_sim* sim) {
+    StepLaunch L = step_launch(sim->cfg);
+    if (L.smem > 200 * 1024) { sim->err = "slots/objects per env need more than 200 KB of shared memory per CTA"; return -4; }
+    size_t b = L.smem > 48 * 1024 ? L.smem : 48 * 1024;
+    switch (L.maxt) {
+        case 256: CK(allow_smem(k_pre<256>, b)); CK(allow_smem(k_dyn<256>, b)); CK(allow_smem(k_post<256>, b)); break;
+        case 512: CK(allow_smem(k_pre<512>, b)); CK(allow_smem(k_dyn<512>, b)); CK(allow_smem(k_post<512>, b)); break;
+        case 640: CK(allow_smem(k_pre<640>, b)); CK(allow_smem(k_dyn<640>, b)); CK(allow_smem(k_post<640>, b)); break;
+        case 768: CK(allow_smem(k_pre<768>, b)); CK(allow_smem(k_dyn<768>, b)); CK(allow_smem(k_post<768>, b)); break;
+        default: CK(allow_smem(k_pre<1024>, b)); CK(allow_smem(k_dyn<1024>, b)); CK(allow_smem(k_post<1024>, b)); break;
+    }
+    size_t lb = lidar_smem_per_warp(sim->cfg.slots_per_env, sim->cfg.objs_per_env) * LIDAR_WARPS;
+    if (lb > 48 * 1024) CK(allow_smem(k_lidar, lb));
+    return 0;
+}
+
+static int launch_pre(md_sim* sim, int mode, const float* actions, float* idm_out, cudaStream_t st) {
+    StepLaunch L = step_launch(sim->cfg);
+    DISPATCH_MAXT(L, k_pre, sim->cfg, sim->dev, mode, L.epb, actions, idm_out, sim->veh_act);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_dyn(md_sim* sim, int mode, const float* ext_act3, int n_sub, cudaStream_t st) {
+    StepLaunch L = step_launch(sim->cfg);
+    DISPATCH_MAXT(L, k_dyn, sim->cfg, sim->dev, mode, L.epb, sim->veh_act, ext_act3, n_sub);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_post(md_sim* sim, int mode, StepOut out, const uint8_t* mask, cudaStream_t st) {
+    StepLaunch L = step_launch(sim->cfg);
+    DISPATCH_MAXT(L, k_post, sim->cfg, sim->dev, mode, L.epb, out, sim->body_tab, mask);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_restore(md_sim* sim, const uint8_t* mask, cudaStream_t st) {
+    long long nv = (long long)sim->cfg.n_envs * sim->cfg.slots_per_env;
+    k_restore<<<(int)((nv + 255) / 256), 256, 0, st>>>(sim->cfg, sim->dev, sim->snap, mask);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1143,7 +1296,8 @@ extern "C" int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev
     CK(cudaSetDevice(sim->device));
     cudaStream_t st = (cudaStream_t)stream;
     StepOut out = {obs_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (launch_step(sim, MODE_RESET, nullptr, nullptr, 0, nullptr, out, env_mask_dev, st)) return -1;
+    if (launch_restore(sim, env_mask_dev, st)) return -1;
+    if (launch_post(sim, MODE_RESET, out, env_mask_dev, st)) return -1;
     return launch_lidar(sim, obs_dev, OBS_STATE + sim->cfg.n_lasers, OBS_STATE, nullptr, env_mask_dev, st);
 }
 
@@ -1154,11 +1308,16 @@ extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, fl
     cudaStream_t st = (cudaStream_t)stream;
     StepOut out = {obs_dev, reward_dev, cost_dev, terminated_dev, truncated_dev, info_flags_dev, info_f_dev};
     const bool prof = sim->prof_n < sim->prof_cap;
-    if (prof) CK(cudaEventRecord(sim->prof_ev[3 * sim->prof_n], st));
-    if (launch_step(sim, MODE_FULL, actions_dev, nullptr, sim->cfg.decision_repeat, nullptr, out, nullptr, st)) return -1;
-    if (prof) CK(cudaEventRecord(sim->prof_ev[3 * sim->prof_n + 1], st));
+    cudaEvent_t* ev = prof ? &sim->prof_ev[5 * sim->prof_n] : nullptr;
+    if (prof) CK(cudaEventRecord(ev[0], st));
+    if (launch_pre(sim, MODE_AGENT_PRE | MODE_TRIGGER | MODE_IDM, actions_dev, nullptr, st)) return -1;
+    if (prof) CK(cudaEventRecord(ev[1], st));
+    if (launch_dyn(sim, MODE_DYN | MODE_CONTACTS, nullptr, sim->cfg.decision_repeat, st)) return -1;
+    if (prof) CK(cudaEventRecord(ev[2], st));
+    if (launch_post(sim, MODE_POST | MODE_OUT | MODE_REMOVE, out, nullptr, st)) return -1;
+    if (prof) CK(cudaEventRecord(ev[3], st));
     if (launch_lidar(sim, obs_dev, OBS_STATE + sim->cfg.n_lasers, OBS_STATE, nullptr, nullptr, st)) return -1;
-    if (prof) { CK(cudaEventRecord(sim->prof_ev[3 * sim->prof_n + 2], st)); sim->prof_n++; }
+    if (prof) { CK(cudaEventRecord(ev[4], st)); sim->prof_n++; }
     return 0;
 }
 
@@ -1166,7 +1325,7 @@ extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, fl
 extern "C" int md_profile_begin(md_sim* sim, int max_steps) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
-    while ((int)sim->prof_ev.size() < 3 * max_steps) {
+    while ((int)sim->prof_ev.size() < 5 * max_steps) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         sim->prof_ev.push_back(e);
@@ -1175,15 +1334,14 @@ extern "C" int md_profile_begin(md_sim* sim, int max_steps) {
     sim->prof_n = 0;
     return 0;
 }
-// after the caller synchronised: ms of k_step_vehicles and k_lidar for each recorded step; returns the count
-extern "C" int md_profile_end(md_sim* sim, float* step_ms, float* lidar_ms, int cap) {
+// after the caller synchronised: ms[4*i + k] = duration of kernel k (k_pre, k_dyn, k_post, k_lidar) of recorded step i
+extern "C" int md_profile_end(md_sim* sim, float* ms, int cap) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     int n = sim->prof_n < cap ? sim->prof_n : cap;
     for (int i = 0; i < n; i++) {
-        CK(cudaEventSynchronize(sim->prof_ev[3 * i + 2]));
-        CK(cudaEventElapsedTime(&step_ms[i], sim->prof_ev[3 * i], sim->prof_ev[3 * i + 1]));
-        CK(cudaEventElapsedTime(&lidar_ms[i], sim->prof_ev[3 * i + 1], sim->prof_ev[3 * i + 2]));
+        CK(cudaEventSynchronize(sim->prof_ev[5 * i + 4]));
+        for (int k = 0; k < 4; k++) CK(cudaEventElapsedTime(&ms[4 * i + k], sim->prof_ev[5 * i + k], sim->prof_ev[5 * i + k + 1]));
     }
     sim->prof_cap = 0;
     sim->prof_n = 0;
@@ -1206,26 +1364,24 @@ extern "C" int md_lidar(md_sim* sim, float* frac_dev, int32_t* hit_dev, void* st
     cudaStream_t st = (cudaStream_t)stream;
     // refresh the body rows from the current state without moving anything
     StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (launch_step(sim, 0, nullptr, nullptr, 0, nullptr, out, nullptr, st)) return -1;
+    if (launch_post(sim, 0, out, nullptr, st)) return -1;
     return launch_lidar(sim, frac_dev, sim->cfg.n_lasers, 0, hit_dev, nullptr, st);
 }
 extern "C" int md_dynamics(md_sim* sim, const float* act3_dev, int n_sub, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
-    StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    return launch_step(sim, MODE_DYN | MODE_EXT_ACT, nullptr, act3_dev, n_sub, nullptr, out, nullptr, (cudaStream_t)stream);
+    return launch_dyn(sim, MODE_DYN | MODE_EXT_ACT, act3_dev, n_sub, (cudaStream_t)stream);
 }
 extern "C" int md_after_step(md_sim* sim, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    return launch_step(sim, MODE_POST | MODE_CLEAR_FLAGS, nullptr, nullptr, 0, nullptr, out, nullptr, (cudaStream_t)stream);
+    return launch_post(sim, MODE_POST | MODE_CLEAR_FLAGS, out, nullptr, (cudaStream_t)stream);
 }
 extern "C" int md_idm(md_sim* sim, float* out_actions_dev, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
-    StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    return launch_step(sim, MODE_IDM_OUT, nullptr, nullptr, 0, out_actions_dev, out, nullptr, (cudaStream_t)stream);
+    return launch_pre(sim, MODE_IDM_OUT, nullptr, out_actions_dev, (cudaStream_t)stream);
 }
 
 extern "C" int md_reset_host(md_sim* sim, const uint8_t* env_mask, float* obs) {

@@ -63,7 +63,7 @@ def load():
     lib.md_set_state.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.md_snapshot.argtypes = [vp]
     lib.md_profile_begin.argtypes = [vp, ip]
-    lib.md_profile_end.argtypes = [vp, vp, vp, ip]
+    lib.md_profile_end.argtypes = [vp, vp, ip]
     lib.md_launch_count.argtypes = [vp]
     lib.md_launch_count.restype = C.c_int64
     for name in EXPORTS:

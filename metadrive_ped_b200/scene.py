@@ -187,6 +187,8 @@ class MapGeometry:
     quad_f: np.ndarray  # [Q,8]
     grid_start: np.ndarray
     grid_items: np.ndarray
+    lgrid_start: np.ndarray
+    lgrid_items: np.ndarray
     grid_origin: tuple
     grid_dims: tuple
     lane_num: int
@@ -216,6 +218,8 @@ def build_map_geometry(mt: MapTable, map_region_size=1024.0) -> MapGeometry:
             s, e = lane_position(row, 0, 0), lane_position(row, row[2], 0)
             lane_f[l, 10:14] = [s[0], s[1], e[0], e[1]]
         poly = lane_polygon(row)
+        if row[0] == 0:  # last polygon sample of a straight lane: its hull is [0, this] x [-w/2, w/2] in lane coordinates
+            lane_f[l, 14] = float(np.arange(0, row[2] + POLYGON_SAMPLE_RATE, POLYGON_SAMPLE_RATE)[-1])
         hull = convex_hull(poly)
         hulls.append(hull)
         lane_bb[l] = [hull[:, 0].min(), hull[:, 1].min(), hull[:, 0].max(), hull[:, 1].max()]
@@ -273,7 +277,21 @@ def build_map_geometry(mt: MapTable, map_region_size=1024.0) -> MapGeometry:
     grid_start = np.zeros(nx * ny + 1, np.int32)
     grid_start[1:] = np.cumsum([len(c) for c in cells])
     grid_items = np.array([it for c in cells for it in c], np.int32)
+    # lanes binned into the same cells by hull AABB (broad phase of ray_localization, utils/pg/utils.py:151-203)
+    lcells = [[] for _ in range(nx * ny)]
+    for l, b in enumerate(lane_bb):
+        x0 = max(0, int(math.floor((b[0] - lo[0]) / GRID_CELL)))
+        x1 = min(nx - 1, int(math.floor((b[2] - lo[0]) / GRID_CELL)))
+        y0 = max(0, int(math.floor((b[1] - lo[1]) / GRID_CELL)))
+        y1 = min(ny - 1, int(math.floor((b[3] - lo[1]) / GRID_CELL)))
+        for cy in range(y0, y1 + 1):
+            for cx in range(x0, x1 + 1):
+                lcells[cy * nx + cx].append(l)
+    lgrid_start = np.zeros(nx * ny + 1, np.int32)
+    lgrid_start[1:] = np.cumsum([len(c) for c in lcells])
+    lgrid_items = np.array([it for c in lcells for it in c], np.int32)
     return MapGeometry(lane_f, lane_i, lane_bb, mt.road_i.copy(), hull_xy, line_f, quad_f, grid_start, grid_items,
+                       lgrid_start, lgrid_items,
                        (float(lo[0]), float(lo[1])), (nx, ny), mt.lane_num, mt.meta)
 
 
@@ -302,10 +320,11 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
     M, E, S, O = len(maps), len(scenarios), slots_per_env, objs_per_env
     map_desc = np.zeros((M, MAPD), np.int32)
     map_descf = np.zeros((M, MAPDF), np.float32)
-    lane_off = road_off = hull_off = line_off = quad_off = grid_off = item_off = 0
+    lane_off = road_off = hull_off = line_off = quad_off = grid_off = item_off = litem_off = 0
     for k, g in enumerate(maps):
-        map_desc[k, :14] = [lane_off, len(g.lane_f), road_off, len(g.road_i), hull_off, line_off, len(g.line_f),
-                            quad_off, len(g.quad_f), grid_off, g.grid_dims[0], g.grid_dims[1], item_off, g.lane_num]
+        map_desc[k, :16] = [lane_off, len(g.lane_f), road_off, len(g.road_i), hull_off, line_off, len(g.line_f),
+                            quad_off, len(g.quad_f), grid_off, g.grid_dims[0], g.grid_dims[1], item_off, g.lane_num,
+                            grid_off, litem_off]
         map_descf[k] = [g.grid_origin[0], g.grid_origin[1], GRID_CELL, 0]
         lane_off += len(g.lane_f)
         road_off += len(g.road_i)
@@ -314,6 +333,7 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
         quad_off += len(g.quad_f)
         grid_off += len(g.grid_start)
         item_off += len(g.grid_items)
+        litem_off += len(g.lgrid_items)
 
     def cat(name, dtype, width=None):
         arrs = [np.asarray(getattr(g, name)) for g in maps]
@@ -328,6 +348,7 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
         road_i=cat("road_i", np.int32, ROAD_I), hull_xy=cat("hull_xy", np.float32, 2),
         line_f=cat("line_f", np.float32, LINE_F), quad_f=cat("quad_f", np.float32, QUAD_F),
         grid_start=cat("grid_start", np.int32), grid_items=cat("grid_items", np.int32),
+        lgrid_start=cat("lgrid_start", np.int32), lgrid_items=cat("lgrid_items", np.int32),
     )
     NV = E * S
     env_i = np.zeros((E, ENV_I), np.int32)
@@ -340,6 +361,8 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
     veh_i[:, 4] = -1
     veh_i[:, 9] = -1
     veh_route = np.full((NV, ROUTE_MAX), -1, np.int32)
+    veh_rroad = np.full((NV, ROUTE_MAX), -1, np.int32)
+    road_lut = [{(int(r[0]), int(r[1])): k for k, r in enumerate(g.road_i)} for g in maps]
     veh_idm = np.zeros((NV, VEH_IDM), np.float32)
     veh_navi = np.zeros((NV, NAVI_DIM), np.float32)
     obj_f = np.zeros((max(E * O, 1), OBJ_F), np.float32)
@@ -371,6 +394,13 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
         veh_i[sl, 10] = sc.veh_dyn[:, 13].astype(np.int32)
         veh_i[sl, 13] = sc.veh_int[:, 2]
         veh_route[sl] = sc.routes
+        lut = road_lut[sc.map_id]
+        for k in range(n):
+            rt = sc.routes[k]
+            for j in range(ROUTE_MAX - 1):
+                if rt[j] < 0 or rt[j + 1] < 0:
+                    break
+                veh_rroad[e * S + k, j] = lut.get((int(rt[j]), int(rt[j + 1])), -1)
         veh_idm[sl, 0] = sc.idm[:, 0]
         veh_idm[sl, 1] = sc.idm[:, 1]
         veh_c[sl, 0:2] = sc.veh_dyn[:, 0:2]
@@ -384,10 +414,10 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
             if sc.objects.shape[1] >= 10:
                 ob[:, 10:12] = sc.objects[:, 8:10]
     arrays.update(env_i=env_i, env_trigger=env_trigger, veh_p=veh_p, veh_s=veh_s, veh_c=veh_c, veh_i=veh_i,
-                  veh_route=veh_route, veh_idm=veh_idm, veh_navi=veh_navi, obj_f=obj_f)
+                  veh_route=veh_route, veh_idm=veh_idm, veh_navi=veh_navi, obj_f=obj_f, veh_rroad=veh_rroad)
     return arrays
 
 
 ARRAY_ORDER = ["map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f", "quad_f",
                "grid_start", "grid_items", "env_i", "env_trigger", "veh_p", "veh_s", "veh_c", "veh_i", "veh_route",
-               "veh_idm", "veh_navi", "obj_f"]
+               "veh_idm", "veh_navi", "obj_f", "lgrid_start", "lgrid_items", "veh_rroad"]

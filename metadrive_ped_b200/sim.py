@@ -138,15 +138,16 @@ class BatchedSim:
         self._check(self.lib.md_profile_begin(self.h, int(max_steps)))
         self._prof_cap = int(max_steps)
 
+    KERNELS = ["k_pre", "k_dyn", "k_post", "k_lidar"]
+
     def profile_end(self):
-        """(k_step_vehicles ms, k_lidar ms) arrays for the md_step calls since profile_begin (synchronises)."""
+        """[n, 4] ms of k_pre, k_dyn, k_post, k_lidar for the md_step calls since profile_begin (synchronises)."""
         self.torch.cuda.synchronize(self.tdev)
-        a = np.zeros(self._prof_cap, np.float32)
-        b = np.zeros(self._prof_cap, np.float32)
-        n = self.lib.md_profile_end(self.h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), self._prof_cap)
+        a = np.zeros((self._prof_cap, 4), np.float32)
+        n = self.lib.md_profile_end(self.h, a.ctypes.data_as(C.c_void_p), self._prof_cap)
         if n < 0:
             self._check(n)
-        return a[:n], b[:n]
+        return a[:n]
 
     @property
     def launch_count(self):
