@@ -42,14 +42,15 @@
 #define RI_N 3
 #define RI_NEG 4     /* Road.is_negative_road() */
 #define RI_BLOCK 5   /* ord(block id char) */
-/* line_f [Stot, 6]: static-world lane-line boxes (component/block/base_block.py:468-519) */
-#define LINE_F 6
+/* line_f [Stot, 8]: static-world lane-line boxes (component/block/base_block.py:468-519); two float4 per row, the
+ * first one holds everything a bounding-circle test needs */
+#define LINE_F 8
 #define LN_CX 0
 #define LN_CY 1
-#define LN_UX 2      /* unit direction */
-#define LN_UY 3
-#define LN_HALF 4    /* half length; half width is 0.0375 */
-#define LN_KIND 5    /* 0 white solid, 1 yellow solid, 2 white broken, 3 yellow broken */
+#define LN_HALF 2    /* half length; half width is 0.0375 */
+#define LN_KIND 3    /* 0 white solid, 1 yellow solid, 2 white broken, 3 yellow broken */
+#define LN_UX 4      /* unit direction */
+#define LN_UY 5
 /* quad_f [Qtot, 8]: sidewalk strip quads, 4 corners CCW (component/pgblock/pg_block.py:294-332) */
 #define QUAD_F 8
 /* map_desc [M, 16] int32 */

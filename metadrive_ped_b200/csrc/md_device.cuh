@@ -130,13 +130,25 @@ __device__ __forceinline__ bool lane_is_previous_of(const float* __restrict__ A,
     float dx = A[LF_EX] - B[LF_SX], dy = A[LF_EY] - B[LF_SY];
     return sqrtf(dx * dx + dy * dy) < 0.1f;
 }
-// component/block/base_block.py:459-466: lane body = convex hull of lane.polygon
+// component/block/base_block.py:459-466: lane body = convex hull of lane.polygon.  The vertex list is stored closed
+// (n edges, n + 1 rows).  Edges are tested four at a time with their loads issued together; the verdict is the AND over
+// all edges, so the grouping does not change the result.
 __device__ __forceinline__ bool point_in_hull(const float* __restrict__ hull, int n, float px, float py) {
-    for (int i = 0; i < n; i++) {
-        int j = i + 1 == n ? 0 : i + 1;
-        float ax = hull[2 * i], ay = hull[2 * i + 1], bx = hull[2 * j], by = hull[2 * j + 1];
-        float c = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
-        if (c < -1e-3f) return false;  // edge counts as inside; Bullet's hull has a 0.04 m margin
+    const float2* __restrict__ v = reinterpret_cast<const float2*>(hull);
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        float2 a = __ldg(v + i), b = __ldg(v + i + 1), c = __ldg(v + i + 2), d = __ldg(v + i + 3), e = __ldg(v + i + 4);
+        float c0 = (b.x - a.x) * (py - a.y) - (b.y - a.y) * (px - a.x);
+        float c1 = (c.x - b.x) * (py - b.y) - (c.y - b.y) * (px - b.x);
+        float c2 = (d.x - c.x) * (py - c.y) - (d.y - c.y) * (px - c.x);
+        float c3 = (e.x - d.x) * (py - d.y) - (e.y - d.y) * (px - d.x);
+        // edge counts as inside (Bullet's hull has a 0.04 m margin)
+        if (c0 < -1e-3f || c1 < -1e-3f || c2 < -1e-3f || c3 < -1e-3f) return false;
+    }
+    for (; i < n; i++) {
+        float2 a = __ldg(v + i), b = __ldg(v + i + 1);
+        float c0 = (b.x - a.x) * (py - a.y) - (b.y - a.y) * (px - a.x);
+        if (c0 < -1e-3f) return false;
     }
     return true;
 }

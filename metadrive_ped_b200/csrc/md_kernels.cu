@@ -374,29 +374,51 @@ __device__ void localise(const MapView& m, const float* S, int* I, const int* __
 }
 
 // BaseVehicle._state_check, static world part + sidewalk sweep (component/vehicle/base_vehicle.py:700-792),
-// broad phase = the map's uniform grid
+// broad phase = the map's uniform grid.  Items of a cell are handled four at a time: ids first, then the first float4
+// of every row (centre + extent), a bounding-circle prune, and only then the exact SAT - so that the global-load
+// latencies of a batch overlap instead of chaining.  Flags are ORed, so the order of evaluation is irrelevant.
 __device__ void state_check_static(const MapView& m, const Rect& r, int& flags) {
-    float rad = sqrtf(r.hu * r.hu + r.hv * r.hv);
+    const float rad = sqrtf(r.hu * r.hu + r.hv * r.hv);
     int x0 = (int)floorf((r.cx - rad - m.gx0) / m.cell), x1 = (int)floorf((r.cx + rad - m.gx0) / m.cell);
     int y0 = (int)floorf((r.cy - rad - m.gy0) / m.cell), y1 = (int)floorf((r.cy + rad - m.gy0) / m.cell);
     x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, m.nx - 1); y1 = min(y1, m.ny - 1);
+    const float4* line4 = reinterpret_cast<const float4*>(m.lines);
+    const float4* quad4 = reinterpret_cast<const float4*>(m.quads);
     for (int cy = y0; cy <= y1; cy++)
         for (int cx = x0; cx <= x1; cx++) {
-            int c = cy * m.nx + cx;
-            int k1 = m.gs[c + 1];
-            for (int k = m.gs[c]; k < k1; k++) {
-                int it = m.gi[k];
-                if (it < m.n_lines) {
-                    const float* Ln = m.lines + it * LINE_F;
-                    int kind = (int)Ln[LN_KIND];
-                    int bit = kind == 0 ? FL_ON_WHITE : (kind == 1 ? FL_ON_YELLOW : FL_ON_BROKEN);
-                    if (flags & bit) continue;
-                    Rect lr;
-                    lr.cx = Ln[LN_CX]; lr.cy = Ln[LN_CY]; lr.ux = Ln[LN_UX]; lr.uy = Ln[LN_UY]; lr.hu = Ln[LN_HALF]; lr.hv = LINE_HALF_W;
-                    if (rect_rect(r, lr)) flags |= bit;
-                } else {
-                    if (flags & FL_CRASH_SIDEWALK) continue;
-                    if (rect_quad(r, m.quads + (it - m.n_lines) * QUAD_F)) flags |= FL_CRASH_SIDEWALK;
+            const int c = cy * m.nx + cx;
+            const int k1 = m.gs[c + 1];
+            for (int k = m.gs[c]; k < k1; k += 4) {
+                int id[4];
+                float4 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) id[j] = k + j < k1 ? __ldg(m.gi + k + j) : -1;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (id[j] < 0) continue;
+                    h[j] = id[j] < m.n_lines ? __ldg(line4 + 2 * id[j]) : __ldg(quad4 + 2 * (id[j] - m.n_lines));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int it = id[j];
+                    if (it < 0) continue;
+                    if (it < m.n_lines) {
+                        const int kind = (int)h[j].w;
+                        const int bit = kind == 0 ? FL_ON_WHITE : (kind == 1 ? FL_ON_YELLOW : FL_ON_BROKEN);
+                        if (flags & bit) continue;
+                        // conservative prune: centre distance beyond the two bounding radii (+1 cm)
+                        const float dx = h[j].x - r.cx, dy = h[j].y - r.cy, rr = rad + h[j].z + LINE_HALF_W + 0.01f;
+                        if (dx * dx + dy * dy > rr * rr) continue;
+                        const float4 u = __ldg(line4 + 2 * it + 1);
+                        Rect lr;
+                        lr.cx = h[j].x; lr.cy = h[j].y; lr.ux = u.x; lr.uy = u.y; lr.hu = h[j].z; lr.hv = LINE_HALF_W;
+                        if (rect_rect(r, lr)) flags |= bit;
+                    } else {
+                        if (flags & FL_CRASH_SIDEWALK) continue;
+                        const float4 q1 = __ldg(quad4 + 2 * (it - m.n_lines) + 1);
+                        float q[8] = {h[j].x, h[j].y, h[j].z, h[j].w, q1.x, q1.y, q1.z, q1.w};
+                        if (rect_quad(r, q)) flags |= FL_CRASH_SIDEWALK;
+                    }
                 }
             }
         }

@@ -20,7 +20,7 @@ from typing import List
 import numpy as np
 
 # column counts / indices mirrored from include/md_layout.h
-LANE_F, LANE_I, ROAD_I, LINE_F, QUAD_F, MAPD, MAPDF = 16, 8, 6, 6, 8, 16, 4
+LANE_F, LANE_I, ROAD_I, LINE_F, QUAD_F, MAPD, MAPDF = 16, 8, 6, 8, 8, 16, 4
 VEH_P, VEH_S, VEH_C, VEH_I, ROUTE_MAX, VEH_IDM, NAVI_DIM, OBJ_F, ENV_I, TRIGGER_MAX = 16, 16, 16, 16, 24, 8, 10, 12, 8, 8
 LINE_NONE, LINE_BROKEN, LINE_CONTINUOUS, LINE_SIDE, LINE_GUARDRAIL = 0, 1, 2, 3, 4
 GRID_CELL = 8.0
@@ -221,10 +221,10 @@ def build_map_geometry(mt: MapTable, map_region_size=1024.0) -> MapGeometry:
         if row[0] == 0:  # last polygon sample of a straight lane: its hull is [0, this] x [-w/2, w/2] in lane coordinates
             lane_f[l, 14] = float(np.arange(0, row[2] + POLYGON_SAMPLE_RATE, POLYGON_SAMPLE_RATE)[-1])
         hull = convex_hull(poly)
-        hulls.append(hull)
+        hulls.append(np.concatenate([hull, hull[:1]]))  # stored closed: edge i = (v[i], v[i+1]), n edges, n+1 rows
         lane_bb[l] = [hull[:, 0].min(), hull[:, 1].min(), hull[:, 0].max(), hull[:, 1].max()]
         lane_i[l] = [ri[0], ri[1], ri[2], ri[3], hull_off, len(hull), ri[4], ri[5]]
-        hull_off += len(hull)
+        hull_off += len(hull) + 1
         # lane lines (pg_block.py:248-255, 334-361): left border only for lane 0 of a positive road
         road = mt.road_i[ri[0]]
         build = [ri[1] == 0 and not road[4], True]
@@ -244,7 +244,7 @@ def build_map_geometry(mt: MapTable, map_region_size=1024.0) -> MapGeometry:
                 mid = (s + e) / 2
                 if ln <= 0 or abs(mid[0]) > half_region or abs(mid[1]) > half_region:
                     continue
-                lines.append([mid[0], mid[1], d[0] / ln, d[1] / ln, ln / 2, kind])
+                lines.append([mid[0], mid[1], ln / 2, kind, d[0] / ln, d[1] / ln, 0.0, 0.0])
             if lt in (LINE_SIDE, LINE_GUARDRAIL) and l not in sidewalk_done:
                 sidewalk_done.add(l)
                 quads.extend(_sidewalk_quads(row, 1 if lt == LINE_SIDE else side))
@@ -254,8 +254,8 @@ def build_map_geometry(mt: MapTable, map_region_size=1024.0) -> MapGeometry:
     # uniform grid over static items
     boxes = []
     for ln in line_f:
-        ex = abs(ln[2]) * ln[4] + abs(ln[3]) * 0.0375
-        ey = abs(ln[3]) * ln[4] + abs(ln[2]) * 0.0375
+        ex = abs(ln[4]) * ln[2] + abs(ln[5]) * 0.0375
+        ey = abs(ln[5]) * ln[2] + abs(ln[4]) * 0.0375
         boxes.append([ln[0] - ex, ln[1] - ey, ln[0] + ex, ln[1] + ey])
     for q in quad_f:
         xs, ys = q[0::2], q[1::2]

@@ -16,8 +16,8 @@ def test_line_boxes_match_reference(tag):
                      np.asarray(g["map_road_i"], np.int32), json.loads(str(g["map_meta"])), int(g["lane_num"]))
     geo = sc.build_map_geometry(mt)
     ref = g["ref_lines"]
-    mine = np.stack([geo.line_f[:, 0], geo.line_f[:, 1], np.arctan2(geo.line_f[:, 3], geo.line_f[:, 2]), geo.line_f[:, 4],
-                     geo.line_f[:, 5]], 1)
+    mine = np.stack([geo.line_f[:, 0], geo.line_f[:, 1], np.arctan2(geo.line_f[:, 5], geo.line_f[:, 4]), geo.line_f[:, 2],
+                     geo.line_f[:, 3]], 1)
     assert mine.shape == ref.shape
 
     def order(a):
