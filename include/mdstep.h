@@ -65,6 +65,10 @@ int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* trun
 int md_step_host(md_sim* sim, const float* actions, float* obs, float* reward, float* cost, uint8_t* terminated,
                  uint8_t* truncated, int32_t* info_flags, float* info_f, int autoreset);
 int md_reset_host(md_sim* sim, const uint8_t* env_mask, float* obs);
+/* zero-copy variant: out8 receives the addresses of the library's pinned staging buffers in the order obs, reward,
+ * cost, terminated, truncated, info_flags, info_f, actions.  md_step_host with NULL output pointers leaves the results
+ * there; with actions == NULL (or == the staging address) it reads the actions the caller wrote there. */
+int md_host_views(md_sim* sim, void** out8);
 
 /* isolated stages, for parity tests and per-kernel ncu captures */
 /* Lidar.perceive (component/sensors/lidar.py:49-73; sensors/distance_detector.py:27-85): frac_dev [A,n_lasers] in

@@ -292,6 +292,7 @@ __device__ __forceinline__ float ray_zcyl(F3 o, F3 d, float cx, float cy, float 
 
 // ------------------------------------------------------------------------------------------------ dynamics
 struct Actuation { float steer_rad, engine, brake; };
+struct SteerCS { float cs, sn; };  // cos / sin of the front-wheel steering angle, constant over the sub-steps
 
 // btTransformUtil::integrateTransform (rotation part); q = w x y z
 __device__ __forceinline__ void quat_integrate(float* q, F3 w, float dt) {
@@ -315,19 +316,21 @@ struct Body {  // rigid-body state kept in registers across the sub-steps
     float q[4];
 };
 
-__device__ __forceinline__ F3 apply_inv_inertia(const M3& R, F3 t, float Ix, float Iy, float Iz) {
+// world-frame inverse inertia applied to a torque impulse; iIx.. are the reciprocals of the principal moments
+// (Bullet keeps m_invInertiaLocal and multiplies, btRigidBody::updateInertiaTensor)
+__device__ __forceinline__ F3 apply_inv_inertia(const M3& R, F3 t, float iIx, float iIy, float iIz) {
     F3 tl = tmul(R, t);
-    tl = f3(tl.x / Ix, tl.y / Iy, tl.z / Iz);
+    tl = f3(tl.x * iIx, tl.y * iIy, tl.z * iIz);
     return mul(R, tl);
 }
 
 // one doPhysics(dt, 1, dt) sub-step of a chassis on four ray-cast wheels over the plane z = 0
 // (base_vehicle.py:577-598,632-671; engine_core.py:350-352; btRaycastVehicle::updateVehicle / updateFriction)
-__device__ void vehicle_substep(const float* __restrict__ P, Body& B, Actuation act, float dt) {
+__device__ void vehicle_substep(const float* __restrict__ P, Body& B, Actuation act, SteerCS scs, float dt) {
     const float mass = P[VP_MASS], inv_m = 1.0f / mass;
     const float lx = P[VP_WIDTH], ly = P[VP_LENGTH], lz = P[VP_HEIGHT];
-    const float Ix = mass / 12.0f * (ly * ly + lz * lz), Iy = mass / 12.0f * (lx * lx + lz * lz),
-                Iz = mass / 12.0f * (lx * lx + ly * ly);
+    const float Ix = 1.0f / (mass / 12.0f * (ly * ly + lz * lz)), Iy = 1.0f / (mass / 12.0f * (lx * lx + lz * lz)),
+                Iz = 1.0f / (mass / 12.0f * (lx * lx + ly * ly));  // reciprocal principal moments
     F3 pos = B.pos, v = B.v, w = B.w;
     v.z += GRAVITY_Z * dt;
     float wl = sqrtf(dot(w, w));
@@ -390,24 +393,30 @@ __device__ void vehicle_substep(const float* __restrict__ P, Body& B, Actuation 
         w = w + apply_inv_inertia(R, cross(rel, imp), Ix, Iy, Iz);
     }
     if (n_ground > 0) {
-        F3 axle[4], fwd[4];
+        // the two front wheels share one steering angle and the rear wheels are unsteered, so there are only two
+        // distinct (axle, forward) pairs; computing each once is bit-identical to computing it per wheel
+        F3 axle2[2], fwd2[2];
         float side[4] = {0, 0, 0, 0}, fimp[4] = {0, 0, 0, 0}, skid[4] = {1, 1, 1, 1};
         bool sliding = false;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            axle[i] = f3(0, 0, 0); fwd[i] = f3(0, 0, 0);
-            if (!on[i]) continue;
-            float st = i < 2 ? act.steer_rad : 0.0f;
-            float cs = cosf(st), sn = sinf(st);
+        for (int p = 0; p < 2; p++) {
+            float cs = p == 0 ? scs.cs : 1.0f, sn = p == 0 ? scs.sn : 0.0f;
             F3 a = (right * cs + cross(up, right) * sn) + up * (dot(up, right) * (1.0f - cs));
             a = a - normal * dot(a, normal);
             a = a * (1.0f / sqrtf(dot(a, a)));
             F3 f = cross(normal, a);
             f = f * (1.0f / sqrtf(dot(f, f)));
-            axle[i] = a; fwd[i] = f;
+            axle2[p] = a; fwd2[p] = f;
+        }
+#define AXLE(i) axle2[(i) < 2 ? 0 : 1]
+#define FWD(i) fwd2[(i) < 2 ? 0 : 1]
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!on[i]) continue;
+            F3 a = AXLE(i);
             F3 rel = cp[i] - pos;
             F3 aj = tmul(R, cross(rel, a));
-            float jac = inv_m + (aj.x * aj.x / Ix + aj.y * aj.y / Iy + aj.z * aj.z / Iz);
+            float jac = inv_m + (aj.x * aj.x * Ix + aj.y * aj.y * Iy + aj.z * aj.z * Iz);
             float rel_vel = dot(a, v + cross(w, rel));
             side[i] = -SIDE_DAMPING * rel_vel / jac;
         }
@@ -419,10 +428,10 @@ __device__ void vehicle_substep(const float* __restrict__ P, Body& B, Actuation 
             else {
                 float max_imp = act.brake;
                 F3 rel = cp[i] - pos;
-                F3 c0 = cross(rel, fwd[i]);
+                F3 c0 = cross(rel, FWD(i));
                 F3 iw = apply_inv_inertia(R, c0, Ix, Iy, Iz);
-                float denom0 = inv_m + dot(fwd[i], cross(iw, rel));
-                float vrel = dot(fwd[i], v + cross(w, rel));
+                float denom0 = inv_m + dot(FWD(i), cross(iw, rel));
+                float vrel = dot(FWD(i), v + cross(w, rel));
                 float j1 = -vrel / denom0 / (float)n_ground;
                 rolling = clipf(j1, -max_imp, max_imp);
             }
@@ -442,18 +451,20 @@ __device__ void vehicle_substep(const float* __restrict__ P, Body& B, Actuation 
             if (!on[i]) continue;
             F3 rel = cp[i] - pos;
             if (fimp[i] != 0.0f) {
-                F3 imp = fwd[i] * fimp[i];
+                F3 imp = FWD(i) * fimp[i];
                 v = v + imp * inv_m;
                 w = w + apply_inv_inertia(R, cross(rel, imp), Ix, Iy, Iz);
             }
             if (side[i] != 0.0f) {
-                F3 imp = axle[i] * side[i];
+                F3 imp = AXLE(i) * side[i];
                 F3 rel2 = rel - up * (dot(up, rel) * (1.0f - ROLL_INFLUENCE));
                 v = v + imp * inv_m;
                 w = w + apply_inv_inertia(R, cross(rel2, imp), Ix, Iy, Iz);
             }
         }
     }
+#undef AXLE
+#undef FWD
     B.pos = pos; B.v = v; B.w = w;
 }
 

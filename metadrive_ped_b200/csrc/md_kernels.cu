@@ -746,9 +746,11 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     B.v = f3(St[VS_VEL], St[VS_VEL + 1], St[VS_VEL + 2]);
     B.w = f3(St[VS_ANGVEL], St[VS_ANGVEL + 1], St[VS_ANGVEL + 2]);
     const bool moves = G.work && alive && !is_static;
+    SteerCS scs;
+    scs.cs = cosf(act.steer_rad); scs.sn = sinf(act.steer_rad);
     for (int rep = 0; rep < n_sub; rep++) {
         if (moves) {
-            vehicle_substep(P, B, act, cfg.dt);
+            vehicle_substep(P, B, act, scs, cfg.dt);
             St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y; St[VS_POS + 2] = B.pos.z;
             St[VS_QUAT] = B.q[0]; St[VS_QUAT + 1] = B.q[1]; St[VS_QUAT + 2] = B.q[2]; St[VS_QUAT + 3] = B.q[3];
         }
@@ -1430,7 +1432,7 @@ extern "C" int md_step_host(md_sim* sim, const float* actions, float* obs, float
     CK(cudaSetDevice(sim->device));
     const MdConfig& c = sim->cfg;
     const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_STATE + c.n_lasers;
-    memcpy(sim->h_actions, actions, NA * 2 * 4);
+    if (actions && actions != sim->h_actions) memcpy(sim->h_actions, actions, NA * 2 * 4);
     CK(cudaMemcpyAsync(sim->d_actions, sim->h_actions, NA * 2 * 4, cudaMemcpyHostToDevice, sim->stream));
     if (md_step(sim, sim->d_actions, sim->d_obs, sim->d_reward, sim->d_cost, sim->d_term, sim->d_trunc, sim->d_info_flags,
                 sim->d_info_f, sim->stream))
@@ -1445,12 +1447,22 @@ extern "C" int md_step_host(md_sim* sim, const float* actions, float* obs, float
     if (autoreset && md_autoreset(sim, sim->d_term, sim->d_trunc, sim->d_obs, sim->stream)) return -1;
     CK(cudaMemcpyAsync(sim->h_obs, sim->d_obs, NA * od * 4, cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaStreamSynchronize(sim->stream));
-    memcpy(obs, sim->h_obs, NA * od * 4);
-    memcpy(reward, sim->h_reward, NA * 4);
-    memcpy(cost, sim->h_cost, NA * 4);
-    memcpy(terminated, sim->h_term, NA);
-    memcpy(truncated, sim->h_trunc, NA);
-    memcpy(info_flags, sim->h_info_flags, NA * 4);
-    memcpy(info_f, sim->h_info_f, NA * 8 * 4);
+    // NULL outputs: the caller reads the pinned staging buffers in place (md_host_views)
+    if (obs) memcpy(obs, sim->h_obs, NA * od * 4);
+    if (reward) memcpy(reward, sim->h_reward, NA * 4);
+    if (cost) memcpy(cost, sim->h_cost, NA * 4);
+    if (terminated) memcpy(terminated, sim->h_term, NA);
+    if (truncated) memcpy(truncated, sim->h_trunc, NA);
+    if (info_flags) memcpy(info_flags, sim->h_info_flags, NA * 4);
+    if (info_f) memcpy(info_f, sim->h_info_f, NA * 8 * 4);
+    return 0;
+}
+
+// addresses of the pinned host staging buffers md_step_host fills: obs, reward, cost, terminated, truncated,
+// info_flags, info_f, actions (the last one is the input buffer; write actions there and pass NULL to skip a copy)
+extern "C" int md_host_views(md_sim* sim, void** out8) {
+    if (!sim || !sim->loaded) return -2;
+    out8[0] = sim->h_obs; out8[1] = sim->h_reward; out8[2] = sim->h_cost; out8[3] = sim->h_term; out8[4] = sim->h_trunc;
+    out8[5] = sim->h_info_flags; out8[6] = sim->h_info_f; out8[7] = sim->h_actions;
     return 0;
 }

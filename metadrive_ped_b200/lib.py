@@ -14,6 +14,7 @@ EXPORTS = [
     "md_abi_version", "md_create", "md_destroy", "md_last_error", "md_load_scene", "md_reset", "md_step",
     "md_autoreset", "md_step_host", "md_reset_host", "md_lidar", "md_dynamics", "md_after_step", "md_idm",
     "md_get_state", "md_set_state", "md_snapshot", "md_launch_count", "md_profile_begin", "md_profile_end",
+    "md_host_views",
 ]
 
 
@@ -64,6 +65,7 @@ def load():
     lib.md_snapshot.argtypes = [vp]
     lib.md_profile_begin.argtypes = [vp, ip]
     lib.md_profile_end.argtypes = [vp, vp, ip]
+    lib.md_host_views.argtypes = [vp, C.POINTER(vp)]
     lib.md_launch_count.argtypes = [vp]
     lib.md_launch_count.restype = C.c_int64
     for name in EXPORTS:

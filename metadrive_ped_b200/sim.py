@@ -76,17 +76,30 @@ class BatchedSim:
         return self.obs, self.reward, self.cost, self.terminated, self.truncated
 
     # ------------------------------------------------------------------ host-buffer API (numpy in, numpy out)
+    def _views(self):
+        """numpy views of the library's pinned staging buffers (no copy)."""
+        if not hasattr(self, "_hv"):
+            na = self.n_agents
+            ptrs = (C.c_void_p * 8)()
+            self._check(self.lib.md_host_views(self.h, ptrs))
+
+            def view(i, ctype, shape):
+                n = int(np.prod(shape))
+                return np.ctypeslib.as_array(C.cast(ptrs[i], C.POINTER(ctype)), shape=(n, )).reshape(shape)
+
+            self._hv = dict(obs=view(0, C.c_float, (na, self.obs_dim)), reward=view(1, C.c_float, (na, )),
+                            cost=view(2, C.c_float, (na, )), term=view(3, C.c_uint8, (na, )), trunc=view(4, C.c_uint8, (na, )),
+                            flags=view(5, C.c_int32, (na, )), info_f=view(6, C.c_float, (na, 8)),
+                            actions=view(7, C.c_float, (na, 2)))
+        return self._hv
+
     def step_host(self, actions: np.ndarray, autoreset=False):
-        na = self.n_agents
-        a = np.ascontiguousarray(actions, np.float32).reshape(na, 2)
-        if not hasattr(self, "_hb"):
-            self._hb = dict(obs=np.zeros((na, self.obs_dim), np.float32), reward=np.zeros(na, np.float32),
-                            cost=np.zeros(na, np.float32), term=np.zeros(na, np.uint8), trunc=np.zeros(na, np.uint8),
-                            flags=np.zeros(na, np.int32), info_f=np.zeros((na, 8), np.float32))
-        b = self._hb
-        p = lambda x: x.ctypes.data_as(C.c_void_p)
-        self._check(self.lib.md_step_host(self.h, p(a), p(b["obs"]), p(b["reward"]), p(b["cost"]), p(b["term"]),
-                                          p(b["trunc"]), p(b["flags"]), p(b["info_f"]), int(bool(autoreset))))
+        """env.step through host memory: actions are copied into the pinned input buffer, H2D, kernels, D2H; the
+        returned arrays are views of the pinned output buffers (valid until the next call)."""
+        b = self._views()
+        b["actions"][...] = np.asarray(actions, np.float32).reshape(self.n_agents, 2)
+        null = C.c_void_p()
+        self._check(self.lib.md_step_host(self.h, null, null, null, null, null, null, null, null, int(bool(autoreset))))
         return b["obs"], b["reward"], b["cost"], b["term"], b["trunc"], b["flags"], b["info_f"]
 
     def reset_host(self, env_mask=None):
