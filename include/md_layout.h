@@ -21,8 +21,10 @@
 #define LF_SY 11
 #define LF_EX 12     /* lane.end */
 #define LF_EY 13
-#define LF_HULL_LONG 14 /* straight lanes: last polygon sample longitude (hull = [0, this] x [-w/2, w/2]) */
-#define LF_SPARE 15
+#define LF_HULL_LONG 14 /* straight lanes: last polygon sample longitude (hull = [0, this] x [-w/2, w/2]);
+                           circular lanes: radius of the circle inscribed in the outer chord polygon, minus 1 cm */
+#define LF_HULL_NOTHER 15 /* number of leading hull edges that are not outer-arc chords (= all edges for straight lanes);
+                             acceleration hints only - the CPU oracle tests every edge */
 /* lane_i [Ltot, 8] */
 #define LANE_I 8
 #define LI_ROAD 0    /* road id local to the map */

@@ -133,9 +133,7 @@ __device__ __forceinline__ bool lane_is_previous_of(const float* __restrict__ A,
 // component/block/base_block.py:459-466: lane body = convex hull of lane.polygon.  The vertex list is stored closed
 // (n edges, n + 1 rows).  Edges are tested four at a time with their loads issued together; the verdict is the AND over
 // all edges, so the grouping does not change the result.
-__device__ __forceinline__ bool point_in_hull(const float* __restrict__ hull, int n, float px, float py) {
-    const float2* __restrict__ v = reinterpret_cast<const float2*>(hull);
-    int i = 0;
+__device__ __forceinline__ bool hull_edges(const float2* __restrict__ v, int i, int n, float px, float py) {
     for (; i + 4 <= n; i += 4) {
         float2 a = __ldg(v + i), b = __ldg(v + i + 1), c = __ldg(v + i + 2), d = __ldg(v + i + 3), e = __ldg(v + i + 4);
         float c0 = (b.x - a.x) * (py - a.y) - (b.y - a.y) * (px - a.x);
@@ -149,6 +147,19 @@ __device__ __forceinline__ bool point_in_hull(const float* __restrict__ hull, in
         float2 a = __ldg(v + i), b = __ldg(v + i + 1);
         float c0 = (b.x - a.x) * (py - a.y) - (b.y - a.y) * (px - a.x);
         if (c0 < -1e-3f) return false;
+    }
+    return true;
+}
+// L = the lane's lane_f row.  For arcs the outer-chord edges (stored last) are skipped when the point lies inside the
+// circle inscribed in the chord polygon: every such chord is then satisfied with >= 1 cm to spare.
+__device__ __forceinline__ bool point_in_hull(const float* __restrict__ L, const float* __restrict__ hull, int n, float px,
+                                              float py) {
+    const float2* __restrict__ v = reinterpret_cast<const float2*>(hull);
+    const int n_other = (int)L[LF_HULL_NOTHER];
+    if (!hull_edges(v, 0, n_other, px, py)) return false;
+    if (n_other < n) {
+        const float ddx = px - L[LF_P0 + 0], ddy = py - L[LF_P0 + 1], rin = L[LF_HULL_LONG];
+        if (ddx * ddx + ddy * ddy > rin * rin) return hull_edges(v, n_other, n, px, py);
     }
     return true;
 }

@@ -23,6 +23,7 @@
 #include "md_device.cuh"
 
 #define STEP_THREADS 128
+#define DYN_EPB 8
 #define LIDAR_WARPS 8
 #define MAX_LASERS 512
 
@@ -310,7 +311,7 @@ __device__ void localise(const MapView& m, const float* S, int* I, const int* __
         const int sc = hull_shortcut(Ll, px, py, lon, lat);
         if (sc < 0) continue;
         if (sc == 0 &&
-            !point_in_hull(m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], px, py)) continue;
+            !point_in_hull(Ll, m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], px, py)) continue;
         on_lane = true;
         float lh = lane_heading_at(Ll, lon);
         float cosang = cosf(lh) * hx + sinf(lh) * hy;
@@ -1234,9 +1235,11 @@ extern "C" int md_set_state(md_sim* sim, const char* name, const void* host_src,
 
 // CTA geometry shared by k_pre / k_dyn / k_post: EPB envs per CTA, EPB * S threads, launch bound MAXT >= threads
 struct StepLaunch { int epb, threads, blocks, maxt; size_t smem; };
-static StepLaunch step_launch(const MdConfig& c) {
+// epb_pref = 32 makes a warp "one slot index of 32 envs" (uniform roles: k_pre, k_post); k_dyn has no role divergence
+// and prefers small CTAs (more resident CTAs, cheaper barriers, no register cap)
+static StepLaunch step_launch(const MdConfig& c, int epb_pref = 32) {
     StepLaunch L;
-    L.epb = 32;
+    L.epb = epb_pref;
     while (L.epb > 1 && L.epb * c.slots_per_env > 1024) L.epb >>= 1;
     L.threads = (L.epb * c.slots_per_env + 31) & ~31;
     L.blocks = (c.n_envs + L.epb - 1) / L.epb;
@@ -1261,15 +1264,26 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
 }
 // dynamic shared memory above the 48 KB default needs an opt-in per kernel instantiation
 static int opt_in_smem(md_sim* sim) {
+    {   // k_dyn runs with its own (smaller) CTA geometry
+        StepLaunch D = step_launch(sim->cfg, DYN_EPB);
+        size_t b = D.smem > 48 * 1024 ? D.smem : 48 * 1024;
+        switch (D.maxt) {
+            case 256: CK(allow_smem(k_dyn<256>, b)); break;
+            case 512: CK(allow_smem(k_dyn<512>, b)); break;
+            case 640: CK(allow_smem(k_dyn<640>, b)); break;
+            case 768: CK(allow_smem(k_dyn<768>, b)); break;
+            default: CK(allow_smem(k_dyn<1024>, b)); break;
+        }
+    }
     StepLaunch L = step_launch(sim->cfg);
     if (L.smem > 200 * 1024) { sim->err = "slots/objects per env need more than 200 KB of shared memory per CTA"; return -4; }
     size_t b = L.smem > 48 * 1024 ? L.smem : 48 * 1024;
     switch (L.maxt) {
-        case 256: CK(allow_smem(k_pre<256>, b)); CK(allow_smem(k_dyn<256>, b)); CK(allow_smem(k_post<256>, b)); break;
-        case 512: CK(allow_smem(k_pre<512>, b)); CK(allow_smem(k_dyn<512>, b)); CK(allow_smem(k_post<512>, b)); break;
-        case 640: CK(allow_smem(k_pre<640>, b)); CK(allow_smem(k_dyn<640>, b)); CK(allow_smem(k_post<640>, b)); break;
-        case 768: CK(allow_smem(k_pre<768>, b)); CK(allow_smem(k_dyn<768>, b)); CK(allow_smem(k_post<768>, b)); break;
-        default: CK(allow_smem(k_pre<1024>, b)); CK(allow_smem(k_dyn<1024>, b)); CK(allow_smem(k_post<1024>, b)); break;
+        case 256: CK(allow_smem(k_pre<256>, b)); CK(allow_smem(k_post<256>, b)); break;
+        case 512: CK(allow_smem(k_pre<512>, b)); CK(allow_smem(k_post<512>, b)); break;
+        case 640: CK(allow_smem(k_pre<640>, b)); CK(allow_smem(k_post<640>, b)); break;
+        case 768: CK(allow_smem(k_pre<768>, b)); CK(allow_smem(k_post<768>, b)); break;
+        default: CK(allow_smem(k_pre<1024>, b)); CK(allow_smem(k_post<1024>, b)); break;
     }
     size_t lb = lidar_smem_per_warp(sim->cfg.slots_per_env, sim->cfg.objs_per_env) * LIDAR_WARPS;
     if (lb > 48 * 1024) CK(allow_smem(k_lidar, lb));
@@ -1284,7 +1298,7 @@ static int launch_pre(md_sim* sim, int mode, const float* actions, float* idm_ou
     return 0;
 }
 static int launch_dyn(md_sim* sim, int mode, const float* ext_act3, int n_sub, cudaStream_t st) {
-    StepLaunch L = step_launch(sim->cfg);
+    StepLaunch L = step_launch(sim->cfg, DYN_EPB);
     DISPATCH_MAXT(L, k_dyn, sim->cfg, sim->dev, mode, L.epb, sim->veh_act, ext_act3, n_sub);
     sim->launches++;
     CK(cudaGetLastError());

@@ -221,6 +221,25 @@ def build_map_geometry(mt: MapTable, map_region_size=1024.0) -> MapGeometry:
         if row[0] == 0:  # last polygon sample of a straight lane: its hull is [0, this] x [-w/2, w/2] in lane coordinates
             lane_f[l, 14] = float(np.arange(0, row[2] + POLYGON_SAMPLE_RATE, POLYGON_SAMPLE_RATE)[-1])
         hull = convex_hull(poly)
+        lane_f[l, 15] = len(hull)
+        if row[0] == 1:
+            # arc strip: rotate the hull so that the run of outer-arc chords (both ends on the radius R + w/2) comes last;
+            # col 15 = number of leading "other" edges, col 14 = radius of the circle inscribed in the chord polygon
+            # (minus 1 cm): a point inside that circle satisfies every outer chord, so kernels may skip those edges.
+            cx, cy, r = row[3], row[4], row[5]
+            ro = r + row[1] / 2
+            on_outer = np.abs(np.hypot(hull[:, 0] - cx, hull[:, 1] - cy) - ro) < 1e-6
+            n = len(hull)
+            chord = np.array([on_outer[i] and on_outer[(i + 1) % n] for i in range(n)])
+            if chord.any() and not chord.all():
+                start = next(i for i in range(n) if chord[i] and not chord[i - 1])  # first edge of the chord run
+                run = 0
+                while chord[(start + run) % n]:
+                    run += 1
+                first_other = (start + run) % n
+                hull = np.roll(hull, -first_other, axis=0)
+                lane_f[l, 15] = n - run
+                lane_f[l, 14] = ro * math.cos(0.5 * POLYGON_SAMPLE_RATE / r) - 0.01
         hulls.append(np.concatenate([hull, hull[:1]]))  # stored closed: edge i = (v[i], v[i+1]), n edges, n+1 rows
         lane_bb[l] = [hull[:, 0].min(), hull[:, 1].min(), hull[:, 0].max(), hull[:, 1].max()]
         lane_i[l] = [ri[0], ri[1], ri[2], ri[3], hull_off, len(hull), ri[4], ri[5]]

@@ -1,10 +1,9 @@
-# plain run first (must exit 0), then the ncu passes of the same command line
+# plain run first (must exit 0), then the ncu passes of the same command line (one GPU, never multi-rank)
 set -x
 mkdir -p gpurun_out
 CMD="python bench.py --steps 3 --warmup 3 --burnin 60 --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 480 -c 80 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 530 -c 48 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"k_pre|k_dyn|k_post" -s 186 -c 3 -o gpurun_out/prof_step $CMD > gpurun_out/ncu_step.log 2>&1
-tail -3 gpurun_out/plain.log gpurun_out/ncu_launch.log gpurun_out/ncu_step.log
+ncu --set full --clock-control none --import-source on -k regex:"k_pre|k_dyn|k_post|k_lidar" -s 266 -c 6 -o gpurun_out/prof_step $CMD > gpurun_out/ncu_step.log 2>&1
 ls -la gpurun_out
