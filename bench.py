@@ -246,6 +246,12 @@ def main():
         }
         assert abs(sum(per_env.values()) - (B_EGO + B_TRAFFIC * T)) < 1.0, per_env
         bytes_per_launch = E * per_env[dom]
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            pass
         dur_ms = float(mean_ms[dom_i])
         achieved = bytes_per_launch / (dur_ms * 1e-3) / 1e9
         line = {
@@ -264,7 +270,7 @@ def main():
             "step_roofline_all_kernels": {"algorithmic_bytes_per_step": E * (B_EGO + B_TRAFFIC * T),
                                           "achieved_gbs": E * (B_EGO + B_TRAFFIC * T) / (float(mean_ms.sum()) * 1e-3) / 1e9},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch},
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke},
