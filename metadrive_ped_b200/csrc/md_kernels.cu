@@ -649,26 +649,34 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
     const int S = G.S, slot = G.slot, env = G.env, g = G.g;
     float P[VEH_P], St[VEH_S], C[VEH_C], D[VEH_IDM];
     int I[VEH_I];
+    bool occupied = false;  // empty slots (kind 0) cost one 16-byte read and publish a dead neighbour record
     if (G.work) {
-        load16(P, A.veh_p + (size_t)g * VEH_P);
-        load16(St, A.veh_s + (size_t)g * VEH_S);
-        load16(C, A.veh_c + (size_t)g * VEH_C);
         load16i(I, A.veh_i + (size_t)g * VEH_I);
-        const float4* d4 = reinterpret_cast<const float4*>(A.veh_idm + (size_t)g * VEH_IDM);
-        float4 d0 = d4[0], d1 = d4[1];
-        D[0] = d0.x; D[1] = d0.y; D[2] = d0.z; D[3] = d0.w; D[4] = d1.x; D[5] = d1.y; D[6] = d1.z; D[7] = d1.w;
-        fill_nb(G.nb[slot], P, St, I);
+        occupied = I[VI_KIND] != 0;
+        if (occupied) {
+            load16(P, A.veh_p + (size_t)g * VEH_P);
+            load16(St, A.veh_s + (size_t)g * VEH_S);
+            load16(C, A.veh_c + (size_t)g * VEH_C);
+            const float4* d4 = reinterpret_cast<const float4*>(A.veh_idm + (size_t)g * VEH_IDM);
+            float4 d0 = d4[0], d1 = d4[1];
+            D[0] = d0.x; D[1] = d0.y; D[2] = d0.z; D[3] = d0.w; D[4] = d1.x; D[5] = d1.y; D[6] = d1.z; D[7] = d1.w;
+            fill_nb(G.nb[slot], P, St, I);
+        } else {
+            G.nb[slot].alive = 0; G.nb[slot].active = 0; G.nb[slot].kind = 0; G.nb[slot].lane = -1;
+        }
     }
     stage_objects(G, A.obj_f);
     Actuation act;
     act.steer_rad = 0.0f; act.engine = 0.0f; act.brake = 2.0f;  // what vehicle.reset() leaves (base_vehicle.py:376)
-    const bool is_agent = G.work && I[VI_KIND] == 1;
-    const bool is_traffic = G.work && I[VI_KIND] == 2;
+    const bool is_agent = occupied && I[VI_KIND] == 1;
+    const bool is_traffic = occupied && I[VI_KIND] == 2;
+    bool dirty = false;  // only vehicles that acted have anything to write back
     // agent_manager.before_step (manager/agent_manager.py:164-202)
     if ((mode & MODE_AGENT_PRE) && is_agent && I[VI_ACTIVE]) {
         latch_before_step(St, C, I);
         const float* a = actions + ((size_t)env * G.NA + slot) * 2;
         act = actuate(P, St, C, a[0], a[1]);
+        dirty = true;
     }
     __syncthreads();
     MapView m;
@@ -690,9 +698,10 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
     }
     if (G.work && slot == 0 && (mode & MODE_AGENT_PRE)) A.env_i[env * ENV_I + EI_STEP] += 1;
     __syncthreads();
-    if (G.work) I[VI_ACTIVE] = G.nb[slot].active;
+    if (occupied && I[VI_ACTIVE] != G.nb[slot].active) { I[VI_ACTIVE] = G.nb[slot].active; dirty = true; }
     // IDM decisions against the pre-step world (policy/idm_policy.py:235-267)
     if ((mode & (MODE_IDM | MODE_IDM_OUT)) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE]) {
+        dirty = true;
         NbrView nv;
         nv.nb = G.nb; nv.obj = G.sobj; nv.S = S; nv.O = G.O; nv.self = slot; nv.px = St[VS_POS]; nv.py = St[VS_POS + 1];
         float a0, a1;
@@ -703,8 +712,8 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
             act = actuate(P, St, C, a0, a1);
         }
     }
-    if (G.work) {
-        veh_act[g] = make_float4(act.steer_rad, act.engine, act.brake, 0.0f);
+    if (occupied) veh_act[g] = make_float4(act.steer_rad, act.engine, act.brake, 0.0f);
+    if (dirty) {
         store16(A.veh_s + (size_t)g * VEH_S, St);
         store16(A.veh_c + (size_t)g * VEH_C, C);
         store16i(A.veh_i + (size_t)g * VEH_I, I);
@@ -727,17 +736,19 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     Actuation act;
     act.steer_rad = 0.0f; act.engine = 0.0f; act.brake = 2.0f;
     if (G.work) {
-        load16(P, A.veh_p + (size_t)g * VEH_P);
-        load16(St, A.veh_s + (size_t)g * VEH_S);
         const int* I = A.veh_i + (size_t)g * VEH_I;
         alive = I[VI_ALIVE]; is_static = I[VI_STATIC]; flags = I[VI_FLAGS];
+        G.nb[slot].alive = alive;
+    }
+    if (G.work && alive) {
+        load16(P, A.veh_p + (size_t)g * VEH_P);
+        load16(St, A.veh_s + (size_t)g * VEH_S);
         if (mode & MODE_EXT_ACT) {
             act.steer_rad = ext_act3[3 * (size_t)g]; act.engine = ext_act3[3 * (size_t)g + 1]; act.brake = ext_act3[3 * (size_t)g + 2];
         } else {
             float4 a = veh_act[g];
             act.steer_rad = a.x; act.engine = a.y; act.brake = a.z;
         }
-        G.nb[slot].alive = alive;
     }
     const bool contacts = (mode & MODE_CONTACTS) != 0;
     if (contacts) stage_objects(G, A.obj_f);
@@ -758,7 +769,7 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
         if (contacts) {
             __syncthreads();  // everyone finished reading the previous footprints
             if (G.work) {
-                G.nb[slot].r = vehicle_rect(P, St);
+                if (alive) G.nb[slot].r = vehicle_rect(P, St);
                 for (int k = slot; k < O; k += S) {  // kinematic movers (traffic_participants/pedestrian.py:67-95)
                     G.obj_first[k] = 0x7fffffff;
                     float* Ob = G.sobj + k * OBJ_F;
@@ -777,10 +788,12 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
             }
         }
     }
-    if (G.work) {
-        St[VS_VEL] = B.v.x; St[VS_VEL + 1] = B.v.y; St[VS_VEL + 2] = B.v.z;
-        St[VS_ANGVEL] = B.w.x; St[VS_ANGVEL + 1] = B.w.y; St[VS_ANGVEL + 2] = B.w.z;
-        store16(A.veh_s + (size_t)g * VEH_S, St);
+    if (G.work && alive) {
+        if (moves) {
+            St[VS_VEL] = B.v.x; St[VS_VEL + 1] = B.v.y; St[VS_VEL + 2] = B.v.z;
+            St[VS_ANGVEL] = B.w.x; St[VS_ANGVEL + 1] = B.w.y; St[VS_ANGVEL + 2] = B.w.z;
+            store16(A.veh_s + (size_t)g * VEH_S, St);
+        }
         A.veh_i[(size_t)g * VEH_I + VI_FLAGS] = flags;
     }
     if (contacts && O > 0) {
@@ -802,26 +815,32 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
     const int S = G.S, slot = G.slot, env = G.env, g = G.g;
     float P[VEH_P], St[VEH_S], C[VEH_C], navi[NAVI_DIM];
     int I[VEH_I];
+    bool occ = false;  // empty slots: one 64-byte read, a dead footprint, nothing else (they still help staging)
     if (G.work) {
+        load16i(I, A.veh_i + (size_t)g * VEH_I);
+        occ = I[VI_KIND] != 0;
+        if (!occ) G.nb[slot].alive = 0;
+    }
+    if (occ) {
         load16(P, A.veh_p + (size_t)g * VEH_P);
         load16(St, A.veh_s + (size_t)g * VEH_S);
         load16(C, A.veh_c + (size_t)g * VEH_C);
-        load16i(I, A.veh_i + (size_t)g * VEH_I);
 #pragma unroll
         for (int k = 0; k < NAVI_DIM; k++) navi[k] = A.veh_navi[(size_t)g * NAVI_DIM + k];
         G.nb[slot].r = vehicle_rect(P, St);
         G.nb[slot].alive = I[VI_ALIVE];
     }
     stage_objects(G, A.obj_f);
-    const bool is_agent = G.work && I[VI_KIND] == 1;
-    const bool is_traffic = G.work && I[VI_KIND] == 2;
-    if ((mode & MODE_RESET) && G.work && I[VI_ALIVE] && (is_agent || is_traffic)) latch_before_step(St, C, I);
+    const bool is_agent = occ && I[VI_KIND] == 1;
+    const bool is_traffic = occ && I[VI_KIND] == 2;
+    if ((mode & MODE_RESET) && occ && I[VI_ALIVE] && (is_agent || is_traffic)) latch_before_step(St, C, I);
     __syncthreads();
     MapView m;
     int env_step = 0;
     if (G.work) { m = map_view(A, A.env_i[env * ENV_I + EI_MAP]); env_step = A.env_i[env * ENV_I + EI_STEP]; }
     const int* rroad = A.veh_rroad + (size_t)g * ROUTE_MAX;
-    const bool do_post = G.work && I[VI_ALIVE] && ((mode & MODE_RESET) ? (is_agent || is_traffic) : (I[VI_ACTIVE] != 0));
+    const bool do_post = (mode & (MODE_POST | MODE_RESET)) && occ && I[VI_ALIVE] &&
+                         ((mode & MODE_RESET) ? (is_agent || is_traffic) : (I[VI_ACTIVE] != 0));
     if (do_post) {
         if (mode & MODE_CLEAR_FLAGS) I[VI_FLAGS] = FL_ON_LANE;
         localise(m, St, I, A.veh_route + (size_t)g * ROUTE_MAX, rroad, navi);
@@ -855,10 +874,10 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         size_t a = (size_t)env * G.NA + slot;
         agent_outputs(cfg, m, env_step, P, St, C, I, rroad, navi, a, out, (mode & MODE_OUT) != 0);
     }
-    if (G.work) {
-        store16(A.veh_c + (size_t)g * VEH_C, C);
-        store16i(A.veh_i + (size_t)g * VEH_I, I);
-        if (do_post) {
+    if (occ) {
+        if (do_post) {  // vehicles that were not localised this step have nothing new to store
+            store16(A.veh_c + (size_t)g * VEH_C, C);
+            store16i(A.veh_i + (size_t)g * VEH_I, I);
 #pragma unroll
             for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = navi[k];
         }
