@@ -137,6 +137,8 @@
 #define VI_EP_LEN 11
 #define VI_DONE 12       /* agent finished (auto-reset pending) */
 #define VI_SPAWN_LANE 13
+#define VI_DYING 14      /* multi-agent: steps left as a static wreck before removal (agent_manager.py:260-263) */
+#define VI_NEW 15        /* multi-agent: spawned during this step (agent_manager.py:136-154) */
 /* veh_route [NV, 24]: checkpoint node ids, -1 padded */
 #define ROUTE_MAX 24
 /* veh_idm [NV, 8] (policy/idm_policy.py:224-233) */
@@ -166,6 +168,8 @@
 #define FL_OUT_OF_ROAD 0x400
 #define FL_ARRIVE 0x800
 #define FL_MAX_STEP 0x1000
+#define FL_VALID 0x2000    /* multi-agent: this agent seat produced a transition this step */
+#define FL_NEWBORN 0x4000  /* multi-agent: the seat was (re)spawned this step: reward 0, first observation */
 
 /* ---- per-object arrays: obj_f [NO, 12] --------------------------------------------------------- */
 #define OBJ_F 12
@@ -189,6 +193,7 @@
 #define EI_STEP 2          /* engine.episode_step */
 #define EI_N_BLOCKS 3
 #define EI_SEED 4
+#define EI_RNG 5           /* multi-agent: number of respawn draws consumed from the env's random tape (ma_tape) */
 /* env_trigger [E, 8]: trigger road id (local to map) per block index */
 #define TRIGGER_MAX 8
 
@@ -207,7 +212,11 @@ typedef struct MdConfig {
     float crash_vehicle_cost, crash_object_cost, out_of_road_cost;
     int use_lateral_reward, out_of_route_done, on_continuous_line_done;
     int crash_vehicle_done, crash_object_done, crash_human_done, truncate_as_terminate;
-    int enable_idm_lane_change, is_multi_agent, delay_done, spare0;
+    int enable_idm_lane_change, is_multi_agent, delay_done, allow_respawn;
+    /* multi-agent respawn tables (manager/spawn_manager.py:117-217): safe places per env, destinations, spawn roads */
+    int ma_places, ma_dests, ma_roads, ma_tape_len;
+    /* MultiAgentMetaDrive.done_function overrides (envs/marl_envs/multi_agent_metadrive.py:114-128) */
+    int ma_crash_done, ma_out_of_road_done, spare1, spare2;
 } MdConfig;
 
 /* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */
@@ -231,14 +240,22 @@ typedef struct MdArrays {
     float* veh_s;             /* [NV, VEH_S] */
     float* veh_c;             /* [NV, VEH_C] */
     int* veh_i;               /* [NV, VEH_I] */
-    const int* veh_route;     /* [NV, ROUTE_MAX] */
+    int* veh_route;           /* [NV, ROUTE_MAX] (rewritten only by a multi-agent respawn) */
     float* veh_idm;           /* [NV, VEH_IDM] */
     float* veh_navi;          /* [NV, NAVI_DIM] */
     float* obj_f;             /* [NO, OBJ_F] */
     /* derived acceleration tables (the CPU oracle ignores them and scans instead) */
     const int* lgrid_start;   /* per map: nx*ny+1 */
     const int* lgrid_items;   /* lane ids local to the map */
-    const int* veh_rroad;     /* [NV, ROUTE_MAX]: road id of route segment k = (route[k] -> route[k+1]), -1 padded */
+    int* veh_rroad;           /* [NV, ROUTE_MAX]: road id of route segment k = (route[k] -> route[k+1]), -1 padded */
+    /* multi-agent respawn tables, per env */
+    const float* ma_place_f;  /* [E*ma_places, 8]: x, y, quat w, quat z (yaw only), lane id, heading cos, sin, spawn-road index */
+    const int* ma_route;      /* [E*ma_roads*ma_dests, ROUTE_MAX]: checkpoints from spawn road r to destination d */
+    const int* ma_rroad;      /* [E*ma_roads*ma_dests, ROUTE_MAX] */
+    /* [E*ma_tape_len, 2] pre-drawn 32-bit random numbers (place draw, destination draw) consumed in order by the
+     * respawns of an env: the reference draws them from unseeded numpy generators (multi_agent_metadrive.py:199,
+     * marl_inout_roundabout.py:138-143), the host fills the tape from its own generator (tests: from the trace) */
+    const int* ma_tape;
 } MdArrays;
 
 #endif

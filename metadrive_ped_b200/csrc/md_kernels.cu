@@ -40,7 +40,7 @@ struct StepOut {
 };
 struct Snapshot {
     const int* env_i; const float* veh_s; const float* veh_c; const int* veh_i; const float* veh_idm;
-    const float* veh_navi; const float* obj_f;
+    const float* veh_navi; const float* obj_f; const int* veh_route; const int* veh_rroad;
 };
 
 // neighbour record of one vehicle slot, shared by the threads of its env
@@ -508,6 +508,11 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         if (flags & FL_CRASH_BUILDING) done = true;
         if ((flags & FL_CRASH_HUMAN) && cfg.crash_human_done) done = true;
         if (max_step && cfg.truncate_as_terminate) done = true;
+        if (cfg.is_multi_agent && !max_step) {  // MultiAgentMetaDrive.done_function (multi_agent_metadrive.py:114-128)
+            const int crash = flags & (FL_CRASH_VEHICLE | FL_CRASH_OBJECT | FL_CRASH_BUILDING | FL_CRASH_SIDEWALK | FL_CRASH_HUMAN);
+            if (crash && !cfg.ma_crash_done && !(arrive || outr)) done = false;
+            if (outr && !cfg.ma_out_of_road_done && !arrive) done = false;
+        }
         float c = 0.0f;
         if (outr) c = cfg.out_of_road_cost;
         else if (flags & FL_CRASH_VEHICLE) c = cfg.crash_vehicle_cost;
@@ -560,6 +565,34 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
     }
 #pragma unroll
     for (int k = 0; k < NAVI_DIM; k++) o[OBS_EGO + k] = navi[k];
+}
+
+// BaseVehicle.after_step for one vehicle (component/vehicle/base_vehicle.py:234-271): localisation, state check
+// against the static world and the env's other bodies, side distances, energy.  `nb` = the env's footprints.
+__device__ __forceinline__ void after_step_vehicle(const MapView& m, const float* St, float* C, int* I,
+                                                   const int* __restrict__ route, const int* __restrict__ rroad, float* navi,
+                                                   const Nb* nb, float* sobj, int S, int O, int slot, const Rect& r,
+                                                   int* obj_first) {
+    localise(m, St, I, route, rroad, navi);
+    int flags = I[VI_FLAGS];
+    state_check_static(m, r, flags);
+    flags |= dynamic_contacts(nb, sobj, S, O, slot, r, false, obj_first, false);
+    I[VI_FLAGS] = flags;
+    int cur_road = rroad[I[VI_CKPT0]];
+    int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+    float lon, lat;
+    lane_local(m.lane_f + cur_first * LANE_F, St[VS_POS], St[VS_POS + 1], lon, lat);
+    float lane_w = m.lane_f[I[VI_LANE] * LANE_F + LF_WIDTH];
+    float to_left = lat + lane_w / 2.0f;
+    float to_right = lane_w * (float)cur_n - to_left;
+    C[VC_DIST_L] = to_left; C[VC_DIST_R] = to_right;
+    if (to_right < 0.0f || to_left < 0.0f) I[VI_FLAGS] |= FL_OUT_OF_ROUTE;
+    float dx = C[VC_LAST_X] - St[VS_POS], dy = C[VC_LAST_Y] - St[VS_POS + 1];
+    float dist_km = sqrtf(dx * dx + dy * dy) / 1000.0f;
+    float speed_kmh = sqrtf(St[VS_VEL] * St[VS_VEL] + St[VS_VEL + 1] * St[VS_VEL + 1]) * 3.6f;
+    float step_energy = 3.25f * expf(0.01f * speed_kmh) * dist_km / 100.0f * 1000.0f;
+    C[VC_STEP_ENERGY] = step_energy;
+    C[VC_ENERGY] += step_energy;
 }
 
 __device__ __forceinline__ void load16(float* dst, const float* src) {
@@ -677,6 +710,16 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         const float* a = actions + ((size_t)env * G.NA + slot) * 2;
         act = actuate(P, St, C, a[0], a[1]);
         dirty = true;
+    }
+    // VehicleAgentManager.before_step, second half (manager/agent_manager.py:189-202): wrecks of finished agents stay
+    // in the world as static bodies for delay_done steps, then leave
+    if ((mode & MODE_AGENT_PRE) && cfg.is_multi_agent && is_agent) {
+        if (I[VI_NEW]) { I[VI_NEW] = 0; dirty = true; }
+        if (I[VI_ALIVE] && !I[VI_ACTIVE] && I[VI_DYING] > 0) {
+            I[VI_DYING] -= 1;
+            if (I[VI_DYING] <= 0) { I[VI_ALIVE] = 0; I[VI_STATIC] = 0; G.nb[slot].alive = 0; }
+            dirty = true;
+        }
     }
     __syncthreads();
     MapView m;
@@ -843,36 +886,35 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
                          ((mode & MODE_RESET) ? (is_agent || is_traffic) : (I[VI_ACTIVE] != 0));
     if (do_post) {
         if (mode & MODE_CLEAR_FLAGS) I[VI_FLAGS] = FL_ON_LANE;
-        localise(m, St, I, A.veh_route + (size_t)g * ROUTE_MAX, rroad, navi);
-        Rect r = G.nb[slot].r;
-        int flags = I[VI_FLAGS];
-        state_check_static(m, r, flags);
-        flags |= dynamic_contacts(G.nb, G.sobj, S, G.O, slot, r, false, G.obj_first, false);
-        I[VI_FLAGS] = flags;
-        int cur_road = rroad[I[VI_CKPT0]];
-        int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
-        float lon, lat;
-        lane_local(m.lane_f + cur_first * LANE_F, St[VS_POS], St[VS_POS + 1], lon, lat);
-        float lane_w = m.lane_f[I[VI_LANE] * LANE_F + LF_WIDTH];
-        float to_left = lat + lane_w / 2.0f;
-        float to_right = lane_w * (float)cur_n - to_left;
-        C[VC_DIST_L] = to_left; C[VC_DIST_R] = to_right;
-        if (to_right < 0.0f || to_left < 0.0f) I[VI_FLAGS] |= FL_OUT_OF_ROUTE;
-        float dx = C[VC_LAST_X] - St[VS_POS], dy = C[VC_LAST_Y] - St[VS_POS + 1];
-        float dist_km = sqrtf(dx * dx + dy * dy) / 1000.0f;
-        float speed_kmh = sqrtf(St[VS_VEL] * St[VS_VEL] + St[VS_VEL + 1] * St[VS_VEL + 1]) * 3.6f;
-        float step_energy = 3.25f * expf(0.01f * speed_kmh) * dist_km / 100.0f * 1000.0f;
-        C[VC_STEP_ENERGY] = step_energy;
-        C[VC_ENERGY] += step_energy;
+        after_step_vehicle(m, St, C, I, A.veh_route + (size_t)g * ROUTE_MAX, rroad, navi, G.nb, G.sobj, S, G.O, slot,
+                           G.nb[slot].r, G.obj_first);
         if ((mode & MODE_RESET) && !I[VI_ACTIVE]) I[VI_FLAGS] = FL_ON_LANE;  // reset() ends with _init_step_info
     }
     // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111)
     if ((mode & MODE_REMOVE) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE] && !(I[VI_FLAGS] & FL_ON_LANE)) {
         I[VI_ALIVE] = 0; I[VI_ACTIVE] = 0;
     }
+    // every agent observes the world as it is after engine.after_step: a vehicle that finishes this step is still
+    // visible to the others' lidar (the body row keeps the pre-finish alive flag; k_respawn clears it afterwards)
+    const int alive_row = occ ? I[VI_ALIVE] : 0;
+    if ((mode & MODE_OUT) && cfg.is_multi_agent && G.work && slot < G.NA && !(is_agent && I[VI_ACTIVE])) {
+        size_t a = (size_t)env * G.NA + slot;  // an empty or wrecked seat produces no transition
+        out.reward[a] = 0.0f; out.cost[a] = 0.0f; out.term[a] = 0; out.trunc[a] = 0; out.info_flags[a] = 0;
+    }
     if ((mode & (MODE_OUT | MODE_RESET)) && is_agent && I[VI_ACTIVE] && slot < G.NA) {
         size_t a = (size_t)env * G.NA + slot;
         agent_outputs(cfg, m, env_step, P, St, C, I, rroad, navi, a, out, (mode & MODE_OUT) != 0);
+        if ((mode & MODE_OUT) && cfg.is_multi_agent) {
+            // MultiAgentMetaDrive._after_vehicle_done -> agent_manager._finish (multi_agent_metadrive.py:153-166,
+            // agent_manager.py:115-128): success leaves at once, everything else becomes a static wreck
+            const int fl = out.info_flags[a];
+            out.info_flags[a] = fl | FL_VALID;
+            if (out.term[a] || out.trunc[a]) {
+                I[VI_ACTIVE] = 0;
+                if ((fl & FL_ARRIVE) || cfg.delay_done <= 0) { I[VI_ALIVE] = 0; }
+                else { I[VI_STATIC] = 1; I[VI_DYING] = cfg.delay_done; }
+            }
+        }
     }
     if (occ) {
         if (do_post) {  // vehicles that were not localised this step have nothing new to store
@@ -881,7 +923,7 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
 #pragma unroll
             for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = navi[k];
         }
-        write_body_row(body_tab + (size_t)g * BODY_ROW, P, St, I[VI_ALIVE]);
+        write_body_row(body_tab + (size_t)g * BODY_ROW, P, St, alive_row);
     }
 }
 
@@ -907,6 +949,14 @@ __global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t
     for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = snap.obj_f[(size_t)env * O * OBJ_F + k];
     if (slot == 0)
         for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = snap.env_i[env * ENV_I + k];
+    if (cfg.is_multi_agent && slot < cfg.agents_per_env) {  // respawns rewrite the seat's route
+        const int4* r4 = reinterpret_cast<const int4*>(snap.veh_route + (size_t)g * ROUTE_MAX);
+        const int4* q4 = reinterpret_cast<const int4*>(snap.veh_rroad + (size_t)g * ROUTE_MAX);
+        int4* dr = reinterpret_cast<int4*>(A.veh_route + (size_t)g * ROUTE_MAX);
+        int4* dq = reinterpret_cast<int4*>(A.veh_rroad + (size_t)g * ROUTE_MAX);
+#pragma unroll
+        for (int k = 0; k < ROUTE_MAX / 4; k++) { dr[k] = r4[k]; dq[k] = q4[k]; }
+    }
 }
 
 // ================================================================================================ k_lidar
@@ -946,7 +996,8 @@ __host__ __device__ inline size_t lidar_smem_per_warp(int S, int O) {
 // conservative bounding-circle test prunes the (ray, body) pairs instead.
 __global__ void __launch_bounds__(LIDAR_WARPS * 32)
 k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restrict__ obj_f, const int* __restrict__ veh_i,
-        float* __restrict__ out, int out_stride, int out_off, int* __restrict__ hit_out, const uint8_t* __restrict__ env_mask) {
+        float* __restrict__ out, int out_stride, int out_off, int* __restrict__ hit_out, const uint8_t* __restrict__ env_mask,
+        const int* __restrict__ agent_flags, int need_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env, N = cfg.n_lasers;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -962,7 +1013,10 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     if (a >= (long long)cfg.n_envs * NA) return;
     const int env = (int)(a / NA), slot = (int)(a - (long long)env * NA);
     if (env_mask != nullptr && env_mask[env] == 0) return;
-    if (!veh_i[(size_t)(env * S + slot) * VEH_I + VI_ACTIVE]) return;
+    // who observes: the active agents; in a multi-agent step the seats that produced a transition (FL_VALID: an agent that
+    // finished this step still gets its last observation) or, in the respawn pass, the newborn seats (FL_NEWBORN)
+    if (agent_flags != nullptr) { if (!(agent_flags[a] & need_flag)) return; }
+    else if (!veh_i[(size_t)(env * S + slot) * VEH_I + VI_ACTIVE]) return;
 
     // stage the env's body rows and object rows: one bulk async copy (TMA 1-D) each, completing on the warp's mbarrier
     if (lane == 0) {
@@ -1059,16 +1113,153 @@ __global__ void k_done_mask(MdConfig cfg, const uint8_t* __restrict__ term, cons
     mask[e] = any_running ? 0 : 1;
 }
 
+// multi-agent: an env is over when no seat is active any more (after this step's respawn)
+__global__ void k_done_mask_ma(MdConfig cfg, const int* __restrict__ veh_i, uint8_t* __restrict__ mask) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cfg.n_envs) return;
+    bool any_active = false;
+    for (int s = 0; s < cfg.agents_per_env; s++)
+        if (veh_i[(size_t)(e * cfg.slots_per_env + s) * VEH_I + VI_ACTIVE]) any_active = true;
+    mask[e] = any_active ? 0 : 1;
+}
+
+// ---- k_respawn: MultiAgentMetaDrive._respawn_vehicles (envs/marl_envs/multi_agent_metadrive.py:133-135, 176-212) -----
+// One warp per env, after every agent has observed.  The lanes rebuild the env's footprints in shared memory and clear
+// the body rows of the vehicles that left this step; lane p tests safe place p (8 x 3 m region, spawn_manager.py:163-209)
+// against all of them; lane 0 then draws place + destination from the env's random tape and runs the newborn's
+// BaseVehicle.reset + after_step + first observation (agent_manager.py:136-154).  At most one respawn per env per step,
+// as in the reference (every clear place is marked used by the first query of a step).
+#define RESPAWN_WARPS 4
+__device__ __forceinline__ uint32_t tape_draw(const MdConfig& cfg, const int* __restrict__ tape, int env, uint32_t ctr, int j) {
+    const uint32_t L = (uint32_t)cfg.ma_tape_len;
+    uint32_t v = (uint32_t)tape[((size_t)env * L + ctr % L) * 2 + j];
+    const uint32_t lap = ctr / L;
+    if (lap) {  // the tape has wrapped: perturb it with a counter hash so that a long run does not repeat itself
+        uint32_t x = (uint32_t)env * 0x9E3779B9u + (lap * 2u + (uint32_t)j) * 0x85EBCA6Bu + 0x165667B1u;
+        x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+        v += x;
+    }
+    return v;
+}
+__global__ void __launch_bounds__(RESPAWN_WARPS * 32)
+k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * RESPAWN_WARPS + warp;
+    if (env >= cfg.n_envs) return;
+    Nb* nb = reinterpret_cast<Nb*>(smem_raw) + (size_t)warp * S;
+    int n_alive = 0, seat = 0x7fffffff;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + lane;
+        int alive = 0, free_seat = 0;
+        if (s < S) {
+            const size_t g = (size_t)env * S + s;
+            const int* I = A.veh_i + g * VEH_I;
+            alive = I[VI_ALIVE];
+            nb[s].alive = alive; nb[s].kind = I[VI_KIND];
+            if (alive) {
+                float P[VEH_P], St[VEH_S];
+                load16(P, A.veh_p + g * VEH_P);
+                load16(St, A.veh_s + g * VEH_S);
+                nb[s].r = vehicle_rect(P, St);
+            } else if (I[VI_KIND] != 0) body_tab[g * BODY_ROW + 15] = 0.0f;  // it left the world this step (or earlier)
+            free_seat = s < NA && I[VI_KIND] == 1 && !alive && !(out.info_flags[(size_t)env * NA + s] & FL_VALID);
+        }
+        const unsigned am = __ballot_sync(0xffffffffu, alive && s < NA);
+        const unsigned fm = __ballot_sync(0xffffffffu, free_seat);
+        n_alive += __popc(am);
+        if (fm && seat == 0x7fffffff) seat = s0 + __ffs(fm) - 1;
+    }
+    __syncwarp();
+    int* E = A.env_i + (size_t)env * ENV_I;
+    const bool allowed = cfg.allow_respawn && !(cfg.horizon > 0 && E[EI_STEP] >= cfg.horizon) &&
+                         seat != 0x7fffffff && n_alive < NA - 1;
+    if (!allowed) return;
+    // rect_region_detection per safe place (utils/pg/utils.py:213-256): lane p <-> place p (+32, ...)
+    unsigned long long clear_mask = 0ull;
+    for (int p0 = 0; p0 < cfg.ma_places && p0 < 64; p0 += 32) {
+        const int p = p0 + lane;
+        bool clear = false;
+        if (p < cfg.ma_places) {
+            const float4* Pl = reinterpret_cast<const float4*>(A.ma_place_f + ((size_t)env * cfg.ma_places + p) * 8);
+            const float4 a = Pl[0], b = Pl[1];
+            Rect pr;
+            pr.cx = a.x; pr.cy = a.y; pr.ux = b.y; pr.uy = b.z; pr.hu = 4.0f; pr.hv = 1.5f;
+            clear = true;
+            for (int k = 0; k < S; k++)
+                if (nb[k].alive && rect_rect(pr, nb[k].r)) { clear = false; break; }
+        }
+        clear_mask |= (unsigned long long)__ballot_sync(0xffffffffu, clear) << p0;
+    }
+    if (lane != 0 || clear_mask == 0ull) return;
+    const int n_clear = __popcll(clear_mask);
+    const uint32_t ctr = (uint32_t)E[EI_RNG];
+    int pick = (int)(tape_draw(cfg, A.ma_tape, env, ctr, 0) % (uint32_t)n_clear);
+    const int dsel = (int)(tape_draw(cfg, A.ma_tape, env, ctr, 1) % (uint32_t)cfg.ma_dests);
+    E[EI_RNG] = (int)(ctr + 1u);
+    int p = 0;
+    for (unsigned long long mk = clear_mask;; mk &= mk - 1) {  // the pick-th clear place
+        p = __ffsll((long long)mk) - 1;
+        if (pick-- == 0) break;
+    }
+    const float* Pl = A.ma_place_f + ((size_t)env * cfg.ma_places + p) * 8;
+    const size_t g = (size_t)env * S + seat;
+    float P[VEH_P], St[VEH_S], C[VEH_C], navi[NAVI_DIM];
+    int I[VEH_I];
+    load16(P, A.veh_p + g * VEH_P);
+    // BaseVehicle.reset (component/vehicle/base_vehicle.py:273-381): pose on the lane, height H/2, everything else zeroed
+#pragma unroll
+    for (int k = 0; k < VEH_S; k++) St[k] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < VEH_C; k++) C[k] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < VEH_I; k++) I[k] = 0;
+#pragma unroll
+    for (int k = 0; k < NAVI_DIM; k++) navi[k] = 0.0f;
+    St[VS_POS] = Pl[0]; St[VS_POS + 1] = Pl[1]; St[VS_POS + 2] = 0.5f * P[VP_HEIGHT];
+    St[VS_QUAT] = Pl[2]; St[VS_QUAT + 3] = Pl[3];
+    const int rsel = (int)Pl[7] * cfg.ma_dests + dsel;
+    const int* rt = A.ma_route + ((size_t)env * cfg.ma_roads * cfg.ma_dests + rsel) * ROUTE_MAX;
+    const int* rr = A.ma_rroad + ((size_t)env * cfg.ma_roads * cfg.ma_dests + rsel) * ROUTE_MAX;
+    int* vr = A.veh_route + g * ROUTE_MAX;
+    int* vrr = A.veh_rroad + g * ROUTE_MAX;
+    int n_ck = 0;
+    for (int k = 0; k < ROUTE_MAX; k++) { const int c = rt[k]; vr[k] = c; vrr[k] = rr[k]; if (c >= 0) n_ck++; }
+    I[VI_KIND] = 1; I[VI_ALIVE] = 1; I[VI_ACTIVE] = 1; I[VI_TRIGGER] = -1;
+    I[VI_LANE] = (int)Pl[4]; I[VI_SPAWN_LANE] = (int)Pl[4];
+    I[VI_CKPT0] = 0; I[VI_CKPT1] = n_ck > 2 ? 1 : 0; I[VI_ROUTE_LEN] = n_ck;
+    I[VI_ROUTING_LANE] = -1; I[VI_NEW] = 1;
+    latch_before_step(St, C, I);
+    nb[seat].alive = 1; nb[seat].r = vehicle_rect(P, St);
+    const MapView m = map_view(A, E[EI_MAP]);
+    after_step_vehicle(m, St, C, I, vr, vrr, navi, nb, A.obj_f + (size_t)env * O * OBJ_F, S, O, seat, nb[seat].r, nullptr);
+    const size_t a = (size_t)env * NA + seat;
+    agent_outputs(cfg, m, E[EI_STEP], P, St, C, I, vrr, navi, a, out, false);
+    // a newborn agent: reward 0, not done, first observation (multi_agent_metadrive.py:137-144)
+    out.reward[a] = 0.0f; out.cost[a] = 0.0f; out.term[a] = 0; out.trunc[a] = 0;
+    out.info_flags[a] = (I[VI_FLAGS] & 0x3ff) | FL_VALID | FL_NEWBORN;
+    float4* inf = reinterpret_cast<float4*>(out.info_f + a * 8);
+    inf[0] = make_float4(0.0f, 0.0f, 0.0f, C[VC_STEP_ENERGY]);
+    inf[1] = make_float4(C[VC_ENERGY], 0.0f, 0.0f, 0.0f);
+    store16(A.veh_s + g * VEH_S, St);
+    store16(A.veh_c + g * VEH_C, C);
+    store16i(A.veh_i + g * VEH_I, I);
+#pragma unroll
+    for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[g * NAVI_DIM + k] = navi[k];
+    write_body_row(body_tab + g * BODY_ROW, P, St, 1);
+}
+
 // ================================================================================================ host side / C ABI
 struct md_sim {
     MdConfig cfg;
     int device;
     std::string err;
     MdArrays dev;           // device pointers
-    int64_t rows[24];
-    size_t bytes[24];
+    int64_t rows[28];
+    size_t bytes[28];
     Snapshot snap;
-    void* snap_bufs[7];
+    void* snap_bufs[9];
     float* body_tab;
     float4* veh_act;        // [NV] steering rad, engine force, brake: k_pre -> k_dyn
     uint8_t* mask;
@@ -1087,15 +1278,16 @@ struct md_sim {
     int prof_cap, prof_n;
 };
 
-#define N_ARR 24
+#define N_ARR 28
 static const char* kNames[N_ARR] = {"map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f",
                                     "quad_f", "grid_start", "grid_items", "env_i", "env_trigger", "veh_p", "veh_s", "veh_c",
                                     "veh_i", "veh_route", "veh_idm", "veh_navi", "obj_f", "lgrid_start", "lgrid_items",
-                                    "veh_rroad"};
+                                    "veh_rroad", "ma_place_f", "ma_route", "ma_rroad", "ma_tape"};
 static const int kRowBytes[N_ARR] = {MAPD * 4, MAPDF * 4, LANE_F * 4, LANE_I * 4, 16, ROAD_I * 4, 8, LINE_F * 4, QUAD_F * 4, 4, 4,
                                      ENV_I * 4, TRIGGER_MAX * 4, VEH_P * 4, VEH_S * 4, VEH_C * 4, VEH_I * 4, ROUTE_MAX * 4,
-                                     VEH_IDM * 4, NAVI_DIM * 4, OBJ_F * 4, 4, 4, ROUTE_MAX * 4};
-static const int kSnapIdx[7] = {11, 14, 15, 16, 18, 19, 20};  // env_i veh_s veh_c veh_i veh_idm veh_navi obj_f
+                                     VEH_IDM * 4, NAVI_DIM * 4, OBJ_F * 4, 4, 4, ROUTE_MAX * 4, 32, ROUTE_MAX * 4, ROUTE_MAX * 4, 8};
+#define N_SNAP 9
+static const int kSnapIdx[N_SNAP] = {11, 14, 15, 16, 18, 19, 20, 17, 23};  // env_i veh_s veh_c veh_i veh_idm veh_navi obj_f veh_route veh_rroad
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -1152,7 +1344,7 @@ extern "C" void md_destroy(md_sim* sim) {
     cudaSetDevice(sim->device);
     if (sim->loaded) {
         for (int i = 0; i < N_ARR; i++) cudaFree(*arr_slot(&sim->dev, i));
-        for (int i = 0; i < 7; i++) cudaFree(sim->snap_bufs[i]);
+        for (int i = 0; i < N_SNAP; i++) cudaFree(sim->snap_bufs[i]);
         cudaFree(sim->body_tab); cudaFree(sim->veh_act); cudaFree(sim->mask);
         cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_reward); cudaFreeHost(sim->h_cost);
         cudaFreeHost(sim->h_info_f); cudaFreeHost(sim->h_term); cudaFreeHost(sim->h_trunc); cudaFreeHost(sim->h_mask);
@@ -1172,13 +1364,15 @@ static int set_snapshot_ptrs(md_sim* sim) {
     sim->snap.veh_idm = (const float*)sim->snap_bufs[4];
     sim->snap.veh_navi = (const float*)sim->snap_bufs[5];
     sim->snap.obj_f = (const float*)sim->snap_bufs[6];
+    sim->snap.veh_route = (const int*)sim->snap_bufs[7];
+    sim->snap.veh_rroad = (const int*)sim->snap_bufs[8];
     return 0;
 }
 
 extern "C" int md_snapshot(md_sim* sim) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
-    for (int k = 0; k < 7; k++)
+    for (int k = 0; k < N_SNAP; k++)
         CK(cudaMemcpy(sim->snap_bufs[k], *arr_slot(&sim->dev, kSnapIdx[k]), sim->bytes[kSnapIdx[k]], cudaMemcpyDeviceToDevice));
     return 0;
 }
@@ -1202,7 +1396,7 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
         if (sim->bytes[i]) CK(cudaMemcpy(d, h, sim->bytes[i], cudaMemcpyHostToDevice));
         *arr_slot(&sim->dev, i) = d;
     }
-    for (int k = 0; k < 7; k++) CK(cudaMalloc(&sim->snap_bufs[k], sim->bytes[kSnapIdx[k]] ? sim->bytes[kSnapIdx[k]] : 16));
+    for (int k = 0; k < N_SNAP; k++) CK(cudaMalloc(&sim->snap_bufs[k], sim->bytes[kSnapIdx[k]] ? sim->bytes[kSnapIdx[k]] : 16));
     set_snapshot_ptrs(sim);
     CK(cudaMalloc(&sim->body_tab, (size_t)NV * BODY_ROW * 4));
     CK(cudaMemset(sim->body_tab, 0, (size_t)NV * BODY_ROW * 4));
@@ -1337,12 +1531,23 @@ static int launch_restore(md_sim* sim, const uint8_t* mask, cudaStream_t st) {
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* hit, const uint8_t* mask, cudaStream_t st) {
+static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* hit, const uint8_t* mask, cudaStream_t st,
+                        const int* agent_flags = nullptr, int need_flag = 0) {
     const MdConfig& c = sim->cfg;
     long long na = (long long)c.n_envs * c.agents_per_env;
     int blocks = (int)((na + LIDAR_WARPS - 1) / LIDAR_WARPS);
     size_t smem = lidar_smem_per_warp(c.slots_per_env, c.objs_per_env) * LIDAR_WARPS;
-    k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, out, stride, off, hit, mask);
+    k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, out, stride, off, hit, mask,
+                                                    agent_flags, need_flag);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_respawn(md_sim* sim, StepOut out, cudaStream_t st) {
+    const MdConfig& c = sim->cfg;
+    int blocks = (c.n_envs + RESPAWN_WARPS - 1) / RESPAWN_WARPS;
+    size_t smem = sizeof(Nb) * (size_t)c.slots_per_env * RESPAWN_WARPS;
+    k_respawn<<<blocks, RESPAWN_WARPS * 32, smem, st>>>(c, sim->dev, out, sim->body_tab);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1373,7 +1578,18 @@ extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, fl
     if (prof) CK(cudaEventRecord(ev[2], st));
     if (launch_post(sim, MODE_POST | MODE_OUT | MODE_REMOVE, out, nullptr, st)) return -1;
     if (prof) CK(cudaEventRecord(ev[3], st));
-    if (launch_lidar(sim, obs_dev, OBS_STATE + sim->cfg.n_lasers, OBS_STATE, nullptr, nullptr, st)) return -1;
+    const int od = OBS_STATE + sim->cfg.n_lasers;
+    if (!sim->cfg.is_multi_agent) {
+        if (launch_lidar(sim, obs_dev, od, OBS_STATE, nullptr, nullptr, st)) return -1;
+    } else {
+        // multi-agent: everyone who produced a transition observes (incl. agents that just finished), then finished
+        // vehicles leave / freeze, at most one agent per env is respawned and observes the world after that
+        if (!info_flags_dev) { sim->err = "multi-agent md_step needs info_flags"; return -2; }
+        if (launch_lidar(sim, obs_dev, od, OBS_STATE, nullptr, nullptr, st, info_flags_dev, FL_VALID)) return -1;
+        if (launch_respawn(sim, out, st)) return -1;
+        if (sim->cfg.allow_respawn && launch_lidar(sim, obs_dev, od, OBS_STATE, nullptr, nullptr, st, info_flags_dev, FL_NEWBORN))
+            return -1;
+    }
     if (prof) { CK(cudaEventRecord(ev[4], st)); sim->prof_n++; }
     return 0;
 }
@@ -1409,7 +1625,10 @@ extern "C" int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const ui
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     cudaStream_t st = (cudaStream_t)stream;
-    k_done_mask<<<(sim->cfg.n_envs + 255) / 256, 256, 0, st>>>(sim->cfg, terminated_dev, truncated_dev, sim->mask);
+    if (sim->cfg.is_multi_agent)
+        k_done_mask_ma<<<(sim->cfg.n_envs + 255) / 256, 256, 0, st>>>(sim->cfg, sim->dev.veh_i, sim->mask);
+    else
+        k_done_mask<<<(sim->cfg.n_envs + 255) / 256, 256, 0, st>>>(sim->cfg, terminated_dev, truncated_dev, sim->mask);
     sim->launches++;
     CK(cudaGetLastError());
     return md_reset(sim, sim->mask, obs_dev, stream);

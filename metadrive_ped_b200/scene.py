@@ -105,11 +105,12 @@ def lane_polygon(row):
     return np.array(pts)
 
 
-HULL_EPS = 1e-7  # m^2; drops the (numerically) collinear samples along straight edges
+HULL_TOL = 1e-6  # m; a hull vertex closer than this to the chord of its neighbours is a sample on a straight edge
 
 
 def convex_hull(points):
-    """Andrew monotone chain; CCW, collinear points dropped (cross <= HULL_EPS)."""
+    """Andrew monotone chain (exact turn test, so the order of nearly-equal abscissae cannot drop a corner), then the
+    samples lying on straight edges are removed by their distance to the chord of their neighbours.  CCW."""
     pts = sorted(set((float(p[0]), float(p[1])) for p in points))
     if len(pts) <= 2:
         return np.array(pts)
@@ -119,14 +120,25 @@ def convex_hull(points):
 
     lower, upper = [], []
     for p in pts:
-        while len(lower) >= 2 and cross(lower[-2], lower[-1], p) <= HULL_EPS:
+        while len(lower) >= 2 and cross(lower[-2], lower[-1], p) <= 0.0:
             lower.pop()
         lower.append(p)
     for p in reversed(pts):
-        while len(upper) >= 2 and cross(upper[-2], upper[-1], p) <= HULL_EPS:
+        while len(upper) >= 2 and cross(upper[-2], upper[-1], p) <= 0.0:
             upper.pop()
         upper.append(p)
-    return np.array(lower[:-1] + upper[:-1])
+    hull = lower[:-1] + upper[:-1]
+    changed = True
+    while changed and len(hull) > 3:
+        changed = False
+        for i in range(len(hull)):
+            o, a, b = hull[i - 1], hull[i], hull[(i + 1) % len(hull)]
+            chord = math.hypot(b[0] - o[0], b[1] - o[1])
+            if chord == 0.0 or abs(cross(o, a, b)) / chord < HULL_TOL:
+                del hull[i]
+                changed = True
+                break
+    return np.array(hull)
 
 
 def _line_segments(row, lat, line_type):
@@ -334,7 +346,7 @@ class Scenario:
 
 
 def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int, agents_per_env: int,
-         objs_per_env: int):
+         objs_per_env: int, ma_tables=None, ma_tables_tape=None):
     """Concatenate maps + scenarios into the flat arrays of `MdArrays` (numpy, C-contiguous, f32/i32)."""
     M, E, S, O = len(maps), len(scenarios), slots_per_env, objs_per_env
     map_desc = np.zeros((M, MAPD), np.int32)
@@ -397,9 +409,18 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
         for b, blk in enumerate(blocks[:TRIGGER_MAX]):
             env_trigger[e, b] = blk["trigger_road"]
         n = len(sc.veh_static)
-        assert n <= S, (n, S)
-        assert int(np.sum(sc.veh_int[:, 0] == 1)) <= agents_per_env
-        sl = slice(e * S, e * S + n)
+        n_ag = int(np.sum(sc.veh_int[:, 0] == 1))
+        assert n_ag <= agents_per_env and np.all(sc.veh_int[:n_ag, 0] == 1), "agents come first in a roster"
+        assert n - n_ag + agents_per_env <= S, (n, agents_per_env, S)
+        # agents fill the first seats; everything else starts after the agent seats.  In a multi-agent world every
+        # seat exists from the start (kind 1, not alive) with the parameters of seat 0 (agent_manager.py:136-154
+        # builds respawned agents from agent_configs["agent0"])
+        sl = e * S + np.concatenate([np.arange(n_ag), agents_per_env + np.arange(n - n_ag)]).astype(np.int64)
+        if agents_per_env > 1:
+            seats = slice(e * S, e * S + agents_per_env)
+            veh_i[seats, 0] = 1
+            veh_i[seats, 3] = -1
+            veh_p[seats] = sc.veh_static[0]
         veh_p[sl] = sc.veh_static
         veh_s[sl, 0:13] = sc.veh_dyn[:, 0:13]
         veh_i[sl, 0] = sc.veh_int[:, 0]
@@ -419,7 +440,7 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
             for j in range(ROUTE_MAX - 1):
                 if rt[j] < 0 or rt[j + 1] < 0:
                     break
-                veh_rroad[e * S + k, j] = lut.get((int(rt[j]), int(rt[j + 1])), -1)
+                veh_rroad[sl[k], j] = lut.get((int(rt[j]), int(rt[j + 1])), -1)
         veh_idm[sl, 0] = sc.idm[:, 0]
         veh_idm[sl, 1] = sc.idm[:, 1]
         veh_c[sl, 0:2] = sc.veh_dyn[:, 0:2]
@@ -432,6 +453,38 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
             ob[:, 8] = sc.objects[:, 7]
             if sc.objects.shape[1] >= 10:
                 ob[:, 10:12] = sc.objects[:, 8:10]
+    # multi-agent respawn tables (metadrive_ped_b200/ma.py): per map id dict(places [P,8], routes [R*D, ROUTE_MAX]),
+    # replicated per env; ma_tape [E*L, 2] = the envs' random tapes
+    if ma_tables:
+        t0 = next(iter(ma_tables.values()))
+        P, RD = len(t0["places"]), len(t0["routes"])
+        ma_place_f = np.zeros((E * P, 8), np.float32)
+        ma_route = np.full((E * RD, ROUTE_MAX), -1, np.int32)
+        ma_rroad = np.full((E * RD, ROUTE_MAX), -1, np.int32)
+        per_map = {}
+        for mid, t in ma_tables.items():
+            pl = np.array(t["places"], np.float64)
+            rr = np.full((RD, ROUTE_MAX), -1, np.int32)
+            lut = road_lut[mid]
+            for k, rt in enumerate(t["routes"]):
+                for j in range(ROUTE_MAX - 1):
+                    if rt[j] < 0 or rt[j + 1] < 0:
+                        break
+                    rr[k, j] = lut.get((int(rt[j]), int(rt[j + 1])), -1)
+            per_map[mid] = (pl.astype(np.float32), np.asarray(t["routes"], np.int32), rr)
+        for e, sc in enumerate(scenarios):
+            pl, rt, rr = per_map[sc.map_id]
+            ma_place_f[e * P:(e + 1) * P] = pl
+            ma_route[e * RD:(e + 1) * RD] = rt
+            ma_rroad[e * RD:(e + 1) * RD] = rr
+        ma_tape = np.ascontiguousarray(ma_tables_tape, np.int32) if ma_tables_tape is not None else np.zeros((E, 2), np.int32)
+        assert ma_tape.shape[0] % E == 0 and ma_tape.shape[1] == 2
+    else:
+        ma_place_f = np.zeros((1, 8), np.float32)
+        ma_route = np.full((1, ROUTE_MAX), -1, np.int32)
+        ma_rroad = np.full((1, ROUTE_MAX), -1, np.int32)
+        ma_tape = np.zeros((1, 2), np.int32)
+    arrays.update(ma_place_f=ma_place_f, ma_route=ma_route, ma_rroad=ma_rroad, ma_tape=ma_tape)
     arrays.update(env_i=env_i, env_trigger=env_trigger, veh_p=veh_p, veh_s=veh_s, veh_c=veh_c, veh_i=veh_i,
                   veh_route=veh_route, veh_idm=veh_idm, veh_navi=veh_navi, obj_f=obj_f, veh_rroad=veh_rroad)
     return arrays
@@ -439,4 +492,5 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
 
 ARRAY_ORDER = ["map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f", "quad_f",
                "grid_start", "grid_items", "env_i", "env_trigger", "veh_p", "veh_s", "veh_c", "veh_i", "veh_route",
-               "veh_idm", "veh_navi", "obj_f", "lgrid_start", "lgrid_items", "veh_rroad"]
+               "veh_idm", "veh_navi", "obj_f", "lgrid_start", "lgrid_items", "veh_rroad", "ma_place_f", "ma_route",
+               "ma_rroad", "ma_tape"]

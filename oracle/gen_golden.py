@@ -86,11 +86,155 @@ def run_episode(env_cls, config, seed, actions, tag):
         env.close()
 
 
+def _lane_follow_action(v, rs, noise):
+    """Test-side driver for multi-agent traces: steer along the localised lane (slower on tight arcs), plus noise."""
+    lane = v.navigation.current_lane
+    lon, lat = lane.local_coordinates(v.position)
+    err = lane.heading_theta_at(lon + 2.0) - v.heading_theta
+    err = (err + np.pi) % (2 * np.pi) - np.pi
+    steer = 2.5 * err + 0.5 * lat + noise * rs.uniform(-1, 1)
+    tight = getattr(lane, "radius", 1e9) < 20
+    target = 16 if tight else 32
+    thr = (0.6 if v.speed_km_h < target else (-0.3 if v.speed_km_h > target + 6 else 0.0)) + noise * rs.uniform(-1, 1)
+    return [float(np.clip(steer, -1, 1)), float(np.clip(thr, -1, 1))]
+
+
+def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0, obs_stride=1):
+    """Multi-agent variant.  Seats: the reset-time agents take seats 0..n-1 and one spare seat follows; a respawned
+    agent takes the lowest seat that is free and produced no transition this step (what the product does).  Outputs are
+    padded per seat: valid[t, k] says whether seat k produced a transition at step t.  `actions` [T, n, 2] or None
+    (lane-follow driver with `noise`).  Respawn draws are recorded as (index in the list of clear places, destination
+    index) per step so that a replay can feed the same random tape."""
+    from oracle import ref_export as rx
+    env = env_cls(config)
+    rs = np.random.RandomState(seed)
+    try:
+        obs0, _ = env.reset()
+        eng = env.engine
+        m, mi = rx.export_map(env.current_map)
+        roster = rx.Roster(env, mi)
+        init = roster_arrays(env, mi, roster)
+        names = list(env.agents.keys())
+        n = len(names)
+        n_seats = n + 1
+        seat_of = {k: j for j, k in enumerate(names)}
+        seat_vehicle = [env.agents[k] for k in names] + [None]
+        seat_name = [v.name for v in seat_vehicle[:n]] + [None]  # engine recycles vehicle objects under new names
+        spawn_roads = list(env.config["spawn_roads"])
+        road_nodes = np.array([[mi.nodes[r.start_node], mi.nodes[r.end_node]] for r in spawn_roads], np.int32)
+        dest_nodes = np.array([mi.nodes[(-r).end_node] for r in spawn_roads], np.int32)
+        sm = eng.spawn_manager
+        place_keys = list(sm.safe_spawn_places.keys())
+        place_lane = [tuple(sm.safe_spawn_places[k]["config"]["spawn_lane_index"]) for k in place_keys]
+        first_query = []
+        orig = sm.get_available_respawn_places
+
+        def recording(*a, **kw):
+            ret = orig(*a, **kw)
+            if not first_query:
+                first_query.append(list(ret.keys()))
+            return ret
+
+        sm.get_available_respawn_places = recording
+
+        def world():
+            fs, is_ = [], []
+            for v, nm in zip(seat_vehicle, seat_name):
+                if v is None or v.name != nm:
+                    fs.append(np.zeros(rx.N_STEP_F)); is_.append(np.zeros(8, np.int32))
+                else:
+                    f, i = rx.record_vehicle(v, roster, env)
+                    fs.append(f); is_.append(i)
+            return np.stack(fs), np.stack(is_)
+
+        f0, i0 = world()
+        fs, is_ = [f0], [i0]
+        od = len(obs0[names[0]])
+        row0 = np.zeros((n_seats, od), np.float32)
+        row0[:n] = np.stack([obs0[k] for k in names])
+        obs = [row0]
+        T = steps if steps is not None else len(actions)
+        rew = np.zeros((T, n_seats)); cost = np.zeros((T, n_seats)); term = np.zeros((T, n_seats), bool)
+        trunc = np.zeros((T, n_seats), bool); valid = np.zeros((T, n_seats), bool); flags = np.zeros((T, n_seats), np.int32)
+        newborn = np.zeros((T, n_seats), bool)
+        acts = np.zeros((T, n_seats, 2))
+        draws = np.full((T, 3), -1, np.int32)  # clear-list index, destination index, number of clear places
+        routes_new = np.full((T, 24), -1, np.int32)
+        done_steps = 0
+        for t in range(T):
+            live = list(env.agents.keys())
+            if not live:
+                break
+            ad = {}
+            for k in live:
+                j = seat_of[k]
+                a = _lane_follow_action(env.agents[k], rs, noise) if actions is None else list(actions[t][j])
+                acts[t, j] = a
+                ad[k] = a
+            first_query.clear()
+            o, r, te, tr, info = env.step(ad)
+            old = [k for k in o if k in seat_of]
+            new = [k for k in o if k not in seat_of]
+            assert len(new) <= 1
+            for k in new:
+                v = env.agents[k]
+                free = [j for j in range(n_seats)
+                        if (seat_name[j] is None or seat_name[j] not in eng._spawned_objects)
+                        and not any(seat_of[q] == j for q in old)]
+                j = free[0]
+                seat_of[k] = j
+                seat_vehicle[j] = v
+                seat_name[j] = v.name
+                keys = first_query[0]
+                pk = place_keys[place_lane.index(tuple(v.config["spawn_lane_index"]))]
+                draws[t] = [keys.index(pk), int(np.nonzero(dest_nodes == mi.nodes[v.config["destination"]])[0][0]), len(keys)]
+                ck = v.navigation.checkpoints
+                routes_new[t, :len(ck)] = [mi.nodes[c] for c in ck]
+                newborn[t, j] = True
+            f, i = world()
+            fs.append(f); is_.append(i)
+            row = np.zeros((n_seats, od), np.float32)
+            for k, ob in o.items():
+                j = seat_of[k]
+                row[j] = ob; rew[t, j] = r[k]; cost[t, j] = info[k].get("cost", 0.0); term[t, j] = te[k]; trunc[t, j] = tr[k]
+                valid[t, j] = True
+                if not newborn[t, j]:
+                    flags[t, j] = (info[k]["crash_vehicle"] * 1 | info[k]["crash_object"] * 2 | info[k]["crash_building"] * 4
+                                   | info[k]["crash_human"] * 8 | info[k]["crash_sidewalk"] * 16
+                                   | info[k]["out_of_road"] * 0x400 | info[k]["arrive_dest"] * 0x800
+                                   | info[k]["max_step"] * 0x1000)
+            obs.append(row)
+            done_steps += 1
+        steps = done_steps
+        obs = np.stack(obs).astype(np.float32)
+        if obs_stride > 1:  # keep the fixture small: full observations for every obs_stride-th seat only
+            keep = np.zeros(n_seats, bool); keep[::obs_stride] = True
+            obs[:, ~keep, 19:] = -1.0
+        conf = {k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))}
+        conf["n_lasers"] = int(env.config["vehicle_config"]["lidar"]["num_lasers"])
+        conf["lidar_dist"] = float(env.config["vehicle_config"]["lidar"]["distance"])
+        out = dict(
+            tag=tag, seed=int(env.current_seed), lane_num=env.config["map_config"]["lane_num"],
+            map_lane_f=m["lane_f"], map_lane_i=m["lane_i"], map_road_i=m["road_i"], map_meta=m["meta"],
+            actions=acts[:steps], veh_f=np.stack(fs), veh_i=np.stack(is_), obs=obs, reward=rew[:steps], cost=cost[:steps],
+            terminated=term[:steps], truncated=trunc[:steps], valid=valid[:steps], newborn=newborn[:steps],
+            info_flags=flags[:steps], respawn_draws=draws[:steps], respawn_routes=routes_new[:steps],
+            ma_spawn_roads=road_nodes, ma_dest_nodes=dest_nodes, ma_alive_seats=np.array([n], np.int32),
+            config=json.dumps(conf), **{"init_" + k: v for k, v in init.items()},
+        )
+        out["ref_lines"] = rx.export_static_bodies(env.engine)["lines"]
+        return out
+    finally:
+        env.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--ma-steps", type=int, default=450)
+    ap.add_argument("--ma-noise", type=float, default=0.08)
     args = ap.parse_args()
     from oracle import refshim
     refshim.install()
@@ -118,6 +262,31 @@ def main():
         ("cfg4_safe_seed2", SafeMetaDriveEnv, dict(num_scenarios=20, start_seed=0, log_level=50), 2, smooth),
         ("cfg4_safe_seed5", SafeMetaDriveEnv, dict(num_scenarios=20, start_seed=0, log_level=50), 5, smooth),
     ]
+    # BASELINE config 3: MultiAgentRoundaboutEnv with 240-beam lidar
+    #   cfg3_ma_roundabout          40 agents, random actions, respawn off (crash / out-of-road / wreck bookkeeping)
+    #   cfg3_ma_roundabout_respawn  12 agents, lane-follow driver + noise, respawn on (arrivals, respawn, new routes)
+    if not args.only or args.only == "cfg3_ma_roundabout":
+        from metadrive.envs.marl_envs.marl_inout_roundabout import MultiAgentRoundaboutEnv
+        T = min(args.steps, 90)
+        rs = np.random.RandomState(3)
+        a = np.stack([0.2 * rs.uniform(-1, 1, (T, 41)), rs.uniform(0.0, 1.0, (T, 41))], -1)
+        lid = dict(vehicle_config=dict(lidar=dict(num_lasers=240, distance=50, num_others=0)))
+        cfg3 = dict(num_agents=40, allow_respawn=False, log_level=50, delay_done=25, horizon=1000, **lid)
+        out = run_episode_ma(MultiAgentRoundaboutEnv, cfg3, a, "cfg3_ma_roundabout", obs_stride=4)
+        path = os.path.join(args.out, "cfg3_ma_roundabout.npz")
+        np.savez_compressed(path, **out)
+        print("cfg3_ma_roundabout steps", len(out["reward"]), "seats", out["veh_f"].shape[1], "->",
+              os.path.getsize(path) // 1024, "KiB", flush=True)
+    if not args.only or args.only == "cfg3_ma_roundabout_respawn":
+        from metadrive.envs.marl_envs.marl_inout_roundabout import MultiAgentRoundaboutEnv
+        lid = dict(vehicle_config=dict(lidar=dict(num_lasers=240, distance=50, num_others=0)))
+        cfg3 = dict(num_agents=12, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, **lid)
+        out = run_episode_ma(MultiAgentRoundaboutEnv, cfg3, None, "cfg3_ma_roundabout_respawn", steps=args.ma_steps,
+                             noise=args.ma_noise, seed=5, obs_stride=3)
+        path = os.path.join(args.out, "cfg3_ma_roundabout_respawn.npz")
+        np.savez_compressed(path, **out)
+        print("cfg3_ma_roundabout_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
+              "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     for tag, cls, cfg, seed, acts in cases:
         if args.only and args.only not in tag:
             continue

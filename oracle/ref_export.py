@@ -262,13 +262,13 @@ def record_vehicle(v, roster, env):
        int row  : alive, active, lane_id, ckpt0, ckpt1, flags bitmask, routing_lane_id, ref_road"""
     eng = env.engine
     mi = roster.mi
-    alive = v.name in eng.get_objects([v.name])
+    alive = v.name in eng._spawned_objects  # engine.get_objects raises KeyError for a cleared name
     f = np.zeros(N_STEP_F)
     i = np.zeros(8, dtype=np.int32)
     if not alive:
         return f, i
     tm = getattr(eng, "traffic_manager", None)
-    active = (v in roster.agents) or (tm is not None and v in tm._traffic_vehicles)
+    active = (v.name in eng.agent_manager._active_objects) or (tm is not None and v in tm._traffic_vehicles)
     f[:N_DYN] = vehicle_dynamic(v)
     f[14] = v.steering
     f[15] = v.throttle_brake

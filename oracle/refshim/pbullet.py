@@ -341,6 +341,10 @@ class _RayHit:
 
     get_node = getNode
 
+    @property
+    def node(self):
+        return self._node
+
     def getHitFraction(self):
         return self._frac
 

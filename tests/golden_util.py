@@ -19,8 +19,54 @@ def load_golden(tag):
     return {k: d[k] for k in d.files}
 
 
+def is_ma(g):
+    return "ma_spawn_roads" in g
+
+
+# MULTI_AGENT_METADRIVE_DEFAULT_CONFIG (envs/marl_envs/multi_agent_metadrive.py:12-62)
+MA_CFG = dict(is_multi_agent=1, out_of_road_penalty=10.0, crash_vehicle_penalty=10.0, crash_object_penalty=10.0,
+              out_of_road_cost=0.0, truncate_as_terminate=1, horizon=1000, delay_done=25)
+
+
+def ma_tape_from_trace(g, length=256):
+    """The random tape that replays the respawn choices of the reference trace: the k-th respawn drew the
+    clear-list index draws[k, 0] and the destination draws[k, 1] (value % n == value since value < n)."""
+    tape = np.zeros((length, 2), np.int32)
+    ev = g["respawn_draws"][g["respawn_draws"][:, 0] >= 0]
+    assert len(ev) <= length
+    tape[:len(ev)] = ev[:, :2]
+    return tape
+
+
+def golden_world_ma(g, replicas=1, **cfg_kw):
+    """(arrays, cfg, geo) for `replicas` identical multi-agent envs: seats = reset-time agents + one spare."""
+    from metadrive_ped_b200 import ma
+    mt = sc.MapTable(np.asarray(g["map_lane_f"], np.float64), np.asarray(g["map_lane_i"], np.int32),
+                     np.asarray(g["map_road_i"], np.int32), json.loads(str(g["map_meta"])), int(g["lane_num"]))
+    geo = sc.build_map_geometry(mt)
+    n = int(g["ma_alive_seats"][0])
+    scen = sc.Scenario(0, g["init_veh_static"][:n], g["init_veh_dyn"][:n], g["init_routes"][:n], g["init_veh_int"][:n],
+                       g["init_idm"][:n], g["init_objects"], int(g["seed"]))
+    NA = n + 1
+    S = ((NA + 3) // 4) * 4
+    tables = ma.build_ma_tables(geo, g["ma_spawn_roads"], g["ma_dest_nodes"])
+    tape = np.tile(ma_tape_from_trace(g), (replicas, 1))
+    arrays = sc.pack([geo], [scen] * replicas, S, NA, 0, ma_tables={0: tables}, ma_tables_tape=tape)
+    conf = json.loads(str(g["config"]))
+    kw = dict(MA_CFG)
+    kw.update(horizon=int(conf.get("horizon", 1000)), delay_done=int(conf.get("delay_done", 25)),
+              allow_respawn=int(bool(conf.get("allow_respawn", True))), n_lasers=int(conf["n_lasers"]),
+              lidar_dist=float(conf["lidar_dist"]), ma_places=len(tables["places"]), ma_dests=tables["n_dests"],
+              ma_roads=tables["n_roads"], ma_tape_len=len(tape) // replicas)
+    kw.update(cfg_kw)
+    cfg = make_config(replicas, S, NA, 0, **kw)
+    return arrays, cfg, geo
+
+
 def golden_world(g, replicas=1, slots=None, objs=None, **cfg_kw):
     """(arrays, cfg) for `replicas` identical envs built from one golden fixture."""
+    if is_ma(g):
+        return golden_world_ma(g, replicas, **cfg_kw)
     mt = sc.MapTable(np.asarray(g["map_lane_f"], np.float64), np.asarray(g["map_lane_i"], np.int32),
                      np.asarray(g["map_road_i"], np.int32), json.loads(str(g["map_meta"])), int(g["lane_num"]))
     geo = sc.build_map_geometry(mt)

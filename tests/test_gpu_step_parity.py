@@ -20,7 +20,51 @@ def _make(tag, replicas):
     return g, cfg, BatchedSim(arrays, cfg), OracleSim(arrays, cfg), torch
 
 
-@pytest.mark.parametrize("tag", list_golden())
+SINGLE = [t for t in list_golden() if not t.startswith("cfg3")]
+MULTI = [t for t in list_golden() if t.startswith("cfg3")]
+
+
+@pytest.mark.parametrize("tag", MULTI)
+def test_multi_agent_step_matches_oracle_and_golden(tag, oracle_lib):
+    """BASELINE config 3 (MultiAgentRoundaboutEnv): the CUDA step incl. wrecks, arrivals and on-device respawn against
+    the oracle (integer state, seat flags, routes bit-exact) and against the reference trace (tests/test_oracle_golden)."""
+    from tests.test_oracle_golden import check_ma_step, grazes
+    g, cfg, sim, orc, torch = _make(tag, replicas=2)
+    NA = cfg.agents_per_env
+    obs_g = sim.reset().cpu().numpy()
+    obs_o = orc.reset_observe().copy()
+    live = orc.a["veh_i"].reshape(cfg.n_envs, cfg.slots_per_env, -1)[:, :NA, 2].reshape(-1) != 0
+    np.testing.assert_allclose(obs_g[live], obs_o[live], atol=1e-5, rtol=0)
+    grazes[0] = 0
+    for t in range(len(g["reward"])):
+        a = np.tile(g["actions"][t].astype(np.float32), (cfg.n_envs, 1, 1)).reshape(-1, 2)
+        sim.step(torch.from_numpy(a).cuda())
+        orc.step(a)
+        np.testing.assert_array_equal(sim.get_state("veh_i"), orc.a["veh_i"], err_msg="veh_i at step %d" % t)
+        np.testing.assert_array_equal(sim.get_state("veh_route"), orc.a["veh_route"], err_msg="routes at step %d" % t)
+        np.testing.assert_array_equal(sim.get_state("env_i"), orc.a["env_i"], err_msg="env_i at step %d" % t)
+        fl = sim.info_flags.cpu().numpy()
+        np.testing.assert_array_equal(fl, orc.info_flags)
+        np.testing.assert_array_equal(sim.terminated.cpu().numpy(), orc.term)
+        np.testing.assert_array_equal(sim.truncated.cpu().numpy(), orc.trunc)
+        vs_g, vs_o = sim.get_state("veh_s"), orc.a["veh_s"]
+        np.testing.assert_allclose(vs_g[:, 0:3], vs_o[:, 0:3], atol=2e-3, rtol=0)
+        np.testing.assert_allclose(vs_g[:, 3:7], vs_o[:, 3:7], atol=5e-4, rtol=0)
+        valid = (fl & 0x2000) != 0
+        og = sim.obs.cpu().numpy()
+        np.testing.assert_allclose(sim.reward.cpu().numpy(), orc.reward, atol=1e-4, rtol=0)
+        np.testing.assert_allclose(og[valid][:, :19], orc.obs[valid][:, :19], atol=2e-4, rtol=0)
+        bad = ~np.isclose(og[valid][:, 19:], orc.obs[valid][:, 19:], atol=2e-4, rtol=1e-4)
+        assert bad.sum(1).max(initial=0) <= 1 and bad.sum() <= 2, "lidar differs from the oracle at step %d" % t
+        # env 0 against the reference's own trace
+        check_ma_step(g, t, (vs_g, sim.get_state("veh_i")),
+                      (og, sim.reward.cpu().numpy(), sim.cost.cpu().numpy(), sim.terminated.cpu().numpy(),
+                       sim.truncated.cpu().numpy(), fl), tag)
+    assert grazes[0] <= 5
+    sim.close()
+
+
+@pytest.mark.parametrize("tag", SINGLE)
 def test_step_matches_oracle_and_golden(tag, oracle_lib):
     g, cfg, sim, orc, torch = _make(tag, replicas=3)
     n = g["veh_f"].shape[1]

@@ -4,7 +4,7 @@ action sequence; flags / lane ids / done exact, lidar 1e-4 relative, poses 1e-2 
 import numpy as np
 import pytest
 
-from tests.golden_util import golden_world, list_golden, load_golden
+from tests.golden_util import golden_world, is_ma, list_golden, load_golden
 
 # (fixture, vehicle slot, first step): float32-vs-float64 knife edges of the reference's own logic, excluded from
 # the pose comparison from that step on.  cfg2_pg3_seed11_dense: two same-type cars spawned at the same longitude on
@@ -13,7 +13,79 @@ from tests.golden_util import golden_world, list_golden, load_golden
 KNIFE_EDGES = {"cfg2_pg3_seed11_dense": {5: 24}}
 
 
-@pytest.mark.parametrize("tag", list_golden())
+SINGLE = [t for t in list_golden() if not t.startswith("cfg3")]
+MULTI = [t for t in list_golden() if t.startswith("cfg3")]
+
+
+grazes = [0]
+
+
+def check_ma_step(g, t, sim_state, out, tag, pose_tol=1e-2, obs_tol=2e-4):
+    """One multi-agent step of an implementation (`sim_state` = veh_s, veh_i; `out` = obs, reward, cost, term, trunc,
+    info_flags) against the reference trace: seat bookkeeping exact, poses / rewards / observations within tolerance."""
+    vs, vi = sim_state
+    obs, rew, cost, term, trunc, fl = out
+    n_seats = g["veh_f"].shape[1]
+    ref_f, ref_i = g["veh_f"][t + 1], g["veh_i"][t + 1]
+    np.testing.assert_array_equal(vi[:n_seats, 1], ref_i[:, 0], err_msg="alive @%d" % t)
+    np.testing.assert_array_equal(vi[:n_seats, 2], ref_i[:, 1], err_msg="active @%d" % t)
+    valid = g["valid"][t]
+    np.testing.assert_array_equal((fl[:n_seats] & 0x2000) != 0, valid, err_msg="valid seats @%d" % t)
+    np.testing.assert_array_equal((fl[:n_seats] & 0x4000) != 0, g["newborn"][t], err_msg="newborn seats @%d" % t)
+    for k in range(n_seats):
+        if ref_i[k, 0] == 1:
+            assert np.abs(vs[k, 0:3] - ref_f[k, 0:3]).max() < pose_tol, (tag, t, k)
+            dq = min(np.abs(vs[k, 3:7] - ref_f[k, 3:7]).max(), np.abs(vs[k, 3:7] + ref_f[k, 3:7]).max())
+            assert dq < 5e-4, (tag, t, k)
+            if ref_i[k, 1]:
+                assert vi[k, 4] == ref_i[k, 2], ("lane", tag, t, k)
+                np.testing.assert_array_equal(vi[k, 5:7], ref_i[k, 3:5])
+                assert (vi[k, 8] & 0x1ff) == (ref_i[k, 5] & 0x1ff), ("flags", tag, t, k, hex(vi[k, 8]), hex(ref_i[k, 5]))
+        if not valid[k]:
+            continue
+        assert abs(rew[k] - g["reward"][t, k]) < 1e-3, ("reward", tag, t, k, rew[k], g["reward"][t, k])
+        assert cost[k] == g["cost"][t, k]
+        assert bool(term[k]) == bool(g["terminated"][t, k]) and bool(trunc[k]) == bool(g["truncated"][t, k]), (tag, t, k)
+        if not g["newborn"][t, k]:
+            assert (fl[k] & 0x1c1f) == g["info_flags"][t, k], ("info", tag, t, k, hex(fl[k]), hex(g["info_flags"][t, k]))
+        ref_o = g["obs"][t + 1][k]
+        np.testing.assert_allclose(obs[k, :19], ref_o[:19], atol=5e-4, rtol=0, err_msg="state obs %d seat %d" % (t, k))
+        if ref_o[19] >= 0.0:  # lidar kept in the fixture for this seat
+            bad = ~np.isclose(obs[k, 19:], ref_o[19:], atol=obs_tol, rtol=1e-4)
+            # a ray through a box corner (entry and exit parameters equal to ~1e-7) is hit-or-miss at float32
+            # precision: at most one such ray per observation, a handful per trace
+            assert bad.sum() <= 1, "lidar %d seat %d: %d rays differ" % (t, k, bad.sum())
+            grazes[0] += int(bad.sum())
+
+
+@pytest.mark.parametrize("tag", MULTI)
+def test_oracle_replays_multi_agent_trace(tag, oracle_lib):
+    """BASELINE config 3 (MultiAgentRoundaboutEnv, 240-beam lidar): crash / out-of-road bookkeeping, wrecks kept for
+    delay_done steps, arrivals, respawn into free seats with the trace's place / destination draws."""
+    from oracle.oracle import OracleSim
+    g = load_golden(tag)
+    arrays, cfg, _ = golden_world(g)
+    sim = OracleSim(arrays, cfg)
+    n_seats = g["veh_f"].shape[1]
+    obs0 = sim.reset_observe().copy()
+    n0 = int(g["ma_alive_seats"][0])
+    np.testing.assert_allclose(obs0[:n0, :19], g["obs"][0][:n0, :19], atol=1e-5, rtol=0)
+    T = len(g["reward"])
+    n_respawn = 0
+    grazes[0] = 0
+    for t in range(T):
+        obs, r, te, tr = sim.step(g["actions"][t].astype(np.float32))
+        check_ma_step(g, t, (sim.a["veh_s"], sim.a["veh_i"]), (obs, r, sim.cost, te, tr, sim.info_flags), tag)
+        if g["respawn_draws"][t, 0] >= 0:  # the respawned agent got the reference's route
+            k = int(np.nonzero(g["newborn"][t])[0][0])
+            np.testing.assert_array_equal(sim.a["veh_route"][k], g["respawn_routes"][t])
+            n_respawn += 1
+    assert grazes[0] <= 5, "%d corner-grazing rays" % grazes[0]
+    if "respawn" in tag:
+        assert n_respawn >= 5 and ((g["info_flags"] & 0x800) != 0).sum() >= 3, "fixture must cover respawns and arrivals"
+
+
+@pytest.mark.parametrize("tag", SINGLE)
 def test_oracle_replays_reference_trace(tag, oracle_lib):
     from oracle.oracle import OracleSim
     g = load_golden(tag)
