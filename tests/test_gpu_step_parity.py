@@ -35,7 +35,7 @@ def test_multi_agent_step_matches_oracle_and_golden(tag, oracle_lib):
     obs_o = orc.reset_observe().copy()
     live = orc.a["veh_i"].reshape(cfg.n_envs, cfg.slots_per_env, -1)[:, :NA, 2].reshape(-1) != 0
     np.testing.assert_allclose(obs_g[live], obs_o[live], atol=1e-5, rtol=0)
-    grazes[0] = 0
+    grazes[0] = grazes[1] = 0
     for t in range(len(g["reward"])):
         a = np.tile(g["actions"][t].astype(np.float32), (cfg.n_envs, 1, 1)).reshape(-1, 2)
         sim.step(torch.from_numpy(a).cuda())
@@ -60,7 +60,7 @@ def test_multi_agent_step_matches_oracle_and_golden(tag, oracle_lib):
         check_ma_step(g, t, (vs_g, sim.get_state("veh_i")),
                       (og, sim.reward.cpu().numpy(), sim.cost.cpu().numpy(), sim.terminated.cpu().numpy(),
                        sim.truncated.cpu().numpy(), fl), tag)
-    assert grazes[0] <= 5
+    assert grazes[0] <= max(2, 5e-5 * grazes[1])
     sim.close()
 
 
