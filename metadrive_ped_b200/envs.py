@@ -66,6 +66,21 @@ def _box(low, high, shape):
         return Box(low, high, shape)
 
 
+class DictSpace:
+    """gymnasium.spaces.Dict stand-in for the multi-agent surface: `.spaces` keyed by agent id, `.contains(dict)`."""
+    def __init__(self, spaces):
+        self.spaces = dict(spaces)
+
+    def contains(self, x):
+        return isinstance(x, dict) and all(k in self.spaces and self.spaces[k].contains(np.asarray(v, np.float32))
+                                           for k, v in x.items())
+
+    __contains__ = contains
+
+    def sample(self):
+        return {k: s.sample() for k, s in self.spaces.items()}
+
+
 def _merge(default, user, path=""):
     out = dict(default)
     for k, v in (user or {}).items():
@@ -263,6 +278,178 @@ class BatchedMetaDriveEnv:
 
     def step(self, actions):
         obs, r, c, te, tr = self.sim.step(actions, autoreset=True)
+        return obs, r, te, tr, dict(cost=c, flags=self.sim.info_flags, scalars=self.sim.info_f)
+
+    def close(self):
+        self.sim.close()
+
+
+# ------------------------------------------------------------------------------------------------ multi-agent
+# MULTI_AGENT_METADRIVE_DEFAULT_CONFIG (envs/marl_envs/multi_agent_metadrive.py:12-62) on top of the MetaDriveEnv keys
+MA_DEFAULTS = dict(
+    is_multi_agent=True, num_agents=15, crash_done=True, out_of_road_done=True, delay_done=25, allow_respawn=True,
+    horizon=1000, out_of_road_penalty=10.0, crash_vehicle_penalty=10.0, crash_object_penalty=10.0,
+    crash_vehicle_cost=1.0, crash_object_cost=1.0, out_of_road_cost=0.0, traffic_density=0.0, truncate_as_terminate=True,
+    force_seed_spawn_manager=False,
+    vehicle_config=dict(lidar=dict(num_lasers=72, distance=40, num_others=0, gaussian_noise=0.0, dropout_prob=0.0,
+                                   add_others_navi=False),
+                        side_detector=dict(num_lasers=0, distance=50), lane_line_detector=dict(num_lasers=0, distance=20),
+                        enable_reverse=False, vehicle_model="static_default"),
+)
+
+
+def _ma_cfg_kw(c):
+    kw = MetaDriveEnv._cfg_kw(type("C", (), {"config": c})())
+    kw.update(delay_done=int(c["delay_done"]), allow_respawn=int(bool(c["allow_respawn"])),
+              ma_crash_done=int(bool(c["crash_done"])), ma_out_of_road_done=int(bool(c["out_of_road_done"])))
+    return kw
+
+
+class MultiAgentMetaDrive:
+    """Dict-keyed multi-agent surface (envs/marl_envs/multi_agent_metadrive.py:65-212) over one batched env.
+
+    Agent ids grow monotonically ("agent{k}", manager/agent_manager.py:156-159): a finished agent appears one last
+    time in the step that finished it; a respawned agent appears with reward 0 in the step that created it; terminated /
+    truncated carry "__all__" (:147-149).  Seats of the device simulation are mapped to ids on the host."""
+    ASSET = None
+    ENV_DEFAULTS = {}
+
+    @classmethod
+    def default_config(cls):
+        d = _merge(STEP_DEFAULTS, {k: v for k, v in MA_DEFAULTS.items() if k in STEP_DEFAULTS})
+        d.update({k: v for k, v in MA_DEFAULTS.items() if k not in STEP_DEFAULTS})
+        d["vehicle_config"] = _merge(STEP_DEFAULTS["vehicle_config"], MA_DEFAULTS["vehicle_config"])
+        d.update(cls.ENV_DEFAULTS)
+        return d
+
+    def __init__(self, config=None):
+        from .ma import MultiAgentLibrary
+        self.config = _merge(self.default_config(), config)
+        for k in UNSUPPORTED_TRUE:
+            if self.config[k]:
+                raise NotImplementedError("config['%s'] is outside the step path this build covers" % k)
+        if self.config["traffic_density"] != 0.0:
+            raise NotImplementedError("multi-agent envs with IDM traffic are not covered")
+        lid = self.config["vehicle_config"]["lidar"]
+        if lid["num_others"] != 0 or lid["gaussian_noise"] != 0 or lid["dropout_prob"] != 0:
+            raise NotImplementedError("lidar num_others / noise are not covered yet")
+        self._lib = MultiAgentLibrary(self.ASSET)
+        self.num_agents = self.config["num_agents"]
+        if self.num_agents == -1:
+            self.num_agents = self._lib.max_capacity
+        assert 0 < self.num_agents <= self._lib.max_capacity, \
+            "Too many agents! We only accept {} agents, but you have {} agents!".format(self._lib.max_capacity, self.num_agents)
+        self._obs_box = _box(-0.0, 1.0, (19 + lid["num_lasers"], ))
+        self._act_box = _box(-1.0, 1.0, (2, ))
+        self._seat_id = ["agent%d" % k for k in range(self.num_agents)] + [None]
+        self._active = set(self._seat_id[:self.num_agents])
+        self._sim = None
+        self._episode = 0
+        self.current_seed = self.config["start_seed"]
+
+    # -- gym surface
+    def reset(self, seed=None):
+        from .sim import BatchedSim
+        if self._sim is not None:
+            self._sim.close()
+        rs = (seed if seed is not None else self.config["start_seed"]) * 1000003 + self._episode
+        self._episode += 1
+        arrays, cfg = self._lib.build_world(1, self.num_agents, seed=rs, **_ma_cfg_kw(self.config))
+        self._sim = BatchedSim(arrays, cfg, device=self.config["device"])
+        self._seat_id = ["agent%d" % k for k in range(self.num_agents)] + [None]
+        self._next_id = self.num_agents
+        self._active = set(self._seat_id[:self.num_agents])
+        obs = self._sim.reset_host()
+        self.episode_step = 0
+        return ({self._seat_id[k]: obs[k].copy() for k in range(self.num_agents)},
+                {self._seat_id[k]: self._info(None) for k in range(self.num_agents)})
+
+    @property
+    def agents(self):
+        return {k: None for k in self._seat_id if k in self._active}
+
+    @property
+    def observation_space(self):
+        return DictSpace({k: self._obs_box for k in self.agents})
+
+    @property
+    def action_space(self):
+        return DictSpace({k: self._act_box for k in self.agents})
+
+    def step(self, actions):
+        assert self._sim is not None, "call reset() first"
+        NA = self.num_agents + 1
+        a = np.zeros((NA, 2), np.float32)
+        acting = {}
+        for k in range(NA):
+            aid = self._seat_id[k]
+            if aid in self._active:
+                assert aid in actions, "missing action for " + aid
+                a[k] = np.asarray(actions[aid], np.float32)
+                acting[k] = aid
+        obs, rew, cost, term, trunc, flags, info_f = self._sim.step_host(a, autoreset=False)
+        self.episode_step += 1
+        o, r, tm, tc, info = {}, {}, {}, {}, {}
+        for k in range(NA):
+            fl = int(flags[k])
+            if not fl & 0x2000:  # FL_VALID
+                continue
+            if fl & 0x4000:  # FL_NEWBORN: a fresh id takes the seat (agent_manager.py:136-159)
+                aid = "agent%d" % self._next_id
+                self._next_id += 1
+                self._seat_id[k] = aid
+                self._active.add(aid)
+                o[aid], r[aid], tm[aid], tc[aid] = obs[k].copy(), 0.0, False, False
+                info[aid] = self._info(None)
+                continue
+            aid = acting[k]
+            o[aid], r[aid], tm[aid], tc[aid] = obs[k].copy(), float(rew[k]), bool(term[k]), bool(trunc[k])
+            info[aid] = self._info((a[k], float(cost[k]), fl, info_f[k]))
+            if tm[aid] or tc[aid]:
+                self._active.discard(aid)
+        tc["__all__"] = all(tc.values())
+        tm["__all__"] = all(tm.values())
+        return o, r, tm, tc, info
+
+    _info = MetaDriveEnv._info
+
+    def close(self):
+        if self._sim is not None:
+            self._sim.close()
+            self._sim = None
+
+
+class MultiAgentRoundaboutEnv(MultiAgentMetaDrive):
+    """envs/marl_envs/marl_inout_roundabout.py:12-24, 145-153"""
+    ASSET = "ma_roundabout.npz"
+    ENV_DEFAULTS = dict(num_agents=40)
+
+
+class MultiAgentIntersectionEnv(MultiAgentMetaDrive):
+    """envs/marl_envs/marl_intersection.py:12-25, 98-108"""
+    ASSET = "ma_intersection.npz"
+    ENV_DEFAULTS = dict(num_agents=30)
+
+
+class BatchedMultiAgentEnv:
+    """E independent multi-agent envs per call, tensors in / tensors out: actions [E, seats, 2] -> obs [E*seats, 19+N],
+    reward / terminated / truncated [E*seats], info flags (FL_VALID marks the seats that produced a transition this step,
+    FL_NEWBORN the seats respawned this step).  seats = num_agents + 1.  Finished envs reset in place on device."""
+    def __init__(self, num_envs, config=None, env_cls=MultiAgentRoundaboutEnv, seed=0):
+        from .ma import MultiAgentLibrary
+        from .sim import BatchedSim
+        c = _merge(env_cls.default_config(), config)
+        lib = MultiAgentLibrary(env_cls.ASSET)
+        n = c["num_agents"] if c["num_agents"] != -1 else lib.max_capacity
+        arrays, cfg = lib.build_world(num_envs, n, seed=seed, **_ma_cfg_kw(c))
+        self.sim = BatchedSim(arrays, cfg, device=c["device"])
+        self.num_envs, self.seats = num_envs, n + 1
+
+    def reset(self):
+        return self.sim.reset()
+
+    def step(self, actions):
+        obs, r, c, te, tr = self.sim.step(actions.reshape(-1, 2), autoreset=True)
         return obs, r, te, tr, dict(cost=c, flags=self.sim.info_flags, scalars=self.sim.info_f)
 
     def close(self):

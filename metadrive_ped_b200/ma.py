@@ -78,3 +78,91 @@ def make_tape(n_envs, seed=0, length=TAPE_LEN):
     """[n_envs * length, 2] uniform 32-bit draws (place, destination) consumed in order by an env's respawns."""
     rng = np.random.default_rng(seed)
     return rng.integers(0, 2**31 - 1, size=(n_envs * length, 2), dtype=np.int64).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------- scenes at reset
+import json
+import os
+
+from .abi import make_config
+
+ASSET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+
+class MultiAgentLibrary:
+    """The fixed map of one multi-agent env (exported by oracle/gen_assets.py --env ma_*) plus what SpawnManager needs.
+
+    `scenario(rng)` restates SpawnManager.reset (manager/spawn_manager.py:72-115): num_agents of the available slots
+    (spawn road x lane x longitudinal slot) drawn without replacement, a random offset inside the slot
+    (`_randomize_position_in_slot`, :211-217) and a random destination per agent (marl_inout_roundabout.py:138-143).
+    The reference draws these from an unseeded generator; here the caller passes the generator."""
+    def __init__(self, name):
+        path = name if os.path.exists(name) else os.path.join(ASSET_DIR, name)
+        d = np.load(path, allow_pickle=False)
+        self.conf = json.loads(str(d["config"]))
+        if self.conf.get("disable_u_turn"):
+            raise NotImplementedError("destination draws without U-turns are not covered")
+        self.table = sc.MapTable(np.asarray(d["lane_f"], np.float64), np.asarray(d["lane_i"], np.int32),
+                                 np.asarray(d["road_i"], np.int32), json.loads(str(d["meta"])), int(self.conf["lane_num"]))
+        self.geo = sc.build_map_geometry(self.table)
+        self.spawn_roads = np.asarray(d["spawn_roads"], np.int32)
+        self.dest_nodes = np.asarray(d["dest_nodes"], np.int32)
+        self.veh_static = np.asarray(d["veh_static"], np.float32)
+        self.tables = build_ma_tables(self.geo, self.spawn_roads, self.dest_nodes)
+        c = self.conf
+        self.n_slots = int(math.floor((c["exit_length"] - c["entrance_length"]) / c["respawn_longitude"]))
+        road_key = {(int(r[0]), int(r[1])): k for k, r in enumerate(self.geo.road_i)}
+        self.slots = []  # (lane id, longitude, spawn-road index) in SpawnManager._auto_fill_spawn_roads_randomly order
+        for ri, (a, b) in enumerate(self.spawn_roads):
+            r = self.geo.road_i[road_key[(int(a), int(b))]]
+            for idx in range(int(c["lane_num"])):
+                for j in range(self.n_slots):
+                    self.slots.append((int(r[2]) + idx, c["respawn_longitude"] / 2 + j * c["respawn_longitude"], ri))
+
+    @property
+    def max_capacity(self):
+        return len(self.slots)
+
+    def scenario(self, rng, num_agents):
+        c = self.conf
+        assert 0 < num_agents <= self.max_capacity, \
+            "Too many agents! We only accept {} agents, but you have {} agents!".format(self.max_capacity, num_agents)
+        pick = rng.choice(len(self.slots), num_agents, replace=False)
+        D = len(self.dest_nodes)
+        dl = (c["respawn_longitude"] - c["max_vehicle_length"]) / 2
+        dw = (c["respawn_lateral"] - c["max_vehicle_width"]) / 2
+        H = float(self.veh_static[3])
+        veh_dyn = np.zeros((num_agents, 14), np.float64)
+        routes = np.full((num_agents, sc.ROUTE_MAX), -1, np.int32)
+        veh_int = np.zeros((num_agents, 6), np.int32)
+        for k, si in enumerate(pick):
+            lane, lon, ri = self.slots[int(si)]
+            lon = lon + rng.uniform(-dl, dl) if dl > 0 else lon + rng.uniform(dl, -dl)
+            lat = rng.uniform(-dw, dw) if dw > 0 else rng.uniform(dw, -dw)
+            row = self.geo.lane_f[lane]
+            x, y = sc.lane_position(row, lon, lat)
+            yaw = sc.lane_heading_at(row, lon) - math.pi / 2
+            veh_dyn[k, 0:3] = [x, y, H / 2]
+            veh_dyn[k, 3:7] = [math.cos(yaw / 2), 0.0, 0.0, math.sin(yaw / 2)]
+            d = int(rng.integers(0, D))
+            rt = self.tables["routes"][ri * D + d]
+            routes[k] = rt
+            n_ck = int((rt >= 0).sum())
+            veh_int[k] = [1, -1, lane, 0, 1 if n_ck > 2 else 0, 1]
+        static = np.tile(self.veh_static, (num_agents, 1))
+        idm = np.tile(np.array([[0.0, 30.0]], np.float32), (num_agents, 1))
+        return sc.Scenario(0, static, veh_dyn, routes, veh_int, idm, np.zeros((0, 8)), 0)
+
+    def build_world(self, n_envs, num_agents, seed=0, **cfg_kw):
+        """(arrays, cfg) for n_envs independent multi-agent envs: num_agents + 1 seats each (the spare seat keeps a
+        finished agent's last transition and a newborn's first observation on different rows)."""
+        rng = np.random.default_rng(seed)
+        scen = [self.scenario(rng, num_agents) for _ in range(n_envs)]
+        NA = num_agents + 1
+        S = ((NA + 3) // 4) * 4
+        tape = make_tape(n_envs, seed=seed + 1)
+        arrays = sc.pack([self.geo], scen, S, NA, 0, ma_tables={0: self.tables}, ma_tables_tape=tape)
+        kw = dict(is_multi_agent=1, ma_places=len(self.tables["places"]), ma_dests=self.tables["n_dests"],
+                  ma_roads=self.tables["n_roads"], ma_tape_len=TAPE_LEN)
+        kw.update(cfg_kw)
+        return arrays, make_config(n_envs, S, NA, 0, **kw)

@@ -19,9 +19,48 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def export_multi_agent(args):
+    """Multi-agent envs have one fixed map; what the product needs besides the lane graph: the spawn roads / destination
+    nodes (envs/marl_envs/marl_inout_roundabout.py:12-24, marl_intersection.py:12-25), the slot geometry constants of
+    SpawnManager (manager/spawn_manager.py:25-35, 117-158) and the parameters of the "static_default" vehicle."""
+    from oracle import ref_export as rx
+    from metadrive.component.pgblock.first_block import FirstPGBlock
+    from metadrive.manager.spawn_manager import SpawnManager
+    if args.env == "ma_roundabout":
+        from metadrive.envs.marl_envs.marl_inout_roundabout import MultiAgentRoundaboutEnv as cls
+    else:
+        from metadrive.envs.marl_envs.marl_intersection import MultiAgentIntersectionEnv as cls
+    env = cls(dict(log_level=50))
+    env.reset()
+    m, mi = rx.export_map(env.current_map)
+    roads = list(env.config["spawn_roads"])
+    v = next(iter(env.agents.values()))
+    conf = dict(
+        env=args.env, num_agents=int(env.config["num_agents"]), lane_num=int(env.config["map_config"]["lane_num"]),
+        exit_length=float(env.config["map_config"]["exit_length"]), entrance_length=float(FirstPGBlock.ENTRANCE_LENGTH),
+        respawn_longitude=float(SpawnManager.RESPAWN_REGION_LONGITUDE), respawn_lateral=float(SpawnManager.RESPAWN_REGION_LATERAL),
+        max_vehicle_length=float(SpawnManager.MAX_VEHICLE_LENGTH), max_vehicle_width=float(SpawnManager.MAX_VEHICLE_WIDTH),
+        disable_u_turn=bool(getattr(env.engine.spawn_manager, "disable_u_turn", False)),
+        defaults={k: env.config[k] for k in (
+            "horizon", "delay_done", "allow_respawn", "crash_done", "out_of_road_done", "out_of_road_penalty",
+            "crash_vehicle_penalty", "crash_object_penalty", "crash_vehicle_cost", "crash_object_cost", "out_of_road_cost",
+            "truncate_as_terminate", "success_reward", "driving_reward", "speed_reward", "traffic_density")},
+        lidar={k: env.config["vehicle_config"]["lidar"][k] for k in ("num_lasers", "distance", "num_others")},
+    )
+    out = dict(
+        lane_f=m["lane_f"], lane_i=m["lane_i"], road_i=m["road_i"], meta=m["meta"], config=json.dumps(conf),
+        spawn_roads=np.array([[mi.nodes[r.start_node], mi.nodes[r.end_node]] for r in roads], np.int32),
+        dest_nodes=np.array([mi.nodes[(-r).end_node] for r in roads], np.int32),
+        veh_static=rx.vehicle_static(v).astype(np.float32),
+    )
+    env.close()
+    np.savez_compressed(args.out, **out)
+    print("wrote", args.out, os.path.getsize(args.out) // 1024, "KiB", "lanes", len(m["lane_f"]))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--env", default="metadrive", choices=["metadrive", "safe"])
+    ap.add_argument("--env", default="metadrive", choices=["metadrive", "safe", "ma_roundabout", "ma_intersection"])
     ap.add_argument("--n", type=int, default=1000)
     ap.add_argument("--start", type=int, default=0)
     ap.add_argument("--density", type=float, default=None)
@@ -34,6 +73,8 @@ def main():
     from oracle.gen_golden import roster_arrays
     from metadrive.envs.metadrive_env import MetaDriveEnv
     from metadrive.envs.safe_metadrive_env import SafeMetaDriveEnv
+    if args.env.startswith("ma_"):
+        return export_multi_agent(args)
     cls = MetaDriveEnv if args.env == "metadrive" else SafeMetaDriveEnv
     mp = int(args.map) if args.map.isdigit() else args.map
     cfg = dict(map=mp, num_scenarios=args.n, start_seed=args.start, log_level=50, store_map=False)

@@ -85,3 +85,97 @@ def test_host_path_equals_device_path_and_autoreset():
     assert (vi[:, 0, 11] < 140).sum() >= 40  # episode_length restarted for the envs that were reset
     a_sim.close()
     b_sim.close()
+
+
+# ------------------------------------------------------------------------------------------------ multi-agent surface
+def _ma_act(env, action):
+    """tests/test_env/test_ma_roundabout_env.py:62-77 of the reference, against the drop-in"""
+    assert env.action_space.contains(action)
+    obs, reward, terminated, truncated, info = env.step(action)
+    if not terminated["__all__"]:
+        assert len(env.agents) > 0
+    assert set(obs.keys()) == set(reward.keys()) == set(info.keys())
+    assert set(terminated.keys()) == set(obs.keys()) | {"__all__"} == set(truncated.keys())
+    for k, o in obs.items():
+        assert o.dtype == np.float32 and env._obs_box.contains(o)
+    # agents that are still running are exactly the ones the env wants actions for next
+    running = {k for k in obs if not (terminated[k] or truncated[k])}
+    assert running == set(env.agents.keys())
+    return obs, reward, terminated, truncated, info
+
+
+@pytest.mark.parametrize("num_agents", [1, 4, 8])
+def test_ma_roundabout_env_surface(num_agents):
+    """metadrive/tests/test_env/test_ma_roundabout_env.py:80-103: spaces, key bookkeeping, no done at step 0."""
+    from metadrive_ped_b200 import MultiAgentRoundaboutEnv
+    env = MultiAgentRoundaboutEnv({"num_agents": num_agents, "delay_done": 0})
+    try:
+        obs, info = env.reset()
+        assert set(obs.keys()) == {"agent%d" % k for k in range(num_agents)} == set(env.agents.keys())
+        assert env.observation_space.contains(obs)
+        assert obs["agent0"].shape == (19 + 72, )  # multi-agent default lidar: 72 lasers, 40 m
+        for step in range(100):
+            act = {k: [1, 1] for k in env.agents.keys()}
+            o, r, tm, tc, i = _ma_act(env, act)
+            if step == 0:
+                assert not any(tm.values()) and not any(tc.values())
+            if tm["__all__"] and not env.agents:
+                break
+        assert INFO_KEYS <= set(next(iter(i.values())))
+    finally:
+        env.close()
+
+
+def test_ma_roundabout_respawn_and_horizon():
+    """metadrive/tests/test_env/test_ma_roundabout_env.py (horizon / respawn): finished agents show up once, new ids
+    appear with reward 0 while respawn is allowed, nobody outlives the horizon."""
+    from metadrive_ped_b200 import MultiAgentRoundaboutEnv
+    env = MultiAgentRoundaboutEnv({"num_agents": 6, "horizon": 60, "delay_done": 5,
+                                   "vehicle_config": {"lidar": {"num_lasers": 240, "distance": 50}}})
+    try:
+        obs, _ = env.reset()
+        seen, finished, lengths = set(obs), set(), {k: 0 for k in obs}
+        for step in range(200):
+            act = {k: [0.3, 1.0] for k in env.agents}   # steer off the road: everybody dies, seats get respawned
+            o, r, tm, tc, i = _ma_act(env, act)
+            for k in o:
+                if k not in seen:                       # a newborn: reward 0, not done
+                    assert r[k] == 0.0 and not tm[k] and not tc[k]
+                    assert env.episode_step < 60, "no respawn after the horizon"
+                    seen.add(k); lengths[k] = 0
+                else:
+                    lengths[k] += 1
+                    assert i[k]["episode_length"] == lengths[k]
+                assert k not in finished, "a finished agent never comes back"
+                if tm[k] or tc[k]:
+                    finished.add(k)
+                    assert lengths[k] <= 60
+            if not env.agents:
+                break
+        assert not env.agents, "after the horizon the env drains"
+        assert len(seen) > 6, "agents were respawned"
+        ids = sorted(int(k[5:]) for k in seen)
+        assert ids == list(range(len(ids))), "agent ids grow monotonically (agent_manager.py:156-159)"
+    finally:
+        env.close()
+
+
+def test_batched_multi_agent_env_autoreset():
+    import torch
+    from metadrive_ped_b200 import BatchedMultiAgentEnv
+    env = BatchedMultiAgentEnv(16, {"num_agents": 10, "horizon": 40, "delay_done": 5})
+    obs = env.reset()
+    assert obs.shape == (16 * 11, 19 + 72)
+    a = torch.zeros((16, 11, 2), device="cuda")
+    a[..., 0] = 0.2
+    a[..., 1] = 1.0
+    steps_valid = 0
+    for t in range(150):
+        obs, r, te, tr, info = env.step(a)
+        valid = (info["flags"] & 0x2000) != 0
+        steps_valid += int(valid.sum())
+        assert torch.isfinite(obs).all() and float(obs.min()) >= 0.0 and float(obs.max()) <= 1.0
+    ei = env.sim.get_state("env_i")
+    assert ei[:, 2].max() < 150, "envs were reset on device after draining"
+    assert steps_valid > 16 * 10 * 40
+    env.close()
