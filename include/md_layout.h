@@ -193,7 +193,9 @@
 #define EI_STEP 2          /* engine.episode_step */
 #define EI_N_BLOCKS 3
 #define EI_SEED 4
-#define EI_RNG 5           /* multi-agent: number of respawn draws consumed from the env's random tape (ma_tape) */
+#define EI_RNG 5           /* number of respawn events that consumed a row of the env's random tape (env_tape) */
+#define EI_N_PLACES 6      /* respawn / hybrid traffic mode: number of respawn lanes of this env (rows of ma_place_f in use) */
+#define TAPE_W 4
 /* env_trigger [E, 8]: trigger road id (local to map) per block index */
 #define TRIGGER_MAX 8
 
@@ -214,7 +216,7 @@ typedef struct MdConfig {
     int crash_vehicle_done, crash_object_done, crash_human_done, truncate_as_terminate;
     int enable_idm_lane_change, is_multi_agent, delay_done, allow_respawn;
     /* multi-agent respawn tables (manager/spawn_manager.py:117-217): safe places per env, destinations, spawn roads */
-    int ma_places, ma_dests, ma_roads, ma_tape_len;
+    int ma_places, ma_dests, ma_roads, tape_len;
     /* MultiAgentMetaDrive.done_function overrides (envs/marl_envs/multi_agent_metadrive.py:114-128) */
     int ma_crash_done, ma_out_of_road_done, spare1, spare2;
 } MdConfig;
@@ -252,10 +254,14 @@ typedef struct MdArrays {
     const float* ma_place_f;  /* [E*ma_places, 8]: x, y, quat w, quat z (yaw only), lane id, heading cos, sin, spawn-road index */
     const int* ma_route;      /* [E*ma_roads*ma_dests, ROUTE_MAX]: checkpoints from spawn road r to destination d */
     const int* ma_rroad;      /* [E*ma_roads*ma_dests, ROUTE_MAX] */
-    /* [E*ma_tape_len, 2] pre-drawn 32-bit random numbers (place draw, destination draw) consumed in order by the
-     * respawns of an env: the reference draws them from unseeded numpy generators (multi_agent_metadrive.py:199,
-     * marl_inout_roundabout.py:138-143), the host fills the tape from its own generator (tests: from the trace) */
-    const int* ma_tape;
+    /* [E*tape_len, TAPE_W] pre-drawn 32-bit words, one row per respawn event of an env, consumed in order.  The
+     * reference draws these from numpy generators at run time (multi_agent_metadrive.py:199,
+     * marl_inout_roundabout.py:138-143; traffic_manager.py:113-121, idm_policy.py:229); the host fills the tape from
+     * its own generator (tests: from the reference trace).
+     *   multi-agent respawn : w0 = place draw (mod clear places), w1 = destination draw (mod destinations)
+     *   traffic respawn     : w0 = respawn-lane draw (mod lanes), w1 = float bits of rand() in [0,1) for the longitude,
+     *                         w2 = overtake-timer draw (mod LANE_CHANGE_FREQ) */
+    const int* env_tape;
 } MdArrays;
 
 #endif

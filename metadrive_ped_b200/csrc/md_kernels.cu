@@ -137,6 +137,37 @@ __device__ __forceinline__ int hash_randint(uint32_t slot, uint32_t counter, int
     return (int)(x % (uint32_t)n);
 }
 
+// word j of the k-th row of an env's random tape (include/md_layout.h: env_tape); once the tape has wrapped it is
+// perturbed with a counter hash so that a long run does not repeat itself
+__device__ __forceinline__ uint32_t tape_draw(const MdConfig& cfg, const int* __restrict__ tape, int env, uint32_t ctr, int j) {
+    const uint32_t L = (uint32_t)cfg.tape_len;
+    uint32_t v = (uint32_t)tape[((size_t)env * L + ctr % L) * TAPE_W + j];
+    const uint32_t lap = ctr / L;
+    if (lap) {
+        uint32_t x = (uint32_t)env * 0x9E3779B9u + (lap * 4u + (uint32_t)j) * 0x85EBCA6Bu + 0x165667B1u;
+        x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+        v += x;
+    }
+    return v;
+}
+// word 1 as a uniform number in [0, 1): the stored float on the first lap, 24 hashed bits afterwards
+__device__ __forceinline__ float tape_frac(const MdConfig& cfg, const int* __restrict__ tape, int env, uint32_t ctr) {
+    const uint32_t v = tape_draw(cfg, tape, env, ctr, 1);
+    if (ctr / (uint32_t)cfg.tape_len == 0) return __uint_as_float(v);
+    return (float)(v >> 8) * (1.0f / 16777216.0f);
+}
+// yaw-only quaternion (w, z) of a body whose +Y axis (the nose) points along the lane at `lon`
+__device__ __forceinline__ void yaw_quat_for_lane(const float* L, float lon, float& qw, float& qz) {
+    if (L[LF_TYPE] == 0.0f) {
+        const float c = L[LF_P0 + 5], s = -L[LF_P0 + 4];  // cos(yaw) = dy, sin(yaw) = -dx
+        const float cw = sqrtf(fmaxf(0.5f * (1.0f + c), 0.0f)), sw = sqrtf(fmaxf(0.5f * (1.0f - c), 0.0f));
+        qw = cw; qz = s < 0.0f ? -sw : sw;
+    } else {
+        const float yaw = lane_heading_at(L, lon) - MD_PI / 2.0f;
+        qw = cosf(0.5f * yaw); qz = sinf(0.5f * yaw);
+    }
+}
+
 // IDMPolicy.act (policy/idm_policy.py:235-402) for one traffic vehicle; S/I/D are this thread's register copies
 __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv, int g, const float* S, int* I, float* D,
                         const int* __restrict__ rroad, float& out_a0, float& out_a1) {
@@ -842,6 +873,15 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     if (contacts && O > 0) {
         __syncthreads();
         if (G.work)
+            for (int k = slot; k < O; k += S) {  // pedestrians turn around at the ends of their crossing (peds.py)
+                float* Ob = G.sobj + k * OBJ_F;
+                if (Ob[OB_KIND] != 3.0f || Ob[OB_B] <= 0.0f) continue;
+                const float speed = sqrtf(Ob[OB_VX] * Ob[OB_VX] + Ob[OB_VY] * Ob[OB_VY]);
+                Ob[OB_HEADING] -= speed * (cfg.dt * (float)n_sub);
+                if (Ob[OB_HEADING] <= 0.0f) { Ob[OB_VX] = -Ob[OB_VX]; Ob[OB_VY] = -Ob[OB_VY]; Ob[OB_HEADING] += Ob[OB_B]; }
+            }
+        __syncthreads();
+        if (G.work)
             for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = G.sobj[k];
     }
 }
@@ -890,9 +930,68 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
                            G.nb[slot].r, G.obj_first);
         if ((mode & MODE_RESET) && !I[VI_ACTIVE]) I[VI_FLAGS] = FL_ON_LANE;  // reset() ends with _init_step_info
     }
-    // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111)
-    if ((mode & MODE_REMOVE) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE] && !(I[VI_FLAGS] & FL_ON_LANE)) {
-        I[VI_ALIVE] = 0; I[VI_ACTIVE] = 0;
+    // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111) ...
+    const bool leaves = (mode & MODE_REMOVE) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE] && !(I[VI_FLAGS] & FL_ON_LANE);
+    if (leaves) { I[VI_ALIVE] = 0; I[VI_ACTIVE] = 0; }
+    // ... and in respawn / hybrid mode comes back as a new vehicle of the same class on a random respawn lane (:112-121).
+    // Tape rows are handed out in slot order, like the sequential loop of the reference.
+    if ((mode & MODE_REMOVE) && cfg.traffic_mode != 0) {
+        uint32_t ctr = 0;
+        int n_places = 0;
+        if (G.work) {
+            G.nb[slot].active = leaves ? 2 : 0;
+            ctr = (uint32_t)A.env_i[env * ENV_I + EI_RNG];
+            n_places = A.env_i[env * ENV_I + EI_N_PLACES];
+        }
+        __syncthreads();
+        if (G.work && n_places > 0) {
+            int rank = 0, total = 0;
+            for (int k = 0; k < S; k++) {
+                const int lv = G.nb[k].active == 2;
+                total += lv;
+                if (k < slot) rank += lv;
+            }
+            if (slot == 0 && total) A.env_i[env * ENV_I + EI_RNG] = (int)(ctr + (uint32_t)total);
+            if (leaves) {
+                ctr += (uint32_t)rank;
+                const int p = (int)(tape_draw(cfg, A.env_tape, env, ctr, 0) % (uint32_t)n_places);
+                const float frac = tape_frac(cfg, A.env_tape, env, ctr);
+                const int timer = (int)(tape_draw(cfg, A.env_tape, env, ctr, 2) % 50u);  // LANE_CHANGE_FREQ
+                const int lane = (int)A.ma_place_f[((size_t)env * cfg.ma_places + p) * 8 + 4];
+                const float* L = m.lane_f + lane * LANE_F;
+                const float lon = frac * L[LF_LENGTH] / 2.0f;
+#pragma unroll
+                for (int k = 0; k < VEH_S; k++) St[k] = 0.0f;
+#pragma unroll
+                for (int k = 0; k < VEH_C; k++) C[k] = 0.0f;
+#pragma unroll
+                for (int k = 0; k < VEH_I; k++) I[k] = 0;
+#pragma unroll
+                for (int k = 0; k < NAVI_DIM; k++) navi[k] = 0.0f;
+                lane_position(L, lon, 0.0f, St[VS_POS], St[VS_POS + 1]);
+                St[VS_POS + 2] = 0.5f * P[VP_HEIGHT];
+                yaw_quat_for_lane(L, lon, St[VS_QUAT], St[VS_QUAT + 3]);
+                const int* rt = A.ma_route + ((size_t)env * cfg.ma_places + p) * ROUTE_MAX;
+                const int* rr = A.ma_rroad + ((size_t)env * cfg.ma_places + p) * ROUTE_MAX;
+                int* vr = A.veh_route + (size_t)g * ROUTE_MAX;
+                int* vrr = A.veh_rroad + (size_t)g * ROUTE_MAX;
+                int n_ck = 0;
+                for (int k = 0; k < ROUTE_MAX; k++) { const int c = rt[k]; vr[k] = c; vrr[k] = rr[k]; if (c >= 0) n_ck++; }
+                I[VI_KIND] = 2; I[VI_ALIVE] = 1; I[VI_ACTIVE] = 1; I[VI_TRIGGER] = -1;
+                I[VI_LANE] = lane; I[VI_SPAWN_LANE] = lane;
+                I[VI_CKPT0] = 0; I[VI_CKPT1] = n_ck > 2 ? 1 : 0; I[VI_ROUTE_LEN] = n_ck;
+                I[VI_ROUTING_LANE] = -1;
+                float4* d4 = reinterpret_cast<float4*>(A.veh_idm + (size_t)g * VEH_IDM);
+                const float rng_ctr = A.veh_idm[(size_t)g * VEH_IDM + VD_RNG];
+                d4[0] = make_float4((float)timer, 30.0f, 0.0f, 0.0f);  // fresh IDMPolicy (policy/idm_policy.py:224-233)
+                d4[1] = make_float4(0.0f, 0.0f, rng_ctr, 0.0f);
+                latch_before_step(St, C, I);
+                const Rect r = vehicle_rect(P, St);
+                after_step_vehicle(m, St, C, I, vr, vrr, navi, G.nb, G.sobj, S, G.O, slot, r, G.obj_first);
+                I[VI_FLAGS] = FL_ON_LANE;  // BaseVehicle.reset ends with _init_step_info (base_vehicle.py:379)
+                store16(A.veh_s + (size_t)g * VEH_S, St);
+            }
+        }
     }
     // every agent observes the world as it is after engine.after_step: a vehicle that finishes this step is still
     // visible to the others' lidar (the body row keeps the pre-finish alive flag; k_respawn clears it afterwards)
@@ -1130,17 +1229,6 @@ __global__ void k_done_mask_ma(MdConfig cfg, const int* __restrict__ veh_i, uint
 // BaseVehicle.reset + after_step + first observation (agent_manager.py:136-154).  At most one respawn per env per step,
 // as in the reference (every clear place is marked used by the first query of a step).
 #define RESPAWN_WARPS 4
-__device__ __forceinline__ uint32_t tape_draw(const MdConfig& cfg, const int* __restrict__ tape, int env, uint32_t ctr, int j) {
-    const uint32_t L = (uint32_t)cfg.ma_tape_len;
-    uint32_t v = (uint32_t)tape[((size_t)env * L + ctr % L) * 2 + j];
-    const uint32_t lap = ctr / L;
-    if (lap) {  // the tape has wrapped: perturb it with a counter hash so that a long run does not repeat itself
-        uint32_t x = (uint32_t)env * 0x9E3779B9u + (lap * 2u + (uint32_t)j) * 0x85EBCA6Bu + 0x165667B1u;
-        x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-        v += x;
-    }
-    return v;
-}
 __global__ void __launch_bounds__(RESPAWN_WARPS * 32)
 k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1195,8 +1283,8 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
     if (lane != 0 || clear_mask == 0ull) return;
     const int n_clear = __popcll(clear_mask);
     const uint32_t ctr = (uint32_t)E[EI_RNG];
-    int pick = (int)(tape_draw(cfg, A.ma_tape, env, ctr, 0) % (uint32_t)n_clear);
-    const int dsel = (int)(tape_draw(cfg, A.ma_tape, env, ctr, 1) % (uint32_t)cfg.ma_dests);
+    int pick = (int)(tape_draw(cfg, A.env_tape, env, ctr, 0) % (uint32_t)n_clear);
+    const int dsel = (int)(tape_draw(cfg, A.env_tape, env, ctr, 1) % (uint32_t)cfg.ma_dests);
     E[EI_RNG] = (int)(ctr + 1u);
     int p = 0;
     for (unsigned long long mk = clear_mask;; mk &= mk - 1) {  // the pick-th clear place
@@ -1282,10 +1370,10 @@ struct md_sim {
 static const char* kNames[N_ARR] = {"map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f",
                                     "quad_f", "grid_start", "grid_items", "env_i", "env_trigger", "veh_p", "veh_s", "veh_c",
                                     "veh_i", "veh_route", "veh_idm", "veh_navi", "obj_f", "lgrid_start", "lgrid_items",
-                                    "veh_rroad", "ma_place_f", "ma_route", "ma_rroad", "ma_tape"};
+                                    "veh_rroad", "ma_place_f", "ma_route", "ma_rroad", "env_tape"};
 static const int kRowBytes[N_ARR] = {MAPD * 4, MAPDF * 4, LANE_F * 4, LANE_I * 4, 16, ROAD_I * 4, 8, LINE_F * 4, QUAD_F * 4, 4, 4,
                                      ENV_I * 4, TRIGGER_MAX * 4, VEH_P * 4, VEH_S * 4, VEH_C * 4, VEH_I * 4, ROUTE_MAX * 4,
-                                     VEH_IDM * 4, NAVI_DIM * 4, OBJ_F * 4, 4, 4, ROUTE_MAX * 4, 32, ROUTE_MAX * 4, ROUTE_MAX * 4, 8};
+                                     VEH_IDM * 4, NAVI_DIM * 4, OBJ_F * 4, 4, 4, ROUTE_MAX * 4, 32, ROUTE_MAX * 4, ROUTE_MAX * 4, TAPE_W * 4};
 #define N_SNAP 9
 static const int kSnapIdx[N_SNAP] = {11, 14, 15, 16, 18, 19, 20, 17, 23};  // env_i veh_s veh_c veh_i veh_idm veh_navi obj_f veh_route veh_rroad
 

@@ -16,6 +16,7 @@ from . import scene as sc
 RESPAWN_REGION_LONGITUDE = 8.0  # manager/spawn_manager.py:31-35
 RESPAWN_REGION_LATERAL = 3.0
 TAPE_LEN = 256
+TAPE_W = 4
 
 
 def shortest_path(road_i, start_node, goal_node):
@@ -75,9 +76,12 @@ def build_ma_tables(geo: "sc.MapGeometry", spawn_roads, dest_nodes):
 
 
 def make_tape(n_envs, seed=0, length=TAPE_LEN):
-    """[n_envs * length, 2] uniform 32-bit draws (place, destination) consumed in order by an env's respawns."""
+    """[n_envs * length, TAPE_W] random tape (include/md_layout.h: env_tape): integer draws in columns 0, 2, 3 and the
+    float bits of a uniform [0, 1) number in column 1."""
     rng = np.random.default_rng(seed)
-    return rng.integers(0, 2**31 - 1, size=(n_envs * length, 2), dtype=np.int64).astype(np.int32)
+    t = rng.integers(0, 2**31 - 1, size=(n_envs * length, TAPE_W), dtype=np.int64).astype(np.int32)
+    t[:, 1] = rng.random(n_envs * length, dtype=np.float32).view(np.int32)
+    return t
 
 
 # ---------------------------------------------------------------------------------------------- scenes at reset
@@ -163,6 +167,6 @@ class MultiAgentLibrary:
         tape = make_tape(n_envs, seed=seed + 1)
         arrays = sc.pack([self.geo], scen, S, NA, 0, ma_tables={0: self.tables}, ma_tables_tape=tape)
         kw = dict(is_multi_agent=1, ma_places=len(self.tables["places"]), ma_dests=self.tables["n_dests"],
-                  ma_roads=self.tables["n_roads"], ma_tape_len=TAPE_LEN)
+                  ma_roads=self.tables["n_roads"], tape_len=TAPE_LEN)
         kw.update(cfg_kw)
         return arrays, make_config(n_envs, S, NA, 0, **kw)

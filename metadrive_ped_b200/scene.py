@@ -346,7 +346,7 @@ class Scenario:
 
 
 def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int, agents_per_env: int,
-         objs_per_env: int, ma_tables=None, ma_tables_tape=None):
+         objs_per_env: int, ma_tables=None, ma_tables_tape=None, traffic_respawn=False):
     """Concatenate maps + scenarios into the flat arrays of `MdArrays` (numpy, C-contiguous, f32/i32)."""
     M, E, S, O = len(maps), len(scenarios), slots_per_env, objs_per_env
     map_desc = np.zeros((M, MAPD), np.int32)
@@ -454,7 +454,7 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
             if sc.objects.shape[1] >= 10:
                 ob[:, 10:12] = sc.objects[:, 8:10]
     # multi-agent respawn tables (metadrive_ped_b200/ma.py): per map id dict(places [P,8], routes [R*D, ROUTE_MAX]),
-    # replicated per env; ma_tape [E*L, 2] = the envs' random tapes
+    # replicated per env; env_tape [E*L, TAPE_W] = the envs' random tapes
     if ma_tables:
         t0 = next(iter(ma_tables.values()))
         P, RD = len(t0["places"]), len(t0["routes"])
@@ -477,14 +477,41 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
             ma_place_f[e * P:(e + 1) * P] = pl
             ma_route[e * RD:(e + 1) * RD] = rt
             ma_rroad[e * RD:(e + 1) * RD] = rr
-        ma_tape = np.ascontiguousarray(ma_tables_tape, np.int32) if ma_tables_tape is not None else np.zeros((E, 2), np.int32)
-        assert ma_tape.shape[0] % E == 0 and ma_tape.shape[1] == 2
+        env_tape = np.ascontiguousarray(ma_tables_tape, np.int32) if ma_tables_tape is not None else np.zeros((E, 4), np.int32)
+        assert env_tape.shape[0] % E == 0 and env_tape.shape[1] == 4
+    elif traffic_respawn:
+        # respawn / hybrid traffic mode (manager/traffic_manager.py:112-121, 279-296): the same tables hold, per env, the
+        # respawn lanes of its map (column 4 = lane id) and the route of a vehicle born on each (one row per lane)
+        P = max(1, max(len(g.meta.get("respawn", [])) for g in maps))
+        ma_place_f = np.zeros((E * P, 8), np.float32)
+        ma_route = np.full((E * P, ROUTE_MAX), -1, np.int32)
+        ma_rroad = np.full((E * P, ROUTE_MAX), -1, np.int32)
+        per_map = {}
+        for mid, g in enumerate(maps):
+            rs = g.meta.get("respawn", [])
+            pl = np.zeros((P, 8), np.float32)
+            rt = np.full((P, ROUTE_MAX), -1, np.int32)
+            rr = np.full((P, ROUTE_MAX), -1, np.int32)
+            for k, it in enumerate(rs):
+                pl[k, 4] = it["lane"]
+                rt[k, :len(it["route"])] = it["route"]
+                for j in range(len(it["route"]) - 1):
+                    rr[k, j] = road_lut[mid].get((int(it["route"][j]), int(it["route"][j + 1])), -1)
+            per_map[mid] = (pl, rt, rr, len(rs))
+        for e, sc in enumerate(scenarios):
+            pl, rt, rr, n = per_map[sc.map_id]
+            ma_place_f[e * P:(e + 1) * P] = pl
+            ma_route[e * P:(e + 1) * P] = rt
+            ma_rroad[e * P:(e + 1) * P] = rr
+            env_i[e, 6] = n
+        env_tape = np.ascontiguousarray(ma_tables_tape, np.int32) if ma_tables_tape is not None else np.zeros((E, 4), np.int32)
+        assert env_tape.shape[0] % E == 0 and env_tape.shape[1] == 4
     else:
         ma_place_f = np.zeros((1, 8), np.float32)
         ma_route = np.full((1, ROUTE_MAX), -1, np.int32)
         ma_rroad = np.full((1, ROUTE_MAX), -1, np.int32)
-        ma_tape = np.zeros((1, 2), np.int32)
-    arrays.update(ma_place_f=ma_place_f, ma_route=ma_route, ma_rroad=ma_rroad, ma_tape=ma_tape)
+        env_tape = np.zeros((1, 4), np.int32)
+    arrays.update(ma_place_f=ma_place_f, ma_route=ma_route, ma_rroad=ma_rroad, env_tape=env_tape)
     arrays.update(env_i=env_i, env_trigger=env_trigger, veh_p=veh_p, veh_s=veh_s, veh_c=veh_c, veh_i=veh_i,
                   veh_route=veh_route, veh_idm=veh_idm, veh_navi=veh_navi, obj_f=obj_f, veh_rroad=veh_rroad)
     return arrays
@@ -493,4 +520,4 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
 ARRAY_ORDER = ["map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f", "quad_f",
                "grid_start", "grid_items", "env_i", "env_trigger", "veh_p", "veh_s", "veh_c", "veh_i", "veh_route",
                "veh_idm", "veh_navi", "obj_f", "lgrid_start", "lgrid_items", "veh_rroad", "ma_place_f", "ma_route",
-               "ma_rroad", "ma_tape"]
+               "ma_rroad", "env_tape"]

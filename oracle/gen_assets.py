@@ -65,6 +65,7 @@ def main():
     ap.add_argument("--start", type=int, default=0)
     ap.add_argument("--density", type=float, default=None)
     ap.add_argument("--map", default="3")
+    ap.add_argument("--traffic-mode", default=None, choices=[None, "trigger", "respawn", "hybrid"])
     ap.add_argument("--out", required=True)
     args = ap.parse_args()
     from oracle import refshim
@@ -80,6 +81,8 @@ def main():
     cfg = dict(map=mp, num_scenarios=args.n, start_seed=args.start, log_level=50, store_map=False)
     if args.density is not None:
         cfg["traffic_density"] = args.density
+    if args.traffic_mode is not None:
+        cfg["traffic_mode"] = args.traffic_mode
     env = cls(cfg)
     acc = {k: [] for k in ("lane_f", "lane_i", "road_i", "veh_static", "veh_dyn", "routes", "veh_int", "idm", "objects")}
     map_off, veh_off, obj_off, metas, seeds = [], [], [], [], []

@@ -86,7 +86,7 @@ def run_episode(env_cls, config, seed, actions, tag):
         env.close()
 
 
-def _lane_follow_action(v, rs, noise):
+def _lane_follow_action(v, rs, noise, fast=32, slow=16):
     """Test-side driver for multi-agent traces: steer along the localised lane (slower on tight arcs), plus noise."""
     lane = v.navigation.current_lane
     lon, lat = lane.local_coordinates(v.position)
@@ -94,7 +94,7 @@ def _lane_follow_action(v, rs, noise):
     err = (err + np.pi) % (2 * np.pi) - np.pi
     steer = 2.5 * err + 0.5 * lat + noise * rs.uniform(-1, 1)
     tight = getattr(lane, "radius", 1e9) < 20
-    target = 16 if tight else 32
+    target = slow if tight else fast
     thr = (0.6 if v.speed_km_h < target else (-0.3 if v.speed_km_h > target + 6 else 0.0)) + noise * rs.uniform(-1, 1)
     return [float(np.clip(steer, -1, 1)), float(np.clip(thr, -1, 1))]
 
@@ -228,13 +228,106 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         env.close()
 
 
+def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
+    """BASELINE config 5, composed from reference pieces: MetaDriveEnv(map="X", traffic_mode="respawn") plus
+    `n_peds` reference `Pedestrian` objects placed and driven (set_velocity between env.steps) by the build-defined
+    crossing model of metadrive_ped_b200/peds.py.  Records traffic respawn events (slot, respawn-lane index, longitude,
+    overtake timer, parameters of the new vehicle) so that a replay can feed the same random tape."""
+    from oracle import ref_export as rx
+    from metadrive.envs.metadrive_env import MetaDriveEnv
+    from metadrive.component.traffic_participants.pedestrian import Pedestrian
+    from metadrive_ped_b200 import scene as sc
+    from metadrive_ped_b200 import peds as pd
+    env = MetaDriveEnv(config)
+    rs = np.random.RandomState(seed)
+    try:
+        obs0, _ = env.reset(seed=seed)
+        eng = env.engine
+        m, mi = rx.export_map(env.current_map)
+        geo = sc.build_map_geometry(sc.MapTable.from_export(m, env.config["map_config"]["lane_num"]))
+        prow = pd.place_pedestrians(geo, np.random.default_rng(seed), n_peds)
+        peds = []
+        for r in prow:
+            p = eng.spawn_object(Pedestrian, position=[r[1], r[2]], heading_theta=float(np.arctan2(r[9], r[8])), random_seed=1)
+            p.set_velocity([r[8], r[9]], in_local_frame=False)
+            peds.append(p)
+        # the first observation must see the pedestrians: observe again now that they exist
+        obs0 = env.observations[next(iter(env.agents))].observe(env.agent)
+        roster = rx.Roster(env, mi)
+        init = roster_arrays(env, mi, roster)
+        init["objects"] = prow.copy()
+        respawn_lanes = [it["lane"] for it in json.loads(m["meta"])["respawn"]]
+        tm = eng.traffic_manager
+        names = [v.name for v in roster.vehicles]
+
+        def world():
+            fs, is_ = [], []
+            for v, nm in zip(roster.vehicles, names):
+                if v.name != nm:
+                    fs.append(np.zeros(rx.N_STEP_F)); is_.append(np.zeros(8, np.int32))
+                else:
+                    f, i = rx.record_vehicle(v, roster, env)
+                    fs.append(f); is_.append(i)
+            return np.stack(fs), np.stack(is_)
+
+        def ped_state():
+            return np.array([[p.position[0], p.position[1], p.velocity[0], p.velocity[1]] for p in peds])
+
+        f0, i0 = world()
+        fs, is_, obs, rew, cost, term, trunc, infos, acts, pst = [f0], [i0], [obs0], [], [], [], [], [], [], [ped_state()]
+        events = []  # step, slot, place index, longitude, timer + new static row
+        ev_static = []
+        dt_step = env.config["decision_repeat"] * env.config["physics_world_step_size"]
+        for t in range(steps):
+            a = _lane_follow_action(env.agent, rs, 0.02, fast=22, slow=14)
+            before = list(tm._traffic_vehicles)
+            o, r, te, tr, info = env.step(a)
+            after = list(tm._traffic_vehicles)
+            removed = [v for v in before if v not in after or v.name != names[roster.vehicles.index(v)]]
+            added = after[len(before) - len(removed):] if removed else []
+            assert len(added) == len(removed), (len(added), len(removed))
+            for old_v, new_v in zip(removed, added):
+                k = roster.vehicles.index(old_v)
+                roster.vehicles[k] = new_v
+                names[k] = new_v.name
+                lane_id = mi.lane_id(eng.current_map.road_network.get_lane(new_v.config["spawn_lane_index"]))
+                pol = eng.get_policy(new_v.name)
+                events.append([t, k, respawn_lanes.index(lane_id), float(new_v.config["spawn_longitude"]), int(pol.overtake_timer)])
+                ev_static.append(rx.vehicle_static(new_v))
+            for k in pd.step_pedestrians_host(prow, dt_step):
+                peds[k].set_velocity([prow[k][8], prow[k][9]], in_local_frame=False)
+            f, i = world()
+            fs.append(f); is_.append(i); obs.append(o); rew.append(r); cost.append(info["cost"]); term.append(te); trunc.append(tr)
+            acts.append(a); pst.append(ped_state())
+            infos.append([info["velocity"], info["steering"], info["acceleration"], info["step_energy"],
+                          info["episode_energy"], info["step_reward"], info["episode_reward"], info["episode_length"]])
+            if te or tr:
+                break
+        conf = {k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))}
+        out = dict(
+            tag=tag, seed=seed, lane_num=env.config["map_config"]["lane_num"],
+            map_lane_f=m["lane_f"], map_lane_i=m["lane_i"], map_road_i=m["road_i"], map_meta=m["meta"],
+            actions=np.asarray(acts, np.float64), veh_f=np.stack(fs), veh_i=np.stack(is_),
+            obs=np.stack(obs).astype(np.float32), reward=np.asarray(rew, np.float64), cost=np.asarray(cost, np.float64),
+            terminated=np.asarray(term, bool), truncated=np.asarray(trunc, bool), info=np.asarray(infos, np.float64),
+            ped_state=np.stack(pst), respawn_events=np.asarray(events, np.float64).reshape(-1, 5),
+            respawn_static=np.asarray(ev_static, np.float64).reshape(-1, 16),
+            config=json.dumps(conf), **{"init_" + k: v for k, v in init.items()},
+        )
+        out["ref_lines"] = rx.export_static_bodies(env.engine)["lines"]
+        return out
+    finally:
+        env.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--only", default=None)
     ap.add_argument("--ma-steps", type=int, default=450)
-    ap.add_argument("--ma-noise", type=float, default=0.08)
+    ap.add_argument("--ma-noise", type=float, default=0.04)
+    ap.add_argument("--cfg5-steps", type=int, default=350)
     args = ap.parse_args()
     from oracle import refshim
     refshim.install()
@@ -281,12 +374,22 @@ def main():
         from metadrive.envs.marl_envs.marl_inout_roundabout import MultiAgentRoundaboutEnv
         lid = dict(vehicle_config=dict(lidar=dict(num_lasers=240, distance=50, num_others=0)))
         cfg3 = dict(num_agents=12, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, **lid)
-        out = run_episode_ma(MultiAgentRoundaboutEnv, cfg3, None, "cfg3_ma_roundabout_respawn", steps=args.ma_steps,
+        out = run_episode_ma(MultiAgentRoundaboutEnv, cfg3, None, "cfg3_ma_roundabout_respawn", steps=max(args.ma_steps, 520),
                              noise=args.ma_noise, seed=5, obs_stride=3)
         path = os.path.join(args.out, "cfg3_ma_roundabout_respawn.npz")
         np.savez_compressed(path, **out)
         print("cfg3_ma_roundabout_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
               "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
+    # BASELINE config 5 (composed): X map, respawn-mode IDM traffic, 16 crossing pedestrians; crashes do not end the
+    # episode here so that the trace keeps running through pedestrian / vehicle contacts
+    if not args.only or args.only == "cfg5_ped_X":
+        cfg5 = dict(map="X", traffic_density=0.1, traffic_mode="respawn", num_scenarios=20, start_seed=0, log_level=50,
+                    crash_vehicle_done=False, crash_human_done=False, crash_object_done=False)
+        out = run_episode_cfg5(cfg5, 4, args.cfg5_steps, "cfg5_ped_X")
+        path = os.path.join(args.out, "cfg5_ped_X.npz")
+        np.savez_compressed(path, **out)
+        print("cfg5_ped_X steps", len(out["reward"]), "vehicles", out["veh_f"].shape[1], "respawns", len(out["respawn_events"]),
+              "crash_human steps", int(((out["veh_i"][:, 0, 5] & 8) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     for tag, cls, cfg, seed, acts in cases:
         if args.only and args.only not in tag:
             continue

@@ -128,8 +128,36 @@ def export_map(current_map):
                 sockets=sockets,
             )
         )
-    meta = dict(nodes=list(mi.nodes.keys()), blocks=blocks)
+    meta = dict(nodes=list(mi.nodes.keys()), blocks=blocks, respawn=export_respawn_lanes(current_map, mi))
     return dict(lane_f=lane_f, lane_i=lane_i, road_i=road_i, meta=json.dumps(meta)), mi
+
+
+def export_respawn_lanes(current_map, mi):
+    """Respawn / hybrid traffic mode (manager/traffic_manager.py:94-122, 279-296): the lanes a removed traffic vehicle
+    may be respawned on, each with the route the reference's navigation assigns to a vehicle born there
+    (node_network_navigation.py:43-91: destination drawn from RandomState(global seed), then the BFS route)."""
+    from metadrive.component.navigation_module.node_network_navigation import NodeNetworkNavigation
+    from metadrive.engine.engine_utils import get_engine
+    roads = []
+    for block in current_map.blocks:
+        for road in block.get_respawn_roads():
+            if road in roads:
+                roads.remove(road)
+            else:
+                roads.append(road)
+    seed = get_engine().global_random_seed
+    out = []
+    for road in roads:
+        for lane in road.get_lanes(current_map.road_network):
+            try:
+                dest = NodeNetworkNavigation.auto_assign_task(current_map, lane.index, None, seed)
+                ck = current_map.road_network.shortest_path(lane.index, dest)
+            except Exception:
+                continue
+            if len(ck) <= 2:
+                ck = [lane.index[0], lane.index[1]]
+            out.append(dict(lane=mi.lane_id(lane), route=[mi.nodes[c] for c in ck]))
+    return out
 
 
 def export_static_bodies(engine):

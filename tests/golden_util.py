@@ -31,10 +31,10 @@ MA_CFG = dict(is_multi_agent=1, out_of_road_penalty=10.0, crash_vehicle_penalty=
 def ma_tape_from_trace(g, length=256):
     """The random tape that replays the respawn choices of the reference trace: the k-th respawn drew the
     clear-list index draws[k, 0] and the destination draws[k, 1] (value % n == value since value < n)."""
-    tape = np.zeros((length, 2), np.int32)
+    tape = np.zeros((length, 4), np.int32)
     ev = g["respawn_draws"][g["respawn_draws"][:, 0] >= 0]
     assert len(ev) <= length
-    tape[:len(ev)] = ev[:, :2]
+    tape[:len(ev), :2] = ev[:, :2]
     return tape
 
 
@@ -57,16 +57,32 @@ def golden_world_ma(g, replicas=1, **cfg_kw):
     kw.update(horizon=int(conf.get("horizon", 1000)), delay_done=int(conf.get("delay_done", 25)),
               allow_respawn=int(bool(conf.get("allow_respawn", True))), n_lasers=int(conf["n_lasers"]),
               lidar_dist=float(conf["lidar_dist"]), ma_places=len(tables["places"]), ma_dests=tables["n_dests"],
-              ma_roads=tables["n_roads"], ma_tape_len=len(tape) // replicas)
+              ma_roads=tables["n_roads"], tape_len=len(tape) // replicas)
     kw.update(cfg_kw)
     cfg = make_config(replicas, S, NA, 0, **kw)
     return arrays, cfg, geo
+
+
+def respawn_tape_from_trace(g, geo, length=256):
+    """Random tape replaying the traffic respawns of a reference trace (rows in (step, slot) order): respawn-lane index,
+    float bits of longitude / (lane length / 2), overtake timer."""
+    ev = np.asarray(g["respawn_events"]).reshape(-1, 5)
+    ev = ev[np.lexsort((ev[:, 1], ev[:, 0]))]
+    tape = np.zeros((length, 4), np.int32)
+    lanes = [it["lane"] for it in geo.meta["respawn"]]
+    for k, (t, slot, place, lon, timer) in enumerate(ev):
+        half = np.float32(geo.lane_f[lanes[int(place)], 2]) / np.float32(2.0)
+        frac = np.float32(lon) / half
+        tape[k] = [int(place), np.array([frac], np.float32).view(np.int32)[0], int(timer), 0]
+    return tape
 
 
 def golden_world(g, replicas=1, slots=None, objs=None, **cfg_kw):
     """(arrays, cfg) for `replicas` identical envs built from one golden fixture."""
     if is_ma(g):
         return golden_world_ma(g, replicas, **cfg_kw)
+    if str(g["tag"]).startswith("cfg5"):
+        return golden_world_cfg5(g, replicas, **cfg_kw)
     mt = sc.MapTable(np.asarray(g["map_lane_f"], np.float64), np.asarray(g["map_lane_i"], np.int32),
                      np.asarray(g["map_road_i"], np.int32), json.loads(str(g["map_meta"])), int(g["lane_num"]))
     geo = sc.build_map_geometry(mt)
@@ -82,6 +98,27 @@ def golden_world(g, replicas=1, slots=None, objs=None, **cfg_kw):
         kw.update(crash_vehicle_done=0, crash_object_done=0)
     if "horizon" in conf and conf["horizon"]:
         kw["horizon"] = int(conf["horizon"])
+    kw.update(cfg_kw)
+    cfg = make_config(replicas, S, 1, O, **kw)
+    return arrays, cfg, geo
+
+
+def golden_world_cfg5(g, replicas=1, **cfg_kw):
+    """BASELINE config 5 fixture: respawn-mode traffic (tape from the trace) + crossing pedestrians as objects."""
+    mt = sc.MapTable(np.asarray(g["map_lane_f"], np.float64), np.asarray(g["map_lane_i"], np.int32),
+                     np.asarray(g["map_road_i"], np.int32), json.loads(str(g["map_meta"])), int(g["lane_num"]))
+    geo = sc.build_map_geometry(mt)
+    scen = sc.Scenario(0, g["init_veh_static"], g["init_veh_dyn"], g["init_routes"], g["init_veh_int"], g["init_idm"],
+                       g["init_objects"], int(g["seed"]))
+    n = len(g["init_veh_static"])
+    S = max(4, ((n + 3) // 4) * 4)
+    O = len(g["init_objects"])
+    tape = np.tile(respawn_tape_from_trace(g, geo), (replicas, 1))
+    arrays = sc.pack([geo], [scen] * replicas, S, 1, O, ma_tables_tape=tape, traffic_respawn=True)
+    conf = json.loads(str(g["config"]))
+    kw = dict(traffic_mode=1, ma_places=len(arrays["ma_place_f"]) // replicas, tape_len=len(tape) // replicas,
+              crash_vehicle_done=int(conf.get("crash_vehicle_done", True)), crash_object_done=int(conf.get("crash_object_done", True)),
+              crash_human_done=int(conf.get("crash_human_done", True)))
     kw.update(cfg_kw)
     cfg = make_config(replicas, S, 1, O, **kw)
     return arrays, cfg, geo
