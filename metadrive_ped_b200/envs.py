@@ -34,8 +34,9 @@ STEP_DEFAULTS = dict(
                                    add_others_navi=False),
                         side_detector=dict(num_lasers=0, distance=50), lane_line_detector=dict(num_lasers=0, distance=20),
                         enable_reverse=False, vehicle_model="default"),
-    # extension of this build: which device hosts the simulation
-    device=0,
+    # extensions of this build: which device hosts the simulation; crossing pedestrians per env (peds.py, BASELINE
+    # config 5 - the reference has the Pedestrian object but no spawner for PG maps)
+    device=0, num_pedestrians=0,
 )
 UNSUPPORTED_TRUE = ("use_render", "image_observation", "manual_control", "discrete_action", "random_agent_model",
                     "need_inverse_traffic", "random_traffic")
@@ -129,7 +130,7 @@ class _Agent:
 
 
 class MetaDriveEnv:
-    LIBRARY = "pg3_density0.1.npz"
+    LIBRARIES = ("pg3_density0.1.npz", "x_respawn_density0.1.npz")
     EXTRA_DEFAULTS = {}
 
     @classmethod
@@ -161,14 +162,21 @@ class MetaDriveEnv:
     # -- scenes
     def _library(self):
         if self._lib is None:
-            lib = ScenarioLibrary(self.LIBRARY)
-            lc = lib.config
-            want = dict(map=self.config["map"], traffic_density=self.config["traffic_density"])
-            have = dict(map=lc.get("map"), traffic_density=lc.get("traffic_density", self.default_config()["traffic_density"]))
-            if want != have or self.config["traffic_mode"] != "trigger":
+            want = dict(map=self.config["map"], traffic_density=self.config["traffic_density"],
+                        traffic_mode=self.config["traffic_mode"])
+            tried = []
+            for name in self.LIBRARIES:
+                lib = ScenarioLibrary(name)
+                lc = lib.config
+                have = dict(map=lc.get("map"), traffic_density=lc.get("traffic_density", self.default_config()["traffic_density"]),
+                            traffic_mode=lc.get("traffic_mode", "trigger"))
+                if want == have:
+                    self._lib = lib
+                    break
+                tried.append(have)
+            else:
                 raise NotImplementedError(
-                    "no shipped scenario library for %s (have %s); generate one with oracle/gen_assets.py" % (want, have))
-            self._lib = lib
+                    "no shipped scenario library for %s (have %s); generate one with oracle/gen_assets.py" % (want, tried))
         return self._lib
 
     def _cfg_kw(self):
@@ -197,7 +205,8 @@ class MetaDriveEnv:
             "scenario_index (seed) should be in [{}:{})".format(self.start_seed, self.start_seed + self.num_scenarios)
         lib = self._library()
         if seed not in self._sims:
-            arrays, cfg = lib.build_world([lib.index_of_seed(seed)], **self._cfg_kw())
+            arrays, cfg = lib.build_world([lib.index_of_seed(seed)], num_pedestrians=self.config["num_pedestrians"],
+                                          seed=seed, **self._cfg_kw())
             self._sims[seed] = BatchedSim(arrays, cfg, device=self.config["device"])
         self._sim = self._sims[seed]
         self.current_seed = seed
@@ -247,7 +256,7 @@ class MetaDriveEnv:
 
 class SafeMetaDriveEnv(MetaDriveEnv):
     """envs/safe_metadrive_env.py:7-35"""
-    LIBRARY = "safe_pg3.npz"
+    LIBRARIES = ("safe_pg3.npz", )
     EXTRA_DEFAULTS = dict(num_scenarios=100, accident_prob=0.8, traffic_density=0.05, crash_vehicle_done=False,
                           crash_object_done=False, cost_to_reward=False)
 
@@ -268,7 +277,7 @@ class BatchedMetaDriveEnv:
         first = lib.index_of_seed(proto.start_seed)
         n = min(proto.num_scenarios, len(lib) - first)
         idx = [first + i for i in shard_scenarios(n, num_envs, rank)]
-        arrays, cfg = lib.build_world(idx, **proto._cfg_kw())
+        arrays, cfg = lib.build_world(idx, num_pedestrians=proto.config["num_pedestrians"], seed=rank, **proto._cfg_kw())
         self.sim = BatchedSim(arrays, cfg, device=proto.config["device"])
         self.num_envs = num_envs
         self.observation_space, self.action_space = proto.observation_space, proto.action_space

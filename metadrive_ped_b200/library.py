@@ -12,7 +12,7 @@ from concurrent.futures import ProcessPoolExecutor
 import numpy as np
 
 from . import scene as sc
-from .abi import make_config
+from .abi import TRAFFIC_MODES, make_config
 
 ASSET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 
@@ -80,18 +80,37 @@ class ScenarioLibrary:
     def max_objects(self):
         return int(self.obj_off[:, 1].max())
 
-    def build_world(self, indices, slots_per_env=None, objs_per_env=None, **cfg_kw):
-        """(arrays, cfg) for one env per entry of `indices` (library indices, repeats allowed)."""
+    def build_world(self, indices, slots_per_env=None, objs_per_env=None, num_pedestrians=0, seed=0, **cfg_kw):
+        """(arrays, cfg) for one env per entry of `indices` (library indices, repeats allowed).  `num_pedestrians` > 0
+        adds that many crossing pedestrians per env (peds.py, BASELINE config 5), drawn with `seed`."""
+        from . import ma, peds
         indices = [int(i) for i in indices]
         uniq = list(dict.fromkeys(indices))
         geos = self.geometries(uniq)
         map_id = {i: k for k, i in enumerate(uniq)}
         scen_cache = {i: self.scenario(i, map_id[i]) for i in uniq}
         scenarios = [scen_cache[i] for i in indices]
+        if num_pedestrians > 0:
+            import dataclasses
+            rng = np.random.default_rng(seed)
+            with_peds = []
+            for s in scenarios:
+                rows = peds.place_pedestrians(geos[s.map_id], rng, num_pedestrians)
+                old = np.zeros((len(s.objects), 10))
+                old[:, :8] = s.objects[:, :8]
+                with_peds.append(dataclasses.replace(s, objects=np.concatenate([old, rows])))
+            scenarios = with_peds
         S = slots_per_env or max(4, -(-max(len(s.veh_static) for s in scenarios) // 4) * 4)
         O = objs_per_env if objs_per_env is not None else max(len(s.objects) for s in scenarios)
-        arrays = sc.pack(geos, scenarios, S, 1, O)
+        respawn = self.config.get("traffic_mode", "trigger") in ("respawn", "hybrid")
         kw = {}
+        if respawn:
+            tape = ma.make_tape(len(indices), seed=seed + 1)
+            arrays = sc.pack(geos, scenarios, S, 1, O, ma_tables_tape=tape, traffic_respawn=True)
+            kw.update(traffic_mode=TRAFFIC_MODES[self.config["traffic_mode"]], tape_len=ma.TAPE_LEN,
+                      ma_places=len(arrays["ma_place_f"]) // len(indices))
+        else:
+            arrays = sc.pack(geos, scenarios, S, 1, O)
         if self.env_kind == "safe":  # envs/safe_metadrive_env.py:10-19
             kw.update(crash_vehicle_done=0, crash_object_done=0)
         kw.update(cfg_kw)
