@@ -203,6 +203,8 @@
 #define OBS_EGO 9
 #define OBS_NAVI 10
 #define OBS_STATE (OBS_EGO + OBS_NAVI)
+#define OBS_OTHERS(cfg) (4 * (cfg).num_others)                       /* component/sensors/lidar.py:93-138 */
+#define OBS_DIM(cfg) (OBS_STATE + OBS_OTHERS(cfg) + (cfg).n_lasers)
 
 /* ---- configuration passed by value through the C ABI ------------------------------------------- */
 typedef struct MdConfig {
@@ -218,7 +220,9 @@ typedef struct MdConfig {
     /* multi-agent respawn tables (manager/spawn_manager.py:117-217): safe places per env, destinations, spawn roads */
     int ma_places, ma_dests, ma_roads, tape_len;
     /* MultiAgentMetaDrive.done_function overrides (envs/marl_envs/multi_agent_metadrive.py:114-128) */
-    int ma_crash_done, ma_out_of_road_done, spare1, spare2;
+    int ma_crash_done, ma_out_of_road_done;
+    int num_others; /* lidar.num_others: the k nearest vehicles, 4 floats each, between the state and the lidar floats */
+    int spare2;
 } MdConfig;
 
 /* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */

@@ -562,7 +562,7 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         inf[0] = make_float4(sqrtf(S[VS_VEL] * S[VS_VEL] + S[VS_VEL + 1] * S[VS_VEL + 1]), S[VS_STEER], S[VS_THROTTLE], C[VC_STEP_ENERGY]);
         inf[1] = make_float4(C[VC_ENERGY], step_reward, C[VC_EP_REWARD], (float)I[VI_EP_LEN]);
     }
-    float* o = out.obs + a * (size_t)(OBS_STATE + cfg.n_lasers);
+    float* o = out.obs + a * (size_t)OBS_DIM(cfg);
     o[0] = clipf(C[VC_DIST_L] / 18.0f, 0.0f, 1.0f);
     o[1] = clipf(C[VC_DIST_R] / 18.0f, 0.0f, 1.0f);
     {
@@ -653,7 +653,7 @@ __device__ __forceinline__ void fill_nb(Nb& n, const float* P, const float* S, c
     n.lane = I[VI_LANE]; n.alive = I[VI_ALIVE]; n.active = I[VI_ACTIVE]; n.kind = I[VI_KIND];
 }
 
-// body row for the lidar kernel (BODY_ROW floats): centre(3) half(3) R(9) alive | origin x y, spare(2)
+// body row for the lidar kernel (BODY_ROW floats): centre(3) half(3) R(9) alive | origin x y, velocity x y
 #define BODY_ROW 20
 __device__ __forceinline__ void write_body_row(float* row, const float* P, const float* S, int alive) {
     M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
@@ -664,7 +664,7 @@ __device__ __forceinline__ void write_body_row(float* row, const float* P, const
     r4[1] = make_float4(0.5f * P[VP_LENGTH], hh, R.m[0][0], R.m[0][1]);
     r4[2] = make_float4(R.m[0][2], R.m[1][0], R.m[1][1], R.m[1][2]);
     r4[3] = make_float4(R.m[2][0], R.m[2][1], R.m[2][2], alive ? 1.0f : 0.0f);
-    r4[4] = make_float4(S[VS_POS], S[VS_POS + 1], 0.0f, 0.0f);
+    r4[4] = make_float4(S[VS_POS], S[VS_POS + 1], S[VS_VEL], S[VS_VEL + 1]);
 }
 
 // ================================================================================================ step kernels
@@ -1095,7 +1095,7 @@ __host__ __device__ inline size_t lidar_smem_per_warp(int S, int O) {
 // conservative bounding-circle test prunes the (ray, body) pairs instead.
 __global__ void __launch_bounds__(LIDAR_WARPS * 32)
 k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restrict__ obj_f, const int* __restrict__ veh_i,
-        float* __restrict__ out, int out_stride, int out_off, int* __restrict__ hit_out, const uint8_t* __restrict__ env_mask,
+        const float* __restrict__ veh_p, float* __restrict__ out, int out_stride, int out_off, int* __restrict__ hit_out, const uint8_t* __restrict__ env_mask,
         const int* __restrict__ agent_flags, int need_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env, N = cfg.n_lasers;
@@ -1151,7 +1151,64 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
         hx = fx / n; hy = fy / n;
     }
     const F3 o = f3(eb[16], eb[17], LIDAR_HEIGHT);
-    float* orow = out + (size_t)a * out_stride + out_off;
+    const int K = out_off >= 0 ? cfg.num_others : 0;
+    float* orow = out + (size_t)a * out_stride + (out_off >= 0 ? out_off + 4 * K : 0);
+    if (K > 0) {
+        // Lidar.get_surrounding_vehicles_info (component/sensors/lidar.py:93-138): the K nearest vehicles of the broad
+        // phase set (bodies overlapping the disc of radius int(distance)), by centre distance.  Lane l holds the
+        // candidates k = l, l + 32, ...; K rounds of a warp arg-min (ties: lower slot).
+        const float rad = (float)(int)D;
+        const float max_speed = veh_p[(size_t)(env * S + slot) * VEH_P + VP_MAX_SPEED];
+        float key[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = lane + 32 * j;
+            key[j] = 3.0e38f;
+            if (k < S && k != slot) {
+                const float* b = sbody + BODY_ROW * k;
+                if (b[15] != 0.0f) {
+                    Rect r;
+                    const float fx = b[7], fy = b[10], fn = sqrtf(fx * fx + fy * fy);
+                    r.cx = b[0]; r.cy = b[1]; r.ux = fx / fn; r.uy = fy / fn; r.hu = b[4]; r.hv = b[3];
+                    if (rect_circle(r, o.x, o.y, rad)) {
+                        const float dx = o.x - b[16], dy = o.y - b[17];
+                        key[j] = dx * dx + dy * dy;
+                    }
+                }
+            }
+        }
+        float* orow_k = out + (size_t)a * out_stride + out_off;
+        for (int n = 0; n < K; n++) {
+            float bd = key[0];
+            int bk = lane;
+#pragma unroll
+            for (int j = 1; j < 4; j++) if (key[j] < bd) { bd = key[j]; bk = lane + 32 * j; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+                const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
+                if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+            }
+            if ((bk & 31) == lane && bd < 3.0e38f) key[bk >> 5] = 3.0e38f;  // taken
+            if (lane == 0) {
+                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (bd < 3.0e38f) {
+                    const float* b = sbody + BODY_ROW * bk;
+                    const float dx = b[16] - o.x, dy = b[17] - o.y;
+                    const float fwd = dx * eb[7] + dy * eb[10];            // base_vehicle.py:983-988
+                    const float rhs = -(dx * eb[6] + dy * eb[9]);
+                    const float vx = b[18] * 3.6f - eb[18] * 3.6f, vy = b[19] * 3.6f - eb[19] * 3.6f;
+                    const float vf = vx * eb[7] + vy * eb[10];
+                    const float vr = -(vx * eb[6] + vy * eb[9]);
+                    v.x = clipf((fwd / D + 1.0f) / 2.0f, 0.0f, 1.0f);
+                    v.y = clipf((rhs / D + 1.0f) / 2.0f, 0.0f, 1.0f);
+                    v.z = clipf((vf / max_speed + 1.0f) / 2.0f, 0.0f, 1.0f);
+                    v.w = clipf((vr / max_speed + 1.0f) / 2.0f, 0.0f, 1.0f);
+                }
+                orow_k[4 * n] = v.x; orow_k[4 * n + 1] = v.y; orow_k[4 * n + 2] = v.z; orow_k[4 * n + 3] = v.w;
+            }
+        }
+    }
     int* hrow = hit_out ? hit_out + (size_t)a * N : nullptr;
     for (int i = lane; i < N; i += 32) {
         const float c = c_ray_cs[2 * i], s = c_ray_cs[2 * i + 1];
@@ -1491,7 +1548,7 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
     CK(cudaMalloc(&sim->veh_act, (size_t)NV * sizeof(float4)));
     CK(cudaMemset(sim->veh_act, 0, (size_t)NV * sizeof(float4)));
     CK(cudaMalloc(&sim->mask, (size_t)c.n_envs));
-    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_STATE + c.n_lasers;
+    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_DIM(c);
     CK(cudaMallocHost(&sim->h_actions, NA * 2 * 4)); CK(cudaMallocHost(&sim->h_obs, NA * od * 4));
     CK(cudaMallocHost(&sim->h_reward, NA * 4)); CK(cudaMallocHost(&sim->h_cost, NA * 4));
     CK(cudaMallocHost(&sim->h_info_f, NA * 8 * 4)); CK(cudaMallocHost(&sim->h_term, NA)); CK(cudaMallocHost(&sim->h_trunc, NA));
@@ -1625,7 +1682,7 @@ static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* h
     long long na = (long long)c.n_envs * c.agents_per_env;
     int blocks = (int)((na + LIDAR_WARPS - 1) / LIDAR_WARPS);
     size_t smem = lidar_smem_per_warp(c.slots_per_env, c.objs_per_env) * LIDAR_WARPS;
-    k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, out, stride, off, hit, mask,
+    k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, sim->dev.veh_p, out, stride, off, hit, mask,
                                                     agent_flags, need_flag);
     sim->launches++;
     CK(cudaGetLastError());
@@ -1648,7 +1705,7 @@ extern "C" int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev
     StepOut out = {obs_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (launch_restore(sim, env_mask_dev, st)) return -1;
     if (launch_post(sim, MODE_RESET, out, env_mask_dev, st)) return -1;
-    return launch_lidar(sim, obs_dev, OBS_STATE + sim->cfg.n_lasers, OBS_STATE, nullptr, env_mask_dev, st);
+    return launch_lidar(sim, obs_dev, OBS_DIM(sim->cfg), OBS_STATE, nullptr, env_mask_dev, st);
 }
 
 extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
@@ -1666,7 +1723,7 @@ extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, fl
     if (prof) CK(cudaEventRecord(ev[2], st));
     if (launch_post(sim, MODE_POST | MODE_OUT | MODE_REMOVE, out, nullptr, st)) return -1;
     if (prof) CK(cudaEventRecord(ev[3], st));
-    const int od = OBS_STATE + sim->cfg.n_lasers;
+    const int od = OBS_DIM(sim->cfg);
     if (!sim->cfg.is_multi_agent) {
         if (launch_lidar(sim, obs_dev, od, OBS_STATE, nullptr, nullptr, st)) return -1;
     } else {
@@ -1729,7 +1786,7 @@ extern "C" int md_lidar(md_sim* sim, float* frac_dev, int32_t* hit_dev, void* st
     // refresh the body rows from the current state without moving anything
     StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (launch_post(sim, 0, out, nullptr, st)) return -1;
-    return launch_lidar(sim, frac_dev, sim->cfg.n_lasers, 0, hit_dev, nullptr, st);
+    return launch_lidar(sim, frac_dev, sim->cfg.n_lasers, -1, hit_dev, nullptr, st);
 }
 extern "C" int md_dynamics(md_sim* sim, const float* act3_dev, int n_sub, void* stream) {
     if (!sim || !sim->loaded) return -2;
@@ -1752,7 +1809,7 @@ extern "C" int md_reset_host(md_sim* sim, const uint8_t* env_mask, float* obs) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     const MdConfig& c = sim->cfg;
-    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_STATE + c.n_lasers;
+    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_DIM(c);
     const uint8_t* dm = nullptr;
     if (env_mask) {
         memcpy(sim->h_mask, env_mask, (size_t)c.n_envs);
@@ -1771,7 +1828,7 @@ extern "C" int md_step_host(md_sim* sim, const float* actions, float* obs, float
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     const MdConfig& c = sim->cfg;
-    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_STATE + c.n_lasers;
+    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_DIM(c);
     if (actions && actions != sim->h_actions) memcpy(sim->h_actions, actions, NA * 2 * 4);
     CK(cudaMemcpyAsync(sim->d_actions, sim->h_actions, NA * 2 * 4, cudaMemcpyHostToDevice, sim->stream));
     if (md_step(sim, sim->d_actions, sim->d_obs, sim->d_reward, sim->d_cost, sim->d_term, sim->d_trunc, sim->d_info_flags,

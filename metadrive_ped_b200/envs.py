@@ -145,8 +145,8 @@ class MetaDriveEnv:
             if self.config[k]:
                 raise NotImplementedError("config['%s'] is outside the step path this build covers" % k)
         lid = self.config["vehicle_config"]["lidar"]
-        if lid["num_others"] != 0 or lid["gaussian_noise"] != 0 or lid["dropout_prob"] != 0:
-            raise NotImplementedError("lidar num_others / noise are not covered yet")
+        if lid["gaussian_noise"] != 0 or lid["dropout_prob"] != 0 or lid["add_others_navi"]:
+            raise NotImplementedError("lidar noise / add_others_navi are not covered yet")
         self.start_seed = self.start_index = self.config["start_seed"]
         self.num_scenarios = self.env_num = self.config["num_scenarios"]
         self._lib = None
@@ -155,7 +155,7 @@ class MetaDriveEnv:
         self.current_seed = None
         self.agent = _Agent(self)
         self.episode_cost = 0.0
-        n = lid["num_lasers"]
+        n = lid["num_lasers"] + 4 * lid["num_others"]
         self.observation_space = _box(-0.0, 1.0, (19 + n, ))
         self.action_space = _box(-1.0, 1.0, (2, ))
 
@@ -183,6 +183,7 @@ class MetaDriveEnv:
         c = self.config
         return dict(
             n_lasers=c["vehicle_config"]["lidar"]["num_lasers"], lidar_dist=float(c["vehicle_config"]["lidar"]["distance"]),
+            num_others=int(c["vehicle_config"]["lidar"]["num_others"]),
             horizon=int(c["horizon"] or 0), decision_repeat=c["decision_repeat"], dt=c["physics_world_step_size"],
             traffic_mode=TRAFFIC_MODES[c["traffic_mode"]], success_reward=c["success_reward"],
             out_of_road_penalty=c["out_of_road_penalty"], crash_vehicle_penalty=c["crash_vehicle_penalty"],
@@ -340,15 +341,15 @@ class MultiAgentMetaDrive:
         if self.config["traffic_density"] != 0.0:
             raise NotImplementedError("multi-agent envs with IDM traffic are not covered")
         lid = self.config["vehicle_config"]["lidar"]
-        if lid["num_others"] != 0 or lid["gaussian_noise"] != 0 or lid["dropout_prob"] != 0:
-            raise NotImplementedError("lidar num_others / noise are not covered yet")
+        if lid["gaussian_noise"] != 0 or lid["dropout_prob"] != 0 or lid["add_others_navi"]:
+            raise NotImplementedError("lidar noise / add_others_navi are not covered yet")
         self._lib = MultiAgentLibrary(self.ASSET)
         self.num_agents = self.config["num_agents"]
         if self.num_agents == -1:
             self.num_agents = self._lib.max_capacity
         assert 0 < self.num_agents <= self._lib.max_capacity, \
             "Too many agents! We only accept {} agents, but you have {} agents!".format(self._lib.max_capacity, self.num_agents)
-        self._obs_box = _box(-0.0, 1.0, (19 + lid["num_lasers"], ))
+        self._obs_box = _box(-0.0, 1.0, (19 + 4 * lid["num_others"] + lid["num_lasers"], ))
         self._act_box = _box(-1.0, 1.0, (2, ))
         self._seat_id = ["agent%d" % k for k in range(self.num_agents)] + [None]
         self._active = set(self._seat_id[:self.num_agents])

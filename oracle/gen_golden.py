@@ -76,7 +76,8 @@ def run_episode(env_cls, config, seed, actions, tag):
             actions=np.asarray(actions[:T], np.float64), veh_f=np.stack(fs), veh_i=np.stack(is_),
             obs=np.stack(obs).astype(np.float32), reward=np.asarray(rew, np.float64), cost=np.asarray(cost, np.float64),
             terminated=np.asarray(term, bool), truncated=np.asarray(trunc, bool), info=np.asarray(infos, np.float64),
-            config=json.dumps({k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))}),
+            config=json.dumps(dict({k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))},
+                                   num_others=int(env.config["vehicle_config"]["lidar"]["num_others"]))),
             **{"init_" + k: v for k, v in init.items()},
         )
         sb = rx.export_static_bodies(env.engine)
@@ -351,6 +352,10 @@ def main():
          dict(map=3, traffic_density=0.3, num_scenarios=20, start_seed=0, log_level=50), 11, smooth),
         ("cfg2_SCO_nolimit", MetaDriveEnv, dict(map="SCO", traffic_density=0.2, log_level=50), 0,
          np.stack([np.zeros(args.steps), np.full(args.steps, 0.3)], 1)),
+        # lidar.num_others = 4 (component/sensors/lidar.py:93-138): the 4 nearest vehicles precede the lidar floats
+        ("cfg2_pg3_seed11_others4", MetaDriveEnv,
+         dict(map=3, traffic_density=0.3, num_scenarios=20, start_seed=0, log_level=50,
+              vehicle_config=dict(lidar=dict(num_others=4))), 11, smooth),
         # BASELINE config 4: SafeMetaDriveEnv with static obstacles
         ("cfg4_safe_seed2", SafeMetaDriveEnv, dict(num_scenarios=20, start_seed=0, log_level=50), 2, smooth),
         ("cfg4_safe_seed5", SafeMetaDriveEnv, dict(num_scenarios=20, start_seed=0, log_level=50), 5, smooth),

@@ -98,6 +98,7 @@ def golden_world(g, replicas=1, slots=None, objs=None, **cfg_kw):
         kw.update(crash_vehicle_done=0, crash_object_done=0)
     if "horizon" in conf and conf["horizon"]:
         kw["horizon"] = int(conf["horizon"])
+    kw["num_others"] = int(conf.get("num_others", 0))
     kw.update(cfg_kw)
     cfg = make_config(replicas, S, 1, O, **kw)
     return arrays, cfg, geo

@@ -104,16 +104,19 @@ def _ma_act(env, action):
     return obs, reward, terminated, truncated, info
 
 
-@pytest.mark.parametrize("num_agents", [1, 4, 8])
-def test_ma_roundabout_env_surface(num_agents):
+@pytest.mark.parametrize("num_agents,num_others", [(1, 8), (1, 0), (4, 8), (4, 0), (8, 0)])
+def test_ma_roundabout_env_surface(num_agents, num_others):
     """metadrive/tests/test_env/test_ma_roundabout_env.py:80-103: spaces, key bookkeeping, no done at step 0."""
     from metadrive_ped_b200 import MultiAgentRoundaboutEnv
-    env = MultiAgentRoundaboutEnv({"num_agents": num_agents, "delay_done": 0})
+    env = MultiAgentRoundaboutEnv({"num_agents": num_agents, "delay_done": 0,
+                                   "vehicle_config": {"lidar": {"num_others": num_others}}})
     try:
         obs, info = env.reset()
         assert set(obs.keys()) == {"agent%d" % k for k in range(num_agents)} == set(env.agents.keys())
         assert env.observation_space.contains(obs)
-        assert obs["agent0"].shape == (19 + 72, )  # multi-agent default lidar: 72 lasers, 40 m
+        assert obs["agent0"].shape == (19 + 4 * num_others + 72, )  # multi-agent default lidar: 72 lasers, 40 m
+        if num_others and num_agents > 1:
+            assert any(o[19:19 + 4 * num_others].any() for o in obs.values()), "neighbours show up in the others block"
         for step in range(100):
             act = {k: [1, 1] for k in env.agents.keys()}
             o, r, tm, tc, i = _ma_act(env, act)

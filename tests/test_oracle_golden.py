@@ -10,7 +10,7 @@ from tests.golden_util import golden_world, is_ma, list_golden, load_golden
 # the pose comparison from that step on.  cfg2_pg3_seed11_dense: two same-type cars spawned at the same longitude on
 # adjacent lanes; `min_front_long > long > 0` (policy/idm_policy.py:110-117) sees long = +1e-15 in float64 and
 # exactly 0 in float32, so the creep / change-lane branch differs (DESIGN.md "Known knife edges").
-KNIFE_EDGES = {"cfg2_pg3_seed11_dense": {5: 24}}
+KNIFE_EDGES = {"cfg2_pg3_seed11_dense": {5: 24}, "cfg2_pg3_seed11_others4": {5: 24}}
 
 
 SINGLE = [t for t in list_golden() if not t.startswith("cfg3")]
@@ -106,10 +106,12 @@ def test_oracle_replays_reference_trace(tag, oracle_lib):
     obs0 = sim.reset_observe().copy()
     np.testing.assert_allclose(obs0[0, :19], g["obs"][0][:19], atol=1e-5, rtol=0)
     np.testing.assert_allclose(obs0[0, 19:], g["obs"][0][19:], atol=1e-5, rtol=1e-4)
+    K4 = 4 * cfg.num_others  # lidar.num_others block between the state and the lidar floats
+    assert obs0.shape[1] == 19 + K4 + cfg.n_lasers == g["obs"].shape[1]
     T, n = len(g["reward"]), g["veh_f"].shape[1]
     skip = KNIFE_EDGES.get(tag, {})
     events = np.asarray(g["respawn_events"]).reshape(-1, 5) if "respawn_events" in g else np.zeros((0, 5))
-    n_glance = 0
+    n_glance = others_checked = 0
     for t in range(T):
         obs, r, te, tr = sim.step(g["actions"][t])
         for e in np.nonzero(events[:, 0] == t)[0]:
@@ -141,9 +143,13 @@ def test_oracle_replays_reference_trace(tag, oracle_lib):
         np.testing.assert_allclose(sim.info_f[0, [0, 1, 2, 5, 6, 7]], g["info"][t][[0, 1, 2, 5, 6, 7]], atol=2e-3, rtol=1e-4)
         np.testing.assert_allclose(obs[0, :19], g["obs"][t + 1][:19], atol=5e-4, rtol=0)
         ego_pose_ok = 0 not in skip
+        if K4 and (not skip or t < min(skip.values())):
+            np.testing.assert_allclose(obs[0, 19:19 + K4], g["obs"][t + 1][19:19 + K4], atol=5e-4, rtol=0)
+            others_checked += 1
         if ego_pose_ok and not skip:
-            n_glance += glancing_rays(obs[0, 19:], g["obs"][t + 1][19:])
+            n_glance += glancing_rays(obs[0, 19 + K4:], g["obs"][t + 1][19 + K4:])
     assert n_glance <= max(2, 1e-4 * 240 * T), "%d glancing rays" % n_glance
+    assert not K4 or others_checked >= 20
 
 
 def test_golden_covers_the_interesting_cases():
