@@ -14,6 +14,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -23,7 +24,26 @@
 #include "md_device.cuh"
 
 #define STEP_THREADS 128
+// register caps per kernel (__maxnreg__): the block size is a run-time choice (envs per CTA x slots per env), so the
+// occupancy is steered through the register budget instead of __launch_bounds__
+#ifndef PRE_REGS
+#define PRE_REGS 48
+#endif
+#ifndef DYN_REGS
+#define DYN_REGS 96
+#endif
+#ifndef POST_REGS
+#define POST_REGS 80
+#endif
+#ifndef PRE_EPB
+#define PRE_EPB 32
+#endif
+#ifndef POST_EPB
+#define POST_EPB 16
+#endif
+#ifndef DYN_EPB
 #define DYN_EPB 8
+#endif
 #define LIDAR_WARPS 8
 #define MAX_LASERS 512
 
@@ -483,6 +503,33 @@ __device__ __forceinline__ int dynamic_contacts(const Nb* nb, float* obj, int S,
     return flags;
 }
 
+// the same contact rules over a candidate bit set (k_dyn's per-step broad phase): bit k < S = vehicle slot k, else object k - S
+__device__ __forceinline__ int contact_pass(const Nb* nb, float* obj, int S, int slot, const Rect& r, unsigned long long lo,
+                                            unsigned long long hi, int* obj_first, bool claim_pass, bool objects_only) {
+    int flags = 0;
+    for (int half = 0; half < 2; half++) {
+        for (unsigned long long mk = half ? hi : lo; mk; mk &= mk - 1) {
+            const int k = __ffsll((long long)mk) - 1 + 64 * half;
+            if (k < S) {
+                if (!objects_only && rect_rect(r, nb[k].r)) flags |= FL_CRASH_VEHICLE;
+                continue;
+            }
+            const int ko = k - S;
+            const float* Ob = obj + ko * OBJ_F;
+            bool hit;
+            if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
+            else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
+            if (!hit) continue;
+            if (Ob[OB_KIND] == 3.0f) flags |= FL_CRASH_HUMAN;
+            else if (Ob[OB_CRASHED] == 0.0f) {
+                if (claim_pass) atomicMin(&obj_first[ko], slot);          // COST_ONCE: lowest slot takes the flag
+                else if (obj_first[ko] == slot) flags |= FL_CRASH_OBJECT;
+            }
+        }
+    }
+    return flags;
+}
+
 // reward / cost / done + the 19 state floats of the observation for one agent
 // (envs/metadrive_env.py:128-279, envs/base_env.py:586-623, obs/state_obs.py:64-151)
 __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_step, const float* P, const float* S, float* C,
@@ -704,8 +751,7 @@ __device__ __forceinline__ void stage_objects(const StepGeom& G, const float* __
 }
 
 // ---- k_pre: engine.before_step (agent actuation, traffic trigger, IDM decisions) ------------------------------
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __maxnreg__(PRE_REGS)
 k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ actions, float* __restrict__ idm_out,
       float4* __restrict__ veh_act) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -798,8 +844,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
 }
 
 // ---- k_dyn: engine.step = n_sub x doPhysics + contact-added callback (engine/base_engine.py:417-445) --------------
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __maxnreg__(DYN_REGS)
 k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ veh_act, const float* __restrict__ ext_act3,
       int n_sub) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -832,6 +877,48 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     B.v = f3(St[VS_VEL], St[VS_VEL + 1], St[VS_VEL + 2]);
     B.w = f3(St[VS_ANGVEL], St[VS_ANGVEL + 1], St[VS_ANGVEL + 2]);
     const bool moves = G.work && alive && !is_static;
+    // Contact candidates of this step (the broad phase): bit k of (cand_lo, cand_hi) = body k (vehicle slot k < S, object
+    // k - S) can come within touching distance during the n_sub sub-steps: centre distance at the start of the step <=
+    // the two bounding radii + 1.5 x the distance both can travel + 0.5 m.  Every truly overlapping pair is a candidate
+    // (accelerations change a speed by < 1 m/s within a step), so the exact SAT below sees the same pairs as a full scan.
+    unsigned long long cand_lo = 0ull, cand_hi = 0ull;
+    int block_any = 0, block_obj = 0;
+    if (contacts) {
+        if (G.work && alive) {
+            const Rect r0 = vehicle_rect(P, St);
+            G.nb[slot].r = r0;
+            G.nb[slot].vx = sqrtf(r0.hu * r0.hu + r0.hv * r0.hv);                                  // bounding radius
+            G.nb[slot].vy = sqrtf(B.v.x * B.v.x + B.v.y * B.v.y + B.v.z * B.v.z);                  // speed
+        }
+        __syncthreads();
+        bool has_obj = false;
+        if (G.work && alive) {
+            const float T = 1.5f * cfg.dt * (float)n_sub;
+            const Rect r0 = G.nb[slot].r;
+            const float my_rad = G.nb[slot].vx + 0.5f, my_speed = G.nb[slot].vy;
+            for (int k = 0; k < S; k++) {
+                if (k == slot || !G.nb[k].alive) continue;
+                const float dx = G.nb[k].r.cx - r0.cx, dy = G.nb[k].r.cy - r0.cy;
+                const float reach = my_rad + G.nb[k].vx + (my_speed + G.nb[k].vy) * T;
+                if (dx * dx + dy * dy <= reach * reach) { if (k < 64) cand_lo |= 1ull << k; else cand_hi |= 1ull << (k - 64); }
+            }
+            for (int k = 0; k < O; k++) {
+                const float* Ob = G.sobj + k * OBJ_F;
+                if (Ob[OB_KIND] < 0.0f) continue;
+                const float orad = Ob[OB_KIND] == 2.0f ? sqrtf(Ob[OB_A] * Ob[OB_A] + Ob[OB_B] * Ob[OB_B]) : Ob[OB_A];
+                const float ospeed = Ob[OB_KIND] == 3.0f ? sqrtf(Ob[OB_VX] * Ob[OB_VX] + Ob[OB_VY] * Ob[OB_VY]) : 0.0f;
+                const float dx = Ob[OB_X] - r0.cx, dy = Ob[OB_Y] - r0.cy;
+                const float reach = my_rad + orad + (my_speed + ospeed) * T;
+                if (dx * dx + dy * dy <= reach * reach) {
+                    const int b = S + k;
+                    if (b < 64) cand_lo |= 1ull << b; else cand_hi |= 1ull << (b - 64);
+                    has_obj = true;
+                }
+            }
+        }
+        block_any = __syncthreads_or((cand_lo | cand_hi) != 0ull);
+        block_obj = __syncthreads_or(has_obj);
+    }
     SteerCS scs;
     scs.cs = cosf(act.steer_rad); scs.sn = sinf(act.steer_rad);
     for (int rep = 0; rep < n_sub; rep++) {
@@ -840,7 +927,7 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
             St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y; St[VS_POS + 2] = B.pos.z;
             St[VS_QUAT] = B.q[0]; St[VS_QUAT + 1] = B.q[1]; St[VS_QUAT + 2] = B.q[2]; St[VS_QUAT + 3] = B.q[3];
         }
-        if (contacts) {
+        if (contacts && block_any) {  // a CTA without candidate pairs has no contact this step: no exchange, no barriers
             __syncthreads();  // everyone finished reading the previous footprints
             if (G.work) {
                 if (alive) G.nb[slot].r = vehicle_rect(P, St);
@@ -851,14 +938,19 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
                 }
             }
             __syncthreads();
-            if (G.work && alive) flags |= dynamic_contacts(G.nb, G.sobj, S, O, slot, G.nb[slot].r, true, G.obj_first, true);
-            if (O > 0) {  // COST_ONCE needs the claims of every vehicle before anyone reads them
+            if (cand_lo | cand_hi) flags |= contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, true, false);
+            if (block_obj) {  // COST_ONCE needs the claims of every vehicle before anyone reads them
                 __syncthreads();
-                if (G.work && alive) flags |= dynamic_contacts(G.nb, G.sobj, 0, O, slot, G.nb[slot].r, true, G.obj_first, false);
+                if (cand_lo | cand_hi) flags |= contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, false, true);
                 __syncthreads();
                 if (G.work)
                     for (int k = slot; k < O; k += S)
                         if (G.obj_first[k] != 0x7fffffff) G.sobj[k * OBJ_F + OB_CRASHED] = 1.0f;
+            }
+        } else if (contacts && G.work) {
+            for (int k = slot; k < O; k += S) {  // nobody looks: the pedestrians still walk, in the same increments
+                float* Ob = G.sobj + k * OBJ_F;
+                if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
             }
         }
     }
@@ -888,8 +980,7 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
 
 // ---- k_post: engine.after_step + _get_step_return (base_vehicle.py:234-271; envs/base_env.py:586-623) -----------
 // MODE_RESET: the reset-time variant (envs/base_env.py:560-584) for the envs selected by env_mask
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __maxnreg__(POST_REGS)
 k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restrict__ body_tab,
        const uint8_t* __restrict__ env_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1592,79 +1683,63 @@ extern "C" int md_set_state(md_sim* sim, const char* name, const void* host_src,
 }
 
 // CTA geometry shared by k_pre / k_dyn / k_post: EPB envs per CTA, EPB * S threads, launch bound MAXT >= threads
-struct StepLaunch { int epb, threads, blocks, maxt; size_t smem; };
-// epb_pref = 32 makes a warp "one slot index of 32 envs" (uniform roles: k_pre, k_post); k_dyn has no role divergence
-// and prefers small CTAs (more resident CTAs, cheaper barriers, no register cap)
-static StepLaunch step_launch(const MdConfig& c, int epb_pref = 32) {
+struct StepLaunch { int epb, threads, blocks; size_t smem; };
+// epb = 32 makes a warp "one slot index of 32 envs" (uniform roles: k_pre, k_post); k_dyn has no role divergence and
+// prefers small CTAs (more resident CTAs, cheaper barriers).  MD_EPB_PRE / MD_EPB_POST / MD_EPB_DYN override (tuning).
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+static StepLaunch step_launch(const MdConfig& c, int epb_pref) {
     StepLaunch L;
     L.epb = epb_pref;
     while (L.epb > 1 && L.epb * c.slots_per_env > 1024) L.epb >>= 1;
     L.threads = (L.epb * c.slots_per_env + 31) & ~31;
     L.blocks = (c.n_envs + L.epb - 1) / L.epb;
-    L.maxt = L.threads <= 256 ? 256 : (L.threads <= 512 ? 512 : (L.threads <= 640 ? 640 : (L.threads <= 768 ? 768 : 1024)));
     L.smem = step_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb);
     return L;
 }
-#define DISPATCH_MAXT(L, KERNEL, ...)                                                                                 \
-    do {                                                                                                              \
-        switch ((L).maxt) {                                                                                           \
-            case 256: KERNEL<256><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
-            case 512: KERNEL<512><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
-            case 640: KERNEL<640><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
-            case 768: KERNEL<768><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
-            default: KERNEL<1024><<<(L).blocks, (L).threads, (L).smem, st>>>(__VA_ARGS__); break;                      \
-        }                                                                                                             \
-    } while (0)
+static int epb_pre() { static int v = env_int("MD_EPB_PRE", PRE_EPB); return v; }
+static int epb_post() { static int v = env_int("MD_EPB_POST", POST_EPB); return v; }
+static int epb_dyn() { static int v = env_int("MD_EPB_DYN", DYN_EPB); return v; }
 
 template <typename K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
-// dynamic shared memory above the 48 KB default needs an opt-in per kernel instantiation
+// dynamic shared memory above the 48 KB default needs an opt-in per kernel
 static int opt_in_smem(md_sim* sim) {
-    {   // k_dyn runs with its own (smaller) CTA geometry
-        StepLaunch D = step_launch(sim->cfg, DYN_EPB);
-        size_t b = D.smem > 48 * 1024 ? D.smem : 48 * 1024;
-        switch (D.maxt) {
-            case 256: CK(allow_smem(k_dyn<256>, b)); break;
-            case 512: CK(allow_smem(k_dyn<512>, b)); break;
-            case 640: CK(allow_smem(k_dyn<640>, b)); break;
-            case 768: CK(allow_smem(k_dyn<768>, b)); break;
-            default: CK(allow_smem(k_dyn<1024>, b)); break;
-        }
+    const size_t floor48 = 48 * 1024;
+    StepLaunch D = step_launch(sim->cfg, epb_dyn()), A = step_launch(sim->cfg, epb_pre()), B = step_launch(sim->cfg, epb_post());
+    if (A.smem > 200 * 1024 || B.smem > 200 * 1024 || D.smem > 200 * 1024) {
+        sim->err = "slots/objects per env need more than 200 KB of shared memory per CTA";
+        return -4;
     }
-    StepLaunch L = step_launch(sim->cfg);
-    if (L.smem > 200 * 1024) { sim->err = "slots/objects per env need more than 200 KB of shared memory per CTA"; return -4; }
-    size_t b = L.smem > 48 * 1024 ? L.smem : 48 * 1024;
-    switch (L.maxt) {
-        case 256: CK(allow_smem(k_pre<256>, b)); CK(allow_smem(k_post<256>, b)); break;
-        case 512: CK(allow_smem(k_pre<512>, b)); CK(allow_smem(k_post<512>, b)); break;
-        case 640: CK(allow_smem(k_pre<640>, b)); CK(allow_smem(k_post<640>, b)); break;
-        case 768: CK(allow_smem(k_pre<768>, b)); CK(allow_smem(k_post<768>, b)); break;
-        default: CK(allow_smem(k_pre<1024>, b)); CK(allow_smem(k_post<1024>, b)); break;
-    }
+    CK(allow_smem(k_dyn, D.smem > floor48 ? D.smem : floor48));
+    CK(allow_smem(k_pre, A.smem > floor48 ? A.smem : floor48));
+    CK(allow_smem(k_post, B.smem > floor48 ? B.smem : floor48));
     size_t lb = lidar_smem_per_warp(sim->cfg.slots_per_env, sim->cfg.objs_per_env) * LIDAR_WARPS;
-    if (lb > 48 * 1024) CK(allow_smem(k_lidar, lb));
+    if (lb > floor48) CK(allow_smem(k_lidar, lb));
     return 0;
 }
 
 static int launch_pre(md_sim* sim, int mode, const float* actions, float* idm_out, cudaStream_t st) {
-    StepLaunch L = step_launch(sim->cfg);
-    DISPATCH_MAXT(L, k_pre, sim->cfg, sim->dev, mode, L.epb, actions, idm_out, sim->veh_act);
+    StepLaunch L = step_launch(sim->cfg, epb_pre());
+    k_pre<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, actions, idm_out, sim->veh_act);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 static int launch_dyn(md_sim* sim, int mode, const float* ext_act3, int n_sub, cudaStream_t st) {
-    StepLaunch L = step_launch(sim->cfg, DYN_EPB);
-    DISPATCH_MAXT(L, k_dyn, sim->cfg, sim->dev, mode, L.epb, sim->veh_act, ext_act3, n_sub);
+    StepLaunch L = step_launch(sim->cfg, epb_dyn());
+    k_dyn<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, sim->veh_act, ext_act3, n_sub);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 static int launch_post(md_sim* sim, int mode, StepOut out, const uint8_t* mask, cudaStream_t st) {
-    StepLaunch L = step_launch(sim->cfg);
-    DISPATCH_MAXT(L, k_post, sim->cfg, sim->dev, mode, L.epb, out, sim->body_tab, mask);
+    StepLaunch L = step_launch(sim->cfg, epb_post());
+    k_post<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, out, sim->body_tab, mask);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;

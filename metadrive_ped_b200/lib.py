@@ -7,7 +7,7 @@ import subprocess
 from .abi import MdArrays, MdConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdstep.so")
+LIB_PATH = os.environ.get("MD_LIB") or os.path.join(_HERE, "libmdstep.so")  # MD_LIB: a tuning build of the same sources
 _lib = None
 
 EXPORTS = [
