@@ -33,7 +33,7 @@
 #define DYN_REGS 96
 #endif
 #ifndef POST_REGS
-#define POST_REGS 80
+#define POST_REGS 128
 #endif
 #ifndef PRE_EPB
 #define PRE_EPB 32
@@ -645,34 +645,6 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
     for (int k = 0; k < NAVI_DIM; k++) o[OBS_EGO + k] = navi[k];
 }
 
-// BaseVehicle.after_step for one vehicle (component/vehicle/base_vehicle.py:234-271): localisation, state check
-// against the static world and the env's other bodies, side distances, energy.  `nb` = the env's footprints.
-__device__ __forceinline__ void after_step_vehicle(const MapView& m, const float* St, float* C, int* I,
-                                                   const int* __restrict__ route, const int* __restrict__ rroad, float* navi,
-                                                   const Nb* nb, float* sobj, int S, int O, int slot, const Rect& r,
-                                                   int* obj_first) {
-    localise(m, St, I, route, rroad, navi);
-    int flags = I[VI_FLAGS];
-    state_check_static(m, r, flags);
-    flags |= dynamic_contacts(nb, sobj, S, O, slot, r, false, obj_first, false);
-    I[VI_FLAGS] = flags;
-    int cur_road = rroad[I[VI_CKPT0]];
-    int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
-    float lon, lat;
-    lane_local(m.lane_f + cur_first * LANE_F, St[VS_POS], St[VS_POS + 1], lon, lat);
-    float lane_w = m.lane_f[I[VI_LANE] * LANE_F + LF_WIDTH];
-    float to_left = lat + lane_w / 2.0f;
-    float to_right = lane_w * (float)cur_n - to_left;
-    C[VC_DIST_L] = to_left; C[VC_DIST_R] = to_right;
-    if (to_right < 0.0f || to_left < 0.0f) I[VI_FLAGS] |= FL_OUT_OF_ROUTE;
-    float dx = C[VC_LAST_X] - St[VS_POS], dy = C[VC_LAST_Y] - St[VS_POS + 1];
-    float dist_km = sqrtf(dx * dx + dy * dy) / 1000.0f;
-    float speed_kmh = sqrtf(St[VS_VEL] * St[VS_VEL] + St[VS_VEL + 1] * St[VS_VEL + 1]) * 3.6f;
-    float step_energy = 3.25f * expf(0.01f * speed_kmh) * dist_km / 100.0f * 1000.0f;
-    C[VC_STEP_ENERGY] = step_energy;
-    C[VC_ENERGY] += step_energy;
-}
-
 __device__ __forceinline__ void load16(float* dst, const float* src) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
@@ -979,141 +951,225 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
 }
 
 // ---- k_post: engine.after_step + _get_step_return (base_vehicle.py:234-271; envs/base_env.py:586-623) -----------
-// MODE_RESET: the reset-time variant (envs/base_env.py:560-584) for the envs selected by env_mask
+// MODE_RESET: the reset-time variant (envs/base_env.py:560-584) for the envs selected by env_mask.
+// A CTA owns `epb` envs and runs POST_WORKERS threads.  Phase 1: the threads sweep the epb x S slot rows (coalesced),
+// publish every alive vehicle's footprint in shared memory and append the vehicles that have after_step work (the active
+// ones: the agent and the triggered traffic) to a work list.  Phase 2: one thread per listed vehicle - so the warps are
+// dense with vehicles that all run the same code, instead of one thread per slot with most lanes idle.  Phase 3
+// (respawn / hybrid traffic only): vehicles that left the lanes are replaced, tape rows handed out in slot order.
+struct __align__(16) Fp { Rect r; int alive; int mark; };   // footprint record of one slot (32 B)
+#ifndef POST_WORKERS
+#define POST_WORKERS 128
+#endif
+__host__ __device__ inline size_t post_smem_bytes(int S, int O, int epb) {
+    return (sizeof(Fp) + sizeof(int)) * (size_t)S * epb + sizeof(float) * OBJ_F * (size_t)O * epb + 16 + sizeof(int) * (size_t)epb;
+}
+__device__ __forceinline__ int fp_contacts(const Fp* fp, const float* obj, int S, int O, int slot, const Rect& r) {
+    int flags = 0;  // BaseVehicle._state_check, dynamic world part (component/vehicle/base_vehicle.py:735-742): no latch
+    for (int k = 0; k < S; k++) {
+        if (k == slot || !fp[k].alive) continue;
+        if (rect_rect(r, fp[k].r)) flags |= FL_CRASH_VEHICLE;
+    }
+    for (int k = 0; k < O; k++) {
+        const float* Ob = obj + k * OBJ_F;
+        if (Ob[OB_KIND] < 0.0f) continue;
+        bool hit;
+        if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
+        else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
+        if (hit) flags |= Ob[OB_KIND] == 3.0f ? FL_CRASH_HUMAN : FL_CRASH_OBJECT;
+    }
+    return flags;
+}
+// BaseVehicle.after_step for one vehicle (component/vehicle/base_vehicle.py:234-271): localisation, state check
+// against the static world and the env's other bodies, side distances, energy.  `fp` = the env's footprints.
+__device__ __forceinline__ void after_step_vehicle(const MapView& m, const float* St, float* C, int* I,
+                                                   const int* __restrict__ route, const int* __restrict__ rroad, float* navi,
+                                                   const Fp* fp, const float* sobj, int S, int O, int slot, const Rect& r) {
+    localise(m, St, I, route, rroad, navi);
+    int flags = I[VI_FLAGS];
+    state_check_static(m, r, flags);
+    flags |= fp_contacts(fp, sobj, S, O, slot, r);
+    I[VI_FLAGS] = flags;
+    int cur_road = rroad[I[VI_CKPT0]];
+    int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+    float lon, lat;
+    lane_local(m.lane_f + cur_first * LANE_F, St[VS_POS], St[VS_POS + 1], lon, lat);
+    float lane_w = m.lane_f[I[VI_LANE] * LANE_F + LF_WIDTH];
+    float to_left = lat + lane_w / 2.0f;
+    float to_right = lane_w * (float)cur_n - to_left;
+    C[VC_DIST_L] = to_left; C[VC_DIST_R] = to_right;
+    if (to_right < 0.0f || to_left < 0.0f) I[VI_FLAGS] |= FL_OUT_OF_ROUTE;
+    float dx = C[VC_LAST_X] - St[VS_POS], dy = C[VC_LAST_Y] - St[VS_POS + 1];
+    float dist_km = sqrtf(dx * dx + dy * dy) / 1000.0f;
+    float speed_kmh = sqrtf(St[VS_VEL] * St[VS_VEL] + St[VS_VEL + 1] * St[VS_VEL + 1]) * 3.6f;
+    float step_energy = 3.25f * expf(0.01f * speed_kmh) * dist_km / 100.0f * 1000.0f;
+    C[VC_STEP_ENERGY] = step_energy;
+    C[VC_ENERGY] += step_energy;
+}
+
 __global__ void __maxnreg__(POST_REGS)
 k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restrict__ body_tab,
        const uint8_t* __restrict__ env_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    StepGeom G = step_geom(cfg, epb, smem_raw);
-    if (G.work && env_mask != nullptr && env_mask[G.env] == 0) G.work = false;
-    const int S = G.S, slot = G.slot, env = G.env, g = G.g;
-    float P[VEH_P], St[VEH_S], C[VEH_C], navi[NAVI_DIM];
-    int I[VEH_I];
-    bool occ = false;  // empty slots: one 64-byte read, a dead footprint, nothing else (they still help staging)
-    if (G.work) {
-        load16i(I, A.veh_i + (size_t)g * VEH_I);
-        occ = I[VI_KIND] != 0;
-        if (!occ) G.nb[slot].alive = 0;
-    }
-    if (occ) {
-        load16(P, A.veh_p + (size_t)g * VEH_P);
-        load16(St, A.veh_s + (size_t)g * VEH_S);
-        load16(C, A.veh_c + (size_t)g * VEH_C);
-#pragma unroll
-        for (int k = 0; k < NAVI_DIM; k++) navi[k] = A.veh_navi[(size_t)g * NAVI_DIM + k];
-        G.nb[slot].r = vehicle_rect(P, St);
-        G.nb[slot].alive = I[VI_ALIVE];
-    }
-    stage_objects(G, A.obj_f);
-    const bool is_agent = occ && I[VI_KIND] == 1;
-    const bool is_traffic = occ && I[VI_KIND] == 2;
-    if ((mode & MODE_RESET) && occ && I[VI_ALIVE] && (is_agent || is_traffic)) latch_before_step(St, C, I);
+    const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
+    const int n_rows = epb * S, env0 = blockIdx.x * epb;
+    Fp* fp_all = reinterpret_cast<Fp*>(smem_raw);
+    float* obj_all = reinterpret_cast<float*>(smem_raw + sizeof(Fp) * (size_t)n_rows);
+    int* list = reinterpret_cast<int*>(smem_raw + sizeof(Fp) * (size_t)n_rows + sizeof(float) * OBJ_F * (size_t)O * epb);
+    int* n_list = list + n_rows;
+    int* ctr_base = n_list + 4;   // per env: EI_RNG before this step's respawns
+    if (threadIdx.x == 0) *n_list = 0;
+    for (int le = threadIdx.x; le < epb; le += blockDim.x)
+        ctr_base[le] = env0 + le < cfg.n_envs ? A.env_i[(env0 + le) * ENV_I + EI_RNG] : 0;
     __syncthreads();
-    MapView m;
-    int env_step = 0;
-    if (G.work) { m = map_view(A, A.env_i[env * ENV_I + EI_MAP]); env_step = A.env_i[env * ENV_I + EI_STEP]; }
-    const int* rroad = A.veh_rroad + (size_t)g * ROUTE_MAX;
-    const bool do_post = (mode & (MODE_POST | MODE_RESET)) && occ && I[VI_ALIVE] &&
-                         ((mode & MODE_RESET) ? (is_agent || is_traffic) : (I[VI_ACTIVE] != 0));
-    if (do_post) {
+    // ---- phase 1: footprints + work list (row v = env_local * S + slot, the order of the global rows)
+    for (int v = threadIdx.x; v < n_rows; v += blockDim.x) {
+        const int le = v / S, slot = v - le * S, env = env0 + le;
+        Fp& f = fp_all[v];
+        f.alive = 0; f.mark = 0;
+        if (env >= cfg.n_envs || (env_mask != nullptr && env_mask[env] == 0)) continue;
+        const size_t g = (size_t)env * S + slot;
+        const int4 i0 = *reinterpret_cast<const int4*>(A.veh_i + g * VEH_I);  // kind, alive, active, trigger
+        const int kind = i0.x, alive = i0.y, active = i0.z;
+        if (kind == 0) continue;
+        const bool has_work = alive && ((mode & MODE_RESET) ? (kind == 1 || kind == 2) : ((mode & MODE_POST) && active));
+        if (alive) {
+            float P4[4], St[VEH_S];
+            const float4 p0 = *reinterpret_cast<const float4*>(A.veh_p + g * VEH_P);
+            P4[0] = p0.x; P4[1] = p0.y; P4[2] = p0.z; P4[3] = p0.w;  // type, length, width, height
+            load16(St, A.veh_s + g * VEH_S);
+            f.r = vehicle_rect(P4, St);
+            f.alive = 1;
+            if (!has_work) write_body_row(body_tab + g * BODY_ROW, P4, St, 1);
+        } else body_tab[g * BODY_ROW + 15] = 0.0f;
+        if (has_work) list[atomicAdd(n_list, 1)] = v;
+        else if ((mode & MODE_OUT) && cfg.is_multi_agent && slot < NA) {
+            const size_t a = (size_t)env * NA + slot;  // an empty or wrecked seat produces no transition
+            out.reward[a] = 0.0f; out.cost[a] = 0.0f; out.term[a] = 0; out.trunc[a] = 0; out.info_flags[a] = 0;
+        }
+    }
+    for (int k = threadIdx.x; k < epb * O * OBJ_F; k += blockDim.x) {
+        const int env = env0 + k / (O * OBJ_F);
+        if (env < cfg.n_envs) obj_all[k] = A.obj_f[(size_t)env0 * O * OBJ_F + k];
+    }
+    __syncthreads();
+    // ---- phase 2: one thread per vehicle with work
+    const int n_work = *n_list;
+    for (int j = threadIdx.x; j < n_work; j += blockDim.x) {
+        const int v = list[j], le = v / S, slot = v - le * S, env = env0 + le;
+        const size_t g = (size_t)env * S + slot;
+        const Fp* fp = fp_all + (size_t)le * S;
+        const float* sobj = obj_all + (size_t)le * O * OBJ_F;
+        float P[VEH_P], St[VEH_S], C[VEH_C], navi[NAVI_DIM];
+        int I[VEH_I];
+        load16i(I, A.veh_i + g * VEH_I);
+        load16(P, A.veh_p + g * VEH_P);
+        load16(St, A.veh_s + g * VEH_S);
+        load16(C, A.veh_c + g * VEH_C);
+#pragma unroll
+        for (int k = 0; k < NAVI_DIM; k++) navi[k] = A.veh_navi[g * NAVI_DIM + k];
+        const bool is_agent = I[VI_KIND] == 1, is_traffic = I[VI_KIND] == 2;
+        if (mode & MODE_RESET) latch_before_step(St, C, I);
+        const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+        const int env_step = A.env_i[env * ENV_I + EI_STEP];
+        const int* rroad = A.veh_rroad + g * ROUTE_MAX;
         if (mode & MODE_CLEAR_FLAGS) I[VI_FLAGS] = FL_ON_LANE;
-        after_step_vehicle(m, St, C, I, A.veh_route + (size_t)g * ROUTE_MAX, rroad, navi, G.nb, G.sobj, S, G.O, slot,
-                           G.nb[slot].r, G.obj_first);
+        after_step_vehicle(m, St, C, I, A.veh_route + g * ROUTE_MAX, rroad, navi, fp, sobj, S, O, slot, fp[slot].r);
         if ((mode & MODE_RESET) && !I[VI_ACTIVE]) I[VI_FLAGS] = FL_ON_LANE;  // reset() ends with _init_step_info
-    }
-    // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111) ...
-    const bool leaves = (mode & MODE_REMOVE) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE] && !(I[VI_FLAGS] & FL_ON_LANE);
-    if (leaves) { I[VI_ALIVE] = 0; I[VI_ACTIVE] = 0; }
-    // ... and in respawn / hybrid mode comes back as a new vehicle of the same class on a random respawn lane (:112-121).
-    // Tape rows are handed out in slot order, like the sequential loop of the reference.
-    if ((mode & MODE_REMOVE) && cfg.traffic_mode != 0) {
-        uint32_t ctr = 0;
-        int n_places = 0;
-        if (G.work) {
-            G.nb[slot].active = leaves ? 2 : 0;
-            ctr = (uint32_t)A.env_i[env * ENV_I + EI_RNG];
-            n_places = A.env_i[env * ENV_I + EI_N_PLACES];
+        // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111); in respawn /
+        // hybrid mode phase 3 brings it back as a new vehicle
+        if ((mode & MODE_REMOVE) && is_traffic && I[VI_ACTIVE] && !(I[VI_FLAGS] & FL_ON_LANE)) {
+            I[VI_ALIVE] = 0; I[VI_ACTIVE] = 0;
+            fp_all[v].mark = 2;
         }
-        __syncthreads();
-        if (G.work && n_places > 0) {
-            int rank = 0, total = 0;
-            for (int k = 0; k < S; k++) {
-                const int lv = G.nb[k].active == 2;
-                total += lv;
-                if (k < slot) rank += lv;
-            }
-            if (slot == 0 && total) A.env_i[env * ENV_I + EI_RNG] = (int)(ctr + (uint32_t)total);
-            if (leaves) {
-                ctr += (uint32_t)rank;
-                const int p = (int)(tape_draw(cfg, A.env_tape, env, ctr, 0) % (uint32_t)n_places);
-                const float frac = tape_frac(cfg, A.env_tape, env, ctr);
-                const int timer = (int)(tape_draw(cfg, A.env_tape, env, ctr, 2) % 50u);  // LANE_CHANGE_FREQ
-                const int lane = (int)A.ma_place_f[((size_t)env * cfg.ma_places + p) * 8 + 4];
-                const float* L = m.lane_f + lane * LANE_F;
-                const float lon = frac * L[LF_LENGTH] / 2.0f;
-#pragma unroll
-                for (int k = 0; k < VEH_S; k++) St[k] = 0.0f;
-#pragma unroll
-                for (int k = 0; k < VEH_C; k++) C[k] = 0.0f;
-#pragma unroll
-                for (int k = 0; k < VEH_I; k++) I[k] = 0;
-#pragma unroll
-                for (int k = 0; k < NAVI_DIM; k++) navi[k] = 0.0f;
-                lane_position(L, lon, 0.0f, St[VS_POS], St[VS_POS + 1]);
-                St[VS_POS + 2] = 0.5f * P[VP_HEIGHT];
-                yaw_quat_for_lane(L, lon, St[VS_QUAT], St[VS_QUAT + 3]);
-                const int* rt = A.ma_route + ((size_t)env * cfg.ma_places + p) * ROUTE_MAX;
-                const int* rr = A.ma_rroad + ((size_t)env * cfg.ma_places + p) * ROUTE_MAX;
-                int* vr = A.veh_route + (size_t)g * ROUTE_MAX;
-                int* vrr = A.veh_rroad + (size_t)g * ROUTE_MAX;
-                int n_ck = 0;
-                for (int k = 0; k < ROUTE_MAX; k++) { const int c = rt[k]; vr[k] = c; vrr[k] = rr[k]; if (c >= 0) n_ck++; }
-                I[VI_KIND] = 2; I[VI_ALIVE] = 1; I[VI_ACTIVE] = 1; I[VI_TRIGGER] = -1;
-                I[VI_LANE] = lane; I[VI_SPAWN_LANE] = lane;
-                I[VI_CKPT0] = 0; I[VI_CKPT1] = n_ck > 2 ? 1 : 0; I[VI_ROUTE_LEN] = n_ck;
-                I[VI_ROUTING_LANE] = -1;
-                float4* d4 = reinterpret_cast<float4*>(A.veh_idm + (size_t)g * VEH_IDM);
-                const float rng_ctr = A.veh_idm[(size_t)g * VEH_IDM + VD_RNG];
-                d4[0] = make_float4((float)timer, 30.0f, 0.0f, 0.0f);  // fresh IDMPolicy (policy/idm_policy.py:224-233)
-                d4[1] = make_float4(0.0f, 0.0f, rng_ctr, 0.0f);
-                latch_before_step(St, C, I);
-                const Rect r = vehicle_rect(P, St);
-                after_step_vehicle(m, St, C, I, vr, vrr, navi, G.nb, G.sobj, S, G.O, slot, r, G.obj_first);
-                I[VI_FLAGS] = FL_ON_LANE;  // BaseVehicle.reset ends with _init_step_info (base_vehicle.py:379)
-                store16(A.veh_s + (size_t)g * VEH_S, St);
+        // every agent observes the world as it is after engine.after_step: a vehicle that finishes this step is still
+        // visible to the others' lidar (the body row keeps the pre-finish alive flag; k_respawn clears it afterwards)
+        const int alive_row = I[VI_ALIVE];
+        if ((mode & (MODE_OUT | MODE_RESET)) && is_agent && I[VI_ACTIVE] && slot < NA) {
+            const size_t a = (size_t)env * NA + slot;
+            agent_outputs(cfg, m, env_step, P, St, C, I, rroad, navi, a, out, (mode & MODE_OUT) != 0);
+            if ((mode & MODE_OUT) && cfg.is_multi_agent) {
+                // MultiAgentMetaDrive._after_vehicle_done -> agent_manager._finish (multi_agent_metadrive.py:153-166,
+                // agent_manager.py:115-128): success leaves at once, everything else becomes a static wreck
+                const int fl = out.info_flags[a];
+                out.info_flags[a] = fl | FL_VALID;
+                if (out.term[a] || out.trunc[a]) {
+                    I[VI_ACTIVE] = 0;
+                    if ((fl & FL_ARRIVE) || cfg.delay_done <= 0) { I[VI_ALIVE] = 0; }
+                    else { I[VI_STATIC] = 1; I[VI_DYING] = cfg.delay_done; }
+                }
             }
         }
-    }
-    // every agent observes the world as it is after engine.after_step: a vehicle that finishes this step is still
-    // visible to the others' lidar (the body row keeps the pre-finish alive flag; k_respawn clears it afterwards)
-    const int alive_row = occ ? I[VI_ALIVE] : 0;
-    if ((mode & MODE_OUT) && cfg.is_multi_agent && G.work && slot < G.NA && !(is_agent && I[VI_ACTIVE])) {
-        size_t a = (size_t)env * G.NA + slot;  // an empty or wrecked seat produces no transition
-        out.reward[a] = 0.0f; out.cost[a] = 0.0f; out.term[a] = 0; out.trunc[a] = 0; out.info_flags[a] = 0;
-    }
-    if ((mode & (MODE_OUT | MODE_RESET)) && is_agent && I[VI_ACTIVE] && slot < G.NA) {
-        size_t a = (size_t)env * G.NA + slot;
-        agent_outputs(cfg, m, env_step, P, St, C, I, rroad, navi, a, out, (mode & MODE_OUT) != 0);
-        if ((mode & MODE_OUT) && cfg.is_multi_agent) {
-            // MultiAgentMetaDrive._after_vehicle_done -> agent_manager._finish (multi_agent_metadrive.py:153-166,
-            // agent_manager.py:115-128): success leaves at once, everything else becomes a static wreck
-            const int fl = out.info_flags[a];
-            out.info_flags[a] = fl | FL_VALID;
-            if (out.term[a] || out.trunc[a]) {
-                I[VI_ACTIVE] = 0;
-                if ((fl & FL_ARRIVE) || cfg.delay_done <= 0) { I[VI_ALIVE] = 0; }
-                else { I[VI_STATIC] = 1; I[VI_DYING] = cfg.delay_done; }
-            }
-        }
-    }
-    if (occ) {
-        if (do_post) {  // vehicles that were not localised this step have nothing new to store
-            store16(A.veh_c + (size_t)g * VEH_C, C);
-            store16i(A.veh_i + (size_t)g * VEH_I, I);
+        store16(A.veh_c + g * VEH_C, C);
+        store16i(A.veh_i + g * VEH_I, I);
 #pragma unroll
-            for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = navi[k];
+        for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[g * NAVI_DIM + k] = navi[k];
+        write_body_row(body_tab + g * BODY_ROW, P, St, alive_row);
+    }
+    // ---- phase 3: respawn / hybrid traffic (manager/traffic_manager.py:112-121)
+    if (!((mode & MODE_REMOVE) && cfg.traffic_mode != 0)) return;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_work; j += blockDim.x) {
+        const int v = list[j];
+        if (fp_all[v].mark != 2) continue;
+        const int le = v / S, slot = v - le * S, env = env0 + le;
+        const size_t g = (size_t)env * S + slot;
+        const Fp* fp = fp_all + (size_t)le * S;
+        const int n_places = A.env_i[env * ENV_I + EI_N_PLACES];
+        if (n_places <= 0) continue;
+        int rank = 0, total = 0;
+        for (int k = 0; k < S; k++) {
+            const int lv = fp[k].mark == 2;
+            total += lv;
+            if (k < slot) rank += lv;
         }
-        write_body_row(body_tab + (size_t)g * BODY_ROW, P, St, alive_row);
+        const uint32_t ctr = (uint32_t)ctr_base[le] + (uint32_t)rank;  // EI_RNG is advanced once, by the last leaver
+        float P[VEH_P], St[VEH_S], C[VEH_C], navi[NAVI_DIM];
+        int I[VEH_I];
+        load16(P, A.veh_p + g * VEH_P);
+        const int p = (int)(tape_draw(cfg, A.env_tape, env, ctr, 0) % (uint32_t)n_places);
+        const float frac = tape_frac(cfg, A.env_tape, env, ctr);
+        const int timer = (int)(tape_draw(cfg, A.env_tape, env, ctr, 2) % 50u);  // LANE_CHANGE_FREQ
+        const int lane = (int)A.ma_place_f[((size_t)env * cfg.ma_places + p) * 8 + 4];
+        const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+        const float* L = m.lane_f + lane * LANE_F;
+        const float lon = frac * L[LF_LENGTH] / 2.0f;
+#pragma unroll
+        for (int k = 0; k < VEH_S; k++) St[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < VEH_C; k++) C[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < VEH_I; k++) I[k] = 0;
+#pragma unroll
+        for (int k = 0; k < NAVI_DIM; k++) navi[k] = 0.0f;
+        lane_position(L, lon, 0.0f, St[VS_POS], St[VS_POS + 1]);
+        St[VS_POS + 2] = 0.5f * P[VP_HEIGHT];
+        yaw_quat_for_lane(L, lon, St[VS_QUAT], St[VS_QUAT + 3]);
+        const int* rt = A.ma_route + ((size_t)env * cfg.ma_places + p) * ROUTE_MAX;
+        const int* rr = A.ma_rroad + ((size_t)env * cfg.ma_places + p) * ROUTE_MAX;
+        int* vr = A.veh_route + g * ROUTE_MAX;
+        int* vrr = A.veh_rroad + g * ROUTE_MAX;
+        int n_ck = 0;
+        for (int k = 0; k < ROUTE_MAX; k++) { const int c = rt[k]; vr[k] = c; vrr[k] = rr[k]; if (c >= 0) n_ck++; }
+        I[VI_KIND] = 2; I[VI_ALIVE] = 1; I[VI_ACTIVE] = 1; I[VI_TRIGGER] = -1;
+        I[VI_LANE] = lane; I[VI_SPAWN_LANE] = lane;
+        I[VI_CKPT0] = 0; I[VI_CKPT1] = n_ck > 2 ? 1 : 0; I[VI_ROUTE_LEN] = n_ck;
+        I[VI_ROUTING_LANE] = -1;
+        float4* d4 = reinterpret_cast<float4*>(A.veh_idm + g * VEH_IDM);
+        const float rng_ctr = A.veh_idm[g * VEH_IDM + VD_RNG];
+        d4[0] = make_float4((float)timer, 30.0f, 0.0f, 0.0f);  // fresh IDMPolicy (policy/idm_policy.py:224-233)
+        d4[1] = make_float4(0.0f, 0.0f, rng_ctr, 0.0f);
+        latch_before_step(St, C, I);
+        const Rect r = vehicle_rect(P, St);
+        after_step_vehicle(m, St, C, I, vr, vrr, navi, fp, obj_all + (size_t)le * O * OBJ_F, S, O, slot, r);
+        I[VI_FLAGS] = FL_ON_LANE;  // BaseVehicle.reset ends with _init_step_info (base_vehicle.py:379)
+        store16(A.veh_s + g * VEH_S, St);
+        store16(A.veh_c + g * VEH_C, C);
+        store16i(A.veh_i + g * VEH_I, I);
+#pragma unroll
+        for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[g * NAVI_DIM + k] = navi[k];
+        write_body_row(body_tab + g * BODY_ROW, P, St, 1);
+        if (rank == total - 1) A.env_i[env * ENV_I + EI_RNG] = (int)(ctr - (uint32_t)rank + (uint32_t)total);
     }
 }
 
@@ -1139,7 +1195,7 @@ __global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t
     for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = snap.obj_f[(size_t)env * O * OBJ_F + k];
     if (slot == 0)
         for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = snap.env_i[env * ENV_I + k];
-    if (cfg.is_multi_agent && slot < cfg.agents_per_env) {  // respawns rewrite the seat's route
+    if ((cfg.is_multi_agent && slot < cfg.agents_per_env) || cfg.traffic_mode != 0) {  // respawns rewrite the slot's route
         const int4* r4 = reinterpret_cast<const int4*>(snap.veh_route + (size_t)g * ROUTE_MAX);
         const int4* q4 = reinterpret_cast<const int4*>(snap.veh_rroad + (size_t)g * ROUTE_MAX);
         int4* dr = reinterpret_cast<int4*>(A.veh_route + (size_t)g * ROUTE_MAX);
@@ -1384,7 +1440,7 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * RESPAWN_WARPS + warp;
     if (env >= cfg.n_envs) return;
-    Nb* nb = reinterpret_cast<Nb*>(smem_raw) + (size_t)warp * S;
+    Fp* nb = reinterpret_cast<Fp*>(smem_raw) + (size_t)warp * S;
     int n_alive = 0, seat = 0x7fffffff;
     for (int s0 = 0; s0 < S; s0 += 32) {
         const int s = s0 + lane;
@@ -1393,7 +1449,7 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
             const size_t g = (size_t)env * S + s;
             const int* I = A.veh_i + g * VEH_I;
             alive = I[VI_ALIVE];
-            nb[s].alive = alive; nb[s].kind = I[VI_KIND];
+            nb[s].alive = alive;
             if (alive) {
                 float P[VEH_P], St[VEH_S];
                 load16(P, A.veh_p + g * VEH_P);
@@ -1469,7 +1525,7 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
     latch_before_step(St, C, I);
     nb[seat].alive = 1; nb[seat].r = vehicle_rect(P, St);
     const MapView m = map_view(A, E[EI_MAP]);
-    after_step_vehicle(m, St, C, I, vr, vrr, navi, nb, A.obj_f + (size_t)env * O * OBJ_F, S, O, seat, nb[seat].r, nullptr);
+    after_step_vehicle(m, St, C, I, vr, vrr, navi, nb, A.obj_f + (size_t)env * O * OBJ_F, S, O, seat, nb[seat].r);
     const size_t a = (size_t)env * NA + seat;
     agent_outputs(cfg, m, E[EI_STEP], P, St, C, I, vrr, navi, a, out, false);
     // a newborn agent: reward 0, not done, first observation (multi_agent_metadrive.py:137-144)
@@ -1702,6 +1758,17 @@ static StepLaunch step_launch(const MdConfig& c, int epb_pref) {
 static int epb_pre() { static int v = env_int("MD_EPB_PRE", PRE_EPB); return v; }
 static int epb_post() { static int v = env_int("MD_EPB_POST", POST_EPB); return v; }
 static int epb_dyn() { static int v = env_int("MD_EPB_DYN", DYN_EPB); return v; }
+static StepLaunch post_launch(const MdConfig& c) {  // k_post: epb envs per CTA, a fixed number of worker threads
+    StepLaunch L;
+    L.epb = epb_post();
+    while (L.epb > 1 && post_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb) > 96 * 1024) L.epb >>= 1;
+    L.threads = env_int("MD_POST_WORKERS", POST_WORKERS);
+    if (L.threads > 1024 || L.threads < 32) L.threads = POST_WORKERS;
+    L.blocks = (c.n_envs + L.epb - 1) / L.epb;
+    L.smem = post_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb);
+    return L;
+}
+
 
 template <typename K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
@@ -1710,7 +1777,7 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
 // dynamic shared memory above the 48 KB default needs an opt-in per kernel
 static int opt_in_smem(md_sim* sim) {
     const size_t floor48 = 48 * 1024;
-    StepLaunch D = step_launch(sim->cfg, epb_dyn()), A = step_launch(sim->cfg, epb_pre()), B = step_launch(sim->cfg, epb_post());
+    StepLaunch D = step_launch(sim->cfg, epb_dyn()), A = step_launch(sim->cfg, epb_pre()), B = post_launch(sim->cfg);
     if (A.smem > 200 * 1024 || B.smem > 200 * 1024 || D.smem > 200 * 1024) {
         sim->err = "slots/objects per env need more than 200 KB of shared memory per CTA";
         return -4;
@@ -1738,7 +1805,7 @@ static int launch_dyn(md_sim* sim, int mode, const float* ext_act3, int n_sub, c
     return 0;
 }
 static int launch_post(md_sim* sim, int mode, StepOut out, const uint8_t* mask, cudaStream_t st) {
-    StepLaunch L = step_launch(sim->cfg, epb_post());
+    StepLaunch L = post_launch(sim->cfg);
     k_post<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, out, sim->body_tab, mask);
     sim->launches++;
     CK(cudaGetLastError());
@@ -1766,7 +1833,7 @@ static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* h
 static int launch_respawn(md_sim* sim, StepOut out, cudaStream_t st) {
     const MdConfig& c = sim->cfg;
     int blocks = (c.n_envs + RESPAWN_WARPS - 1) / RESPAWN_WARPS;
-    size_t smem = sizeof(Nb) * (size_t)c.slots_per_env * RESPAWN_WARPS;
+    size_t smem = sizeof(Fp) * (size_t)c.slots_per_env * RESPAWN_WARPS;
     k_respawn<<<blocks, RESPAWN_WARPS * 32, smem, st>>>(c, sim->dev, out, sim->body_tab);
     sim->launches++;
     CK(cudaGetLastError());
