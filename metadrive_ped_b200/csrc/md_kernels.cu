@@ -820,18 +820,39 @@ __global__ void __maxnreg__(DYN_REGS)
 k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ veh_act, const float* __restrict__ ext_act3,
       int n_sub) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const StepGeom G = step_geom(cfg, epb, smem_raw);
-    const int S = G.S, O = G.O, slot = G.slot, env = G.env, g = G.g;
+    // Two identities per thread.  H ("housekeeping", thread t <-> slot row t of the CTA's envs) sweeps the rows, stages and
+    // maintains the objects.  The vehicle identity comes from a compacted list of the alive vehicles, so that the warps
+    // that integrate are dense (a third to a half of the slot rows of a PG scene are empty or not alive).
+    const StepGeom H = step_geom(cfg, epb, smem_raw);
+    const int S = H.S, O = H.O;
+    int* list = reinterpret_cast<int*>(smem_raw + step_smem_bytes(S, O, epb));
+    int* n_list = list + epb * S;
+    if (threadIdx.x == 0) *n_list = 0;
+    __syncthreads();
+    if (H.work) {
+        const int alive0 = A.veh_i[(size_t)H.g * VEH_I + VI_ALIVE];
+        H.nb[H.slot].alive = alive0;
+        if (alive0) list[atomicAdd(n_list, 1)] = H.le * S + H.slot;
+    }
+    __syncthreads();
+    StepGeom G = H;
+    G.work = (int)threadIdx.x < *n_list;
+    if (G.work) {
+        const int v = list[threadIdx.x];
+        G.le = v / S; G.slot = v - G.le * S;
+        G.env = blockIdx.x * epb + G.le; G.g = G.env * S + G.slot;
+        G.nb = H.nb + ((ptrdiff_t)G.le - H.le) * S;
+        G.sobj = H.sobj + ((ptrdiff_t)G.le - H.le) * O * OBJ_F;
+        G.obj_first = H.obj_first + ((ptrdiff_t)G.le - H.le) * ((O + 3) & ~3);
+    }
+    const int slot = G.slot, g = G.g;
     float P[VEH_P], St[VEH_S];
     int alive = 0, is_static = 1, flags = 0;
     Actuation act;
     act.steer_rad = 0.0f; act.engine = 0.0f; act.brake = 2.0f;
     if (G.work) {
         const int* I = A.veh_i + (size_t)g * VEH_I;
-        alive = I[VI_ALIVE]; is_static = I[VI_STATIC]; flags = I[VI_FLAGS];
-        G.nb[slot].alive = alive;
-    }
-    if (G.work && alive) {
+        alive = 1; is_static = I[VI_STATIC]; flags = I[VI_FLAGS];
         load16(P, A.veh_p + (size_t)g * VEH_P);
         load16(St, A.veh_s + (size_t)g * VEH_S);
         if (mode & MODE_EXT_ACT) {
@@ -842,7 +863,7 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
         }
     }
     const bool contacts = (mode & MODE_CONTACTS) != 0;
-    if (contacts) stage_objects(G, A.obj_f);
+    if (contacts) stage_objects(H, A.obj_f);
     Body B;
     B.pos = f3(St[VS_POS], St[VS_POS + 1], St[VS_POS + 2]);
     B.q[0] = St[VS_QUAT]; B.q[1] = St[VS_QUAT + 1]; B.q[2] = St[VS_QUAT + 2]; B.q[3] = St[VS_QUAT + 3];
@@ -901,27 +922,26 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
         }
         if (contacts && block_any) {  // a CTA without candidate pairs has no contact this step: no exchange, no barriers
             __syncthreads();  // everyone finished reading the previous footprints
-            if (G.work) {
-                if (alive) G.nb[slot].r = vehicle_rect(P, St);
-                for (int k = slot; k < O; k += S) {  // kinematic movers (traffic_participants/pedestrian.py:67-95)
-                    G.obj_first[k] = 0x7fffffff;
-                    float* Ob = G.sobj + k * OBJ_F;
+            if (G.work) G.nb[slot].r = vehicle_rect(P, St);
+            if (H.work)
+                for (int k = H.slot; k < O; k += S) {  // kinematic movers (traffic_participants/pedestrian.py:67-95)
+                    H.obj_first[k] = 0x7fffffff;
+                    float* Ob = H.sobj + k * OBJ_F;
                     if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
                 }
-            }
             __syncthreads();
             if (cand_lo | cand_hi) flags |= contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, true, false);
             if (block_obj) {  // COST_ONCE needs the claims of every vehicle before anyone reads them
                 __syncthreads();
                 if (cand_lo | cand_hi) flags |= contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, false, true);
                 __syncthreads();
-                if (G.work)
-                    for (int k = slot; k < O; k += S)
-                        if (G.obj_first[k] != 0x7fffffff) G.sobj[k * OBJ_F + OB_CRASHED] = 1.0f;
+                if (H.work)
+                    for (int k = H.slot; k < O; k += S)
+                        if (H.obj_first[k] != 0x7fffffff) H.sobj[k * OBJ_F + OB_CRASHED] = 1.0f;
             }
-        } else if (contacts && G.work) {
-            for (int k = slot; k < O; k += S) {  // nobody looks: the pedestrians still walk, in the same increments
-                float* Ob = G.sobj + k * OBJ_F;
+        } else if (contacts && H.work) {
+            for (int k = H.slot; k < O; k += S) {  // nobody looks: the pedestrians still walk, in the same increments
+                float* Ob = H.sobj + k * OBJ_F;
                 if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
             }
         }
@@ -936,17 +956,17 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     }
     if (contacts && O > 0) {
         __syncthreads();
-        if (G.work)
-            for (int k = slot; k < O; k += S) {  // pedestrians turn around at the ends of their crossing (peds.py)
-                float* Ob = G.sobj + k * OBJ_F;
+        if (H.work)
+            for (int k = H.slot; k < O; k += S) {  // pedestrians turn around at the ends of their crossing (peds.py)
+                float* Ob = H.sobj + k * OBJ_F;
                 if (Ob[OB_KIND] != 3.0f || Ob[OB_B] <= 0.0f) continue;
                 const float speed = sqrtf(Ob[OB_VX] * Ob[OB_VX] + Ob[OB_VY] * Ob[OB_VY]);
                 Ob[OB_HEADING] -= speed * (cfg.dt * (float)n_sub);
                 if (Ob[OB_HEADING] <= 0.0f) { Ob[OB_VX] = -Ob[OB_VX]; Ob[OB_VY] = -Ob[OB_VY]; Ob[OB_HEADING] += Ob[OB_B]; }
             }
         __syncthreads();
-        if (G.work)
-            for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = G.sobj[k];
+        if (H.work)
+            for (int k = H.slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)H.env * O * OBJ_F + k] = H.sobj[k];
     }
 }
 
@@ -1758,6 +1778,11 @@ static StepLaunch step_launch(const MdConfig& c, int epb_pref) {
 static int epb_pre() { static int v = env_int("MD_EPB_PRE", PRE_EPB); return v; }
 static int epb_post() { static int v = env_int("MD_EPB_POST", POST_EPB); return v; }
 static int epb_dyn() { static int v = env_int("MD_EPB_DYN", DYN_EPB); return v; }
+static StepLaunch dyn_launch(const MdConfig& c) {  // k_dyn appends the compacted list of alive vehicles to the shared tables
+    StepLaunch L = step_launch(c, epb_dyn());
+    L.smem += sizeof(int) * ((size_t)L.epb * c.slots_per_env + 4);
+    return L;
+}
 static StepLaunch post_launch(const MdConfig& c) {  // k_post: epb envs per CTA, a fixed number of worker threads
     StepLaunch L;
     L.epb = epb_post();
@@ -1777,7 +1802,7 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
 // dynamic shared memory above the 48 KB default needs an opt-in per kernel
 static int opt_in_smem(md_sim* sim) {
     const size_t floor48 = 48 * 1024;
-    StepLaunch D = step_launch(sim->cfg, epb_dyn()), A = step_launch(sim->cfg, epb_pre()), B = post_launch(sim->cfg);
+    StepLaunch D = dyn_launch(sim->cfg), A = step_launch(sim->cfg, epb_pre()), B = post_launch(sim->cfg);
     if (A.smem > 200 * 1024 || B.smem > 200 * 1024 || D.smem > 200 * 1024) {
         sim->err = "slots/objects per env need more than 200 KB of shared memory per CTA";
         return -4;
@@ -1798,7 +1823,7 @@ static int launch_pre(md_sim* sim, int mode, const float* actions, float* idm_ou
     return 0;
 }
 static int launch_dyn(md_sim* sim, int mode, const float* ext_act3, int n_sub, cudaStream_t st) {
-    StepLaunch L = step_launch(sim->cfg, epb_dyn());
+    StepLaunch L = dyn_launch(sim->cfg);
     k_dyn<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, sim->veh_act, ext_act3, n_sub);
     sim->launches++;
     CK(cudaGetLastError());
