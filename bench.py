@@ -199,7 +199,7 @@ def main():
             done_count += (sim.terminated | sim.truncated).sum()
         barrier()
     step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(K)])
-    kms = sim.profile_end()  # [K, 4]: k_pre, k_dyn, k_post, k_lidar
+    kms = sim.profile_end()  # [K, 5]: k_pre, k_dyn, k_post, fused reset (k_post in reset mode), k_lidar
     launches = sim.launch_count - launches0
     total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
     if world > 1:
@@ -231,7 +231,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        names = ["k_pre", "k_dyn", "k_post", "k_lidar"]
+        names = ["k_pre", "k_dyn", "k_post", "k_reset", "k_lidar"]
         mean_ms = kms.mean(0)
         dom_i = int(np.argmax(mean_ms))
         dom = names[dom_i]
@@ -242,6 +242,7 @@ def main():
             "k_pre": (8 + 64) + T * (64 + 256),             # action + latches r/w ; traffic: PID/timer/route r/w + neighbours
             "k_dyn": (192 + 48) * (1 + T),                  # state r/w + params, every vehicle
             "k_post": 64 + 76 + 16,                         # episode/nav state r/w + 19 state floats + scalars (ego)
+            "k_reset": 0.0,                                 # auto-reset of finished envs: not part of the per-step figure
             "k_lidar": B_LIDAR_SHARE,                       # neighbour footprints + 240 lidar floats
         }
         assert abs(sum(per_env.values()) - (B_EGO + B_TRAFFIC * T)) < 1.0, per_env

@@ -59,6 +59,11 @@ int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward
  * and its agents' observation rows are overwritten with the reset observation (the user-side loop
  * `if done: env.reset()` of examples/profile_metadrive.py:26-29, without a host round trip). */
 int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, void* stream);
+/* md_step + md_autoreset in one call.  Single-agent worlds take a fused path: k_post marks the finished envs, one more
+ * launch restores and re-localises them, and the lidar observes the post-reset world once (the reward / cost / done /
+ * info outputs keep the finished step's values, the observation rows of finished envs hold the reset observation). */
+int md_step_autoreset(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
+                      uint8_t* terminated_dev, uint8_t* truncated_dev, int32_t* info_flags_dev, float* info_f_dev, void* stream);
 
 /* the same step through HOST buffers: pinned staging, H2D of actions and D2H of all outputs on the sim's own stream,
  * synchronous.  This is the call the Gymnasium-surface classes make. */
@@ -88,9 +93,10 @@ int md_get_state(md_sim* sim, const char* name, void* host_dst, size_t bytes);
 int md_set_state(md_sim* sim, const char* name, const void* host_src, size_t bytes);
 /* make the current device state the snapshot md_reset restores */
 int md_snapshot(md_sim* sim);
-/* per-kernel device timing of the next max_steps md_step calls: five cudaEvents per call recorded on the launch
- * stream (no synchronisation added).  md_profile_end (after the caller synchronised) fills ms[4*i + k] with the
- * milliseconds of kernel k (0 k_pre, 1 k_dyn, 2 k_post, 3 k_lidar) of recorded step i and returns how many steps. */
+/* per-stage device timing of the next max_steps md_step / md_step_autoreset calls: six cudaEvents per call recorded on
+ * the launch stream (no synchronisation added).  md_profile_end (after the caller synchronised) fills ms[5*i + k] with
+ * the milliseconds of stage k (0 k_pre, 1 k_dyn, 2 k_post, 3 fused reset, 4 k_lidar) of recorded step i and returns
+ * how many steps. */
 int md_profile_begin(md_sim* sim, int max_steps);
 int md_profile_end(md_sim* sim, float* ms, int cap);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */

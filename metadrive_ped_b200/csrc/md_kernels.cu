@@ -52,6 +52,8 @@ __constant__ float c_ray_cs[2 * MAX_LASERS];
 enum {
     MODE_AGENT_PRE = 1, MODE_TRIGGER = 2, MODE_IDM = 4, MODE_DYN = 8, MODE_CONTACTS = 16, MODE_POST = 32,
     MODE_OUT = 64, MODE_EXT_ACT = 128, MODE_IDM_OUT = 256, MODE_RESET = 512, MODE_REMOVE = 1024, MODE_CLEAR_FLAGS = 2048,
+    MODE_MARK_DONE = 4096,  // k_post writes done_mask[env] (single agent: the agent terminated or truncated)
+    MODE_RESTORE = 8192,    // k_post(MODE_RESET) first restores the masked envs from the reset snapshot
     MODE_FULL = MODE_AGENT_PRE | MODE_TRIGGER | MODE_IDM | MODE_DYN | MODE_CONTACTS | MODE_POST | MODE_OUT | MODE_REMOVE
 };
 
@@ -970,6 +972,61 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     }
 }
 
+// ---- env.reset state restore of one slot row (snapshot -> live arrays) -----------------------------------------
+__device__ __forceinline__ void restore_row(const MdConfig& cfg, const MdArrays& A, const Snapshot& snap, long long g) {
+    const int S = cfg.slots_per_env, O = cfg.objs_per_env;
+    const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
+    const float4* s4 = reinterpret_cast<const float4*>(snap.veh_s + (size_t)g * VEH_S);
+    const float4* c4 = reinterpret_cast<const float4*>(snap.veh_c + (size_t)g * VEH_C);
+    const int4* i4 = reinterpret_cast<const int4*>(snap.veh_i + (size_t)g * VEH_I);
+    float4* ds = reinterpret_cast<float4*>(A.veh_s + (size_t)g * VEH_S);
+    float4* dc = reinterpret_cast<float4*>(A.veh_c + (size_t)g * VEH_C);
+    int4* di = reinterpret_cast<int4*>(A.veh_i + (size_t)g * VEH_I);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { ds[k] = s4[k]; dc[k] = c4[k]; di[k] = i4[k]; }
+    const float4* d4 = reinterpret_cast<const float4*>(snap.veh_idm + (size_t)g * VEH_IDM);
+    float4* dd = reinterpret_cast<float4*>(A.veh_idm + (size_t)g * VEH_IDM);
+    dd[0] = d4[0]; dd[1] = d4[1];
+    for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = snap.veh_navi[(size_t)g * NAVI_DIM + k];
+    for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = snap.obj_f[(size_t)env * O * OBJ_F + k];
+    if (slot == 0)
+        for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = snap.env_i[env * ENV_I + k];
+    if ((cfg.is_multi_agent && slot < cfg.agents_per_env) || cfg.traffic_mode != 0) {  // respawns rewrite the slot's route
+        const int4* r4 = reinterpret_cast<const int4*>(snap.veh_route + (size_t)g * ROUTE_MAX);
+        const int4* q4 = reinterpret_cast<const int4*>(snap.veh_rroad + (size_t)g * ROUTE_MAX);
+        int4* dr = reinterpret_cast<int4*>(A.veh_route + (size_t)g * ROUTE_MAX);
+        int4* dq = reinterpret_cast<int4*>(A.veh_rroad + (size_t)g * ROUTE_MAX);
+#pragma unroll
+        for (int k = 0; k < ROUTE_MAX / 4; k++) { dr[k] = r4[k]; dq[k] = q4[k]; }
+    }
+}
+// auto-reset as a row copy: the post-reset snapshot already holds the localised state, the body rows and the state part
+// of the reset observation (md_reset records them after a full reset)
+__global__ void k_restore_post(MdConfig cfg, MdArrays A, Snapshot post, const float* __restrict__ post_body,
+                               const float* __restrict__ post_obs, float* __restrict__ body_tab, float* __restrict__ obs,
+                               const uint8_t* __restrict__ env_mask) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int S = cfg.slots_per_env;
+    if (g >= (long long)cfg.n_envs * S) return;
+    const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
+    if (env_mask[env] == 0) return;
+    restore_row(cfg, A, post, g);
+    const float4* b4 = reinterpret_cast<const float4*>(post_body + (size_t)g * BODY_ROW);
+    float4* d4 = reinterpret_cast<float4*>(body_tab + (size_t)g * BODY_ROW);
+#pragma unroll
+    for (int k = 0; k < BODY_ROW / 4; k++) d4[k] = b4[k];
+    if (slot < cfg.agents_per_env) {
+        const size_t a = (size_t)env * cfg.agents_per_env + slot;
+        for (int k = 0; k < OBS_STATE; k++) obs[a * (size_t)OBS_DIM(cfg) + k] = post_obs[a * OBS_STATE + k];
+    }
+}
+__global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t* __restrict__ env_mask) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)cfg.n_envs * cfg.slots_per_env) return;
+    if (env_mask != nullptr && env_mask[g / cfg.slots_per_env] == 0) return;
+    restore_row(cfg, A, snap, g);
+}
+
 // ---- k_post: engine.after_step + _get_step_return (base_vehicle.py:234-271; envs/base_env.py:586-623) -----------
 // MODE_RESET: the reset-time variant (envs/base_env.py:560-584) for the envs selected by env_mask.
 // A CTA owns `epb` envs and runs POST_WORKERS threads.  Phase 1: the threads sweep the epb x S slot rows (coalesced),
@@ -1029,10 +1086,23 @@ __device__ __forceinline__ void after_step_vehicle(const MapView& m, const float
 
 __global__ void __maxnreg__(POST_REGS)
 k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restrict__ body_tab,
-       const uint8_t* __restrict__ env_mask) {
+       const uint8_t* __restrict__ env_mask, uint8_t* __restrict__ done_mask, Snapshot snap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     const int n_rows = epb * S, env0 = blockIdx.x * epb;
+    if (mode & MODE_RESTORE) {
+        // env.reset of the masked envs, part 1: snapshot -> live arrays (what k_restore does, fused in so that an
+        // auto-reset costs one launch).  CTAs without a finished env leave at once.
+        int any = 0;
+        for (int le = 0; le < epb; le++) any |= (env0 + le < cfg.n_envs) && env_mask[env0 + le];
+        if (!any) return;
+        for (int v = threadIdx.x; v < n_rows; v += blockDim.x) {
+            const int le = v / S, env = env0 + le;
+            if (env >= cfg.n_envs || !env_mask[env]) continue;
+            restore_row(cfg, A, snap, (long long)env * S + (v - le * S));
+        }
+        __syncthreads();
+    }
     Fp* fp_all = reinterpret_cast<Fp*>(smem_raw);
     float* obj_all = reinterpret_cast<float*>(smem_raw + sizeof(Fp) * (size_t)n_rows);
     int* list = reinterpret_cast<int*>(smem_raw + sizeof(Fp) * (size_t)n_rows + sizeof(float) * OBJ_F * (size_t)O * epb);
@@ -1120,6 +1190,10 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
                 }
             }
         }
+        if ((mode & MODE_MARK_DONE) && is_agent && slot == 0) {
+            const size_t a = (size_t)env * NA;
+            done_mask[env] = (out.term[a] || out.trunc[a]) ? 1 : 0;
+        }
         store16(A.veh_c + g * VEH_C, C);
         store16i(A.veh_i + g * VEH_I, I);
 #pragma unroll
@@ -1190,38 +1264,6 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[g * NAVI_DIM + k] = navi[k];
         write_body_row(body_tab + g * BODY_ROW, P, St, 1);
         if (rank == total - 1) A.env_i[env * ENV_I + EI_RNG] = (int)(ctr - (uint32_t)rank + (uint32_t)total);
-    }
-}
-
-// ---- k_restore: env.reset state restore for the masked envs (snapshot -> live arrays), thread per slot row ------
-__global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t* __restrict__ env_mask) {
-    const int S = cfg.slots_per_env, O = cfg.objs_per_env;
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)cfg.n_envs * S) return;
-    const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
-    if (env_mask != nullptr && env_mask[env] == 0) return;
-    const float4* s4 = reinterpret_cast<const float4*>(snap.veh_s + (size_t)g * VEH_S);
-    const float4* c4 = reinterpret_cast<const float4*>(snap.veh_c + (size_t)g * VEH_C);
-    const int4* i4 = reinterpret_cast<const int4*>(snap.veh_i + (size_t)g * VEH_I);
-    float4* ds = reinterpret_cast<float4*>(A.veh_s + (size_t)g * VEH_S);
-    float4* dc = reinterpret_cast<float4*>(A.veh_c + (size_t)g * VEH_C);
-    int4* di = reinterpret_cast<int4*>(A.veh_i + (size_t)g * VEH_I);
-#pragma unroll
-    for (int k = 0; k < 4; k++) { ds[k] = s4[k]; dc[k] = c4[k]; di[k] = i4[k]; }
-    const float4* d4 = reinterpret_cast<const float4*>(snap.veh_idm + (size_t)g * VEH_IDM);
-    float4* dd = reinterpret_cast<float4*>(A.veh_idm + (size_t)g * VEH_IDM);
-    dd[0] = d4[0]; dd[1] = d4[1];
-    for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = snap.veh_navi[(size_t)g * NAVI_DIM + k];
-    for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = snap.obj_f[(size_t)env * O * OBJ_F + k];
-    if (slot == 0)
-        for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = snap.env_i[env * ENV_I + k];
-    if ((cfg.is_multi_agent && slot < cfg.agents_per_env) || cfg.traffic_mode != 0) {  // respawns rewrite the slot's route
-        const int4* r4 = reinterpret_cast<const int4*>(snap.veh_route + (size_t)g * ROUTE_MAX);
-        const int4* q4 = reinterpret_cast<const int4*>(snap.veh_rroad + (size_t)g * ROUTE_MAX);
-        int4* dr = reinterpret_cast<int4*>(A.veh_route + (size_t)g * ROUTE_MAX);
-        int4* dq = reinterpret_cast<int4*>(A.veh_rroad + (size_t)g * ROUTE_MAX);
-#pragma unroll
-        for (int k = 0; k < ROUTE_MAX / 4; k++) { dr[k] = r4[k]; dq[k] = q4[k]; }
     }
 }
 
@@ -1572,6 +1614,12 @@ struct md_sim {
     size_t bytes[28];
     Snapshot snap;
     void* snap_bufs[9];
+    // the state right after a full reset (restore + reset-time after_step), so that an auto-reset is a row copy
+    Snapshot post;
+    void* post_bufs[9];
+    float* post_body;       // [NV, BODY_ROW]
+    float* post_obs;        // [A, OBS_STATE]: the state part of the reset observation
+    bool post_valid;
     float* body_tab;
     float4* veh_act;        // [NV] steering rad, engine force, brake: k_pre -> k_dyn
     uint8_t* mask;
@@ -1626,6 +1674,7 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     sim->cfg = *cfg;
     sim->device = device;
     sim->loaded = false;
+    sim->post_valid = false;
     sim->launches = 0;
     sim->prof_cap = 0;
     sim->prof_n = 0;
@@ -1656,7 +1705,8 @@ extern "C" void md_destroy(md_sim* sim) {
     cudaSetDevice(sim->device);
     if (sim->loaded) {
         for (int i = 0; i < N_ARR; i++) cudaFree(*arr_slot(&sim->dev, i));
-        for (int i = 0; i < N_SNAP; i++) cudaFree(sim->snap_bufs[i]);
+        for (int i = 0; i < N_SNAP; i++) { cudaFree(sim->snap_bufs[i]); cudaFree(sim->post_bufs[i]); }
+        cudaFree(sim->post_body); cudaFree(sim->post_obs);
         cudaFree(sim->body_tab); cudaFree(sim->veh_act); cudaFree(sim->mask);
         cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_reward); cudaFreeHost(sim->h_cost);
         cudaFreeHost(sim->h_info_f); cudaFreeHost(sim->h_term); cudaFreeHost(sim->h_trunc); cudaFreeHost(sim->h_mask);
@@ -1668,22 +1718,22 @@ extern "C" void md_destroy(md_sim* sim) {
     delete sim;
 }
 
-static int set_snapshot_ptrs(md_sim* sim) {
-    sim->snap.env_i = (const int*)sim->snap_bufs[0];
-    sim->snap.veh_s = (const float*)sim->snap_bufs[1];
-    sim->snap.veh_c = (const float*)sim->snap_bufs[2];
-    sim->snap.veh_i = (const int*)sim->snap_bufs[3];
-    sim->snap.veh_idm = (const float*)sim->snap_bufs[4];
-    sim->snap.veh_navi = (const float*)sim->snap_bufs[5];
-    sim->snap.obj_f = (const float*)sim->snap_bufs[6];
-    sim->snap.veh_route = (const int*)sim->snap_bufs[7];
-    sim->snap.veh_rroad = (const int*)sim->snap_bufs[8];
-    return 0;
+static void set_snapshot_ptrs(Snapshot& sn, void* const* bufs) {
+    sn.env_i = (const int*)bufs[0];
+    sn.veh_s = (const float*)bufs[1];
+    sn.veh_c = (const float*)bufs[2];
+    sn.veh_i = (const int*)bufs[3];
+    sn.veh_idm = (const float*)bufs[4];
+    sn.veh_navi = (const float*)bufs[5];
+    sn.obj_f = (const float*)bufs[6];
+    sn.veh_route = (const int*)bufs[7];
+    sn.veh_rroad = (const int*)bufs[8];
 }
 
 extern "C" int md_snapshot(md_sim* sim) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
+    sim->post_valid = false;
     for (int k = 0; k < N_SNAP; k++)
         CK(cudaMemcpy(sim->snap_bufs[k], *arr_slot(&sim->dev, kSnapIdx[k]), sim->bytes[kSnapIdx[k]], cudaMemcpyDeviceToDevice));
     return 0;
@@ -1709,12 +1759,17 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
         *arr_slot(&sim->dev, i) = d;
     }
     for (int k = 0; k < N_SNAP; k++) CK(cudaMalloc(&sim->snap_bufs[k], sim->bytes[kSnapIdx[k]] ? sim->bytes[kSnapIdx[k]] : 16));
-    set_snapshot_ptrs(sim);
+    set_snapshot_ptrs(sim->snap, sim->snap_bufs);
+    for (int k = 0; k < N_SNAP; k++) CK(cudaMalloc(&sim->post_bufs[k], sim->bytes[kSnapIdx[k]] ? sim->bytes[kSnapIdx[k]] : 16));
+    set_snapshot_ptrs(sim->post, sim->post_bufs);
+    CK(cudaMalloc(&sim->post_body, (size_t)NV * BODY_ROW * 4));
+    CK(cudaMalloc(&sim->post_obs, (size_t)c.n_envs * c.agents_per_env * OBS_STATE * 4));
     CK(cudaMalloc(&sim->body_tab, (size_t)NV * BODY_ROW * 4));
     CK(cudaMemset(sim->body_tab, 0, (size_t)NV * BODY_ROW * 4));
     CK(cudaMalloc(&sim->veh_act, (size_t)NV * sizeof(float4)));
     CK(cudaMemset(sim->veh_act, 0, (size_t)NV * sizeof(float4)));
     CK(cudaMalloc(&sim->mask, (size_t)c.n_envs));
+    CK(cudaMemset(sim->mask, 0, (size_t)c.n_envs));
     const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_DIM(c);
     CK(cudaMallocHost(&sim->h_actions, NA * 2 * 4)); CK(cudaMallocHost(&sim->h_obs, NA * od * 4));
     CK(cudaMallocHost(&sim->h_reward, NA * 4)); CK(cudaMallocHost(&sim->h_cost, NA * 4));
@@ -1753,6 +1808,7 @@ extern "C" int md_set_state(md_sim* sim, const char* name, const void* host_src,
     CK(cudaSetDevice(sim->device));
     int i = find_name(name);
     if (i < 0 || bytes != sim->bytes[i]) { sim->err = std::string("md_set_state: bad name or size for ") + name; return -7; }
+    sim->post_valid = false;
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(*arr_slot(&sim->dev, i), host_src, bytes, cudaMemcpyHostToDevice));
     return 0;
@@ -1831,7 +1887,7 @@ static int launch_dyn(md_sim* sim, int mode, const float* ext_act3, int n_sub, c
 }
 static int launch_post(md_sim* sim, int mode, StepOut out, const uint8_t* mask, cudaStream_t st) {
     StepLaunch L = post_launch(sim->cfg);
-    k_post<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, out, sim->body_tab, mask);
+    k_post<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, out, sim->body_tab, mask, sim->mask, sim->snap);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1872,45 +1928,85 @@ extern "C" int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev
     StepOut out = {obs_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (launch_restore(sim, env_mask_dev, st)) return -1;
     if (launch_post(sim, MODE_RESET, out, env_mask_dev, st)) return -1;
+    if (env_mask_dev == nullptr && obs_dev != nullptr) {
+        // a full reset: keep the resulting state so that later auto-resets are plain row copies (k_restore_post)
+        const MdConfig& c = sim->cfg;
+        for (int k = 0; k < N_SNAP; k++)
+            CK(cudaMemcpyAsync(sim->post_bufs[k], *arr_slot(&sim->dev, kSnapIdx[k]), sim->bytes[kSnapIdx[k]], cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(sim->post_body, sim->body_tab, (size_t)c.n_envs * c.slots_per_env * BODY_ROW * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpy2DAsync(sim->post_obs, OBS_STATE * 4, obs_dev, (size_t)OBS_DIM(c) * 4, OBS_STATE * 4,
+                             (size_t)c.n_envs * c.agents_per_env, cudaMemcpyDeviceToDevice, st));
+        sim->post_valid = true;
+    }
     return launch_lidar(sim, obs_dev, OBS_DIM(sim->cfg), OBS_STATE, nullptr, env_mask_dev, st);
+}
+
+// one env.step; `fused_reset` (single agent only): finished envs are reset in place before the observation is taken, so
+// that the auto-reset costs one extra launch (k_post in MODE_RESET | MODE_RESTORE over the envs k_post just marked)
+#define N_PROF_EV 6
+static int step_impl(md_sim* sim, const float* actions_dev, StepOut out, cudaStream_t st, bool fused_reset) {
+    const bool prof = sim->prof_n < sim->prof_cap;
+    cudaEvent_t* ev = prof ? &sim->prof_ev[N_PROF_EV * sim->prof_n] : nullptr;
+    if (prof) CK(cudaEventRecord(ev[0], st));
+    if (launch_pre(sim, MODE_AGENT_PRE | MODE_TRIGGER | MODE_IDM, actions_dev, nullptr, st)) return -1;
+    if (prof) CK(cudaEventRecord(ev[1], st));
+    if (launch_dyn(sim, MODE_DYN | MODE_CONTACTS, nullptr, sim->cfg.decision_repeat, st)) return -1;
+    if (prof) CK(cudaEventRecord(ev[2], st));
+    if (launch_post(sim, MODE_POST | MODE_OUT | MODE_REMOVE | (fused_reset ? MODE_MARK_DONE : 0), out, nullptr, st)) return -1;
+    if (prof) CK(cudaEventRecord(ev[3], st));
+    if (fused_reset && sim->post_valid) {
+        const long long nv = (long long)sim->cfg.n_envs * sim->cfg.slots_per_env;
+        k_restore_post<<<(int)((nv + 255) / 256), 256, 0, st>>>(sim->cfg, sim->dev, sim->post, sim->post_body, sim->post_obs,
+                                                               sim->body_tab, out.obs, sim->mask);
+        sim->launches++;
+        CK(cudaGetLastError());
+    } else if (fused_reset) {
+        StepOut ro = {out.obs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (launch_post(sim, MODE_RESET | MODE_RESTORE, ro, sim->mask, st)) return -1;
+    }
+    if (prof) CK(cudaEventRecord(ev[4], st));
+    const int od = OBS_DIM(sim->cfg);
+    if (!sim->cfg.is_multi_agent) {
+        if (launch_lidar(sim, out.obs, od, OBS_STATE, nullptr, nullptr, st)) return -1;
+    } else {
+        // multi-agent: everyone who produced a transition observes (incl. agents that just finished), then finished
+        // vehicles leave / freeze, at most one agent per env is respawned and observes the world after that
+        if (!out.info_flags) { sim->err = "multi-agent md_step needs info_flags"; return -2; }
+        if (launch_lidar(sim, out.obs, od, OBS_STATE, nullptr, nullptr, st, out.info_flags, FL_VALID)) return -1;
+        if (launch_respawn(sim, out, st)) return -1;
+        if (sim->cfg.allow_respawn && launch_lidar(sim, out.obs, od, OBS_STATE, nullptr, nullptr, st, out.info_flags, FL_NEWBORN))
+            return -1;
+    }
+    if (prof) { CK(cudaEventRecord(ev[5], st)); sim->prof_n++; }
+    return 0;
 }
 
 extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
                        uint8_t* terminated_dev, uint8_t* truncated_dev, int32_t* info_flags_dev, float* info_f_dev, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
-    cudaStream_t st = (cudaStream_t)stream;
     StepOut out = {obs_dev, reward_dev, cost_dev, terminated_dev, truncated_dev, info_flags_dev, info_f_dev};
-    const bool prof = sim->prof_n < sim->prof_cap;
-    cudaEvent_t* ev = prof ? &sim->prof_ev[5 * sim->prof_n] : nullptr;
-    if (prof) CK(cudaEventRecord(ev[0], st));
-    if (launch_pre(sim, MODE_AGENT_PRE | MODE_TRIGGER | MODE_IDM, actions_dev, nullptr, st)) return -1;
-    if (prof) CK(cudaEventRecord(ev[1], st));
-    if (launch_dyn(sim, MODE_DYN | MODE_CONTACTS, nullptr, sim->cfg.decision_repeat, st)) return -1;
-    if (prof) CK(cudaEventRecord(ev[2], st));
-    if (launch_post(sim, MODE_POST | MODE_OUT | MODE_REMOVE, out, nullptr, st)) return -1;
-    if (prof) CK(cudaEventRecord(ev[3], st));
-    const int od = OBS_DIM(sim->cfg);
-    if (!sim->cfg.is_multi_agent) {
-        if (launch_lidar(sim, obs_dev, od, OBS_STATE, nullptr, nullptr, st)) return -1;
-    } else {
-        // multi-agent: everyone who produced a transition observes (incl. agents that just finished), then finished
-        // vehicles leave / freeze, at most one agent per env is respawned and observes the world after that
-        if (!info_flags_dev) { sim->err = "multi-agent md_step needs info_flags"; return -2; }
-        if (launch_lidar(sim, obs_dev, od, OBS_STATE, nullptr, nullptr, st, info_flags_dev, FL_VALID)) return -1;
-        if (launch_respawn(sim, out, st)) return -1;
-        if (sim->cfg.allow_respawn && launch_lidar(sim, obs_dev, od, OBS_STATE, nullptr, nullptr, st, info_flags_dev, FL_NEWBORN))
-            return -1;
-    }
-    if (prof) { CK(cudaEventRecord(ev[4], st)); sim->prof_n++; }
-    return 0;
+    return step_impl(sim, actions_dev, out, (cudaStream_t)stream, false);
+}
+
+extern "C" int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, void* stream);
+extern "C" int md_step_autoreset(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
+                                 uint8_t* terminated_dev, uint8_t* truncated_dev, int32_t* info_flags_dev, float* info_f_dev,
+                                 void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    StepOut out = {obs_dev, reward_dev, cost_dev, terminated_dev, truncated_dev, info_flags_dev, info_f_dev};
+    if (!sim->cfg.is_multi_agent && terminated_dev && truncated_dev)
+        return step_impl(sim, actions_dev, out, (cudaStream_t)stream, true);
+    if (step_impl(sim, actions_dev, out, (cudaStream_t)stream, false)) return -1;
+    return md_autoreset(sim, terminated_dev, truncated_dev, obs_dev, stream);
 }
 
 // per-kernel device timing of the next `max_steps` md_step calls (events on the launch stream, no sync added)
 extern "C" int md_profile_begin(md_sim* sim, int max_steps) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
-    while ((int)sim->prof_ev.size() < 5 * max_steps) {
+    while ((int)sim->prof_ev.size() < N_PROF_EV * max_steps) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
         sim->prof_ev.push_back(e);
@@ -1919,14 +2015,15 @@ extern "C" int md_profile_begin(md_sim* sim, int max_steps) {
     sim->prof_n = 0;
     return 0;
 }
-// after the caller synchronised: ms[4*i + k] = duration of kernel k (k_pre, k_dyn, k_post, k_lidar) of recorded step i
+// after the caller synchronised: ms[5*i + k] = duration of stage k (k_pre, k_dyn, k_post, fused reset, k_lidar) of step i
 extern "C" int md_profile_end(md_sim* sim, float* ms, int cap) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     int n = sim->prof_n < cap ? sim->prof_n : cap;
     for (int i = 0; i < n; i++) {
-        CK(cudaEventSynchronize(sim->prof_ev[5 * i + 4]));
-        for (int k = 0; k < 4; k++) CK(cudaEventElapsedTime(&ms[4 * i + k], sim->prof_ev[5 * i + k], sim->prof_ev[5 * i + k + 1]));
+        CK(cudaEventSynchronize(sim->prof_ev[N_PROF_EV * i + 5]));
+        for (int k = 0; k < 5; k++)
+            CK(cudaEventElapsedTime(&ms[5 * i + k], sim->prof_ev[N_PROF_EV * i + k], sim->prof_ev[N_PROF_EV * i + k + 1]));
     }
     sim->prof_cap = 0;
     sim->prof_n = 0;
@@ -1998,17 +2095,18 @@ extern "C" int md_step_host(md_sim* sim, const float* actions, float* obs, float
     const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_DIM(c);
     if (actions && actions != sim->h_actions) memcpy(sim->h_actions, actions, NA * 2 * 4);
     CK(cudaMemcpyAsync(sim->d_actions, sim->h_actions, NA * 2 * 4, cudaMemcpyHostToDevice, sim->stream));
-    if (md_step(sim, sim->d_actions, sim->d_obs, sim->d_reward, sim->d_cost, sim->d_term, sim->d_trunc, sim->d_info_flags,
-                sim->d_info_f, sim->stream))
+    // auto-reset overwrites only the observation rows of finished envs; the scalars keep the finished step's values
+    if (autoreset ? md_step_autoreset(sim, sim->d_actions, sim->d_obs, sim->d_reward, sim->d_cost, sim->d_term, sim->d_trunc,
+                                      sim->d_info_flags, sim->d_info_f, sim->stream)
+                  : md_step(sim, sim->d_actions, sim->d_obs, sim->d_reward, sim->d_cost, sim->d_term, sim->d_trunc,
+                            sim->d_info_flags, sim->d_info_f, sim->stream))
         return -1;
-    // scalars are read before the optional auto-reset overwrites the observation rows of finished envs
     CK(cudaMemcpyAsync(sim->h_reward, sim->d_reward, NA * 4, cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaMemcpyAsync(sim->h_cost, sim->d_cost, NA * 4, cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaMemcpyAsync(sim->h_term, sim->d_term, NA, cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaMemcpyAsync(sim->h_trunc, sim->d_trunc, NA, cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaMemcpyAsync(sim->h_info_flags, sim->d_info_flags, NA * 4, cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaMemcpyAsync(sim->h_info_f, sim->d_info_f, NA * 8 * 4, cudaMemcpyDeviceToHost, sim->stream));
-    if (autoreset && md_autoreset(sim, sim->d_term, sim->d_trunc, sim->d_obs, sim->stream)) return -1;
     CK(cudaMemcpyAsync(sim->h_obs, sim->d_obs, NA * od * 4, cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaStreamSynchronize(sim->stream));
     // NULL outputs: the caller reads the pinned staging buffers in place (md_host_views)

@@ -67,12 +67,10 @@ class BatchedSim:
     def step(self, actions, autoreset=False):
         assert actions.is_cuda and actions.dtype == self.torch.float32 and actions.is_contiguous()
         assert actions.numel() == self.n_agents * 2
-        self._check(self.lib.md_step(self.h, self._ptr(actions), self._ptr(self.obs), self._ptr(self.reward),
-                                     self._ptr(self.cost), self._ptr(self.terminated), self._ptr(self.truncated),
-                                     self._ptr(self.info_flags), self._ptr(self.info_f), self._stream()))
-        if autoreset:
-            self._check(self.lib.md_autoreset(self.h, self._ptr(self.terminated), self._ptr(self.truncated),
-                                              self._ptr(self.obs), self._stream()))
+        fn = self.lib.md_step_autoreset if autoreset else self.lib.md_step
+        self._check(fn(self.h, self._ptr(actions), self._ptr(self.obs), self._ptr(self.reward), self._ptr(self.cost),
+                       self._ptr(self.terminated), self._ptr(self.truncated), self._ptr(self.info_flags),
+                       self._ptr(self.info_f), self._stream()))
         return self.obs, self.reward, self.cost, self.terminated, self.truncated
 
     # ------------------------------------------------------------------ host-buffer API (numpy in, numpy out)
@@ -151,12 +149,12 @@ class BatchedSim:
         self._check(self.lib.md_profile_begin(self.h, int(max_steps)))
         self._prof_cap = int(max_steps)
 
-    KERNELS = ["k_pre", "k_dyn", "k_post", "k_lidar"]
+    KERNELS = ["k_pre", "k_dyn", "k_post", "k_reset", "k_lidar"]
 
     def profile_end(self):
-        """[n, 4] ms of k_pre, k_dyn, k_post, k_lidar for the md_step calls since profile_begin (synchronises)."""
+        """[n, 5] ms of k_pre, k_dyn, k_post, fused reset, k_lidar for the step calls since profile_begin (synchronises)."""
         self.torch.cuda.synchronize(self.tdev)
-        a = np.zeros((self._prof_cap, 4), np.float32)
+        a = np.zeros((self._prof_cap, 5), np.float32)
         n = self.lib.md_profile_end(self.h, a.ctypes.data_as(C.c_void_p), self._prof_cap)
         if n < 0:
             self._check(n)
