@@ -27,7 +27,7 @@
 // register caps per kernel (__maxnreg__): the block size is a run-time choice (envs per CTA x slots per env), so the
 // occupancy is steered through the register budget instead of __launch_bounds__
 #ifndef PRE_REGS
-#define PRE_REGS 48
+#define PRE_REGS 64
 #endif
 #ifndef DYN_REGS
 #define DYN_REGS 96
@@ -36,7 +36,7 @@
 #define POST_REGS 128
 #endif
 #ifndef PRE_EPB
-#define PRE_EPB 32
+#define PRE_EPB 16
 #endif
 #ifndef POST_EPB
 #define POST_EPB 16
@@ -725,95 +725,140 @@ __device__ __forceinline__ void stage_objects(const StepGeom& G, const float* __
 }
 
 // ---- k_pre: engine.before_step (agent actuation, traffic trigger, IDM decisions) ------------------------------
+// Same shape as k_post: a CTA owns `epb` envs and runs PRE_WORKERS threads.  Phase 1 sweeps the slot rows: neighbour
+// records of the alive vehicles go to shared memory, agents are actuated on the spot, alive traffic is appended to a work
+// list.  Then one thread per env runs the trigger, and phase 2 runs the IDM with one thread per listed vehicle.
+#ifndef PRE_WORKERS
+#define PRE_WORKERS 256
+#endif
+__host__ __device__ inline size_t pre_smem_bytes(int S, int O, int epb) {
+    return (sizeof(Nb) + sizeof(int)) * (size_t)S * epb + sizeof(float) * OBJ_F * (size_t)O * epb + 16;
+}
 __global__ void __maxnreg__(PRE_REGS)
 k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ actions, float* __restrict__ idm_out,
       float4* __restrict__ veh_act) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const StepGeom G = step_geom(cfg, epb, smem_raw);
-    const int S = G.S, slot = G.slot, env = G.env, g = G.g;
-    float P[VEH_P], St[VEH_S], C[VEH_C], D[VEH_IDM];
-    int I[VEH_I];
-    bool occupied = false;  // empty slots (kind 0) cost one 16-byte read and publish a dead neighbour record
-    if (G.work) {
-        load16i(I, A.veh_i + (size_t)g * VEH_I);
-        occupied = I[VI_KIND] != 0;
-        if (occupied) {
-            load16(P, A.veh_p + (size_t)g * VEH_P);
-            load16(St, A.veh_s + (size_t)g * VEH_S);
-            load16(C, A.veh_c + (size_t)g * VEH_C);
-            const float4* d4 = reinterpret_cast<const float4*>(A.veh_idm + (size_t)g * VEH_IDM);
-            float4 d0 = d4[0], d1 = d4[1];
-            D[0] = d0.x; D[1] = d0.y; D[2] = d0.z; D[3] = d0.w; D[4] = d1.x; D[5] = d1.y; D[6] = d1.z; D[7] = d1.w;
-            fill_nb(G.nb[slot], P, St, I);
-        } else {
-            G.nb[slot].alive = 0; G.nb[slot].active = 0; G.nb[slot].kind = 0; G.nb[slot].lane = -1;
-        }
-    }
-    stage_objects(G, A.obj_f);
-    Actuation act;
-    act.steer_rad = 0.0f; act.engine = 0.0f; act.brake = 2.0f;  // what vehicle.reset() leaves (base_vehicle.py:376)
-    const bool is_agent = occupied && I[VI_KIND] == 1;
-    const bool is_traffic = occupied && I[VI_KIND] == 2;
-    bool dirty = false;  // only vehicles that acted have anything to write back
-    // agent_manager.before_step (manager/agent_manager.py:164-202)
-    if ((mode & MODE_AGENT_PRE) && is_agent && I[VI_ACTIVE]) {
-        latch_before_step(St, C, I);
-        const float* a = actions + ((size_t)env * G.NA + slot) * 2;
-        act = actuate(P, St, C, a[0], a[1]);
-        dirty = true;
-    }
-    // VehicleAgentManager.before_step, second half (manager/agent_manager.py:189-202): wrecks of finished agents stay
-    // in the world as static bodies for delay_done steps, then leave
-    if ((mode & MODE_AGENT_PRE) && cfg.is_multi_agent && is_agent) {
-        if (I[VI_NEW]) { I[VI_NEW] = 0; dirty = true; }
-        if (I[VI_ALIVE] && !I[VI_ACTIVE] && I[VI_DYING] > 0) {
-            I[VI_DYING] -= 1;
-            if (I[VI_DYING] <= 0) { I[VI_ALIVE] = 0; I[VI_STATIC] = 0; G.nb[slot].alive = 0; }
-            dirty = true;
-        }
-    }
+    const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
+    const int n_rows = epb * S, env0 = blockIdx.x * epb;
+    Nb* nb_all = reinterpret_cast<Nb*>(smem_raw);
+    float* obj_all = reinterpret_cast<float*>(smem_raw + sizeof(Nb) * (size_t)n_rows);
+    int* list = reinterpret_cast<int*>(smem_raw + sizeof(Nb) * (size_t)n_rows + sizeof(float) * OBJ_F * (size_t)O * epb);
+    int* n_list = list + n_rows;
+    if (threadIdx.x == 0) *n_list = 0;
     __syncthreads();
-    MapView m;
-    if (G.work) m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
-    // PGTrafficManager.before_step: trigger (manager/traffic_manager.py:74-88), one thread per env
-    if ((mode & MODE_TRIGGER) && G.work && slot == 0 && cfg.traffic_mode != 1) {
-        int nt = A.env_i[env * ENV_I + EI_NEXT_TRIGGER];
-        const int n_blocks = A.env_i[env * ENV_I + EI_N_BLOCKS];
-        for (int s = 0; s < G.NA && nt > 0; s++) {
-            if (!G.nb[s].active || G.nb[s].kind != 1) continue;
-            int road = m.lane_i[G.nb[s].lane * LANE_I + LI_ROAD];
-            if (road == A.env_trigger[env * TRIGGER_MAX + nt]) {
-                for (int k = 0; k < S; k++)
-                    if (G.nb[k].kind == 2 && G.nb[k].alive && A.veh_i[(size_t)(env * S + k) * VEH_I + VI_TRIGGER] == nt) G.nb[k].active = 1;
-                nt = nt + 1 < n_blocks ? nt + 1 : 0;
+    const float4 idle = make_float4(0.0f, 0.0f, 2.0f, 0.0f);  // what vehicle.reset() leaves (base_vehicle.py:376): brake 2
+    // ---- phase 1
+    for (int v = threadIdx.x; v < n_rows; v += blockDim.x) {
+        const int le = v / S, slot = v - le * S, env = env0 + le;
+        Nb& n = nb_all[v];
+        n.alive = 0; n.active = 0; n.kind = 0; n.lane = -1;
+        if (env >= cfg.n_envs) continue;
+        const size_t g = (size_t)env * S + slot;
+        int I[VEH_I];
+        load16i(I, A.veh_i + g * VEH_I);
+        if (I[VI_KIND] == 0) continue;
+        const bool is_agent = I[VI_KIND] == 1;
+        bool dirty_i = false;
+        // VehicleAgentManager.before_step, second half (manager/agent_manager.py:189-202): wrecks of finished agents
+        // stay in the world as static bodies for delay_done steps, then leave
+        if ((mode & MODE_AGENT_PRE) && cfg.is_multi_agent && is_agent) {
+            if (I[VI_NEW]) { I[VI_NEW] = 0; dirty_i = true; }
+            if (I[VI_ALIVE] && !I[VI_ACTIVE] && I[VI_DYING] > 0) {
+                I[VI_DYING] -= 1;
+                if (I[VI_DYING] <= 0) { I[VI_ALIVE] = 0; I[VI_STATIC] = 0; }
+                dirty_i = true;
             }
         }
-        A.env_i[env * ENV_I + EI_NEXT_TRIGGER] = nt;
+        n.kind = I[VI_KIND]; n.lane = I[VI_LANE]; n.active = I[VI_ACTIVE];
+        if (I[VI_ALIVE]) {
+            float P[VEH_P], St[VEH_S];
+            load16(P, A.veh_p + g * VEH_P);
+            load16(St, A.veh_s + g * VEH_S);
+            fill_nb(n, P, St, I);
+            // agent_manager.before_step (manager/agent_manager.py:164-202)
+            if ((mode & MODE_AGENT_PRE) && is_agent && I[VI_ACTIVE]) {
+                float C[VEH_C];
+                load16(C, A.veh_c + g * VEH_C);
+                latch_before_step(St, C, I);
+                const float* a = actions + ((size_t)env * NA + slot) * 2;
+                const Actuation act = actuate(P, St, C, a[0], a[1]);
+                veh_act[g] = make_float4(act.steer_rad, act.engine, act.brake, 0.0f);
+                store16(A.veh_s + g * VEH_S, St);
+                store16(A.veh_c + g * VEH_C, C);
+                dirty_i = true;
+            } else {
+                veh_act[g] = idle;
+                if (I[VI_KIND] == 2) list[atomicAdd(n_list, 1)] = v;
+            }
+        } else veh_act[g] = idle;
+        if (dirty_i) store16i(A.veh_i + g * VEH_I, I);
     }
-    if (G.work && slot == 0 && (mode & MODE_AGENT_PRE)) A.env_i[env * ENV_I + EI_STEP] += 1;
+    for (int k = threadIdx.x; k < epb * O * OBJ_F; k += blockDim.x) {
+        const int env = env0 + k / (O * OBJ_F);
+        if (env < cfg.n_envs) obj_all[k] = A.obj_f[(size_t)env0 * O * OBJ_F + k];
+    }
     __syncthreads();
-    if (occupied && I[VI_ACTIVE] != G.nb[slot].active) { I[VI_ACTIVE] = G.nb[slot].active; dirty = true; }
-    // IDM decisions against the pre-step world (policy/idm_policy.py:235-267)
-    if ((mode & (MODE_IDM | MODE_IDM_OUT)) && is_traffic && I[VI_ACTIVE] && I[VI_ALIVE]) {
-        dirty = true;
+    // ---- PGTrafficManager.before_step: trigger (manager/traffic_manager.py:74-88), one thread per env
+    for (int le = threadIdx.x; le < epb; le += blockDim.x) {
+        const int env = env0 + le;
+        if (env >= cfg.n_envs) continue;
+        Nb* nb = nb_all + (size_t)le * S;
+        if ((mode & MODE_TRIGGER) && cfg.traffic_mode != 1) {
+            int nt = A.env_i[env * ENV_I + EI_NEXT_TRIGGER];
+            if (nt > 0) {
+                const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+                const int n_blocks = A.env_i[env * ENV_I + EI_N_BLOCKS];
+                for (int s = 0; s < NA && nt > 0; s++) {
+                    if (!nb[s].active || nb[s].kind != 1) continue;
+                    const int road = m.lane_i[nb[s].lane * LANE_I + LI_ROAD];
+                    if (road == A.env_trigger[env * TRIGGER_MAX + nt]) {
+                        for (int k = 0; k < S; k++)
+                            if (nb[k].kind == 2 && nb[k].alive && A.veh_i[(size_t)(env * S + k) * VEH_I + VI_TRIGGER] == nt) nb[k].active = 1;
+                        nt = nt + 1 < n_blocks ? nt + 1 : 0;
+                    }
+                }
+                A.env_i[env * ENV_I + EI_NEXT_TRIGGER] = nt;
+            }
+        }
+        if (mode & MODE_AGENT_PRE) A.env_i[env * ENV_I + EI_STEP] += 1;
+    }
+    __syncthreads();
+    // ---- phase 2: IDM decisions against the pre-step world (policy/idm_policy.py:235-267), one thread per active vehicle
+    if (!(mode & (MODE_IDM | MODE_IDM_OUT))) return;
+    const int n_work = *n_list;
+    for (int j = threadIdx.x; j < n_work; j += blockDim.x) {
+        const int v = list[j];
+        if (!nb_all[v].active) continue;
+        const int le = v / S, slot = v - le * S, env = env0 + le;
+        const size_t g = (size_t)env * S + slot;
+        float P[VEH_P], St[VEH_S], C[VEH_C], D[VEH_IDM];
+        int I[VEH_I];
+        load16i(I, A.veh_i + g * VEH_I);
+        load16(P, A.veh_p + g * VEH_P);
+        load16(St, A.veh_s + g * VEH_S);
+        load16(C, A.veh_c + g * VEH_C);
+        const float4* d4 = reinterpret_cast<const float4*>(A.veh_idm + g * VEH_IDM);
+        const float4 d0 = d4[0], d1 = d4[1];
+        D[0] = d0.x; D[1] = d0.y; D[2] = d0.z; D[3] = d0.w; D[4] = d1.x; D[5] = d1.y; D[6] = d1.z; D[7] = d1.w;
+        I[VI_ACTIVE] = 1;  // possibly triggered just now
+        const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
         NbrView nv;
-        nv.nb = G.nb; nv.obj = G.sobj; nv.S = S; nv.O = G.O; nv.self = slot; nv.px = St[VS_POS]; nv.py = St[VS_POS + 1];
+        nv.nb = nb_all + (size_t)le * S; nv.obj = obj_all + (size_t)le * O * OBJ_F; nv.S = S; nv.O = O; nv.self = slot;
+        nv.px = St[VS_POS]; nv.py = St[VS_POS + 1];
         float a0, a1;
-        idm_act(cfg, m, nv, g, St, I, D, A.veh_rroad + (size_t)g * ROUTE_MAX, a0, a1);
-        if (mode & MODE_IDM_OUT) { idm_out[2 * (size_t)g] = a0; idm_out[2 * (size_t)g + 1] = a1; }
+        idm_act(cfg, m, nv, (int)g, St, I, D, A.veh_rroad + g * ROUTE_MAX, a0, a1);
+        if (mode & MODE_IDM_OUT) { idm_out[2 * g] = a0; idm_out[2 * g + 1] = a1; }
         if (mode & MODE_IDM) {
             latch_before_step(St, C, I);
-            act = actuate(P, St, C, a0, a1);
+            const Actuation act = actuate(P, St, C, a0, a1);
+            veh_act[g] = make_float4(act.steer_rad, act.engine, act.brake, 0.0f);
         }
-    }
-    if (occupied) veh_act[g] = make_float4(act.steer_rad, act.engine, act.brake, 0.0f);
-    if (dirty) {
-        store16(A.veh_s + (size_t)g * VEH_S, St);
-        store16(A.veh_c + (size_t)g * VEH_C, C);
-        store16i(A.veh_i + (size_t)g * VEH_I, I);
-        float4* d4 = reinterpret_cast<float4*>(A.veh_idm + (size_t)g * VEH_IDM);
-        d4[0] = make_float4(D[0], D[1], D[2], D[3]);
-        d4[1] = make_float4(D[4], D[5], D[6], D[7]);
+        store16(A.veh_s + g * VEH_S, St);
+        store16(A.veh_c + g * VEH_C, C);
+        store16i(A.veh_i + g * VEH_I, I);
+        float4* o4 = reinterpret_cast<float4*>(A.veh_idm + g * VEH_IDM);
+        o4[0] = make_float4(D[0], D[1], D[2], D[3]);
+        o4[1] = make_float4(D[4], D[5], D[6], D[7]);
     }
 }
 
@@ -1839,6 +1884,16 @@ static StepLaunch dyn_launch(const MdConfig& c) {  // k_dyn appends the compacte
     L.smem += sizeof(int) * ((size_t)L.epb * c.slots_per_env + 4);
     return L;
 }
+static StepLaunch pre_launch(const MdConfig& c) {  // k_pre: epb envs per CTA, a fixed number of worker threads
+    StepLaunch L;
+    L.epb = epb_pre();
+    while (L.epb > 1 && pre_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb) > 96 * 1024) L.epb >>= 1;
+    L.threads = env_int("MD_PRE_WORKERS", PRE_WORKERS);
+    if (L.threads > 1024 || L.threads < 32) L.threads = PRE_WORKERS;
+    L.blocks = (c.n_envs + L.epb - 1) / L.epb;
+    L.smem = pre_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb);
+    return L;
+}
 static StepLaunch post_launch(const MdConfig& c) {  // k_post: epb envs per CTA, a fixed number of worker threads
     StepLaunch L;
     L.epb = epb_post();
@@ -1858,7 +1913,7 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
 // dynamic shared memory above the 48 KB default needs an opt-in per kernel
 static int opt_in_smem(md_sim* sim) {
     const size_t floor48 = 48 * 1024;
-    StepLaunch D = dyn_launch(sim->cfg), A = step_launch(sim->cfg, epb_pre()), B = post_launch(sim->cfg);
+    StepLaunch D = dyn_launch(sim->cfg), A = pre_launch(sim->cfg), B = post_launch(sim->cfg);
     if (A.smem > 200 * 1024 || B.smem > 200 * 1024 || D.smem > 200 * 1024) {
         sim->err = "slots/objects per env need more than 200 KB of shared memory per CTA";
         return -4;
@@ -1872,7 +1927,7 @@ static int opt_in_smem(md_sim* sim) {
 }
 
 static int launch_pre(md_sim* sim, int mode, const float* actions, float* idm_out, cudaStream_t st) {
-    StepLaunch L = step_launch(sim->cfg, epb_pre());
+    StepLaunch L = pre_launch(sim->cfg);
     k_pre<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, actions, idm_out, sim->veh_act);
     sim->launches++;
     CK(cudaGetLastError());
