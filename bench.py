@@ -25,6 +25,18 @@ sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 8192
 LIBRARY = "pg3_density0.1.npz"
+# BASELINE.json configs.  cfg2 is the one the metric is quoted on (the default and the only driver-run line); the others
+# are the parity-test configurations, measurable with --workload for the record (profiles/).
+WORKLOADS = {
+    "cfg2": dict(lib="pg3_density0.1.npz", envs=8192, peds=0,
+                 name="MetaDriveEnv PG 3-block maps, IDM traffic density 0.1, 1000 reference scenarios, 240-beam lidar"),
+    "cfg4": dict(lib="safe_pg3.npz", envs=8192, peds=0,
+                 name="SafeMetaDriveEnv (accident_prob 0.8, static obstacles, cost), 100 reference scenarios, 240-beam lidar"),
+    "cfg5": dict(lib="x_respawn_density0.1.npz", envs=4096, peds=16,
+                 name="MetaDriveEnv map X, respawn-mode IDM traffic + 16 crossing pedestrians per env, 240-beam lidar"),
+    "cfg3": dict(lib=None, envs=2048, peds=0,
+                 name="MultiAgentRoundaboutEnv 40 agents per env, respawn on, 240-beam lidar + crash checks"),
+}
 # SURVEY.md 8(d) algorithmic bytes per unit of work
 B_EGO = 1684.0
 B_TRAFFIC = 560.0
@@ -78,16 +90,24 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_world(n_envs, rank):
+def build_world(n_envs, rank, workload="cfg2"):
+    w = WORKLOADS[workload]
+    if workload == "cfg3":
+        from metadrive_ped_b200.envs import MultiAgentRoundaboutEnv, _ma_cfg_kw, _merge
+        from metadrive_ped_b200.ma import MultiAgentLibrary
+        c = _merge(MultiAgentRoundaboutEnv.default_config(), {"vehicle_config": {"lidar": {"num_lasers": 240, "distance": 50}}})
+        lib = MultiAgentLibrary(MultiAgentRoundaboutEnv.ASSET)
+        arrays, cfg = lib.build_world(n_envs, c["num_agents"], seed=rank, **_ma_cfg_kw(c))
+        return lib, arrays, cfg
     from metadrive_ped_b200.library import ScenarioLibrary
-    lib = ScenarioLibrary(LIBRARY)
+    lib = ScenarioLibrary(w["lib"])
     idx = [(rank * n_envs + e) % len(lib) for e in range(n_envs)]
-    arrays, cfg = lib.build_world(idx, slots_per_env=None)
+    arrays, cfg = lib.build_world(idx, slots_per_env=None, num_pedestrians=w["peds"], seed=rank)
     return lib, arrays, cfg
 
 
-def workload_name():
-    return "MetaDriveEnv PG 3-block maps, IDM traffic density 0.1, 1000 reference scenarios, 240-beam lidar"
+def workload_name(workload="cfg2"):
+    return WORKLOADS[workload]["name"]
 
 
 def run_reference(args, rank):
@@ -132,7 +152,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--actions", default="profile", choices=["profile", "random"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--burnin", type=int, default=150,
@@ -154,9 +175,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from metadrive_ped_b200.sim import BatchedSim
-    E = args.envs_per_gpu
+    E = args.envs_per_gpu or WORKLOADS[args.workload]["envs"]
+    multi = args.workload == "cfg3"
     t_build = time.time()
-    lib, arrays, cfg = build_world(E, rank)
+    lib, arrays, cfg = build_world(E, rank, args.workload)
     sim = BatchedSim(arrays, cfg, device=local_rank)
     t_build = time.time() - t_build
     A = sim.n_agents
@@ -164,7 +186,11 @@ def main():
     traffic_per_env = float((kind == 2).sum(1).mean())
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    if args.actions == "profile":
+    if multi:  # small steering noise, throttle in [0, 1]: agents drive, crash, leave the road, arrive and are respawned
+        act_dev = torch.rand((A, 2), generator=g, device=dev)
+        act_dev[:, 0] = (act_dev[:, 0] - 0.5) * 0.2
+        act_dev = act_dev.contiguous()
+    elif args.actions == "profile":
         act_dev = torch.tensor([0.0, 1.0], device=dev).repeat(A, 1).contiguous()
     else:
         act_dev = (torch.rand((A, 2), generator=g, device=dev) * 2 - 1).contiguous()
@@ -189,6 +215,7 @@ def main():
     launches0 = sim.launch_count
     sim.profile_begin(K)
     done_count = torch.zeros((), dtype=torch.int64, device=dev)
+    valid_count = torch.zeros((), dtype=torch.int64, device=dev)
     with ClockSampler(local_rank) as clocks:
         barrier()
         for k in range(K):
@@ -197,6 +224,8 @@ def main():
             sim.step(act_dev, autoreset=True)
             ev1[k].record()
             done_count += (sim.terminated | sim.truncated).sum()
+            if multi:
+                valid_count += ((sim.info_flags & 0x2000) != 0).sum()
         barrier()
     step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(K)])
     kms = sim.profile_end()  # [K, 5]: k_pre, k_dyn, k_post, fused reset (k_post in reset mode), k_lidar
@@ -205,7 +234,13 @@ def main():
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_s = float(total_ms.item()) / 1e3
-    value = world * A * K / total_s
+    # agent-steps: every env's agent steps every step; in the multi-agent workload only the seats that produced a
+    # transition count (wrecks waiting out delay_done and empty seats do not)
+    units = torch.tensor([float(valid_count.item()) if multi else float(A * K)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    value = float(units.item()) / total_s
+    live_frac = float(units.item()) / (world * A * K)
 
     # ---------------- e2e: the host-buffer call (pinned staging, H2D actions + D2H outputs inside), wall clock
     a_host = act_dev.cpu().numpy()
@@ -220,7 +255,7 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * A * Ke / float(e2e_s.item())
+    e2e_value = world * A * Ke * live_frac / float(e2e_s.item())
     h2d = A * 2 * 4
     d2h = A * (sim.obs_dim * 4 + 4 + 4 + 1 + 1 + 4 + 8 * 4)
 
@@ -238,14 +273,17 @@ def main():
         # algorithmic bytes per launch of each kernel: the SURVEY 8(d) per-unit figures split
         # by what each kernel must touch; T = alive traffic vehicles per env
         T = traffic_per_env
+        NAg = float(cfg.agents_per_env) * live_frac  # agents that step per env (1 in the single-agent workloads)
+        NP = float(WORKLOADS[args.workload]["peds"])
         per_env = {
-            "k_pre": (8 + 64) + T * (64 + 256),             # action + latches r/w ; traffic: PID/timer/route r/w + neighbours
-            "k_dyn": (192 + 48) * (1 + T),                  # state r/w + params, every vehicle
-            "k_post": 64 + 76 + 16,                         # episode/nav state r/w + 19 state floats + scalars (ego)
+            "k_pre": NAg * (8 + 64) + T * (64 + 256),       # action + latches r/w ; traffic: PID/timer/route r/w + neighbours
+            "k_dyn": (192 + 48) * (NAg + T) + 32 * NP,      # state r/w + params, every vehicle; pedestrians pos/vel r/w
+            "k_post": NAg * (64 + 76 + 16),                 # episode/nav state r/w + 19 state floats + scalars (agents)
             "k_reset": 0.0,                                 # auto-reset of finished envs: not part of the per-step figure
-            "k_lidar": B_LIDAR_SHARE,                       # neighbour footprints + 240 lidar floats
+            "k_lidar": NAg * B_LIDAR_SHARE,                 # neighbour footprints + 240 lidar floats
         }
-        assert abs(sum(per_env.values()) - (B_EGO + B_TRAFFIC * T)) < 1.0, per_env
+        B_STEP = NAg * B_EGO + B_TRAFFIC * T + 32 * NP      # bytes per env-step
+        assert abs(sum(per_env.values()) - B_STEP) < 1.0, per_env
         bytes_per_launch = E * per_env[dom]
         traffic = None
         try:
@@ -259,17 +297,18 @@ def main():
             "metric": "agent_steps_per_sec_240beam_lidar", "value": value, "unit": "agent-steps/s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(), "envs_per_gpu": E, "agents_per_env": 1,
+            "config": {"workload": workload_name(args.workload), "baseline_config": args.workload, "envs_per_gpu": E,
+                       "agents_per_env": cfg.agents_per_env - (1 if multi else 0), "live_agent_fraction": live_frac,
                        "slots_per_env": cfg.slots_per_env, "traffic_per_env_mean": traffic_per_env,
-                       "distinct_scenarios": min(len(lib), E * world), "actions": args.actions,
+                       "distinct_scenarios": (E * world if multi else min(len(lib), E * world)), "actions": args.actions,
                        "autoreset": "on device, inside the timed region", "l2": "flushed between steps (256 MiB memset, untimed)",
                        "scene_build_s": round(t_build, 1), "burnin_steps": args.burnin},
             "lidar_rays_per_sec": value * cfg.n_lasers,
             "gpu_launches": int(launches),
             "kernel_ms": {**{n: float(v) for n, v in zip(names, mean_ms)},
                           "step_total_incl_autoreset": float(step_ms.mean())},
-            "step_roofline_all_kernels": {"algorithmic_bytes_per_step": E * (B_EGO + B_TRAFFIC * T),
-                                          "achieved_gbs": E * (B_EGO + B_TRAFFIC * T) / (float(mean_ms.sum()) * 1e-3) / 1e9},
+            "step_roofline_all_kernels": {"algorithmic_bytes_per_step": E * B_STEP,
+                                          "achieved_gbs": E * B_STEP / (float(mean_ms.sum()) * 1e-3) / 1e9},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch},
@@ -278,19 +317,19 @@ def main():
             "clocks": clocks.summary(),
             "episodes_finished_frac": float(stats[0].item() / max(stats[1].item(), 1.0)),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(lib)
+        if world == 1 and not args.no_cpu_baseline and not multi:
+            line["cpu_baseline"] = cpu_baseline(lib, WORKLOADS[args.workload]["peds"])
         print(json.dumps(line), flush=True)
     sim.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(lib):
+def cpu_baseline(lib, peds=0):
     """The oracle port on the box's host cores over a bounded sample (about 10-20 s of CPU work)."""
     from oracle.oracle import OracleSim
     sample = 512
-    arrays, cfg = lib.build_world(list(range(sample)))
+    arrays, cfg = lib.build_world([i % len(lib) for i in range(sample)], num_pedestrians=peds)
     orc = OracleSim(arrays, cfg)
     orc.reset_observe()
     a = np.tile(np.array([0.0, 1.0], np.float32), (sample, 1))

@@ -347,6 +347,7 @@ __device__ void localise(const MapView& m, const float* S, int* I, const int* __
     bool on_lane = false;
     int best_any = -1, best_cur = -1, best_next = -1;
     float d_any = 1e30f, d_cur = 1e30f, d_next = 1e30f;
+    float lon_any = 0.0f, lat_any = 0.0f, lon_cur = 0.0f, lat_cur = 0.0f, lon_next = 0.0f, lat_next = 0.0f;
     const float4* bb4 = reinterpret_cast<const float4*>(m.lane_bb);
     // broad phase: only the lanes binned into the grid cell under the vehicle (ascending lane id, like a full scan)
     int k0 = 0, k1 = 0;
@@ -369,18 +370,24 @@ __device__ void localise(const MapView& m, const float* S, int* I, const int* __
         float lh = lane_heading_at(Ll, lon);
         float cosang = cosf(lh) * hx + sinf(lh) * hy;
         if (!(cosang > 0.0f)) continue;
-        float dist = lane_distance(Ll, px, py);
-        if (dist < d_any) { d_any = dist; best_any = l; }
-        if (l >= cur_first && l < cur_first + cur_n && dist < d_cur) { d_cur = dist; best_cur = l; }
-        if (next_road >= 0 && l >= nx_first && l < nx_first + nx_n && dist < d_next) { d_next = dist; best_next = l; }
+        // lane.distance (abs_lane.py:76-82) from the local coordinates already at hand (same arithmetic as lane_distance)
+        const float over = lon - Ll[LF_LENGTH], under = 0.0f - lon;
+        const float dist = fabsf(lat) + (over > 0.0f ? over : 0.0f) + (under > 0.0f ? under : 0.0f);
+        if (dist < d_any) { d_any = dist; best_any = l; lon_any = lon; lat_any = lat; }
+        if (l >= cur_first && l < cur_first + cur_n && dist < d_cur) { d_cur = dist; best_cur = l; lon_cur = lon; lat_cur = lat; }
+        if (next_road >= 0 && l >= nx_first && l < nx_first + nx_n && dist < d_next) { d_next = dist; best_next = l; lon_next = lon; lat_next = lat; }
     }
-    int lane = best_cur >= 0 ? best_cur : (next_road < 0 ? best_any : (best_next >= 0 ? best_next : best_any));
+    int lane;
+    float lon, lat;
+    if (best_cur >= 0) { lane = best_cur; lon = lon_cur; lat = lat_cur; }
+    else if (next_road >= 0 && best_next >= 0) { lane = best_next; lon = lon_next; lat = lat_next; }
+    else { lane = best_any; lon = lon_any; lat = lat_any; }
     if (on_lane) I[VI_FLAGS] |= FL_ON_LANE; else I[VI_FLAGS] &= ~FL_ON_LANE;
-    if (lane < 0) lane = I[VI_LANE];
+    const bool kept = lane < 0;
+    if (kept) lane = I[VI_LANE];
     I[VI_LANE] = lane;
     const float* Lc = m.lane_f + lane * LANE_F;
-    float lon, lat;
-    lane_local(Lc, px, py, lon, lat);
+    if (kept) lane_local(Lc, px, py, lon, lat);
     if (c0 != c1) {  // _update_target_checkpoints (:181-201)
         int start = m.lane_i[lane * LANE_I + LI_FROM];
         bool in_tail = false;
@@ -1340,7 +1347,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 __host__ __device__ inline size_t lidar_smem_per_warp(int S, int O) {
-    size_t b = (size_t)S * BODY_ROW * 4 + (size_t)O * OBJ_F * 4 + sizeof(float) * (size_t)(S + O);
+    size_t b = (size_t)S * BODY_ROW * 4 + (size_t)O * OBJ_F * 4 + (sizeof(float) + sizeof(int)) * (size_t)(S + O);
     return ((b + 15) & ~(size_t)15) + 16;
 }
 
@@ -1360,6 +1367,7 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     float* sbody = reinterpret_cast<float*>(my);
     float* sobj = reinterpret_cast<float*>(my + body_bytes);
     float* srad = reinterpret_cast<float*>(my + body_bytes + obj_bytes);
+    int* sidx = reinterpret_cast<int*>(srad + S + O);
     uint64_t* bar = reinterpret_cast<uint64_t*>(my + per_warp - 16);
 
     const long long a = (long long)blockIdx.x * LIDAR_WARPS + warp;
@@ -1463,6 +1471,26 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
             }
         }
     }
+    // candidate list: the bodies a ray of length D can reach at all (centre within D + bounding radius), in ascending
+    // index order so that ties between equal hit fractions resolve as in a full scan
+    int n_cand = 0;
+    for (int base = 0; base < S + O; base += 32) {
+        const int k = base + lane;
+        bool ok = false;
+        if (k < S + O) {
+            const float rb = srad[k];
+            if (rb >= 0.0f) {
+                const float cx = k < S ? sbody[BODY_ROW * k] : sobj[OBJ_F * (k - S) + OB_X];
+                const float cy = k < S ? sbody[BODY_ROW * k + 1] : sobj[OBJ_F * (k - S) + OB_Y];
+                const float dx = cx - o.x, dy = cy - o.y, reach = D + rb + 0.01f;
+                ok = dx * dx + dy * dy <= reach * reach;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (ok) sidx[n_cand + __popc(bal & ((1u << lane) - 1u))] = k;
+        n_cand += __popc(bal);
+    }
+    __syncwarp();
     int* hrow = hit_out ? hit_out + (size_t)a * N : nullptr;
     for (int i = lane; i < N; i += 32) {
         const float c = c_ray_cs[2 * i], s = c_ray_cs[2 * i + 1];
@@ -1470,40 +1498,38 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
         const F3 d = f3(ux * D, uy * D, 0.0f);
         float best = 2.0f;
         int hit = -1;
-        for (int k = 0; k < S; k++) {
+        for (int ci = 0; ci < n_cand; ci++) {
+            const int k = sidx[ci];
             const float rb = srad[k];
-            if (rb < 0.0f) continue;
-            const float* b = sbody + BODY_ROW * k;
-            const float rx = b[0] - o.x, ry = b[1] - o.y;
-            const float proj = rx * ux + ry * uy;
-            const float perp2 = (rx * rx + ry * ry) - proj * proj;
-            if (perp2 > rb * rb + 1e-3f || proj < -rb || proj > D + rb) continue;
-            M3 R;
-            R.m[0][0] = b[6]; R.m[0][1] = b[7]; R.m[0][2] = b[8];
-            R.m[1][0] = b[9]; R.m[1][1] = b[10]; R.m[1][2] = b[11];
-            R.m[2][0] = b[12]; R.m[2][1] = b[13]; R.m[2][2] = b[14];
-            float t = ray_obb(o, d, f3(b[0], b[1], b[2]), R, f3(b[3], b[4], b[5]));
-            if (t < best) { best = t; hit = k; }
-        }
-        for (int k = 0; k < O; k++) {
-            const float rb = srad[S + k];
-            if (rb < 0.0f) continue;
-            const float* ob = sobj + OBJ_F * k;
-            const float rx = ob[OB_X] - o.x, ry = ob[OB_Y] - o.y;
-            const float proj = rx * ux + ry * uy;
-            const float perp2 = (rx * rx + ry * ry) - proj * proj;
-            if (perp2 > rb * rb + 1e-3f || proj < -rb || proj > D + rb) continue;
             float t;
-            if (ob[OB_KIND] == 2.0f) {
-                float ch = cosf(ob[OB_HEADING]), sh = sinf(ob[OB_HEADING]);
+            if (k < S) {
+                const float* b = sbody + BODY_ROW * k;
+                const float rx = b[0] - o.x, ry = b[1] - o.y;
+                const float proj = rx * ux + ry * uy;
+                const float perp2 = (rx * rx + ry * ry) - proj * proj;
+                if (perp2 > rb * rb + 1e-3f || proj < -rb || proj > D + rb) continue;
                 M3 R;
-                R.m[0][0] = ch; R.m[0][1] = -sh; R.m[0][2] = 0.0f; R.m[1][0] = sh; R.m[1][1] = ch; R.m[1][2] = 0.0f;
-                R.m[2][0] = 0.0f; R.m[2][1] = 0.0f; R.m[2][2] = 1.0f;
-                t = ray_obb(o, d, f3(ob[OB_X], ob[OB_Y], ob[OB_ZC]), R, f3(ob[OB_B], ob[OB_A], 0.5f * ob[OB_HEIGHT]));
+                R.m[0][0] = b[6]; R.m[0][1] = b[7]; R.m[0][2] = b[8];
+                R.m[1][0] = b[9]; R.m[1][1] = b[10]; R.m[1][2] = b[11];
+                R.m[2][0] = b[12]; R.m[2][1] = b[13]; R.m[2][2] = b[14];
+                t = ray_obb(o, d, f3(b[0], b[1], b[2]), R, f3(b[3], b[4], b[5]));
             } else {
-                t = ray_zcyl(o, d, ob[OB_X], ob[OB_Y], ob[OB_ZC], ob[OB_A], 0.5f * ob[OB_HEIGHT]);
+                const float* ob = sobj + OBJ_F * (k - S);
+                const float rx = ob[OB_X] - o.x, ry = ob[OB_Y] - o.y;
+                const float proj = rx * ux + ry * uy;
+                const float perp2 = (rx * rx + ry * ry) - proj * proj;
+                if (perp2 > rb * rb + 1e-3f || proj < -rb || proj > D + rb) continue;
+                if (ob[OB_KIND] == 2.0f) {
+                    float ch = cosf(ob[OB_HEADING]), sh = sinf(ob[OB_HEADING]);
+                    M3 R;
+                    R.m[0][0] = ch; R.m[0][1] = -sh; R.m[0][2] = 0.0f; R.m[1][0] = sh; R.m[1][1] = ch; R.m[1][2] = 0.0f;
+                    R.m[2][0] = 0.0f; R.m[2][1] = 0.0f; R.m[2][2] = 1.0f;
+                    t = ray_obb(o, d, f3(ob[OB_X], ob[OB_Y], ob[OB_ZC]), R, f3(ob[OB_B], ob[OB_A], 0.5f * ob[OB_HEIGHT]));
+                } else {
+                    t = ray_zcyl(o, d, ob[OB_X], ob[OB_Y], ob[OB_ZC], ob[OB_A], 0.5f * ob[OB_HEIGHT]);
+                }
             }
-            if (t < best) { best = t; hit = S + k; }
+            if (t < best) { best = t; hit = k; }
         }
         orow[i] = best <= 1.0f ? best : 1.0f;
         if (hrow) hrow[i] = best <= 1.0f ? hit : -1;
