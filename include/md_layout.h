@@ -200,11 +200,17 @@
 #define TRIGGER_MAX 8
 
 /* ---- observation row (obs/state_obs.py:64-151, 185-232), N = 240, num_others = 0 ---------------- */
-#define OBS_EGO 9
+/* ego block = [side: 2 distances | n_side detector rays] + 6 + [lane: 1 lateral offset | n_lane detector rays]
+ * (obs/state_obs.py:77-98, 129-149; sensors/distance_detector.py:194-209) */
+#define OBS_SIDE(cfg) ((cfg).n_side_lasers > 0 ? (cfg).n_side_lasers : 2)
+#define OBS_LANE(cfg) ((cfg).n_lane_lasers > 0 ? (cfg).n_lane_lasers : 1)
+#define OBS_EGO(cfg) (OBS_SIDE(cfg) + 6 + OBS_LANE(cfg))
 #define OBS_NAVI 10
-#define OBS_STATE (OBS_EGO + OBS_NAVI)
+#define OBS_STATE(cfg) (OBS_EGO(cfg) + OBS_NAVI)
+#define MAX_DET_LASERS 128
+#define DET_HEIGHT 0.2f      /* DistanceDetector.DEFAULT_HEIGHT (sensors/distance_detector.py:92) */
 #define OBS_OTHERS(cfg) (4 * (cfg).num_others)                       /* component/sensors/lidar.py:93-138 */
-#define OBS_DIM(cfg) (OBS_STATE + OBS_OTHERS(cfg) + (cfg).n_lasers)
+#define OBS_DIM(cfg) (OBS_STATE(cfg) + OBS_OTHERS(cfg) + (cfg).n_lasers)
 
 /* ---- configuration passed by value through the C ABI ------------------------------------------- */
 typedef struct MdConfig {
@@ -222,6 +228,9 @@ typedef struct MdConfig {
     /* MultiAgentMetaDrive.done_function overrides (envs/marl_envs/multi_agent_metadrive.py:114-128) */
     int ma_crash_done, ma_out_of_road_done;
     int num_others; /* lidar.num_others: the k nearest vehicles, 4 floats each, between the state and the lidar floats */
+    /* side_detector / lane_line_detector (vehicle_config; 0 lasers = off, the reference's default) */
+    int n_side_lasers, n_lane_lasers;
+    float side_dist, lane_dist;
     int spare2;
 } MdConfig;
 

@@ -47,7 +47,8 @@
 #define LIDAR_WARPS 8
 #define MAX_LASERS 512
 
-__constant__ float c_ray_cs[2 * MAX_LASERS];
+// ray direction tables (cos, sin per laser) live in global memory, one set per handle: every lane reads a different entry
+// (constant memory would serialise that), and two handles with different laser counts must not share them
 
 enum {
     MODE_AGENT_PRE = 1, MODE_TRIGGER = 2, MODE_IDM = 4, MODE_DYN = 8, MODE_CONTACTS = 16, MODE_POST = 32,
@@ -360,6 +361,11 @@ __device__ void localise(const MapView& m, const float* S, int* I, const int* __
         float4 bb = __ldg(bb4 + l);
         if (px < bb.x || py < bb.y || px > bb.z || py > bb.w) continue;
         const float* Ll = m.lane_f + l * LANE_F;
+        if (Ll[LF_TYPE] != 0.0f) {  // hull_shortcut's radial rejection, before paying for the arc coordinates (atan2)
+            const float ro = Ll[LF_P0 + 2] + 0.5f * Ll[LF_WIDTH];
+            const float ddx = px - Ll[LF_P0 + 0], ddy = py - Ll[LF_P0 + 1];
+            if (ddx * ddx + ddy * ddy > ro * ro + 1.0f + 0.5f * ro) continue;
+        }
         float lon, lat;
         lane_local(Ll, px, py, lon, lat);
         const int sc = hull_shortcut(Ll, px, py, lon, lat);
@@ -619,8 +625,11 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         inf[1] = make_float4(C[VC_ENERGY], step_reward, C[VC_EP_REWARD], (float)I[VI_EP_LEN]);
     }
     float* o = out.obs + a * (size_t)OBS_DIM(cfg);
-    o[0] = clipf(C[VC_DIST_L] / 18.0f, 0.0f, 1.0f);
-    o[1] = clipf(C[VC_DIST_R] / 18.0f, 0.0f, 1.0f);
+    const int sd = OBS_SIDE(cfg);
+    if (cfg.n_side_lasers == 0) {  // else k_linedet fills the block
+        o[0] = clipf(C[VC_DIST_L] / 18.0f, 0.0f, 1.0f);
+        o[1] = clipf(C[VC_DIST_R] / 18.0f, 0.0f, 1.0f);
+    }
     {
         const float* Lr = m.lane_f + (cur_first + cur_n - 1) * LANE_F;
         float lx, ly;
@@ -633,25 +642,25 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         float ln = sqrtf(lx * lx + ly * ly), fn = sqrtf(hx * hx + hy * hy);
         float hd = 0.0f;
         if (ln * fn != 0.0f) hd = clipf((hx * lx + hy * ly) / (ln * fn), -1.0f, 1.0f) / 2.0f + 0.5f;
-        o[2] = hd;
+        o[sd + 0] = hd;
     }
-    o[3] = clipf((speed_kmh + 1.0f) / (P[VP_MAX_SPEED] + 1.0f), 0.0f, 1.0f);
-    o[4] = clipf((S[VS_STEER] / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
-    o[5] = clipf((C[VC_CUR_A0] + 1.0f) / 2.0f, 0.0f, 1.0f);
-    o[6] = clipf((C[VC_CUR_A1] + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o[sd + 1] = clipf((speed_kmh + 1.0f) / (P[VP_MAX_SPEED] + 1.0f), 0.0f, 1.0f);
+    o[sd + 2] = clipf((S[VS_STEER] / 60.0f + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o[sd + 3] = clipf((C[VC_CUR_A0] + 1.0f) / 2.0f, 0.0f, 1.0f);
+    o[sd + 4] = clipf((C[VC_CUR_A1] + 1.0f) / 2.0f, 0.0f, 1.0f);
     {
         float lhx = C[VC_LAST_HX], lhy = C[VC_LAST_HY];
         float dotp = hx * lhx + hy * lhy, crs = hx * lhy - hy * lhx;
         float beta = dotp <= 0.0f ? 0.5f * MD_PI : atan2f(fabsf(crs), dotp);
-        o[7] = clipf(beta / 0.1f, 0.0f, 1.0f);
+        o[sd + 5] = clipf(beta / 0.1f, 0.0f, 1.0f);
     }
-    {
+    if (cfg.n_lane_lasers == 0) {
         float lon, lat;
         lane_local(m.lane_f + lane * LANE_F, px, py, lon, lat);
-        o[8] = clipf((lat * 2.0f / 4.5f + 1.0f) / 2.0f, 0.0f, 1.0f);
+        o[sd + 6] = clipf((lat * 2.0f / 4.5f + 1.0f) / 2.0f, 0.0f, 1.0f);
     }
 #pragma unroll
-    for (int k = 0; k < NAVI_DIM; k++) o[OBS_EGO + k] = navi[k];
+    for (int k = 0; k < NAVI_DIM; k++) o[OBS_EGO(cfg) + k] = navi[k];
 }
 
 __device__ __forceinline__ void load16(float* dst, const float* src) {
@@ -1069,7 +1078,7 @@ __global__ void k_restore_post(MdConfig cfg, MdArrays A, Snapshot post, const fl
     for (int k = 0; k < BODY_ROW / 4; k++) d4[k] = b4[k];
     if (slot < cfg.agents_per_env) {
         const size_t a = (size_t)env * cfg.agents_per_env + slot;
-        for (int k = 0; k < OBS_STATE; k++) obs[a * (size_t)OBS_DIM(cfg) + k] = post_obs[a * OBS_STATE + k];
+        for (int k = 0; k < OBS_STATE(cfg); k++) obs[a * (size_t)OBS_DIM(cfg) + k] = post_obs[a * OBS_STATE(cfg) + k];
     }
 }
 __global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t* __restrict__ env_mask) {
@@ -1357,7 +1366,7 @@ __host__ __device__ inline size_t lidar_smem_per_warp(int S, int O) {
 __global__ void __launch_bounds__(LIDAR_WARPS * 32)
 k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restrict__ obj_f, const int* __restrict__ veh_i,
         const float* __restrict__ veh_p, float* __restrict__ out, int out_stride, int out_off, int* __restrict__ hit_out, const uint8_t* __restrict__ env_mask,
-        const int* __restrict__ agent_flags, int need_flag) {
+        const int* __restrict__ agent_flags, int need_flag, const float* __restrict__ ray_cs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env, N = cfg.n_lasers;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1493,7 +1502,8 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     __syncwarp();
     int* hrow = hit_out ? hit_out + (size_t)a * N : nullptr;
     for (int i = lane; i < N; i += 32) {
-        const float c = c_ray_cs[2 * i], s = c_ray_cs[2 * i + 1];
+        const float2 cs = __ldg(reinterpret_cast<const float2*>(ray_cs) + i);
+        const float c = cs.x, s = cs.y;
         const float ux = hx * c - hy * s, uy = hy * c + hx * s;   // unit direction (distance_detector.py:177-180)
         const F3 d = f3(ux * D, uy * D, 0.0f);
         float best = 2.0f;
@@ -1533,6 +1543,78 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
         }
         orow[i] = best <= 1.0f ? best : 1.0f;
         if (hrow) hrow[i] = best <= 1.0f ? hit : -1;
+    }
+}
+
+// ---- k_linedet: SideDetector / LaneLineDetector.perceive (sensors/distance_detector.py:27-85, 194-209; called from
+// obs/state_obs.py:77-86, 129-140).  One warp per agent, one lane per ray: horizontal rays at z = 0.2 from the vehicle
+// position, start phase 90 degrees, against the lane-line ghost boxes of the static world (half extents len/2 x 0.0375 x
+// 1.0 at z = 0.5).  The ray walks the map's 8 m uniform grid (the static broad phase) cell by cell and stops as soon as
+// the nearest hit lies before the cell's exit.  Pass 0 = side detector (continuous lines), pass 1 = lane-line detector
+// (continuous + broken).
+__global__ void __launch_bounds__(LIDAR_WARPS * 32)
+k_linedet(MdConfig cfg, MdArrays A, const float* __restrict__ body_tab, float* __restrict__ out,
+          const uint8_t* __restrict__ env_mask, const int* __restrict__ agent_flags, int need_flag,
+          const float* __restrict__ side_cs, const float* __restrict__ lane_cs) {
+    const int S = cfg.slots_per_env, NA = cfg.agents_per_env;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long a = (long long)blockIdx.x * LIDAR_WARPS + warp;
+    if (a >= (long long)cfg.n_envs * NA) return;
+    const int env = (int)(a / NA), slot = (int)(a - (long long)env * NA);
+    if (env_mask != nullptr && env_mask[env] == 0) return;
+    if (agent_flags != nullptr) { if (!(agent_flags[a] & need_flag)) return; }
+    else if (!A.veh_i[(size_t)(env * S + slot) * VEH_I + VI_ACTIVE]) return;
+    const float* eb = body_tab + (size_t)(env * S + slot) * BODY_ROW;
+    float hx, hy;
+    {
+        const float fx = eb[7], fy = eb[10], n = sqrtf(fx * fx + fy * fy);
+        hx = fx / n; hy = fy / n;
+    }
+    const F3 o = f3(eb[16], eb[17], DET_HEIGHT);
+    const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+    const float4* line4 = reinterpret_cast<const float4*>(m.lines);
+    float* orow = out + (size_t)a * OBS_DIM(cfg);
+    for (int pass = 0; pass < 2; pass++) {
+        const int n = pass == 0 ? cfg.n_side_lasers : cfg.n_lane_lasers;
+        const float D = pass == 0 ? cfg.side_dist : cfg.lane_dist;
+        const float* tab = pass == 0 ? side_cs : lane_cs;
+        float* dst = orow + (pass == 0 ? 0 : OBS_SIDE(cfg) + 6);
+        for (int i = lane; i < n; i += 32) {
+            const float c = tab[2 * i], s = tab[2 * i + 1];
+            const float ux = hx * c - hy * s, uy = hy * c + hx * s;
+            const F3 d = f3(ux * D, uy * D, 0.0f);
+            float best = 2.0f;
+            // grid walk (Amanatides-Woo) in units of the ray parameter t in [0, 1]
+            int cx = (int)floorf((o.x - m.gx0) / m.cell), cy = (int)floorf((o.y - m.gy0) / m.cell);
+            const int sx = d.x > 0.0f ? 1 : -1, sy = d.y > 0.0f ? 1 : -1;
+            const float inv_x = d.x != 0.0f ? 1.0f / d.x : 3.0e38f, inv_y = d.y != 0.0f ? 1.0f / d.y : 3.0e38f;
+            float tx = d.x != 0.0f ? ((m.gx0 + (float)(cx + (sx > 0)) * m.cell) - o.x) * inv_x : 3.0e38f;
+            float ty = d.y != 0.0f ? ((m.gy0 + (float)(cy + (sy > 0)) * m.cell) - o.y) * inv_y : 3.0e38f;
+            const float dtx = fabsf(m.cell * inv_x), dty = fabsf(m.cell * inv_y);
+            for (int guard = 0; guard < 64; guard++) {
+                if (cx >= 0 && cy >= 0 && cx < m.nx && cy < m.ny) {
+                    const int cidx = cy * m.nx + cx;
+                    const int k1 = m.gs[cidx + 1];
+                    for (int k = m.gs[cidx]; k < k1; k++) {
+                        const int it = __ldg(m.gi + k);
+                        if (it >= m.n_lines) continue;  // sidewalk quads live in the same grid
+                        const float4 h = __ldg(line4 + 2 * it);   // cx cy half kind
+                        if (pass == 0 && h.w >= 2.0f) continue;   // ContinuousLaneLine only
+                        const float4 u = __ldg(line4 + 2 * it + 1);
+                        M3 R;
+                        R.m[0][0] = u.x; R.m[0][1] = -u.y; R.m[0][2] = 0.0f; R.m[1][0] = u.y; R.m[1][1] = u.x; R.m[1][2] = 0.0f;
+                        R.m[2][0] = 0.0f; R.m[2][1] = 0.0f; R.m[2][2] = 1.0f;
+                        const float t = ray_obb(o, d, f3(h.x, h.y, 0.5f), R, f3(h.z, LINE_HALF_W, 1.0f));
+                        if (t < best) best = t;
+                    }
+                }
+                const float t_exit = fminf(tx, ty);
+                // a hit found so far lies inside the visited cells (+ 5 cm slack for boxes registered by their AABB)
+                if (best <= t_exit || t_exit > 1.0f) break;
+                if (tx < ty) { cx += sx; tx += dtx; } else { cy += sy; ty += dty; }
+            }
+            dst[i] = best <= 1.0f ? best : 1.0f;
+        }
     }
 }
 
@@ -1692,6 +1774,7 @@ struct md_sim {
     float* post_obs;        // [A, OBS_STATE]: the state part of the reset observation
     bool post_valid;
     float* body_tab;
+    float* ray_tab;         // [2*MAX_LASERS lidar | 2*MAX_DET_LASERS side | 2*MAX_DET_LASERS lane] (cos, sin) pairs
     float4* veh_act;        // [NV] steering rad, engine force, brake: k_pre -> k_dyn
     uint8_t* mask;
     cudaStream_t stream;    // own stream for the *_host entry points
@@ -1745,6 +1828,7 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     sim->cfg = *cfg;
     sim->device = device;
     sim->loaded = false;
+    sim->ray_tab = nullptr;
     sim->post_valid = false;
     sim->launches = 0;
     sim->prof_cap = 0;
@@ -1758,13 +1842,29 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     }
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
-    std::vector<float> tab(2 * MAX_LASERS, 0.0f);
+    if (cfg->n_side_lasers > MAX_DET_LASERS || cfg->n_lane_lasers > MAX_DET_LASERS) {
+        sim->err = "side / lane-line detector: at most 128 lasers";
+        return -4;
+    }
+    // ray tables: lidar laser i points at heading + i*2pi/N (distance_detector.py:177-180); the detectors start at 90 degrees
+    // (distance_detector.py:197, 206).  cos / sin in double, rounded to float - the same table the oracle builds.
+    std::vector<float> tab(2 * MAX_LASERS + 4 * MAX_DET_LASERS, 0.0f);
     for (int i = 0; i < cfg->n_lasers; i++) {
         double a = (double)i * (2.0 * 3.14159265358979323846 / (double)cfg->n_lasers);
         tab[2 * i] = (float)cos(a);
         tab[2 * i + 1] = (float)sin(a);
     }
-    CK(cudaMemcpyToSymbol(c_ray_cs, tab.data(), sizeof(float) * 2 * MAX_LASERS));
+    for (int pass = 0; pass < 2; pass++) {
+        const int n = pass == 0 ? cfg->n_side_lasers : cfg->n_lane_lasers;
+        float* dt = tab.data() + 2 * MAX_LASERS + pass * 2 * MAX_DET_LASERS;
+        for (int i = 0; i < n; i++) {
+            double a = (double)i * (2.0 * 3.14159265358979323846 / (double)n);
+            dt[2 * i] = -(float)sin(a);
+            dt[2 * i + 1] = (float)cos(a);
+        }
+    }
+    CK(cudaMalloc(&sim->ray_tab, tab.size() * sizeof(float)));
+    CK(cudaMemcpy(sim->ray_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -1785,6 +1885,7 @@ extern "C" void md_destroy(md_sim* sim) {
         cudaFree(sim->d_actions); cudaFree(sim->d_obs); cudaFree(sim->d_reward); cudaFree(sim->d_cost); cudaFree(sim->d_info_f);
         cudaFree(sim->d_term); cudaFree(sim->d_trunc); cudaFree(sim->d_mask_in); cudaFree(sim->d_info_flags);
     }
+    cudaFree(sim->ray_tab);
     cudaStreamDestroy(sim->stream);
     delete sim;
 }
@@ -1834,7 +1935,7 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
     for (int k = 0; k < N_SNAP; k++) CK(cudaMalloc(&sim->post_bufs[k], sim->bytes[kSnapIdx[k]] ? sim->bytes[kSnapIdx[k]] : 16));
     set_snapshot_ptrs(sim->post, sim->post_bufs);
     CK(cudaMalloc(&sim->post_body, (size_t)NV * BODY_ROW * 4));
-    CK(cudaMalloc(&sim->post_obs, (size_t)c.n_envs * c.agents_per_env * OBS_STATE * 4));
+    CK(cudaMalloc(&sim->post_obs, (size_t)c.n_envs * c.agents_per_env * OBS_STATE(c) * 4));
     CK(cudaMalloc(&sim->body_tab, (size_t)NV * BODY_ROW * 4));
     CK(cudaMemset(sim->body_tab, 0, (size_t)NV * BODY_ROW * 4));
     CK(cudaMalloc(&sim->veh_act, (size_t)NV * sizeof(float4)));
@@ -1987,9 +2088,15 @@ static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* h
     int blocks = (int)((na + LIDAR_WARPS - 1) / LIDAR_WARPS);
     size_t smem = lidar_smem_per_warp(c.slots_per_env, c.objs_per_env) * LIDAR_WARPS;
     k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, sim->dev.veh_p, out, stride, off, hit, mask,
-                                                    agent_flags, need_flag);
+                                                    agent_flags, need_flag, sim->ray_tab);
     sim->launches++;
     CK(cudaGetLastError());
+    if (off >= 0 && (c.n_side_lasers > 0 || c.n_lane_lasers > 0)) {  // the detector blocks of the same observation rows
+        k_linedet<<<blocks, LIDAR_WARPS * 32, 0, st>>>(c, sim->dev, sim->body_tab, out, mask, agent_flags, need_flag,
+                                                       sim->ray_tab + 2 * MAX_LASERS, sim->ray_tab + 2 * MAX_LASERS + 2 * MAX_DET_LASERS);
+        sim->launches++;
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 static int launch_respawn(md_sim* sim, StepOut out, cudaStream_t st) {
@@ -2015,11 +2122,11 @@ extern "C" int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev
         for (int k = 0; k < N_SNAP; k++)
             CK(cudaMemcpyAsync(sim->post_bufs[k], *arr_slot(&sim->dev, kSnapIdx[k]), sim->bytes[kSnapIdx[k]], cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(sim->post_body, sim->body_tab, (size_t)c.n_envs * c.slots_per_env * BODY_ROW * 4, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpy2DAsync(sim->post_obs, OBS_STATE * 4, obs_dev, (size_t)OBS_DIM(c) * 4, OBS_STATE * 4,
+        CK(cudaMemcpy2DAsync(sim->post_obs, OBS_STATE(c) * 4, obs_dev, (size_t)OBS_DIM(c) * 4, OBS_STATE(c) * 4,
                              (size_t)c.n_envs * c.agents_per_env, cudaMemcpyDeviceToDevice, st));
         sim->post_valid = true;
     }
-    return launch_lidar(sim, obs_dev, OBS_DIM(sim->cfg), OBS_STATE, nullptr, env_mask_dev, st);
+    return launch_lidar(sim, obs_dev, OBS_DIM(sim->cfg), OBS_STATE(sim->cfg), nullptr, env_mask_dev, st);
 }
 
 // one env.step; `fused_reset` (single agent only): finished envs are reset in place before the observation is taken, so
@@ -2048,14 +2155,14 @@ static int step_impl(md_sim* sim, const float* actions_dev, StepOut out, cudaStr
     if (prof) CK(cudaEventRecord(ev[4], st));
     const int od = OBS_DIM(sim->cfg);
     if (!sim->cfg.is_multi_agent) {
-        if (launch_lidar(sim, out.obs, od, OBS_STATE, nullptr, nullptr, st)) return -1;
+        if (launch_lidar(sim, out.obs, od, OBS_STATE(sim->cfg), nullptr, nullptr, st)) return -1;
     } else {
         // multi-agent: everyone who produced a transition observes (incl. agents that just finished), then finished
         // vehicles leave / freeze, at most one agent per env is respawned and observes the world after that
         if (!out.info_flags) { sim->err = "multi-agent md_step needs info_flags"; return -2; }
-        if (launch_lidar(sim, out.obs, od, OBS_STATE, nullptr, nullptr, st, out.info_flags, FL_VALID)) return -1;
+        if (launch_lidar(sim, out.obs, od, OBS_STATE(sim->cfg), nullptr, nullptr, st, out.info_flags, FL_VALID)) return -1;
         if (launch_respawn(sim, out, st)) return -1;
-        if (sim->cfg.allow_respawn && launch_lidar(sim, out.obs, od, OBS_STATE, nullptr, nullptr, st, out.info_flags, FL_NEWBORN))
+        if (sim->cfg.allow_respawn && launch_lidar(sim, out.obs, od, OBS_STATE(sim->cfg), nullptr, nullptr, st, out.info_flags, FL_NEWBORN))
             return -1;
     }
     if (prof) { CK(cudaEventRecord(ev[5], st)); sim->prof_n++; }

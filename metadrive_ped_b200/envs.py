@@ -92,6 +92,14 @@ def _merge(default, user, path=""):
     return out
 
 
+def _obs_dim(vc):
+    """LidarStateObservation.observation_space (obs/state_obs.py:30-62, 172-183): side block (2 distances or the side
+    detector's rays) + 6 + lane block (1 offset or the lane-line detector's rays) + navi 10 + others 4k + lidar N."""
+    side = vc["side_detector"]["num_lasers"] or 2
+    lane = vc["lane_line_detector"]["num_lasers"] or 1
+    return side + 6 + lane + 10 + 4 * vc["lidar"]["num_others"] + vc["lidar"]["num_lasers"]
+
+
 class _Agent:
     """Read-only view of the ego for the attributes the reference's tests poke at (env.agent.position, ...)."""
     def __init__(self, env):
@@ -155,8 +163,7 @@ class MetaDriveEnv:
         self.current_seed = None
         self.agent = _Agent(self)
         self.episode_cost = 0.0
-        n = lid["num_lasers"] + 4 * lid["num_others"]
-        self.observation_space = _box(-0.0, 1.0, (19 + n, ))
+        self.observation_space = _box(-0.0, 1.0, (_obs_dim(self.config["vehicle_config"]), ))
         self.action_space = _box(-1.0, 1.0, (2, ))
 
     # -- scenes
@@ -184,6 +191,10 @@ class MetaDriveEnv:
         return dict(
             n_lasers=c["vehicle_config"]["lidar"]["num_lasers"], lidar_dist=float(c["vehicle_config"]["lidar"]["distance"]),
             num_others=int(c["vehicle_config"]["lidar"]["num_others"]),
+            n_side_lasers=int(c["vehicle_config"]["side_detector"]["num_lasers"]),
+            side_dist=float(c["vehicle_config"]["side_detector"]["distance"]),
+            n_lane_lasers=int(c["vehicle_config"]["lane_line_detector"]["num_lasers"]),
+            lane_dist=float(c["vehicle_config"]["lane_line_detector"]["distance"]),
             horizon=int(c["horizon"] or 0), decision_repeat=c["decision_repeat"], dt=c["physics_world_step_size"],
             traffic_mode=TRAFFIC_MODES[c["traffic_mode"]], success_reward=c["success_reward"],
             out_of_road_penalty=c["out_of_road_penalty"], crash_vehicle_penalty=c["crash_vehicle_penalty"],
@@ -349,7 +360,7 @@ class MultiAgentMetaDrive:
             self.num_agents = self._lib.max_capacity
         assert 0 < self.num_agents <= self._lib.max_capacity, \
             "Too many agents! We only accept {} agents, but you have {} agents!".format(self._lib.max_capacity, self.num_agents)
-        self._obs_box = _box(-0.0, 1.0, (19 + 4 * lid["num_others"] + lid["num_lasers"], ))
+        self._obs_box = _box(-0.0, 1.0, (_obs_dim(self.config["vehicle_config"]), ))
         self._act_box = _box(-1.0, 1.0, (2, ))
         self._seat_id = ["agent%d" % k for k in range(self.num_agents)] + [None]
         self._active = set(self._seat_id[:self.num_agents])

@@ -35,7 +35,8 @@ class BatchedSim:
         ha = MdArrays(**{k: self._host[k].ctypes.data_as(C.c_void_p) for k in ARRAY_ORDER})
         self._check(self.lib.md_load_scene(self.h, C.byref(ha), rows))
         self.n_agents = cfg.n_envs * cfg.agents_per_env
-        self.obs_dim = 19 + 4 * cfg.num_others + cfg.n_lasers
+        self.state_dim = (cfg.n_side_lasers or 2) + 6 + (cfg.n_lane_lasers or 1) + 10
+        self.obs_dim = self.state_dim + 4 * cfg.num_others + cfg.n_lasers
         na = self.n_agents
         kw = dict(device=self.tdev)
         self.obs = torch.zeros((na, self.obs_dim), dtype=torch.float32, **kw)

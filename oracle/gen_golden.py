@@ -77,7 +77,11 @@ def run_episode(env_cls, config, seed, actions, tag):
             obs=np.stack(obs).astype(np.float32), reward=np.asarray(rew, np.float64), cost=np.asarray(cost, np.float64),
             terminated=np.asarray(term, bool), truncated=np.asarray(trunc, bool), info=np.asarray(infos, np.float64),
             config=json.dumps(dict({k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))},
-                                   num_others=int(env.config["vehicle_config"]["lidar"]["num_others"]))),
+                                   num_others=int(env.config["vehicle_config"]["lidar"]["num_others"]),
+                                   n_side_lasers=int(env.config["vehicle_config"]["side_detector"]["num_lasers"]),
+                                   side_dist=float(env.config["vehicle_config"]["side_detector"]["distance"]),
+                                   n_lane_lasers=int(env.config["vehicle_config"]["lane_line_detector"]["num_lasers"]),
+                                   lane_dist=float(env.config["vehicle_config"]["lane_line_detector"]["distance"]))),
             **{"init_" + k: v for k, v in init.items()},
         )
         sb = rx.export_static_bodies(env.engine)
@@ -356,6 +360,11 @@ def main():
         ("cfg2_pg3_seed11_others4", MetaDriveEnv,
          dict(map=3, traffic_density=0.3, num_scenarios=20, start_seed=0, log_level=50,
               vehicle_config=dict(lidar=dict(num_others=4))), 11, smooth),
+        # side / lane-line detectors on (sensors/distance_detector.py:194-209): their rays replace the 2 + 1 floats
+        ("cfg2_pg3_seed3_detectors", MetaDriveEnv,
+         dict(map=3, traffic_density=0.1, num_scenarios=20, start_seed=0, log_level=50,
+              vehicle_config=dict(side_detector=dict(num_lasers=32, distance=50),
+                                  lane_line_detector=dict(num_lasers=16, distance=20))), 3, smooth),
         # BASELINE config 4: SafeMetaDriveEnv with static obstacles
         ("cfg4_safe_seed2", SafeMetaDriveEnv, dict(num_scenarios=20, start_seed=0, log_level=50), 2, smooth),
         ("cfg4_safe_seed5", SafeMetaDriveEnv, dict(num_scenarios=20, start_seed=0, log_level=50), 5, smooth),

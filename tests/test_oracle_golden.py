@@ -104,10 +104,19 @@ def test_oracle_replays_reference_trace(tag, oracle_lib):
     arrays, cfg, _ = golden_world(g)
     sim = OracleSim(arrays, cfg)
     obs0 = sim.reset_observe().copy()
-    np.testing.assert_allclose(obs0[0, :19], g["obs"][0][:19], atol=1e-5, rtol=0)
-    np.testing.assert_allclose(obs0[0, 19:], g["obs"][0][19:], atol=1e-5, rtol=1e-4)
+    # observation layout: [side block | 6 | lane block | navi 10] [others 4k] [lidar N]; the side / lane blocks are
+    # detector rays when the detectors are on (obs/state_obs.py:77-98, 129-149)
+    SD = sim.state_dim
+    ns, nl = cfg.n_side_lasers, cfg.n_lane_lasers
+    ray_cols = np.zeros(SD, bool)
+    if ns:
+        ray_cols[:ns] = True
+    if nl:
+        ray_cols[(ns or 2) + 6:(ns or 2) + 6 + nl] = True
+    np.testing.assert_allclose(obs0[0, :SD], g["obs"][0][:SD], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(obs0[0, SD:], g["obs"][0][SD:], atol=1e-5, rtol=1e-4)
     K4 = 4 * cfg.num_others  # lidar.num_others block between the state and the lidar floats
-    assert obs0.shape[1] == 19 + K4 + cfg.n_lasers == g["obs"].shape[1]
+    assert obs0.shape[1] == SD + K4 + cfg.n_lasers == g["obs"].shape[1]
     T, n = len(g["reward"]), g["veh_f"].shape[1]
     skip = KNIFE_EDGES.get(tag, {})
     events = np.asarray(g["respawn_events"]).reshape(-1, 5) if "respawn_events" in g else np.zeros((0, 5))
@@ -141,14 +150,21 @@ def test_oracle_replays_reference_trace(tag, oracle_lib):
         assert sim.cost[0] == g["cost"][t]
         assert bool(te[0]) == bool(g["terminated"][t]) and bool(tr[0]) == bool(g["truncated"][t])
         np.testing.assert_allclose(sim.info_f[0, [0, 1, 2, 5, 6, 7]], g["info"][t][[0, 1, 2, 5, 6, 7]], atol=2e-3, rtol=1e-4)
-        np.testing.assert_allclose(obs[0, :19], g["obs"][t + 1][:19], atol=5e-4, rtol=0)
+        ref_o = g["obs"][t + 1]
+        np.testing.assert_allclose(obs[0, :SD][~ray_cols], ref_o[:SD][~ray_cols], atol=5e-4, rtol=0)
+        if ns:  # detector rays: same tolerance and glancing rule as the lidar (line ends are silhouette edges)
+            n_glance += glancing_rays(obs[0, :ns], ref_o[:ns], atol=5e-4)
+        if nl:
+            n_glance += glancing_rays(obs[0, (ns or 2) + 6:(ns or 2) + 6 + nl], ref_o[(ns or 2) + 6:(ns or 2) + 6 + nl], atol=5e-4)
         ego_pose_ok = 0 not in skip
         if K4 and (not skip or t < min(skip.values())):
-            np.testing.assert_allclose(obs[0, 19:19 + K4], g["obs"][t + 1][19:19 + K4], atol=5e-4, rtol=0)
+            np.testing.assert_allclose(obs[0, SD:SD + K4], ref_o[SD:SD + K4], atol=5e-4, rtol=0)
             others_checked += 1
         if ego_pose_ok and not skip:
-            n_glance += glancing_rays(obs[0, 19 + K4:], g["obs"][t + 1][19 + K4:])
-    assert n_glance <= max(2, 1e-4 * 240 * T), "%d glancing rays" % n_glance
+            n_glance += glancing_rays(obs[0, SD + K4:], ref_o[SD + K4:])
+    assert n_glance <= max(2, 1e-4 * (240 + ns + nl) * T), "%d glancing rays" % n_glance
+    if ns:
+        assert (g["obs"][:, :ns] < 1.0).any() and (g["obs"][:, (ns or 2) + 6:(ns or 2) + 6 + nl] < 1.0).any()
     assert not K4 or others_checked >= 20
 
 
