@@ -37,19 +37,19 @@ const char* md_last_error(const md_sim* sim);
 /* scene upload: replaces PGMap/BaseBlock.create_in_world + manager.reset() spawning bodies into the Bullet worlds
  * (component/pgblock/pg_block.py:248-256, component/block/base_block.py:431-519, manager/traffic_manager.py:51-72,
  * manager/object_manager.py:40-91).  `host` holds HOST pointers in the md_layout.h layouts; `rows[i]` is the row
- * count of the i-th array in MdArrays field order (24 arrays).  The library copies everything and keeps a device snapshot of the
+ * count of the i-th array in MdArrays field order (28 arrays).  The library copies everything and keeps a device snapshot of the
  * mutable arrays as the reset state.  Caller keeps ownership of the host buffers. */
 int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* rows);
 
 /* env.reset(): replaces BaseEnv.reset -> engine.reset + _get_reset_return (envs/base_env.py:502-584).
  * Restores the snapshot of every env whose mask byte is non-zero (all envs if env_mask_dev == NULL), runs the
- * reset-time after_step and writes the first observation of their agents into obs_dev [A, 19 + n_lasers]. */
+ * reset-time after_step and writes the first observation of their agents into obs_dev [A, OBS_DIM(cfg)]. */
 int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev, void* stream);
 
 /* env.step(): replaces BaseEnv.step = _step_simulator + _get_step_return (envs/base_env.py:426-463, 586-623):
  * engine.before_step (agent actuation, trigger, IDM), decision_repeat x doPhysics + contact callback,
  * engine.after_step (localisation, state check), reward / cost / done, LidarStateObservation.observe.
- * actions_dev [A,2]; obs_dev [A, 19+n_lasers]; reward/cost [A] f32; terminated/truncated [A] u8;
+ * actions_dev [A,2]; obs_dev [A, OBS_DIM(cfg)] (19 + 4*num_others + n_lasers by default); reward/cost [A] f32; terminated/truncated [A] u8;
  * info_flags [A] i32 (FL_* bits); info_f [A,8] f32 = velocity, steering, acceleration, step_energy, episode_energy,
  * step_reward, episode_reward, episode_length. */
 int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
