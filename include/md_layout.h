@@ -231,7 +231,9 @@ typedef struct MdConfig {
     /* side_detector / lane_line_detector (vehicle_config; 0 lasers = off, the reference's default) */
     int n_side_lasers, n_lane_lasers;
     float side_dist, lane_dist;
-    int spare2;
+    /* EnvInputPolicy.convert_to_continuous_action (policy/env_input_policy.py:40-48): 0 = continuous [steer, throttle];
+     * 1 = Discrete(steering_dim * throttle_dim), the index travels in actions[:, 0]; 2 = MultiDiscrete([sd, td]) */
+    int discrete_action, discrete_steering_dim, discrete_throttle_dim;
 } MdConfig;
 
 /* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */

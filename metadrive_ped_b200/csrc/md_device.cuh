@@ -479,6 +479,15 @@ __device__ void vehicle_substep(const float* __restrict__ P, Body& B, Actuation 
     B.pos = pos; B.v = v; B.w = w;
 }
 
+// EnvInputPolicy.convert_to_continuous_action (policy/env_input_policy.py:40-48); the reference computes in float64
+__device__ __forceinline__ void decode_action(const MdConfig& cfg, float& a0, float& a1) {
+    if (cfg.discrete_action == 0) return;
+    const double su = 2.0 / (double)(cfg.discrete_steering_dim - 1), tu = 2.0 / (double)(cfg.discrete_throttle_dim - 1);
+    if (cfg.discrete_action == 2) { a0 = (float)((double)a0 * su - 1.0); a1 = (float)((double)a1 * tu - 1.0); return; }
+    const int idx = (int)a0;
+    a0 = (float)((double)(idx % cfg.discrete_steering_dim) * su - 1.0);
+    a1 = (float)((double)(idx / cfg.discrete_steering_dim) * tu - 1.0);
+}
 // BaseVehicle._preprocess_action + _set_action + _apply_throttle_brake (base_vehicle.py:204-209, 447-484)
 __device__ __forceinline__ float scrub(float a) {  // utils/math.py:16-26
     if (isnan(a)) return 0.0f;

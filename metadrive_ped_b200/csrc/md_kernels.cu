@@ -797,7 +797,9 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
                 load16(C, A.veh_c + g * VEH_C);
                 latch_before_step(St, C, I);
                 const float* a = actions + ((size_t)env * NA + slot) * 2;
-                const Actuation act = actuate(P, St, C, a[0], a[1]);
+                float a0 = a[0], a1 = a[1];
+                decode_action(cfg, a0, a1);
+                const Actuation act = actuate(P, St, C, a0, a1);
                 veh_act[g] = make_float4(act.steer_rad, act.engine, act.brake, 0.0f);
                 store16(A.veh_s + g * VEH_S, St);
                 store16(A.veh_c + g * VEH_C, C);

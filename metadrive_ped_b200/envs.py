@@ -25,6 +25,7 @@ STEP_DEFAULTS = dict(
     start_seed=0, num_scenarios=1, map=3, traffic_density=0.1, traffic_mode="trigger", need_inverse_traffic=False,
     random_traffic=False, accident_prob=0.0, static_traffic_object=True, random_spawn_lane_index=True, horizon=None,
     truncate_as_terminate=False, decision_repeat=5, physics_world_step_size=2e-2, discrete_action=False,
+    use_multi_discrete=False, discrete_steering_dim=5, discrete_throttle_dim=5,
     success_reward=10.0, out_of_road_penalty=5.0, crash_vehicle_penalty=5.0, crash_object_penalty=5.0,
     driving_reward=1.0, speed_reward=0.1, use_lateral_reward=False, crash_vehicle_cost=1.0, crash_object_cost=1.0,
     out_of_road_cost=1.0, out_of_route_done=False, on_continuous_line_done=True, crash_vehicle_done=True,
@@ -38,7 +39,7 @@ STEP_DEFAULTS = dict(
     # config 5 - the reference has the Pedestrian object but no spawner for PG maps)
     device=0, num_pedestrians=0,
 )
-UNSUPPORTED_TRUE = ("use_render", "image_observation", "manual_control", "discrete_action", "random_agent_model",
+UNSUPPORTED_TRUE = ("use_render", "image_observation", "manual_control", "random_agent_model",
                     "need_inverse_traffic", "random_traffic")
 
 
@@ -57,6 +58,38 @@ class Box:
 
     def sample(self):
         return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+
+class Discrete:
+    """gymnasium.spaces.Discrete / MultiDiscrete stand-in (policy/env_input_policy.py:50-68)."""
+    def __init__(self, nvec):
+        self.nvec = np.atleast_1d(np.asarray(nvec, np.int64))
+        self.n = int(self.nvec[0]) if self.nvec.size == 1 else None
+        self.shape = () if self.nvec.size == 1 else (self.nvec.size, )
+
+    def contains(self, x):
+        x = np.atleast_1d(np.asarray(x))
+        return x.shape == self.nvec.shape and np.issubdtype(x.dtype, np.integer) and bool(np.all((x >= 0) & (x < self.nvec)))
+
+    __contains__ = contains
+
+    def sample(self):
+        v = np.array([np.random.randint(n) for n in self.nvec])
+        return int(v[0]) if self.nvec.size == 1 else v
+
+
+def _action_space(c):
+    if not c["discrete_action"]:
+        return _box(-1.0, 1.0, (2, ))
+    sd, td = c["discrete_steering_dim"], c["discrete_throttle_dim"]
+    return Discrete([sd, td]) if c["use_multi_discrete"] else Discrete(sd * td)
+
+
+def _action_row(c, action):
+    """One agent's action as the [A, 2] float row the library takes (Discrete: the index travels in column 0)."""
+    if c["discrete_action"] and not c["use_multi_discrete"]:
+        return np.array([float(int(action)), 0.0], np.float32)
+    return np.asarray(action, np.float32).reshape(2)
 
 
 def _box(low, high, shape):
@@ -164,7 +197,7 @@ class MetaDriveEnv:
         self.agent = _Agent(self)
         self.episode_cost = 0.0
         self.observation_space = _box(-0.0, 1.0, (_obs_dim(self.config["vehicle_config"]), ))
-        self.action_space = _box(-1.0, 1.0, (2, ))
+        self.action_space = _action_space(self.config)
 
     # -- scenes
     def _library(self):
@@ -205,6 +238,8 @@ class MetaDriveEnv:
             crash_vehicle_done=int(c["crash_vehicle_done"]), crash_object_done=int(c["crash_object_done"]),
             crash_human_done=int(c["crash_human_done"]), truncate_as_terminate=int(c["truncate_as_terminate"]),
             enable_idm_lane_change=int(c["enable_idm_lane_change"]),
+            discrete_action=(2 if c["use_multi_discrete"] else 1) if c["discrete_action"] else 0,
+            discrete_steering_dim=int(c["discrete_steering_dim"]), discrete_throttle_dim=int(c["discrete_throttle_dim"]),
         )
 
     # -- gym surface
@@ -228,7 +263,7 @@ class MetaDriveEnv:
 
     def step(self, action):
         assert self._sim is not None, "call reset() first"
-        a = np.asarray(action, np.float32).reshape(1, 2)
+        a = _action_row(self.config, action).reshape(1, 2)
         obs, rew, cost, term, trunc, flags, info_f = self._sim.step_host(a, autoreset=False)
         self.episode_cost += float(cost[0])
         info = self._info((a[0], float(cost[0]), int(flags[0]), info_f[0]))
@@ -361,7 +396,7 @@ class MultiAgentMetaDrive:
         assert 0 < self.num_agents <= self._lib.max_capacity, \
             "Too many agents! We only accept {} agents, but you have {} agents!".format(self._lib.max_capacity, self.num_agents)
         self._obs_box = _box(-0.0, 1.0, (_obs_dim(self.config["vehicle_config"]), ))
-        self._act_box = _box(-1.0, 1.0, (2, ))
+        self._act_box = _action_space(self.config)
         self._seat_id = ["agent%d" % k for k in range(self.num_agents)] + [None]
         self._active = set(self._seat_id[:self.num_agents])
         self._sim = None
@@ -406,7 +441,7 @@ class MultiAgentMetaDrive:
             aid = self._seat_id[k]
             if aid in self._active:
                 assert aid in actions, "missing action for " + aid
-                a[k] = np.asarray(actions[aid], np.float32)
+                a[k] = _action_row(self.config, actions[aid])
                 acting[k] = aid
         obs, rew, cost, term, trunc, flags, info_f = self._sim.step_host(a, autoreset=False)
         self.episode_step += 1

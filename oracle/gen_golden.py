@@ -56,7 +56,10 @@ def run_episode(env_cls, config, seed, actions, tag):
         f0, i0 = rx.record_world(env, roster)
         fs, is_, obs, rew, cost, term, trunc, infos = [f0], [i0], [obs0], [], [], [], [], []
         for a in actions:
-            o, r, te, tr, info = env.step(a)
+            if config.get("discrete_action"):  # Discrete: the index travels in column 0; MultiDiscrete: both columns
+                o, r, te, tr, info = env.step([int(a[0]), int(a[1])] if config.get("use_multi_discrete") else int(a[0]))
+            else:
+                o, r, te, tr, info = env.step(a)
             f, i = rx.record_world(env, roster)
             fs.append(f)
             is_.append(i)
@@ -81,7 +84,10 @@ def run_episode(env_cls, config, seed, actions, tag):
                                    n_side_lasers=int(env.config["vehicle_config"]["side_detector"]["num_lasers"]),
                                    side_dist=float(env.config["vehicle_config"]["side_detector"]["distance"]),
                                    n_lane_lasers=int(env.config["vehicle_config"]["lane_line_detector"]["num_lasers"]),
-                                   lane_dist=float(env.config["vehicle_config"]["lane_line_detector"]["distance"]))),
+                                   lane_dist=float(env.config["vehicle_config"]["lane_line_detector"]["distance"]),
+                                   discrete_action=(2 if env.config["use_multi_discrete"] else 1) if env.config["discrete_action"] else 0,
+                                   discrete_steering_dim=int(env.config["discrete_steering_dim"]),
+                                   discrete_throttle_dim=int(env.config["discrete_throttle_dim"]))),
             **{"init_" + k: v for k, v in init.items()},
         )
         sb = rx.export_static_bodies(env.engine)
@@ -356,6 +362,10 @@ def main():
          dict(map=3, traffic_density=0.3, num_scenarios=20, start_seed=0, log_level=50), 11, smooth),
         ("cfg2_SCO_nolimit", MetaDriveEnv, dict(map="SCO", traffic_density=0.2, log_level=50), 0,
          np.stack([np.zeros(args.steps), np.full(args.steps, 0.3)], 1)),
+        # discrete actions (policy/env_input_policy.py:40-48): Discrete(7 x 5) index in column 0
+        ("cfg1_S_discrete", MetaDriveEnv,
+         dict(map="S", traffic_density=0.1, log_level=50, discrete_action=True, discrete_steering_dim=7, discrete_throttle_dim=5),
+         0, np.stack([np.random.RandomState(4).randint(14, 35, args.steps), np.zeros(args.steps)], 1).astype(np.float64)),
         # lidar.num_others = 4 (component/sensors/lidar.py:93-138): the 4 nearest vehicles precede the lidar floats
         ("cfg2_pg3_seed11_others4", MetaDriveEnv,
          dict(map=3, traffic_density=0.3, num_scenarios=20, start_seed=0, log_level=50,

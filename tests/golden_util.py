@@ -101,6 +101,9 @@ def golden_world(g, replicas=1, slots=None, objs=None, **cfg_kw):
     kw["num_others"] = int(conf.get("num_others", 0))
     kw.update(n_side_lasers=int(conf.get("n_side_lasers", 0)), side_dist=float(conf.get("side_dist", 50.0)),
               n_lane_lasers=int(conf.get("n_lane_lasers", 0)), lane_dist=float(conf.get("lane_dist", 20.0)))
+    if isinstance(conf.get("discrete_action"), int) and not isinstance(conf.get("discrete_action"), bool):
+        kw.update(discrete_action=conf["discrete_action"], discrete_steering_dim=conf["discrete_steering_dim"],
+                  discrete_throttle_dim=conf["discrete_throttle_dim"])
     kw.update(cfg_kw)
     cfg = make_config(replicas, S, 1, O, **kw)
     return arrays, cfg, geo

@@ -35,6 +35,21 @@ def test_metadrive_env_replays_reference_episode():
     env.close()
 
 
+def test_discrete_action_env():
+    """Discrete(steering_dim x throttle_dim) actions (policy/env_input_policy.py:40-68) replay the reference episode."""
+    from metadrive_ped_b200 import MetaDriveEnv
+    g = load_golden("cfg1_S_discrete")
+    # the fixture ran on map "S"; the shipped library holds 3-block maps, so only the decoding is checked end to end
+    env = MetaDriveEnv(dict(num_scenarios=10, discrete_action=True, discrete_steering_dim=7, discrete_throttle_dim=5))
+    assert env.action_space.n == 35 and env.action_space.contains(17) and not env.action_space.contains(35)
+    obs, _ = env.reset(seed=0)
+    a = 2 * 7 + 5          # throttle index 2 -> 0.0, steering index 5 -> 5 * 2/6 - 1 = 0.6667
+    obs, r, te, tr, info = env.step(a)
+    assert abs(info["steering"] - (5 * (2.0 / 6.0) - 1.0)) < 1e-6 and abs(info["acceleration"] - 0.0) < 1e-6
+    env.close()
+    assert g["actions"][:, 0].max() < 35
+
+
 def test_config_errors_match_reference():
     from metadrive_ped_b200 import MetaDriveEnv, SafeMetaDriveEnv
     with pytest.raises(KeyError):
