@@ -114,13 +114,13 @@ def run_reference(args, rank):
     """CPU arm: the oracle port of the reference's path on all host threads, bounded sample per step."""
     if rank != 0:
         return
-    from oracle.oracle import OracleSim
+    from oracle.oracle import OracleSim, set_threads
+    cores = set_threads()  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread
     sample = 1024
     lib, arrays, cfg = build_world(sample, 0)
     orc = OracleSim(arrays, cfg)
     orc.reset_observe()
     a = np.tile(np.array([0.0, 1.0], np.float32), (sample, 1))
-    cores = os.cpu_count() or 1
     for _ in range(args.warmup):
         orc.step(a)
         orc.reset_envs(orc.term | orc.trunc)
@@ -327,7 +327,8 @@ def main():
 
 def cpu_baseline(lib, peds=0):
     """The oracle port on the box's host cores over a bounded sample (about 10-20 s of CPU work)."""
-    from oracle.oracle import OracleSim
+    from oracle.oracle import OracleSim, set_threads
+    cores = set_threads()
     sample = 512
     arrays, cfg = lib.build_world([i % len(lib) for i in range(sample)], num_pedestrians=peds)
     orc = OracleSim(arrays, cfg)
@@ -344,7 +345,7 @@ def cpu_baseline(lib, peds=0):
         if done.any():
             orc.reset_envs(done)
     dt = time.perf_counter() - t0
-    return {"value": sample * steps / dt, "unit": "agent-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+    return {"value": sample * steps / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
             "sample": "%d envs x %d steps of the same workload, OpenMP over envs" % (sample, steps)}
 
 

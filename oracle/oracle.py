@@ -34,6 +34,11 @@ def lib():
     return _lib
 
 
+def set_threads(n=None):
+    """Use `n` (default: all) host threads for the OpenMP loop over envs; returns the thread count in effect."""
+    return int(lib().mdo_set_threads(int(n or os.cpu_count() or 1)))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
