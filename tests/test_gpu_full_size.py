@@ -1,0 +1,150 @@
+"""-m gpu: the BASELINE.json configurations at their FULL per-GPU sizes (bench.py's worlds), every env with its own
+random action sequence, fused on-device auto-reset on.
+
+1. CUDA step vs the CPU oracle, env by env: integer state (lanes, checkpoints, flags, rosters, seat bookkeeping),
+   done flags and info flags bit-exact; poses / rewards / observations within the north-star tolerances.  The two
+   paths are float32 with different libm (CUDA vs glibc sinf / cosf / atan2f), so over ~10^6 vehicle-steps a
+   knife-edge decision may flip in a handful of envs; such an env is counted, dropped from the comparison from then
+   on, and the count is bounded (<= 0.1 % of the envs).
+2. Size-independent properties: shuffling the envs of the batch shuffles the outputs bit for bit (no cross-env
+   leakage through the CTA-level staging, work lists or candidate sets), and two runs are bit-identical (determinism).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MUTABLE = ("env_i", "veh_s", "veh_c", "veh_i", "veh_idm", "veh_navi", "obj_f", "veh_route", "veh_rroad")
+
+
+def _world(workload, n_envs=None):
+    import bench
+    n = n_envs or bench.WORKLOADS[workload]["envs"]
+    _, arrays, cfg = bench.build_world(n, 0, workload)
+    return arrays, cfg
+
+
+def _actions(rng, cfg, multi):
+    """Every agent its own action sequence: throttle mostly forward, steering = a per-agent bias + noise, so that within
+    a few dozen steps agents leave the road, hit traffic / cones / pedestrians, and (multi-agent) arrive and respawn."""
+    n = cfg.n_envs * cfg.agents_per_env
+    bias = np.random.RandomState(11).uniform(-0.25, 0.25, n)
+    a = rng.uniform(-1.0, 1.0, (n, 2)).astype(np.float32)
+    a[:, 0] = (0.3 * a[:, 0] + bias).astype(np.float32)
+    a[:, 1] = np.where(a[:, 1] > -0.8, np.abs(a[:, 1]), a[:, 1])
+    return a
+
+
+@pytest.mark.parametrize("workload,steps", [("cfg2", 60), ("cfg4", 40), ("cfg5", 40), ("cfg3", 25)])
+def test_full_size_step_matches_oracle(workload, steps, oracle_lib):
+    import torch
+    from metadrive_ped_b200.sim import BatchedSim
+    from oracle.oracle import OracleSim, set_threads
+    set_threads()
+    multi = workload == "cfg3"
+    arrays, cfg = _world(workload)
+    E, S, NA, O = cfg.n_envs, cfg.slots_per_env, cfg.agents_per_env, cfg.objs_per_env
+    sim, orc = BatchedSim(arrays, cfg), OracleSim(arrays, cfg)
+    obs0_g = sim.reset().cpu().numpy().copy()
+    obs0_o = orc.reset_observe().copy()
+    live = orc.a["veh_i"].reshape(E, S, -1)[:, :NA, 2].reshape(-1) != 0
+    np.testing.assert_allclose(obs0_g[live], obs0_o[live], atol=1e-5, rtol=0)
+    # the state a finished env returns to (the product restores the same rows from its post-reset snapshot)
+    post = {k: orc.a[k].copy() for k in MUTABLE}
+    rows = {"env_i": 1, "obj_f": O}
+    ok = np.ones(E, bool)  # envs still in lock-step
+    rng = np.random.RandomState(7)
+    n_done = n_rays = n_bad_rays = 0
+    for t in range(steps):
+        a = _actions(rng, cfg, multi)
+        sim.step(torch.from_numpy(a).cuda(), autoreset=not multi)
+        orc.step(a)
+        done = (orc.term | orc.trunc).astype(bool)
+        fl_g, fl_o = sim.info_flags.cpu().numpy(), orc.info_flags
+        te_g, tr_g = sim.terminated.cpu().numpy(), sim.truncated.cpu().numpy()
+        og, rg = sim.obs.cpu().numpy(), sim.reward.cpu().numpy()
+        oo = orc.obs.copy()
+        if not multi and done.any():  # env.reset of the finished envs on the oracle side
+            n_done += int(done.sum())
+            for e in np.nonzero(done)[0]:
+                for k in MUTABLE:
+                    r = rows.get(k, S)
+                    if r:
+                        orc.a[k][e * r:(e + 1) * r] = post[k][e * r:(e + 1) * r]
+                oo[e] = obs0_o[e]
+        vi_g = sim.get_state("veh_i").reshape(E, -1)
+        same = (vi_g == orc.a["veh_i"].reshape(E, -1)).all(1)
+        same &= (sim.get_state("env_i").reshape(E, -1) == orc.a["env_i"].reshape(E, -1)).all(1)
+        per_env = lambda x: x.reshape(E, -1)
+        same &= (per_env(fl_g) == per_env(fl_o)).all(1) & (per_env(te_g) == per_env(orc.term)).all(1)
+        same &= (per_env(tr_g) == per_env(orc.trunc)).all(1)
+        ok &= same
+        assert (~ok).sum() <= max(1, E // 1000), "%d of %d envs left lock-step by step %d" % ((~ok).sum(), E, t)
+        m_env = ok
+        m_veh = np.repeat(m_env, S)
+        m_ag = np.repeat(m_env, NA)
+        vs_g, vs_o = sim.get_state("veh_s"), orc.a["veh_s"]
+        np.testing.assert_allclose(vs_g[m_veh, 0:3], vs_o[m_veh, 0:3], atol=1e-2, rtol=0)
+        np.testing.assert_allclose(vs_g[m_veh, 3:7], vs_o[m_veh, 3:7], atol=1e-3, rtol=0)
+        np.testing.assert_allclose(rg[m_ag], orc.reward[m_ag], atol=1e-3, rtol=0)
+        valid = m_ag & (((fl_o & 0x2000) != 0) if multi else True)
+        sd = sim.state_dim + 4 * cfg.num_others
+        np.testing.assert_allclose(og[valid][:, :sd], oo[valid][:, :sd], atol=1e-3, rtol=0)
+        bad = ~np.isclose(og[valid][:, sd:], oo[valid][:, sd:], atol=2e-4, rtol=1e-4)
+        n_rays += bad.size
+        n_bad_rays += int(bad.sum())
+        assert bad.sum(1).max(initial=0) <= 2, "more than two glancing rays in one observation at step %d" % t
+    assert n_bad_rays <= 1e-4 * n_rays, (n_bad_rays, n_rays)
+    if not multi:
+        assert n_done > 0, "the run must exercise the fused auto-reset"
+    print("%s: %d envs x %d steps, %d envs left lock-step, %d resets, %d / %d glancing rays"
+          % (workload, E, steps, (~ok).sum(), n_done, n_bad_rays, n_rays))
+    sim.close()
+
+
+@pytest.mark.parametrize("workload,steps", [("cfg2", 40), ("cfg5", 30), ("cfg3", 20)])
+def test_full_size_env_permutation_and_determinism(workload, steps):
+    """Envs never interact: the batch shuffled gives the outputs shuffled, bit for bit; a second run repeats the first."""
+    import torch
+    from metadrive_ped_b200.sim import BatchedSim
+    multi = workload == "cfg3"
+    arrays, cfg = _world(workload)
+    E, NA = cfg.n_envs, cfg.agents_per_env
+    rng = np.random.RandomState(3)
+    perm = rng.permutation(E)
+    shuffled = {}
+    per_env_rows = {}
+    for k, v in arrays.items():
+        v = np.asarray(v)
+        if k.startswith(("env_", "veh_", "obj_", "ma_")) and v.shape[0] % E == 0 and v.shape[0] > 0:
+            r = v.shape[0] // E
+            per_env_rows[k] = r
+            shuffled[k] = np.ascontiguousarray(v.reshape((E, r) + v.shape[1:])[perm].reshape(v.shape))
+        else:
+            shuffled[k] = v
+    assert {"env_i", "veh_s", "veh_i", "veh_p"} <= set(per_env_rows)
+    acts = [_actions(rng, cfg, multi) for _ in range(steps)]
+
+    def run(arr, order):
+        sim = BatchedSim(arr, cfg)
+        out = [sim.reset().cpu().numpy().copy()]
+        for a in acts:
+            a = a.reshape(E, NA, 2)[order].reshape(-1, 2)
+            sim.step(torch.from_numpy(np.ascontiguousarray(a)).cuda(), autoreset=not multi)
+            out.append((sim.obs.cpu().numpy().copy(), sim.reward.cpu().numpy().copy(), sim.terminated.cpu().numpy().copy(),
+                        sim.truncated.cpu().numpy().copy(), sim.info_flags.cpu().numpy().copy()))
+        vi = sim.get_state("veh_i").copy()
+        sim.close()
+        return out, vi
+
+    ident = np.arange(E)
+    base, vi_a = run(arrays, ident)
+    again, vi_b = run(arrays, ident)
+    shuf, vi_c = run(shuffled, perm)
+    np.testing.assert_array_equal(vi_a, vi_b)
+    np.testing.assert_array_equal(vi_a.reshape(E, -1)[perm], vi_c.reshape(E, -1))
+    np.testing.assert_array_equal(base[0].reshape(E, -1)[perm], shuf[0].reshape(E, -1))
+    for t in range(1, steps + 1):
+        for x, y, z in zip(base[t], again[t], shuf[t]):
+            np.testing.assert_array_equal(x, y, err_msg="run-to-run difference at step %d" % t)
+            np.testing.assert_array_equal(x.reshape(E, -1)[perm], z.reshape(E, -1), err_msg="env leakage at step %d" % t)
