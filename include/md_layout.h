@@ -234,6 +234,11 @@ typedef struct MdConfig {
     /* EnvInputPolicy.convert_to_continuous_action (policy/env_input_policy.py:40-48): 0 = continuous [steer, throttle];
      * 1 = Discrete(steering_dim * throttle_dim), the index travels in actions[:, 0]; 2 = MultiDiscrete([sd, td]) */
     int discrete_action, discrete_steering_dim, discrete_throttle_dim;
+    /* LidarStateObservation._add_noise_to_cloud_points (obs/state_obs.py:236-244): clip(x + N(0, sigma), 0, 1), then a
+     * ray is zeroed with probability dropout_prob.  The reference draws from numpy's unseeded global generator; here the
+     * draws are a counter hash of (noise_seed, observation pass, agent, ray). */
+    float lidar_gaussian_noise, lidar_dropout_prob;
+    int noise_seed;
 } MdConfig;
 
 /* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */

@@ -25,7 +25,7 @@ extern "C" {
 
 typedef struct md_sim md_sim;
 
-#define MD_ABI_VERSION 2
+#define MD_ABI_VERSION 3
 int md_abi_version(void);
 
 /* engine construction: replaces initialize_engine / BaseEngine.__init__ + PhysicsWorld

@@ -255,6 +255,111 @@ __device__ __forceinline__ Rect vehicle_rect(const float* __restrict__ P, const 
     r.hv = 0.5f * P[VP_WIDTH];
     return r;
 }
+// ------------------------------------------------------------------------------------------------ contact response
+// The dynamic-world part of BulletWorld.doPhysics (engine/core/engine_core.py:350-352) that pushes bodies apart.  Bullet's
+// sequential-impulse solver over GJK/EPA manifolds is not restated: this is the simple impulse model SURVEY.md 7.3 #2
+// allows (DESIGN.md "Contact response"): planar contacts between chassis footprints and static obstacles, one Jacobi pass
+// per sub-step from a snapshot of the post-move state, frictionless inelastic normal impulse + a position push-out of
+// ERP x (depth - slop) split by inverse mass.  Every product and sum is written in one fixed order (the CPU checker in the test tree follows the same).
+#define CONTACT_ERP 0.2f
+#define CONTACT_SLOP 0.01f
+#define CORNER_EPS 1e-4f
+#define CONTACT_TIE 1e-6f
+#define AXIS_MARGIN 1e-3f
+struct __align__(16) CBody { float ox, oy, vx, vy, w, im, ii, pad; };   // origin, planar velocity, yaw rate, 1/m, 1/Izz
+
+__device__ __forceinline__ void corners_inside(const Rect& in, const Rect& box, int& cnt, float& sx, float& sy) {
+    const float vx = -in.uy, vy = in.ux;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float su = (k == 0 || k == 3) ? 1.0f : -1.0f, sv = k < 2 ? 1.0f : -1.0f;
+        const float px = in.cx + in.ux * (su * in.hu) + vx * (sv * in.hv);
+        const float py = in.cy + in.uy * (su * in.hu) + vy * (sv * in.hv);
+        const float dx = px - box.cx, dy = py - box.cy;
+        if (fabsf(dx * box.ux + dy * box.uy) <= box.hu + CORNER_EPS &&
+            fabsf(-dx * box.uy + dy * box.ux) <= box.hv + CORNER_EPS) {
+            cnt += 1; sx += px; sy += py;
+        }
+    }
+}
+// normal (A -> B), depth and contact point of two overlapping rectangles; false when they do not overlap (rect_rect's verdict)
+__device__ __forceinline__ bool rr_contact(const Rect& a, const Rect& b, float& nx, float& ny, float& depth, float& px, float& py) {
+    const float dx = b.cx - a.cx, dy = b.cy - a.cy;
+    const float c = a.ux * b.ux + a.uy * b.uy;
+    const float s = a.ux * b.uy - a.uy * b.ux;
+    const float ac = fabsf(c), as = fabsf(s);
+    const float s0 = dx * a.ux + dy * a.uy, ov0 = a.hu + (b.hu * ac + b.hv * as) - fabsf(s0);
+    const float s1 = -dx * a.uy + dy * a.ux, ov1 = a.hv + (b.hu * as + b.hv * ac) - fabsf(s1);
+    const float s2 = dx * b.ux + dy * b.uy, ov2 = b.hu + (a.hu * ac + a.hv * as) - fabsf(s2);
+    const float s3 = -dx * b.uy + dy * b.ux, ov3 = b.hv + (a.hu * as + a.hv * ac) - fabsf(s3);
+    if (ov0 < 0.0f || ov1 < 0.0f || ov2 < 0.0f || ov3 < 0.0f) return false;
+    // minimum-translation axis; B's axes win only by a clear margin: two nearly parallel boxes overlap by almost the same
+    // amount along A's and B's axis and the pick would otherwise flip on rounding noise
+    float best = ov0, ax = a.ux, ay = a.uy, sg = s0;
+    if (ov1 < best) { best = ov1; ax = -a.uy; ay = a.ux; sg = s1; }
+    float bb = ov2, bx = b.ux, by = b.uy, bs = s2;
+    if (ov3 < bb) { bb = ov3; bx = -b.uy; by = b.ux; bs = s3; }
+    if (bb < best - AXIS_MARGIN) { best = bb; ax = bx; ay = by; sg = bs; }
+    if (sg > -CONTACT_TIE) { nx = ax; ny = ay; } else { nx = -ax; ny = -ay; }  // centres level: "+axis" by convention
+    depth = best;
+    int cnt = 0; float sx = 0.0f, sy = 0.0f;
+    corners_inside(b, a, cnt, sx, sy);
+    corners_inside(a, b, cnt, sx, sy);
+    if (cnt > 0) { px = sx / (float)cnt; py = sy / (float)cnt; }
+    else { px = 0.5f * (a.cx + b.cx); py = 0.5f * (a.cy + b.cy); }
+    return true;
+}
+// rectangle A against a circle: normal A -> circle (rect_circle's verdict)
+__device__ __forceinline__ bool rc_contact(const Rect& a, float cx, float cy, float r, float& nx, float& ny, float& depth,
+                                           float& px, float& py) {
+    const float dx = cx - a.cx, dy = cy - a.cy;
+    const float vx = -a.uy, vy = a.ux;
+    const float lx = dx * a.ux + dy * a.uy;
+    const float ly = -dx * a.uy + dy * a.ux;
+    const float qx = clipf(lx, -a.hu, a.hu), qy = clipf(ly, -a.hv, a.hv);
+    const float ex = lx - qx, ey = ly - qy;
+    const float d2 = ex * ex + ey * ey;
+    if (!(d2 <= r * r)) return false;
+    if (d2 > 1e-12f) {
+        const float dist = sqrtf(d2);
+        const float e0 = ex / dist, e1 = ey / dist;
+        nx = a.ux * e0 + vx * e1; ny = a.uy * e0 + vy * e1;
+        depth = r - dist;
+        px = a.cx + a.ux * qx + vx * qy; py = a.cy + a.uy * qx + vy * qy;
+        return true;
+    }
+    const float fx = a.hu - fabsf(lx), fy = a.hv - fabsf(ly);
+    if (fx < fy) {
+        const float sg = lx >= 0.0f ? 1.0f : -1.0f;
+        nx = a.ux * sg; ny = a.uy * sg; depth = fx + r;
+        px = a.cx + a.ux * (sg * a.hu) + vx * ly; py = a.cy + a.uy * (sg * a.hu) + vy * ly;
+    } else {
+        const float sg = ly >= 0.0f ? 1.0f : -1.0f;
+        nx = vx * sg; ny = vy * sg; depth = fy + r;
+        px = a.cx + a.ux * lx + vx * (sg * a.hv); py = a.cy + a.uy * lx + vy * (sg * a.hv);
+    }
+    return true;
+}
+// one pair's contribution to body `me` (A when !me_is_b): d = dvx dvy dw dpx dpy
+__device__ __forceinline__ void pair_impulse(const CBody& A, const CBody& B, float nx, float ny, float depth, float px, float py,
+                                             bool me_is_b, float* d) {
+    const float rax = px - A.ox, ray = py - A.oy, rbx = px - B.ox, rby = py - B.oy;
+    const float vpax = A.vx + A.w * (-ray), vpay = A.vy + A.w * rax;
+    const float vpbx = B.vx + B.w * (-rby), vpby = B.vy + B.w * rbx;
+    const float vn = (vpbx - vpax) * nx + (vpby - vpay) * ny;
+    const float can = rax * ny - ray * nx, cbn = rbx * ny - rby * nx;
+    const float K = A.im + B.im + can * can * A.ii + cbn * cbn * B.ii;
+    const float J = vn < 0.0f ? -vn / K : 0.0f;
+    const float push = CONTACT_ERP * fmaxf(depth - CONTACT_SLOP, 0.0f) / (A.im + B.im);
+    const float sgn = me_is_b ? 1.0f : -1.0f, cn = me_is_b ? cbn : can;
+    const float mim = me_is_b ? B.im : A.im, mii = me_is_b ? B.ii : A.ii;
+    const float sj = sgn * J * mim;
+    d[0] += nx * sj; d[1] += ny * sj;
+    d[2] += sgn * J * cn * mii;
+    const float sp = sgn * push * mim;
+    d[3] += nx * sp; d[4] += ny * sp;
+}
+
 // TrafficBarrier: BulletBoxShape((WIDTH/2, LENGTH/2, h/2)) (static_object/traffic_object.py:143)
 __device__ __forceinline__ Rect object_rect(const float* O) {
     Rect r;

@@ -518,6 +518,7 @@ __device__ __forceinline__ int dynamic_contacts(const Nb* nb, float* obj, int S,
     return flags;
 }
 
+#define FL_TOUCH 0x40000000  // contact_pass only, never stored: a vehicle or solid obstacle overlaps (-> contact response)
 // the same contact rules over a candidate bit set (k_dyn's per-step broad phase): bit k < S = vehicle slot k, else object k - S
 __device__ __forceinline__ int contact_pass(const Nb* nb, float* obj, int S, int slot, const Rect& r, unsigned long long lo,
                                             unsigned long long hi, int* obj_first, bool claim_pass, bool objects_only) {
@@ -526,7 +527,7 @@ __device__ __forceinline__ int contact_pass(const Nb* nb, float* obj, int S, int
         for (unsigned long long mk = half ? hi : lo; mk; mk &= mk - 1) {
             const int k = __ffsll((long long)mk) - 1 + 64 * half;
             if (k < S) {
-                if (!objects_only && rect_rect(r, nb[k].r)) flags |= FL_CRASH_VEHICLE;
+                if (!objects_only && rect_rect(r, nb[k].r)) flags |= FL_CRASH_VEHICLE | FL_TOUCH;
                 continue;
             }
             const int ko = k - S;
@@ -535,8 +536,9 @@ __device__ __forceinline__ int contact_pass(const Nb* nb, float* obj, int S, int
             if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
             else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
             if (!hit) continue;
-            if (Ob[OB_KIND] == 3.0f) flags |= FL_CRASH_HUMAN;
-            else if (Ob[OB_CRASHED] == 0.0f) {
+            if (Ob[OB_KIND] == 3.0f) { flags |= FL_CRASH_HUMAN; continue; }
+            flags |= FL_TOUCH;   // a solid obstacle overlaps, whether or not its COST_ONCE flag is still to be had
+            if (Ob[OB_CRASHED] == 0.0f) {
                 if (claim_pass) atomicMin(&obj_first[ko], slot);          // COST_ONCE: lowest slot takes the flag
                 else if (obj_first[ko] == slot) flags |= FL_CRASH_OBJECT;
             }
@@ -881,6 +883,42 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
 }
 
 // ---- k_dyn: engine.step = n_sub x doPhysics + contact-added callback (engine/base_engine.py:417-445) --------------
+#ifndef MD_RESP_INL
+#define MD_RESP_INL __forceinline__   // out of line (__noinline__) triples the spills of the sub-step loop around the call
+#endif
+// Contact response of vehicle `slot` over its candidate set (bit k < S = vehicle slot k, else object k - S), from the
+// snapshot every vehicle of the env published after moving (nb[].r footprints, cd[] origin / velocity / inverse mass).
+// The pair (i, k) is evaluated with A = the lower slot on both sides, so the two threads compute the same impulse.
+__device__ MD_RESP_INL void contact_response(const Nb* nb, const CBody* cd, const float* obj, int S, int slot,
+                                              unsigned long long lo, unsigned long long hi, float* d) {
+    d[0] = d[1] = d[2] = d[3] = d[4] = 0.0f;
+    const CBody me = cd[slot];
+    const Rect mr = nb[slot].r;
+    for (int half = 0; half < 2; half++) {
+        for (unsigned long long mk = half ? hi : lo; mk; mk &= mk - 1) {
+            const int k = __ffsll((long long)mk) - 1 + 64 * half;
+            float nx, ny, depth, px, py;
+            if (k < S) {
+                const bool me_is_b = k < slot;
+                const Rect& ra = me_is_b ? nb[k].r : mr;
+                const Rect& rb = me_is_b ? mr : nb[k].r;
+                if (!rr_contact(ra, rb, nx, ny, depth, px, py)) continue;
+                if (me_is_b) pair_impulse(cd[k], me, nx, ny, depth, px, py, true, d);
+                else pair_impulse(me, cd[k], nx, ny, depth, px, py, false, d);
+                continue;
+            }
+            const float* Ob = obj + (k - S) * OBJ_F;
+            if (Ob[OB_KIND] == 3.0f) continue;  // pedestrians neither push nor are pushed
+            CBody ob;
+            ob.ox = Ob[OB_X]; ob.oy = Ob[OB_Y]; ob.vx = 0.0f; ob.vy = 0.0f; ob.w = 0.0f; ob.im = 0.0f; ob.ii = 0.0f;
+            bool hit;
+            if (Ob[OB_KIND] == 2.0f) { const Rect ro = object_rect(Ob); hit = rr_contact(mr, ro, nx, ny, depth, px, py); }
+            else hit = rc_contact(mr, Ob[OB_X], Ob[OB_Y], Ob[OB_A], nx, ny, depth, px, py);
+            if (hit) pair_impulse(me, ob, nx, ny, depth, px, py, false, d);
+        }
+    }
+}
+
 __global__ void __maxnreg__(DYN_REGS)
 k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ veh_act, const float* __restrict__ ext_act3,
       int n_sub) {
@@ -890,7 +928,8 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     // that integrate are dense (a third to a half of the slot rows of a PG scene are empty or not alive).
     const StepGeom H = step_geom(cfg, epb, smem_raw);
     const int S = H.S, O = H.O;
-    int* list = reinterpret_cast<int*>(smem_raw + step_smem_bytes(S, O, epb));
+    CBody* cd_all = reinterpret_cast<CBody*>(smem_raw + step_smem_bytes(S, O, epb));
+    int* list = reinterpret_cast<int*>(smem_raw + step_smem_bytes(S, O, epb) + sizeof(CBody) * (size_t)epb * S);
     int* n_list = list + epb * S;
     if (threadIdx.x == 0) *n_list = 0;
     __syncthreads();
@@ -911,6 +950,7 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
         G.obj_first = H.obj_first + ((ptrdiff_t)G.le - H.le) * ((O + 3) & ~3);
     }
     const int slot = G.slot, g = G.g;
+    CBody* cd = cd_all + (size_t)G.le * S;
     float P[VEH_P], St[VEH_S];
     int alive = 0, is_static = 1, flags = 0;
     Actuation act;
@@ -937,8 +977,10 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     const bool moves = G.work && alive && !is_static;
     // Contact candidates of this step (the broad phase): bit k of (cand_lo, cand_hi) = body k (vehicle slot k < S, object
     // k - S) can come within touching distance during the n_sub sub-steps: centre distance at the start of the step <=
-    // the two bounding radii + 1.5 x the distance both can travel + 0.5 m.  Every truly overlapping pair is a candidate
-    // (accelerations change a speed by < 1 m/s within a step), so the exact SAT below sees the same pairs as a full scan.
+    // the two bounding radii + 1.5 x the distance both can travel + 0.5 m.  "Can travel" uses the speed of the env's
+    // fastest body for both sides: an inelastic contact impulse hands a hit body at most the speed of the one that hit
+    // it.  Every truly overlapping pair is a candidate (accelerations change a speed by < 1 m/s within a step), so the
+    // exact SAT below sees the same pairs as a full scan.
     unsigned long long cand_lo = 0ull, cand_hi = 0ull;
     int block_any = 0, block_obj = 0;
     if (contacts) {
@@ -953,11 +995,21 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
         if (G.work && alive) {
             const float T = 1.5f * cfg.dt * (float)n_sub;
             const Rect r0 = G.nb[slot].r;
+            float vmax = 0.0f;
+#ifndef MD_CAND_OWN_SPEED
+            for (int k = 0; k < S; k++) if (G.nb[k].alive) vmax = fmaxf(vmax, G.nb[k].vy);
+            const float my_rad = G.nb[slot].vx + 0.5f, my_speed = vmax;
+#else
             const float my_rad = G.nb[slot].vx + 0.5f, my_speed = G.nb[slot].vy;
+#endif
             for (int k = 0; k < S; k++) {
                 if (k == slot || !G.nb[k].alive) continue;
                 const float dx = G.nb[k].r.cx - r0.cx, dy = G.nb[k].r.cy - r0.cy;
+#ifndef MD_CAND_OWN_SPEED
+                const float reach = my_rad + G.nb[k].vx + (my_speed + vmax) * T;
+#else
                 const float reach = my_rad + G.nb[k].vx + (my_speed + G.nb[k].vy) * T;
+#endif
                 if (dx * dx + dy * dy <= reach * reach) { if (k < 64) cand_lo |= 1ull << k; else cand_hi |= 1ull << (k - 64); }
             }
             for (int k = 0; k < O; k++) {
@@ -987,7 +1039,14 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
         }
         if (contacts && block_any) {  // a CTA without candidate pairs has no contact this step: no exchange, no barriers
             __syncthreads();  // everyone finished reading the previous footprints
-            if (G.work) G.nb[slot].r = vehicle_rect(P, St);
+            if (G.work) {  // snapshot of the post-move state: the contact flags and the response both read it
+                G.nb[slot].r = vehicle_rect(P, St);
+                CBody c;
+                c.ox = B.pos.x; c.oy = B.pos.y; c.vx = B.v.x; c.vy = B.v.y; c.w = B.w.z; c.pad = 0.0f;
+                c.im = moves ? 1.0f / P[VP_MASS] : 0.0f;
+                c.ii = moves ? 1.0f / (P[VP_MASS] / 12.0f * (P[VP_WIDTH] * P[VP_WIDTH] + P[VP_LENGTH] * P[VP_LENGTH])) : 0.0f;
+                cd[slot] = c;
+            }
             if (H.work)
                 for (int k = H.slot; k < O; k += S) {  // kinematic movers (traffic_participants/pedestrian.py:67-95)
                     H.obj_first[k] = 0x7fffffff;
@@ -995,10 +1054,23 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
                     if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
                 }
             __syncthreads();
-            if (cand_lo | cand_hi) flags |= contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, true, false);
+            if (cand_lo | cand_hi) {
+                const int f = contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, true, false);
+                flags |= f & ~FL_TOUCH;
+#ifndef MD_NO_RESPONSE
+                if (moves && (f & FL_TOUCH)) {  // something overlaps: push apart (registers only;
+                    float d[5];                                           // the snapshot stays as it is for the others)
+                    contact_response(G.nb, cd, G.sobj, S, slot, cand_lo, cand_hi, d);
+                    B.v.x += d[0]; B.v.y += d[1]; B.w.z += d[2];
+                    B.pos.x += d[3]; B.pos.y += d[4];
+                    St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y;
+                }
+#endif
+            }
             if (block_obj) {  // COST_ONCE needs the claims of every vehicle before anyone reads them
                 __syncthreads();
-                if (cand_lo | cand_hi) flags |= contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, false, true);
+                if (cand_lo | cand_hi)
+                    flags |= contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, false, true) & ~FL_TOUCH;
                 __syncthreads();
                 if (H.work)
                     for (int k = H.slot; k < O; k += S)
@@ -1365,10 +1437,30 @@ __host__ __device__ inline size_t lidar_smem_per_warp(int S, int O) {
 // Lidar.perceive (component/sensors/lidar.py:49-73 -> sensors/distance_detector.py:27-85), one warp per agent.
 // The reference's angular mask (lidar.py:140-168) only skips rays that provably miss; here every ray is cast and a
 // conservative bounding-circle test prunes the (ray, body) pairs instead.
+// LidarStateObservation._add_noise_to_cloud_points (obs/state_obs.py:236-244) for one ray: Gaussian noise, clip to [0, 1],
+// then dropout to 0.  Uniforms come from a counter hash of (seed, observation pass, agent, ray); Box-Muller for the normal.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ float lidar_noise(const MdConfig& cfg, float frac, uint32_t agent, uint32_t ray, uint32_t pass) {
+    const uint32_t key = mix32((uint32_t)cfg.noise_seed * 0x9E3779B9u + pass) ^ mix32(agent * 0x85EBCA6Bu + ray * 0xC2B2AE35u + 0x27D4EB2Fu);
+    if (cfg.lidar_gaussian_noise > 0.0f) {
+        const float u1 = ((float)(mix32(key + 1u) >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
+        const float u2 = (float)(mix32(key + 2u) >> 8) * (1.0f / 16777216.0f);           // [0, 1)
+        const float z = sqrtf(-2.0f * logf(u1)) * cosf(MD_TWO_PI * u2);
+        frac = clipf(frac + cfg.lidar_gaussian_noise * z, 0.0f, 1.0f);
+    }
+    if (cfg.lidar_dropout_prob > 0.0f) {
+        const float u3 = (float)(mix32(key + 3u) >> 8) * (1.0f / 16777216.0f);
+        if (u3 < cfg.lidar_dropout_prob) frac = 0.0f;
+    }
+    return frac;
+}
 __global__ void __launch_bounds__(LIDAR_WARPS * 32)
 k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restrict__ obj_f, const int* __restrict__ veh_i,
         const float* __restrict__ veh_p, float* __restrict__ out, int out_stride, int out_off, int* __restrict__ hit_out, const uint8_t* __restrict__ env_mask,
-        const int* __restrict__ agent_flags, int need_flag, const float* __restrict__ ray_cs) {
+        const int* __restrict__ agent_flags, int need_flag, const float* __restrict__ ray_cs, uint32_t noise_pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env, N = cfg.n_lasers;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1389,6 +1481,8 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     // finished this step still gets its last observation) or, in the respawn pass, the newborn seats (FL_NEWBORN)
     if (agent_flags != nullptr) { if (!(agent_flags[a] & need_flag)) return; }
     else if (!veh_i[(size_t)(env * S + slot) * VEH_I + VI_ACTIVE]) return;
+    // sensor noise belongs to the observation (obs/state_obs.py:225-229), not to Lidar.perceive: md_lidar (out_off < 0) is clean
+    const bool noisy = out_off >= 0 && (cfg.lidar_gaussian_noise > 0.0f || cfg.lidar_dropout_prob > 0.0f);
 
     // stage the env's body rows and object rows: one bulk async copy (TMA 1-D) each, completing on the warp's mbarrier
     if (lane == 0) {
@@ -1543,7 +1637,9 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
             }
             if (t < best) { best = t; hit = k; }
         }
-        orow[i] = best <= 1.0f ? best : 1.0f;
+        float frac = best <= 1.0f ? best : 1.0f;
+        if (noisy) frac = lidar_noise(cfg, frac, (uint32_t)a, (uint32_t)i, noise_pass);
+        orow[i] = frac;
         if (hrow) hrow[i] = best <= 1.0f ? hit : -1;
     }
 }
@@ -1788,6 +1884,7 @@ struct md_sim {
     uint8_t *d_term, *d_trunc, *d_mask_in;
     int32_t* d_info_flags;
     int64_t launches;
+    uint32_t noise_pass;   // observation passes so far: the counter of the lidar noise hash
     bool loaded;
     // optional per-kernel timing: 3 events per md_step on the launch stream (bench.py's roofline leg)
     std::vector<cudaEvent_t> prof_ev;
@@ -1833,6 +1930,7 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     sim->ray_tab = nullptr;
     sim->post_valid = false;
     sim->launches = 0;
+    sim->noise_pass = 0;
     sim->prof_cap = 0;
     sim->prof_n = 0;
     memset(&sim->dev, 0, sizeof(sim->dev));
@@ -2010,7 +2108,7 @@ static int epb_post() { static int v = env_int("MD_EPB_POST", POST_EPB); return 
 static int epb_dyn() { static int v = env_int("MD_EPB_DYN", DYN_EPB); return v; }
 static StepLaunch dyn_launch(const MdConfig& c) {  // k_dyn appends the compacted list of alive vehicles to the shared tables
     StepLaunch L = step_launch(c, epb_dyn());
-    L.smem += sizeof(int) * ((size_t)L.epb * c.slots_per_env + 4);
+    L.smem += sizeof(CBody) * (size_t)L.epb * c.slots_per_env + sizeof(int) * ((size_t)L.epb * c.slots_per_env + 4);
     return L;
 }
 static StepLaunch pre_launch(const MdConfig& c) {  // k_pre: epb envs per CTA, a fixed number of worker threads
@@ -2090,7 +2188,7 @@ static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* h
     int blocks = (int)((na + LIDAR_WARPS - 1) / LIDAR_WARPS);
     size_t smem = lidar_smem_per_warp(c.slots_per_env, c.objs_per_env) * LIDAR_WARPS;
     k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, sim->dev.veh_p, out, stride, off, hit, mask,
-                                                    agent_flags, need_flag, sim->ray_tab);
+                                                    agent_flags, need_flag, sim->ray_tab, sim->noise_pass++);
     sim->launches++;
     CK(cudaGetLastError());
     if (off >= 0 && (c.n_side_lasers > 0 || c.n_lane_lasers > 0)) {  // the detector blocks of the same observation rows

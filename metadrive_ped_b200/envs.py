@@ -186,8 +186,9 @@ class MetaDriveEnv:
             if self.config[k]:
                 raise NotImplementedError("config['%s'] is outside the step path this build covers" % k)
         lid = self.config["vehicle_config"]["lidar"]
-        if lid["gaussian_noise"] != 0 or lid["dropout_prob"] != 0 or lid["add_others_navi"]:
-            raise NotImplementedError("lidar noise / add_others_navi are not covered yet")
+        assert 0.0 <= lid["dropout_prob"] <= 1.0  # obs/state_obs.py:240
+        if lid["add_others_navi"]:
+            raise NotImplementedError("lidar add_others_navi is not covered yet")
         self.start_seed = self.start_index = self.config["start_seed"]
         self.num_scenarios = self.env_num = self.config["num_scenarios"]
         self._lib = None
@@ -224,6 +225,9 @@ class MetaDriveEnv:
         return dict(
             n_lasers=c["vehicle_config"]["lidar"]["num_lasers"], lidar_dist=float(c["vehicle_config"]["lidar"]["distance"]),
             num_others=int(c["vehicle_config"]["lidar"]["num_others"]),
+            lidar_gaussian_noise=float(c["vehicle_config"]["lidar"]["gaussian_noise"]),
+            lidar_dropout_prob=float(c["vehicle_config"]["lidar"]["dropout_prob"]),
+            noise_seed=int(c.get("start_seed", 0) or 0),
             n_side_lasers=int(c["vehicle_config"]["side_detector"]["num_lasers"]),
             side_dist=float(c["vehicle_config"]["side_detector"]["distance"]),
             n_lane_lasers=int(c["vehicle_config"]["lane_line_detector"]["num_lasers"]),
@@ -387,8 +391,9 @@ class MultiAgentMetaDrive:
         if self.config["traffic_density"] != 0.0:
             raise NotImplementedError("multi-agent envs with IDM traffic are not covered")
         lid = self.config["vehicle_config"]["lidar"]
-        if lid["gaussian_noise"] != 0 or lid["dropout_prob"] != 0 or lid["add_others_navi"]:
-            raise NotImplementedError("lidar noise / add_others_navi are not covered yet")
+        assert 0.0 <= lid["dropout_prob"] <= 1.0  # obs/state_obs.py:240
+        if lid["add_others_navi"]:
+            raise NotImplementedError("lidar add_others_navi is not covered yet")
         self._lib = MultiAgentLibrary(self.ASSET)
         self.num_agents = self.config["num_agents"]
         if self.num_agents == -1:

@@ -292,6 +292,8 @@ def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
         for t in range(steps):
             a = _lane_follow_action(env.agent, rs, 0.02, fast=22, slow=14)
             before = list(tm._traffic_vehicles)
+            for k, v in enumerate(roster.vehicles):
+                v.body._md_slot = k  # index order of the contact model = the trace's slot order (refshim/pbullet.py)
             o, r, te, tr, info = env.step(a)
             after = list(tm._traffic_vehicles)
             removed = [v for v in before if v not in after or v.name != names[roster.vehicles.index(v)]]
@@ -348,6 +350,7 @@ def main():
     rng = np.random.RandomState(0)
     rand_actions = rng.uniform(-1, 1, (args.steps, 2))
     smooth = np.stack([0.15 * np.sin(np.arange(args.steps) / 7.0), np.full(args.steps, 0.6)], 1)
+    smooth_long = np.stack([0.15 * np.sin(np.arange(130) / 7.0), np.full(130, 0.6)], 1)
     cases = [
         # BASELINE config 1: default single agent on map "S", profiling action [0, 1]
         ("cfg1_S_straight", MetaDriveEnv, dict(map="S", traffic_density=0.1, log_level=50), 0,
@@ -378,6 +381,10 @@ def main():
         # BASELINE config 4: SafeMetaDriveEnv with static obstacles
         ("cfg4_safe_seed2", SafeMetaDriveEnv, dict(num_scenarios=20, start_seed=0, log_level=50), 2, smooth),
         ("cfg4_safe_seed5", SafeMetaDriveEnv, dict(num_scenarios=20, start_seed=0, log_level=50), 5, smooth),
+        # non-terminal contacts, i.e. the contact response: seed 40 drives into the cones of an accident scene (step ~72),
+        # seed 8 into a traffic vehicle (step ~81), and both keep going (crash_*_done=False, safe_metadrive_env.py:15-16)
+        ("cfg4_safe_seed40_cones", SafeMetaDriveEnv, dict(num_scenarios=100, start_seed=0, log_level=50), 40, smooth_long),
+        ("cfg4_safe_seed8_bump", SafeMetaDriveEnv, dict(num_scenarios=100, start_seed=0, log_level=50), 8, smooth_long),
     ]
     # BASELINE config 3: MultiAgentRoundaboutEnv with 240-beam lidar
     #   cfg3_ma_roundabout          40 agents, random actions, respawn off (crash / out-of-road / wreck bookkeeping)

@@ -739,9 +739,68 @@ class BulletWorld:
             # zero-friction slide at their set planar velocity; z is held by the ground contact.
             b.pos = b.pos + np.array([b.lin_vel[0], b.lin_vel[1], 0.0]) * dt
             b._geom_cache = None
+        # contact flags are raised on the poses every body reached this sub-step; the response (physics.contact_deltas)
+        # is computed from the same snapshot and applied afterwards
+        deltas = self._contact_response()
         self._contact_callbacks(chassis_nodes)
+        for c, (dv, dw, dp) in deltas:
+            c.lin_vel = c.lin_vel + np.array([dv[0], dv[1], 0.0])
+            c.ang_vel = c.ang_vel + np.array([0.0, 0.0, dw])
+            c.pos = c.pos + np.array([dp[0], dp[1], 0.0])
+            c._geom_cache = None
 
     do_physics = doPhysics
+
+    def _contact_response(self):
+        """One Jacobi pass of the planar contact model (physics.contact_deltas) over the chassis of this world, ordered
+        like self.vehicles, followed by the static obstacles that collide with the Vehicle group."""
+        bodies, nodes = [], []
+        chassis = set()
+        # index order = the trace's slot order when the golden generator tagged the chassis (a respawned vehicle takes
+        # over the slot of the one that left), else creation order
+        order = sorted(range(len(self.vehicles)), key=lambda i: (self.vehicles[i].chassis.__dict__.get("_md_slot", i), i))
+        for veh in (self.vehicles[i] for i in order):
+            c = veh.chassis
+            chassis.add(c)
+            if c.world is not self:
+                continue
+            box = c.shapes[0][0]
+            ts = c.shapes[0][1]
+            off = ts.pos if ts is not None else np.zeros(3)
+            centre = c.pos + c.mat @ off
+            u = c.mat[:2, 1]
+            u = u / math.hypot(u[0], u[1])
+            dyn = not c.static and c.mass > 0
+            izz = c.mass / 12.0 * ((2 * box.half[0])**2 + (2 * box.half[1])**2) if dyn else 0.0
+            bodies.append(dict(shape="rect", c=centre[:2].copy(), u=u, h=(box.half[1], box.half[0]), o=c.pos[:2].copy(),
+                               v=c.lin_vel[:2].copy(), w=float(c.ang_vel[2]), im=1.0 / c.mass if dyn else 0.0,
+                               ii=1.0 / izz if dyn else 0.0))
+            nodes.append(c)
+        n_veh = len(bodies)
+        if n_veh == 0:
+            return []
+        probe = nodes[0]
+        for b in self.bodies:
+            if b in chassis or isinstance(b, BulletGhostNode) or not isinstance(b, BulletRigidBodyNode):
+                continue
+            if not (b.static or b.mass <= 0) or not self._groups_collide(probe.into_mask, b.into_mask):
+                continue  # free movers (pedestrians, loose cones) neither push nor are pushed in this model
+            prims = _cached(b)[0]
+            if len(prims) != 1 or prims[0][0] not in ("box", "cyl"):
+                continue
+            pr = prims[0]
+            if pr[0] == "box":
+                ce, u, h = _footprint(pr)
+                bodies.append(dict(shape="rect", c=np.array(ce), u=np.array(u), h=h, o=np.array(ce), v=np.zeros(2), w=0.0,
+                                   im=0.0, ii=0.0))
+            else:
+                bodies.append(dict(shape="circle", c=pr[1][:2].copy(), r=pr[2], o=pr[1][:2].copy(), v=np.zeros(2), w=0.0,
+                                   im=0.0, ii=0.0))
+            nodes.append(b)
+        # broad phase: only bodies near a moving chassis matter; the pair loop itself is exact
+        out = ph.contact_deltas(bodies)
+        return [(nodes[k], out[k]) for k in range(n_veh) if bodies[k]["im"] > 0.0
+                and (out[k][0].any() or out[k][1] != 0.0 or out[k][2].any())]
 
     def _contact_callbacks(self, chassis_nodes):
         if self.contact_cb is None:

@@ -415,3 +415,136 @@ def _ccw(pts):
         x1, y1 = pts[(i + 1) % len(pts)]
         s += x0 * y1 - x1 * y0
     return s > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# contact response between the bodies of the dynamic world
+# ---------------------------------------------------------------------------------------------
+# Bullet resolves chassis-chassis and chassis-obstacle contacts inside doPhysics with its sequential-impulse solver over
+# persistent GJK/EPA manifolds (btSequentialImpulseConstraintSolver, btConvexConvexAlgorithm; NOT in /root/reference).
+# That machinery is not restated; SURVEY.md 7.3 #2 asks for "a simple impulse model, stated as such".  The model, shared
+# word for word by oracle/md_oracle.c and the CUDA kernel (DESIGN.md "Contact response"):
+#   * planar (x, y, yaw) contacts between the chassis footprints (rectangles) and static obstacles (cone / warning
+#     cylinders -> circles, barrier -> rectangle); pedestrians and other free movers are not pushed and do not push;
+#   * per sub-step, after every body has moved: one Jacobi pass over the overlapping pairs from a snapshot of the
+#     post-move state - normal = minimum-translation axis (A -> B, A = the lower index), contact point = mean of the
+#     corners of either rectangle lying inside the other (circle: closest point of the rectangle), frictionless
+#     inelastic normal impulse J = max(0, -v_n) / K with K = 1/mA + 1/mB + (rA x n)^2 / IzA + (rB x n)^2 / IzB, plus a
+#     position push-out of CONTACT_ERP x (depth - CONTACT_SLOP) split by inverse mass (Bullet's erp is 0.2 as well);
+#   * static bodies (mass 0: obstacles, wrecks, broken-down cars) have 1/m = 1/Iz = 0 and never move.
+CONTACT_ERP = 0.2
+CONTACT_SLOP = 0.01
+CORNER_EPS = 1e-4
+CONTACT_TIE = 1e-6
+AXIS_MARGIN = 1e-3
+
+
+def _perp(u):
+    return np.array([-u[1], u[0]])
+
+
+def _corners_inside(c_in, u_in, h_in, c_box, u_box, h_box):
+    """corners of rectangle `in` that lie inside rectangle `box` -> (count, sum_x, sum_y)"""
+    n, sx, sy = 0, 0.0, 0.0
+    vb = _perp(u_box)
+    vi = _perp(u_in)
+    for su, sv in ((1.0, 1.0), (-1.0, 1.0), (-1.0, -1.0), (1.0, -1.0)):
+        p = c_in + u_in * (su * h_in[0]) + vi * (sv * h_in[1])
+        d = p - c_box
+        if abs(float(d @ u_box)) <= h_box[0] + CORNER_EPS and abs(float(d @ vb)) <= h_box[1] + CORNER_EPS:
+            n += 1
+            sx += p[0]
+            sy += p[1]
+    return n, sx, sy
+
+
+def rect_rect_contact(cA, uA, hA, cB, uB, hB):
+    """(n, depth, p) with n the unit normal from A to B, or None when the rectangles do not overlap."""
+    cA, uA, cB, uB = (np.asarray(x, dtype=np.float64) for x in (cA, uA, cB, uB))
+    d = cB - cA
+    cand = []
+    for a in (uA, _perp(uA), uB, _perp(uB)):
+        rA = abs(float(a @ uA)) * hA[0] + abs(float(a @ _perp(uA))) * hA[1]
+        rB = abs(float(a @ uB)) * hB[0] + abs(float(a @ _perp(uB))) * hB[1]
+        s = float(a @ d)
+        ov = rA + rB - abs(s)
+        if ov < 0.0:
+            return None
+        cand.append((ov, a if s > -CONTACT_TIE else -a))  # centres level along the axis: A -> B is "+axis" by convention
+    # minimum-translation axis.  Two nearly parallel boxes overlap by almost the same amount along A's and B's axis, and
+    # the pick would flip on rounding noise: B's axes win only by a clear margin (AXIS_MARGIN)
+    bestA = cand[1] if cand[1][0] < cand[0][0] else cand[0]
+    bestB = cand[3] if cand[3][0] < cand[2][0] else cand[2]
+    best, n = bestB if bestB[0] < bestA[0] - AXIS_MARGIN else bestA
+    k0, x0, y0 = _corners_inside(cB, uB, hB, cA, uA, hA)
+    k1, x1, y1 = _corners_inside(cA, uA, hA, cB, uB, hB)
+    if k0 + k1 > 0:
+        p = np.array([(x0 + x1) / (k0 + k1), (y0 + y1) / (k0 + k1)])
+    else:
+        p = 0.5 * (cA + cB)
+    return n, best, p
+
+
+def rect_circle_contact(cA, uA, hA, cB, r):
+    cA, uA, cB = (np.asarray(x, dtype=np.float64) for x in (cA, uA, cB))
+    vA = _perp(uA)
+    d = cB - cA
+    lx, ly = float(d @ uA), float(d @ vA)
+    qx, qy = min(max(lx, -hA[0]), hA[0]), min(max(ly, -hA[1]), hA[1])
+    ex, ey = lx - qx, ly - qy
+    d2 = ex * ex + ey * ey
+    if d2 > r * r:
+        return None
+    if d2 > 1e-12:  # centre outside the rectangle: normal from the closest point to the centre
+        dist = math.sqrt(d2)
+        n = uA * (ex / dist) + vA * (ey / dist)
+        return n, r - dist, cA + uA * qx + vA * qy
+    dx, dy = hA[0] - abs(lx), hA[1] - abs(ly)  # centre inside: leave through the nearest face
+    if dx < dy:
+        sgn = 1.0 if lx >= 0.0 else -1.0
+        return uA * sgn, dx + r, cA + uA * (sgn * hA[0]) + vA * ly
+    sgn = 1.0 if ly >= 0.0 else -1.0
+    return vA * sgn, dy + r, cA + uA * lx + vA * (sgn * hA[1])
+
+
+def contact_deltas(bodies):
+    """bodies: list of dict(shape='rect'|'circle', c, u, h | r, o, v, w, im, ii) ordered by index; returns per body
+    (dv[2], dw, dp[2]) of one Jacobi pass.  Bodies with im == 0 get no deltas."""
+    out = [(np.zeros(2), 0.0, np.zeros(2)) for _ in bodies]
+    rad = [b["r"] if b["shape"] == "circle" else math.hypot(b["h"][0], b["h"][1]) for b in bodies]
+    for i, A in enumerate(bodies):
+        for j in range(i + 1, len(bodies)):
+            B = bodies[j]
+            if A["im"] == 0.0 and B["im"] == 0.0:
+                continue
+            dc = B["c"] - A["c"]
+            if dc[0] * dc[0] + dc[1] * dc[1] > (rad[i] + rad[j])**2:
+                continue  # bounding circles apart: the exact tests below cannot overlap
+            if A["shape"] == "circle" and B["shape"] == "circle":
+                continue
+            if A["shape"] == "rect" and B["shape"] == "rect":
+                res = rect_rect_contact(A["c"], A["u"], A["h"], B["c"], B["u"], B["h"])
+            elif A["shape"] == "rect":
+                res = rect_circle_contact(A["c"], A["u"], A["h"], B["c"], B["r"])
+            else:
+                res = rect_circle_contact(B["c"], B["u"], B["h"], A["c"], A["r"])
+                if res is not None:
+                    res = (-res[0], res[1], res[2])
+            if res is None:
+                continue
+            n, depth, p = res
+            rA, rB = p - A["o"], p - B["o"]
+            vpA = A["v"] + A["w"] * np.array([-rA[1], rA[0]])
+            vpB = B["v"] + B["w"] * np.array([-rB[1], rB[0]])
+            vn = float((vpB - vpA) @ n)
+            cAn = rA[0] * n[1] - rA[1] * n[0]
+            cBn = rB[0] * n[1] - rB[1] * n[0]
+            K = A["im"] + B["im"] + cAn * cAn * A["ii"] + cBn * cBn * B["ii"]
+            J = -vn / K if vn < 0.0 else 0.0
+            push = CONTACT_ERP * max(depth - CONTACT_SLOP, 0.0) / (A["im"] + B["im"])
+            for k, sgn, body, cn in ((i, -1.0, A, cAn), (j, 1.0, B, cBn)):
+                if body["im"] == 0.0:
+                    continue
+                dv, dw, dp = out[k]
+                out[k] = (dv + n * (sgn * J * body["im"]), dw + sgn * J * cn * body["ii"], dp + n * (sgn * push * body["im"]))
+    return out

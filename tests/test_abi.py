@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(h, n), n
     assert set(names) == set(mdlib.EXPORTS)
     h.md_abi_version.restype = ctypes.c_int
-    assert h.md_abi_version() == 2
+    assert h.md_abi_version() == 3
 
 
 def test_config_struct_matches_header():
@@ -58,3 +58,12 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 s = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in s and "from oracle" not in s and "md_oracle" not in s, f
+
+
+def test_integration_stub_matches_the_struct():
+    """INTEGRATION.md shows the reference-side ctypes stub; its MdConfig must list the header's fields in order."""
+    import re
+    from metadrive_ped_b200.abi import MdConfig
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blk = text[text.index("class MdConfig(C.Structure):"):text.index("# include/md_layout.h: struct MdArrays")]
+    assert re.findall(r'"([a-z_0-9]+)"', blk) == [f[0] for f in MdConfig._fields_]

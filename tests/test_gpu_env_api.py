@@ -234,3 +234,44 @@ def test_pedestrian_intersection_env():
     vi = b.sim.get_state("veh_i").reshape(128, -1, 16)
     assert (vi[:, 1:, 1].sum(1) >= 8).all(), "respawn mode keeps the traffic population alive"
     b.close()
+
+
+def test_lidar_noise_and_dropout():
+    """vehicle_config.lidar.gaussian_noise / dropout_prob (obs/state_obs.py:236-244): clip(x + N(0, sigma), 0, 1), then
+    zeroed with probability p.  The reference draws from numpy's unseeded generator, so the check is statistical; the
+    state part of the observation, the hit ids and md_lidar stay clean, and a handle is reproducible."""
+    from metadrive_ped_b200.library import ScenarioLibrary
+    from metadrive_ped_b200.sim import BatchedSim
+    lib = ScenarioLibrary("pg3_density0.1.npz")
+    idx = list(range(256))
+    arrays, cfg0 = lib.build_world(idx)
+    _, cfg1 = lib.build_world(idx, lidar_gaussian_noise=0.05, lidar_dropout_prob=0.1, noise_seed=3)
+    clean, noisy, again = BatchedSim(arrays, cfg0), BatchedSim(arrays, cfg1), BatchedSim(arrays, cfg1)
+    o0, o1, o2 = clean.reset().cpu().numpy(), noisy.reset().cpu().numpy(), again.reset().cpu().numpy()
+    np.testing.assert_array_equal(o1, o2)                       # same seed, same pass -> same draws
+    np.testing.assert_array_equal(o0[:, :19], o1[:, :19])       # state floats untouched
+    l0, l1 = o0[:, 19:], o1[:, 19:]
+    assert (l1 >= 0).all() and (l1 <= 1).all()
+    dropped = (l1 == 0.0) & (l0 > 0.2)
+    frac = dropped.sum() / (l0 > 0.2).sum()
+    assert abs(frac - 0.1) < 0.01, frac
+    mid = (l0 > 0.2) & (l0 < 0.8) & ~dropped                    # away from the clip
+    if mid.sum() > 200:
+        res = (l1 - l0)[mid]
+        assert abs(res.mean()) < 0.01 and abs(res.std() - 0.05) < 0.01, (res.mean(), res.std())
+    miss = (l0 == 1.0) & ~dropped                               # a miss stays 1.0 half of the time (clip), else drops below
+    below = (l1[miss] < 1.0).mean()
+    assert abs(below - 0.5) < 0.02, below
+    f_clean, h_clean = clean.lidar()
+    f_noisy, h_noisy = noisy.lidar()                            # Lidar.perceive itself carries no noise
+    np.testing.assert_array_equal(f_clean.cpu().numpy(), f_noisy.cpu().numpy())
+    np.testing.assert_array_equal(h_clean.cpu().numpy(), h_noisy.cpu().numpy())
+    o3 = noisy.reset().cpu().numpy()                            # a later observation pass draws fresh noise
+    assert (o3[:, 19:] != o1[:, 19:]).mean() > 0.3
+    for s in (clean, noisy, again):
+        s.close()
+    from metadrive_ped_b200 import MetaDriveEnv
+    env = MetaDriveEnv(dict(map=3, num_scenarios=10, vehicle_config=dict(lidar=dict(gaussian_noise=0.1, dropout_prob=0.2))))
+    obs, _ = env.reset(seed=1)
+    assert obs.shape == (259, ) and (obs[19:] == 0.0).sum() > 20
+    env.close()
