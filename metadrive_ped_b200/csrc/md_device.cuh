@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "../../include/md_layout.h"
+#include "../../include/md_math.h"
 
 #define MD_PI 3.14159265358979323846f
 #define MD_TWO_PI 6.28318530717958647692f
@@ -87,8 +88,8 @@ __device__ __forceinline__ void lane_position(const float* __restrict__ L, float
         float r = L[LF_P0 + 2], dir = L[LF_P0 + 5];
         float phi = dir * lon / r + L[LF_P0 + 3];
         float rr = r + lat * dir;
-        x = L[LF_P0 + 0] + rr * cosf(phi);
-        y = L[LF_P0 + 1] + rr * sinf(phi);
+        x = L[LF_P0 + 0] + rr * md_cosf(phi);
+        y = L[LF_P0 + 1] + rr * md_sinf(phi);
     }
 }
 __device__ __forceinline__ float lane_heading_at(const float* __restrict__ L, float lon) {
@@ -105,7 +106,7 @@ __device__ __forceinline__ void lane_local(const float* __restrict__ L, float px
         lat = ddx * dy + ddy * (-dx);
     } else {
         float r = L[LF_P0 + 2], sp = L[LF_P0 + 3], ep = L[LF_P0 + 4], dir = L[LF_P0 + 5];
-        float abs_phase = wrap_to_pi(atan2f(ddy, ddx));
+        float abs_phase = wrap_to_pi(md_atan2f(ddy, ddx));
         float sp_w = wrap_to_pi(sp), ep_w = wrap_to_pi(ep);
         float d_s = fabsf(wrap_to_pi(abs_phase - sp_w));
         float d_e = fabsf(wrap_to_pi(abs_phase - ep_w));
@@ -364,7 +365,7 @@ __device__ __forceinline__ void pair_impulse(const CBody& A, const CBody& B, flo
 __device__ __forceinline__ Rect object_rect(const float* O) {
     Rect r;
     r.cx = O[OB_X]; r.cy = O[OB_Y];
-    r.ux = cosf(O[OB_HEADING]); r.uy = sinf(O[OB_HEADING]);
+    r.ux = md_cosf(O[OB_HEADING]); r.uy = md_sinf(O[OB_HEADING]);
     r.hu = O[OB_B]; r.hv = O[OB_A];
     return r;
 }
@@ -416,8 +417,8 @@ __device__ __forceinline__ void quat_integrate(float* q, F3 w, float dt) {
     if (ang * dt > 0.25f * MD_PI) ang = 0.25f * MD_PI / dt;
     F3 axis;
     if (ang < 0.001f) axis = w * (0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang);
-    else axis = w * (sinf(0.5f * ang * dt) / ang);
-    float aw = cosf(ang * dt * 0.5f), ax = axis.x, ay = axis.y, az = axis.z;
+    else axis = w * (md_sinf(0.5f * ang * dt) / ang);
+    float aw = md_cosf(ang * dt * 0.5f), ax = axis.x, ay = axis.y, az = axis.z;
     float bw = q[0], bx = q[1], by = q[2], bz = q[3];
     float rw = aw * bw - ax * bx - ay * by - az * bz;
     float rx = aw * bx + ax * bw + ay * bz - az * by;

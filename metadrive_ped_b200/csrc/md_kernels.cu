@@ -187,7 +187,7 @@ __device__ __forceinline__ void yaw_quat_for_lane(const float* L, float lon, flo
         qw = cw; qz = s < 0.0f ? -sw : sw;
     } else {
         const float yaw = lane_heading_at(L, lon) - MD_PI / 2.0f;
-        qw = cosf(0.5f * yaw); qz = sinf(0.5f * yaw);
+        qw = md_cosf(0.5f * yaw); qz = md_sinf(0.5f * yaw);
     }
 }
 
@@ -307,7 +307,7 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
     float lon, lat;
     lane_local(Ls, px, py, lon, lat);
     float lane_heading = lane_heading_at(Ls, lon + 1.0f);
-    float v_heading = atan2f(hy, hx);
+    float v_heading = md_atan2f(hy, hx);
     float steering = pid(1.7f, 0.01f, 3.5f, D[VD_H_PERR], D[VD_H_IERR], -wrap_to_pi(lane_heading - v_heading));
     steering += pid(0.3f, 0.002f, 0.05f, D[VD_L_PERR], D[VD_L_IERR], -lat);
     // acceleration (:303-320), km/h units
@@ -374,7 +374,7 @@ __device__ void localise(const MapView& m, const float* S, int* I, const int* __
             !point_in_hull(Ll, m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], px, py)) continue;
         on_lane = true;
         float lh = lane_heading_at(Ll, lon);
-        float cosang = cosf(lh) * hx + sinf(lh) * hy;
+        float cosang = md_cosf(lh) * hx + md_sinf(lh) * hy;
         if (!(cosang > 0.0f)) continue;
         // lane.distance (abs_lane.py:76-82) from the local coordinates already at hand (same arithmetic as lane_distance)
         const float over = lon - Ll[LF_LENGTH], under = 0.0f - lon;
@@ -653,7 +653,7 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
     {
         float lhx = C[VC_LAST_HX], lhy = C[VC_LAST_HY];
         float dotp = hx * lhx + hy * lhy, crs = hx * lhy - hy * lhx;
-        float beta = dotp <= 0.0f ? 0.5f * MD_PI : atan2f(fabsf(crs), dotp);
+        float beta = dotp <= 0.0f ? 0.5f * MD_PI : md_atan2f(fabsf(crs), dotp);
         o[sd + 5] = clipf(beta / 0.1f, 0.0f, 1.0f);
     }
     if (cfg.n_lane_lasers == 0) {
@@ -1030,7 +1030,7 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
         block_obj = __syncthreads_or(has_obj);
     }
     SteerCS scs;
-    scs.cs = cosf(act.steer_rad); scs.sn = sinf(act.steer_rad);
+    scs.cs = md_cosf(act.steer_rad); scs.sn = md_sinf(act.steer_rad);
     for (int rep = 0; rep < n_sub; rep++) {
         if (moves) {
             vehicle_substep(P, B, act, scs, cfg.dt);
@@ -1214,7 +1214,7 @@ __device__ __forceinline__ void after_step_vehicle(const MapView& m, const float
     float dx = C[VC_LAST_X] - St[VS_POS], dy = C[VC_LAST_Y] - St[VS_POS + 1];
     float dist_km = sqrtf(dx * dx + dy * dy) / 1000.0f;
     float speed_kmh = sqrtf(St[VS_VEL] * St[VS_VEL] + St[VS_VEL + 1] * St[VS_VEL + 1]) * 3.6f;
-    float step_energy = 3.25f * expf(0.01f * speed_kmh) * dist_km / 100.0f * 1000.0f;
+    float step_energy = 3.25f * md_expf(0.01f * speed_kmh) * dist_km / 100.0f * 1000.0f;
     C[VC_STEP_ENERGY] = step_energy;
     C[VC_ENERGY] += step_energy;
 }
@@ -1448,7 +1448,7 @@ __device__ __forceinline__ float lidar_noise(const MdConfig& cfg, float frac, ui
     if (cfg.lidar_gaussian_noise > 0.0f) {
         const float u1 = ((float)(mix32(key + 1u) >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
         const float u2 = (float)(mix32(key + 2u) >> 8) * (1.0f / 16777216.0f);           // [0, 1)
-        const float z = sqrtf(-2.0f * logf(u1)) * cosf(MD_TWO_PI * u2);
+        const float z = sqrtf(-2.0f * logf(u1)) * md_cosf(MD_TWO_PI * u2);
         frac = clipf(frac + cfg.lidar_gaussian_noise * z, 0.0f, 1.0f);
     }
     if (cfg.lidar_dropout_prob > 0.0f) {
@@ -1626,7 +1626,7 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
                 const float perp2 = (rx * rx + ry * ry) - proj * proj;
                 if (perp2 > rb * rb + 1e-3f || proj < -rb || proj > D + rb) continue;
                 if (ob[OB_KIND] == 2.0f) {
-                    float ch = cosf(ob[OB_HEADING]), sh = sinf(ob[OB_HEADING]);
+                    float ch = md_cosf(ob[OB_HEADING]), sh = md_sinf(ob[OB_HEADING]);
                     M3 R;
                     R.m[0][0] = ch; R.m[0][1] = -sh; R.m[0][2] = 0.0f; R.m[1][0] = sh; R.m[1][1] = ch; R.m[1][2] = 0.0f;
                     R.m[2][0] = 0.0f; R.m[2][1] = 0.0f; R.m[2][2] = 1.0f;

@@ -26,7 +26,7 @@ def build(force=False):
     """Compile libmdstep.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     src_dir = os.path.join(_HERE, "csrc")
     srcs = [os.path.join(src_dir, f) for f in ("md_kernels.cu", "md_device.cuh")]
-    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("mdstep.h", "md_layout.h")]
+    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("mdstep.h", "md_layout.h", "md_math.h")]
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", src_dir, "-s"] + (["-B"] if force else []))

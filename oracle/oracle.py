@@ -18,9 +18,9 @@ _lib = None
 
 def build(force=False):
     src = os.path.join(_HERE, "md_oracle.c")
-    hdr = os.path.join(_HERE, "..", "include", "md_layout.h")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src),
-                                                                                   os.path.getmtime(hdr)):
+    hdrs = [os.path.join(_HERE, "..", "include", h) for h in ("md_layout.h", "md_math.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+            os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 

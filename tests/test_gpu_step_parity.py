@@ -1,6 +1,7 @@
-"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on identical inputs, and against the
-golden traces of the reference.  Index / flag outputs bit-exact, floats within the north-star tolerances:
-lidar fractions 1e-4 relative, poses 1e-2 m / 1e-3 rad over 100 steps."""
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on identical inputs - EVERY output bit-identical,
+integers and floats alike (shared elementary functions, include/md_math.h; same operation order; no FMA contraction) -
+and against the golden traces of the reference within the north-star tolerances (lidar fractions 1e-4 relative, poses
+1e-2 m / 1e-3 rad over 100 steps)."""
 import numpy as np
 import pytest
 
@@ -48,14 +49,11 @@ def test_multi_agent_step_matches_oracle_and_golden(tag, oracle_lib):
         np.testing.assert_array_equal(sim.terminated.cpu().numpy(), orc.term)
         np.testing.assert_array_equal(sim.truncated.cpu().numpy(), orc.trunc)
         vs_g, vs_o = sim.get_state("veh_s"), orc.a["veh_s"]
-        np.testing.assert_allclose(vs_g[:, 0:3], vs_o[:, 0:3], atol=2e-3, rtol=0)
-        np.testing.assert_allclose(vs_g[:, 3:7], vs_o[:, 3:7], atol=5e-4, rtol=0)
+        np.testing.assert_array_equal(vs_g, vs_o, err_msg="veh_s at step %d" % t)   # bit-identical, like every float below
         valid = (fl & 0x2000) != 0
         og = sim.obs.cpu().numpy()
-        np.testing.assert_allclose(sim.reward.cpu().numpy(), orc.reward, atol=1e-4, rtol=0)
-        np.testing.assert_allclose(og[valid][:, :19], orc.obs[valid][:, :19], atol=2e-4, rtol=0)
-        bad = ~np.isclose(og[valid][:, 19:], orc.obs[valid][:, 19:], atol=2e-4, rtol=1e-4)
-        assert bad.sum(1).max(initial=0) <= 1 and bad.sum() <= 2, "lidar differs from the oracle at step %d" % t
+        np.testing.assert_array_equal(sim.reward.cpu().numpy(), orc.reward)
+        np.testing.assert_array_equal(og[valid], orc.obs[valid], err_msg="observations at step %d" % t)
         # env 0 against the reference's own trace
         check_ma_step(g, t, (vs_g, sim.get_state("veh_i")),
                       (og, sim.reward.cpu().numpy(), sim.cost.cpu().numpy(), sim.terminated.cpu().numpy(),
@@ -75,6 +73,7 @@ def test_step_matches_oracle_and_golden(tag, oracle_lib):
     np.testing.assert_allclose(obs_g[0], g["obs"][0], atol=2e-4, rtol=0)
     T = len(g["reward"])
     events = np.asarray(g["respawn_events"]).reshape(-1, 5) if "respawn_events" in g else np.zeros((0, 5))
+    ego_touched = False
     for t in range(T):
         a = np.tile(g["actions"][t].astype(np.float32), (cfg.n_envs, 1))
         sim.step(torch.from_numpy(a).cuda())
@@ -93,25 +92,22 @@ def test_step_matches_oracle_and_golden(tag, oracle_lib):
         np.testing.assert_array_equal(sim.info_flags.cpu().numpy(), orc.info_flags)
         np.testing.assert_array_equal(sim.terminated.cpu().numpy(), orc.term)
         np.testing.assert_array_equal(sim.truncated.cpu().numpy(), orc.trunc)
-        # poses: 1e-2 m / 1e-3 rad is the bar; the two float32 paths stay far inside it
-        np.testing.assert_allclose(vs_g[:, 0:3], vs_o[:, 0:3], atol=2e-3, rtol=0)
-        np.testing.assert_allclose(vs_g[:, 3:7], vs_o[:, 3:7], atol=5e-4, rtol=0)
-        np.testing.assert_allclose(sim.reward.cpu().numpy(), orc.reward, atol=1e-4, rtol=0)
-        np.testing.assert_allclose(sim.cost.cpu().numpy(), orc.cost, atol=0, rtol=0)
+        # every float: the two float32 paths share their elementary functions (include/md_math.h) and write products and
+        # sums in the same order without FMA contraction, so poses, rewards and the whole observation are BIT-identical
+        np.testing.assert_array_equal(vs_g, vs_o, err_msg="veh_s at step %d" % t)
+        np.testing.assert_array_equal(sim.reward.cpu().numpy(), orc.reward)
+        np.testing.assert_array_equal(sim.cost.cpu().numpy(), orc.cost)
+        np.testing.assert_array_equal(sim.info_f.cpu().numpy(), orc.info_f)
         og = sim.obs.cpu().numpy()
-        np.testing.assert_allclose(og[:, :19], orc.obs[:, :19], atol=2e-4, rtol=0)
-        np.testing.assert_allclose(og[:, 19:], orc.obs[:, 19:], atol=2e-4, rtol=1e-4)
-        touching = (vi_o[:, 8] & 0x3) != 0
-        if touching.any():
-            # bodies in a SUSTAINED contact amplify the last-bit differences of the two libms (CUDA vs glibc sinf / cosf)
-            # by ~100x over a hundred steps: they are re-synchronised to the oracle after having been compared
-            vs_sync = vs_g.copy()
-            vs_sync[touching] = vs_o[touching]
-            sim.set_state("veh_s", vs_sync)
-        # against the reference's own trace (ego): reward, done, observation
-        assert abs(float(sim.reward[0]) - g["reward"][t]) < 2e-3
-        assert bool(sim.terminated[0]) == bool(g["terminated"][t])
-        np.testing.assert_allclose(og[0, :19], g["obs"][t + 1][:19], atol=2e-3, rtol=0)
+        np.testing.assert_array_equal(og, orc.obs, err_msg="observation at step %d" % t)
+        # against the reference's own trace (ego): reward, done, observation - while the replay is free-running.  Once
+        # the ego has been in a non-terminal contact, the float32 replay drifts from the float64 trace (see
+        # tests/test_oracle_golden.py, which re-synchronises and goes on); the oracle comparison above continues
+        ego_touched = ego_touched or bool(vi_o[0, 8] & 0x3)
+        if not ego_touched:
+            assert abs(float(sim.reward[0]) - g["reward"][t]) < 2e-3
+            assert bool(sim.terminated[0]) == bool(g["terminated"][t])
+            np.testing.assert_allclose(og[0, :19], g["obs"][t + 1][:19], atol=2e-3, rtol=0)
     sim.close()
 
 
