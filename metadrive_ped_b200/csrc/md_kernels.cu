@@ -931,18 +931,25 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     CBody* cd_all = reinterpret_cast<CBody*>(smem_raw + step_smem_bytes(S, O, epb));
     int* list = reinterpret_cast<int*>(smem_raw + step_smem_bytes(S, O, epb) + sizeof(CBody) * (size_t)epb * S);
     int* n_list = list + epb * S;
-    if (threadIdx.x == 0) *n_list = 0;
+    if (threadIdx.x == 0) { n_list[0] = 0; n_list[1] = 0; }
     __syncthreads();
     if (H.work) {
-        const int alive0 = A.veh_i[(size_t)H.g * VEH_I + VI_ALIVE];
-        H.nb[H.slot].alive = alive0;
-        if (alive0) list[atomicAdd(n_list, 1)] = H.le * S + H.slot;
+        // the list is filled from both ends: driven vehicles (agents, triggered traffic) from the front, parked ones (the
+        // untriggered traffic of later blocks: brakes on, four wheels down - the majority in a PG scene) from the back, so
+        // that a warp integrates vehicles on the same control-flow path
+        const int4 i0 = *reinterpret_cast<const int4*>(A.veh_i + (size_t)H.g * VEH_I);  // kind, alive, active, trigger
+        H.nb[H.slot].alive = i0.y;
+        if (i0.y) {
+            if (i0.z) list[atomicAdd(&n_list[0], 1)] = H.le * S + H.slot;
+            else list[epb * S - 1 - atomicAdd(&n_list[1], 1)] = H.le * S + H.slot;
+        }
     }
     __syncthreads();
     StepGeom G = H;
-    G.work = (int)threadIdx.x < *n_list;
+    const int n_front = n_list[0], n_back = n_list[1];
+    G.work = (int)threadIdx.x < n_front + n_back;
     if (G.work) {
-        const int v = list[threadIdx.x];
+        const int v = (int)threadIdx.x < n_front ? list[threadIdx.x] : list[epb * S - 1 - ((int)threadIdx.x - n_front)];
         G.le = v / S; G.slot = v - G.le * S;
         G.env = blockIdx.x * epb + G.le; G.g = G.env * S + G.slot;
         G.nb = H.nb + ((ptrdiff_t)G.le - H.le) * S;
