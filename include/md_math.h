@@ -18,6 +18,16 @@
 #define MDM_FN static inline
 #endif
 
+/* Fused multiply-adds are written out explicitly (fmaf is correctly rounded on both sides: FFMA on the GPU, vfmadd or
+ * libm on the host); the compilers themselves never contract (-fmad=false / -ffp-contract=off), so both implementations
+ * fuse exactly the same products.  These are the building blocks of every dot / cross / matrix product on the path. */
+MDM_FN float md_dot3(float ax, float ay, float az, float bx, float by, float bz) { return fmaf(az, bz, fmaf(ay, by, ax * bx)); }
+MDM_FN float md_dot4(float aw, float ax, float ay, float az, float bw, float bx, float by, float bz) {
+    return fmaf(az, bz, fmaf(ay, by, fmaf(ax, bx, aw * bw)));
+}
+MDM_FN float md_sum2(float a, float b, float c, float d) { return fmaf(a, b, c * d); }      /* a*b + c*d */
+MDM_FN float md_diff2(float a, float b, float c, float d) { return fmaf(a, b, -(c * d)); }  /* a*b - c*d */
+
 #define MDM_PIO2_1 1.5703125f                 /* pi/2 split in three: 8 + 11 + 24 significant bits */
 #define MDM_PIO2_2 4.837512969970703125e-4f
 #define MDM_PIO2_3 7.54978995489188216e-8f

@@ -30,28 +30,28 @@ __device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y
 __device__ __forceinline__ F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float dot(F3 a, F3 b) { return md_dot3(a.x, a.y, a.z, b.x, b.y, b.z); }
 __device__ __forceinline__ F3 cross(F3 a, F3 b) {
-    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return f3(md_diff2(a.y, b.z, a.z, b.y), md_diff2(a.z, b.x, a.x, b.z), md_diff2(a.x, b.y, a.y, b.x));
 }
 struct M3 { float m[3][3]; };  // world = m * local
 __device__ __forceinline__ M3 quat_to_m3(float w, float x, float y, float z) {
-    float n = w * w + x * x + y * y + z * z;
+    float n = md_dot4(w, x, y, z, w, x, y, z);
     float s = n > 0.0f ? 2.0f / n : 0.0f;
     M3 r;
-    r.m[0][0] = 1.0f - s * (y * y + z * z); r.m[0][1] = s * (x * y - w * z); r.m[0][2] = s * (x * z + w * y);
-    r.m[1][0] = s * (x * y + w * z); r.m[1][1] = 1.0f - s * (x * x + z * z); r.m[1][2] = s * (y * z - w * x);
-    r.m[2][0] = s * (x * z - w * y); r.m[2][1] = s * (y * z + w * x); r.m[2][2] = 1.0f - s * (x * x + y * y);
+    r.m[0][0] = 1.0f - s * md_sum2(y, y, z, z); r.m[0][1] = s * md_diff2(x, y, w, z); r.m[0][2] = s * md_sum2(x, z, w, y);
+    r.m[1][0] = s * md_sum2(x, y, w, z); r.m[1][1] = 1.0f - s * md_sum2(x, x, z, z); r.m[1][2] = s * md_diff2(y, z, w, x);
+    r.m[2][0] = s * md_diff2(x, z, w, y); r.m[2][1] = s * md_sum2(y, z, w, x); r.m[2][2] = 1.0f - s * md_sum2(x, x, y, y);
     return r;
 }
 __device__ __forceinline__ F3 col(const M3& r, int c) { return f3(r.m[0][c], r.m[1][c], r.m[2][c]); }
 __device__ __forceinline__ F3 mul(const M3& r, F3 a) {
-    return f3(r.m[0][0] * a.x + r.m[0][1] * a.y + r.m[0][2] * a.z, r.m[1][0] * a.x + r.m[1][1] * a.y + r.m[1][2] * a.z,
-              r.m[2][0] * a.x + r.m[2][1] * a.y + r.m[2][2] * a.z);
+    return f3(md_dot3(r.m[0][0], r.m[0][1], r.m[0][2], a.x, a.y, a.z), md_dot3(r.m[1][0], r.m[1][1], r.m[1][2], a.x, a.y, a.z),
+              md_dot3(r.m[2][0], r.m[2][1], r.m[2][2], a.x, a.y, a.z));
 }
 __device__ __forceinline__ F3 tmul(const M3& r, F3 a) {
-    return f3(r.m[0][0] * a.x + r.m[1][0] * a.y + r.m[2][0] * a.z, r.m[0][1] * a.x + r.m[1][1] * a.y + r.m[2][1] * a.z,
-              r.m[0][2] * a.x + r.m[1][2] * a.y + r.m[2][2] * a.z);
+    return f3(md_dot3(r.m[0][0], r.m[1][0], r.m[2][0], a.x, a.y, a.z), md_dot3(r.m[0][1], r.m[1][1], r.m[2][1], a.x, a.y, a.z),
+              md_dot3(r.m[0][2], r.m[1][2], r.m[2][2], a.x, a.y, a.z));
 }
 __device__ __forceinline__ float clipf(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
 // utils/math.py:29-42
@@ -420,11 +420,11 @@ __device__ __forceinline__ void quat_integrate(float* q, F3 w, float dt) {
     else axis = w * (md_sinf(0.5f * ang * dt) / ang);
     float aw = md_cosf(ang * dt * 0.5f), ax = axis.x, ay = axis.y, az = axis.z;
     float bw = q[0], bx = q[1], by = q[2], bz = q[3];
-    float rw = aw * bw - ax * bx - ay * by - az * bz;
-    float rx = aw * bx + ax * bw + ay * bz - az * by;
-    float ry = aw * by - ax * bz + ay * bw + az * bx;
-    float rz = aw * bz + ax * by - ay * bx + az * bw;
-    float n = sqrtf(rw * rw + rx * rx + ry * ry + rz * rz);
+    float rw = md_dot4(aw, -ax, -ay, -az, bw, bx, by, bz);
+    float rx = md_dot4(aw, ax, ay, -az, bx, bw, bz, by);
+    float ry = md_dot4(aw, -ax, ay, az, by, bz, bw, bx);
+    float rz = md_dot4(aw, ax, -ay, az, bz, by, bx, bw);
+    float n = sqrtf(md_dot4(rw, rx, ry, rz, rw, rx, ry, rz));
     q[0] = rw / n; q[1] = rx / n; q[2] = ry / n; q[3] = rz / n;
 }
 
