@@ -102,8 +102,18 @@ def build_world(n_envs, rank, workload="cfg2"):
     from metadrive_ped_b200.library import ScenarioLibrary
     lib = ScenarioLibrary(w["lib"])
     idx = [(rank * n_envs + e) % len(lib) for e in range(n_envs)]
-    arrays, cfg = lib.build_world(idx, slots_per_env=None, num_pedestrians=w["peds"], seed=rank)
+    arrays, cfg = lib.build_world(idx, num_pedestrians=w["peds"], seed=rank, **bank_kw(lib, workload))
     return lib, arrays, cfg
+
+
+def bank_kw(lib, workload):
+    """Trigger-mode workloads resample the scenario at every reset, like `env.reset()` in the reference's profiling loop
+    (examples/profile_metadrive.py:26-29 -> envs/base_env.py:886-891): both the live world and the scenario bank load the
+    whole library's map set and use the library-wide slot / object capacity."""
+    if workload not in ("cfg2", "cfg4"):
+        return {}
+    return dict(slots_per_env=max(4, -(-lib.max_vehicles() // 4) * 4), objs_per_env=lib.max_objects(),
+                map_universe=list(range(len(lib))))
 
 
 def workload_name(workload="cfg2"):
@@ -156,6 +166,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--actions", default="profile", choices=["profile", "random"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-resample", action="store_true", help="finished envs replay their own scenario instead of drawing a new one")
     ap.add_argument("--burnin", type=int, default=150,
                     help="untimed setup steps (with auto-reset) so that envs sit at mixed episode phases")
     args = ap.parse_args()
@@ -180,6 +191,13 @@ def main():
     t_build = time.time()
     lib, arrays, cfg = build_world(E, rank, args.workload)
     sim = BatchedSim(arrays, cfg, device=local_rank)
+    resample = args.workload in ("cfg2", "cfg4") and not args.no_resample
+    if resample:  # the scenario bank: one env per library scenario, fully reset; finished envs draw their next scenario from it
+        b_arrays, b_cfg = lib.build_world(list(range(len(lib))), seed=rank, **bank_kw(lib, args.workload))
+        bank = BatchedSim(b_arrays, b_cfg, device=local_rank)
+        bank.reset()
+        sim.reset()
+        sim.attach_bank(bank, seed=1000 + rank)
     t_build = time.time() - t_build
     A = sim.n_agents
     kind = arrays["veh_i"][:, 0].reshape(E, cfg.slots_per_env)
@@ -301,7 +319,9 @@ def main():
                        "agents_per_env": cfg.agents_per_env - (1 if multi else 0), "live_agent_fraction": live_frac,
                        "slots_per_env": cfg.slots_per_env, "traffic_per_env_mean": traffic_per_env,
                        "distinct_scenarios": (E * world if multi else min(len(lib), E * world)), "actions": args.actions,
-                       "autoreset": "on device, inside the timed region", "l2": "flushed between steps (256 MiB memset, untimed)",
+                       "autoreset": "on device, inside the timed region" + (
+                           "; every reset draws a new scenario from the %d-scenario bank (md_attach_bank)" % len(lib) if resample else ""),
+                       "l2": "flushed between steps (256 MiB memset, untimed)",
                        "scene_build_s": round(t_build, 1), "burnin_steps": args.burnin},
             "lidar_rays_per_sec": value * cfg.n_lasers,
             "gpu_launches": int(launches),

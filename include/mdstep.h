@@ -91,6 +91,14 @@ int md_idm(md_sim* sim, float* out_actions_dev, void* stream);
  * name ("veh_s", "veh_i", "obj_f", ...); synchronous host <-> device copy of the whole array. */
 int md_get_state(md_sim* sim, const char* name, void* host_dst, size_t bytes);
 int md_set_state(md_sim* sim, const char* name, const void* host_src, size_t bytes);
+/* Scenario resampling at reset.  The reference draws a scenario per reset: BaseEnv.reset(seed=None) ->
+ * _reset_global_seed picks current_seed in [start_seed, start_seed + num_scenarios) (envs/base_env.py:502-537, 886-891), the
+ * map manager loads that map and the managers respawn their bodies.  Here `bank` is a second handle on the same device
+ * holding ONE ENV PER SCENARIO of the library, fully reset; after md_attach_bank a finished env of `sim` (md_step_autoreset)
+ * restarts as scenario hash(seed, env, episode) % n_bank by copying that scenario's rows from the bank's post-reset snapshot.
+ * Both handles must have loaded the same map set (same map ids) and the same slots / objects / agents per env; single-agent,
+ * trigger-mode worlds.  The bank must outlive `sim` (or be detached with bank = NULL).  Returns 0 or a negative code. */
+int md_attach_bank(md_sim* sim, md_sim* bank, int seed);
 /* make the current device state the snapshot md_reset restores */
 int md_snapshot(md_sim* sim);
 /* per-stage device timing of the next max_steps md_step / md_step_autoreset calls: six cudaEvents per call recorded on

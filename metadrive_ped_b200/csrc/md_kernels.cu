@@ -1162,6 +1162,62 @@ __global__ void k_restore_post(MdConfig cfg, MdArrays A, Snapshot post, const fl
         for (int k = 0; k < OBS_STATE(cfg); k++) obs[a * (size_t)OBS_DIM(cfg) + k] = post_obs[a * OBS_STATE(cfg) + k];
     }
 }
+// ---- scenario resampling at reset (BaseEnv.reset(seed=None) -> _reset_global_seed draws a scenario, envs/base_env.py:
+// 886-891).  The scenario BANK is a second handle holding one env per scenario of the library, fully reset: its
+// post-reset snapshot is the source of the rows.  k_pick_scenario draws a scenario for every finished env (a counter hash
+// instead of numpy's generator), k_restore_bank copies that scenario's rows into the env - everything that differs between
+// two scenarios: vehicle parameters, routes, trigger roads, state, objects, env row (map id, seed), body rows and the
+// state part of the reset observation.
+struct BankView {
+    Snapshot post;
+    const float* body; const float* obs; const float* veh_p; const int* env_trigger;
+    int n;
+};
+__global__ void k_pick_scenario(int n_envs, int n_bank, uint32_t seed, const uint8_t* __restrict__ env_mask,
+                                int* __restrict__ env_episode, int* __restrict__ env_scn) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n_envs || env_mask[env] == 0) return;
+    const uint32_t ep = (uint32_t)(++env_episode[env]);
+    uint32_t x = seed * 0x9E3779B9u + (uint32_t)env * 0x85EBCA6Bu + ep * 0xC2B2AE35u + 0x165667B1u;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    env_scn[env] = (int)(x % (uint32_t)n_bank);
+}
+__global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, const int* __restrict__ env_scn, float* __restrict__ body_tab,
+                               float* __restrict__ obs, const uint8_t* __restrict__ env_mask) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
+    if (g >= (long long)cfg.n_envs * S) return;
+    const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
+    if (env_mask[env] == 0) return;
+    const int scn = env_scn[env];
+    const size_t b = (size_t)scn * S + slot;   // source row in the bank
+#define COPY4(dst, src, n4)                                                                            \
+    {                                                                                                  \
+        const int4* s4_ = reinterpret_cast<const int4*>(src);                                          \
+        int4* d4_ = reinterpret_cast<int4*>(dst);                                                      \
+        _Pragma("unroll") for (int k_ = 0; k_ < (n4); k_++) d4_[k_] = s4_[k_];                         \
+    }
+    COPY4(A.veh_s + (size_t)g * VEH_S, B.post.veh_s + b * VEH_S, VEH_S / 4)
+    COPY4(A.veh_c + (size_t)g * VEH_C, B.post.veh_c + b * VEH_C, VEH_C / 4)
+    COPY4(A.veh_i + (size_t)g * VEH_I, B.post.veh_i + b * VEH_I, VEH_I / 4)
+    COPY4(A.veh_idm + (size_t)g * VEH_IDM, B.post.veh_idm + b * VEH_IDM, VEH_IDM / 4)
+    COPY4(const_cast<float*>(A.veh_p) + (size_t)g * VEH_P, B.veh_p + b * VEH_P, VEH_P / 4)
+    COPY4(A.veh_route + (size_t)g * ROUTE_MAX, B.post.veh_route + b * ROUTE_MAX, ROUTE_MAX / 4)
+    COPY4(A.veh_rroad + (size_t)g * ROUTE_MAX, B.post.veh_rroad + b * ROUTE_MAX, ROUTE_MAX / 4)
+    COPY4(body_tab + (size_t)g * BODY_ROW, B.body + b * BODY_ROW, BODY_ROW / 4)
+#undef COPY4
+    for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = B.post.veh_navi[b * NAVI_DIM + k];
+    for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = B.post.obj_f[(size_t)scn * O * OBJ_F + k];
+    if (slot == 0) {
+        for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = B.post.env_i[scn * ENV_I + k];
+        int* trig = const_cast<int*>(A.env_trigger);
+        for (int k = 0; k < TRIGGER_MAX; k++) trig[env * TRIGGER_MAX + k] = B.env_trigger[scn * TRIGGER_MAX + k];
+    }
+    if (slot < NA) {
+        const size_t a = (size_t)env * NA + slot, ab = (size_t)scn * NA + slot;
+        for (int k = 0; k < OBS_STATE(cfg); k++) obs[a * (size_t)OBS_DIM(cfg) + k] = B.obs[ab * OBS_STATE(cfg) + k];
+    }
+}
 __global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t* __restrict__ env_mask) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)cfg.n_envs * cfg.slots_per_env) return;
@@ -1892,6 +1948,9 @@ struct md_sim {
     int32_t* d_info_flags;
     int64_t launches;
     uint32_t noise_pass;   // observation passes so far: the counter of the lidar noise hash
+    md_sim* bank;          // scenario bank (md_attach_bank): finished envs restart as a scenario drawn from it
+    uint32_t bank_seed;
+    int *env_episode, *env_scn;   // [E] episodes started so far / scenario (bank row) the env currently plays
     bool loaded;
     // optional per-kernel timing: 3 events per md_step on the launch stream (bench.py's roofline leg)
     std::vector<cudaEvent_t> prof_ev;
@@ -1938,6 +1997,7 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     sim->post_valid = false;
     sim->launches = 0;
     sim->noise_pass = 0;
+    sim->bank = nullptr; sim->bank_seed = 0; sim->env_episode = nullptr; sim->env_scn = nullptr;
     sim->prof_cap = 0;
     sim->prof_n = 0;
     memset(&sim->dev, 0, sizeof(sim->dev));
@@ -1986,6 +2046,7 @@ extern "C" void md_destroy(md_sim* sim) {
         for (int i = 0; i < N_SNAP; i++) { cudaFree(sim->snap_bufs[i]); cudaFree(sim->post_bufs[i]); }
         cudaFree(sim->post_body); cudaFree(sim->post_obs);
         cudaFree(sim->body_tab); cudaFree(sim->veh_act); cudaFree(sim->mask);
+        cudaFree(sim->env_episode); cudaFree(sim->env_scn);
         cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_reward); cudaFreeHost(sim->h_cost);
         cudaFreeHost(sim->h_info_f); cudaFreeHost(sim->h_term); cudaFreeHost(sim->h_trunc); cudaFreeHost(sim->h_mask);
         cudaFreeHost(sim->h_info_flags);
@@ -2249,7 +2310,18 @@ static int step_impl(md_sim* sim, const float* actions_dev, StepOut out, cudaStr
     if (prof) CK(cudaEventRecord(ev[2], st));
     if (launch_post(sim, MODE_POST | MODE_OUT | MODE_REMOVE | (fused_reset ? MODE_MARK_DONE : 0), out, nullptr, st)) return -1;
     if (prof) CK(cudaEventRecord(ev[3], st));
-    if (fused_reset && sim->post_valid) {
+    if (fused_reset && sim->post_valid && sim->bank) {
+        const MdConfig& c = sim->cfg;
+        const md_sim* bk = sim->bank;
+        const long long nv = (long long)c.n_envs * c.slots_per_env;
+        BankView B;
+        B.post = bk->post; B.body = bk->post_body; B.obs = bk->post_obs; B.veh_p = bk->dev.veh_p;
+        B.env_trigger = bk->dev.env_trigger; B.n = bk->cfg.n_envs;
+        k_pick_scenario<<<(c.n_envs + 255) / 256, 256, 0, st>>>(c.n_envs, B.n, sim->bank_seed, sim->mask, sim->env_episode, sim->env_scn);
+        k_restore_bank<<<(int)((nv + 255) / 256), 256, 0, st>>>(c, sim->dev, B, sim->env_scn, sim->body_tab, out.obs, sim->mask);
+        sim->launches += 2;
+        CK(cudaGetLastError());
+    } else if (fused_reset && sim->post_valid) {
         const long long nv = (long long)sim->cfg.n_envs * sim->cfg.slots_per_env;
         k_restore_post<<<(int)((nv + 255) / 256), 256, 0, st>>>(sim->cfg, sim->dev, sim->post, sim->post_body, sim->post_obs,
                                                                sim->body_tab, out.obs, sim->mask);
@@ -2295,6 +2367,34 @@ extern "C" int md_step_autoreset(md_sim* sim, const float* actions_dev, float* o
         return step_impl(sim, actions_dev, out, (cudaStream_t)stream, true);
     if (step_impl(sim, actions_dev, out, (cudaStream_t)stream, false)) return -1;
     return md_autoreset(sim, terminated_dev, truncated_dev, obs_dev, stream);
+}
+
+extern "C" int md_attach_bank(md_sim* sim, md_sim* bank, int seed) {
+    if (!sim || !sim->loaded) return -2;
+    if (!bank) { sim->bank = nullptr; return 0; }
+    if (!bank->loaded || !bank->post_valid) { sim->err = "the scenario bank must be loaded and fully reset (md_reset with a NULL mask)"; return -2; }
+    const MdConfig &a = sim->cfg, &b = bank->cfg;
+    if (bank->device != sim->device || a.slots_per_env != b.slots_per_env || a.objs_per_env != b.objs_per_env ||
+        a.agents_per_env != b.agents_per_env || a.n_lasers != b.n_lasers || a.n_side_lasers != b.n_side_lasers ||
+        a.n_lane_lasers != b.n_lane_lasers || a.num_others != b.num_others) {
+        sim->err = "scenario bank: device, slots / objects / agents per env and the observation layout must match";
+        return -2;
+    }
+    if (a.is_multi_agent || a.traffic_mode != 0 || b.traffic_mode != 0) {
+        sim->err = "scenario bank: single-agent, trigger-mode worlds only (respawn-mode tables are per env)";
+        return -2;
+    }
+    if (sim->bytes[0] != bank->bytes[0]) { sim->err = "scenario bank: both handles must load the same map set (same map ids)"; return -2; }
+    CK(cudaSetDevice(sim->device));
+    if (!sim->env_episode) {
+        CK(cudaMalloc(&sim->env_episode, sizeof(int) * (size_t)a.n_envs));
+        CK(cudaMalloc(&sim->env_scn, sizeof(int) * (size_t)a.n_envs));
+    }
+    CK(cudaMemset(sim->env_episode, 0, sizeof(int) * (size_t)a.n_envs));
+    CK(cudaMemset(sim->env_scn, 0xff, sizeof(int) * (size_t)a.n_envs));
+    sim->bank = bank;
+    sim->bank_seed = (uint32_t)seed;
+    return 0;
 }
 
 // per-kernel device timing of the next `max_steps` md_step calls (events on the launch stream, no sync added)

@@ -320,7 +320,10 @@ class SafeMetaDriveEnv(MetaDriveEnv):
 class BatchedMetaDriveEnv:
     """E independent MetaDriveEnv instances stepped per call, device tensors in and out (the fast path the Gym dict
     surface cannot offer at 10^6+ steps/s).  Finished envs reset in place on device."""
-    def __init__(self, num_envs, config=None, env_cls=MetaDriveEnv, rank=0):
+    def __init__(self, num_envs, config=None, env_cls=MetaDriveEnv, rank=0, resample_scenarios=False):
+        """`resample_scenarios`: like BaseEnv.reset(seed=None) (envs/base_env.py:886-891), a finished env restarts in a
+        scenario drawn from [start_seed, start_seed + num_scenarios) instead of replaying its own - on device, from a
+        scenario bank (sim.attach_bank)."""
         from .shard import shard_scenarios
         from .sim import BatchedSim
         proto = env_cls(config)
@@ -328,8 +331,17 @@ class BatchedMetaDriveEnv:
         first = lib.index_of_seed(proto.start_seed)
         n = min(proto.num_scenarios, len(lib) - first)
         idx = [first + i for i in shard_scenarios(n, num_envs, rank)]
-        arrays, cfg = lib.build_world(idx, num_pedestrians=proto.config["num_pedestrians"], seed=rank, **proto._cfg_kw())
+        universe = list(range(first, first + n)) if resample_scenarios else None
+        S = max(4, -(-lib.max_vehicles() // 4) * 4) if resample_scenarios else None
+        O = lib.max_objects() if resample_scenarios else None
+        kw = dict(slots_per_env=S, objs_per_env=O, num_pedestrians=proto.config["num_pedestrians"], map_universe=universe)
+        arrays, cfg = lib.build_world(idx, seed=rank, **kw, **proto._cfg_kw())
         self.sim = BatchedSim(arrays, cfg, device=proto.config["device"])
+        if resample_scenarios:
+            b_arrays, b_cfg = lib.build_world(universe, seed=rank, **kw, **proto._cfg_kw())
+            self.bank = BatchedSim(b_arrays, b_cfg, device=proto.config["device"])
+            self.bank.reset()
+            self.sim.attach_bank(self.bank, seed=proto.start_seed + 7919 * rank)
         self.num_envs = num_envs
         self.observation_space, self.action_space = proto.observation_space, proto.action_space
 
@@ -342,6 +354,8 @@ class BatchedMetaDriveEnv:
 
     def close(self):
         self.sim.close()
+        if getattr(self, "bank", None) is not None:
+            self.bank.close()
 
 
 # ------------------------------------------------------------------------------------------------ multi-agent

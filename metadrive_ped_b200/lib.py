@@ -14,7 +14,7 @@ EXPORTS = [
     "md_abi_version", "md_create", "md_destroy", "md_last_error", "md_load_scene", "md_reset", "md_step",
     "md_autoreset", "md_step_autoreset", "md_step_host", "md_reset_host", "md_lidar", "md_dynamics", "md_after_step", "md_idm",
     "md_get_state", "md_set_state", "md_snapshot", "md_launch_count", "md_profile_begin", "md_profile_end",
-    "md_host_views",
+    "md_host_views", "md_attach_bank",
 ]
 
 
@@ -52,6 +52,7 @@ def load():
     lib.md_last_error.restype = C.c_char_p
     lib.md_load_scene.argtypes = [vp, C.POINTER(MdArrays), C.POINTER(C.c_int64)]
     lib.md_reset.argtypes = [vp, vp, vp, vp]
+    lib.md_attach_bank.argtypes = [vp, vp, ip]
     lib.md_step.argtypes = [vp] + [vp] * 8 + [vp]
     lib.md_autoreset.argtypes = [vp, vp, vp, vp, vp]
     lib.md_step_autoreset.argtypes = [vp] + [vp] * 8 + [vp]

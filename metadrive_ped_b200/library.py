@@ -80,12 +80,15 @@ class ScenarioLibrary:
     def max_objects(self):
         return int(self.obj_off[:, 1].max())
 
-    def build_world(self, indices, slots_per_env=None, objs_per_env=None, num_pedestrians=0, seed=0, **cfg_kw):
+    def build_world(self, indices, slots_per_env=None, objs_per_env=None, num_pedestrians=0, seed=0, map_universe=None,
+                    **cfg_kw):
         """(arrays, cfg) for one env per entry of `indices` (library indices, repeats allowed).  `num_pedestrians` > 0
-        adds that many crossing pedestrians per env (peds.py, BASELINE config 5), drawn with `seed`."""
+        adds that many crossing pedestrians per env (peds.py, BASELINE config 5), drawn with `seed`.  `map_universe`
+        (library indices) fixes the loaded map set and its numbering: two worlds built with the same universe share
+        their map ids, which is what a scenario bank needs (sim.attach_bank)."""
         from . import ma, peds
         indices = [int(i) for i in indices]
-        uniq = list(dict.fromkeys(indices))
+        uniq = list(dict.fromkeys([int(i) for i in (map_universe or [])] + indices))
         geos = self.geometries(uniq)
         map_id = {i: k for k, i in enumerate(uniq)}
         scen_cache = {i: self.scenario(i, map_id[i]) for i in uniq}

@@ -143,6 +143,12 @@ class BatchedSim:
         self.torch.cuda.synchronize(self.tdev)
         self._check(self.lib.md_set_state(self.h, name.encode(), v.ctypes.data_as(C.c_void_p), v.nbytes))
 
+    def attach_bank(self, bank, seed=0):
+        """Finished envs restart as a scenario drawn from `bank` (a fully reset BatchedSim with one env per scenario of
+        the library, same map set); see md_attach_bank in include/mdstep.h.  The bank is kept alive by this object."""
+        self._check(self.lib.md_attach_bank(self.h, bank.h if bank is not None else None, int(seed)))
+        self._bank = bank
+
     def snapshot(self):
         self._check(self.lib.md_snapshot(self.h))
 

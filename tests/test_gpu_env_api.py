@@ -275,3 +275,66 @@ def test_lidar_noise_and_dropout():
     obs, _ = env.reset(seed=1)
     assert obs.shape == (259, ) and (obs[19:] == 0.0).sum() > 20
     env.close()
+
+
+def test_scenario_resampling_on_device(oracle_lib):
+    """md_attach_bank: a finished env restarts in a scenario DRAWN from the library (BaseEnv.reset(seed=None),
+    envs/base_env.py:886-891) by a row copy from the scenario bank.  Checked against the oracle, which is handed the
+    scenario the device drew (the draw replaces numpy's generator and is not part of the parity) and must then stay
+    bit-identical - so every array that differs between two scenarios has to be part of the copy."""
+    import torch
+    from metadrive_ped_b200.library import ScenarioLibrary
+    from metadrive_ped_b200.sim import BatchedSim
+    from oracle.oracle import OracleSim
+    lib = ScenarioLibrary("pg3_density0.1.npz")
+    B, E = 48, 192
+    universe = list(range(B))
+    S = max(4, -(-lib.max_vehicles() // 4) * 4)
+    kw = dict(slots_per_env=S, objs_per_env=0, map_universe=universe)
+    b_arrays, b_cfg = lib.build_world(universe, **kw)
+    arrays, cfg = lib.build_world([e % B for e in range(E)], **kw)
+    bank, sim = BatchedSim(b_arrays, b_cfg), BatchedSim(arrays, cfg)
+    bank.reset()
+    sim.reset()
+    sim.attach_bank(bank, seed=5)
+    orc, borc = OracleSim(arrays, cfg), OracleSim(b_arrays, b_cfg)
+    orc.reset_observe()
+    b_obs0 = borc.reset_observe().copy()
+    MUT = ("env_i", "veh_s", "veh_c", "veh_i", "veh_idm", "veh_navi", "veh_route", "veh_rroad", "veh_p", "env_trigger")
+    rows = {"env_i": 1, "env_trigger": 1}
+    act = np.tile(np.array([0.0, 1.0], np.float32), (E, 1))
+    act_d = torch.from_numpy(act).cuda()
+    n_reset, seen = 0, set()
+    for t in range(160):
+        sim.step(act_d, autoreset=True)
+        orc.step(act)
+        done = (orc.term | orc.trunc).astype(bool)
+        np.testing.assert_array_equal(sim.terminated.cpu().numpy(), orc.term)
+        np.testing.assert_array_equal(sim.truncated.cpu().numpy(), orc.trunc)
+        oo = orc.obs.copy()
+        env_i = sim.get_state("env_i")
+        for e in np.nonzero(done)[0]:
+            scn = int(env_i[e, 0])          # EI_MAP = the bank row (the bank lists the universe in order)
+            assert 0 <= scn < B and int(env_i[e, 4]) == int(lib.seeds[scn])   # EI_SEED
+            seen.add(scn)
+            n_reset += 1
+            for k in MUT:
+                r = rows.get(k, S)
+                orc.a[k][e * r:(e + 1) * r] = borc.a[k][scn * r:(scn + 1) * r]
+            oo[e] = b_obs0[scn]
+        for k in MUT:
+            np.testing.assert_array_equal(sim.get_state(k), orc.a[k], err_msg="%s at step %d" % (k, t))
+        np.testing.assert_array_equal(sim.obs.cpu().numpy(), oo, err_msg="observation at step %d" % t)
+    assert n_reset >= E // 2 and len(seen) >= B // 2, (n_reset, len(seen))
+    sim.close()
+    bank.close()
+    from metadrive_ped_b200 import BatchedMetaDriveEnv
+    env = BatchedMetaDriveEnv(64, dict(map=3, num_scenarios=32, start_seed=0), resample_scenarios=True)
+    env.reset()
+    a = torch.tensor([0.0, 1.0], device="cuda").repeat(64, 1).contiguous()
+    seeds0 = env.sim.get_state("env_i")[:, 4].copy()
+    for _ in range(150):
+        env.step(a)
+    seeds1 = env.sim.get_state("env_i")[:, 4]
+    assert (seeds1 != seeds0).sum() >= 16 and seeds1.min() >= 0 and seeds1.max() < 32
+    env.close()
