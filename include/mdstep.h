@@ -95,7 +95,7 @@ int md_set_state(md_sim* sim, const char* name, const void* host_src, size_t byt
  * _reset_global_seed picks current_seed in [start_seed, start_seed + num_scenarios) (envs/base_env.py:502-537, 886-891), the
  * map manager loads that map and the managers respawn their bodies.  Here `bank` is a second handle on the same device
  * holding ONE ENV PER SCENARIO of the library, fully reset; after md_attach_bank a finished env of `sim` (md_step_autoreset)
- * restarts as scenario hash(seed, env, episode) % n_bank by copying that scenario's rows from the bank's post-reset snapshot.
+ * restarts as scenario hash(seed, env, reset pass) % n_bank by copying that scenario's rows from the bank's post-reset snapshot.
  * Both handles must have loaded the same map set (same map ids) and the same slots / objects / agents per env; single-agent,
  * trigger-mode worlds.  The bank must outlive `sim` (or be detached with bank = NULL).  Returns 0 or a negative code. */
 int md_attach_bank(md_sim* sim, md_sim* bank, int seed);

@@ -1164,8 +1164,8 @@ __global__ void k_restore_post(MdConfig cfg, MdArrays A, Snapshot post, const fl
 }
 // ---- scenario resampling at reset (BaseEnv.reset(seed=None) -> _reset_global_seed draws a scenario, envs/base_env.py:
 // 886-891).  The scenario BANK is a second handle holding one env per scenario of the library, fully reset: its
-// post-reset snapshot is the source of the rows.  k_pick_scenario draws a scenario for every finished env (a counter hash
-// instead of numpy's generator), k_restore_bank copies that scenario's rows into the env - everything that differs between
+// post-reset snapshot is the source of the rows.  k_restore_bank draws a scenario for every finished env (a counter hash
+// instead of numpy's generator) and copies that scenario's rows into the env - everything that differs between
 // two scenarios: vehicle parameters, routes, trigger roads, state, objects, env row (map id, seed), body rows and the
 // state part of the reset observation.
 struct BankView {
@@ -1173,23 +1173,17 @@ struct BankView {
     const float* body; const float* obs; const float* veh_p; const int* env_trigger;
     int n;
 };
-__global__ void k_pick_scenario(int n_envs, int n_bank, uint32_t seed, const uint8_t* __restrict__ env_mask,
-                                int* __restrict__ env_episode, int* __restrict__ env_scn) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= n_envs || env_mask[env] == 0) return;
-    const uint32_t ep = (uint32_t)(++env_episode[env]);
-    uint32_t x = seed * 0x9E3779B9u + (uint32_t)env * 0x85EBCA6Bu + ep * 0xC2B2AE35u + 0x165667B1u;
-    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-    env_scn[env] = (int)(x % (uint32_t)n_bank);
-}
-__global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, const int* __restrict__ env_scn, float* __restrict__ body_tab,
+__global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, uint32_t seed, uint32_t pass, float* __restrict__ body_tab,
                                float* __restrict__ obs, const uint8_t* __restrict__ env_mask) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     if (g >= (long long)cfg.n_envs * S) return;
     const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
     if (env_mask[env] == 0) return;
-    const int scn = env_scn[env];
+    // the draw: a counter hash of (seed, env, reset pass) - every thread of the env computes the same scenario
+    uint32_t x = seed * 0x9E3779B9u + (uint32_t)env * 0x85EBCA6Bu + pass * 0xC2B2AE35u + 0x165667B1u;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    const int scn = (int)(x % (uint32_t)B.n);
     const size_t b = (size_t)scn * S + slot;   // source row in the bank
 #define COPY4(dst, src, n4)                                                                            \
     {                                                                                                  \
@@ -1949,8 +1943,7 @@ struct md_sim {
     int64_t launches;
     uint32_t noise_pass;   // observation passes so far: the counter of the lidar noise hash
     md_sim* bank;          // scenario bank (md_attach_bank): finished envs restart as a scenario drawn from it
-    uint32_t bank_seed;
-    int *env_episode, *env_scn;   // [E] episodes started so far / scenario (bank row) the env currently plays
+    uint32_t bank_seed, bank_pass;   // the scenario draw is a hash of (seed, env, reset pass)
     bool loaded;
     // optional per-kernel timing: 3 events per md_step on the launch stream (bench.py's roofline leg)
     std::vector<cudaEvent_t> prof_ev;
@@ -1997,7 +1990,7 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     sim->post_valid = false;
     sim->launches = 0;
     sim->noise_pass = 0;
-    sim->bank = nullptr; sim->bank_seed = 0; sim->env_episode = nullptr; sim->env_scn = nullptr;
+    sim->bank = nullptr; sim->bank_seed = 0; sim->bank_pass = 0;
     sim->prof_cap = 0;
     sim->prof_n = 0;
     memset(&sim->dev, 0, sizeof(sim->dev));
@@ -2046,7 +2039,6 @@ extern "C" void md_destroy(md_sim* sim) {
         for (int i = 0; i < N_SNAP; i++) { cudaFree(sim->snap_bufs[i]); cudaFree(sim->post_bufs[i]); }
         cudaFree(sim->post_body); cudaFree(sim->post_obs);
         cudaFree(sim->body_tab); cudaFree(sim->veh_act); cudaFree(sim->mask);
-        cudaFree(sim->env_episode); cudaFree(sim->env_scn);
         cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_reward); cudaFreeHost(sim->h_cost);
         cudaFreeHost(sim->h_info_f); cudaFreeHost(sim->h_term); cudaFreeHost(sim->h_trunc); cudaFreeHost(sim->h_mask);
         cudaFreeHost(sim->h_info_flags);
@@ -2317,9 +2309,8 @@ static int step_impl(md_sim* sim, const float* actions_dev, StepOut out, cudaStr
         BankView B;
         B.post = bk->post; B.body = bk->post_body; B.obs = bk->post_obs; B.veh_p = bk->dev.veh_p;
         B.env_trigger = bk->dev.env_trigger; B.n = bk->cfg.n_envs;
-        k_pick_scenario<<<(c.n_envs + 255) / 256, 256, 0, st>>>(c.n_envs, B.n, sim->bank_seed, sim->mask, sim->env_episode, sim->env_scn);
-        k_restore_bank<<<(int)((nv + 255) / 256), 256, 0, st>>>(c, sim->dev, B, sim->env_scn, sim->body_tab, out.obs, sim->mask);
-        sim->launches += 2;
+        k_restore_bank<<<(int)((nv + 255) / 256), 256, 0, st>>>(c, sim->dev, B, sim->bank_seed, sim->bank_pass++, sim->body_tab, out.obs, sim->mask);
+        sim->launches++;
         CK(cudaGetLastError());
     } else if (fused_reset && sim->post_valid) {
         const long long nv = (long long)sim->cfg.n_envs * sim->cfg.slots_per_env;
@@ -2385,15 +2376,9 @@ extern "C" int md_attach_bank(md_sim* sim, md_sim* bank, int seed) {
         return -2;
     }
     if (sim->bytes[0] != bank->bytes[0]) { sim->err = "scenario bank: both handles must load the same map set (same map ids)"; return -2; }
-    CK(cudaSetDevice(sim->device));
-    if (!sim->env_episode) {
-        CK(cudaMalloc(&sim->env_episode, sizeof(int) * (size_t)a.n_envs));
-        CK(cudaMalloc(&sim->env_scn, sizeof(int) * (size_t)a.n_envs));
-    }
-    CK(cudaMemset(sim->env_episode, 0, sizeof(int) * (size_t)a.n_envs));
-    CK(cudaMemset(sim->env_scn, 0xff, sizeof(int) * (size_t)a.n_envs));
     sim->bank = bank;
     sim->bank_seed = (uint32_t)seed;
+    sim->bank_pass = 0;
     return 0;
 }
 
