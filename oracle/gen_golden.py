@@ -411,6 +411,17 @@ def main():
         np.savez_compressed(path, **out)
         print("cfg3_ma_roundabout_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
               "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
+    # the other shipped multi-agent map (envs/marl_envs/marl_intersection.py): same seats / respawn bookkeeping on the X block
+    if not args.only or args.only == "cfg3_ma_intersection_respawn":
+        from metadrive.envs.marl_envs.marl_intersection import MultiAgentIntersectionEnv
+        lid = dict(vehicle_config=dict(lidar=dict(num_lasers=240, distance=50, num_others=0)))
+        cfgi = dict(num_agents=10, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, **lid)
+        out = run_episode_ma(MultiAgentIntersectionEnv, cfgi, None, "cfg3_ma_intersection_respawn", steps=300,
+                             noise=args.ma_noise, seed=7, obs_stride=3)
+        path = os.path.join(args.out, "cfg3_ma_intersection_respawn.npz")
+        np.savez_compressed(path, **out)
+        print("cfg3_ma_intersection_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
+              "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     # BASELINE config 5 (composed): X map, respawn-mode IDM traffic, 16 crossing pedestrians; crashes do not end the
     # episode here so that the trace keeps running through pedestrian / vehicle contacts
     if not args.only or args.only == "cfg5_ped_X":
