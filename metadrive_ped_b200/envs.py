@@ -43,6 +43,21 @@ UNSUPPORTED_TRUE = ("use_render", "image_observation", "manual_control", "random
                     "need_inverse_traffic", "random_traffic")
 
 
+VP_REVERSE = 15  # include/md_layout.h: column of veh_p
+
+
+def _apply_vehicle_config(arrays, config):
+    """Per-agent vehicle_config entries that act on the step path are written over the library's rows: enable_reverse
+    (component/vehicle/base_vehicle.py:157, 479-481).  The library was exported with the reference's defaults."""
+    vc = config["vehicle_config"]
+    if vc["vehicle_model"] not in ("default", "static_default"):
+        raise NotImplementedError("vehicle_model %r: the shipped libraries hold the default agent vehicle" % vc["vehicle_model"])
+    agents = arrays["veh_i"][:, 0] == 1
+    arrays["veh_p"] = np.array(arrays["veh_p"], np.float32, copy=True)
+    arrays["veh_p"][agents, VP_REVERSE] = 1.0 if vc["enable_reverse"] else 0.0
+    return arrays
+
+
 class Box:
     """Minimal gymnasium.spaces.Box stand-in used when gymnasium is not installed (same fields / contains)."""
     def __init__(self, low, high, shape, dtype=np.float32):
@@ -258,6 +273,7 @@ class MetaDriveEnv:
         if seed not in self._sims:
             arrays, cfg = lib.build_world([lib.index_of_seed(seed)], num_pedestrians=self.config["num_pedestrians"],
                                           seed=seed, **self._cfg_kw())
+            _apply_vehicle_config(arrays, self.config)
             self._sims[seed] = BatchedSim(arrays, cfg, device=self.config["device"])
         self._sim = self._sims[seed]
         self.current_seed = seed
@@ -336,9 +352,11 @@ class BatchedMetaDriveEnv:
         O = lib.max_objects() if resample_scenarios else None
         kw = dict(slots_per_env=S, objs_per_env=O, num_pedestrians=proto.config["num_pedestrians"], map_universe=universe)
         arrays, cfg = lib.build_world(idx, seed=rank, **kw, **proto._cfg_kw())
+        _apply_vehicle_config(arrays, proto.config)
         self.sim = BatchedSim(arrays, cfg, device=proto.config["device"])
         if resample_scenarios:
             b_arrays, b_cfg = lib.build_world(universe, seed=rank, **kw, **proto._cfg_kw())
+            _apply_vehicle_config(b_arrays, proto.config)
             self.bank = BatchedSim(b_arrays, b_cfg, device=proto.config["device"])
             self.bank.reset()
             self.sim.attach_bank(self.bank, seed=proto.start_seed + 7919 * rank)
@@ -430,6 +448,7 @@ class MultiAgentMetaDrive:
         rs = (seed if seed is not None else self.config["start_seed"]) * 1000003 + self._episode
         self._episode += 1
         arrays, cfg = self._lib.build_world(1, self.num_agents, seed=rs, **_ma_cfg_kw(self.config))
+        _apply_vehicle_config(arrays, self.config)
         self._sim = BatchedSim(arrays, cfg, device=self.config["device"])
         self._seat_id = ["agent%d" % k for k in range(self.num_agents)] + [None]
         self._next_id = self.num_agents
@@ -517,6 +536,7 @@ class BatchedMultiAgentEnv:
         lib = MultiAgentLibrary(env_cls.ASSET)
         n = c["num_agents"] if c["num_agents"] != -1 else lib.max_capacity
         arrays, cfg = lib.build_world(num_envs, n, seed=seed, **_ma_cfg_kw(c))
+        _apply_vehicle_config(arrays, c)
         self.sim = BatchedSim(arrays, cfg, device=c["device"])
         self.num_envs, self.seats = num_envs, n + 1
 

@@ -338,3 +338,27 @@ def test_scenario_resampling_on_device(oracle_lib):
     seeds1 = env.sim.get_state("env_i")[:, 4]
     assert (seeds1 != seeds0).sum() >= 16 and seeds1.min() >= 0 and seeds1.max() < 32
     env.close()
+
+
+def test_enable_reverse():
+    """vehicle_config.enable_reverse (base_vehicle.py:479-481): a negative throttle drives the engine backwards instead of
+    braking.  Default: the car brakes to a stop and stays; with reverse it ends up moving backwards."""
+    from metadrive_ped_b200 import MetaDriveEnv
+    out = {}
+    for rev in (False, True):
+        env = MetaDriveEnv(dict(map=3, num_scenarios=10, traffic_density=0.1, vehicle_config=dict(enable_reverse=rev)))
+        env.reset(seed=2)
+        x0 = np.array(env.agent.position)
+        for _ in range(15):
+            env.step([0.0, 1.0])
+        x1 = np.array(env.agent.position)
+        for _ in range(60):
+            obs, r, te, tr, info = env.step([0.0, -1.0])
+            if te or tr:
+                break
+        x2 = np.array(env.agent.position)
+        fwd = (x1 - x0) / np.linalg.norm(x1 - x0)
+        out[rev] = float((x2 - x1) @ fwd), float(info["velocity"])
+        env.close()
+    assert out[False][0] > 0.0 and abs(out[False][1]) < 0.5          # braked to a stop ahead of where braking began
+    assert out[True][0] < out[False][0] - 3.0 and out[True][1] > 1.0  # rolled back past it, still moving (speed is unsigned)
