@@ -218,14 +218,17 @@ class MetaDriveEnv:
     # -- scenes
     def _library(self):
         if self._lib is None:
-            want = dict(map=self.config["map"], traffic_density=self.config["traffic_density"],
-                        traffic_mode=self.config["traffic_mode"])
+            # every key that shapes the scene at reset must be the one the library was exported with (keys absent from
+            # the export's config were left at this env class's defaults)
+            scene_keys = ("map", "traffic_density", "traffic_mode", "accident_prob", "static_traffic_object",
+                          "random_spawn_lane_index")
+            dflt = self.default_config()
+            want = {k: self.config[k] for k in scene_keys}
             tried = []
             for name in self.LIBRARIES:
                 lib = ScenarioLibrary(name)
                 lc = lib.config
-                have = dict(map=lc.get("map"), traffic_density=lc.get("traffic_density", self.default_config()["traffic_density"]),
-                            traffic_mode=lc.get("traffic_mode", "trigger"))
+                have = {k: lc.get(k, dflt[k]) for k in scene_keys}
                 if want == have:
                     self._lib = lib
                     break
