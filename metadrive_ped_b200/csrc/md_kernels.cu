@@ -331,58 +331,97 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
 #undef IN_CUR
 }
 
+// What the candidate scan of update_localization leaves behind for one vehicle: whether any lane hull contains the centre,
+// and the nearest lane (lane.distance) overall / among the current reference lanes / among the next road's lanes.  A slot
+// without a lane has best = -1.  The scan of one vehicle can be spread over the lanes of a sub-warp team (k_post phase
+// 2a): a (distance, lane id) lexicographic minimum reproduces the serial scan, which walks ascending lane ids with `<`.
+struct __align__(16) LocScan {
+    float d_any, lon_any, lat_any; int best_any;
+    float d_cur, lon_cur, lat_cur; int best_cur;
+    float d_next, lon_next, lat_next; int best_next;
+    int on_lane, static_flags, contact_flags, pad;
+};
+struct LocCtx { float px, py, hx, hy; int cur_first, cur_n, next_road, nx_first, nx_n; };
+__device__ __forceinline__ void loc_scan_init(LocScan& s) {
+    s.d_any = s.d_cur = s.d_next = 1e30f;
+    s.best_any = s.best_cur = s.best_next = -1;
+    s.lon_any = s.lat_any = s.lon_cur = s.lat_cur = s.lon_next = s.lat_next = 0.0f;
+    s.on_lane = 0; s.static_flags = 0; s.contact_flags = 0; s.pad = 0;
+}
+// one candidate lane of the grid cell under the vehicle (ray_localization, utils/pg/utils.py:151-203, answered by AABB ->
+// point-in-convex-hull; lane choice of node_network_navigation.py:219-241)
+__device__ __forceinline__ void loc_candidate(const MapView& m, const LocCtx& c, int l, LocScan& s) {
+    const float px = c.px, py = c.py;
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(m.lane_bb) + l);
+    if (px < bb.x || py < bb.y || px > bb.z || py > bb.w) return;
+    const float* Ll = m.lane_f + l * LANE_F;
+    if (Ll[LF_TYPE] != 0.0f) {  // hull_shortcut's radial rejection, before paying for the arc coordinates (atan2)
+        const float ro = Ll[LF_P0 + 2] + 0.5f * Ll[LF_WIDTH];
+        const float ddx = px - Ll[LF_P0 + 0], ddy = py - Ll[LF_P0 + 1];
+        if (ddx * ddx + ddy * ddy > ro * ro + 1.0f + 0.5f * ro) return;
+    }
+    float lon, lat;
+    lane_local(Ll, px, py, lon, lat);
+    const int sc = hull_shortcut(Ll, px, py, lon, lat);
+    if (sc < 0) return;
+    if (sc == 0 &&
+        !point_in_hull(Ll, m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], px, py)) return;
+    s.on_lane = 1;
+    float lh = lane_heading_at(Ll, lon);
+    float cosang = md_cosf(lh) * c.hx + md_sinf(lh) * c.hy;
+    if (!(cosang > 0.0f)) return;
+    // lane.distance (abs_lane.py:76-82) from the local coordinates already at hand (same arithmetic as lane_distance)
+    const float over = lon - Ll[LF_LENGTH], under = 0.0f - lon;
+    const float dist = fabsf(lat) + (over > 0.0f ? over : 0.0f) + (under > 0.0f ? under : 0.0f);
+    if (dist < s.d_any) { s.d_any = dist; s.best_any = l; s.lon_any = lon; s.lat_any = lat; }
+    if (l >= c.cur_first && l < c.cur_first + c.cur_n && dist < s.d_cur) { s.d_cur = dist; s.best_cur = l; s.lon_cur = lon; s.lat_cur = lat; }
+    if (c.next_road >= 0 && l >= c.nx_first && l < c.nx_first + c.nx_n && dist < s.d_next) { s.d_next = dist; s.best_next = l; s.lon_next = lon; s.lat_next = lat; }
+}
+__device__ __forceinline__ LocCtx loc_ctx(const MapView& m, const float* S, const int* I, const int* __restrict__ rroad) {
+    LocCtx c;
+    c.px = S[VS_POS]; c.py = S[VS_POS + 1];
+    M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
+    heading_vec(R, c.hx, c.hy);
+    const int c0 = I[VI_CKPT0], c1 = I[VI_CKPT1];
+    const int cur_road = rroad[c0];
+    c.next_road = c1 != c0 ? rroad[c1] : -1;
+    c.cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST]; c.cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+    c.nx_first = c.next_road >= 0 ? m.road_i[c.next_road * ROAD_I + RI_FIRST] : -1;
+    c.nx_n = c.next_road >= 0 ? m.road_i[c.next_road * ROAD_I + RI_N] : 0;
+    return c;
+}
+// the candidate lanes: those binned into the grid cell under the vehicle (ascending lane id, like a full scan)
+__device__ __forceinline__ void loc_cell(const MapView& m, float px, float py, int& k0, int& k1) {
+    k0 = 0; k1 = 0;
+    int cx = (int)floorf((px - m.gx0) / m.cell), cy = (int)floorf((py - m.gy0) / m.cell);
+    if (cx >= 0 && cy >= 0 && cx < m.nx && cy < m.ny) { k0 = m.lgs[cy * m.nx + cx]; k1 = m.lgs[cy * m.nx + cx + 1]; }
+}
+
 // NodeNetworkNavigation.update_localization (component/navigation_module/node_network_navigation.py:130-304) with
-// ray_localization (utils/pg/utils.py:151-203) answered by AABB -> point-in-convex-hull over the map's lane table
+// ray_localization (utils/pg/utils.py:151-203) answered by AABB -> point-in-convex-hull over the map's lane table.
+// `pre` = the candidate scan if a team already ran it (k_post phase 2a), else it runs here.
 __device__ void localise(const MapView& m, const float* S, int* I, const int* __restrict__ route,
-                         const int* __restrict__ rroad, float* navi) {
+                         const int* __restrict__ rroad, float* navi, const LocScan* pre) {
     float px = S[VS_POS], py = S[VS_POS + 1];
     M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
-    float hx, hy;
-    heading_vec(R, hx, hy);
     int c0 = I[VI_CKPT0], c1 = I[VI_CKPT1], n_ck = I[VI_ROUTE_LEN];
     int cur_road = rroad[c0];
     int next_road = c1 != c0 ? rroad[c1] : -1;
     int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
     int nx_first = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_FIRST] : -1;
-    int nx_n = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_N] : 0;
-    bool on_lane = false;
-    int best_any = -1, best_cur = -1, best_next = -1;
-    float d_any = 1e30f, d_cur = 1e30f, d_next = 1e30f;
-    float lon_any = 0.0f, lat_any = 0.0f, lon_cur = 0.0f, lat_cur = 0.0f, lon_next = 0.0f, lat_next = 0.0f;
-    const float4* bb4 = reinterpret_cast<const float4*>(m.lane_bb);
-    // broad phase: only the lanes binned into the grid cell under the vehicle (ascending lane id, like a full scan)
-    int k0 = 0, k1 = 0;
-    {
-        int cx = (int)floorf((px - m.gx0) / m.cell), cy = (int)floorf((py - m.gy0) / m.cell);
-        if (cx >= 0 && cy >= 0 && cx < m.nx && cy < m.ny) { k0 = m.lgs[cy * m.nx + cx]; k1 = m.lgs[cy * m.nx + cx + 1]; }
+    LocScan sc;
+    if (pre != nullptr) sc = *pre;
+    else {
+        const LocCtx c = loc_ctx(m, S, I, rroad);
+        loc_scan_init(sc);
+        int k0, k1;
+        loc_cell(m, px, py, k0, k1);
+        for (int kk = k0; kk < k1; kk++) loc_candidate(m, c, m.lgi[kk], sc);
     }
-    for (int kk = k0; kk < k1; kk++) {
-        const int l = m.lgi[kk];
-        float4 bb = __ldg(bb4 + l);
-        if (px < bb.x || py < bb.y || px > bb.z || py > bb.w) continue;
-        const float* Ll = m.lane_f + l * LANE_F;
-        if (Ll[LF_TYPE] != 0.0f) {  // hull_shortcut's radial rejection, before paying for the arc coordinates (atan2)
-            const float ro = Ll[LF_P0 + 2] + 0.5f * Ll[LF_WIDTH];
-            const float ddx = px - Ll[LF_P0 + 0], ddy = py - Ll[LF_P0 + 1];
-            if (ddx * ddx + ddy * ddy > ro * ro + 1.0f + 0.5f * ro) continue;
-        }
-        float lon, lat;
-        lane_local(Ll, px, py, lon, lat);
-        const int sc = hull_shortcut(Ll, px, py, lon, lat);
-        if (sc < 0) continue;
-        if (sc == 0 &&
-            !point_in_hull(Ll, m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], px, py)) continue;
-        on_lane = true;
-        float lh = lane_heading_at(Ll, lon);
-        float cosang = md_cosf(lh) * hx + md_sinf(lh) * hy;
-        if (!(cosang > 0.0f)) continue;
-        // lane.distance (abs_lane.py:76-82) from the local coordinates already at hand (same arithmetic as lane_distance)
-        const float over = lon - Ll[LF_LENGTH], under = 0.0f - lon;
-        const float dist = fabsf(lat) + (over > 0.0f ? over : 0.0f) + (under > 0.0f ? under : 0.0f);
-        if (dist < d_any) { d_any = dist; best_any = l; lon_any = lon; lat_any = lat; }
-        if (l >= cur_first && l < cur_first + cur_n && dist < d_cur) { d_cur = dist; best_cur = l; lon_cur = lon; lat_cur = lat; }
-        if (next_road >= 0 && l >= nx_first && l < nx_first + nx_n && dist < d_next) { d_next = dist; best_next = l; lon_next = lon; lat_next = lat; }
-    }
+    const bool on_lane = sc.on_lane != 0;
+    const int best_any = sc.best_any, best_cur = sc.best_cur, best_next = sc.best_next;
+    const float lon_any = sc.lon_any, lat_any = sc.lat_any, lon_cur = sc.lon_cur, lat_cur = sc.lat_cur,
+                lon_next = sc.lon_next, lat_next = sc.lat_next;
     int lane;
     float lon, lat;
     if (best_cur >= 0) { lane = best_cur; lon = lon_cur; lat = lat_cur; }
@@ -489,6 +528,44 @@ __device__ void state_check_static(const MapView& m, const Rect& r, int& flags) 
                 }
             }
         }
+}
+
+// team version of state_check_static: the items of the cells under the bounding circle are strided over the T lanes of a
+// sub-warp team; every lane returns the flags of its share (the caller ORs them: the order of evaluation is irrelevant)
+__device__ __forceinline__ int state_check_static_team(const MapView& m, const Rect& r, int sub, int T) {
+    int flags = 0;
+    const float rad = sqrtf(r.hu * r.hu + r.hv * r.hv);
+    int x0 = (int)floorf((r.cx - rad - m.gx0) / m.cell), x1 = (int)floorf((r.cx + rad - m.gx0) / m.cell);
+    int y0 = (int)floorf((r.cy - rad - m.gy0) / m.cell), y1 = (int)floorf((r.cy + rad - m.gy0) / m.cell);
+    x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, m.nx - 1); y1 = min(y1, m.ny - 1);
+    const float4* line4 = reinterpret_cast<const float4*>(m.lines);
+    const float4* quad4 = reinterpret_cast<const float4*>(m.quads);
+    for (int cy = y0; cy <= y1; cy++)
+        for (int cx = x0; cx <= x1; cx++) {
+            const int c = cy * m.nx + cx;
+            const int k1 = m.gs[c + 1];
+            for (int k = m.gs[c] + sub; k < k1; k += T) {
+                const int it = __ldg(m.gi + k);
+                if (it < m.n_lines) {
+                    const float4 h = __ldg(line4 + 2 * it);
+                    const int kind = (int)h.w;
+                    const int bit = kind == 0 ? FL_ON_WHITE : (kind == 1 ? FL_ON_YELLOW : FL_ON_BROKEN);
+                    if (flags & bit) continue;
+                    const float dx = h.x - r.cx, dy = h.y - r.cy, rr = rad + h.z + LINE_HALF_W + 0.01f;
+                    if (dx * dx + dy * dy > rr * rr) continue;
+                    const float4 u = __ldg(line4 + 2 * it + 1);
+                    Rect lr;
+                    lr.cx = h.x; lr.cy = h.y; lr.ux = u.x; lr.uy = u.y; lr.hu = h.z; lr.hv = LINE_HALF_W;
+                    if (rect_rect(r, lr)) flags |= bit;
+                } else {
+                    if (flags & FL_CRASH_SIDEWALK) continue;
+                    const float4 q0 = __ldg(quad4 + 2 * (it - m.n_lines)), q1 = __ldg(quad4 + 2 * (it - m.n_lines) + 1);
+                    float q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    if (rect_quad(r, q)) flags |= FL_CRASH_SIDEWALK;
+                }
+            }
+        }
+    return flags;
 }
 
 // contact pairs of vehicle `slot` against the env's other bodies (engine/core/collision_callback.py:5-42 when
@@ -1230,8 +1307,13 @@ struct __align__(16) Fp { Rect r; int alive; int mark; };   // footprint record 
 #ifndef POST_WORKERS
 #define POST_WORKERS 128
 #endif
+#define POST_TEAM 4   // lanes per vehicle in phase 2a (2 when the CTA holds more vehicles than worker threads)
+__host__ __device__ inline size_t post_scan_offset(int S, int O, int epb) {   // LocScan rows follow the older tables, 16-byte aligned
+    size_t b = (sizeof(Fp) + sizeof(int)) * (size_t)S * epb + sizeof(float) * OBJ_F * (size_t)O * epb + 16 + sizeof(int) * (size_t)epb;
+    return (b + 15) & ~(size_t)15;
+}
 __host__ __device__ inline size_t post_smem_bytes(int S, int O, int epb) {
-    return (sizeof(Fp) + sizeof(int)) * (size_t)S * epb + sizeof(float) * OBJ_F * (size_t)O * epb + 16 + sizeof(int) * (size_t)epb;
+    return post_scan_offset(S, O, epb) + sizeof(LocScan) * (size_t)S * epb;
 }
 __device__ __forceinline__ int fp_contacts(const Fp* fp, const float* obj, int S, int O, int slot, const Rect& r) {
     int flags = 0;  // BaseVehicle._state_check, dynamic world part (component/vehicle/base_vehicle.py:735-742): no latch
@@ -1249,15 +1331,35 @@ __device__ __forceinline__ int fp_contacts(const Fp* fp, const float* obj, int S
     }
     return flags;
 }
+__device__ __forceinline__ int fp_contacts_team(const Fp* fp, const float* obj, int S, int O, int slot, const Rect& r, int sub, int T) {
+    int flags = 0;  // fp_contacts with the bodies strided over the lanes of a team
+    for (int k = sub; k < S; k += T) {
+        if (k == slot || !fp[k].alive) continue;
+        if (rect_rect(r, fp[k].r)) flags |= FL_CRASH_VEHICLE;
+    }
+    for (int k = sub; k < O; k += T) {
+        const float* Ob = obj + k * OBJ_F;
+        if (Ob[OB_KIND] < 0.0f) continue;
+        bool hit;
+        if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
+        else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
+        if (hit) flags |= Ob[OB_KIND] == 3.0f ? FL_CRASH_HUMAN : FL_CRASH_OBJECT;
+    }
+    return flags;
+}
 // BaseVehicle.after_step for one vehicle (component/vehicle/base_vehicle.py:234-271): localisation, state check
 // against the static world and the env's other bodies, side distances, energy.  `fp` = the env's footprints.
 __device__ __forceinline__ void after_step_vehicle(const MapView& m, const float* St, float* C, int* I,
                                                    const int* __restrict__ route, const int* __restrict__ rroad, float* navi,
-                                                   const Fp* fp, const float* sobj, int S, int O, int slot, const Rect& r) {
-    localise(m, St, I, route, rroad, navi);
+                                                   const Fp* fp, const float* sobj, int S, int O, int slot, const Rect& r,
+                                                   const LocScan* pre = nullptr) {
+    localise(m, St, I, route, rroad, navi, pre);
     int flags = I[VI_FLAGS];
-    state_check_static(m, r, flags);
-    flags |= fp_contacts(fp, sobj, S, O, slot, r);
+    if (pre != nullptr) flags |= pre->static_flags | pre->contact_flags;   // a team already ran the three scans (phase 2a)
+    else {
+        state_check_static(m, r, flags);
+        flags |= fp_contacts(fp, sobj, S, O, slot, r);
+    }
     I[VI_FLAGS] = flags;
     int cur_road = rroad[I[VI_CKPT0]];
     int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
@@ -1278,7 +1380,7 @@ __device__ __forceinline__ void after_step_vehicle(const MapView& m, const float
 
 __global__ void __maxnreg__(POST_REGS)
 k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restrict__ body_tab,
-       const uint8_t* __restrict__ env_mask, uint8_t* __restrict__ done_mask, Snapshot snap) {
+       const uint8_t* __restrict__ env_mask, uint8_t* __restrict__ done_mask, Snapshot snap, int team_pref) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     const int n_rows = epb * S, env0 = blockIdx.x * epb;
@@ -1335,8 +1437,57 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         if (env < cfg.n_envs) obj_all[k] = A.obj_f[(size_t)env0 * O * OBJ_F + k];
     }
     __syncthreads();
-    // ---- phase 2: one thread per vehicle with work
+    // ---- phase 2a: the three scans of a vehicle's after_step that walk tables - candidate lanes of update_localization,
+    // line / sidewalk items of _state_check, the env's bodies for the post-step contacts - spread over a team of 2 - 4
+    // lanes per vehicle.  A GPU holds only ~200 active vehicles per SM at BASELINE cfg2: one thread per vehicle leaves 6
+    // warps per SM walking long dependent chains; the teams multiply the warps in flight and shorten the chains.
     const int n_work = *n_list;
+    LocScan* scan = reinterpret_cast<LocScan*>(smem_raw + post_scan_offset(S, O, epb));
+    // team size (measured, gpurun_out/tune.log: k_post at T = 1 / 2 / 4 / 8 / 16 is 0.132 / 0.107 / 0.099 / 0.103 / 0.130 ms at
+    // cfg2, 0.115 / 0.105 / 0.115 / 0.136 / 0.184 at cfg3, 0.227 / 0.192 / 0.184 / 0.189 / 0.245 at cfg5): 4 lanes per
+    // vehicle while the CTA's vehicles fit the worker threads, else 2 - every round of the team loop pays the dependent
+    // loads of map_view / loc_ctx once, so many rounds eat the gain.  MD_POST_TEAM overrides; T = 1 = no team phase.
+    int T = team_pref;
+    if (T <= 0) T = n_work <= (int)blockDim.x ? POST_TEAM : POST_TEAM / 2;
+    const bool use_teams = T > 1;
+    if (use_teams) {
+        const int sub = threadIdx.x & (T - 1), team = threadIdx.x / T, n_teams = blockDim.x / T;
+        const unsigned team_mask = (T >= 32 ? 0xffffffffu : ((1u << T) - 1u)) << ((threadIdx.x & 31) & ~(T - 1));
+        for (int j = team; j < n_work; j += n_teams) {
+            const int v = list[j], le = v / S, slot = v - le * S, env = env0 + le;
+            const size_t g = (size_t)env * S + slot;
+            const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+            const LocCtx c = loc_ctx(m, A.veh_s + g * VEH_S, A.veh_i + g * VEH_I, A.veh_rroad + g * ROUTE_MAX);
+            LocScan sc;
+            loc_scan_init(sc);
+            int k0, k1;
+            loc_cell(m, c.px, c.py, k0, k1);
+            for (int kk = k0 + sub; kk < k1; kk += T) loc_candidate(m, c, m.lgi[kk], sc);
+            const Rect r = fp_all[v].r;
+            sc.static_flags = state_check_static_team(m, r, sub, T);
+            sc.contact_flags = fp_contacts_team(fp_all + (size_t)le * S, obj_all + (size_t)le * O * OBJ_F, S, O, slot, r, sub, T);
+            __syncwarp(team_mask);
+#define TEAM_MIN(D, L, LON, LAT)                                                                         \
+            {                                                                                            \
+                const float od_ = __shfl_xor_sync(team_mask, D, off), olon_ = __shfl_xor_sync(team_mask, LON, off), \
+                            olat_ = __shfl_xor_sync(team_mask, LAT, off);                                \
+                const int ol_ = __shfl_xor_sync(team_mask, L, off);                                      \
+                if (od_ < D || (od_ == D && ol_ >= 0 && (L < 0 || ol_ < L))) { D = od_; L = ol_; LON = olon_; LAT = olat_; } \
+            }
+            for (int off = T >> 1; off > 0; off >>= 1) {
+                TEAM_MIN(sc.d_any, sc.best_any, sc.lon_any, sc.lat_any)
+                TEAM_MIN(sc.d_cur, sc.best_cur, sc.lon_cur, sc.lat_cur)
+                TEAM_MIN(sc.d_next, sc.best_next, sc.lon_next, sc.lat_next)
+                sc.on_lane |= __shfl_xor_sync(team_mask, sc.on_lane, off);
+                sc.static_flags |= __shfl_xor_sync(team_mask, sc.static_flags, off);
+                sc.contact_flags |= __shfl_xor_sync(team_mask, sc.contact_flags, off);
+            }
+#undef TEAM_MIN
+            if (sub == 0) scan[j] = sc;
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: one thread per vehicle with work
     for (int j = threadIdx.x; j < n_work; j += blockDim.x) {
         const int v = list[j], le = v / S, slot = v - le * S, env = env0 + le;
         const size_t g = (size_t)env * S + slot;
@@ -1356,7 +1507,7 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         const int env_step = A.env_i[env * ENV_I + EI_STEP];
         const int* rroad = A.veh_rroad + g * ROUTE_MAX;
         if (mode & MODE_CLEAR_FLAGS) I[VI_FLAGS] = FL_ON_LANE;
-        after_step_vehicle(m, St, C, I, A.veh_route + g * ROUTE_MAX, rroad, navi, fp, sobj, S, O, slot, fp[slot].r);
+        after_step_vehicle(m, St, C, I, A.veh_route + g * ROUTE_MAX, rroad, navi, fp, sobj, S, O, slot, fp[slot].r, use_teams ? scan + j : nullptr);
         if ((mode & MODE_RESET) && !I[VI_ACTIVE]) I[VI_FLAGS] = FL_ON_LANE;  // reset() ends with _init_step_info
         // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111); in respawn /
         // hybrid mode phase 3 brings it back as a new vehicle
@@ -2229,7 +2380,8 @@ static int launch_dyn(md_sim* sim, int mode, const float* ext_act3, int n_sub, c
 }
 static int launch_post(md_sim* sim, int mode, StepOut out, const uint8_t* mask, cudaStream_t st) {
     StepLaunch L = post_launch(sim->cfg);
-    k_post<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, out, sim->body_tab, mask, sim->mask, sim->snap);
+    static const int team_pref = env_int("MD_POST_TEAM", 0);   // 0 = adaptive, 1 = off, 2 / 4 / 8 / 16 / 32 lanes per vehicle
+    k_post<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, out, sim->body_tab, mask, sim->mask, sim->snap, team_pref);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
