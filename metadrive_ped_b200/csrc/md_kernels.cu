@@ -147,6 +147,79 @@ __device__ void find_front_back(const MapView& m, const NbrView& nv, unsigned lo
     }
 }
 
+// find_front_back with the expensive part - lane coordinates of every surrounding object on the three lanes, and whether
+// its lane continues / precedes them - spread over the T lanes of a sub-warp team (the search is 60 % of k_pre).  The
+// object loop of the reference is ORDER dependent (an object on a successor lane only counts until one on the lane itself
+// was found), so the team only fills a table (`scratch`, one float4 per neighbour index), and every lane then runs the
+// ordered fold over it redundantly - all lanes of the team end with the same, exact result.
+//   scratch[k] = (code, lane_local longitude on this lane / on its own lane): code bit 0 same lane, bit 1 this lane is the
+//   previous of its lane, bit 2 its lane is the previous of this lane
+__device__ void find_front_back_team(const MapView& m, const NbrView& nv, unsigned long long valid_lo, unsigned long long valid_hi,
+                                     int lane, float px, float py, float max_d, bool use_ref, int ref_first, int ref_n,
+                                     FrontBack& out, int sub, int T, unsigned team_mask, float2* scratch) {
+    int lanes[3] = {-1, lane, -1};
+    if (use_ref) {
+        int idx = m.lane_i[lane * LANE_I + LI_IDX];
+        if (idx > 0) lanes[0] = ref_first + idx - 1;
+        if (idx + 1 < ref_n) lanes[2] = ref_first + idx + 1;
+    }
+    for (int i = 0; i < 3; i++) {
+        out.fobj[i] = out.bobj[i] = OBJ_NONE;
+        out.exists[i] = lanes[i] >= 0;
+        out.fdist[i] = out.bdist[i] = max_d;
+        if (lanes[i] < 0) continue;
+        const float* Li = m.lane_f + lanes[i] * LANE_F;
+        float cur_long, lat;
+        lane_local(Li, px, py, cur_long, lat);
+        float left_long = Li[LF_LENGTH] - cur_long;
+        // the table: the ord-th valid neighbour belongs to lane ord % T of the team
+        int ord = 0;
+        for (int half = 0; half < 2; half++)
+            for (unsigned long long mk = half ? valid_hi : valid_lo; mk; mk &= mk - 1, ord++) {
+                if ((ord & (T - 1)) != sub) continue;
+                const int k = __ffsll((long long)mk) - 1 + 64 * half;
+                float ox, oy, ovx, ovy; int olane; bool ped;
+                nv.get(k, ox, oy, ovx, ovy, olane, ped);
+                float2 rec = make_float2(0.0f, 0.0f);
+                if (olane >= 0) {
+                    const float* Lo = m.lane_f + olane * LANE_F;
+                    float lon, lt;
+                    if (olane == lanes[i]) { lane_local(Li, ox, oy, lon, lt); rec.x = 1.0f; rec.y = lon; }
+                    else {
+                        const int code = (lane_is_previous_of(Li, Lo) ? 2 : 0) | (lane_is_previous_of(Lo, Li) ? 4 : 0);
+                        if (code) { lane_local(Lo, ox, oy, lon, lt); rec.y = lon; }
+                        rec.x = (float)code;
+                    }
+                }
+                scratch[k] = rec;
+            }
+        __syncwarp(team_mask);
+        // the ordered fold (policy/idm_policy.py:100-131), identical on every lane
+        bool ffound = false, bfound = false;
+        for (int half = 0; half < 2; half++)
+            for (unsigned long long mk = half ? valid_hi : valid_lo; mk; mk &= mk - 1) {
+                const int k = __ffsll((long long)mk) - 1 + 64 * half;
+                const float2 rec = scratch[k];
+                const int code = (int)rec.x;
+                float lon = rec.y;
+                if (code & 1) {
+                    lon -= cur_long;
+                    if (out.fdist[i] > lon && lon > 0.0f) { out.fdist[i] = lon; out.fobj[i] = k; ffound = true; }
+                    if (lon < 0.0f && fabsf(lon) < out.bdist[i]) { out.bdist[i] = fabsf(lon); out.bobj[i] = k; bfound = true; }
+                } else if (!ffound && (code & 2)) {
+                    lon += left_long;
+                    if (out.fdist[i] > lon && lon > 0.0f) { out.fdist[i] = lon; out.fobj[i] = k; }
+                } else if (!bfound && (code & 4)) {
+                    float ox, oy, ovx, ovy; int olane; bool ped;
+                    nv.get(k, ox, oy, ovx, ovy, olane, ped);
+                    lon = m.lane_f[olane * LANE_F + LF_LENGTH] - lon + cur_long;
+                    if (out.bdist[i] > lon) { out.bdist[i] = lon; out.bobj[i] = k; }
+                }
+            }
+        __syncwarp(team_mask);  // the table is rewritten for the next lane
+    }
+}
+
 __device__ __forceinline__ float pid(float kp, float ki, float kd, float& p_err, float& i_err, float err) {
     i_err += err;
     float d = err - p_err;
@@ -192,8 +265,11 @@ __device__ __forceinline__ void yaw_quat_for_lane(const float* L, float lon, flo
 }
 
 // IDMPolicy.act (policy/idm_policy.py:235-402) for one traffic vehicle; S/I/D are this thread's register copies
+// With T > 1 the T lanes of a sub-warp team run this together for the same vehicle (same inputs, same control flow, same
+// results); only the front / back search actually splits its work over them.
 __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv, int g, const float* S, int* I, float* D,
-                        const int* __restrict__ rroad, float& out_a0, float& out_a1) {
+                        const int* __restrict__ rroad, float& out_a0, float& out_a1, int sub = 0, int T = 1,
+                        unsigned team_mask = 0u, float2* scratch = nullptr) {
     float px = S[VS_POS], py = S[VS_POS + 1];
     M3 Rg = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
     float hx, hy;
@@ -245,7 +321,8 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
     if (has_ped) {
         front = OBJ_NONE; front_dist = 5.0f; steer_lane = rt;
     } else if (success && cfg.enable_idm_lane_change) {
-        find_front_back(m, nv, vlo, vhi, rt, px, py, 30.0f, true, cur_first, cur_n, fb);
+        if (T > 1) find_front_back_team(m, nv, vlo, vhi, rt, px, py, 30.0f, true, cur_first, cur_n, fb, sub, T, team_mask, scratch);
+        else find_front_back(m, nv, vlo, vhi, rt, px, py, 30.0f, true, cur_first, cur_n, fb);
         int next_n = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_N] : 0;
         int next_first = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_FIRST] : -1;
         int diff = next_road >= 0 ? cur_n - next_n : 0;
@@ -299,7 +376,8 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
             }
         }
     } else {
-        find_front_back(m, nv, vlo, vhi, rt, px, py, 30.0f, false, 0, 0, fb);
+        if (T > 1) find_front_back_team(m, nv, vlo, vhi, rt, px, py, 30.0f, false, 0, 0, fb, sub, T, team_mask, scratch);
+        else find_front_back(m, nv, vlo, vhi, rt, px, py, 30.0f, false, 0, 0, fb);
         front = fb.fobj[1]; front_dist = fb.fdist[1]; steer_lane = rt;
     }
     // steering_control (:293-301)
@@ -826,12 +904,22 @@ __device__ __forceinline__ void stage_objects(const StepGeom& G, const float* __
 #ifndef PRE_WORKERS
 #define PRE_WORKERS 256
 #endif
-__host__ __device__ inline size_t pre_smem_bytes(int S, int O, int epb) {
-    return (sizeof(Nb) + sizeof(int)) * (size_t)S * epb + sizeof(float) * OBJ_F * (size_t)O * epb + 16;
+#define PRE_TEAM 4                    // lanes per vehicle in the IDM phase
+#define PRE_TEAM_SCRATCH (32 * 1024)  // the teams' tables (one float2 per neighbour index and team) must fit this
+__host__ __device__ inline size_t pre_base_bytes(int S, int O, int epb) {   // Nb rows | objects | list | counters | active list
+    size_t b = (sizeof(Nb) + 2 * sizeof(int)) * (size_t)S * epb + sizeof(float) * OBJ_F * (size_t)O * epb + 32;
+    return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline int pre_team_size(int S, int O, int threads) {
+    return sizeof(float2) * (size_t)(S + O) * (threads / PRE_TEAM) <= PRE_TEAM_SCRATCH ? PRE_TEAM : 1;
+}
+__host__ __device__ inline size_t pre_smem_bytes(int S, int O, int epb, int threads) {
+    const int T = pre_team_size(S, O, threads);
+    return pre_base_bytes(S, O, epb) + (T > 1 ? sizeof(float2) * (size_t)(S + O) * (threads / T) : 0);
 }
 __global__ void __maxnreg__(PRE_REGS)
 k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ actions, float* __restrict__ idm_out,
-      float4* __restrict__ veh_act) {
+      float4* __restrict__ veh_act, int use_teams) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     const int n_rows = epb * S, env0 = blockIdx.x * epb;
@@ -922,10 +1010,25 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
     __syncthreads();
     // ---- phase 2: IDM decisions against the pre-step world (policy/idm_policy.py:235-267), one thread per active vehicle
     if (!(mode & (MODE_IDM | MODE_IDM_OUT))) return;
+    // The listed vehicles that are active (triggered) are compacted once more, and a team of PRE_TEAM lanes runs each
+    // of them: a GPU holds ~150 active traffic vehicles per SM at BASELINE cfg2 - one thread per vehicle would leave
+    // 5 warps per SM walking the neighbour tables one entry at a time.
     const int n_work = *n_list;
-    for (int j = threadIdx.x; j < n_work; j += blockDim.x) {
-        const int v = list[j];
-        if (!nb_all[v].active) continue;
+    int* alist = list + n_rows + 8;
+    int* n_alist = n_list + 1;
+    if (threadIdx.x == 0) *n_alist = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_work; j += blockDim.x)
+        if (nb_all[list[j]].active) alist[atomicAdd(n_alist, 1)] = list[j];
+    __syncthreads();
+    const int n_act = *n_alist;
+    // teams only while one round covers the CTA's active vehicles (each round is a full IDM chain) and the tables fit
+    const int T = (use_teams && n_act * PRE_TEAM <= (int)blockDim.x) ? pre_team_size(S, O, blockDim.x) : 1;
+    const int sub = threadIdx.x & (T - 1), team = threadIdx.x / T, n_teams = blockDim.x / T;
+    const unsigned team_mask = T > 1 ? (((1u << T) - 1u) << ((threadIdx.x & 31) & ~(T - 1))) : 0u;
+    float2* scratch = reinterpret_cast<float2*>(smem_raw + pre_base_bytes(S, O, epb)) + (size_t)team * (S + O);
+    for (int j = team; j < n_act; j += n_teams) {
+        const int v = alist[j];
         const int le = v / S, slot = v - le * S, env = env0 + le;
         const size_t g = (size_t)env * S + slot;
         float P[VEH_P], St[VEH_S], C[VEH_C], D[VEH_IDM];
@@ -943,7 +1046,8 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         nv.nb = nb_all + (size_t)le * S; nv.obj = obj_all + (size_t)le * O * OBJ_F; nv.S = S; nv.O = O; nv.self = slot;
         nv.px = St[VS_POS]; nv.py = St[VS_POS + 1];
         float a0, a1;
-        idm_act(cfg, m, nv, (int)g, St, I, D, A.veh_rroad + g * ROUTE_MAX, a0, a1);
+        idm_act(cfg, m, nv, (int)g, St, I, D, A.veh_rroad + g * ROUTE_MAX, a0, a1, sub, T, team_mask, scratch);
+        if (sub != 0) continue;   // the lanes of a team hold identical results: one of them writes
         if (mode & MODE_IDM_OUT) { idm_out[2 * g] = a0; idm_out[2 * g + 1] = a1; }
         if (mode & MODE_IDM) {
             latch_before_step(St, C, I);
@@ -2325,11 +2429,11 @@ static StepLaunch dyn_launch(const MdConfig& c) {  // k_dyn appends the compacte
 static StepLaunch pre_launch(const MdConfig& c) {  // k_pre: epb envs per CTA, a fixed number of worker threads
     StepLaunch L;
     L.epb = epb_pre();
-    while (L.epb > 1 && pre_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb) > 96 * 1024) L.epb >>= 1;
     L.threads = env_int("MD_PRE_WORKERS", PRE_WORKERS);
     if (L.threads > 1024 || L.threads < 32) L.threads = PRE_WORKERS;
+    while (L.epb > 1 && pre_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb, L.threads) > 128 * 1024) L.epb >>= 1;
     L.blocks = (c.n_envs + L.epb - 1) / L.epb;
-    L.smem = pre_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb);
+    L.smem = pre_smem_bytes(c.slots_per_env, c.objs_per_env, L.epb, L.threads);
     return L;
 }
 static StepLaunch post_launch(const MdConfig& c) {  // k_post: epb envs per CTA, a fixed number of worker threads
@@ -2366,7 +2470,8 @@ static int opt_in_smem(md_sim* sim) {
 
 static int launch_pre(md_sim* sim, int mode, const float* actions, float* idm_out, cudaStream_t st) {
     StepLaunch L = pre_launch(sim->cfg);
-    k_pre<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, actions, idm_out, sim->veh_act);
+    static const int use_teams = env_int("MD_PRE_TEAM", 1);
+    k_pre<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, actions, idm_out, sim->veh_act, use_teams);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
