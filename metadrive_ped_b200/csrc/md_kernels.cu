@@ -1366,31 +1366,58 @@ __global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, uint32_t se
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
     const int scn = (int)(x % (uint32_t)B.n);
     const size_t b = (size_t)scn * S + slot;   // source row in the bank
-#define COPY4(dst, src, n4)                                                                            \
+    // The copies are latency bound (a few finished envs per step, rows cold in DRAM): every thread first issues all the
+    // loads of a batch, then stores, and the env-level rows are strided over the env's threads instead of being one
+    // thread's chain of dependent round trips.
+#define LOAD4(buf, src, n4)                                                                            \
     {                                                                                                  \
         const int4* s4_ = reinterpret_cast<const int4*>(src);                                          \
+        _Pragma("unroll") for (int k_ = 0; k_ < (n4); k_++) buf[k_] = __ldg(s4_ + k_);                 \
+    }
+#define STORE4(dst, buf, n4)                                                                           \
+    {                                                                                                  \
         int4* d4_ = reinterpret_cast<int4*>(dst);                                                      \
-        _Pragma("unroll") for (int k_ = 0; k_ < (n4); k_++) d4_[k_] = s4_[k_];                         \
+        _Pragma("unroll") for (int k_ = 0; k_ < (n4); k_++) d4_[k_] = buf[k_];                         \
     }
-    COPY4(A.veh_s + (size_t)g * VEH_S, B.post.veh_s + b * VEH_S, VEH_S / 4)
-    COPY4(A.veh_c + (size_t)g * VEH_C, B.post.veh_c + b * VEH_C, VEH_C / 4)
-    COPY4(A.veh_i + (size_t)g * VEH_I, B.post.veh_i + b * VEH_I, VEH_I / 4)
-    COPY4(A.veh_idm + (size_t)g * VEH_IDM, B.post.veh_idm + b * VEH_IDM, VEH_IDM / 4)
-    COPY4(const_cast<float*>(A.veh_p) + (size_t)g * VEH_P, B.veh_p + b * VEH_P, VEH_P / 4)
-    COPY4(A.veh_route + (size_t)g * ROUTE_MAX, B.post.veh_route + b * ROUTE_MAX, ROUTE_MAX / 4)
-    COPY4(A.veh_rroad + (size_t)g * ROUTE_MAX, B.post.veh_rroad + b * ROUTE_MAX, ROUTE_MAX / 4)
-    COPY4(body_tab + (size_t)g * BODY_ROW, B.body + b * BODY_ROW, BODY_ROW / 4)
-#undef COPY4
-    for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = B.post.veh_navi[b * NAVI_DIM + k];
+    {
+        int4 s_[VEH_S / 4], c_[VEH_C / 4], i_[VEH_I / 4], d_[VEH_IDM / 4], p_[VEH_P / 4];
+        LOAD4(s_, B.post.veh_s + b * VEH_S, VEH_S / 4)
+        LOAD4(c_, B.post.veh_c + b * VEH_C, VEH_C / 4)
+        LOAD4(i_, B.post.veh_i + b * VEH_I, VEH_I / 4)
+        LOAD4(d_, B.post.veh_idm + b * VEH_IDM, VEH_IDM / 4)
+        LOAD4(p_, B.veh_p + b * VEH_P, VEH_P / 4)
+        STORE4(A.veh_s + (size_t)g * VEH_S, s_, VEH_S / 4)
+        STORE4(A.veh_c + (size_t)g * VEH_C, c_, VEH_C / 4)
+        STORE4(A.veh_i + (size_t)g * VEH_I, i_, VEH_I / 4)
+        STORE4(A.veh_idm + (size_t)g * VEH_IDM, d_, VEH_IDM / 4)
+        STORE4(const_cast<float*>(A.veh_p) + (size_t)g * VEH_P, p_, VEH_P / 4)
+    }
+    {
+        int4 r_[ROUTE_MAX / 4], q_[ROUTE_MAX / 4], y_[BODY_ROW / 4];
+        float nav_[NAVI_DIM];
+        LOAD4(r_, B.post.veh_route + b * ROUTE_MAX, ROUTE_MAX / 4)
+        LOAD4(q_, B.post.veh_rroad + b * ROUTE_MAX, ROUTE_MAX / 4)
+        LOAD4(y_, B.body + b * BODY_ROW, BODY_ROW / 4)
+#pragma unroll
+        for (int k = 0; k < NAVI_DIM; k++) nav_[k] = __ldg(B.post.veh_navi + b * NAVI_DIM + k);
+        STORE4(A.veh_route + (size_t)g * ROUTE_MAX, r_, ROUTE_MAX / 4)
+        STORE4(A.veh_rroad + (size_t)g * ROUTE_MAX, q_, ROUTE_MAX / 4)
+        STORE4(body_tab + (size_t)g * BODY_ROW, y_, BODY_ROW / 4)
+#pragma unroll
+        for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[(size_t)g * NAVI_DIM + k] = nav_[k];
+    }
+#undef LOAD4
+#undef STORE4
     for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = B.post.obj_f[(size_t)scn * O * OBJ_F + k];
-    if (slot == 0) {
-        for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = B.post.env_i[scn * ENV_I + k];
-        int* trig = const_cast<int*>(A.env_trigger);
-        for (int k = 0; k < TRIGGER_MAX; k++) trig[env * TRIGGER_MAX + k] = B.env_trigger[scn * TRIGGER_MAX + k];
+    int* trig = const_cast<int*>(A.env_trigger);
+    for (int k = slot; k < ENV_I + TRIGGER_MAX; k += S) {   // the env row and its trigger roads
+        if (k < ENV_I) A.env_i[env * ENV_I + k] = B.post.env_i[scn * ENV_I + k];
+        else trig[env * TRIGGER_MAX + (k - ENV_I)] = B.env_trigger[scn * TRIGGER_MAX + (k - ENV_I)];
     }
-    if (slot < NA) {
-        const size_t a = (size_t)env * NA + slot, ab = (size_t)scn * NA + slot;
-        for (int k = 0; k < OBS_STATE(cfg); k++) obs[a * (size_t)OBS_DIM(cfg) + k] = B.obs[ab * OBS_STATE(cfg) + k];
+    const int n_state = NA * OBS_STATE(cfg);                // the state part of the agents' reset observation
+    for (int k = slot; k < n_state; k += S) {
+        const int ag = k / OBS_STATE(cfg), col = k - ag * OBS_STATE(cfg);
+        obs[((size_t)env * NA + ag) * (size_t)OBS_DIM(cfg) + col] = B.obs[((size_t)scn * NA + ag) * OBS_STATE(cfg) + col];
     }
 }
 __global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t* __restrict__ env_mask) {
