@@ -134,3 +134,38 @@ def test_lidar_kernel_bit_exact_hits(tag, oracle_lib):
     np.testing.assert_allclose(frac_g.cpu().numpy(), frac_o, rtol=1e-4, atol=1e-6)
     assert (hit_o >= 0).sum() > 50, "test scene must actually hit things"
     sim.close()
+
+
+def test_isolated_stage_entry_points(oracle_lib):
+    """md_idm / md_dynamics / md_after_step (per-kernel entry points for parity tests and ncu captures of a kernel
+    in isolation) against the oracle's isolated stages, bit for bit, in the middle of an episode with triggered traffic."""
+    g, cfg, sim, orc, torch = _make("cfg2_SCO_nolimit", replicas=4)
+    sim.reset()
+    orc.reset_observe()
+    for t in range(40):
+        a = np.tile(g["actions"][t].astype(np.float32), (cfg.n_envs, 1))
+        sim.step(torch.from_numpy(a).cuda())
+        orc.step(a)
+    vi = orc.a["veh_i"]
+    traffic = (vi[:, 0] == 2) & (vi[:, 2] == 1)
+    assert traffic.sum() >= 8, "the episode must have triggered traffic by now"
+    # IDMPolicy.act of every active traffic vehicle (policy/idm_policy.py:235-267) + its bookkeeping (timers, routing lane)
+    out_g = sim.idm().cpu().numpy()
+    out_o = orc.idm()
+    np.testing.assert_array_equal(out_g[traffic], out_o[traffic])
+    np.testing.assert_array_equal(sim.get_state("veh_i"), orc.a["veh_i"])
+    np.testing.assert_array_equal(sim.get_state("veh_idm"), orc.a["veh_idm"])
+    # 5 sub-steps of the raycast-vehicle dynamics under external actuation (steering rad, engine force, brake), no contacts
+    rng = np.random.RandomState(0)
+    nv = cfg.n_envs * cfg.slots_per_env
+    act3 = np.stack([rng.uniform(-0.3, 0.3, nv), rng.uniform(0, 700, nv) * (rng.rand(nv) > 0.3), np.zeros(nv)], 1).astype(np.float32)
+    act3[act3[:, 1] == 0, 2] = 40.0
+    sim.dynamics(torch.from_numpy(act3).cuda(), 5)
+    orc.dynamics(act3, 5)
+    np.testing.assert_array_equal(sim.get_state("veh_s"), orc.a["veh_s"])
+    # BaseVehicle.after_step of every active vehicle: localisation, state check, side distances, energy
+    sim.after_step()
+    orc.after_step()
+    for k in ("veh_i", "veh_c", "veh_navi"):
+        np.testing.assert_array_equal(sim.get_state(k), orc.a[k], err_msg=k)
+    sim.close()
