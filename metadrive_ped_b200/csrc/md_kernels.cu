@@ -1768,14 +1768,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-__host__ __device__ inline size_t lidar_smem_per_warp(int S, int O) {
+__host__ __device__ inline size_t lidar_best_offset(int S, int O) {   // the per-ray nearest-hit words follow the older tables
     size_t b = (size_t)S * BODY_ROW * 4 + (size_t)O * OBJ_F * 4 + (sizeof(float) + sizeof(int)) * (size_t)(S + O);
-    return ((b + 15) & ~(size_t)15) + 16;
+    return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t lidar_smem_per_warp(int S, int O, int N) {
+    return lidar_best_offset(S, O) + (((size_t)N * 8 + 15) & ~(size_t)15) + 16;
 }
 
 // Lidar.perceive (component/sensors/lidar.py:49-73 -> sensors/distance_detector.py:27-85), one warp per agent.
-// The reference's angular mask (lidar.py:140-168) only skips rays that provably miss; here every ray is cast and a
-// conservative bounding-circle test prunes the (ray, body) pairs instead.
+// The reference's angular mask (lidar.py:140-168) only skips rays that provably miss; here the same idea is applied body by
+// body: a candidate is cast only against the rays inside the (padded) angle its bounding circle subtends.
 // LidarStateObservation._add_noise_to_cloud_points (obs/state_obs.py:236-244) for one ray: Gaussian noise, clip to [0, 1],
 // then dropout to 0.  Uniforms come from a counter hash of (seed, observation pass, agent, ray); Box-Muller for the normal.
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -1804,7 +1807,7 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env, N = cfg.n_lasers;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t body_bytes = (size_t)S * BODY_ROW * 4, obj_bytes = (size_t)O * OBJ_F * 4;
-    const size_t per_warp = lidar_smem_per_warp(S, O);
+    const size_t per_warp = lidar_smem_per_warp(S, O, N);
     unsigned char* my = smem_raw + per_warp * warp;
     float* sbody = reinterpret_cast<float*>(my);
     float* sobj = reinterpret_cast<float*>(my + body_bytes);
@@ -1936,50 +1939,70 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     }
     __syncwarp();
     int* hrow = hit_out ? hit_out + (size_t)a * N : nullptr;
-    for (int i = lane; i < N; i += 32) {
-        const float2 cs = __ldg(reinterpret_cast<const float2*>(ray_cs) + i);
-        const float c = cs.x, s = cs.y;
-        const float ux = hx * c - hy * s, uy = hy * c + hx * s;   // unit direction (distance_detector.py:177-180)
-        const F3 d = f3(ux * D, uy * D, 0.0f);
-        float best = 2.0f;
-        int hit = -1;
-        for (int ci = 0; ci < n_cand; ci++) {
-            const int k = sidx[ci];
-            const float rb = srad[k];
-            float t;
-            if (k < S) {
-                const float* b = sbody + BODY_ROW * k;
-                const float rx = b[0] - o.x, ry = b[1] - o.y;
-                const float proj = rx * ux + ry * uy;
-                const float perp2 = (rx * rx + ry * ry) - proj * proj;
-                if (perp2 > rb * rb + 1e-3f || proj < -rb || proj > D + rb) continue;
-                M3 R;
-                R.m[0][0] = b[6]; R.m[0][1] = b[7]; R.m[0][2] = b[8];
-                R.m[1][0] = b[9]; R.m[1][1] = b[10]; R.m[1][2] = b[11];
-                R.m[2][0] = b[12]; R.m[2][1] = b[13]; R.m[2][2] = b[14];
-                t = ray_obb(o, d, f3(b[0], b[1], b[2]), R, f3(b[3], b[4], b[5]));
-            } else {
-                const float* ob = sobj + OBJ_F * (k - S);
-                const float rx = ob[OB_X] - o.x, ry = ob[OB_Y] - o.y;
-                const float proj = rx * ux + ry * uy;
-                const float perp2 = (rx * rx + ry * ry) - proj * proj;
-                if (perp2 > rb * rb + 1e-3f || proj < -rb || proj > D + rb) continue;
-                if (ob[OB_KIND] == 2.0f) {
-                    float ch = md_cosf(ob[OB_HEADING]), sh = md_sinf(ob[OB_HEADING]);
-                    M3 R;
-                    R.m[0][0] = ch; R.m[0][1] = -sh; R.m[0][2] = 0.0f; R.m[1][0] = sh; R.m[1][1] = ch; R.m[1][2] = 0.0f;
-                    R.m[2][0] = 0.0f; R.m[2][1] = 0.0f; R.m[2][2] = 1.0f;
-                    t = ray_obb(o, d, f3(ob[OB_X], ob[OB_Y], ob[OB_ZC]), R, f3(ob[OB_B], ob[OB_A], 0.5f * ob[OB_HEIGHT]));
-                } else {
-                    t = ray_zcyl(o, d, ob[OB_X], ob[OB_Y], ob[OB_ZC], ob[OB_A], 0.5f * ob[OB_HEIGHT]);
-                }
-            }
-            if (t < best) { best = t; hit = k; }
+    // Body-major casting.  A body can only be hit by the rays inside the angle its bounding circle subtends (the
+    // reference's own angular mask, lidar.py:140-168, turned around): for every candidate the warp casts just those rays
+    // - a few per cent of the 240 x K (ray, body) pairs - and keeps the nearest hit per ray in shared memory as a
+    // packed (fraction bits, body index) word, so that equal fractions resolve to the lower index as in a full scan.
+    // The range is padded by two rays and 1e-3 rad: it is a prune, the exact slab / cylinder test decides.
+    unsigned long long* sbest = reinterpret_cast<unsigned long long*>(my + lidar_best_offset(S, O));
+    const unsigned long long none = ((unsigned long long)__float_as_uint(2.0f) << 32) | 0xffffffffull;
+    for (int i = lane; i < N; i += 32) sbest[i] = none;
+    __syncwarp();
+    const float dth = MD_TWO_PI / (float)N;
+    for (int ci = 0; ci < n_cand; ci++) {
+        const int k = sidx[ci];
+        const float rb = srad[k];
+        const float* b = k < S ? sbody + BODY_ROW * k : nullptr;
+        const float* ob = k < S ? nullptr : sobj + OBJ_F * (k - S);
+        const float cx = k < S ? b[0] : ob[OB_X], cy = k < S ? b[1] : ob[OB_Y];
+        const float rx = cx - o.x, ry = cy - o.y;
+        const float d2 = rx * rx + ry * ry;
+        int i_lo = 0, count = N;
+        const float rpad = rb * 1.01f + 0.05f;
+        if (d2 > rpad * rpad) {
+            const float lx = rx * hx + ry * hy, ly = -rx * hy + ry * hx;        // centre in the heading frame
+            const float th = md_atan2f(ly, lx);                                   // ray i points at angle i * dth
+            const float al = md_atan2f(rpad, sqrtf(d2 - rpad * rpad)) + 1e-3f;    // half angle of the bounding circle
+            i_lo = (int)floorf((th - al) / dth) - 2;
+            count = (int)ceilf((2.0f * al) / dth) + 5;
+            if (count > N) count = N;
         }
+        M3 R;
+        F3 cen, half;
+        bool is_box = true;
+        if (k < S) {
+            R.m[0][0] = b[6]; R.m[0][1] = b[7]; R.m[0][2] = b[8];
+            R.m[1][0] = b[9]; R.m[1][1] = b[10]; R.m[1][2] = b[11];
+            R.m[2][0] = b[12]; R.m[2][1] = b[13]; R.m[2][2] = b[14];
+            cen = f3(b[0], b[1], b[2]); half = f3(b[3], b[4], b[5]);
+        } else if (ob[OB_KIND] == 2.0f) {
+            const float ch = md_cosf(ob[OB_HEADING]), sh = md_sinf(ob[OB_HEADING]);
+            R.m[0][0] = ch; R.m[0][1] = -sh; R.m[0][2] = 0.0f; R.m[1][0] = sh; R.m[1][1] = ch; R.m[1][2] = 0.0f;
+            R.m[2][0] = 0.0f; R.m[2][1] = 0.0f; R.m[2][2] = 1.0f;
+            cen = f3(ob[OB_X], ob[OB_Y], ob[OB_ZC]); half = f3(ob[OB_B], ob[OB_A], 0.5f * ob[OB_HEIGHT]);
+        } else is_box = false;
+        for (int j = lane; j < count; j += 32) {
+            int i = (i_lo + j) % N;
+            if (i < 0) i += N;
+            const float2 cs = __ldg(reinterpret_cast<const float2*>(ray_cs) + i);
+            const float ux = hx * cs.x - hy * cs.y, uy = hy * cs.x + hx * cs.y;   // unit direction (distance_detector.py:177-180)
+            const F3 d = f3(ux * D, uy * D, 0.0f);
+            const float t = is_box ? ray_obb(o, d, cen, R, half)
+                                   : ray_zcyl(o, d, ob[OB_X], ob[OB_Y], ob[OB_ZC], ob[OB_A], 0.5f * ob[OB_HEIGHT]);
+            if (t < 2.0f) {
+                const unsigned long long w = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)k;
+                if (w < sbest[i]) sbest[i] = w;   // rays of one pass are distinct (count <= N): no conflict inside the warp
+            }
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < N; i += 32) {
+        const unsigned long long w = sbest[i];
+        const float best = __uint_as_float((unsigned)(w >> 32));
         float frac = best <= 1.0f ? best : 1.0f;
         if (noisy) frac = lidar_noise(cfg, frac, (uint32_t)a, (uint32_t)i, noise_pass);
         orow[i] = frac;
-        if (hrow) hrow[i] = best <= 1.0f ? hit : -1;
+        if (hrow) hrow[i] = best <= 1.0f ? (int)(unsigned)(w & 0xffffffffull) : -1;
     }
 }
 
@@ -2490,7 +2513,7 @@ static int opt_in_smem(md_sim* sim) {
     CK(allow_smem(k_dyn, D.smem > floor48 ? D.smem : floor48));
     CK(allow_smem(k_pre, A.smem > floor48 ? A.smem : floor48));
     CK(allow_smem(k_post, B.smem > floor48 ? B.smem : floor48));
-    size_t lb = lidar_smem_per_warp(sim->cfg.slots_per_env, sim->cfg.objs_per_env) * LIDAR_WARPS;
+    size_t lb = lidar_smem_per_warp(sim->cfg.slots_per_env, sim->cfg.objs_per_env, sim->cfg.n_lasers) * LIDAR_WARPS;
     if (lb > floor48) CK(allow_smem(k_lidar, lb));
     return 0;
 }
@@ -2530,7 +2553,7 @@ static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* h
     const MdConfig& c = sim->cfg;
     long long na = (long long)c.n_envs * c.agents_per_env;
     int blocks = (int)((na + LIDAR_WARPS - 1) / LIDAR_WARPS);
-    size_t smem = lidar_smem_per_warp(c.slots_per_env, c.objs_per_env) * LIDAR_WARPS;
+    size_t smem = lidar_smem_per_warp(c.slots_per_env, c.objs_per_env, c.n_lasers) * LIDAR_WARPS;
     k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, sim->dev.veh_p, out, stride, off, hit, mask,
                                                     agent_flags, need_flag, sim->ray_tab, sim->noise_pass++);
     sim->launches++;
