@@ -1773,7 +1773,7 @@ __host__ __device__ inline size_t lidar_best_offset(int S, int O) {   // the per
     return (b + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t lidar_smem_per_warp(int S, int O, int N) {
-    return lidar_best_offset(S, O) + (((size_t)N * 8 + 15) & ~(size_t)15) + 16;
+    return lidar_best_offset(S, O) + (((size_t)N * 8 + sizeof(int) * (2 * (size_t)(S + O) + 2) + 15) & ~(size_t)15) + 16;
 }
 
 // Lidar.perceive (component/sensors/lidar.py:49-73 -> sensors/distance_detector.py:27-85), one warp per agent.
@@ -1941,61 +1941,84 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     int* hrow = hit_out ? hit_out + (size_t)a * N : nullptr;
     // Body-major casting.  A body can only be hit by the rays inside the angle its bounding circle subtends (the
     // reference's own angular mask, lidar.py:140-168, turned around): for every candidate the warp casts just those rays
-    // - a few per cent of the 240 x K (ray, body) pairs - and keeps the nearest hit per ray in shared memory as a
-    // packed (fraction bits, body index) word, so that equal fractions resolve to the lower index as in a full scan.
+    // - a few per cent of the 240 x K (ray, body) pairs, flattened into one list so that the lanes stay dense - and keeps
+    // the nearest hit per ray in shared memory as a packed (fraction bits, body index) word, so that equal fractions
+    // resolve to the lower index as in a full scan.
     // The range is padded by two rays and 1e-3 rad: it is a prune, the exact slab / cylinder test decides.
     unsigned long long* sbest = reinterpret_cast<unsigned long long*>(my + lidar_best_offset(S, O));
+    int* s_lo = reinterpret_cast<int*>(sbest + N);     // per candidate: first ray of its range, and the running offset of
+    int* s_off = s_lo + (S + O);                        // its (candidate, ray) pairs in the flattened list (n_cand + 1 entries)
     const unsigned long long none = ((unsigned long long)__float_as_uint(2.0f) << 32) | 0xffffffffull;
     for (int i = lane; i < N; i += 32) sbest[i] = none;
-    __syncwarp();
     const float dth = MD_TWO_PI / (float)N;
-    for (int ci = 0; ci < n_cand; ci++) {
-        const int k = sidx[ci];
-        const float rb = srad[k];
-        const float* b = k < S ? sbody + BODY_ROW * k : nullptr;
-        const float* ob = k < S ? nullptr : sobj + OBJ_F * (k - S);
-        const float cx = k < S ? b[0] : ob[OB_X], cy = k < S ? b[1] : ob[OB_Y];
-        const float rx = cx - o.x, ry = cy - o.y;
-        const float d2 = rx * rx + ry * ry;
-        int i_lo = 0, count = N;
-        const float rpad = rb * 1.01f + 0.05f;
-        if (d2 > rpad * rpad) {
-            const float lx = rx * hx + ry * hy, ly = -rx * hy + ry * hx;        // centre in the heading frame
-            const float th = md_atan2f(ly, lx);                                   // ray i points at angle i * dth
-            const float al = md_atan2f(rpad, sqrtf(d2 - rpad * rpad)) + 1e-3f;    // half angle of the bounding circle
-            i_lo = (int)floorf((th - al) / dth) - 2;
-            count = (int)ceilf((2.0f * al) / dth) + 5;
-            if (count > N) count = N;
+    // (a) one lane per candidate: the padded range of rays its bounding circle can meet, and the prefix sum of the counts
+    int total = 0;
+    for (int base = 0; base < n_cand; base += 32) {
+        const int ci = base + lane;
+        int i_lo = 0, count = 0;
+        if (ci < n_cand) {
+            const int k = sidx[ci];
+            const float cx = k < S ? sbody[BODY_ROW * k] : sobj[OBJ_F * (k - S) + OB_X];
+            const float cy = k < S ? sbody[BODY_ROW * k + 1] : sobj[OBJ_F * (k - S) + OB_Y];
+            const float rx = cx - o.x, ry = cy - o.y;
+            const float d2 = rx * rx + ry * ry;
+            const float rpad = srad[k] * 1.01f + 0.05f;
+            count = N;
+            if (d2 > rpad * rpad) {
+                const float lx = rx * hx + ry * hy, ly = -rx * hy + ry * hx;        // centre in the heading frame
+                const float th = md_atan2f(ly, lx);                                   // ray i points at angle i * dth
+                const float al = md_atan2f(rpad, sqrtf(d2 - rpad * rpad)) + 1e-3f;    // half angle of the bounding circle
+                i_lo = (int)floorf((th - al) / dth) - 2;
+                count = (int)ceilf((2.0f * al) / dth) + 5;
+                if (count > N) count = N;
+            }
         }
-        M3 R;
-        F3 cen, half;
-        bool is_box = true;
+        int incl = count;   // inclusive warp scan
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (ci < n_cand) { s_lo[ci] = i_lo; s_off[ci] = total + incl - count; }
+        total += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_off[n_cand] = total;
+    __syncwarp();
+    // (b) the flattened (candidate, ray) pairs, 32 at a time: dense lanes whatever the ranges look like
+    for (int p = lane; p < total; p += 32) {
+        int lo = 0, hi = n_cand;            // the candidate ci with s_off[ci] <= p < s_off[ci + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= p) lo = mid; else hi = mid;
+        }
+        const int k = sidx[lo];
+        int i = (s_lo[lo] + (p - s_off[lo])) % N;
+        if (i < 0) i += N;
+        const float2 cs = __ldg(reinterpret_cast<const float2*>(ray_cs) + i);
+        const float ux = hx * cs.x - hy * cs.y, uy = hy * cs.x + hx * cs.y;   // unit direction (distance_detector.py:177-180)
+        const F3 d = f3(ux * D, uy * D, 0.0f);
+        float t;
         if (k < S) {
+            const float* b = sbody + BODY_ROW * k;
+            M3 R;
             R.m[0][0] = b[6]; R.m[0][1] = b[7]; R.m[0][2] = b[8];
             R.m[1][0] = b[9]; R.m[1][1] = b[10]; R.m[1][2] = b[11];
             R.m[2][0] = b[12]; R.m[2][1] = b[13]; R.m[2][2] = b[14];
-            cen = f3(b[0], b[1], b[2]); half = f3(b[3], b[4], b[5]);
-        } else if (ob[OB_KIND] == 2.0f) {
-            const float ch = md_cosf(ob[OB_HEADING]), sh = md_sinf(ob[OB_HEADING]);
-            R.m[0][0] = ch; R.m[0][1] = -sh; R.m[0][2] = 0.0f; R.m[1][0] = sh; R.m[1][1] = ch; R.m[1][2] = 0.0f;
-            R.m[2][0] = 0.0f; R.m[2][1] = 0.0f; R.m[2][2] = 1.0f;
-            cen = f3(ob[OB_X], ob[OB_Y], ob[OB_ZC]); half = f3(ob[OB_B], ob[OB_A], 0.5f * ob[OB_HEIGHT]);
-        } else is_box = false;
-        for (int j = lane; j < count; j += 32) {
-            int i = (i_lo + j) % N;
-            if (i < 0) i += N;
-            const float2 cs = __ldg(reinterpret_cast<const float2*>(ray_cs) + i);
-            const float ux = hx * cs.x - hy * cs.y, uy = hy * cs.x + hx * cs.y;   // unit direction (distance_detector.py:177-180)
-            const F3 d = f3(ux * D, uy * D, 0.0f);
-            const float t = is_box ? ray_obb(o, d, cen, R, half)
-                                   : ray_zcyl(o, d, ob[OB_X], ob[OB_Y], ob[OB_ZC], ob[OB_A], 0.5f * ob[OB_HEIGHT]);
-            if (t < 2.0f) {
-                const unsigned long long w = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)k;
-                if (w < sbest[i]) sbest[i] = w;   // rays of one pass are distinct (count <= N): no conflict inside the warp
-            }
+            t = ray_obb(o, d, f3(b[0], b[1], b[2]), R, f3(b[3], b[4], b[5]));
+        } else {
+            const float* ob = sobj + OBJ_F * (k - S);
+            if (ob[OB_KIND] == 2.0f) {
+                const float ch = md_cosf(ob[OB_HEADING]), sh = md_sinf(ob[OB_HEADING]);
+                M3 R;
+                R.m[0][0] = ch; R.m[0][1] = -sh; R.m[0][2] = 0.0f; R.m[1][0] = sh; R.m[1][1] = ch; R.m[1][2] = 0.0f;
+                R.m[2][0] = 0.0f; R.m[2][1] = 0.0f; R.m[2][2] = 1.0f;
+                t = ray_obb(o, d, f3(ob[OB_X], ob[OB_Y], ob[OB_ZC]), R, f3(ob[OB_B], ob[OB_A], 0.5f * ob[OB_HEIGHT]));
+            } else t = ray_zcyl(o, d, ob[OB_X], ob[OB_Y], ob[OB_ZC], ob[OB_A], 0.5f * ob[OB_HEIGHT]);
         }
-        __syncwarp();
+        // two candidates may meet the same ray in one pass: the packed minimum is atomic
+        if (t < 2.0f) atomicMin(&sbest[i], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)k);
     }
+    __syncwarp();
     for (int i = lane; i < N; i += 32) {
         const unsigned long long w = sbest[i];
         const float best = __uint_as_float((unsigned)(w >> 32));
