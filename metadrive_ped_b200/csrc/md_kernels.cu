@@ -1799,10 +1799,26 @@ __device__ __forceinline__ float lidar_noise(const MdConfig& cfg, float frac, ui
     }
     return frac;
 }
+// Multi-agent passes: the seats that observe (FL_VALID / FL_NEWBORN) are a fraction of all seats (wrecks, empty seats,
+// nothing new in the respawn pass).  With a warp per SEAT every CTA of k_lidar lived as long as its one or two live warps -
+// 18 waves of mostly empty CTAs; the observing seats are therefore compacted first and k_lidar takes a warp per ENTRY.
+__global__ void k_lidar_list(long long n_agents, const int* __restrict__ agent_flags, int need_flag, int* __restrict__ list,
+                             unsigned int* __restrict__ count) {
+    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = a < n_agents && (agent_flags[a] & need_flag) != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (bal == 0u) return;
+    const int lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned int)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) list[base + __popc(bal & ((1u << lane) - 1u))] = (int)a;
+}
 __global__ void __launch_bounds__(LIDAR_WARPS * 32)
 k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restrict__ obj_f, const int* __restrict__ veh_i,
         const float* __restrict__ veh_p, float* __restrict__ out, int out_stride, int out_off, int* __restrict__ hit_out, const uint8_t* __restrict__ env_mask,
-        const int* __restrict__ agent_flags, int need_flag, const float* __restrict__ ray_cs, uint32_t noise_pass) {
+        const int* __restrict__ agent_flags, int need_flag, const float* __restrict__ ray_cs, uint32_t noise_pass,
+        const int* __restrict__ list, const unsigned int* __restrict__ list_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env, N = cfg.n_lasers;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1815,7 +1831,11 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     int* sidx = reinterpret_cast<int*>(srad + S + O);
     uint64_t* bar = reinterpret_cast<uint64_t*>(my + per_warp - 16);
 
-    const long long a = (long long)blockIdx.x * LIDAR_WARPS + warp;
+    long long a = (long long)blockIdx.x * LIDAR_WARPS + warp;
+    if (list != nullptr) {   // compacted pass: entry -> seat
+        if (a >= (long long)*list_count) return;
+        a = list[a];
+    }
     if (a >= (long long)cfg.n_envs * NA) return;
     const int env = (int)(a / NA), slot = (int)(a - (long long)env * NA);
     if (env_mask != nullptr && env_mask[env] == 0) return;
@@ -2270,6 +2290,8 @@ struct md_sim {
     int32_t* d_info_flags;
     int64_t launches;
     uint32_t noise_pass;   // observation passes so far: the counter of the lidar noise hash
+    int* lidar_list;            // multi-agent lidar passes: the observing seats, compacted (k_lidar_list)
+    unsigned int* lidar_count;
     md_sim* bank;          // scenario bank (md_attach_bank): finished envs restart as a scenario drawn from it
     uint32_t bank_seed, bank_pass;   // the scenario draw is a hash of (seed, env, reset pass)
     bool loaded;
@@ -2319,6 +2341,7 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     sim->launches = 0;
     sim->noise_pass = 0;
     sim->bank = nullptr; sim->bank_seed = 0; sim->bank_pass = 0;
+    sim->lidar_list = nullptr; sim->lidar_count = nullptr;
     sim->prof_cap = 0;
     sim->prof_n = 0;
     memset(&sim->dev, 0, sizeof(sim->dev));
@@ -2374,6 +2397,7 @@ extern "C" void md_destroy(md_sim* sim) {
         cudaFree(sim->d_term); cudaFree(sim->d_trunc); cudaFree(sim->d_mask_in); cudaFree(sim->d_info_flags);
     }
     cudaFree(sim->ray_tab);
+    cudaFree(sim->lidar_list); cudaFree(sim->lidar_count);
     cudaStreamDestroy(sim->stream);
     delete sim;
 }
@@ -2577,8 +2601,19 @@ static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* h
     long long na = (long long)c.n_envs * c.agents_per_env;
     int blocks = (int)((na + LIDAR_WARPS - 1) / LIDAR_WARPS);
     size_t smem = lidar_smem_per_warp(c.slots_per_env, c.objs_per_env, c.n_lasers) * LIDAR_WARPS;
+    const int* list = nullptr;
+    if (agent_flags != nullptr) {   // multi-agent pass: compact the observing seats first (k_lidar_list)
+        if (!sim->lidar_list) {
+            CK(cudaMalloc(&sim->lidar_list, sizeof(int) * (size_t)na));
+            CK(cudaMalloc(&sim->lidar_count, sizeof(unsigned int)));
+        }
+        CK(cudaMemsetAsync(sim->lidar_count, 0, sizeof(unsigned int), st));
+        k_lidar_list<<<(int)((na + 255) / 256), 256, 0, st>>>(na, agent_flags, need_flag, sim->lidar_list, sim->lidar_count);
+        sim->launches++;
+        list = sim->lidar_list;
+    }
     k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, sim->dev.veh_p, out, stride, off, hit, mask,
-                                                    agent_flags, need_flag, sim->ray_tab, sim->noise_pass++);
+                                                    agent_flags, need_flag, sim->ray_tab, sim->noise_pass++, list, sim->lidar_count);
     sim->launches++;
     CK(cudaGetLastError());
     if (off >= 0 && (c.n_side_lasers > 0 || c.n_lane_lasers > 0)) {  // the detector blocks of the same observation rows
