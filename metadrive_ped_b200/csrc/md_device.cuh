@@ -425,7 +425,8 @@ __device__ __forceinline__ void quat_integrate(float* q, F3 w, float dt) {
     float ry = md_dot4(aw, -ax, ay, az, by, bz, bw, bx);
     float rz = md_dot4(aw, ax, -ay, az, bz, by, bx, bw);
     float n = sqrtf(md_dot4(rw, rx, ry, rz, rw, rx, ry, rz));
-    q[0] = rw / n; q[1] = rx / n; q[2] = ry / n; q[3] = rz / n;
+    const float inv_n = 1.0f / n;   /* one division for the four components */
+    q[0] = rw * inv_n; q[1] = rx * inv_n; q[2] = ry * inv_n; q[3] = rz * inv_n;
 }
 
 struct Body {  // rigid-body state kept in registers across the sub-steps
@@ -549,7 +550,7 @@ __device__ void vehicle_substep(const float* __restrict__ P, Body& B, Actuation 
                 F3 iw = apply_inv_inertia(R, c0, Ix, Iy, Iz);
                 float denom0 = inv_m + dot(FWD(i), cross(iw, rel));
                 float vrel = dot(FWD(i), v + cross(w, rel));
-                float j1 = -vrel / denom0 / (float)n_ground;
+                float j1 = -vrel / (denom0 * (float)n_ground);
                 rolling = clipf(j1, -max_imp, max_imp);
             }
             fimp[i] = rolling;
