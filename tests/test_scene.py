@@ -61,3 +61,23 @@ def test_hulls_are_convex_ccw_and_contain_centreline():
             p = sc.lane_position(mt.lane_f[l], lon, 0.0)
             c = e[:, 0] * (p[1] - h[:, 1]) - e[:, 1] * (p[0] - h[:, 0])
             assert (c >= -1e-9).all()
+
+
+def test_map_universe_gives_both_worlds_the_same_map_ids():
+    """md_attach_bank needs the live world and the scenario bank to number their maps identically: build_world's
+    `map_universe` fixes the loaded map set, whatever scenarios the envs of a world happen to play."""
+    from metadrive_ped_b200.library import ScenarioLibrary
+    lib = ScenarioLibrary("pg3_density0.1.npz")
+    uni = list(range(12))
+    S = max(4, -(-lib.max_vehicles() // 4) * 4)
+    live, cfg_l = lib.build_world([7, 3, 3, 11, 0], slots_per_env=S, objs_per_env=0, map_universe=uni)
+    bank, cfg_b = lib.build_world(uni, slots_per_env=S, objs_per_env=0, map_universe=uni)
+    for k in ("map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f", "quad_f",
+              "grid_start", "grid_items", "lgrid_start", "lgrid_items"):
+        np.testing.assert_array_equal(live[k], bank[k], err_msg=k)
+    assert cfg_l.slots_per_env == cfg_b.slots_per_env and cfg_b.n_envs == 12
+    # env e of the live world plays scenario idx[e]: its rows are the bank's rows of that scenario (env_i[:, 0] = map id)
+    for e, scn in enumerate([7, 3, 3, 11, 0]):
+        assert live["env_i"][e, 0] == bank["env_i"][scn, 0] == scn
+        np.testing.assert_array_equal(live["veh_p"][e * S:(e + 1) * S], bank["veh_p"][scn * S:(scn + 1) * S])
+        np.testing.assert_array_equal(live["veh_route"][e * S:(e + 1) * S], bank["veh_route"][scn * S:(scn + 1) * S])
