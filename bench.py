@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--actions", default="profile", choices=["profile", "random"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-resample", action="store_true", help="finished envs replay their own scenario instead of drawing a new one")
+    ap.add_argument("--host-groups", type=int, default=4, help="host groups of the e2e leg (md_host_groups)")
     ap.add_argument("--burnin", type=int, default=150,
                     help="untimed setup steps (with auto-reset) so that envs sit at mixed episode phases")
     args = ap.parse_args()
@@ -260,22 +261,54 @@ def main():
     value = float(units.item()) / total_s
     live_frac = float(units.item()) / (world * A * K)
 
-    # ---------------- e2e: the host-buffer call (pinned staging, H2D actions + D2H outputs inside), wall clock
+    # ---------------- e2e: the host-buffer API (pinned staging, H2D actions + D2H outputs of EVERY env EVERY step inside the
+    # timed region), wall clock.  Two numbers: `sync` = one md_step_host call per step over --host-groups groups (group k's
+    # D2H overlaps group k+1's kernels inside the call); `pipelined` (the headline) = the same groups driven through
+    # send / recv, the EnvPool-style split of the batch: group g's next actions are sent only after its observations
+    # were received, while the other groups are being stepped - the way a host-side learner hides PCIe time.
     a_host = act_dev.cpu().numpy()
-    for _ in range(3):
-        sim.step_host(a_host, autoreset=True)
-    barrier()
+    G = max(1, args.host_groups)
+    sim.host_groups(G)
+    if multi:
+        sim.host_compact(True)
+    gv = sim._group_views()
+    a_grp = [np.ascontiguousarray(a_host[g["a0"]:g["a0"] + g["na"]]) for g in gv]
     Ke = max(10, min(K, 100))
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        sim.step_host(a_host, autoreset=True)
-    torch.cuda.synchronize(dev)
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * A * Ke * live_frac / float(e2e_s.item())
+
+    def e2e_sync(n):
+        rows = 0
+        for _ in range(n):
+            out = sim.step_host(a_host, autoreset=True)
+            rows += out[0].shape[0]
+        return rows
+
+    def e2e_pipelined(n):
+        rows = 0
+        for g in range(G):
+            sim.send(g, a_grp[g], autoreset=True)
+        for i in range(n):
+            for g in range(G):
+                out = sim.recv(g)
+                rows += out[0].shape[0]
+                if i + 1 < n:
+                    sim.send(g, a_grp[g], autoreset=True)
+        return rows
+
+    e2e = {}
+    for name, fn in (("sync", e2e_sync), ("pipelined", e2e_pipelined)):
+        fn(3)
+        barrier()
+        t0 = time.perf_counter()
+        rows = fn(Ke)
+        torch.cuda.synchronize(dev)
+        dt_e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
+        e2e[name] = (world * A * Ke * live_frac / float(dt_e.item()), rows / Ke)
+    e2e_value = e2e["pipelined"][0]
+    obs_rows = e2e["pipelined"][1]     # observation rows copied per step (multi-agent: only the FL_VALID seats travel)
     h2d = A * 2 * 4
-    d2h = A * (sim.obs_dim * 4 + 4 + 4 + 1 + 1 + 4 + 8 * 4)
+    d2h = int(obs_rows * sim.obs_dim * 4 + A * (4 + 4 + 1 + 1 + 4 + 8 * 4))
 
     # ---------------- episode statistics: the only cross-GPU exchange of this path (one tiny all-reduce)
     stats = torch.tensor([float(done_count.item()), float(A * K)], device=dev, dtype=torch.float64)
@@ -333,7 +366,10 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch},
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke},
+                    "steps": Ke, "api": "BatchedSim.send/recv over %d host groups (md_host_send / md_host_recv): every env gets "
+                                        "its actions H2D and its results D2H every step; a group's next actions are sent "
+                                        "after its results were received" % G,
+                    "sync_call_value": e2e["sync"][0], "host_groups": G},
             "clocks": clocks.summary(),
             "episodes_finished_frac": float(stats[0].item() / max(stats[1].item(), 1.0)),
         }

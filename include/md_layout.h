@@ -239,6 +239,11 @@ typedef struct MdConfig {
      * draws are a counter hash of (noise_seed, observation pass, agent, ray). */
     float lidar_gaussian_noise, lidar_dropout_prob;
     int noise_seed;
+    /* first env of a launch's env range within the handle.  Callers pass 0; the library sets it when it runs the step
+     * over a sub-range of the envs (the host-buffer groups of md_host_groups), so that the counter hashes (scenario
+     * draw, random tape laps, IDM randint, lidar noise) see the same global env / slot / agent index as a whole-batch
+     * launch and the results do not depend on how the batch was split. */
+    int env_base;
 } MdConfig;
 
 /* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */

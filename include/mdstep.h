@@ -25,8 +25,11 @@ extern "C" {
 
 typedef struct md_sim md_sim;
 
-#define MD_ABI_VERSION 3
+#define MD_ABI_VERSION 4
 int md_abi_version(void);
+/* sizeof(MdConfig) / sizeof(MdArrays) the library was built with: the loader compares them with its own mirror */
+int md_sizeof_config(void);
+int md_sizeof_arrays(void);
 
 /* engine construction: replaces initialize_engine / BaseEngine.__init__ + PhysicsWorld
  * (engine/engine_utils.py:8-15, engine/base_engine.py:51-96, engine/core/physics_world.py:9-17) */
@@ -43,7 +46,9 @@ int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* rows);
 
 /* env.reset(): replaces BaseEnv.reset -> engine.reset + _get_reset_return (envs/base_env.py:502-584).
  * Restores the snapshot of every env whose mask byte is non-zero (all envs if env_mask_dev == NULL), runs the
- * reset-time after_step and writes the first observation of their agents into obs_dev [A, OBS_DIM(cfg)]. */
+ * reset-time after_step and writes the first observation of their agents into obs_dev [A, OBS_DIM(cfg)].
+ * With a scenario bank attached (md_attach_bank) the selected envs restart in a scenario DRAWN from the bank instead,
+ * like BaseEnv.reset(seed=None) - the same draw an auto-reset makes. */
 int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev, void* stream);
 
 /* env.step(): replaces BaseEnv.step = _step_simulator + _get_step_return (envs/base_env.py:426-463, 586-623):
@@ -65,15 +70,37 @@ int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* trun
 int md_step_autoreset(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
                       uint8_t* terminated_dev, uint8_t* truncated_dev, int32_t* info_flags_dev, float* info_f_dev, void* stream);
 
-/* the same step through HOST buffers: pinned staging, H2D of actions and D2H of all outputs on the sim's own stream,
- * synchronous.  This is the call the Gymnasium-surface classes make. */
+/* ---- the same step through HOST buffers (what the Gymnasium-surface classes call) ------------------------------------
+ * The batch is partitioned into HOST GROUPS: contiguous env ranges, each with its own stream (earlier groups at higher
+ * priority), a packed device output block with a pinned mirror of the same layout (reward | cost | info_flags | info_f |
+ * terminated | truncated | valid-row count: ONE D2H copy for all scalars of a step) and its rows of the handle-wide pinned
+ * action / observation buffers (one more copy).  One group (the default) behaves like a plain synchronous call; with
+ * several groups
+ *   - md_step_host overlaps group k's D2H copies with group k+1's kernels inside the one synchronous call, and
+ *   - md_host_send / md_host_recv pipeline ACROSS steps (the EnvPool-style split: while the caller consumes group A's
+ *     observations and picks its next actions, group B is being stepped), which hides the PCIe time behind compute.
+ * Results do not depend on the partition (MdConfig.env_base keeps every counter hash on global indices).
+ * md_step_host: actions [A,2] host floats or NULL (= already written into the pinned action buffers); output pointers
+ * may be NULL, the results then stay in the pinned buffers (md_host_views / md_host_group_views).  Synchronous. */
 int md_step_host(md_sim* sim, const float* actions, float* obs, float* reward, float* cost, uint8_t* terminated,
                  uint8_t* truncated, int32_t* info_flags, float* info_f, int autoreset);
 int md_reset_host(md_sim* sim, const uint8_t* env_mask, float* obs);
-/* zero-copy variant: out8 receives the addresses of the library's pinned staging buffers in the order obs, reward,
- * cost, terminated, truncated, info_flags, info_f, actions.  md_step_host with NULL output pointers leaves the results
- * there; with actions == NULL (or == the staging address) it reads the actions the caller wrote there. */
+/* (re)partition into n_groups (1..32) host groups; no group may be in flight */
+int md_host_groups(md_sim* sim, int n_groups);
+int md_host_group_count(const md_sim* sim);
+/* out8 = addresses of the group's pinned buffers in the order obs rows, reward, cost, terminated, truncated, info_flags,
+ * info_f, actions; range3 = first env, env count, observation rows delivered by the last received step */
+int md_host_group_views(md_sim* sim, int group, void** out8, int* range3);
+/* group 0's buffers (the whole batch while there is one group) */
 int md_host_views(md_sim* sim, void** out8);
+/* enqueue one env.step of a group (H2D actions, kernels, D2H results) and return; md_host_recv waits for it */
+int md_host_send(md_sim* sim, int group, const float* actions, int autoreset);
+int md_host_recv(md_sim* sim, int group);
+/* multi-agent handles: compact != 0 -> only the observation rows of seats that produced a transition this step
+ * (FL_VALID) are copied to the host, packed in ascending seat order at the start of the group's obs rows; the scalars
+ * still come back for every seat (row j belongs to the j-th seat whose info_flags carry FL_VALID).  A roundabout env keeps
+ * 41 seats for <= 40 live agents and wrecks / empty seats produce no transition: their 1036-byte rows are not sent. */
+int md_host_compact(md_sim* sim, int compact);
 
 /* isolated stages, for parity tests and per-kernel ncu captures */
 /* Lidar.perceive (component/sensors/lidar.py:49-73; sensors/distance_detector.py:27-85): frac_dev [A,n_lasers] in

@@ -64,6 +64,7 @@ struct StepOut {
 struct Snapshot {
     const int* env_i; const float* veh_s; const float* veh_c; const int* veh_i; const float* veh_idm;
     const float* veh_navi; const float* obj_f; const int* veh_route; const int* veh_rroad;
+    const float* veh_p; const int* env_trigger;   // only read by a `full` restore (after scenario-bank draws)
 };
 
 // neighbour record of one vehicle slot, shared by the threads of its env
@@ -240,7 +241,7 @@ __device__ __forceinline__ uint32_t tape_draw(const MdConfig& cfg, const int* __
     uint32_t v = (uint32_t)tape[((size_t)env * L + ctr % L) * TAPE_W + j];
     const uint32_t lap = ctr / L;
     if (lap) {
-        uint32_t x = (uint32_t)env * 0x9E3779B9u + (lap * 4u + (uint32_t)j) * 0x85EBCA6Bu + 0x165667B1u;
+        uint32_t x = (uint32_t)(env + cfg.env_base) * 0x9E3779B9u + (lap * 4u + (uint32_t)j) * 0x85EBCA6Bu + 0x165667B1u;
         x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
         v += x;
     }
@@ -919,8 +920,11 @@ __host__ __device__ inline size_t pre_smem_bytes(int S, int O, int epb, int thre
 }
 __global__ void __maxnreg__(PRE_REGS)
 k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ actions, float* __restrict__ idm_out,
-      float4* __restrict__ veh_act, int use_teams) {
+      float4* __restrict__ veh_act, int use_teams, uint32_t* __restrict__ pass_ctr, uint32_t d_bank, uint32_t d_noise) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // the first kernel of a step advances the view's pass counters (scenario draws, observation passes); they live in
+    // device memory so that a whole step is a fixed launch sequence (CUDA-graph replayable).  Nobody reads them in k_pre.
+    if (pass_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { pass_ctr[0] += d_bank; pass_ctr[1] += d_noise; }
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     const int n_rows = epb * S, env0 = blockIdx.x * epb;
     Nb* nb_all = reinterpret_cast<Nb*>(smem_raw);
@@ -1046,7 +1050,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         nv.nb = nb_all + (size_t)le * S; nv.obj = obj_all + (size_t)le * O * OBJ_F; nv.S = S; nv.O = O; nv.self = slot;
         nv.px = St[VS_POS]; nv.py = St[VS_POS + 1];
         float a0, a1;
-        idm_act(cfg, m, nv, (int)g, St, I, D, A.veh_rroad + g * ROUTE_MAX, a0, a1, sub, T, team_mask, scratch);
+        idm_act(cfg, m, nv, (int)g + cfg.env_base * S, St, I, D, A.veh_rroad + g * ROUTE_MAX, a0, a1, sub, T, team_mask, scratch);
         if (sub != 0) continue;   // the lanes of a team hold identical results: one of them writes
         if (mode & MODE_IDM_OUT) { idm_out[2 * g] = a0; idm_out[2 * g + 1] = a1; }
         if (mode & MODE_IDM) {
@@ -1296,7 +1300,9 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
 }
 
 // ---- env.reset state restore of one slot row (snapshot -> live arrays) -----------------------------------------
-__device__ __forceinline__ void restore_row(const MdConfig& cfg, const MdArrays& A, const Snapshot& snap, long long g) {
+// `full`: the env may hold another scenario than the snapshot's (scenario-bank draws rewrite vehicle parameters, routes
+// and trigger roads), so those rows are restored as well
+__device__ __forceinline__ void restore_row(const MdConfig& cfg, const MdArrays& A, const Snapshot& snap, long long g, bool full = false) {
     const int S = cfg.slots_per_env, O = cfg.objs_per_env;
     const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
     const float4* s4 = reinterpret_cast<const float4*>(snap.veh_s + (size_t)g * VEH_S);
@@ -1314,7 +1320,17 @@ __device__ __forceinline__ void restore_row(const MdConfig& cfg, const MdArrays&
     for (int k = slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)env * O * OBJ_F + k] = snap.obj_f[(size_t)env * O * OBJ_F + k];
     if (slot == 0)
         for (int k = 0; k < ENV_I; k++) A.env_i[env * ENV_I + k] = snap.env_i[env * ENV_I + k];
-    if ((cfg.is_multi_agent && slot < cfg.agents_per_env) || cfg.traffic_mode != 0) {  // respawns rewrite the slot's route
+    if (full) {
+        const float4* p4 = reinterpret_cast<const float4*>(snap.veh_p + (size_t)g * VEH_P);
+        float4* dp = reinterpret_cast<float4*>(const_cast<float*>(A.veh_p) + (size_t)g * VEH_P);
+#pragma unroll
+        for (int k = 0; k < VEH_P / 4; k++) dp[k] = p4[k];
+        if (slot == 0) {
+            int* trig = const_cast<int*>(A.env_trigger);
+            for (int k = 0; k < TRIGGER_MAX; k++) trig[env * TRIGGER_MAX + k] = snap.env_trigger[env * TRIGGER_MAX + k];
+        }
+    }
+    if (full || (cfg.is_multi_agent && slot < cfg.agents_per_env) || cfg.traffic_mode != 0) {  // respawns rewrite the slot's route
         const int4* r4 = reinterpret_cast<const int4*>(snap.veh_route + (size_t)g * ROUTE_MAX);
         const int4* q4 = reinterpret_cast<const int4*>(snap.veh_rroad + (size_t)g * ROUTE_MAX);
         int4* dr = reinterpret_cast<int4*>(A.veh_route + (size_t)g * ROUTE_MAX);
@@ -1354,15 +1370,17 @@ struct BankView {
     const float* body; const float* obs; const float* veh_p; const int* env_trigger;
     int n;
 };
-__global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, uint32_t seed, uint32_t pass, float* __restrict__ body_tab,
-                               float* __restrict__ obs, const uint8_t* __restrict__ env_mask) {
+__global__ void k_bump(uint32_t* __restrict__ pass_ctr, uint32_t d_bank, uint32_t d_noise) { pass_ctr[0] += d_bank; pass_ctr[1] += d_noise; }
+__global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, uint32_t seed, const uint32_t* __restrict__ pass_ctr,
+                               float* __restrict__ body_tab, float* __restrict__ obs, const uint8_t* __restrict__ env_mask) {
+    const uint32_t pass = pass_ctr[0];
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     if (g >= (long long)cfg.n_envs * S) return;
     const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
-    if (env_mask[env] == 0) return;
+    if (env_mask != nullptr && env_mask[env] == 0) return;
     // the draw: a counter hash of (seed, env, reset pass) - every thread of the env computes the same scenario
-    uint32_t x = seed * 0x9E3779B9u + (uint32_t)env * 0x85EBCA6Bu + pass * 0xC2B2AE35u + 0x165667B1u;
+    uint32_t x = seed * 0x9E3779B9u + (uint32_t)(env + cfg.env_base) * 0x85EBCA6Bu + pass * 0xC2B2AE35u + 0x165667B1u;
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
     const int scn = (int)(x % (uint32_t)B.n);
     const size_t b = (size_t)scn * S + slot;   // source row in the bank
@@ -1420,11 +1438,11 @@ __global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, uint32_t se
         obs[((size_t)env * NA + ag) * (size_t)OBS_DIM(cfg) + col] = B.obs[((size_t)scn * NA + ag) * OBS_STATE(cfg) + col];
     }
 }
-__global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t* __restrict__ env_mask) {
+__global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t* __restrict__ env_mask, int full) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)cfg.n_envs * cfg.slots_per_env) return;
     if (env_mask != nullptr && env_mask[g / cfg.slots_per_env] == 0) return;
-    restore_row(cfg, A, snap, g);
+    restore_row(cfg, A, snap, g, full != 0);
 }
 
 // ---- k_post: engine.after_step + _get_step_return (base_vehicle.py:234-271; envs/base_env.py:586-623) -----------
@@ -1817,8 +1835,9 @@ __global__ void k_lidar_list(long long n_agents, const int* __restrict__ agent_f
 __global__ void __launch_bounds__(LIDAR_WARPS * 32)
 k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restrict__ obj_f, const int* __restrict__ veh_i,
         const float* __restrict__ veh_p, float* __restrict__ out, int out_stride, int out_off, int* __restrict__ hit_out, const uint8_t* __restrict__ env_mask,
-        const int* __restrict__ agent_flags, int need_flag, const float* __restrict__ ray_cs, uint32_t noise_pass,
-        const int* __restrict__ list, const unsigned int* __restrict__ list_count) {
+        const int* __restrict__ agent_flags, int need_flag, const float* __restrict__ ray_cs, const uint32_t* __restrict__ pass_ctr,
+        uint32_t noise_off, const int* __restrict__ list, const unsigned int* __restrict__ list_count) {
+    const uint32_t noise_pass = (pass_ctr != nullptr ? pass_ctr[1] : 0u) + noise_off;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env, N = cfg.n_lasers;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2043,7 +2062,7 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
         const unsigned long long w = sbest[i];
         const float best = __uint_as_float((unsigned)(w >> 32));
         float frac = best <= 1.0f ? best : 1.0f;
-        if (noisy) frac = lidar_noise(cfg, frac, (uint32_t)a, (uint32_t)i, noise_pass);
+        if (noisy) frac = lidar_noise(cfg, frac, (uint32_t)a + (uint32_t)(cfg.env_base * NA), (uint32_t)i, noise_pass);
         orow[i] = frac;
         if (hrow) hrow[i] = best <= 1.0f ? (int)(unsigned)(w & 0xffffffffull) : -1;
     }
@@ -2260,19 +2279,105 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
     write_body_row(body_tab + g * BODY_ROW, P, St, 1);
 }
 
+// ---- host-path compaction of a multi-agent step: only the observation rows of seats that produced a transition
+// (FL_VALID) travel to the host.  Ordered (ascending seat) and deterministic: per-block counts, then every block sums the
+// counts before it, ranks its own seats with a ballot scan and its warps copy the rows.
+#define COMPACT_T 256
+__global__ void __launch_bounds__(COMPACT_T)
+k_valid_count(long long n_agents, const int* __restrict__ flags, unsigned int* __restrict__ block_counts) {
+    const long long a = (long long)blockIdx.x * COMPACT_T + threadIdx.x;
+    const int ok = a < n_agents && (flags[a] & FL_VALID) != 0;
+    const int n = __syncthreads_count(ok);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned int)n;
+}
+__global__ void __launch_bounds__(COMPACT_T)
+k_valid_gather(long long n_agents, const int* __restrict__ flags, const unsigned int* __restrict__ block_counts, int od,
+               const float* __restrict__ obs, float* __restrict__ cobs, unsigned int* __restrict__ total) {
+    __shared__ unsigned int s_base, s_warp[COMPACT_T / 32];
+    __shared__ int s_seat[COMPACT_T];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    unsigned int part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += COMPACT_T) part += block_counts[b];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (lane == 0 && part) atomicAdd(&s_base, part);
+    const long long a = (long long)blockIdx.x * COMPACT_T + threadIdx.x;
+    const bool ok = a < n_agents && (flags[a] & FL_VALID) != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = (unsigned int)__popc(bal);
+    __syncthreads();
+    unsigned int before = 0, count = 0;
+    for (int w = 0; w < COMPACT_T / 32; w++) { if (w < warp) before += s_warp[w]; count += s_warp[w]; }
+    if (ok) s_seat[before + __popc(bal & ((1u << lane) - 1u))] = threadIdx.x;
+    __syncthreads();
+    const unsigned int base = s_base;
+    for (unsigned int j = warp; j < count; j += COMPACT_T / 32) {
+        const float* src = obs + ((size_t)blockIdx.x * COMPACT_T + s_seat[j]) * od;
+        float* dst = cobs + (size_t)(base + j) * od;
+        for (int k = lane; k < od; k += 32) dst[k] = src[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = base + count;
+}
+
 // ================================================================================================ host side / C ABI
+// A View is a contiguous range of a handle's envs with everything a launch needs: the configuration with n_envs /
+// env_base set to the range, the per-env arrays advanced to its first env (the map tables are shared), its slices of the
+// snapshots and work buffers, and its own pass counters.  The device-resident entry points (md_step, md_reset ...) run on
+// the view of the whole batch; the host-buffer entry points run one view per host group, each on its own stream, so that
+// one group's D2H copy overlaps another group's kernels.
+struct View {
+    MdConfig cfg;
+    MdArrays dev;
+    Snapshot snap, post;
+    float *post_body, *post_obs, *body_tab;
+    float4* veh_act;
+    uint8_t* mask;
+    int* lidar_list;             // multi-agent lidar passes: the observing seats, compacted (k_lidar_list)
+    unsigned int* lidar_count;
+    uint32_t* pass;              // device: [0] scenario-draw passes so far (the counter of the draw hash (seed, env, pass)),
+                                 // [1] observation passes so far (the counter of the lidar noise hash)
+};
+
+// One host group: an env range stepped through host buffers.  Device output block `d_blk` and its pinned mirror `h_blk`
+// share one layout - reward | cost | info_flags | info_f | terminated | truncated | valid-row count - so the scalars of a
+// step come back with ONE copy; the observation rows are a slice of the handle-wide obs buffers (one more copy).
+struct HostGroup {
+    View v;
+    int env0, n_envs;
+    size_t na;                   // agents (seats) of the group
+    cudaStream_t stream;
+    cudaEvent_t done;
+    unsigned char *d_blk, *h_blk;
+    size_t blk_bytes, off_cost, off_flags, off_info_f, off_term, off_trunc, off_count;
+    StepOut out;                 // device pointers into d_blk (+ the group's rows of d_obs)
+    float *d_actions, *h_actions, *h_obs;
+    float* d_cobs;               // multi-agent, compact mode: the valid observation rows, gathered (k_valid_gather)
+    unsigned int* d_block_counts;
+    // the group's whole step (H2D, kernels, D2H) as an instantiated CUDA graph: one launch per send instead of ~10 API
+    // calls.  Every kernel argument is a fixed pointer or constant (the pass counters live in device memory), so the
+    // captured sequence replays as is; it is re-captured when what shapes the sequence changes (`gkey`).
+    cudaGraphExec_t gexec;
+    uint64_t gkey;
+    int glaunches;               // kernels inside the graph (md_launch_count)
+    bool in_flight;              // md_host_send issued, md_host_recv pending
+    bool pending_compact;        // the compact observation rows still have to be fetched (their count is known after `done`)
+};
+#define MAX_HOST_GROUPS 32
+
+#define N_ARR 28
+#define N_SNAP 11
 struct md_sim {
     MdConfig cfg;
     int device;
     std::string err;
     MdArrays dev;           // device pointers
-    int64_t rows[28];
-    size_t bytes[28];
-    Snapshot snap;
-    void* snap_bufs[9];
+    int64_t rows[N_ARR];
+    size_t bytes[N_ARR];
+    void* snap_bufs[N_SNAP];
     // the state right after a full reset (restore + reset-time after_step), so that an auto-reset is a row copy
-    Snapshot post;
-    void* post_bufs[9];
+    void* post_bufs[N_SNAP];
     float* post_body;       // [NV, BODY_ROW]
     float* post_obs;        // [A, OBS_STATE]: the state part of the reset observation
     bool post_valid;
@@ -2280,27 +2385,25 @@ struct md_sim {
     float* ray_tab;         // [2*MAX_LASERS lidar | 2*MAX_DET_LASERS side | 2*MAX_DET_LASERS lane] (cos, sin) pairs
     float4* veh_act;        // [NV] steering rad, engine force, brake: k_pre -> k_dyn
     uint8_t* mask;
-    cudaStream_t stream;    // own stream for the *_host entry points
-    // pinned host staging + device mirrors for the *_host entry points
-    float *h_actions, *h_obs, *h_reward, *h_cost, *h_info_f;
-    uint8_t *h_term, *h_trunc, *h_mask;
-    int32_t* h_info_flags;
-    float *d_actions, *d_obs, *d_reward, *d_cost, *d_info_f;
-    uint8_t *d_term, *d_trunc, *d_mask_in;
-    int32_t* d_info_flags;
+    int* lidar_list;
+    unsigned int* lidar_count;   // [1 + MAX_HOST_GROUPS]: the whole-batch view, then one per host group
+    uint32_t* d_pass;            // [2 * (1 + MAX_HOST_GROUPS)] pass counters, same order
+    View all;               // the whole batch
+    // host-buffer path: pinned staging + device mirrors, split into host groups
+    float *h_actions, *h_obs, *d_actions, *d_obs;
+    uint8_t *h_mask, *d_mask_in;
+    std::vector<HostGroup> groups;
+    int compact;            // multi-agent: only valid observation rows travel to the host
     int64_t launches;
-    uint32_t noise_pass;   // observation passes so far: the counter of the lidar noise hash
-    int* lidar_list;            // multi-agent lidar passes: the observing seats, compacted (k_lidar_list)
-    unsigned int* lidar_count;
-    md_sim* bank;          // scenario bank (md_attach_bank): finished envs restart as a scenario drawn from it
-    uint32_t bank_seed, bank_pass;   // the scenario draw is a hash of (seed, env, reset pass)
+    md_sim* bank;           // scenario bank (md_attach_bank): finished envs restart as a scenario drawn from it
+    uint32_t bank_seed;
+    bool bank_ever;         // a bank was attached at some point: envs may hold drawn scenarios, restores must be `full`
     bool loaded;
-    // optional per-kernel timing: 3 events per md_step on the launch stream (bench.py's roofline leg)
+    // optional per-kernel timing: 6 events per md_step on the launch stream (bench.py's roofline leg)
     std::vector<cudaEvent_t> prof_ev;
     int prof_cap, prof_n;
 };
 
-#define N_ARR 28
 static const char* kNames[N_ARR] = {"map_desc", "map_descf", "lane_f", "lane_i", "lane_bb", "road_i", "hull_xy", "line_f",
                                     "quad_f", "grid_start", "grid_items", "env_i", "env_trigger", "veh_p", "veh_s", "veh_c",
                                     "veh_i", "veh_route", "veh_idm", "veh_navi", "obj_f", "lgrid_start", "lgrid_items",
@@ -2308,8 +2411,11 @@ static const char* kNames[N_ARR] = {"map_desc", "map_descf", "lane_f", "lane_i",
 static const int kRowBytes[N_ARR] = {MAPD * 4, MAPDF * 4, LANE_F * 4, LANE_I * 4, 16, ROAD_I * 4, 8, LINE_F * 4, QUAD_F * 4, 4, 4,
                                      ENV_I * 4, TRIGGER_MAX * 4, VEH_P * 4, VEH_S * 4, VEH_C * 4, VEH_I * 4, ROUTE_MAX * 4,
                                      VEH_IDM * 4, NAVI_DIM * 4, OBJ_F * 4, 4, 4, ROUTE_MAX * 4, 32, ROUTE_MAX * 4, ROUTE_MAX * 4, TAPE_W * 4};
-#define N_SNAP 9
-static const int kSnapIdx[N_SNAP] = {11, 14, 15, 16, 18, 19, 20, 17, 23};  // env_i veh_s veh_c veh_i veh_idm veh_navi obj_f veh_route veh_rroad
+// env_i veh_s veh_c veh_i veh_idm veh_navi obj_f veh_route veh_rroad veh_p env_trigger
+static const int kSnapIdx[N_SNAP] = {11, 14, 15, 16, 18, 19, 20, 17, 23, 13, 12};
+static const bool kPerEnv[N_ARR] = {false, false, false, false, false, false, false, false, false, false, false,
+                                    true, true, true, true, true, true, true, true, true, true, false, false,
+                                    true, true, true, true, true};
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -2322,8 +2428,58 @@ static const int kSnapIdx[N_SNAP] = {11, 14, 15, 16, 18, 19, 20, 17, 23};  // en
 
 static int opt_in_smem(md_sim* sim);
 static void** arr_slot(MdArrays* a, int i) { return reinterpret_cast<void**>(a) + i; }
+// rows of array i that belong to one env (0 = the array is shared, or a dummy row)
+static int64_t rows_per_env(const md_sim* sim, int i) {
+    const int64_t E = sim->cfg.n_envs;
+    return (kPerEnv[i] && sim->rows[i] >= E && sim->rows[i] % E == 0) ? sim->rows[i] / E : 0;
+}
+
+static void set_snapshot_ptrs(Snapshot& sn, void* const* bufs, const md_sim* sim, int env0) {
+    const void* p[N_SNAP];
+    for (int k = 0; k < N_SNAP; k++)
+        p[k] = (const char*)bufs[k] + (size_t)env0 * rows_per_env(sim, kSnapIdx[k]) * kRowBytes[kSnapIdx[k]];
+    sn.env_i = (const int*)p[0];
+    sn.veh_s = (const float*)p[1];
+    sn.veh_c = (const float*)p[2];
+    sn.veh_i = (const int*)p[3];
+    sn.veh_idm = (const float*)p[4];
+    sn.veh_navi = (const float*)p[5];
+    sn.obj_f = (const float*)p[6];
+    sn.veh_route = (const int*)p[7];
+    sn.veh_rroad = (const int*)p[8];
+    sn.veh_p = (const float*)p[9];
+    sn.env_trigger = (const int*)p[10];
+}
+
+// the view of envs [env0, env0 + n) of a loaded handle; `count_slot` picks the view's own lidar-list counter
+static View make_view(const md_sim* sim, int env0, int n, int count_slot) {
+    View v;
+    const MdConfig& c = sim->cfg;
+    v.cfg = c;
+    v.cfg.n_envs = n;
+    v.cfg.env_base = env0;
+    v.dev = sim->dev;
+    for (int i = 0; i < N_ARR; i++) {
+        char* base = (char*)*arr_slot(const_cast<MdArrays*>(&sim->dev), i);
+        *arr_slot(&v.dev, i) = base + (size_t)env0 * rows_per_env(sim, i) * kRowBytes[i];
+    }
+    set_snapshot_ptrs(v.snap, sim->snap_bufs, sim, env0);
+    set_snapshot_ptrs(v.post, sim->post_bufs, sim, env0);
+    const size_t nv0 = (size_t)env0 * c.slots_per_env, na0 = (size_t)env0 * c.agents_per_env;
+    v.post_body = sim->post_body + nv0 * BODY_ROW;
+    v.post_obs = sim->post_obs + na0 * OBS_STATE(c);
+    v.body_tab = sim->body_tab + nv0 * BODY_ROW;
+    v.veh_act = sim->veh_act + nv0;
+    v.mask = sim->mask + env0;
+    v.lidar_list = sim->lidar_list ? sim->lidar_list + na0 : nullptr;
+    v.lidar_count = sim->lidar_count ? sim->lidar_count + count_slot : nullptr;
+    v.pass = sim->d_pass + 2 * count_slot;
+    return v;
+}
 
 extern "C" int md_abi_version(void) { return MD_ABI_VERSION; }
+extern "C" int md_sizeof_config(void) { return (int)sizeof(MdConfig); }
+extern "C" int md_sizeof_arrays(void) { return (int)sizeof(MdArrays); }
 
 extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     if (!cfg || !out) return -2;
@@ -2334,14 +2490,15 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     }
     md_sim* sim = new md_sim();
     sim->cfg = *cfg;
+    sim->cfg.env_base = 0;
     sim->device = device;
     sim->loaded = false;
     sim->ray_tab = nullptr;
     sim->post_valid = false;
     sim->launches = 0;
-    sim->noise_pass = 0;
-    sim->bank = nullptr; sim->bank_seed = 0; sim->bank_pass = 0;
-    sim->lidar_list = nullptr; sim->lidar_count = nullptr;
+    sim->bank = nullptr; sim->bank_seed = 0; sim->bank_ever = false;
+    sim->lidar_list = nullptr; sim->lidar_count = nullptr; sim->d_pass = nullptr;
+    sim->compact = 0;
     sim->prof_cap = 0;
     sim->prof_n = 0;
     memset(&sim->dev, 0, sizeof(sim->dev));
@@ -2352,7 +2509,6 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
         return -4;
     }
     CK(cudaSetDevice(device));
-    CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
     if (cfg->n_side_lasers > MAX_DET_LASERS || cfg->n_lane_lasers > MAX_DET_LASERS) {
         sim->err = "side / lane-line detector: at most 128 lasers";
         return -4;
@@ -2382,36 +2538,33 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
 extern "C" const char* md_last_error(const md_sim* sim) { return sim ? sim->err.c_str() : "null handle"; }
 extern "C" int64_t md_launch_count(const md_sim* sim) { return sim ? sim->launches : 0; }
 
+static void free_groups(md_sim* sim) {
+    for (HostGroup& g : sim->groups) {
+        if (g.in_flight) cudaStreamSynchronize(g.stream);
+        if (g.gexec) cudaGraphExecDestroy(g.gexec);
+        cudaFree(g.d_blk); cudaFreeHost(g.h_blk); cudaFree(g.d_cobs); cudaFree(g.d_block_counts);
+        cudaEventDestroy(g.done);
+        cudaStreamDestroy(g.stream);
+    }
+    sim->groups.clear();
+}
+
 extern "C" void md_destroy(md_sim* sim) {
     if (!sim) return;
     cudaSetDevice(sim->device);
     if (sim->loaded) {
+        free_groups(sim);
         for (int i = 0; i < N_ARR; i++) cudaFree(*arr_slot(&sim->dev, i));
         for (int i = 0; i < N_SNAP; i++) { cudaFree(sim->snap_bufs[i]); cudaFree(sim->post_bufs[i]); }
         cudaFree(sim->post_body); cudaFree(sim->post_obs);
         cudaFree(sim->body_tab); cudaFree(sim->veh_act); cudaFree(sim->mask);
-        cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_reward); cudaFreeHost(sim->h_cost);
-        cudaFreeHost(sim->h_info_f); cudaFreeHost(sim->h_term); cudaFreeHost(sim->h_trunc); cudaFreeHost(sim->h_mask);
-        cudaFreeHost(sim->h_info_flags);
-        cudaFree(sim->d_actions); cudaFree(sim->d_obs); cudaFree(sim->d_reward); cudaFree(sim->d_cost); cudaFree(sim->d_info_f);
-        cudaFree(sim->d_term); cudaFree(sim->d_trunc); cudaFree(sim->d_mask_in); cudaFree(sim->d_info_flags);
+        cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_mask);
+        cudaFree(sim->d_actions); cudaFree(sim->d_obs); cudaFree(sim->d_mask_in);
     }
     cudaFree(sim->ray_tab);
-    cudaFree(sim->lidar_list); cudaFree(sim->lidar_count);
-    cudaStreamDestroy(sim->stream);
+    cudaFree(sim->lidar_list); cudaFree(sim->lidar_count); cudaFree(sim->d_pass);
+    for (cudaEvent_t e : sim->prof_ev) cudaEventDestroy(e);
     delete sim;
-}
-
-static void set_snapshot_ptrs(Snapshot& sn, void* const* bufs) {
-    sn.env_i = (const int*)bufs[0];
-    sn.veh_s = (const float*)bufs[1];
-    sn.veh_c = (const float*)bufs[2];
-    sn.veh_i = (const int*)bufs[3];
-    sn.veh_idm = (const float*)bufs[4];
-    sn.veh_navi = (const float*)bufs[5];
-    sn.obj_f = (const float*)bufs[6];
-    sn.veh_route = (const int*)bufs[7];
-    sn.veh_rroad = (const int*)bufs[8];
 }
 
 extern "C" int md_snapshot(md_sim* sim) {
@@ -2422,6 +2575,8 @@ extern "C" int md_snapshot(md_sim* sim) {
         CK(cudaMemcpy(sim->snap_bufs[k], *arr_slot(&sim->dev, kSnapIdx[k]), sim->bytes[kSnapIdx[k]], cudaMemcpyDeviceToDevice));
     return 0;
 }
+
+extern "C" int md_host_groups(md_sim* sim, int n_groups);
 
 extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* rows) {
     if (!sim || !host || !rows) return -2;
@@ -2443,9 +2598,7 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
         *arr_slot(&sim->dev, i) = d;
     }
     for (int k = 0; k < N_SNAP; k++) CK(cudaMalloc(&sim->snap_bufs[k], sim->bytes[kSnapIdx[k]] ? sim->bytes[kSnapIdx[k]] : 16));
-    set_snapshot_ptrs(sim->snap, sim->snap_bufs);
     for (int k = 0; k < N_SNAP; k++) CK(cudaMalloc(&sim->post_bufs[k], sim->bytes[kSnapIdx[k]] ? sim->bytes[kSnapIdx[k]] : 16));
-    set_snapshot_ptrs(sim->post, sim->post_bufs);
     CK(cudaMalloc(&sim->post_body, (size_t)NV * BODY_ROW * 4));
     CK(cudaMalloc(&sim->post_obs, (size_t)c.n_envs * c.agents_per_env * OBS_STATE(c) * 4));
     CK(cudaMalloc(&sim->body_tab, (size_t)NV * BODY_ROW * 4));
@@ -2455,16 +2608,21 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
     CK(cudaMalloc(&sim->mask, (size_t)c.n_envs));
     CK(cudaMemset(sim->mask, 0, (size_t)c.n_envs));
     const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_DIM(c);
+    if (c.is_multi_agent) {
+        CK(cudaMalloc(&sim->lidar_list, sizeof(int) * NA));
+        CK(cudaMalloc(&sim->lidar_count, sizeof(unsigned int) * (1 + MAX_HOST_GROUPS)));
+        CK(cudaMemset(sim->lidar_count, 0, sizeof(unsigned int) * (1 + MAX_HOST_GROUPS)));
+    }
+    CK(cudaMalloc(&sim->d_pass, sizeof(uint32_t) * 2 * (1 + MAX_HOST_GROUPS)));
+    CK(cudaMemset(sim->d_pass, 0, sizeof(uint32_t) * 2 * (1 + MAX_HOST_GROUPS)));
     CK(cudaMallocHost(&sim->h_actions, NA * 2 * 4)); CK(cudaMallocHost(&sim->h_obs, NA * od * 4));
-    CK(cudaMallocHost(&sim->h_reward, NA * 4)); CK(cudaMallocHost(&sim->h_cost, NA * 4));
-    CK(cudaMallocHost(&sim->h_info_f, NA * 8 * 4)); CK(cudaMallocHost(&sim->h_term, NA)); CK(cudaMallocHost(&sim->h_trunc, NA));
-    CK(cudaMallocHost(&sim->h_mask, (size_t)c.n_envs)); CK(cudaMallocHost(&sim->h_info_flags, NA * 4));
+    CK(cudaMallocHost(&sim->h_mask, (size_t)c.n_envs));
     CK(cudaMalloc(&sim->d_actions, NA * 2 * 4)); CK(cudaMalloc(&sim->d_obs, NA * od * 4));
-    CK(cudaMalloc(&sim->d_reward, NA * 4)); CK(cudaMalloc(&sim->d_cost, NA * 4)); CK(cudaMalloc(&sim->d_info_f, NA * 8 * 4));
-    CK(cudaMalloc(&sim->d_term, NA)); CK(cudaMalloc(&sim->d_trunc, NA)); CK(cudaMalloc(&sim->d_mask_in, (size_t)c.n_envs));
-    CK(cudaMalloc(&sim->d_info_flags, NA * 4));
+    CK(cudaMalloc(&sim->d_mask_in, (size_t)c.n_envs));
     sim->loaded = true;
+    sim->all = make_view(sim, 0, c.n_envs, 0);
     if (opt_in_smem(sim)) return -4;
+    if (md_host_groups(sim, 1)) return -1;
     return md_snapshot(sim);
 }
 
@@ -2544,7 +2702,6 @@ static StepLaunch post_launch(const MdConfig& c) {  // k_post: epb envs per CTA,
     return L;
 }
 
-
 template <typename K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -2565,70 +2722,110 @@ static int opt_in_smem(md_sim* sim) {
     return 0;
 }
 
-static int launch_pre(md_sim* sim, int mode, const float* actions, float* idm_out, cudaStream_t st) {
-    StepLaunch L = pre_launch(sim->cfg);
+static int launch_pre(md_sim* sim, const View& v, int mode, const float* actions, float* idm_out, cudaStream_t st,
+                      uint32_t d_bank = 0, uint32_t d_noise = 0) {
+    StepLaunch L = pre_launch(v.cfg);
     static const int use_teams = env_int("MD_PRE_TEAM", 1);
-    k_pre<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, actions, idm_out, sim->veh_act, use_teams);
+    k_pre<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, actions, idm_out, v.veh_act, use_teams,
+                                               (d_bank | d_noise) ? v.pass : nullptr, d_bank, d_noise);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_dyn(md_sim* sim, int mode, const float* ext_act3, int n_sub, cudaStream_t st) {
-    StepLaunch L = dyn_launch(sim->cfg);
-    k_dyn<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, sim->veh_act, ext_act3, n_sub);
+static int launch_dyn(md_sim* sim, const View& v, int mode, const float* ext_act3, int n_sub, cudaStream_t st) {
+    StepLaunch L = dyn_launch(v.cfg);
+    k_dyn<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, v.veh_act, ext_act3, n_sub);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_post(md_sim* sim, int mode, StepOut out, const uint8_t* mask, cudaStream_t st) {
-    StepLaunch L = post_launch(sim->cfg);
+static int launch_post(md_sim* sim, const View& v, int mode, StepOut out, const uint8_t* mask, cudaStream_t st) {
+    StepLaunch L = post_launch(v.cfg);
     static const int team_pref = env_int("MD_POST_TEAM", 0);   // 0 = adaptive, 1 = off, 2 / 4 / 8 / 16 / 32 lanes per vehicle
-    k_post<<<L.blocks, L.threads, L.smem, st>>>(sim->cfg, sim->dev, mode, L.epb, out, sim->body_tab, mask, sim->mask, sim->snap, team_pref);
+    k_post<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, out, v.body_tab, mask, v.mask, v.snap, team_pref);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_restore(md_sim* sim, const uint8_t* mask, cudaStream_t st) {
-    long long nv = (long long)sim->cfg.n_envs * sim->cfg.slots_per_env;
-    k_restore<<<(int)((nv + 255) / 256), 256, 0, st>>>(sim->cfg, sim->dev, sim->snap, mask);
+static int launch_restore(md_sim* sim, const View& v, const uint8_t* mask, cudaStream_t st) {
+    long long nv = (long long)v.cfg.n_envs * v.cfg.slots_per_env;
+    k_restore<<<(int)((nv + 255) / 256), 256, 0, st>>>(v.cfg, v.dev, v.snap, mask, sim->bank_ever ? 1 : 0);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_lidar(md_sim* sim, float* out, int stride, int off, int32_t* hit, const uint8_t* mask, cudaStream_t st,
-                        const int* agent_flags = nullptr, int need_flag = 0) {
-    const MdConfig& c = sim->cfg;
+// scenario draw from the bank for the masked envs (all envs if mask == NULL): rows + body rows + state observation
+static int launch_restore_bank(md_sim* sim, View& v, float* obs, const uint8_t* mask, cudaStream_t st) {
+    const MdConfig& c = v.cfg;
+    const md_sim* bk = sim->bank;
+    const long long nv = (long long)c.n_envs * c.slots_per_env;
+    BankView B;
+    B.post = bk->all.post; B.body = bk->post_body; B.obs = bk->post_obs; B.veh_p = bk->dev.veh_p;
+    B.env_trigger = bk->dev.env_trigger; B.n = bk->cfg.n_envs;
+    k_restore_bank<<<(int)((nv + 255) / 256), 256, 0, st>>>(c, v.dev, B, sim->bank_seed, v.pass, v.body_tab, obs, mask);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_lidar(md_sim* sim, const View& v, uint32_t noise_off, float* out, int stride, int off, int32_t* hit,
+                        const uint8_t* mask, cudaStream_t st, const int* agent_flags = nullptr, int need_flag = 0) {
+    const MdConfig& c = v.cfg;
     long long na = (long long)c.n_envs * c.agents_per_env;
     int blocks = (int)((na + LIDAR_WARPS - 1) / LIDAR_WARPS);
     size_t smem = lidar_smem_per_warp(c.slots_per_env, c.objs_per_env, c.n_lasers) * LIDAR_WARPS;
     const int* list = nullptr;
-    if (agent_flags != nullptr) {   // multi-agent pass: compact the observing seats first (k_lidar_list)
-        if (!sim->lidar_list) {
-            CK(cudaMalloc(&sim->lidar_list, sizeof(int) * (size_t)na));
-            CK(cudaMalloc(&sim->lidar_count, sizeof(unsigned int)));
-        }
-        CK(cudaMemsetAsync(sim->lidar_count, 0, sizeof(unsigned int), st));
-        k_lidar_list<<<(int)((na + 255) / 256), 256, 0, st>>>(na, agent_flags, need_flag, sim->lidar_list, sim->lidar_count);
+    if (agent_flags != nullptr && v.lidar_list != nullptr) {   // multi-agent pass: compact the observing seats first
+        CK(cudaMemsetAsync(v.lidar_count, 0, sizeof(unsigned int), st));
+        k_lidar_list<<<(int)((na + 255) / 256), 256, 0, st>>>(na, agent_flags, need_flag, v.lidar_list, v.lidar_count);
         sim->launches++;
-        list = sim->lidar_list;
+        list = v.lidar_list;
     }
-    k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, sim->body_tab, sim->dev.obj_f, sim->dev.veh_i, sim->dev.veh_p, out, stride, off, hit, mask,
-                                                    agent_flags, need_flag, sim->ray_tab, sim->noise_pass++, list, sim->lidar_count);
+    k_lidar<<<blocks, LIDAR_WARPS * 32, smem, st>>>(c, v.body_tab, v.dev.obj_f, v.dev.veh_i, v.dev.veh_p, out, stride, off, hit, mask,
+                                                    agent_flags, need_flag, sim->ray_tab, off >= 0 ? v.pass : nullptr, noise_off, list,
+                                                    v.lidar_count);
     sim->launches++;
     CK(cudaGetLastError());
     if (off >= 0 && (c.n_side_lasers > 0 || c.n_lane_lasers > 0)) {  // the detector blocks of the same observation rows
-        k_linedet<<<blocks, LIDAR_WARPS * 32, 0, st>>>(c, sim->dev, sim->body_tab, out, mask, agent_flags, need_flag,
+        k_linedet<<<blocks, LIDAR_WARPS * 32, 0, st>>>(c, v.dev, v.body_tab, out, mask, agent_flags, need_flag,
                                                        sim->ray_tab + 2 * MAX_LASERS, sim->ray_tab + 2 * MAX_LASERS + 2 * MAX_DET_LASERS);
         sim->launches++;
         CK(cudaGetLastError());
     }
     return 0;
 }
-static int launch_respawn(md_sim* sim, StepOut out, cudaStream_t st) {
-    const MdConfig& c = sim->cfg;
+static int launch_respawn(md_sim* sim, const View& v, StepOut out, cudaStream_t st) {
+    const MdConfig& c = v.cfg;
     int blocks = (c.n_envs + RESPAWN_WARPS - 1) / RESPAWN_WARPS;
     size_t smem = sizeof(Fp) * (size_t)c.slots_per_env * RESPAWN_WARPS;
-    k_respawn<<<blocks, RESPAWN_WARPS * 32, smem, st>>>(c, sim->dev, out, sim->body_tab);
+    k_respawn<<<blocks, RESPAWN_WARPS * 32, smem, st>>>(c, v.dev, out, v.body_tab);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// env.reset of a view's masked envs (all of them if mask == NULL).  With a scenario bank attached the envs restart in a
+// scenario DRAWN from the bank, exactly like the auto-reset of md_step_autoreset (BaseEnv.reset(seed=None),
+// envs/base_env.py:886-891) - never a mix of the env's first scenario and its last draw.
+static int reset_impl(md_sim* sim, View& v, const uint8_t* env_mask_dev, float* obs_dev, cudaStream_t st, bool whole_batch) {
+    StepOut out = {obs_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (sim->bank && obs_dev != nullptr) {
+        if (launch_restore_bank(sim, v, obs_dev, env_mask_dev, st)) return -1;
+    } else {
+        if (launch_restore(sim, v, env_mask_dev, st)) return -1;
+        if (launch_post(sim, v, MODE_RESET, out, env_mask_dev, st)) return -1;
+        if (whole_batch && env_mask_dev == nullptr && obs_dev != nullptr) {
+            // a full reset: keep the resulting state so that later auto-resets are plain row copies (k_restore_post)
+            const MdConfig& c = sim->cfg;
+            for (int k = 0; k < N_SNAP; k++)
+                CK(cudaMemcpyAsync(sim->post_bufs[k], *arr_slot(&sim->dev, kSnapIdx[k]), sim->bytes[kSnapIdx[k]], cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(sim->post_body, sim->body_tab, (size_t)c.n_envs * c.slots_per_env * BODY_ROW * 4, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpy2DAsync(sim->post_obs, OBS_STATE(c) * 4, obs_dev, (size_t)OBS_DIM(c) * 4, OBS_STATE(c) * 4,
+                                 (size_t)c.n_envs * c.agents_per_env, cudaMemcpyDeviceToDevice, st));
+            sim->post_valid = true;
+        }
+    }
+    if (launch_lidar(sim, v, 0, obs_dev, OBS_DIM(v.cfg), OBS_STATE(v.cfg), nullptr, env_mask_dev, st)) return -1;
+    k_bump<<<1, 1, 0, st>>>(v.pass, (sim->bank && obs_dev != nullptr) ? 1u : 0u, 1u);   // this pass is spent
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -2637,71 +2834,68 @@ static int launch_respawn(md_sim* sim, StepOut out, cudaStream_t st) {
 extern "C" int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    StepOut out = {obs_dev, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (launch_restore(sim, env_mask_dev, st)) return -1;
-    if (launch_post(sim, MODE_RESET, out, env_mask_dev, st)) return -1;
-    if (env_mask_dev == nullptr && obs_dev != nullptr) {
-        // a full reset: keep the resulting state so that later auto-resets are plain row copies (k_restore_post)
-        const MdConfig& c = sim->cfg;
-        for (int k = 0; k < N_SNAP; k++)
-            CK(cudaMemcpyAsync(sim->post_bufs[k], *arr_slot(&sim->dev, kSnapIdx[k]), sim->bytes[kSnapIdx[k]], cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(sim->post_body, sim->body_tab, (size_t)c.n_envs * c.slots_per_env * BODY_ROW * 4, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpy2DAsync(sim->post_obs, OBS_STATE(c) * 4, obs_dev, (size_t)OBS_DIM(c) * 4, OBS_STATE(c) * 4,
-                             (size_t)c.n_envs * c.agents_per_env, cudaMemcpyDeviceToDevice, st));
-        sim->post_valid = true;
-    }
-    return launch_lidar(sim, obs_dev, OBS_DIM(sim->cfg), OBS_STATE(sim->cfg), nullptr, env_mask_dev, st);
+    return reset_impl(sim, sim->all, env_mask_dev, obs_dev, (cudaStream_t)stream, true);
 }
 
-// one env.step; `fused_reset` (single agent only): finished envs are reset in place before the observation is taken, so
-// that the auto-reset costs one extra launch (k_post in MODE_RESET | MODE_RESTORE over the envs k_post just marked)
+// one env.step of a view; `fused_reset` (single agent only): finished envs are reset in place before the observation is
+// taken, so that the auto-reset costs one extra launch (a row copy from the post-reset snapshot or from the scenario bank)
 #define N_PROF_EV 6
-static int step_impl(md_sim* sim, const float* actions_dev, StepOut out, cudaStream_t st, bool fused_reset) {
-    const bool prof = sim->prof_n < sim->prof_cap;
+static int step_impl(md_sim* sim, View& v, const float* actions_dev, StepOut out, cudaStream_t st, bool fused_reset, bool may_prof) {
+    const bool prof = may_prof && sim->prof_n < sim->prof_cap;
     cudaEvent_t* ev = prof ? &sim->prof_ev[N_PROF_EV * sim->prof_n] : nullptr;
     if (prof) CK(cudaEventRecord(ev[0], st));
-    if (launch_pre(sim, MODE_AGENT_PRE | MODE_TRIGGER | MODE_IDM, actions_dev, nullptr, st)) return -1;
+    // k_pre spends the step's passes up front: one scenario-draw pass if finished envs will draw from a bank, two
+    // observation passes (single agent uses the first; multi-agent: transition pass + newborn pass)
+    const uint32_t d_bank = (fused_reset && sim->post_valid && sim->bank) ? 1u : 0u;
+    if (launch_pre(sim, v, MODE_AGENT_PRE | MODE_TRIGGER | MODE_IDM, actions_dev, nullptr, st, d_bank, 2u)) return -1;
     if (prof) CK(cudaEventRecord(ev[1], st));
-    if (launch_dyn(sim, MODE_DYN | MODE_CONTACTS, nullptr, sim->cfg.decision_repeat, st)) return -1;
+    if (launch_dyn(sim, v, MODE_DYN | MODE_CONTACTS, nullptr, v.cfg.decision_repeat, st)) return -1;
     if (prof) CK(cudaEventRecord(ev[2], st));
-    if (launch_post(sim, MODE_POST | MODE_OUT | MODE_REMOVE | (fused_reset ? MODE_MARK_DONE : 0), out, nullptr, st)) return -1;
+    if (launch_post(sim, v, MODE_POST | MODE_OUT | MODE_REMOVE | (fused_reset ? MODE_MARK_DONE : 0), out, nullptr, st)) return -1;
     if (prof) CK(cudaEventRecord(ev[3], st));
     if (fused_reset && sim->post_valid && sim->bank) {
-        const MdConfig& c = sim->cfg;
-        const md_sim* bk = sim->bank;
-        const long long nv = (long long)c.n_envs * c.slots_per_env;
-        BankView B;
-        B.post = bk->post; B.body = bk->post_body; B.obs = bk->post_obs; B.veh_p = bk->dev.veh_p;
-        B.env_trigger = bk->dev.env_trigger; B.n = bk->cfg.n_envs;
-        k_restore_bank<<<(int)((nv + 255) / 256), 256, 0, st>>>(c, sim->dev, B, sim->bank_seed, sim->bank_pass++, sim->body_tab, out.obs, sim->mask);
-        sim->launches++;
-        CK(cudaGetLastError());
+        if (launch_restore_bank(sim, v, out.obs, v.mask, st)) return -1;
     } else if (fused_reset && sim->post_valid) {
-        const long long nv = (long long)sim->cfg.n_envs * sim->cfg.slots_per_env;
-        k_restore_post<<<(int)((nv + 255) / 256), 256, 0, st>>>(sim->cfg, sim->dev, sim->post, sim->post_body, sim->post_obs,
-                                                               sim->body_tab, out.obs, sim->mask);
+        const long long nv = (long long)v.cfg.n_envs * v.cfg.slots_per_env;
+        k_restore_post<<<(int)((nv + 255) / 256), 256, 0, st>>>(v.cfg, v.dev, v.post, v.post_body, v.post_obs, v.body_tab, out.obs, v.mask);
         sim->launches++;
         CK(cudaGetLastError());
     } else if (fused_reset) {
         StepOut ro = {out.obs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-        if (launch_post(sim, MODE_RESET | MODE_RESTORE, ro, sim->mask, st)) return -1;
+        if (launch_post(sim, v, MODE_RESET | MODE_RESTORE, ro, v.mask, st)) return -1;
     }
     if (prof) CK(cudaEventRecord(ev[4], st));
-    const int od = OBS_DIM(sim->cfg);
-    if (!sim->cfg.is_multi_agent) {
-        if (launch_lidar(sim, out.obs, od, OBS_STATE(sim->cfg), nullptr, nullptr, st)) return -1;
+    const int od = OBS_DIM(v.cfg), os = OBS_STATE(v.cfg);
+    const uint32_t np = 0;
+    if (!v.cfg.is_multi_agent) {
+        if (launch_lidar(sim, v, np, out.obs, od, os, nullptr, nullptr, st)) return -1;
     } else {
         // multi-agent: everyone who produced a transition observes (incl. agents that just finished), then finished
         // vehicles leave / freeze, at most one agent per env is respawned and observes the world after that
         if (!out.info_flags) { sim->err = "multi-agent md_step needs info_flags"; return -2; }
-        if (launch_lidar(sim, out.obs, od, OBS_STATE(sim->cfg), nullptr, nullptr, st, out.info_flags, FL_VALID)) return -1;
-        if (launch_respawn(sim, out, st)) return -1;
-        if (sim->cfg.allow_respawn && launch_lidar(sim, out.obs, od, OBS_STATE(sim->cfg), nullptr, nullptr, st, out.info_flags, FL_NEWBORN))
+        if (launch_lidar(sim, v, np, out.obs, od, os, nullptr, nullptr, st, out.info_flags, FL_VALID)) return -1;
+        if (launch_respawn(sim, v, out, st)) return -1;
+        if (v.cfg.allow_respawn && launch_lidar(sim, v, np + 1, out.obs, od, os, nullptr, nullptr, st, out.info_flags, FL_NEWBORN))
             return -1;
     }
     if (prof) { CK(cudaEventRecord(ev[5], st)); sim->prof_n++; }
     return 0;
+}
+
+static int autoreset_impl(md_sim* sim, View& v, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, cudaStream_t st,
+                          bool whole_batch) {
+    if (v.cfg.is_multi_agent)
+        k_done_mask_ma<<<(v.cfg.n_envs + 255) / 256, 256, 0, st>>>(v.cfg, v.dev.veh_i, v.mask);
+    else
+        k_done_mask<<<(v.cfg.n_envs + 255) / 256, 256, 0, st>>>(v.cfg, terminated_dev, truncated_dev, v.mask);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return reset_impl(sim, v, v.mask, obs_dev, st, whole_batch);
+}
+static int step_autoreset_impl(md_sim* sim, View& v, const float* actions_dev, StepOut out, cudaStream_t st, bool whole_batch) {
+    if (!v.cfg.is_multi_agent && out.term && out.trunc) return step_impl(sim, v, actions_dev, out, st, true, whole_batch);
+    if (step_impl(sim, v, actions_dev, out, st, false, whole_batch)) return -1;
+    return autoreset_impl(sim, v, out.term, out.trunc, out.obs, st, whole_batch);
 }
 
 extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
@@ -2709,20 +2903,22 @@ extern "C" int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, fl
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     StepOut out = {obs_dev, reward_dev, cost_dev, terminated_dev, truncated_dev, info_flags_dev, info_f_dev};
-    return step_impl(sim, actions_dev, out, (cudaStream_t)stream, false);
+    return step_impl(sim, sim->all, actions_dev, out, (cudaStream_t)stream, false, true);
 }
 
-extern "C" int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, void* stream);
 extern "C" int md_step_autoreset(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
                                  uint8_t* terminated_dev, uint8_t* truncated_dev, int32_t* info_flags_dev, float* info_f_dev,
                                  void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     StepOut out = {obs_dev, reward_dev, cost_dev, terminated_dev, truncated_dev, info_flags_dev, info_f_dev};
-    if (!sim->cfg.is_multi_agent && terminated_dev && truncated_dev)
-        return step_impl(sim, actions_dev, out, (cudaStream_t)stream, true);
-    if (step_impl(sim, actions_dev, out, (cudaStream_t)stream, false)) return -1;
-    return md_autoreset(sim, terminated_dev, truncated_dev, obs_dev, stream);
+    return step_autoreset_impl(sim, sim->all, actions_dev, out, (cudaStream_t)stream, true);
+}
+
+extern "C" int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    return autoreset_impl(sim, sim->all, terminated_dev, truncated_dev, obs_dev, (cudaStream_t)stream, true);
 }
 
 extern "C" int md_attach_bank(md_sim* sim, md_sim* bank, int seed) {
@@ -2740,10 +2936,17 @@ extern "C" int md_attach_bank(md_sim* sim, md_sim* bank, int seed) {
         sim->err = "scenario bank: single-agent, trigger-mode worlds only (respawn-mode tables are per env)";
         return -2;
     }
-    if (sim->bytes[0] != bank->bytes[0]) { sim->err = "scenario bank: both handles must load the same map set (same map ids)"; return -2; }
+    for (int i = 0; i < 11; i++)   // the shared map tables (map_desc ... grid_items) and the lane grids
+        if (sim->rows[i] != bank->rows[i]) { sim->err = "scenario bank: both handles must load the same map set (same map ids)"; return -2; }
+    if (sim->rows[21] != bank->rows[21] || sim->rows[22] != bank->rows[22]) {
+        sim->err = "scenario bank: both handles must load the same map set (same map ids)";
+        return -2;
+    }
     sim->bank = bank;
+    sim->bank_ever = true;
     sim->bank_seed = (uint32_t)seed;
-    sim->bank_pass = 0;
+    // every view's draw counter restarts
+    CK(cudaMemset2D(sim->d_pass, 2 * sizeof(uint32_t), 0, sizeof(uint32_t), 1 + MAX_HOST_GROUPS));
     return 0;
 }
 
@@ -2775,101 +2978,253 @@ extern "C" int md_profile_end(md_sim* sim, float* ms, int cap) {
     return n;
 }
 
-extern "C" int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, void* stream) {
-    if (!sim || !sim->loaded) return -2;
-    CK(cudaSetDevice(sim->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    if (sim->cfg.is_multi_agent)
-        k_done_mask_ma<<<(sim->cfg.n_envs + 255) / 256, 256, 0, st>>>(sim->cfg, sim->dev.veh_i, sim->mask);
-    else
-        k_done_mask<<<(sim->cfg.n_envs + 255) / 256, 256, 0, st>>>(sim->cfg, terminated_dev, truncated_dev, sim->mask);
-    sim->launches++;
-    CK(cudaGetLastError());
-    return md_reset(sim, sim->mask, obs_dev, stream);
-}
-
 extern "C" int md_lidar(md_sim* sim, float* frac_dev, int32_t* hit_dev, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     cudaStream_t st = (cudaStream_t)stream;
     // refresh the body rows from the current state without moving anything
     StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (launch_post(sim, 0, out, nullptr, st)) return -1;
-    return launch_lidar(sim, frac_dev, sim->cfg.n_lasers, -1, hit_dev, nullptr, st);
+    if (launch_post(sim, sim->all, 0, out, nullptr, st)) return -1;
+    return launch_lidar(sim, sim->all, 0, frac_dev, sim->cfg.n_lasers, -1, hit_dev, nullptr, st);
 }
 extern "C" int md_dynamics(md_sim* sim, const float* act3_dev, int n_sub, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
-    return launch_dyn(sim, MODE_DYN | MODE_EXT_ACT, act3_dev, n_sub, (cudaStream_t)stream);
+    return launch_dyn(sim, sim->all, MODE_DYN | MODE_EXT_ACT, act3_dev, n_sub, (cudaStream_t)stream);
 }
 extern "C" int md_after_step(md_sim* sim, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     StepOut out = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    return launch_post(sim, MODE_POST | MODE_CLEAR_FLAGS, out, nullptr, (cudaStream_t)stream);
+    return launch_post(sim, sim->all, MODE_POST | MODE_CLEAR_FLAGS, out, nullptr, (cudaStream_t)stream);
 }
 extern "C" int md_idm(md_sim* sim, float* out_actions_dev, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
-    return launch_pre(sim, MODE_IDM_OUT, nullptr, out_actions_dev, (cudaStream_t)stream);
+    return launch_pre(sim, sim->all, MODE_IDM_OUT, nullptr, out_actions_dev, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer path
+// (Re)partition the batch into n_groups contiguous env ranges for the host-buffer entry points.  Every group owns a
+// stream, a packed output block on the device with a pinned mirror of the same layout, and its rows of the handle-wide
+// action / observation staging buffers.  Earlier groups get the higher stream priority, so inside one md_step_host call
+// group k's kernels finish - and its D2H copy starts - while group k+1 is still computing.
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+extern "C" int md_host_groups(md_sim* sim, int n_groups) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    const MdConfig& c = sim->cfg;
+    if (n_groups < 1) n_groups = 1;
+    if (n_groups > MAX_HOST_GROUPS) n_groups = MAX_HOST_GROUPS;
+    if (n_groups > c.n_envs) n_groups = c.n_envs;
+    for (HostGroup& g : sim->groups)
+        if (g.in_flight) { sim->err = "md_host_groups: a group is in flight (md_host_recv it first)"; return -8; }
+    // the new groups continue the counters of group 0 (of the whole-batch view when there were no groups yet)
+    uint32_t ctr[2];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(ctr, sim->d_pass + (sim->groups.empty() ? 0 : 2), sizeof(ctr), cudaMemcpyDeviceToHost));
+    free_groups(sim);
+    int lo_prio = 0, hi_prio = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));   // numerically lower = higher priority
+    const size_t od = OBS_DIM(c);
+    sim->groups.resize(n_groups);
+    for (int k = 0; k < n_groups; k++) {
+        HostGroup& g = sim->groups[k];
+        g.env0 = (int)((long long)c.n_envs * k / n_groups);
+        g.n_envs = (int)((long long)c.n_envs * (k + 1) / n_groups) - g.env0;
+        g.na = (size_t)g.n_envs * c.agents_per_env;
+        g.v = make_view(sim, g.env0, g.n_envs, 1 + k);
+        CK(cudaMemcpy(g.v.pass, ctr, sizeof(ctr), cudaMemcpyHostToDevice));
+        int prio = hi_prio + k;
+        if (prio > lo_prio) prio = lo_prio;
+        CK(cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, prio));
+        CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+        const size_t n = g.na;
+        g.off_cost = align16(n * 4);
+        g.off_flags = g.off_cost + align16(n * 4);
+        g.off_info_f = g.off_flags + align16(n * 4);
+        g.off_term = g.off_info_f + align16(n * 32);
+        g.off_trunc = g.off_term + align16(n);
+        g.off_count = g.off_trunc + align16(n);
+        g.blk_bytes = g.off_count + 16;
+        CK(cudaMalloc(&g.d_blk, g.blk_bytes));
+        CK(cudaMemset(g.d_blk, 0, g.blk_bytes));
+        CK(cudaMallocHost(&g.h_blk, g.blk_bytes));
+        memset(g.h_blk, 0, g.blk_bytes);
+        const size_t a0 = (size_t)g.env0 * c.agents_per_env;
+        g.d_actions = sim->d_actions + a0 * 2; g.h_actions = sim->h_actions + a0 * 2;
+        g.h_obs = sim->h_obs + a0 * od;
+        g.out.obs = sim->d_obs + a0 * od;
+        g.out.reward = (float*)g.d_blk; g.out.cost = (float*)(g.d_blk + g.off_cost);
+        g.out.info_flags = (int*)(g.d_blk + g.off_flags); g.out.info_f = (float*)(g.d_blk + g.off_info_f);
+        g.out.term = g.d_blk + g.off_term; g.out.trunc = g.d_blk + g.off_trunc;
+        g.d_cobs = nullptr; g.d_block_counts = nullptr;
+        g.gexec = nullptr; g.gkey = 0; g.glaunches = 0;
+        g.in_flight = false; g.pending_compact = false;
+    }
+    return 0;
+}
+extern "C" int md_host_group_count(const md_sim* sim) { return sim && sim->loaded ? (int)sim->groups.size() : 0; }
+
+// Multi-agent handles: with compact != 0 only the observation rows of the seats that produced a transition (FL_VALID in
+// info_flags, newborn seats included) are copied to the host, packed in ascending seat order at the start of the group's
+// obs rows; the scalars always come back for every seat, so the host finds row j's seat as the j-th FL_VALID entry.
+extern "C" int md_host_compact(md_sim* sim, int compact) {
+    if (!sim || !sim->loaded) return -2;
+    if (compact && !sim->cfg.is_multi_agent) { sim->err = "md_host_compact: multi-agent handles only"; return -2; }
+    sim->compact = compact ? 1 : 0;
+    return 0;
+}
+
+// out[0..7] = addresses of group `group`'s pinned buffers: obs rows, reward, cost, terminated, truncated, info_flags,
+// info_f, actions; range[0..2] = first env, env count, valid-row count of the last received step (compact mode, else all)
+extern "C" int md_host_group_views(md_sim* sim, int group, void** out8, int* range3) {
+    if (!sim || !sim->loaded || group < 0 || group >= (int)sim->groups.size()) return -2;
+    HostGroup& g = sim->groups[group];
+    if (out8) {
+        out8[0] = g.h_obs; out8[1] = g.h_blk; out8[2] = g.h_blk + g.off_cost; out8[3] = g.h_blk + g.off_term;
+        out8[4] = g.h_blk + g.off_trunc; out8[5] = g.h_blk + g.off_flags; out8[6] = g.h_blk + g.off_info_f; out8[7] = g.h_actions;
+    }
+    if (range3) {
+        range3[0] = g.env0; range3[1] = g.n_envs;
+        range3[2] = sim->compact ? (int)*(unsigned int*)(g.h_blk + g.off_count) : (int)g.na;
+    }
+    return 0;
+}
+// the handle-wide view (group 0's buffers; with one group - the default - they cover the whole batch)
+extern "C" int md_host_views(md_sim* sim, void** out8) { return md_host_group_views(sim, 0, out8, nullptr); }
+
+// the stream work of one group step: H2D of its actions, the kernels, D2H of the packed scalars and of the observation rows
+static int enqueue_group_step(md_sim* sim, HostGroup& g, int autoreset) {
+    const size_t od = OBS_DIM(sim->cfg);
+    CK(cudaMemcpyAsync(g.d_actions, g.h_actions, g.na * 2 * 4, cudaMemcpyHostToDevice, g.stream));
+    // auto-reset overwrites only the observation rows of finished envs; the scalars keep the finished step's values
+    if (autoreset ? step_autoreset_impl(sim, g.v, g.d_actions, g.out, g.stream, false)
+                  : step_impl(sim, g.v, g.d_actions, g.out, g.stream, false, false))
+        return -1;
+    if (sim->compact) {
+        const int nb = (int)((g.na + COMPACT_T - 1) / COMPACT_T);
+        k_valid_count<<<nb, COMPACT_T, 0, g.stream>>>((long long)g.na, g.out.info_flags, g.d_block_counts);
+        k_valid_gather<<<nb, COMPACT_T, 0, g.stream>>>((long long)g.na, g.out.info_flags, g.d_block_counts, (int)od, g.out.obs, g.d_cobs,
+                                                       (unsigned int*)(g.d_blk + g.off_count));
+        sim->launches += 2;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(g.h_blk, g.d_blk, g.blk_bytes, cudaMemcpyDeviceToHost, g.stream));
+    if (!sim->compact) CK(cudaMemcpyAsync(g.h_obs, g.out.obs, g.na * od * 4, cudaMemcpyDeviceToHost, g.stream));
+    return 0;
+}
+// enqueue one env.step of a group on its stream and return without waiting; md_host_recv completes it.
+// actions == NULL: the caller already wrote them into the group's pinned action buffer.
+extern "C" int md_host_send(md_sim* sim, int group, const float* actions, int autoreset) {
+    if (!sim || !sim->loaded || group < 0 || group >= (int)sim->groups.size()) return -2;
+    CK(cudaSetDevice(sim->device));
+    HostGroup& g = sim->groups[group];
+    if (g.in_flight) { sim->err = "md_host_send: the group is already in flight"; return -8; }
+    if (actions && actions != g.h_actions) memcpy(g.h_actions, actions, g.na * 2 * 4);
+    if (sim->compact && !g.d_cobs) {
+        CK(cudaMalloc(&g.d_cobs, g.na * OBS_DIM(sim->cfg) * 4));
+        CK(cudaMalloc(&g.d_block_counts, sizeof(unsigned int) * ((g.na + COMPACT_T - 1) / COMPACT_T)));
+    }
+    static const int use_graph = env_int("MD_HOST_GRAPH", 1);
+    if (use_graph) {
+        // what shapes the launch sequence of a step: auto-reset or not, compaction, the bank, whether resets are row copies
+        const uint64_t key = 1ull | (autoreset ? 2ull : 0ull) | (sim->compact ? 4ull : 0ull) | (sim->post_valid ? 8ull : 0ull) |
+                             ((uint64_t)(uintptr_t)sim->bank << 4);
+        if (g.gexec == nullptr || g.gkey != key) {
+            if (g.gexec) { cudaGraphExecDestroy(g.gexec); g.gexec = nullptr; }
+            const int64_t l0 = sim->launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_group_step(sim, g, autoreset);
+            const cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+            g.glaunches = (int)(sim->launches - l0);
+            sim->launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            CK(ce);
+            CK(cudaGraphInstantiate(&g.gexec, graph, 0));
+            CK(cudaGraphDestroy(graph));
+            g.gkey = key;
+        }
+        CK(cudaGraphLaunch(g.gexec, g.stream));
+        sim->launches += g.glaunches;
+    } else if (enqueue_group_step(sim, g, autoreset)) return -1;
+    g.pending_compact = sim->compact != 0;
+    CK(cudaEventRecord(g.done, g.stream));
+    g.in_flight = true;
+    return 0;
+}
+// wait for a group's step; afterwards its pinned buffers hold the results (md_host_group_views)
+extern "C" int md_host_recv(md_sim* sim, int group) {
+    if (!sim || !sim->loaded || group < 0 || group >= (int)sim->groups.size()) return -2;
+    CK(cudaSetDevice(sim->device));
+    HostGroup& g = sim->groups[group];
+    if (!g.in_flight) { sim->err = "md_host_recv: nothing in flight for this group"; return -8; }
+    CK(cudaEventSynchronize(g.done));
+    if (g.pending_compact) {   // the number of valid rows came back with the scalars: fetch exactly those rows
+        const size_t cnt = *(unsigned int*)(g.h_blk + g.off_count);
+        if (cnt) {
+            CK(cudaMemcpyAsync(g.h_obs, g.d_cobs, cnt * OBS_DIM(sim->cfg) * 4, cudaMemcpyDeviceToHost, g.stream));
+            CK(cudaStreamSynchronize(g.stream));
+        }
+        g.pending_compact = false;
+    }
+    g.in_flight = false;
+    return 0;
 }
 
 extern "C" int md_reset_host(md_sim* sim, const uint8_t* env_mask, float* obs) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
+    for (HostGroup& g : sim->groups)
+        if (g.in_flight) { sim->err = "md_reset_host: a group is in flight (md_host_recv it first)"; return -8; }
     const MdConfig& c = sim->cfg;
     const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_DIM(c);
+    cudaStream_t st = sim->groups[0].stream;
     const uint8_t* dm = nullptr;
     if (env_mask) {
         memcpy(sim->h_mask, env_mask, (size_t)c.n_envs);
-        CK(cudaMemcpyAsync(sim->d_mask_in, sim->h_mask, (size_t)c.n_envs, cudaMemcpyHostToDevice, sim->stream));
+        CK(cudaMemcpyAsync(sim->d_mask_in, sim->h_mask, (size_t)c.n_envs, cudaMemcpyHostToDevice, st));
         dm = sim->d_mask_in;
     }
-    if (md_reset(sim, dm, sim->d_obs, sim->stream)) return -1;
-    CK(cudaMemcpyAsync(sim->h_obs, sim->d_obs, NA * od * 4, cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
-    memcpy(obs, sim->h_obs, NA * od * 4);
+    if (reset_impl(sim, sim->all, dm, sim->d_obs, st, true)) return -1;
+    CK(cudaMemcpyAsync(sim->h_obs, sim->d_obs, NA * od * 4, cudaMemcpyDeviceToHost, st));
+    for (HostGroup& g : sim->groups) {   // a whole-batch pass advances every group's counters
+        k_bump<<<1, 1, 0, st>>>(g.v.pass, sim->bank ? 1u : 0u, 1u);
+        sim->launches++;
+    }
+    CK(cudaStreamSynchronize(st));
+    if (obs) memcpy(obs, sim->h_obs, NA * od * 4);
     return 0;
 }
 
+// env.step of the whole batch through HOST buffers, synchronous: every group is sent, then every group is received.
+// Output pointers may be NULL: the caller then reads the pinned buffers in place (md_host_group_views).
 extern "C" int md_step_host(md_sim* sim, const float* actions, float* obs, float* reward, float* cost, uint8_t* terminated,
                             uint8_t* truncated, int32_t* info_flags, float* info_f, int autoreset) {
     if (!sim || !sim->loaded) return -2;
-    CK(cudaSetDevice(sim->device));
     const MdConfig& c = sim->cfg;
-    const size_t NA = (size_t)c.n_envs * c.agents_per_env, od = OBS_DIM(c);
-    if (actions && actions != sim->h_actions) memcpy(sim->h_actions, actions, NA * 2 * 4);
-    CK(cudaMemcpyAsync(sim->d_actions, sim->h_actions, NA * 2 * 4, cudaMemcpyHostToDevice, sim->stream));
-    // auto-reset overwrites only the observation rows of finished envs; the scalars keep the finished step's values
-    if (autoreset ? md_step_autoreset(sim, sim->d_actions, sim->d_obs, sim->d_reward, sim->d_cost, sim->d_term, sim->d_trunc,
-                                      sim->d_info_flags, sim->d_info_f, sim->stream)
-                  : md_step(sim, sim->d_actions, sim->d_obs, sim->d_reward, sim->d_cost, sim->d_term, sim->d_trunc,
-                            sim->d_info_flags, sim->d_info_f, sim->stream))
-        return -1;
-    CK(cudaMemcpyAsync(sim->h_reward, sim->d_reward, NA * 4, cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaMemcpyAsync(sim->h_cost, sim->d_cost, NA * 4, cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaMemcpyAsync(sim->h_term, sim->d_term, NA, cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaMemcpyAsync(sim->h_trunc, sim->d_trunc, NA, cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaMemcpyAsync(sim->h_info_flags, sim->d_info_flags, NA * 4, cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaMemcpyAsync(sim->h_info_f, sim->d_info_f, NA * 8 * 4, cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaMemcpyAsync(sim->h_obs, sim->d_obs, NA * od * 4, cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
-    // NULL outputs: the caller reads the pinned staging buffers in place (md_host_views)
-    if (obs) memcpy(obs, sim->h_obs, NA * od * 4);
-    if (reward) memcpy(reward, sim->h_reward, NA * 4);
-    if (cost) memcpy(cost, sim->h_cost, NA * 4);
-    if (terminated) memcpy(terminated, sim->h_term, NA);
-    if (truncated) memcpy(truncated, sim->h_trunc, NA);
-    if (info_flags) memcpy(info_flags, sim->h_info_flags, NA * 4);
-    if (info_f) memcpy(info_f, sim->h_info_f, NA * 8 * 4);
-    return 0;
-}
-
-// addresses of the pinned host staging buffers md_step_host fills: obs, reward, cost, terminated, truncated,
-// info_flags, info_f, actions (the last one is the input buffer; write actions there and pass NULL to skip a copy)
-extern "C" int md_host_views(md_sim* sim, void** out8) {
-    if (!sim || !sim->loaded) return -2;
-    out8[0] = sim->h_obs; out8[1] = sim->h_reward; out8[2] = sim->h_cost; out8[3] = sim->h_term; out8[4] = sim->h_trunc;
-    out8[5] = sim->h_info_flags; out8[6] = sim->h_info_f; out8[7] = sim->h_actions;
+    const size_t od = OBS_DIM(c);
+    const int G = (int)sim->groups.size();
+    for (int k = 0; k < G; k++) {
+        HostGroup& g = sim->groups[k];
+        const size_t a0 = (size_t)g.env0 * c.agents_per_env;
+        const float* a = nullptr;
+        if (actions && actions != sim->h_actions) a = actions + a0 * 2;
+        if (md_host_send(sim, k, a, autoreset)) return -1;
+    }
+    for (int k = 0; k < G; k++) {
+        if (md_host_recv(sim, k)) return -1;
+        HostGroup& g = sim->groups[k];
+        const size_t a0 = (size_t)g.env0 * c.agents_per_env, n = g.na;
+        if (obs && !sim->compact) memcpy(obs + a0 * od, g.h_obs, n * od * 4);
+        if (reward) memcpy(reward + a0, g.h_blk, n * 4);
+        if (cost) memcpy(cost + a0, g.h_blk + g.off_cost, n * 4);
+        if (terminated) memcpy(terminated + a0, g.h_blk + g.off_term, n);
+        if (truncated) memcpy(truncated + a0, g.h_blk + g.off_trunc, n);
+        if (info_flags) memcpy(info_flags + a0, g.h_blk + g.off_flags, n * 4);
+        if (info_f) memcpy(info_f + a0 * 8, g.h_blk + g.off_info_f, n * 32);
+    }
+    if (obs && sim->compact) { sim->err = "md_step_host: compact mode leaves the rows in the pinned buffers (obs must be NULL)"; return -2; }
     return 0;
 }

@@ -14,8 +14,10 @@ EXPORTS = [
     "md_abi_version", "md_create", "md_destroy", "md_last_error", "md_load_scene", "md_reset", "md_step",
     "md_autoreset", "md_step_autoreset", "md_step_host", "md_reset_host", "md_lidar", "md_dynamics", "md_after_step", "md_idm",
     "md_get_state", "md_set_state", "md_snapshot", "md_launch_count", "md_profile_begin", "md_profile_end",
-    "md_host_views", "md_attach_bank",
+    "md_host_views", "md_attach_bank", "md_sizeof_config", "md_sizeof_arrays", "md_host_groups", "md_host_group_count",
+    "md_host_group_views", "md_host_send", "md_host_recv", "md_host_compact",
 ]
+ABI_VERSION = 4  # include/mdstep.h MD_ABI_VERSION
 
 
 class MdStepError(RuntimeError):
@@ -45,6 +47,12 @@ def load():
     lib = C.CDLL(LIB_PATH)
     vp, ip = C.c_void_p, C.c_int
     lib.md_abi_version.restype = ip
+    # a stale or tuning build with another struct layout would silently misread the configuration passed by value
+    if lib.md_abi_version() != ABI_VERSION:
+        raise MdStepError("%s has ABI version %d, this package expects %d: rebuild it" % (LIB_PATH, lib.md_abi_version(), ABI_VERSION))
+    if lib.md_sizeof_config() != C.sizeof(MdConfig) or lib.md_sizeof_arrays() != C.sizeof(MdArrays):
+        raise MdStepError("%s was built with another MdConfig / MdArrays layout (%d / %d bytes, expected %d / %d): rebuild it" % (
+            LIB_PATH, lib.md_sizeof_config(), lib.md_sizeof_arrays(), C.sizeof(MdConfig), C.sizeof(MdArrays)))
     lib.md_create.argtypes = [C.POINTER(MdConfig), ip, C.POINTER(vp)]
     lib.md_destroy.argtypes = [vp]
     lib.md_destroy.restype = None
@@ -68,6 +76,12 @@ def load():
     lib.md_profile_begin.argtypes = [vp, ip]
     lib.md_profile_end.argtypes = [vp, vp, ip]
     lib.md_host_views.argtypes = [vp, C.POINTER(vp)]
+    lib.md_host_groups.argtypes = [vp, ip]
+    lib.md_host_group_count.argtypes = [vp]
+    lib.md_host_group_views.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(ip)]
+    lib.md_host_send.argtypes = [vp, ip, vp, ip]
+    lib.md_host_recv.argtypes = [vp, ip]
+    lib.md_host_compact.argtypes = [vp, ip]
     lib.md_launch_count.argtypes = [vp]
     lib.md_launch_count.restype = C.c_int64
     for name in EXPORTS:

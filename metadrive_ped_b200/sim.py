@@ -75,31 +75,97 @@ class BatchedSim:
         return self.obs, self.reward, self.cost, self.terminated, self.truncated
 
     # ------------------------------------------------------------------ host-buffer API (numpy in, numpy out)
-    def _views(self):
-        """numpy views of the library's pinned staging buffers (no copy)."""
-        if not hasattr(self, "_hv"):
-            na = self.n_agents
-            ptrs = (C.c_void_p * 8)()
-            self._check(self.lib.md_host_views(self.h, ptrs))
+    # The batch is split into host groups (md_host_groups, include/mdstep.h): contiguous env ranges with their own stream
+    # and pinned buffers.  step_host() steps every group in one synchronous call; send() / recv() pipeline the groups
+    # across steps, so that a group's PCIe copies and the caller's own work overlap the other groups' kernels.
+    def host_groups(self, n_groups):
+        self._check(self.lib.md_host_groups(self.h, int(n_groups)))
+        self._gv = None
+        return self.n_host_groups
 
-            def view(i, ctype, shape):
-                n = int(np.prod(shape))
-                return np.ctypeslib.as_array(C.cast(ptrs[i], C.POINTER(ctype)), shape=(n, )).reshape(shape)
+    @property
+    def n_host_groups(self):
+        return int(self.lib.md_host_group_count(self.h))
 
-            self._hv = dict(obs=view(0, C.c_float, (na, self.obs_dim)), reward=view(1, C.c_float, (na, )),
-                            cost=view(2, C.c_float, (na, )), term=view(3, C.c_uint8, (na, )), trunc=view(4, C.c_uint8, (na, )),
-                            flags=view(5, C.c_int32, (na, )), info_f=view(6, C.c_float, (na, 8)),
-                            actions=view(7, C.c_float, (na, 2)))
-        return self._hv
+    def host_compact(self, on=True):
+        """Multi-agent: only the observation rows of seats with FL_VALID are copied to the host (md_host_compact)."""
+        self._check(self.lib.md_host_compact(self.h, int(bool(on))))
+        self._compact = bool(on)
+
+    def _group_views(self):
+        """per group: numpy views of its pinned buffers (no copy) + its env range"""
+        if getattr(self, "_gv", None) is None:
+            self._gv = []
+            A = self.cfg.agents_per_env
+            for k in range(self.n_host_groups):
+                ptrs, rng = (C.c_void_p * 8)(), (C.c_int * 3)()
+                self._check(self.lib.md_host_group_views(self.h, k, ptrs, rng))
+                na = rng[1] * A
+
+                def view(i, ctype, shape):
+                    n = int(np.prod(shape))
+                    return np.ctypeslib.as_array(C.cast(ptrs[i], C.POINTER(ctype)), shape=(n, )).reshape(shape)
+
+                self._gv.append(dict(
+                    obs=view(0, C.c_float, (na, self.obs_dim)), reward=view(1, C.c_float, (na, )),
+                    cost=view(2, C.c_float, (na, )), term=view(3, C.c_uint8, (na, )), trunc=view(4, C.c_uint8, (na, )),
+                    flags=view(5, C.c_int32, (na, )), info_f=view(6, C.c_float, (na, 8)),
+                    actions=view(7, C.c_float, (na, 2)), env0=rng[0], n_envs=rng[1], a0=rng[0] * A, na=na))
+        return self._gv
+
+    def _rows(self, k):
+        rng = (C.c_int * 3)()
+        self._check(self.lib.md_host_group_views(self.h, k, None, rng))
+        return rng[2]
+
+    def send(self, group, actions=None, autoreset=False):
+        """Enqueue one env.step of host group `group` and return at once.  `actions` [group agents, 2]; None = the caller
+        wrote them into the group's pinned action buffer (`group_buffers(group)["actions"]`) already."""
+        if actions is not None:
+            g = self._group_views()[group]
+            g["actions"][...] = np.asarray(actions, np.float32).reshape(g["na"], 2)
+        rc = self.lib.md_host_send(self.h, group, None, 1 if autoreset else 0)
+        if rc:
+            self._check(rc)
+
+    def group_buffers(self, group):
+        """numpy views of a host group's pinned buffers: obs, reward, cost, term, trunc, flags, info_f, actions; plus its
+        env range (env0, n_envs) and agent range (a0, na)."""
+        return self._group_views()[group]
+
+    def recv(self, group):
+        """Wait for the group's step.  Returns views of its pinned buffers (valid until its next send):
+        obs, reward, cost, terminated, truncated, info_flags, info_f.  In compact mode `obs` holds only the rows of the
+        seats whose info_flags carry FL_VALID, in ascending seat order."""
+        rc = self.lib.md_host_recv(self.h, group)
+        if rc:
+            self._check(rc)
+        g = self._group_views()[group]
+        obs = g["obs"][:self._rows(group)] if getattr(self, "_compact", False) else g["obs"]
+        return obs, g["reward"], g["cost"], g["term"], g["trunc"], g["flags"], g["info_f"]
 
     def step_host(self, actions: np.ndarray, autoreset=False):
-        """env.step through host memory: actions are copied into the pinned input buffer, H2D, kernels, D2H; the
-        returned arrays are views of the pinned output buffers (valid until the next call)."""
-        b = self._views()
-        b["actions"][...] = np.asarray(actions, np.float32).reshape(self.n_agents, 2)
+        """env.step through host memory: actions are copied into the pinned input buffers, H2D, kernels, D2H; the
+        returned arrays are views of the pinned output buffers where those are contiguous over the batch (the observation
+        rows always; everything with one host group), else concatenated copies of the groups' (small) scalar blocks.
+        Valid until the next call."""
+        gv = self._group_views()
+        a = np.asarray(actions, np.float32).reshape(self.n_agents, 2)
+        for g in gv:
+            g["actions"][...] = a[g["a0"]:g["a0"] + g["na"]]
         null = C.c_void_p()
         self._check(self.lib.md_step_host(self.h, null, null, null, null, null, null, null, null, int(bool(autoreset))))
-        return b["obs"], b["reward"], b["cost"], b["term"], b["trunc"], b["flags"], b["info_f"]
+        if len(gv) == 1:
+            b = gv[0]
+            obs = b["obs"][:self._rows(0)] if getattr(self, "_compact", False) else b["obs"]
+            return obs, b["reward"], b["cost"], b["term"], b["trunc"], b["flags"], b["info_f"]
+        cat = lambda name: np.concatenate([g[name] for g in gv])
+        if getattr(self, "_compact", False):
+            obs = np.concatenate([g["obs"][:self._rows(k)] for k, g in enumerate(gv)])
+        else:  # the groups' observation rows are consecutive slices of one pinned buffer
+            obs = np.ctypeslib.as_array(C.cast(gv[0]["obs"].ctypes.data, C.POINTER(C.c_float)),
+                                        shape=(self.n_agents * self.obs_dim, )).reshape(self.n_agents, self.obs_dim)
+        return obs, cat("reward"), cat("cost"), cat("term"), cat("trunc"), cat("flags"), cat("info_f")
 
     def reset_host(self, env_mask=None):
         na = self.n_agents
