@@ -9,6 +9,8 @@ maps with IDM traffic, 8192 environments per GPU cycling through the 1000 refere
 library, reference profiling protocol (examples/profile_metadrive.py:16-29): action [0, 1], finished envs reset
 in place (on device).  A step = one env.step of every env: before_step (actuation, trigger, IDM), 5 physics
 sub-steps with contacts, after_step, reward/cost/done, 259-float observation, plus the auto-reset of finished envs.
+The other BASELINE configurations (cfg3 multi-agent roundabout, cfg4 SafeMetaDriveEnv, cfg5 pedestrian intersection)
+ride along as short `other_configs` entries of the same JSON line (or alone with --workload).
 """
 import argparse
 import json
@@ -23,10 +25,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ENVS_PER_GPU = 8192
-LIBRARY = "pg3_density0.1.npz"
-# BASELINE.json configs.  cfg2 is the one the metric is quoted on (the default and the only driver-run line); the others
-# are the parity-test configurations, measurable with --workload for the record (profiles/).
+# BASELINE.json configs.  cfg2 is the one the metric is quoted on (the headline line); cfg4 = 65,536 envs over 8 GPUs and
+# cfg5 = 32,768 envs over 8 GPUs are 8,192 / 4,096 envs per GPU; cfg3 = 40 agents x 2,048 envs per GPU.
 WORKLOADS = {
     "cfg2": dict(lib="pg3_density0.1.npz", envs=8192, peds=0,
                  name="MetaDriveEnv PG 3-block maps, IDM traffic density 0.1, 1000 reference scenarios, 240-beam lidar"),
@@ -41,6 +41,7 @@ WORKLOADS = {
 B_EGO = 1684.0
 B_TRAFFIC = 560.0
 B_LIDAR_SHARE = 256.0 + 960.0  # neighbour footprints read + the 240 lidar floats written (k_lidar's part of B_EGO)
+KERNELS = ["k_pre", "k_dyn", "k_post", "k_reset", "k_lidar"]
 
 
 def load_peaks():
@@ -52,6 +53,17 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_ncu(kernel):
+    """Per-launch DRAM bytes and FP32 flops of a kernel from this round's `ncu --set full` capture of this very command
+    (profiles/r02_ncu_counters.json, written by scripts/ncu_counters.py); None when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_counters.json")) as f:
+            d = json.load(f)
+        return d.get(kernel), d.get("_source")
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -121,39 +133,281 @@ def workload_name(workload="cfg2"):
 
 
 def run_reference(args, rank):
-    """CPU arm: the oracle port of the reference's path on all host threads, bounded sample per step."""
+    """CPU arm: the reference's path on the box's host cores - the oracle port (`kind: port`; the reference itself needs
+    panda3d, absent from this image), every host thread, on the SAME configuration as our arm: the 8192 envs of the
+    workload, action [0, 1], finished envs reset in place.  Each step is one pass over all 8192 envs (about 50 ms on 16
+    cores), so the default --steps / --warmup end within seconds."""
     if rank != 0:
         return
     from oracle.oracle import OracleSim, set_threads
     cores = set_threads()  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread
-    sample = 1024
-    lib, arrays, cfg = build_world(sample, 0)
+    wl = args.workload
+    E = args.envs_per_gpu or WORKLOADS[wl]["envs"]
+    lib, arrays, cfg = build_world(E, 0, wl)
     orc = OracleSim(arrays, cfg)
     orc.reset_observe()
-    a = np.tile(np.array([0.0, 1.0], np.float32), (sample, 1))
-    for _ in range(args.warmup):
+    A = orc.n_agents
+    a = np.tile(np.array([0.0, 1.0], np.float32), (A, 1))
+    steps = max(1, min(args.steps, 200))
+    for _ in range(min(args.warmup, 20)):
         orc.step(a)
         orc.reset_envs(orc.term | orc.trunc)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         orc.step(a)
         done = (orc.term | orc.trunc).astype(bool)
         if done.any():
-            orc.reset_envs(done)
-            # reset observation of the restored envs: the oracle recomputes it with the next step's observe
+            orc.reset_envs(done)   # the restored envs' reset observation comes with the next step's observe
     dt = time.perf_counter() - t0
-    v = sample * args.steps / dt
+    v = A * steps / dt
     line = {
         "impl": "reference", "metric": "agent_steps_per_sec_240beam_lidar", "value": v, "unit": "agent-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "envs_per_step": sample, "actions": "[0,1] (profile_metadrive.py)"},
+        "config": {"workload": workload_name(wl), "baseline_config": wl, "envs_per_gpu": E,
+                   "actions": "profile"},
         "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d envs x %d steps, OpenMP over envs" % (sample, args.steps)},
+                         "sample": "%d envs x %d steps (the whole workload every step), OpenMP over envs" % (E, steps)},
         "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "lidar_rays_per_sec": v * 240,
     }
     print(json.dumps(line), flush=True)
+
+
+def ma_driver(torch, obs, sd, gen, noise=0.05):
+    """Obs-driven driver of the multi-agent workload (the lane-follow + noise driver of oracle/gen_golden.py, from the
+    observation instead of the vehicle object): steer along the route lane - heading error from the `heading_diff` entry
+    (obs/state_obs.py:115), lateral offset from the lane-centre entry (:141-148), a pull towards the next checkpoint from
+    the navigation block (node_network_navigation.py:243-292) - and hold ~28 km/h, slower where the route bends.  Keeps
+    most agents alive until they arrive, so the 40 seats of an env really hold ~40 driving agents."""
+    herr = torch.asin((2.0 * obs[:, sd] - 1.0).clamp(-1.0, 1.0))           # lane heading - vehicle heading
+    lat = (2.0 * obs[:, sd + 6] - 1.0) * 2.25                              # +: right of the lane centre
+    fwd, rhs = (2.0 * obs[:, sd + 7] - 1.0) * 50.0, (2.0 * obs[:, sd + 8] - 1.0) * 50.0
+    near = (fwd * fwd + rhs * rhs) < 64.0                                  # almost at checkpoint 1: look at checkpoint 2
+    fwd = torch.where(near, (2.0 * obs[:, sd + 12] - 1.0) * 50.0, fwd)
+    rhs = torch.where(near, (2.0 * obs[:, sd + 13] - 1.0) * 50.0, rhs)
+    ang = torch.atan2(rhs, fwd.clamp_min(1.0))                              # navi 'rhs' grows to the LEFT (in_rhs = -d.right)
+    bend = torch.maximum(obs[:, sd + 9], obs[:, sd + 14])                  # radius / (60 + n * w); 0 on straights
+    v = obs[:, sd + 1] * 81.0 - 1.0
+    target = torch.where((bend > 0.0) & (bend < 0.3), 16.0, 28.0)
+    u = torch.rand((obs.shape[0], 2), generator=gen, device=obs.device) * 2.0 - 1.0
+    steer = (2.2 * herr + 0.45 * lat + 0.4 * ang + noise * u[:, 0]).clamp(-1.0, 1.0)
+    thr = torch.where(v < target, 0.6, torch.where(v > target + 6.0, -0.3, 0.0)) + noise * u[:, 1]
+    return torch.stack([steer, thr.clamp(-1.0, 1.0)], 1).contiguous()
+
+
+def measure(args, workload, rank, local_rank, world, K, warmup, full):
+    """One workload on this rank's GPU.  `full`: the headline protocol (per-kernel roofline, both e2e legs, clocks); else a
+    short line for `other_configs`.  Returns the dict rank 0 prints (None on other ranks)."""
+    import torch
+    import torch.distributed as dist
+    from metadrive_ped_b200.sim import BatchedSim
+    dev = torch.device("cuda", local_rank)
+    E = (args.envs_per_gpu if full and args.envs_per_gpu else None) or WORKLOADS[workload]["envs"]
+    multi = workload == "cfg3"
+    t_build = time.time()
+    lib, arrays, cfg = build_world(E, rank, workload)
+    sim = BatchedSim(arrays, cfg, device=local_rank)
+    resample = workload in ("cfg2", "cfg4") and not args.no_resample
+    bank = None
+    if resample:  # the scenario bank: one env per library scenario, fully reset; finished envs draw their next scenario from it
+        b_arrays, b_cfg = lib.build_world(list(range(len(lib))), seed=rank, **bank_kw(lib, workload))
+        bank = BatchedSim(b_arrays, b_cfg, device=local_rank)
+        bank.reset()
+        sim.reset()
+        sim.attach_bank(bank, seed=1000 + rank)
+    t_build = time.time() - t_build
+    A = sim.n_agents
+    kind = arrays["veh_i"][:, 0].reshape(E, cfg.slots_per_env)
+    traffic_per_env = float((kind == 2).sum(1).mean())
+    sd = (cfg.n_side_lasers or 2)
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    if multi:
+        actions_kind = "obs-driven lane-follow driver + noise (bench.ma_driver), recomputed on device every step"
+        policy = lambda: ma_driver(torch, sim.obs, sd, g)
+    elif args.actions == "profile":
+        actions_kind = "profile"
+        const = torch.tensor([0.0, 1.0], device=dev).repeat(A, 1).contiguous()
+        policy = lambda: const
+    else:
+        actions_kind = "random"
+        const = (torch.rand((A, 2), generator=g, device=dev) * 2 - 1).contiguous()
+        policy = lambda: const
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sim.reset()
+    for _ in range(args.burnin):  # setup, not warm-up: de-synchronise the episodes (traffic triggered, resets spread)
+        sim.step(policy(), autoreset=True)
+    for _ in range(warmup):
+        sim.step(policy(), autoreset=True)
+    barrier()
+
+    # ---------------- timed region: device-resident inputs, CUDA events on the launch stream, L2 flushed between steps
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches0 = sim.launch_count
+    sim.profile_begin(K)
+    done_count = torch.zeros((), dtype=torch.int64, device=dev)
+    valid_count = torch.zeros((), dtype=torch.int64, device=dev)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        for k in range(K):
+            act = policy()
+            flush.zero_()
+            ev0[k].record()
+            sim.step(act, autoreset=True)
+            ev1[k].record()
+            done_count += (sim.terminated | sim.truncated).sum()
+            if multi:
+                valid_count += ((sim.info_flags & 0x2000) != 0).sum()
+        barrier()
+    step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(K)])
+    kms = sim.profile_end()  # [K, 5]: k_pre, k_dyn, k_post, fused reset, k_lidar
+    launches = sim.launch_count - launches0
+    total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) / 1e3
+    # agent-steps: every env's agent steps every step; in the multi-agent workload only the seats that produced a
+    # transition count (wrecks waiting out delay_done and empty seats do not)
+    units = torch.tensor([float(valid_count.item()) if multi else float(A * K)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    value = float(units.item()) / total_s
+    n_ag = cfg.agents_per_env - (1 if multi else 0)                 # a multi-agent env carries one spare seat
+    live_frac = float(units.item()) / (world * E * n_ag * K)
+
+    # ---------------- e2e: the host-buffer API (pinned staging, H2D actions + D2H outputs of EVERY env EVERY step inside the
+    # timed region), wall clock.  `pipelined` (the headline) = --host-groups groups driven through send / recv, the
+    # EnvPool-style split of the batch: group g's next actions are sent only after its results were received, while the
+    # other groups are being stepped - the way a host-side learner hides PCIe time.  `sync` = one md_step_host call per step
+    # over the same groups (group k's D2H overlaps group k+1's kernels inside the call).
+    a_host = policy().cpu().numpy()
+    G = max(1, args.host_groups)
+    sim.host_groups(G)
+    if multi:
+        sim.host_compact(True)
+    gv = sim._group_views()
+    for gr in gv:
+        gr["actions"][...] = a_host[gr["a0"]:gr["a0"] + gr["na"]]       # actions sit in the pinned buffers; H2D every step
+    Ke = max(10, min(K, 100))
+
+    def e2e_sync(n):
+        rows = 0
+        for _ in range(n):
+            rows += sim.step_host(a_host, autoreset=True)[0].shape[0]
+        return rows
+
+    def e2e_pipelined(n):
+        rows = 0
+        for gi in range(G):
+            sim.send(gi, None, autoreset=True)
+        for i in range(n):
+            for gi in range(G):
+                rows += sim.recv(gi)[0].shape[0]
+                if i + 1 < n:
+                    sim.send(gi, None, autoreset=True)
+        return rows
+
+    e2e = {}
+    for name, fn in (("sync", e2e_sync), ("pipelined", e2e_pipelined)) if full else (("pipelined", e2e_pipelined), ):
+        fn(3)
+        barrier()
+        t0 = time.perf_counter()
+        rows = fn(Ke)
+        torch.cuda.synchronize(dev)
+        dt_e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
+        e2e[name] = (world * E * n_ag * Ke * live_frac / float(dt_e.item()), rows / Ke)
+    obs_rows = e2e["pipelined"][1]     # observation rows copied per step (multi-agent: only the FL_VALID seats travel)
+    h2d = A * 2 * 4
+    d2h = int(obs_rows * sim.obs_dim * 4 + A * (4 + 4 + 1 + 1 + 4 + 8 * 4))
+
+    # ---------------- episode statistics: the only cross-GPU exchange of this path (one tiny all-reduce)
+    stats = torch.tensor([float(done_count.item()), float(A * K)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    line = None
+    if rank == 0:
+        mean_ms = kms.mean(0)
+        config = {"workload": workload_name(workload), "baseline_config": workload, "envs_per_gpu": E,
+                  "agents_per_env": n_ag, "live_agent_fraction": live_frac,
+                  "slots_per_env": cfg.slots_per_env, "traffic_per_env_mean": traffic_per_env,
+                  "distinct_scenarios": (E * world if multi else min(len(lib), E * world)), "actions": actions_kind,
+                  "autoreset": "on device, inside the timed region" + (
+                      "; every reset draws a new scenario from the %d-scenario bank (md_attach_bank)" % len(lib) if resample else ""),
+                  "l2": "flushed between steps (256 MiB memset, untimed)",
+                  "dynamic_broad_phase": "per-env shared-memory scan (slots + objects <= 128 per env; md_create fails above)",
+                  "scene_build_s": round(t_build, 1), "burnin_steps": args.burnin}
+        e2e_d = {"value": e2e["pipelined"][0], "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                 "steps": Ke, "host_groups": G,
+                 "api": "BatchedSim.send/recv over %d host groups (md_host_send / md_host_recv): every env gets its actions "
+                        "H2D and its results D2H every step; a group's next actions are sent after its results were received" % G}
+        if "sync" in e2e:
+            e2e_d["sync_call_value"] = e2e["sync"][0]
+        line = {"metric": "agent_steps_per_sec_240beam_lidar", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+                "steps": K, "warmup": warmup, "ms_per_step": 1e3 * total_s / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "lidar_rays_per_sec": value * cfg.n_lasers, "gpu_launches": int(launches),
+                "kernel_ms": {**{n: float(v) for n, v in zip(KERNELS, mean_ms)},
+                              "step_total_incl_autoreset": float(step_ms.mean())},
+                "e2e": e2e_d}
+        if full:
+            peak, peak_src = load_peaks()
+            dom_i = int(np.argmax(mean_ms))
+            dom = KERNELS[dom_i]
+            # algorithmic bytes per launch of each kernel (DESIGN.md section 3): the SURVEY 8(d) per-unit figures split
+            # by what each kernel must touch; T = alive traffic vehicles per env
+            T = traffic_per_env
+            NAg = float(n_ag) * live_frac  # agents that step per env (1 in the single-agent workloads)
+            NP = float(WORKLOADS[workload]["peds"])
+            per_env = {
+                "k_pre": NAg * (8 + 64) + T * (64 + 256),       # action + latches r/w ; traffic: PID/timer/route r/w + neighbours
+                "k_dyn": (192 + 48) * (NAg + T) + 32 * NP,      # state r/w + params, every vehicle; pedestrians pos/vel r/w
+                "k_post": NAg * (64 + 76 + 16),                 # episode/nav state r/w + 19 state floats + scalars (agents)
+                "k_reset": 0.0,                                 # auto-reset of finished envs: not part of the per-step figure
+                "k_lidar": NAg * B_LIDAR_SHARE,                 # neighbour footprints + 240 lidar floats
+            }
+            B_STEP = NAg * B_EGO + B_TRAFFIC * T + 32 * NP      # SURVEY.md 8(d): bytes per env-step
+            assert abs(sum(per_env.values()) - B_STEP) < 1.0, per_env
+            bytes_per_launch = E * per_env[dom]
+            ncu, ncu_src = load_ncu(dom)
+            dur_ms = float(mean_ms[dom_i])
+            achieved = bytes_per_launch / (dur_ms * 1e-3) / 1e9
+            line["step_roofline_all_kernels"] = {"algorithmic_bytes_per_step": E * B_STEP,
+                                                 "achieved_gbs": E * B_STEP / (float(mean_ms.sum()) * 1e-3) / 1e9}
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                "frac": achieved / peak, "traffic": (ncu or {}).get("dram_bytes"), "traffic_source": ncu_src,
+                                "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch}
+            # secondary roofline (SURVEY.md 8d): FP32 pipe.  Peak = measured FFMA micro-benchmark on this GPU; flops per
+            # launch = FADD + FMUL + 2 FFMA thread-instructions of the kernel from the round's ncu capture of this command.
+            fp32_peak = sim.fp32_peak()
+            rf = {"peak": fp32_peak, "unit": "TFLOP/s", "peak_source": "measured in this run (md_fp32_peak: independent FFMA chains)",
+                  "kernels": {}}
+            for i, n in enumerate(KERNELS):
+                c, _ = load_ncu(n)
+                if c and c.get("fp32_flops") and mean_ms[i] > 0:
+                    ach = c["fp32_flops"] / (float(mean_ms[i]) * 1e-3) / 1e12
+                    rf["kernels"][n] = {"flops_per_launch": c["fp32_flops"], "achieved": ach, "frac": ach / fp32_peak}
+            rf["flops_source"] = ncu_src
+            line["roofline_fp32"] = rf
+            line["clocks"] = clocks.summary()
+            line["episodes_finished_frac"] = float(stats[0].item() / max(stats[1].item(), 1.0))
+            if world == 1 and not args.no_cpu_baseline and not multi:
+                line["cpu_baseline"] = cpu_baseline(lib, WORKLOADS[workload]["peds"])
+    sim.close()
+    if bank is not None:
+        bank.close()
+    del flush
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():
@@ -166,6 +420,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--actions", default="profile", choices=["profile", "random"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short cfg3 / cfg4 / cfg5 entries")
     ap.add_argument("--no-resample", action="store_true", help="finished envs replay their own scenario instead of drawing a new one")
     ap.add_argument("--host-groups", type=int, default=4, help="host groups of the e2e leg (md_host_groups)")
     ap.add_argument("--burnin", type=int, default=150,
@@ -182,201 +437,25 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (ours) needs a GPU: the product has no CPU fallback")
+    from metadrive_ped_b200.shard import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank)   # before any pinned allocation: the staging buffers land on the GPU's NUMA node
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from metadrive_ped_b200.sim import BatchedSim
-    E = args.envs_per_gpu or WORKLOADS[args.workload]["envs"]
-    multi = args.workload == "cfg3"
-    t_build = time.time()
-    lib, arrays, cfg = build_world(E, rank, args.workload)
-    sim = BatchedSim(arrays, cfg, device=local_rank)
-    resample = args.workload in ("cfg2", "cfg4") and not args.no_resample
-    if resample:  # the scenario bank: one env per library scenario, fully reset; finished envs draw their next scenario from it
-        b_arrays, b_cfg = lib.build_world(list(range(len(lib))), seed=rank, **bank_kw(lib, args.workload))
-        bank = BatchedSim(b_arrays, b_cfg, device=local_rank)
-        bank.reset()
-        sim.reset()
-        sim.attach_bank(bank, seed=1000 + rank)
-    t_build = time.time() - t_build
-    A = sim.n_agents
-    kind = arrays["veh_i"][:, 0].reshape(E, cfg.slots_per_env)
-    traffic_per_env = float((kind == 2).sum(1).mean())
-
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    if multi:  # small steering noise, throttle in [0, 1]: agents drive, crash, leave the road, arrive and are respawned
-        act_dev = torch.rand((A, 2), generator=g, device=dev)
-        act_dev[:, 0] = (act_dev[:, 0] - 0.5) * 0.2
-        act_dev = act_dev.contiguous()
-    elif args.actions == "profile":
-        act_dev = torch.tensor([0.0, 1.0], device=dev).repeat(A, 1).contiguous()
-    else:
-        act_dev = (torch.rand((A, 2), generator=g, device=dev) * 2 - 1).contiguous()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    sim.reset()
-    for _ in range(args.burnin):  # setup, not warm-up: de-synchronise the episodes (traffic triggered, resets spread)
-        sim.step(act_dev, autoreset=True)
-    for _ in range(args.warmup):
-        sim.step(act_dev, autoreset=True)
-    barrier()
-
-    # ---------------- timed region: device-resident inputs, CUDA events on the launch stream, L2 flushed between steps
-    K = args.steps
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    launches0 = sim.launch_count
-    sim.profile_begin(K)
-    done_count = torch.zeros((), dtype=torch.int64, device=dev)
-    valid_count = torch.zeros((), dtype=torch.int64, device=dev)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        for k in range(K):
-            flush.zero_()
-            ev0[k].record()
-            sim.step(act_dev, autoreset=True)
-            ev1[k].record()
-            done_count += (sim.terminated | sim.truncated).sum()
-            if multi:
-                valid_count += ((sim.info_flags & 0x2000) != 0).sum()
-        barrier()
-    step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(K)])
-    kms = sim.profile_end()  # [K, 5]: k_pre, k_dyn, k_post, fused reset (k_post in reset mode), k_lidar
-    launches = sim.launch_count - launches0
-    total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms.item()) / 1e3
-    # agent-steps: every env's agent steps every step; in the multi-agent workload only the seats that produced a
-    # transition count (wrecks waiting out delay_done and empty seats do not)
-    units = torch.tensor([float(valid_count.item()) if multi else float(A * K)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(units, op=dist.ReduceOp.SUM)
-    value = float(units.item()) / total_s
-    live_frac = float(units.item()) / (world * A * K)
-
-    # ---------------- e2e: the host-buffer API (pinned staging, H2D actions + D2H outputs of EVERY env EVERY step inside the
-    # timed region), wall clock.  Two numbers: `sync` = one md_step_host call per step over --host-groups groups (group k's
-    # D2H overlaps group k+1's kernels inside the call); `pipelined` (the headline) = the same groups driven through
-    # send / recv, the EnvPool-style split of the batch: group g's next actions are sent only after its observations
-    # were received, while the other groups are being stepped - the way a host-side learner hides PCIe time.
-    a_host = act_dev.cpu().numpy()
-    G = max(1, args.host_groups)
-    sim.host_groups(G)
-    if multi:
-        sim.host_compact(True)
-    gv = sim._group_views()
-    a_grp = [np.ascontiguousarray(a_host[g["a0"]:g["a0"] + g["na"]]) for g in gv]
-    Ke = max(10, min(K, 100))
-
-    def e2e_sync(n):
-        rows = 0
-        for _ in range(n):
-            out = sim.step_host(a_host, autoreset=True)
-            rows += out[0].shape[0]
-        return rows
-
-    def e2e_pipelined(n):
-        rows = 0
-        for g in range(G):
-            sim.send(g, a_grp[g], autoreset=True)
-        for i in range(n):
-            for g in range(G):
-                out = sim.recv(g)
-                rows += out[0].shape[0]
-                if i + 1 < n:
-                    sim.send(g, a_grp[g], autoreset=True)
-        return rows
-
-    e2e = {}
-    for name, fn in (("sync", e2e_sync), ("pipelined", e2e_pipelined)):
-        fn(3)
-        barrier()
-        t0 = time.perf_counter()
-        rows = fn(Ke)
-        torch.cuda.synchronize(dev)
-        dt_e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
-        e2e[name] = (world * A * Ke * live_frac / float(dt_e.item()), rows / Ke)
-    e2e_value = e2e["pipelined"][0]
-    obs_rows = e2e["pipelined"][1]     # observation rows copied per step (multi-agent: only the FL_VALID seats travel)
-    h2d = A * 2 * 4
-    d2h = int(obs_rows * sim.obs_dim * 4 + A * (4 + 4 + 1 + 1 + 4 + 8 * 4))
-
-    # ---------------- episode statistics: the only cross-GPU exchange of this path (one tiny all-reduce)
-    stats = torch.tensor([float(done_count.item()), float(A * K)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-
+    line = measure(args, args.workload, rank, local_rank, world, args.steps, args.warmup, True)
+    others = []
+    if args.workload == "cfg2" and not args.no_other_configs:
+        for wl in ("cfg3", "cfg4", "cfg5"):   # short entries so that every BASELINE config has a driver-run line at every N
+            o = measure(args, wl, rank, local_rank, world, 20, 5, False)
+            if o is not None:
+                others.append({k: o[k] for k in ("value", "unit", "n_gpus", "steps", "ms_per_step", "config", "kernel_ms", "e2e",
+                                                 "gpu_launches", "lidar_rays_per_sec")})
     if rank == 0:
-        peak, peak_src = load_peaks()
-        names = ["k_pre", "k_dyn", "k_post", "k_reset", "k_lidar"]
-        mean_ms = kms.mean(0)
-        dom_i = int(np.argmax(mean_ms))
-        dom = names[dom_i]
-        # algorithmic bytes per launch of each kernel: the SURVEY 8(d) per-unit figures split
-        # by what each kernel must touch; T = alive traffic vehicles per env
-        T = traffic_per_env
-        NAg = float(cfg.agents_per_env) * live_frac  # agents that step per env (1 in the single-agent workloads)
-        NP = float(WORKLOADS[args.workload]["peds"])
-        per_env = {
-            "k_pre": NAg * (8 + 64) + T * (64 + 256),       # action + latches r/w ; traffic: PID/timer/route r/w + neighbours
-            "k_dyn": (192 + 48) * (NAg + T) + 32 * NP,      # state r/w + params, every vehicle; pedestrians pos/vel r/w
-            "k_post": NAg * (64 + 76 + 16),                 # episode/nav state r/w + 19 state floats + scalars (agents)
-            "k_reset": 0.0,                                 # auto-reset of finished envs: not part of the per-step figure
-            "k_lidar": NAg * B_LIDAR_SHARE,                 # neighbour footprints + 240 lidar floats
-        }
-        B_STEP = NAg * B_EGO + B_TRAFFIC * T + 32 * NP      # bytes per env-step
-        assert abs(sum(per_env.values()) - B_STEP) < 1.0, per_env
-        bytes_per_launch = E * per_env[dom]
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get(dom)
-        except Exception:
-            pass
-        dur_ms = float(mean_ms[dom_i])
-        achieved = bytes_per_launch / (dur_ms * 1e-3) / 1e9
-        line = {
-            "metric": "agent_steps_per_sec_240beam_lidar", "value": value, "unit": "agent-steps/s", "n_gpus": world,
-            "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "baseline_config": args.workload, "envs_per_gpu": E,
-                       "agents_per_env": cfg.agents_per_env - (1 if multi else 0), "live_agent_fraction": live_frac,
-                       "slots_per_env": cfg.slots_per_env, "traffic_per_env_mean": traffic_per_env,
-                       "distinct_scenarios": (E * world if multi else min(len(lib), E * world)), "actions": args.actions,
-                       "autoreset": "on device, inside the timed region" + (
-                           "; every reset draws a new scenario from the %d-scenario bank (md_attach_bank)" % len(lib) if resample else ""),
-                       "l2": "flushed between steps (256 MiB memset, untimed)",
-                       "scene_build_s": round(t_build, 1), "burnin_steps": args.burnin},
-            "lidar_rays_per_sec": value * cfg.n_lasers,
-            "gpu_launches": int(launches),
-            "kernel_ms": {**{n: float(v) for n, v in zip(names, mean_ms)},
-                          "step_total_incl_autoreset": float(step_ms.mean())},
-            "step_roofline_all_kernels": {"algorithmic_bytes_per_step": E * B_STEP,
-                                          "achieved_gbs": E * B_STEP / (float(mean_ms.sum()) * 1e-3) / 1e9},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_launch},
-            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": "BatchedSim.send/recv over %d host groups (md_host_send / md_host_recv): every env gets "
-                                        "its actions H2D and its results D2H every step; a group's next actions are sent "
-                                        "after its results were received" % G,
-                    "sync_call_value": e2e["sync"][0], "host_groups": G},
-            "clocks": clocks.summary(),
-            "episodes_finished_frac": float(stats[0].item() / max(stats[1].item(), 1.0)),
-        }
-        if world == 1 and not args.no_cpu_baseline and not multi:
-            line["cpu_baseline"] = cpu_baseline(lib, WORKLOADS[args.workload]["peds"])
+        line["numa"] = numa
+        if others:
+            line["other_configs"] = others
         print(json.dumps(line), flush=True)
-    sim.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -134,6 +134,9 @@ int md_snapshot(md_sim* sim);
  * how many steps. */
 int md_profile_begin(md_sim* sim, int max_steps);
 int md_profile_end(md_sim* sim, float* ms, int cap);
+/* measured FP32-FMA peak of `device` in TFLOP/s (a 2 ms micro-benchmark of independent FFMA chains): the denominator of
+ * the secondary, ray-test roofline bench.py reports */
+int md_fp32_peak(int device, double* tflops);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t md_launch_count(const md_sim* sim);
 

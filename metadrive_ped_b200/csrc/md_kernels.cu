@@ -3228,3 +3228,44 @@ extern "C" int md_step_host(md_sim* sim, const float* actions, float* obs, float
     if (obs && sim->compact) { sim->err = "md_step_host: compact mode leaves the rows in the pinned buffers (obs must be NULL)"; return -2; }
     return 0;
 }
+
+// ---- FP32-FMA peak of this GPU, measured: the denominator of the secondary (ray-test) roofline.  Every
+// thread runs 8 independent chains of explicit fmaf (FFMA whatever -fmad says); 2 flops per FMA.
+__global__ void __launch_bounds__(256) k_fma_peak(float* __restrict__ out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f, x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[0] = s;   // keeps the chains alive
+}
+extern "C" int md_fp32_peak(int device, double* tflops) {
+    if (!tflops) return -2;
+    if (cudaSetDevice(device) != cudaSuccess) return -3;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    float* out = nullptr;
+    if (cudaMalloc(&out, 16) != cudaSuccess) return -1;
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {   // the first repetitions warm the clocks up; the best one counts (burst figure)
+        cudaEventRecord(e0, 0);
+        k_fma_peak<<<blocks, 256>>>(out, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1, 0);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return -1; }
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+        if (ms > 0.0f && flops / (ms * 1e-3) / 1e12 > best) best = flops / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return 0;
+}

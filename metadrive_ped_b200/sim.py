@@ -233,6 +233,12 @@ class BatchedSim:
             self._check(n)
         return a[:n]
 
+    def fp32_peak(self):
+        """Measured FP32-FMA peak of this GPU in TFLOP/s (md_fp32_peak)."""
+        v = C.c_double()
+        self._check(self.lib.md_fp32_peak(self.device, C.byref(v)))
+        return float(v.value)
+
     @property
     def launch_count(self):
         return int(self.lib.md_launch_count(self.h))
