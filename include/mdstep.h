@@ -126,6 +126,12 @@ int md_set_state(md_sim* sim, const char* name, const void* host_src, size_t byt
  * Both handles must have loaded the same map set (same map ids) and the same slots / objects / agents per env; single-agent,
  * trigger-mode worlds.  The bank must outlive `sim` (or be detached with bank = NULL).  Returns 0 or a negative code. */
 int md_attach_bank(md_sim* sim, md_sim* bank, int seed);
+/* Contact pairs of the last step: what the reference's contact-added callback sees (engine/core/collision_callback.py:5-42).
+ * After md_enable_contacts(sim, 1) every step records, per vehicle slot, the bodies its chassis touched during the sub-steps:
+ * 128 bits, bit k < slots_per_env = vehicle slot k of the same env, bit slots_per_env + j = object j of the env.
+ * md_get_contacts copies the [NV, 4] uint32 table to the host (synchronous). */
+int md_enable_contacts(md_sim* sim, int on);
+int md_get_contacts(md_sim* sim, uint32_t* host_dst, size_t bytes);
 /* make the current device state the snapshot md_reset restores */
 int md_snapshot(md_sim* sim);
 /* per-stage device timing of the next max_steps md_step / md_step_autoreset calls: six cudaEvents per call recorded on

@@ -676,14 +676,20 @@ __device__ __forceinline__ int dynamic_contacts(const Nb* nb, float* obj, int S,
 
 #define FL_TOUCH 0x40000000  // contact_pass only, never stored: a vehicle or solid obstacle overlaps (-> contact response)
 // the same contact rules over a candidate bit set (k_dyn's per-step broad phase): bit k < S = vehicle slot k, else object k - S
+// `touch` (optional, the vehicle's own two words in shared memory): bit k is set for every body the vehicle overlaps - the
+// pairs the contact-added callback reports (engine/core/collision_callback.py:5-42), exported by md_get_contacts.
 __device__ __forceinline__ int contact_pass(const Nb* nb, float* obj, int S, int slot, const Rect& r, unsigned long long lo,
-                                            unsigned long long hi, int* obj_first, bool claim_pass, bool objects_only) {
+                                            unsigned long long hi, int* obj_first, bool claim_pass, bool objects_only,
+                                            unsigned long long* touch = nullptr) {
     int flags = 0;
     for (int half = 0; half < 2; half++) {
         for (unsigned long long mk = half ? hi : lo; mk; mk &= mk - 1) {
             const int k = __ffsll((long long)mk) - 1 + 64 * half;
             if (k < S) {
-                if (!objects_only && rect_rect(r, nb[k].r)) flags |= FL_CRASH_VEHICLE | FL_TOUCH;
+                if (!objects_only && rect_rect(r, nb[k].r)) {
+                    flags |= FL_CRASH_VEHICLE | FL_TOUCH;
+                    if (touch) touch[half] |= 1ull << (k & 63);
+                }
                 continue;
             }
             const int ko = k - S;
@@ -692,6 +698,7 @@ __device__ __forceinline__ int contact_pass(const Nb* nb, float* obj, int S, int
             if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
             else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
             if (!hit) continue;
+            if (touch && claim_pass) touch[half] |= 1ull << (k & 63);
             if (Ob[OB_KIND] == 3.0f) { flags |= FL_CRASH_HUMAN; continue; }
             flags |= FL_TOUCH;   // a solid obstacle overlaps, whether or not its COST_ONCE flag is still to be had
             if (Ob[OB_CRASHED] == 0.0f) {
@@ -1106,7 +1113,7 @@ __device__ MD_RESP_INL void contact_response(const Nb* nb, const CBody* cd, cons
 
 __global__ void __maxnreg__(DYN_REGS)
 k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ veh_act, const float* __restrict__ ext_act3,
-      int n_sub) {
+      int n_sub, uint4* __restrict__ contact_tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // Two identities per thread.  H ("housekeeping", thread t <-> slot row t of the CTA's envs) sweeps the rows, stages and
     // maintains the objects.  The vehicle identity comes from a compacted list of the alive vehicles, so that the warps
@@ -1116,7 +1123,11 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
     CBody* cd_all = reinterpret_cast<CBody*>(smem_raw + step_smem_bytes(S, O, epb));
     int* list = reinterpret_cast<int*>(smem_raw + step_smem_bytes(S, O, epb) + sizeof(CBody) * (size_t)epb * S);
     int* n_list = list + epb * S;
+    // contact export (md_enable_contacts): two words per slot row in shared memory, ORed by the row's own vehicle thread
+    unsigned long long* touch_all = reinterpret_cast<unsigned long long*>(
+        smem_raw + ((step_smem_bytes(S, O, epb) + sizeof(CBody) * (size_t)epb * S + sizeof(int) * ((size_t)epb * S + 4) + 15) & ~(size_t)15));
     if (threadIdx.x == 0) { n_list[0] = 0; n_list[1] = 0; }
+    if (contact_tab != nullptr && H.work) { touch_all[2 * (H.le * S + H.slot)] = 0ull; touch_all[2 * (H.le * S + H.slot) + 1] = 0ull; }
     __syncthreads();
     if (H.work) {
         // the list is filled from both ends: driven vehicles (agents, triggered traffic) from the front, parked ones (the
@@ -1247,7 +1258,8 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
                 }
             __syncthreads();
             if (cand_lo | cand_hi) {
-                const int f = contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, true, false);
+                const int f = contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, true, false,
+                                           contact_tab != nullptr ? touch_all + 2 * (G.le * S + slot) : nullptr);
                 flags |= f & ~FL_TOUCH;
 #ifndef MD_NO_RESPONSE
                 if (moves && (f & FL_TOUCH)) {  // something overlaps: push apart (registers only;
@@ -1282,6 +1294,13 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
             store16(A.veh_s + (size_t)g * VEH_S, St);
         }
         A.veh_i[(size_t)g * VEH_I + VI_FLAGS] = flags;
+    }
+    if (contact_tab != nullptr) {   // one 16-byte row per slot: the bodies touched during this step (zero for empty slots)
+        __syncthreads();
+        if (H.work) {
+            const unsigned long long a = touch_all[2 * (H.le * S + H.slot)], b = touch_all[2 * (H.le * S + H.slot) + 1];
+            contact_tab[H.g] = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
+        }
     }
     if (contacts && O > 0) {
         __syncthreads();
@@ -2333,6 +2352,7 @@ struct View {
     Snapshot snap, post;
     float *post_body, *post_obs, *body_tab;
     float4* veh_act;
+    uint4* contact_tab;          // optional (md_enable_contacts): per slot, the bodies touched during the last step
     uint8_t* mask;
     int* lidar_list;             // multi-agent lidar passes: the observing seats, compacted (k_lidar_list)
     unsigned int* lidar_count;
@@ -2384,6 +2404,7 @@ struct md_sim {
     float* body_tab;
     float* ray_tab;         // [2*MAX_LASERS lidar | 2*MAX_DET_LASERS side | 2*MAX_DET_LASERS lane] (cos, sin) pairs
     float4* veh_act;        // [NV] steering rad, engine force, brake: k_pre -> k_dyn
+    uint4* contact_tab;     // [NV] or NULL
     uint8_t* mask;
     int* lidar_list;
     unsigned int* lidar_count;   // [1 + MAX_HOST_GROUPS]: the whole-batch view, then one per host group
@@ -2470,6 +2491,7 @@ static View make_view(const md_sim* sim, int env0, int n, int count_slot) {
     v.post_obs = sim->post_obs + na0 * OBS_STATE(c);
     v.body_tab = sim->body_tab + nv0 * BODY_ROW;
     v.veh_act = sim->veh_act + nv0;
+    v.contact_tab = sim->contact_tab ? sim->contact_tab + nv0 : nullptr;
     v.mask = sim->mask + env0;
     v.lidar_list = sim->lidar_list ? sim->lidar_list + na0 : nullptr;
     v.lidar_count = sim->lidar_count ? sim->lidar_count + count_slot : nullptr;
@@ -2497,7 +2519,7 @@ extern "C" int md_create(const MdConfig* cfg, int device, md_sim** out) {
     sim->post_valid = false;
     sim->launches = 0;
     sim->bank = nullptr; sim->bank_seed = 0; sim->bank_ever = false;
-    sim->lidar_list = nullptr; sim->lidar_count = nullptr; sim->d_pass = nullptr;
+    sim->lidar_list = nullptr; sim->lidar_count = nullptr; sim->d_pass = nullptr; sim->contact_tab = nullptr;
     sim->compact = 0;
     sim->prof_cap = 0;
     sim->prof_n = 0;
@@ -2562,7 +2584,7 @@ extern "C" void md_destroy(md_sim* sim) {
         cudaFree(sim->d_actions); cudaFree(sim->d_obs); cudaFree(sim->d_mask_in);
     }
     cudaFree(sim->ray_tab);
-    cudaFree(sim->lidar_list); cudaFree(sim->lidar_count); cudaFree(sim->d_pass);
+    cudaFree(sim->lidar_list); cudaFree(sim->lidar_count); cudaFree(sim->d_pass); cudaFree(sim->contact_tab);
     for (cudaEvent_t e : sim->prof_ev) cudaEventDestroy(e);
     delete sim;
 }
@@ -2679,6 +2701,7 @@ static int epb_dyn() { static int v = env_int("MD_EPB_DYN", DYN_EPB); return v; 
 static StepLaunch dyn_launch(const MdConfig& c) {  // k_dyn appends the compacted list of alive vehicles to the shared tables
     StepLaunch L = step_launch(c, epb_dyn());
     L.smem += sizeof(CBody) * (size_t)L.epb * c.slots_per_env + sizeof(int) * ((size_t)L.epb * c.slots_per_env + 4);
+    L.smem = ((L.smem + 15) & ~(size_t)15) + 16 * (size_t)L.epb * c.slots_per_env;   // contact export words
     return L;
 }
 static StepLaunch pre_launch(const MdConfig& c) {  // k_pre: epb envs per CTA, a fixed number of worker threads
@@ -2734,7 +2757,8 @@ static int launch_pre(md_sim* sim, const View& v, int mode, const float* actions
 }
 static int launch_dyn(md_sim* sim, const View& v, int mode, const float* ext_act3, int n_sub, cudaStream_t st) {
     StepLaunch L = dyn_launch(v.cfg);
-    k_dyn<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, v.veh_act, ext_act3, n_sub);
+    k_dyn<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, v.veh_act, ext_act3, n_sub,
+                                               (mode & MODE_CONTACTS) ? v.contact_tab : nullptr);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -2947,6 +2971,39 @@ extern "C" int md_attach_bank(md_sim* sim, md_sim* bank, int seed) {
     sim->bank_seed = (uint32_t)seed;
     // every view's draw counter restarts
     CK(cudaMemset2D(sim->d_pass, 2 * sizeof(uint32_t), 0, sizeof(uint32_t), 1 + MAX_HOST_GROUPS));
+    return 0;
+}
+
+// Contact export.  With it on, every step records per vehicle slot the set of bodies its chassis touched during the step's
+// sub-steps - bit k < slots_per_env = vehicle slot k of the same env, bit slots_per_env + j = object j - i.e. the pairs
+// the reference's contact-added callback sees (engine/core/collision_callback.py:5-42).  md_get_contacts copies the table
+// ([NV, 4] uint32, 128 bits per slot) to the host; synchronous.
+extern "C" int md_enable_contacts(md_sim* sim, int on) {
+    if (!sim || !sim->loaded) return -2;
+    CK(cudaSetDevice(sim->device));
+    CK(cudaDeviceSynchronize());
+    for (HostGroup& g : sim->groups)
+        if (g.gexec) { cudaGraphExecDestroy(g.gexec); g.gexec = nullptr; }   // the captured launches hold the old pointer
+    const size_t NV = (size_t)sim->cfg.n_envs * sim->cfg.slots_per_env;
+    if (on && !sim->contact_tab) {
+        CK(cudaMalloc(&sim->contact_tab, NV * sizeof(uint4)));
+        CK(cudaMemset(sim->contact_tab, 0, NV * sizeof(uint4)));
+    } else if (!on && sim->contact_tab) {
+        CK(cudaFree(sim->contact_tab));
+        sim->contact_tab = nullptr;
+    }
+    sim->all.contact_tab = sim->contact_tab;
+    for (HostGroup& g : sim->groups)
+        g.v.contact_tab = sim->contact_tab ? sim->contact_tab + (size_t)g.env0 * sim->cfg.slots_per_env : nullptr;
+    return 0;
+}
+extern "C" int md_get_contacts(md_sim* sim, uint32_t* host_dst, size_t bytes) {
+    if (!sim || !sim->loaded) return -2;
+    const size_t NV = (size_t)sim->cfg.n_envs * sim->cfg.slots_per_env;
+    if (!sim->contact_tab || bytes != NV * sizeof(uint4)) { sim->err = "md_get_contacts: not enabled, or a wrong size"; return -7; }
+    CK(cudaSetDevice(sim->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host_dst, sim->contact_tab, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -8,14 +8,16 @@ Surface mirrored (paths relative to /root/reference/metadrive):
   observation_space / action_space    obs/state_obs.py:172-183; policy/env_input_policy.py:50-68
   info keys                           component/vehicle/base_vehicle.py:243-252; envs/metadrive_env.py:132-152, 204, 269;
                                       envs/base_env.py:614-616; envs/safe_metadrive_env.py:31-35
-Scenes come from the shipped scenario library (maps + reset-time rosters exported from the reference); a config the
-library does not cover raises, it is never silently approximated.  Rendering / image observation / manual control
-keys raise NotImplementedError.
+Scenes are GENERATED on the product side (pgmap: BIG + the PG blocks; pgspawn: ego, IDM traffic, accident scenes, with
+the reference's seeded streams), so `map="S"`, `map="SCO"`, `map=5`, any `traffic_density` / `accident_prob` run; the
+scenario libraries exported from the reference are its goldens (tests/test_pgmap.py) and a fast path for the benchmark.
+A config outside what is restated raises, it is never silently approximated.  Rendering / image observation / manual
+control keys raise NotImplementedError.
 """
 import numpy as np
 
 from .abi import TRAFFIC_MODES
-from .library import ScenarioLibrary
+from .library import GeneratedLibrary, ScenarioLibrary
 
 DEFAULT_AGENT = "default_agent"
 
@@ -31,16 +33,17 @@ STEP_DEFAULTS = dict(
     out_of_road_cost=1.0, out_of_route_done=False, on_continuous_line_done=True, crash_vehicle_done=True,
     crash_object_done=True, crash_human_done=True, cost_to_reward=False, enable_idm_lane_change=True,
     use_render=False, image_observation=False, manual_control=False, log_level=20, random_agent_model=False,
+    random_lane_width=False, random_lane_num=False, map_config=dict(lane_width=3.5, lane_num=3, exit_length=50),
     vehicle_config=dict(lidar=dict(num_lasers=240, distance=50, num_others=0, gaussian_noise=0.0, dropout_prob=0.0,
                                    add_others_navi=False),
                         side_detector=dict(num_lasers=0, distance=50), lane_line_detector=dict(num_lasers=0, distance=20),
-                        enable_reverse=False, vehicle_model="default"),
+                        enable_reverse=False, vehicle_model="default", overtake_stat=False),
     # extensions of this build: which device hosts the simulation; crossing pedestrians per env (peds.py, BASELINE
     # config 5 - the reference has the Pedestrian object but no spawner for PG maps)
     device=0, num_pedestrians=0,
 )
-UNSUPPORTED_TRUE = ("use_render", "image_observation", "manual_control", "random_agent_model",
-                    "need_inverse_traffic", "random_traffic")
+UNSUPPORTED_TRUE = ("use_render", "image_observation", "manual_control")
+MAX_HANDLES = 8   # GPU handles a single-env wrapper keeps alive (least recently used seeds are closed)
 
 
 VP_REVERSE = 15  # include/md_layout.h: column of veh_p
@@ -50,8 +53,8 @@ def _apply_vehicle_config(arrays, config):
     """Per-agent vehicle_config entries that act on the step path are written over the library's rows: enable_reverse
     (component/vehicle/base_vehicle.py:157, 479-481).  The library was exported with the reference's defaults."""
     vc = config["vehicle_config"]
-    if vc["vehicle_model"] not in ("default", "static_default"):
-        raise NotImplementedError("vehicle_model %r: the shipped libraries hold the default agent vehicle" % vc["vehicle_model"])
+    if vc["vehicle_model"] not in ("default", "static_default", "s", "m", "l", "xl"):
+        raise NotImplementedError("vehicle_model %r is not one of the reference's PG vehicle types" % vc["vehicle_model"])
     agents = arrays["veh_i"][:, 0] == 1
     arrays["veh_p"] = np.array(arrays["veh_p"], np.float32, copy=True)
     arrays["veh_p"][agents, VP_REVERSE] = 1.0 if vc["enable_reverse"] else 0.0
@@ -186,7 +189,7 @@ class _Agent:
 
 
 class MetaDriveEnv:
-    LIBRARIES = ("pg3_density0.1.npz", "x_respawn_density0.1.npz")
+    ENV_KIND = "metadrive"
     EXTRA_DEFAULTS = {}
 
     @classmethod
@@ -200,6 +203,8 @@ class MetaDriveEnv:
         for k in UNSUPPORTED_TRUE:
             if self.config[k]:
                 raise NotImplementedError("config['%s'] is outside the step path this build covers" % k)
+        if not self.config["static_traffic_object"]:
+            raise NotImplementedError("static_traffic_object=False (loose cones that can be pushed) is not covered")
         lid = self.config["vehicle_config"]["lidar"]
         assert 0.0 <= lid["dropout_prob"] <= 1.0  # obs/state_obs.py:240
         if lid["add_others_navi"]:
@@ -207,35 +212,30 @@ class MetaDriveEnv:
         self.start_seed = self.start_index = self.config["start_seed"]
         self.num_scenarios = self.env_num = self.config["num_scenarios"]
         self._lib = None
-        self._sims = {}
+        self._sims = {}     # seed -> handle, at most MAX_HANDLES (least recently used first)
         self._sim = None
+        self._rng = np.random.RandomState()   # BaseEnv._reset_global_seed draws from an unseeded stream (base_env.py:886-891)
         self.current_seed = None
         self.agent = _Agent(self)
         self.episode_cost = 0.0
+        self._overtake = (set(), set())
         self.observation_space = _box(-0.0, 1.0, (_obs_dim(self.config["vehicle_config"]), ))
         self.action_space = _action_space(self.config)
 
     # -- scenes
     def _library(self):
+        """The scenario source of this config: generated on the product side (library.GeneratedLibrary)."""
         if self._lib is None:
-            # every key that shapes the scene at reset must be the one the library was exported with (keys absent from
-            # the export's config were left at this env class's defaults)
-            scene_keys = ("map", "traffic_density", "traffic_mode", "accident_prob", "static_traffic_object",
-                          "random_spawn_lane_index")
-            dflt = self.default_config()
-            want = {k: self.config[k] for k in scene_keys}
-            tried = []
-            for name in self.LIBRARIES:
-                lib = ScenarioLibrary(name)
-                lc = lib.config
-                have = {k: lc.get(k, dflt[k]) for k in scene_keys}
-                if want == have:
-                    self._lib = lib
-                    break
-                tried.append(have)
-            else:
-                raise NotImplementedError(
-                    "no shipped scenario library for %s (have %s); generate one with oracle/gen_assets.py" % (want, tried))
+            c = self.config
+            mc = c["map_config"]
+            self._lib = GeneratedLibrary(
+                c["start_seed"], c["num_scenarios"], env_kind=self.ENV_KIND, map=c["map"], traffic_density=c["traffic_density"],
+                traffic_mode=c["traffic_mode"], accident_prob=c["accident_prob"], lane_num=mc["lane_num"],
+                lane_width=mc["lane_width"], exit_length=mc["exit_length"], random_lane_width=c["random_lane_width"],
+                random_lane_num=c["random_lane_num"], random_spawn_lane_index=c["random_spawn_lane_index"],
+                need_inverse_traffic=c["need_inverse_traffic"], random_traffic=c["random_traffic"],
+                random_agent_model=c["random_agent_model"],
+                agent_model=c["vehicle_config"]["vehicle_model"])
         return self._lib
 
     def _cfg_kw(self):
@@ -267,44 +267,91 @@ class MetaDriveEnv:
     # -- gym surface
     def reset(self, seed=None):
         from .sim import BatchedSim
-        if seed is None:
-            seed = self.start_seed if self.current_seed is None else \
-                self.start_seed + (self.current_seed + 1 - self.start_seed) % self.num_scenarios
+        if seed is None:   # BaseEnv._reset_global_seed: a uniform draw over the scenario range (envs/base_env.py:886-891)
+            seed = int(self._rng.randint(self.start_seed, self.start_seed + self.num_scenarios))
         assert self.start_seed <= seed < self.start_seed + self.num_scenarios, \
             "scenario_index (seed) should be in [{}:{})".format(self.start_seed, self.start_seed + self.num_scenarios)
         lib = self._library()
-        if seed not in self._sims:
+        if seed in self._sims:
+            self._sims[seed] = self._sims.pop(seed)                 # most recently used last
+        else:
             arrays, cfg = lib.build_world([lib.index_of_seed(seed)], num_pedestrians=self.config["num_pedestrians"],
                                           seed=seed, **self._cfg_kw())
             _apply_vehicle_config(arrays, self.config)
             self._sims[seed] = BatchedSim(arrays, cfg, device=self.config["device"])
+            self._scene = {seed: arrays} if not hasattr(self, "_scene") else {**self._scene, seed: arrays}
+            while len(self._sims) > MAX_HANDLES:                    # a long run over 1000 seeds keeps 8 handles, not 1000
+                old = next(iter(self._sims))
+                self._sims.pop(old).close()
+                self._scene.pop(old, None)
         self._sim = self._sims[seed]
         self.current_seed = seed
         self.episode_cost = 0.0
+        self._overtake = (set(), set())
         obs = self._sim.reset_host()[0].copy()
         return obs, self._info(None)
+
+    def _processed_action(self, action):
+        """What EnvInputPolicy.act leaves in info["action"] and BaseVehicle._preprocess_action in info["raw_action"]
+        (policy/env_input_policy.py:26-48, component/vehicle/base_vehicle.py:204-209): the continuous pair - decoded
+        from the discrete index if need be - with nan -> 0 and clipped to [-1, 1]."""
+        c = self.config
+        if c["discrete_action"]:
+            sd, td = c["discrete_steering_dim"], c["discrete_throttle_dim"]
+            if c["use_multi_discrete"]:
+                a = (float(action[0]) * (2.0 / (sd - 1)) - 1.0, float(action[1]) * (2.0 / (td - 1)) - 1.0)
+            else:
+                a = (float(int(action) % sd) * (2.0 / (sd - 1)) - 1.0, float(int(action) // sd) * (2.0 / (td - 1)) - 1.0)
+        else:
+            a = (float(action[0]), float(action[1]))
+        return tuple(0.0 if np.isnan(x) else min(max(x, -1.0), 1.0) for x in a)
 
     def step(self, action):
         assert self._sim is not None, "call reset() first"
         a = _action_row(self.config, action).reshape(1, 2)
         obs, rew, cost, term, trunc, flags, info_f = self._sim.step_host(a, autoreset=False)
         self.episode_cost += float(cost[0])
-        info = self._info((a[0], float(cost[0]), int(flags[0]), info_f[0]))
-        r = float(rew[0])
-        if self.config["cost_to_reward"]:
-            r -= float(cost[0])
-        return obs[0].copy(), r, bool(term[0]), bool(trunc[0]), info
+        info = self._info((self._processed_action(action), float(cost[0]), int(flags[0]), info_f[0]))
+        # cost_to_reward is only declared by the reference (envs/safe_metadrive_env.py:17), never read: the reward stays as is
+        return obs[0].copy(), float(rew[0]), bool(term[0]), bool(trunc[0]), info
+
+    def _overtake_num(self):
+        """BaseVehicle._update_overtake_stat (component/vehicle/base_vehicle.py:873-892), only with
+        vehicle_config.overtake_stat: vehicles of the lidar's broad phase on the ego's current route road are filed as
+        "in front" or "behind" by their longitude on the ego's lane; a vehicle seen in front once and behind later counts."""
+        if not self.config["vehicle_config"]["overtake_stat"] or self._sim is None:
+            return 0
+        from . import scene as sc
+        arrays = self._scene[self.current_seed]
+        vi, vs, rr = self._sim.get_state("veh_i"), self._sim.get_state("veh_s"), self._sim.get_state("veh_rroad")
+        lane_f, lane_i = arrays["lane_f"], arrays["lane_i"]
+        ego_lane, road = int(vi[0, 4]), int(rr[0, int(vi[0, 5])])
+        D = float(self.config["vehicle_config"]["lidar"]["distance"])
+        me = sc.lane_local(lane_f[ego_lane], vs[0, 0], vs[0, 1])[0]
+        front, back = self._overtake
+        for k in range(1, len(vi)):
+            if not vi[k, 1] or vi[k, 4] < 0 or int(lane_i[int(vi[k, 4]), 0]) != road:
+                continue
+            if np.hypot(vs[k, 0] - vs[0, 0], vs[k, 1] - vs[0, 1]) > int(D) + 3.0:
+                continue
+            if me - sc.lane_local(lane_f[ego_lane], vs[k, 0], vs[k, 1])[0] < 0:
+                front.add(k)
+                back.discard(k)
+            else:
+                back.add(k)
+        return len(front & back)
 
     def _info(self, step):
         if step is None:
-            a, cost, flags, f = np.zeros(2, np.float32), 0.0, 0x100, np.zeros(8, np.float32)
+            a, cost, flags, f = (0.0, 0.0), 0.0, 0x100, np.zeros(8, np.float32)
         else:
             a, cost, flags, f = step
         crash = bool(flags & 0x1f)
         info = {
             "velocity": float(f[0]), "steering": float(f[1]), "acceleration": float(f[2]), "step_energy": float(f[3]),
-            "episode_energy": float(f[4]), "policy": "EnvInputPolicy", "overtake_vehicle_num": 0,
-            "action": (float(a[0]), float(a[1])), "raw_action": (float(a[0]), float(a[1])),
+            "episode_energy": float(f[4]), "policy": "EnvInputPolicy",
+            "overtake_vehicle_num": self._overtake_num() if step is not None and hasattr(self, "_overtake") else 0,
+            "action": [float(a[0]), float(a[1])], "raw_action": (float(a[0]), float(a[1])),
             "crash_vehicle": bool(flags & 0x1), "crash_object": bool(flags & 0x2), "crash_building": bool(flags & 0x4),
             "crash_human": bool(flags & 0x8), "crash_sidewalk": bool(flags & 0x10), "out_of_road": bool(flags & 0x400),
             "arrive_dest": bool(flags & 0x800), "max_step": bool(flags & 0x1000), "env_seed": self.current_seed,
@@ -317,6 +364,7 @@ class MetaDriveEnv:
         for s in self._sims.values():
             s.close()
         self._sims = {}
+        self._scene = {}
         self._sim = None
 
     @property
@@ -326,7 +374,7 @@ class MetaDriveEnv:
 
 class SafeMetaDriveEnv(MetaDriveEnv):
     """envs/safe_metadrive_env.py:7-35"""
-    LIBRARIES = ("safe_pg3.npz", )
+    ENV_KIND = "safe"
     EXTRA_DEFAULTS = dict(num_scenarios=100, accident_prob=0.8, traffic_density=0.05, crash_vehicle_done=False,
                           crash_object_done=False, cost_to_reward=False)
 
@@ -352,7 +400,8 @@ class BatchedMetaDriveEnv:
         idx = [first + i for i in shard_scenarios(n, num_envs, rank)]
         universe = list(range(first, first + n)) if resample_scenarios else None
         S = max(4, -(-lib.max_vehicles() // 4) * 4) if resample_scenarios else None
-        O = lib.max_objects() if resample_scenarios else None
+        # object capacity of the whole scenario range, plus the pedestrians build_world appends per env
+        O = lib.max_objects() + proto.config["num_pedestrians"] if resample_scenarios else None
         kw = dict(slots_per_env=S, objs_per_env=O, num_pedestrians=proto.config["num_pedestrians"], map_universe=universe)
         arrays, cfg = lib.build_world(idx, seed=rank, **kw, **proto._cfg_kw())
         _apply_vehicle_config(arrays, proto.config)

@@ -15,7 +15,7 @@ EXPORTS = [
     "md_autoreset", "md_step_autoreset", "md_step_host", "md_reset_host", "md_lidar", "md_dynamics", "md_after_step", "md_idm",
     "md_get_state", "md_set_state", "md_snapshot", "md_launch_count", "md_profile_begin", "md_profile_end",
     "md_host_views", "md_attach_bank", "md_sizeof_config", "md_sizeof_arrays", "md_host_groups", "md_host_group_count",
-    "md_host_group_views", "md_host_send", "md_host_recv", "md_host_compact", "md_fp32_peak",
+    "md_host_group_views", "md_host_send", "md_host_recv", "md_host_compact", "md_fp32_peak", "md_enable_contacts", "md_get_contacts",
 ]
 ABI_VERSION = 4  # include/mdstep.h MD_ABI_VERSION
 
@@ -83,6 +83,8 @@ def load():
     lib.md_host_recv.argtypes = [vp, ip]
     lib.md_host_compact.argtypes = [vp, ip]
     lib.md_fp32_peak.argtypes = [ip, C.POINTER(C.c_double)]
+    lib.md_enable_contacts.argtypes = [vp, ip]
+    lib.md_get_contacts.argtypes = [vp, vp, C.c_size_t]
     lib.md_launch_count.argtypes = [vp]
     lib.md_launch_count.restype = C.c_int64
     for name in EXPORTS:

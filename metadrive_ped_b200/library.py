@@ -23,6 +23,7 @@ def _build_geo(args):
 
 
 class ScenarioLibrary:
+    """Scenarios exported from the reference (an .npz under assets/)."""
     def __init__(self, path):
         if not os.path.isabs(path) and not os.path.exists(path):
             path = os.path.join(ASSET_DIR, path)
@@ -119,3 +120,83 @@ class ScenarioLibrary:
         kw.update(cfg_kw)
         cfg = make_config(len(indices), S, 1, O, **kw)
         return arrays, cfg
+
+
+def _generate_one(args):
+    """(map tables, roster) of one seed: pgmap.BIG + pgspawn.populate (a picklable unit for the process pool)"""
+    from . import pgmap, pgspawn
+    seed, c = args
+    lane_num, lane_width = c["lane_num"], c["lane_width"]
+    if c["random_lane_width"] or c["random_lane_num"]:   # PGMapManager.add_random_to_map (manager/pg_map_manager.py:76-83)
+        rng = pgmap.seeded_rng(seed)
+        if c["random_lane_width"]:
+            lane_width = rng.rand() * (4.5 - 3.0) + 3.0
+        if c["random_lane_num"]:
+            lane_num = int(rng.randint(2, 3 + 1))
+    lane_f, lane_i, road_i, meta, big = pgmap.generate(seed, c["map"], lane_num, lane_width, c["exit_length"])
+    sc_ = pgspawn.populate(big, seed, c["traffic_density"], c["traffic_mode"], c["accident_prob"], lane_num, lane_width,
+                           include_breakdown=c["include_breakdown"], random_spawn_lane=c["random_spawn_lane_index"],
+                           need_inverse_traffic=c["need_inverse_traffic"], random_traffic=c["random_traffic"],
+                           random_agent_model=c["random_agent_model"], agent_model=c["agent_model"])
+    meta["respawn"] = pgspawn.respawn_table(big, seed)
+    return seed, (lane_f, lane_i, road_i, meta, lane_num), sc_
+
+
+class GeneratedLibrary(ScenarioLibrary):
+    """Scenarios GENERATED on the product side for any supported config: `pgmap` (BIG + PG blocks) builds the map of a
+    seed, `pgspawn` populates it (ego, IDM traffic, accident scenes) with the reference's seeded streams.  Same interface
+    as the exported libraries, which double as its goldens (tests/test_pgmap.py)."""
+    DEFAULTS = dict(map=3, traffic_density=0.1, traffic_mode="trigger", accident_prob=0.0, lane_num=3, lane_width=3.5,
+                    exit_length=50, random_lane_width=False, random_lane_num=False, random_spawn_lane_index=True,
+                    need_inverse_traffic=False, random_traffic=False, random_agent_model=False, agent_model="default",
+                    include_breakdown=True)
+
+    def __init__(self, start_seed=0, num_scenarios=1, env_kind="metadrive", **config):
+        c = dict(self.DEFAULTS)
+        for k, v in config.items():
+            if k not in c:
+                raise KeyError(k)
+            c[k] = v
+        self.gen = c
+        self.path = "<generated>"
+        self.seeds = np.arange(start_seed, start_seed + num_scenarios, dtype=np.int32)
+        self.env_kind = env_kind
+        self.config = dict(map=c["map"], traffic_density=c["traffic_density"], traffic_mode=c["traffic_mode"],
+                           accident_prob=c["accident_prob"], start_seed=start_seed, num_scenarios=num_scenarios)
+        self._maps, self._rosters, self._geo = {}, {}, {}
+
+    def ensure(self, indices):
+        todo = [int(i) for i in dict.fromkeys(indices) if int(i) not in self._maps]
+        if not todo:
+            return
+        jobs = [(int(self.seeds[i]), self.gen) for i in todo]
+        workers = min(len(jobs), os.cpu_count() or 1)
+        if workers > 1 and len(jobs) > 8:
+            with ProcessPoolExecutor(workers) as ex:
+                results = list(ex.map(_generate_one, jobs, chunksize=4))
+        else:
+            results = [_generate_one(j) for j in jobs]
+        for i, (_, m, r) in zip(todo, results):
+            self._maps[i], self._rosters[i] = m, r
+
+    def _map_args(self, i):
+        self.ensure([i])
+        lane_f, lane_i, road_i, meta, lane_num = self._maps[int(i)]
+        return (lane_f, lane_i, road_i, meta, lane_num)
+
+    def geometries(self, indices, workers=None):
+        self.ensure(indices)
+        return super().geometries(indices, workers)
+
+    def scenario(self, i, map_id):
+        import dataclasses
+        self.ensure([i])
+        return dataclasses.replace(self._rosters[int(i)], map_id=map_id)
+
+    def max_vehicles(self):
+        self.ensure(range(len(self)))
+        return max(len(r.veh_static) for r in self._rosters.values())
+
+    def max_objects(self):
+        self.ensure(range(len(self)))
+        return max(len(r.objects) for r in self._rosters.values())

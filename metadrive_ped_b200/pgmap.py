@@ -965,11 +965,15 @@ class BIG:
     """component/algorithm/BIG.py:28-169: forward / destruct / search-sibling / back state machine."""
     MAX_TRIAL = 5
 
-    def __init__(self, lane_num, lane_width, seed, exit_length=50):
+    def __init__(self, lane_num, lane_width, seed, exit_length=50, block_overrides=None):
         self.rng = seeded_rng(seed)
         self.world = Net()
         self.blocks = [FirstBlock(self.world, lane_width, lane_num, exit_length)]
         self.sequence = None
+        # per block ID, class constants to replace - the multi-agent maps lengthen the exits of their block by assigning
+        # the CLASS attribute (envs/marl_envs/marl_inout_roundabout.py:46, marl_intersection.py:46), which in the reference
+        # then leaks into every later map of the same process; here it is an explicit, per-map argument
+        self.block_overrides = block_overrides or {}
 
     def generate(self, spec):
         if isinstance(spec, int) and not isinstance(spec, bool):
@@ -1012,7 +1016,10 @@ class BIG:
         last = self.blocks[-1]
         key = self.rng.choice(list(last.sockets.keys()))
         sock = last.get_socket(list(last.sockets).index(key))
-        return cls(len(self.blocks), sock, self.world, self.rng.randint(0, 10000))
+        blk = cls(len(self.blocks), sock, self.world, self.rng.randint(0, 10000))
+        for k, v in self.block_overrides.get(cls.ID, {}).items():
+            setattr(blk, k, v)
+        return blk
 
     def _construct(self, b):
         ok = b.construct()
@@ -1067,8 +1074,8 @@ def to_tables(big):
     return lane_f, lane_i, road_i, meta
 
 
-def generate(seed, map_spec=3, lane_num=3, lane_width=3.5, exit_length=50):
+def generate(seed, map_spec=3, lane_num=3, lane_width=3.5, exit_length=50, block_overrides=None):
     """The map `MetaDriveEnv(dict(map=map_spec, ...)).reset(seed)` builds (component/map/pg_map.py:55-80,
     manager/pg_map_manager.py:57-74): BIG seeded with the scenario seed.  Returns (lane_f, lane_i, road_i, meta, big)."""
-    big = BIG(lane_num, lane_width, seed, exit_length).generate(map_spec)
+    big = BIG(lane_num, lane_width, seed, exit_length, block_overrides).generate(map_spec)
     return to_tables(big) + (big, )

@@ -71,6 +71,24 @@ def lane_position(row, lon, lat):
     return np.array([cx + rr * math.cos(phi), cy + rr * math.sin(phi)])
 
 
+def lane_local(row, x, y):
+    """(longitude, lateral) of a point on a lane row (straight_lane.py:60-66, circular_lane.py:57-121); rows of the packed
+    `lane_f` table [type, width, length, 7 shape parameters, ...]"""
+    if row[0] == 0:
+        sx, sy, ex, ey = row[3:7]
+        ln = math.hypot(ex - sx, ey - sy)
+        dx, dy = (ex - sx) / ln, (ey - sy) / ln
+        return (x - sx) * dx + (y - sy) * dy, (x - sx) * dy - (y - sy) * dx
+    cx, cy, r, sp, ep, direction = row[3:9]
+    wrap = lambda a: (a + math.pi) % (2 * math.pi) - math.pi
+    phase = math.atan2(y - cy, x - cx)
+    if abs(wrap(phase - sp)) > abs(wrap(phase - ep)):
+        lon = wrap((ep - phase) if direction < 0 else (phase - ep)) * r + row[2]
+    else:
+        lon = wrap((sp - phase) if direction < 0 else (phase - sp)) * r
+    return lon, direction * (math.hypot(x - cx, y - cy) - r)
+
+
 def lane_heading_at(row, lon):
     if row[0] == 0:
         sx, sy, ex, ey = row[3:7]
@@ -445,7 +463,8 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
         veh_idm[sl, 1] = sc.idm[:, 1]
         veh_c[sl, 0:2] = sc.veh_dyn[:, 0:2]
         m = len(sc.objects)
-        assert m <= O, (m, O)
+        if m > O:
+            raise ValueError("an env holds %d objects but objs_per_env is %d" % (m, O))
         if m:
             ob = obj_f[e * O:e * O + m]
             ob[:, 0:7] = sc.objects[:, 0:7]

@@ -233,6 +233,32 @@ class BatchedSim:
             self._check(n)
         return a[:n]
 
+    def enable_contacts(self, on=True):
+        """Record the contact pairs of every step (md_enable_contacts)."""
+        self._check(self.lib.md_enable_contacts(self.h, int(bool(on))))
+
+    def contacts(self):
+        """[NV, 4] uint32: per vehicle slot the bodies touched during the last step (bit k < S: vehicle slot k of the env,
+        bit S + j: object j)."""
+        out = np.zeros((self.cfg.n_envs * self.cfg.slots_per_env, 4), np.uint32)
+        self._check(self.lib.md_get_contacts(self.h, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def contact_pairs(self, env=0):
+        """the last step's contact pairs of one env as sorted (low, high) index pairs; objects are S + j"""
+        S = self.cfg.slots_per_env
+        rows = self.contacts()[env * S:(env + 1) * S]
+        pairs = set()
+        for i in range(S):
+            for w in range(4):
+                m = int(rows[i, w])
+                while m:
+                    b = (m & -m).bit_length() - 1
+                    k = 32 * w + b
+                    pairs.add((min(i, k), max(i, k)))
+                    m &= m - 1
+        return sorted(pairs)
+
     def fp32_peak(self):
         """Measured FP32-FMA peak of this GPU in TFLOP/s (md_fp32_peak)."""
         v = C.c_double()

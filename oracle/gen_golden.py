@@ -45,8 +45,86 @@ def roster_arrays(env, mi, roster):
                 objects=roster.objects_table())
 
 
+class Recorders:
+    """What the reference decides per step, besides the state: for every Lidar.perceive call the object each ray hit
+    (sensors/distance_detector.py:27-85: `detected_objects` holds one result per hitting ray, in ray order) and the body
+    pairs the contact-added callback saw (engine/core/collision_callback.py:5-42).  Installed by wrapping the two module
+    functions the engine binds, before the engine exists."""
+    def __init__(self):
+        import metadrive.component.sensors.distance_detector as dd
+        import metadrive.engine.core.engine_core as ec
+        from metadrive.utils.utils import get_object_from_node
+        self.scans, self.pairs = [], []
+        orig_p, orig_c = dd.perceive, ec.collision_callback
+
+        def obj_of(node):
+            try:
+                return get_object_from_node(node)
+            except Exception:
+                return None
+
+        def perceive(*a, **kw):
+            cp, objs, colors = orig_p(*a, **kw)
+            self.scans.append((float(kw["vehicle_position_x"]), float(kw["vehicle_position_y"]), float(kw["height"]),
+                               int(kw["num_lasers"]), np.array(cp, np.float64), [obj_of(r.getNode()) for r in objs]))
+            return cp, objs, colors
+
+        def callback(contact):
+            self.pairs.append((obj_of(contact.getNode0()), obj_of(contact.getNode1())))
+            return orig_c(contact)
+
+        dd.perceive, ec.collision_callback = perceive, callback
+
+    def clear(self):
+        self.scans.clear()
+        self.pairs.clear()
+
+    def index_of(self, roster, obj):
+        """roster vehicle k -> k; obstacle j -> 1000 + j; anything else -> -2"""
+        for k, v in enumerate(roster.vehicles):
+            if v is obj:
+                return k
+        kept = [o for o in roster.objects if type(o).__name__ in ("TrafficCone", "TrafficWarning", "TrafficBarrier")]
+        for j, o in enumerate(kept):
+            if o is obj:
+                return 1000 + j
+        return -2
+
+    def ego_hits(self, roster, n_lasers):
+        """hit id per lidar ray of the LAST lidar scan (height 1.2, lidar.py:19), -1 = no hit"""
+        scans = [s for s in self.scans if abs(s[2] - 1.2) < 1e-9 and s[3] == n_lasers]
+        out = np.full(n_lasers, -1, np.int32)
+        if not scans:
+            return out
+        _, _, _, _, cp, objs = scans[-1]
+        it = iter(objs)
+        for i in range(n_lasers):
+            if cp[i] < 1.0:
+                out[i] = self.index_of(roster, next(it))
+        return out
+
+    def step_pairs(self, roster):
+        """sorted unique (low, high) index pairs the contact-added callback reported since the last clear()"""
+        got = set()
+        for a, b in self.pairs:
+            i, j = self.index_of(roster, a), self.index_of(roster, b)
+            if i >= 0 and j >= 0 and i != j and (i < 1000 or j < 1000):
+                got.add((min(i, j), max(i, j)))
+        return sorted(got)
+
+
+def _pad_pairs(per_step):
+    width = max([len(p) for p in per_step] + [1])
+    out = np.full((len(per_step), width, 2), -1, np.int32)
+    for t, p in enumerate(per_step):
+        if p:
+            out[t, :len(p)] = p
+    return out
+
+
 def run_episode(env_cls, config, seed, actions, tag):
     from oracle import ref_export as rx
+    rec = Recorders()
     env = env_cls(config)
     try:
         obs0, _ = env.reset(seed=seed)
@@ -54,12 +132,17 @@ def run_episode(env_cls, config, seed, actions, tag):
         roster = rx.Roster(env, mi)
         init = roster_arrays(env, mi, roster)
         f0, i0 = rx.record_world(env, roster)
+        n_lasers = int(env.config["vehicle_config"]["lidar"]["num_lasers"])
+        hits, pairs = [rec.ego_hits(roster, n_lasers)], []
         fs, is_, obs, rew, cost, term, trunc, infos = [f0], [i0], [obs0], [], [], [], [], []
         for a in actions:
+            rec.clear()
             if config.get("discrete_action"):  # Discrete: the index travels in column 0; MultiDiscrete: both columns
                 o, r, te, tr, info = env.step([int(a[0]), int(a[1])] if config.get("use_multi_discrete") else int(a[0]))
             else:
                 o, r, te, tr, info = env.step(a)
+            hits.append(rec.ego_hits(roster, n_lasers))
+            pairs.append(rec.step_pairs(roster))
             f, i = rx.record_world(env, roster)
             fs.append(f)
             is_.append(i)
@@ -79,6 +162,7 @@ def run_episode(env_cls, config, seed, actions, tag):
             actions=np.asarray(actions[:T], np.float64), veh_f=np.stack(fs), veh_i=np.stack(is_),
             obs=np.stack(obs).astype(np.float32), reward=np.asarray(rew, np.float64), cost=np.asarray(cost, np.float64),
             terminated=np.asarray(term, bool), truncated=np.asarray(trunc, bool), info=np.asarray(infos, np.float64),
+            lidar_hit=np.stack(hits), contact_pairs=_pad_pairs(pairs),
             config=json.dumps(dict({k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))},
                                    num_others=int(env.config["vehicle_config"]["lidar"]["num_others"]),
                                    n_side_lasers=int(env.config["vehicle_config"]["side_detector"]["num_lasers"]),
@@ -117,10 +201,15 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
     (lane-follow driver with `noise`).  Respawn draws are recorded as (index in the list of clear places, destination
     index) per step so that a replay can feed the same random tape."""
     from oracle import ref_export as rx
+    # reproducible multi-agent episodes, the way the reference's own tests pin them
+    # (tests/test_env/test_ma_roundabout_env.py:2-3): the spawn manager takes the global seed and the respawn place draw
+    # (multi_agent_metadrive.py:199) a fixed one
+    config = dict(config, force_seed_spawn_manager=True)
+    env_cls._DEBUG_RANDOM_SEED = 10 + seed
     env = env_cls(config)
     rs = np.random.RandomState(seed)
     try:
-        obs0, _ = env.reset()
+        obs0, _ = env.reset(seed=0)
         eng = env.engine
         m, mi = rx.export_map(env.current_map)
         roster = rx.Roster(env, mi)
@@ -333,6 +422,12 @@ def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
         env.close()
 
 
+ALL_TAGS = ["cfg1_S_straight", "cfg1_S_random", "cfg1_S_discrete", "cfg2_pg3_seed3", "cfg2_pg3_seed7", "cfg2_pg3_seed11_dense",
+            "cfg2_SCO_nolimit", "cfg2_pg3_seed11_others4", "cfg2_pg3_seed3_detectors", "cfg4_safe_seed2", "cfg4_safe_seed5",
+            "cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg3_ma_roundabout", "cfg3_ma_roundabout_respawn",
+            "cfg3_ma_intersection_respawn", "cfg5_ped_X"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
@@ -341,7 +436,22 @@ def main():
     ap.add_argument("--ma-steps", type=int, default=450)
     ap.add_argument("--ma-noise", type=float, default=0.04)
     ap.add_argument("--cfg5-steps", type=int, default=350)
+    ap.add_argument("--exact", action="store_true", help="--only names one tag exactly (not a substring)")
     args = ap.parse_args()
+    if not args.only:
+        # ONE FRESH PROCESS PER TAG.  The reference keeps state in class attributes - the multi-agent maps assign
+        # Roundabout.EXIT_PART_LENGTH / InterSection.EXIT_PART_LENGTH / TInterSection.EXIT_PART_LENGTH
+        # (envs/marl_envs/marl_inout_roundabout.py:46, marl_intersection.py:46, marl_parking_lot.py:171) - so an env built
+        # after a multi-agent env in the same process gets other maps for the same (config, seed).  Round 1 generated all
+        # tags in one process: `cfg2_SCO_nolimit` carried a roundabout with 60 m exits.
+        import subprocess
+        for tag in ALL_TAGS:
+            cmd = [sys.executable, "-m", "oracle.gen_golden", "--only", tag, "--exact", "--out", args.out,
+                   "--steps", str(args.steps), "--ma-steps", str(args.ma_steps), "--ma-noise", str(args.ma_noise),
+                   "--cfg5-steps", str(args.cfg5_steps)]
+            subprocess.check_call(cmd, cwd=ROOT, env=dict(os.environ, PYTHONHASHSEED="0"))
+        return
+    match = (lambda tag: tag == args.only) if args.exact else (lambda tag: args.only in tag)
     from oracle import refshim
     refshim.install()
     from metadrive.envs.metadrive_env import MetaDriveEnv
@@ -389,7 +499,7 @@ def main():
     # BASELINE config 3: MultiAgentRoundaboutEnv with 240-beam lidar
     #   cfg3_ma_roundabout          40 agents, random actions, respawn off (crash / out-of-road / wreck bookkeeping)
     #   cfg3_ma_roundabout_respawn  12 agents, lane-follow driver + noise, respawn on (arrivals, respawn, new routes)
-    if not args.only or args.only == "cfg3_ma_roundabout":
+    if match("cfg3_ma_roundabout") and args.only == "cfg3_ma_roundabout":
         from metadrive.envs.marl_envs.marl_inout_roundabout import MultiAgentRoundaboutEnv
         T = min(args.steps, 90)
         rs = np.random.RandomState(3)
@@ -401,7 +511,7 @@ def main():
         np.savez_compressed(path, **out)
         print("cfg3_ma_roundabout steps", len(out["reward"]), "seats", out["veh_f"].shape[1], "->",
               os.path.getsize(path) // 1024, "KiB", flush=True)
-    if not args.only or args.only == "cfg3_ma_roundabout_respawn":
+    if args.only == "cfg3_ma_roundabout_respawn":
         from metadrive.envs.marl_envs.marl_inout_roundabout import MultiAgentRoundaboutEnv
         lid = dict(vehicle_config=dict(lidar=dict(num_lasers=240, distance=50, num_others=0)))
         cfg3 = dict(num_agents=12, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, **lid)
@@ -412,7 +522,7 @@ def main():
         print("cfg3_ma_roundabout_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
               "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     # the other shipped multi-agent map (envs/marl_envs/marl_intersection.py): same seats / respawn bookkeeping on the X block
-    if not args.only or args.only == "cfg3_ma_intersection_respawn":
+    if args.only == "cfg3_ma_intersection_respawn":
         from metadrive.envs.marl_envs.marl_intersection import MultiAgentIntersectionEnv
         lid = dict(vehicle_config=dict(lidar=dict(num_lasers=240, distance=50, num_others=0)))
         cfgi = dict(num_agents=10, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, **lid)
@@ -424,7 +534,7 @@ def main():
               "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     # BASELINE config 5 (composed): X map, respawn-mode IDM traffic, 16 crossing pedestrians; crashes do not end the
     # episode here so that the trace keeps running through pedestrian / vehicle contacts
-    if not args.only or args.only == "cfg5_ped_X":
+    if args.only == "cfg5_ped_X":
         cfg5 = dict(map="X", traffic_density=0.1, traffic_mode="respawn", num_scenarios=20, start_seed=0, log_level=50,
                     crash_vehicle_done=False, crash_human_done=False, crash_object_done=False)
         out = run_episode_cfg5(cfg5, 4, args.cfg5_steps, "cfg5_ped_X")
@@ -433,7 +543,7 @@ def main():
         print("cfg5_ped_X steps", len(out["reward"]), "vehicles", out["veh_f"].shape[1], "respawns", len(out["respawn_events"]),
               "crash_human steps", int(((out["veh_i"][:, 0, 5] & 8) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     for tag, cls, cfg, seed, acts in cases:
-        if args.only and args.only not in tag:
+        if not match(tag):
             continue
         out = run_episode(cls, cfg, seed, acts, tag)
         path = os.path.join(args.out, tag + ".npz")

@@ -65,6 +65,22 @@ class OracleSim:
         self.info_f = np.zeros((na, 8), np.float32)
         self.hit = np.zeros((na, cfg.n_lasers), np.int32)
 
+    def enable_contacts(self):
+        """record the contact pairs of every step: self.contacts [NV, 4] uint32 (the layout of md_get_contacts)"""
+        self.contacts = np.zeros((self.cfg.n_envs * self.cfg.slots_per_env, 4), np.uint32)
+
+    def contact_pairs(self, env=0):
+        S = self.cfg.slots_per_env
+        pairs = set()
+        for i in range(S):
+            for w in range(4):
+                m = int(self.contacts[env * S + i, w])
+                while m:
+                    b = (m & -m).bit_length() - 1
+                    pairs.add((min(i, 32 * w + b), max(i, 32 * w + b)))
+                    m &= m - 1
+        return sorted(pairs)
+
     def reset_observe(self):
         lib().mdo_reset_observe(C.byref(self.cfg), C.byref(self.A), _p(self.ray_cs), _p(self.obs), _p(self.hit))
         return self.obs
@@ -73,9 +89,12 @@ class OracleSim:
         actions = np.ascontiguousarray(actions, np.float32).reshape(self.n_agents, 2)
         if env_end is None:
             env_end = self.cfg.n_envs
+        # the output pointer is a global of the C library: (re)bind it for this call, never leave a dangling one behind
+        lib().mdo_set_contact_out(_p(self.contacts) if getattr(self, "contacts", None) is not None else None)
         lib().mdo_step(C.byref(self.cfg), C.byref(self.A), _p(self.ray_cs), _p(actions), _p(self.obs), _p(self.reward),
                        _p(self.cost), _p(self.term), _p(self.trunc), _p(self.info_flags), _p(self.info_f),
                        _p(self.hit), C.c_int(env_begin), C.c_int(env_end))
+        lib().mdo_set_contact_out(None)
         return self.obs, self.reward, self.term, self.trunc
 
     def reset_envs(self, mask):

@@ -245,9 +245,16 @@ class Roster:
                 for name in bv.vehicles:
                     self.traffic.append(eng.get_objects([name])[name])
                     self.trigger_block.append(k + 1)
-        self.vehicles = self.agents + self.traffic
         om = getattr(eng, "object_manager", None)
         self.objects = list(om.spawned_objects.values()) if om is not None else []
+        # the broken-down car of a break-down scene (manager/object_manager.py:95-102) is a vehicle body in the world that
+        # no manager drives: it closes the roster with trigger block 0 (never triggered)
+        from metadrive.component.vehicle.base_vehicle import BaseVehicle
+        for o in self.objects:
+            if isinstance(o, BaseVehicle):
+                self.traffic.append(o)
+                self.trigger_block.append(0)
+        self.vehicles = self.agents + self.traffic
 
     def static_table(self):
         return np.stack([vehicle_static(v) for v in self.vehicles])

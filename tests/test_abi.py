@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     src = open(os.path.join(ROOT, "include", "mdstep.h")).read()
-    return sorted(set(re.findall(r"\b(md_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(md_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():

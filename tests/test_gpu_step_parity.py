@@ -10,6 +10,9 @@ from tests.golden_util import golden_world, list_golden, load_golden
 pytestmark = pytest.mark.gpu
 
 STATE_FLAG_MASK = 0x3ff
+# fixtures whose ego observation is not compared with the trace step by step (tests/test_oracle_golden.KNIFE_EDGES: an IDM
+# float32 / float64 knife edge changes one traffic vehicle's branch, the ego's num_others block sees it)
+KNIFE_TAGS = ("cfg2_pg3_seed11_others4", )
 
 
 def _make(tag, replicas):
@@ -67,13 +70,15 @@ def test_step_matches_oracle_and_golden(tag, oracle_lib):
     g, cfg, sim, orc, torch = _make(tag, replicas=3)
     n = g["veh_f"].shape[1]
     S = cfg.slots_per_env
+    sim.enable_contacts()
+    orc.enable_contacts()
     obs_g = sim.reset().cpu().numpy()
     obs_o = orc.reset_observe().copy()
     np.testing.assert_allclose(obs_g, obs_o, atol=1e-5, rtol=0)
     np.testing.assert_allclose(obs_g[0], g["obs"][0], atol=2e-4, rtol=0)
     T = len(g["reward"])
     events = np.asarray(g["respawn_events"]).reshape(-1, 5) if "respawn_events" in g else np.zeros((0, 5))
-    ego_touched = False
+    n_contact_steps = 0
     for t in range(T):
         a = np.tile(g["actions"][t].astype(np.float32), (cfg.n_envs, 1))
         sim.step(torch.from_numpy(a).cuda())
@@ -100,14 +105,28 @@ def test_step_matches_oracle_and_golden(tag, oracle_lib):
         np.testing.assert_array_equal(sim.info_f.cpu().numpy(), orc.info_f)
         og = sim.obs.cpu().numpy()
         np.testing.assert_array_equal(og, orc.obs, err_msg="observation at step %d" % t)
-        # against the reference's own trace (ego): reward, done, observation - while the replay is free-running.  Once
-        # the ego has been in a non-terminal contact, the float32 replay drifts from the float64 trace (see
-        # tests/test_oracle_golden.py, which re-synchronises and goes on); the oracle comparison above continues
-        ego_touched = ego_touched or bool(vi_o[0, 8] & 0x3)
-        if not ego_touched:
-            assert abs(float(sim.reward[0]) - g["reward"][t]) < 2e-3
-            assert bool(sim.terminated[0]) == bool(g["terminated"][t])
-            np.testing.assert_allclose(og[0, :19], g["obs"][t + 1][:19], atol=2e-3, rtol=0)
+        # collision pair sets (north star: bit-exact): the bodies every chassis touched during the sub-steps
+        np.testing.assert_array_equal(sim.contacts(), orc.contacts, err_msg="contact pairs at step %d" % t)
+        n_contact_steps += bool(orc.contacts.any())
+        # against the reference's own trace (ego): reward, done, observation - over the WHOLE episode.  Bodies in a
+        # sustained contact drift from the float64 trace by ~1e-4 m per step (tests/test_oracle_golden.py), so - exactly
+        # as there - they are re-synchronised to the trace AFTER having been compared: a one-step-ahead check during the
+        # contact, a free-running replay everywhere else.  Both implementations get the same state back.
+        tol = 5e-3 if (int(g["veh_i"][t + 1][0, 5]) & 0x3) else 2e-3
+        assert abs(float(sim.reward[0]) - g["reward"][t]) < 2e-3, ("reward", tag, t)
+        assert bool(sim.terminated[0]) == bool(g["terminated"][t]), ("terminated", tag, t)
+        if tag not in KNIFE_TAGS:
+            np.testing.assert_allclose(og[0, :19], g["obs"][t + 1][:19], atol=tol, rtol=0, err_msg="state obs at step %d" % t)
+        ref_f, ref_i = g["veh_f"][t + 1], g["veh_i"][t + 1]
+        touching = [k for k in range(n) if ref_i[k, 0] == 1 and (ref_i[k, 5] & 0x3)]
+        if touching:
+            vs = vs_o.copy().reshape(cfg.n_envs, S, -1)
+            for k in touching:
+                vs[:, k, 0:13] = ref_f[k, 0:13].astype(np.float32)
+            orc.a["veh_s"][:] = vs.reshape(-1, vs.shape[-1])
+            sim.set_state("veh_s", orc.a["veh_s"])
+    if tag in ("cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg5_ped_X"):
+        assert n_contact_steps >= (2 if "bump" in tag else 5), "the fixture must hold contacts"
     sim.close()
 
 
