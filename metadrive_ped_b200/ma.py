@@ -93,16 +93,54 @@ from .abi import make_config
 ASSET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 
 
+# The multi-agent envs' fixed maps and spawn roads (envs/marl_envs/marl_inout_roundabout.py:12-24, 27-60;
+# marl_intersection.py:12-25, 27-71), built on the product side by pgmap.build_fixed.  The exported assets
+# (assets/ma_*.npz, oracle/gen_assets.py --env ma_*) are their goldens (tests/test_pgmap.py).
+MA_MAPS = {
+    "roundabout": dict(env="ma_roundabout", num_agents=40, block="O", spawn_nodes=[(0, 2, 3), (1, 2, 3), (2, 2, 3)]),
+    "intersection": dict(env="ma_intersection", num_agents=30, block="X", spawn_nodes=[(0, 0, 1), (1, 0, 1), (2, 0, 1)]),
+}
+ASSET_KIND = {"ma_roundabout.npz": "roundabout", "ma_intersection.npz": "intersection"}
+
+
+def generated_source(kind, lane_num=2, lane_width=3.5, exit_length=60.0):
+    """What an exported multi-agent asset holds, generated: lane tables, spawn roads (the first block's second road and the
+    three roads ENTERING the block, i.e. the negatives of its exits), destination nodes, the static_default vehicle row
+    (component/pg_space.py:227-234, vehicle_type.py:35-36) and SpawnManager's slot constants (spawn_manager.py:25-35)."""
+    from . import pgmap, pgspawn
+    m = MA_MAPS[kind]
+    lane_f, lane_i, road_i, meta, big = pgmap.build_fixed(kind, lane_num, lane_width, exit_length)
+    node = {n: k for k, n in enumerate(meta["nodes"])}
+    roads = [(">>", ">>>")]
+    for part, a, b in m["spawn_nodes"]:
+        blk = big.blocks[1]
+        roads.append(pgmap.neg_road((blk.node(part, a), blk.node(part, b))))
+    d = pgspawn.DIMS["static_default"]
+    static = [pgspawn.VEHICLE_TYPES.index("static_default"), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], 800, 150, 40,
+              0.9, 80, 0.0]
+    conf = dict(env=m["env"], num_agents=m["num_agents"], lane_num=lane_num, exit_length=float(exit_length), entrance_length=10.0,
+                respawn_longitude=RESPAWN_REGION_LONGITUDE, respawn_lateral=RESPAWN_REGION_LATERAL, max_vehicle_length=10.0,
+                max_vehicle_width=2.5, disable_u_turn=False)
+    return dict(lane_f=lane_f, lane_i=lane_i, road_i=road_i, meta=json.dumps(meta), config=json.dumps(conf),
+                spawn_roads=np.array([[node[a], node[b]] for a, b in roads], np.int32),
+                dest_nodes=np.array([node[pgmap.neg_road(r)[1]] for r in roads], np.int32),
+                veh_static=np.asarray(static, np.float32))
+
+
 class MultiAgentLibrary:
-    """The fixed map of one multi-agent env (exported by oracle/gen_assets.py --env ma_*) plus what SpawnManager needs.
+    """The fixed map of one multi-agent env plus what SpawnManager needs.  `name` = "roundabout" / "intersection" (generated
+    by pgmap.build_fixed) or an exported asset file (oracle/gen_assets.py --env ma_*).
 
     `scenario(rng)` restates SpawnManager.reset (manager/spawn_manager.py:72-115): num_agents of the available slots
     (spawn road x lane x longitudinal slot) drawn without replacement, a random offset inside the slot
     (`_randomize_position_in_slot`, :211-217) and a random destination per agent (marl_inout_roundabout.py:138-143).
     The reference draws these from an unseeded generator; here the caller passes the generator."""
-    def __init__(self, name):
-        path = name if os.path.exists(name) else os.path.join(ASSET_DIR, name)
-        d = np.load(path, allow_pickle=False)
+    def __init__(self, name, from_asset=False):
+        if not from_asset and ASSET_KIND.get(name, name) in MA_MAPS:
+            d = generated_source(ASSET_KIND.get(name, name))
+        else:
+            path = name if os.path.exists(name) else os.path.join(ASSET_DIR, name)
+            d = np.load(path, allow_pickle=False)
         self.conf = json.loads(str(d["config"]))
         if self.conf.get("disable_u_turn"):
             raise NotImplementedError("destination draws without U-turns are not covered")

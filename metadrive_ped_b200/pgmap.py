@@ -535,8 +535,11 @@ class Block:
         self.respawn_roads.clear()
         self.sockets.clear()
 
-    def construct(self):
+    def construct(self, extra=None):
+        """BaseBlock.construct_block (block/base_block.py:95-131); `extra` = construct_from_config's overrides"""
         self.resample()
+        if extra:
+            self.cfg.update(extra)
         self.clear()
         self.trials += 1
         ok = self.plug()
@@ -741,9 +744,12 @@ class InterSection(Block):
     ID = "X"
     SPACE = {"radius": const(10), "change_lane_num": disc(0, 1), "decrease_increase": disc(0, 1)}
     ANGLE, EXIT_LEN = 90, 35
+    u_turn = False          # InterSection.enable_u_turn (the multi-agent intersection map turns it on)
+    std = True              # StdInterSection: the lane number never changes across the junction
 
     def plug(self):
-        self.cfg["change_lane_num"] = 0
+        if self.std:
+            self.cfg["change_lane_num"] = 0
         return self.plug_x()
 
     def plug_x(self):
@@ -779,6 +785,12 @@ class InterSection(Block):
         ok = True
         left = attach_lanes[0]
         self._left_turn(radius, n, left, attach, nodes, part)
+        if self.u_turn:      # _create_u_turn (intersection.py:213-235): a half circle back onto the opposite road
+            lanes = self.net.lanes(attach) if part != 0 else self.pos_lanes
+            bend, _ = bend_then_straight(lanes[0], 0.1, self.lane_width / 2, np.deg2rad(180), False, lanes[0].width_at(0),
+                                         (L_NONE, L_NONE))
+            road_from(bend, len(lanes), (attach[1], neg_road(attach)[0]), self.net, self.world, toward_smaller=False,
+                      center_line=L_NONE, side_line=L_NONE, inner_line=L_NONE, kind=LANE_UNSTRUCTURED)
         on_road = list(attach_lanes)
         through = 2 * radius + (2 * n - 1) * on_road[0].width_at(0)
         for l in on_road:
@@ -1072,6 +1084,30 @@ def to_tables(big):
                      for s in blk.sockets.values()]))
     meta = dict(nodes=list(nodes.keys()), blocks=blocks)
     return lane_f, lane_i, road_i, meta
+
+
+def build_fixed(kind, lane_num=2, lane_width=3.5, exit_length=60):
+    """The fixed maps of the multi-agent envs (envs/marl_envs/marl_inout_roundabout.py:27-60, marl_intersection.py:27-71):
+    a first block and ONE block built from a given configuration with block seed 1."""
+    big = BIG.__new__(BIG)
+    big.rng, big.sequence, big.block_overrides = None, None, {}
+    big.world = Net()
+    big.blocks = [FirstBlock(big.world, lane_width, lane_num, exit_length)]
+    sock = big.blocks[0].get_socket(0)
+    if kind == "roundabout":
+        blk = Roundabout(1, sock, big.world, 1)
+        blk.EXIT_LEN = exit_length
+        blk.construct(dict(exit_radius=10, inner_radius=30, angle=70))
+    elif kind == "intersection":
+        blk = InterSection(1, sock, big.world, 1)
+        blk.EXIT_LEN = exit_length
+        blk.std = False
+        blk.u_turn = lane_num > 1
+        blk.construct()
+    else:
+        raise NotImplementedError("multi-agent map %r is not restated" % kind)
+    big.blocks.append(blk)
+    return to_tables(big) + (big, )
 
 
 def generate(seed, map_spec=3, lane_num=3, lane_width=3.5, exit_length=50, block_overrides=None):

@@ -154,3 +154,24 @@ def test_golden_fixtures_regenerate_identically(tag, tmp_path):
             assert str(old[k]) == str(new[k]), k
         else:
             np.testing.assert_array_equal(old[k], new[k], err_msg=k)
+
+
+@pytest.mark.parametrize("asset", ["ma_roundabout.npz", "ma_intersection.npz"])
+def test_generated_multi_agent_maps_equal_the_exported_assets(asset):
+    """MARoundaboutMap / MAIntersectionMap (exit length 60, two lanes, U-turns on the intersection) and the spawn roads,
+    destination nodes, slot constants and static_default vehicle of the multi-agent envs, generated vs exported."""
+    from metadrive_ped_b200.ma import MultiAgentLibrary
+    gen, ref = MultiAgentLibrary(asset), MultiAgentLibrary(asset, from_asset=True)
+    for k in ("lane_f", "lane_i", "road_i"):
+        np.testing.assert_array_equal(getattr(gen.table, k), getattr(ref.table, k), err_msg=k)
+    np.testing.assert_array_equal(gen.spawn_roads, ref.spawn_roads)
+    np.testing.assert_array_equal(gen.dest_nodes, ref.dest_nodes)
+    np.testing.assert_array_equal(gen.veh_static, ref.veh_static)
+    assert gen.slots == ref.slots and gen.max_capacity == ref.max_capacity
+    for k in ("lane_num", "exit_length", "entrance_length", "respawn_longitude", "respawn_lateral", "max_vehicle_length",
+              "max_vehicle_width", "num_agents"):
+        assert gen.conf[k] == ref.conf[k], k
+    a, ca = gen.build_world(3, 8, seed=5)
+    b, cb = ref.build_world(3, 8, seed=5)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
