@@ -244,6 +244,9 @@ typedef struct MdConfig {
      * draw, random tape laps, IDM randint, lidar noise) see the same global env / slot / agent index as a whole-batch
      * launch and the results do not depend on how the batch was split. */
     int env_base;
+    /* MultiAgentBottleneckEnv / MultiAgentTollgateEnv.reward_function (envs/marl_envs/marl_bottleneck.py:89-127) drop the
+     * `positive_road` sign MetaDriveEnv.reward_function applies off the reference lanes (envs/metadrive_env.py:249-266) */
+    int ignore_road_sign;
 } MdConfig;
 
 /* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */

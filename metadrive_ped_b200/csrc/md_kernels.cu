@@ -732,7 +732,7 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         float positive = 1.0f;
         if (!(lane >= cur_first && lane < cur_first + cur_n)) {
             rl = cur_first;
-            positive = m.road_i[cur_road * ROAD_I + RI_NEG] ? -1.0f : 1.0f;
+            positive = (m.road_i[cur_road * ROAD_I + RI_NEG] && !cfg.ignore_road_sign) ? -1.0f : 1.0f;
         }
         float long_last, long_now, lat_now, tmp;
         lane_local(m.lane_f + rl * LANE_F, C[VC_LAST_X], C[VC_LAST_Y], long_last, tmp);

@@ -446,6 +446,12 @@ def _ma_cfg_kw(c):
     kw = MetaDriveEnv._cfg_kw(type("C", (), {"config": c})())
     kw.update(delay_done=int(c["delay_done"]), allow_respawn=int(bool(c["allow_respawn"])),
               ma_crash_done=int(bool(c["crash_done"])), ma_out_of_road_done=int(bool(c["out_of_road_done"])))
+    if "cross_yellow_line_done" in c:
+        # MultiAgentBottleneckEnv._is_out_of_road / reward_function (envs/marl_envs/marl_bottleneck.py:89-135): white solid
+        # line | off the lanes | sidewalk, plus the yellow solid line when cross_yellow_line_done; no positive_road sign
+        if not c["cross_yellow_line_done"]:
+            raise NotImplementedError("cross_yellow_line_done=False is not covered")
+        kw.update(out_of_route_done=0, on_continuous_line_done=1, ignore_road_sign=1)
     return kw
 
 
@@ -463,7 +469,8 @@ class MultiAgentMetaDrive:
         d = _merge(STEP_DEFAULTS, {k: v for k, v in MA_DEFAULTS.items() if k in STEP_DEFAULTS})
         d.update({k: v for k, v in MA_DEFAULTS.items() if k not in STEP_DEFAULTS})
         d["vehicle_config"] = _merge(STEP_DEFAULTS["vehicle_config"], MA_DEFAULTS["vehicle_config"])
-        d.update(cls.ENV_DEFAULTS)
+        d.update({k: v for k, v in cls.ENV_DEFAULTS.items() if k != "vehicle_config"})
+        d["vehicle_config"] = _merge(d["vehicle_config"], cls.ENV_DEFAULTS.get("vehicle_config", {}))
         return d
 
     def __init__(self, config=None):
@@ -575,6 +582,15 @@ class MultiAgentIntersectionEnv(MultiAgentMetaDrive):
     """envs/marl_envs/marl_intersection.py:12-25, 98-108"""
     ASSET = "ma_intersection.npz"
     ENV_DEFAULTS = dict(num_agents=30)
+
+
+class MultiAgentBottleneckEnv(MultiAgentMetaDrive):
+    """envs/marl_envs/marl_bottleneck.py:10-25, 81-139: 4 lanes merge into 1 and split again (I -> Merge -> Split); agents
+    are born at both ends and drive to the other end (no destination draw), 4-ray side / lane-line detectors"""
+    ASSET = "ma_bottleneck.npz"
+    ENV_DEFAULTS = dict(num_agents=20, cross_yellow_line_done=True,
+                        vehicle_config=dict(side_detector=dict(num_lasers=4, distance=50),
+                                            lane_line_detector=dict(num_lasers=4, distance=20)))
 
 
 class BatchedMultiAgentEnv:

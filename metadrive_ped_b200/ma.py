@@ -51,7 +51,10 @@ def build_ma_tables(geo: "sc.MapGeometry", spawn_roads, dest_nodes):
     """places [R*lanes, 8] = x, y, quat w, quat z, lane id, cos(heading), sin(heading), spawn-road index
        routes [R*D, ROUTE_MAX] node ids, -1 padded (row = road * D + destination)."""
     spawn_roads = np.asarray(spawn_roads, np.int32).reshape(-1, 2)
-    dest_nodes = np.asarray(dest_nodes, np.int32).reshape(-1)
+    dest_nodes = np.asarray(dest_nodes, np.int32)
+    if dest_nodes.ndim == 1:      # one destination list shared by every spawn road (a destination is DRAWN per agent)
+        dest_nodes = np.tile(dest_nodes, (len(spawn_roads), 1))
+    # else [R, D]: per-road lists, e.g. D = 1 for the maps whose destination follows from the spawn road (auto_assign_task)
     road_key = {(int(r[0]), int(r[1])): k for k, r in enumerate(geo.road_i)}
     places = []
     for ri, (a, b) in enumerate(spawn_roads):
@@ -65,11 +68,11 @@ def build_ma_tables(geo: "sc.MapGeometry", spawn_roads, dest_nodes):
             heading = sc.lane_heading_at(row, lon)
             yaw = heading - math.pi / 2  # the chassis +Y axis is the nose (component/vehicle/base_vehicle.py:990-1001)
             places.append([x, y, math.cos(yaw / 2), math.sin(yaw / 2), lane, math.cos(heading), math.sin(heading), ri])
-    R, D = len(spawn_roads), len(dest_nodes)
+    R, D = dest_nodes.shape
     routes = np.full((R * D, sc.ROUTE_MAX), -1, np.int32)
     for ri in range(R):
         for d in range(D):
-            p = route_for(geo.road_i, spawn_roads[ri], dest_nodes[d])
+            p = route_for(geo.road_i, spawn_roads[ri], dest_nodes[ri, d])
             assert 2 <= len(p) <= sc.ROUTE_MAX, (ri, d, p)
             routes[ri * D + d, :len(p)] = p
     return dict(places=np.array(places, np.float64), routes=routes, n_roads=R, n_dests=D)
@@ -96,31 +99,51 @@ ASSET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 # The multi-agent envs' fixed maps and spawn roads (envs/marl_envs/marl_inout_roundabout.py:12-24, 27-60;
 # marl_intersection.py:12-25, 27-71), built on the product side by pgmap.build_fixed.  The exported assets
 # (assets/ma_*.npz, oracle/gen_assets.py --env ma_*) are their goldens (tests/test_pgmap.py).
+# `spawn_nodes`: (block index, part, node a, node b) of the roads whose NEGATIVE is a spawn road.  `fixed_dest`: no
+# destination draw - the default SpawnManager leaves `destination` None and NodeNetworkNavigation.auto_assign_task
+# (component/navigation_module/node_network_navigation.py:71-91) sends an agent born on a positive road to the end of the last
+# block's socket and one born on a negative road to the end of the first block's negative road.
 MA_MAPS = {
-    "roundabout": dict(env="ma_roundabout", num_agents=40, block="O", spawn_nodes=[(0, 2, 3), (1, 2, 3), (2, 2, 3)]),
-    "intersection": dict(env="ma_intersection", num_agents=30, block="X", spawn_nodes=[(0, 0, 1), (1, 0, 1), (2, 0, 1)]),
+    "roundabout": dict(env="ma_roundabout", num_agents=40, spawn_nodes=[(1, 0, 2, 3), (1, 1, 2, 3), (1, 2, 2, 3)],
+                       lane_num=2, exit_length=60.0),
+    "intersection": dict(env="ma_intersection", num_agents=30, spawn_nodes=[(1, 0, 0, 1), (1, 1, 0, 1), (1, 2, 0, 1)],
+                         lane_num=2, exit_length=60.0),
+    # envs/marl_envs/marl_bottleneck.py:10-25: first road + the negative of Split's socket road
+    "bottleneck": dict(env="ma_bottleneck", num_agents=20, spawn_nodes=[(2, 0, 0, 1)], lane_num=4, exit_length=60.0,
+                       fixed_dest=True),
+    # envs/marl_envs/marl_tollgate.py:15-36: first road + the negative of the closing Merge's socket road (map only: the env's
+    # toll observation / stay-time rules are not on the device)
+    "tollgate": dict(env="ma_tollgate", num_agents=40, spawn_nodes=[(3, 0, 0, 1)], lane_num=3, exit_length=70.0,
+                     fixed_dest=True),
+    # envs/marl_envs/marl_bidirection.py:10-25 (map only: the reference's env raises KeyError('use_lateral') in its
+    # reward_function, :113, at the first step, so there is no behaviour to pin)
+    "bidirection": dict(env="ma_bidirection", num_agents=20, spawn_nodes=[(3, 0, 0, 1)], lane_num=4, exit_length=60.0,
+                        fixed_dest=True),
 }
-ASSET_KIND = {"ma_roundabout.npz": "roundabout", "ma_intersection.npz": "intersection"}
+ASSET_KIND = {"ma_roundabout.npz": "roundabout", "ma_intersection.npz": "intersection", "ma_bottleneck.npz": "bottleneck",
+              "ma_tollgate.npz": "tollgate", "ma_bidirection.npz": "bidirection"}
 
 
-def generated_source(kind, lane_num=2, lane_width=3.5, exit_length=60.0):
+def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None):
     """What an exported multi-agent asset holds, generated: lane tables, spawn roads (the first block's second road and the
     three roads ENTERING the block, i.e. the negatives of its exits), destination nodes, the static_default vehicle row
     (component/pg_space.py:227-234, vehicle_type.py:35-36) and SpawnManager's slot constants (spawn_manager.py:25-35)."""
     from . import pgmap, pgspawn
     m = MA_MAPS[kind]
+    lane_num = m["lane_num"] if lane_num is None else lane_num
+    exit_length = m["exit_length"] if exit_length is None else exit_length
     lane_f, lane_i, road_i, meta, big = pgmap.build_fixed(kind, lane_num, lane_width, exit_length)
     node = {n: k for k, n in enumerate(meta["nodes"])}
     roads = [(">>", ">>>")]
-    for part, a, b in m["spawn_nodes"]:
-        blk = big.blocks[1]
+    for bi, part, a, b in m["spawn_nodes"]:
+        blk = big.blocks[bi]
         roads.append(pgmap.neg_road((blk.node(part, a), blk.node(part, b))))
     d = pgspawn.DIMS["static_default"]
     static = [pgspawn.VEHICLE_TYPES.index("static_default"), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], 800, 150, 40,
               0.9, 80, 0.0]
     conf = dict(env=m["env"], num_agents=m["num_agents"], lane_num=lane_num, exit_length=float(exit_length), entrance_length=10.0,
                 respawn_longitude=RESPAWN_REGION_LONGITUDE, respawn_lateral=RESPAWN_REGION_LATERAL, max_vehicle_length=10.0,
-                max_vehicle_width=2.5, disable_u_turn=False)
+                max_vehicle_width=2.5, disable_u_turn=False, fixed_dest=bool(m.get("fixed_dest", False)))
     return dict(lane_f=lane_f, lane_i=lane_i, road_i=road_i, meta=json.dumps(meta), config=json.dumps(conf),
                 spawn_roads=np.array([[node[a], node[b]] for a, b in roads], np.int32),
                 dest_nodes=np.array([node[pgmap.neg_road(r)[1]] for r in roads], np.int32),
@@ -150,6 +173,9 @@ class MultiAgentLibrary:
         self.spawn_roads = np.asarray(d["spawn_roads"], np.int32)
         self.dest_nodes = np.asarray(d["dest_nodes"], np.int32)
         self.veh_static = np.asarray(d["veh_static"], np.float32)
+        if self.conf.get("fixed_dest") or self.conf["env"] in ("ma_bottleneck", "ma_tollgate", "ma_bidirection"):
+            # destination of spawn road k = the far end of the map = the end node of the OTHER spawn road's negative
+            self.dest_nodes = self.dest_nodes[::-1].reshape(-1, 1)
         self.tables = build_ma_tables(self.geo, self.spawn_roads, self.dest_nodes)
         c = self.conf
         self.n_slots = int(math.floor((c["exit_length"] - c["entrance_length"]) / c["respawn_longitude"]))
@@ -170,7 +196,7 @@ class MultiAgentLibrary:
         assert 0 < num_agents <= self.max_capacity, \
             "Too many agents! We only accept {} agents, but you have {} agents!".format(self.max_capacity, num_agents)
         pick = rng.choice(len(self.slots), num_agents, replace=False)
-        D = len(self.dest_nodes)
+        D = self.tables["n_dests"]
         dl = (c["respawn_longitude"] - c["max_vehicle_length"]) / 2
         dw = (c["respawn_lateral"] - c["max_vehicle_width"]) / 2
         H = float(self.veh_static[3])

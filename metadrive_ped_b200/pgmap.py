@@ -162,6 +162,10 @@ class SLane(Lane):
     def position(self, lon, lat):
         return self.start + lon * self.direction + lat * self.direction_lateral
 
+    def move(self, start, end):   # StraightLane.reset_start_end
+        self.start, self.end = start, end
+        self.refresh()
+
     def local(self, p):
         dx, dy = p[0] - self.start[0], p[1] - self.start[1]
         return (float(dx * self.direction[0] + dy * self.direction[1]),
@@ -471,11 +475,28 @@ def adverse_road(road, block_net, world_net, ignore=None, center_line=None, side
     return ok
 
 
+def wave_lanes(prev, lateral, wave_len, last_len, width, toward_left=True):
+    """create_wave_lanes (create_pg_block_utils.py:352-380): two opposite arcs that shift a lane sideways by `lateral`
+    over `wave_len`, and the straight lane that follows"""
+    angle = np.pi - 2 * np.arctan(wave_len / (2 * lateral))
+    radius = wave_len / (2 * math.sin(angle))
+    c1, mid = bend_then_straight(prev, 10, radius, angle, False if toward_left else True, width, [L_NONE, L_NONE])
+    mid.move(mid.position(-10, 0), mid.position(mid.length - 10, 0))
+    c2, straight = bend_then_straight(mid, last_len, radius, angle, True if toward_left else False, width, [L_NONE, L_NONE])
+    return c1, c2, straight
+
+
 # ---------------------------------------------------------------------------------------------- blocks
 class Socket:
-    def __init__(self, positive, negative=None):
+    def __init__(self, positive, negative=None, fake_positive=None, fake_negative=None):
         self.positive, self.negative = positive, negative
         self.index = None
+        # BidirectionSocket (pgblock/bidirection.py:57-67): the next block is built from two stand-in lanes instead of the
+        # (overlapping) lanes of the socket roads
+        self.fake_positive, self.fake_negative = fake_positive, fake_negative
+
+    def positive_lanes(self, net):
+        return [self.fake_positive] if self.fake_positive is not None else net.lanes(self.positive)
 
 
 class Block:
@@ -496,7 +517,7 @@ class Block:
         self.cfg = {}
         self.resample()                                    # BaseRunnable.__init__ samples once (base_runnable.py:26)
         if index != 0:
-            self.pos_lanes = world_net.lanes(pre_socket.positive)
+            self.pos_lanes = pre_socket.positive_lanes(world_net)
             self.n_pos = len(self.pos_lanes)
             self.basic = self.pos_lanes[-1]
             self.lane_width = self.basic.width_at(0)
@@ -963,12 +984,160 @@ class Roundabout(Block):
         return self.respawn_lanes() + self.inner_places
 
 
+class Bottleneck(Block):
+    """pgblock/bottleneck.py: Merge ("y") narrows the road by `lane_num` lanes, Split ("Y") widens it"""
+    SPACE = {"length": box(20, 50), "lane_num": disc(1, 2), "bottle_len": const(20), "solid_center_line": const(0)}
+
+    def spawn_lanes(self):
+        return [lanes for lanes in super().spawn_lanes() if isinstance(lanes[0], SLane)]
+
+    def _single(self, lane, road, side):
+        return road_from(lane, 1, road, self.net, self.world, center_line=L_NONE, side_line=side, inner_line=L_NONE)
+
+
+class Merge(Bottleneck):
+    ID = "y"
+
+    def plug(self):
+        c = self.cfg
+        ok = True
+        center = L_CONT if c["solid_center_line"] else L_BROKEN
+        blen = c["bottle_len"]
+        start = self.pre_socket.positive[1]
+        n_straight = max(1, int(self.n_pos - c["lane_num"]))
+        n_wave = self.n_pos - n_straight
+        ref = extend_straight(self.pos_lanes[n_straight - 1], blen, [L_NONE, L_NONE])
+        straight_road = (start, self.node(0, 0))
+        side = L_SIDE if n_wave == 0 else L_NONE
+        ok = road_from(ref, n_straight, straight_road, self.net, self.world, center_line=center, side_line=side,
+                       inner_line=L_NONE) and ok
+        ok = adverse_road(straight_road, self.net, self.world, inner_line=L_NONE, side_line=side, center_line=center) and ok
+        ref = extend_straight(ref, c["length"], [L_NONE, L_NONE])
+        socket_road = (self.node(0, 0), self.node(0, 1))
+        ok = road_from(ref, n_straight, socket_road, self.net, self.world, center_line=center, side_line=L_SIDE,
+                       inner_line=L_BROKEN) and ok
+        ok = adverse_road(socket_road, self.net, self.world, inner_line=L_BROKEN, side_line=L_SIDE, center_line=center) and ok
+        neg_socket = neg_road(socket_road)
+        self.add_socket(Socket(socket_road, neg_socket))
+        for index, lane in enumerate(self.pos_lanes[n_straight:], 1):
+            lateral = index * self.lane_width / 2
+            inner = self.node(1, index)
+            side = L_SIDE if index == self.n_pos - n_straight else L_NONE
+            c1, c2, _ = wave_lanes(lane, lateral, blen, 5, self.lane_width)
+            road_1, road_2 = (start, inner), (inner, self.node(0, 0))
+            ok = self._single(c1, road_1, side) and ok
+            ok = self._single(c2, road_2, side) and ok
+            lane = self.net.lanes(neg_socket)[-1]
+            c2, c1, _ = wave_lanes(lane, lateral, blen, 5, self.lane_width, False)
+            ok = self._single(c2, neg_road(road_2), side) and ok
+            ok = self._single(c1, neg_road(road_1), side) and ok
+        return ok
+
+
+class Split(Bottleneck):
+    ID = "Y"
+
+    def plug(self):
+        c = self.cfg
+        ok = True
+        blen = c["bottle_len"]
+        center = L_CONT if c["solid_center_line"] else L_BROKEN
+        n_wave = c["lane_num"]
+        start = self.pre_socket.positive[1]
+        n_straight = self.n_pos
+        total = n_straight + n_wave
+        ref = extend_straight(self.pos_lanes[n_straight - 1], blen, [L_NONE, L_NONE])
+        straight_road = (start, self.node(0, 0))
+        ok = road_from(ref, n_straight, straight_road, self.net, self.world, center_line=center, side_line=L_NONE,
+                       inner_line=L_NONE) and ok
+        ok = adverse_road(straight_road, self.net, self.world, inner_line=L_NONE, side_line=L_NONE, center_line=center) and ok
+        lane = self.pos_lanes[-1]
+        socket_ref = None
+        for index in range(1, n_wave + 1):
+            lateral = index * self.lane_width / 2
+            inner = self.node(1, index)
+            side = L_SIDE if index == n_wave else L_NONE
+            c1, c2, straight = wave_lanes(lane, lateral, blen, c["length"], self.lane_width, False)
+            if index == n_wave:
+                socket_ref = straight
+            ok = self._single(c1, (start, inner), side) and ok
+            ok = self._single(c2, (inner, self.node(0, 0)), side) and ok
+        socket_road = (self.node(0, 0), self.node(0, 1))
+        ok = road_from(socket_ref, total, socket_road, self.net, self.world, center_line=L_CONT, side_line=L_SIDE,
+                       inner_line=L_BROKEN) and ok
+        ok = adverse_road(socket_road, self.net, self.world, inner_line=L_BROKEN, side_line=L_SIDE, center_line=L_CONT) and ok
+        neg_socket = neg_road(socket_road)
+        self.add_socket(Socket(socket_road, neg_socket))
+        for index, lane in enumerate(self.net.lanes(neg_socket)[self.n_pos:], 1):
+            lateral = index * self.lane_width / 2
+            inner = self.node(1, index)
+            side = L_SIDE if index == n_wave else L_NONE
+            c1, c2, _ = wave_lanes(lane, lateral, blen, 5, self.lane_width)
+            ok = self._single(c1, neg_road((inner, self.node(0, 0))), side) and ok
+            ok = self._single(c2, neg_road((start, inner)), side) and ok
+        return ok
+
+
+class Bidirection(Block):
+    """pgblock/bidirection.py: ONE lane used in both directions (the positive and the negative road overlap)"""
+    ID = "B"
+    SPACE = {"length": box(40.0, 80.0)}
+
+    def plug(self):
+        self.set_part(0)
+        length = self.cfg["length"]
+        basic = self.pos_lanes[0]
+        fake_pos = extend_straight(basic, length, [L_BROKEN, L_SIDE])
+        fake_neg = SLane(fake_pos.position(fake_pos.length, -fake_pos.width), fake_pos.position(0, -fake_pos.width), fake_pos.width)
+        new = SLane(basic.position(basic.length, -basic.width / 2), basic.position(basic.length + length, -basic.width / 2),
+                    basic.width, [L_BROKEN, L_SIDE])
+        road = (self.pre_socket.positive[1], self.new_node())
+        ok = road_from(new, 1, road, self.net, self.world)
+        # create_overlap_road (bidirection.py:10-54): the adverse road lies ON the positive one
+        lanes = self.net.lanes(road)
+        ref = lanes[-1]
+        sym = SLane(ref.position(lanes[-1].length, 0), ref.position(0, 0), lanes[-1].width_at(0), lanes[-1].line_types,
+                    ref.speed_limit)
+        sym.line_colors = (GREY, GREY)
+        ok = road_from(sym, int(len(lanes) * 2 / 2), neg_road(road), self.net, self.world, side_line=L_SIDE, inner_line=L_BROKEN,
+                       center_line=L_CONT, center_color=YELLOW) and ok
+        self.net.lanes(road)[0].line_colors = (YELLOW, GREY)
+        new.line_colors = (GREY, GREY)
+        self.add_socket(Socket(road, neg_road(road), fake_pos, fake_neg))
+        return ok
+
+
+class TollGate(Block):
+    """pgblock/tollgate.py: a straight stretch of solid-lined lanes with a speed limit and a booth on every second lane"""
+    ID = "$"
+    SPACE = Bottleneck.SPACE
+    SPEED_LIMIT = 3
+
+    def plug(self):
+        self.set_part(0)
+        length = self.cfg["length"]
+        new = extend_straight(self.basic, length, [L_CONT, L_SIDE])
+        road = (self.pre_socket.positive[1], self.new_node())
+        ok = road_from(new, self.n_pos, road, self.net, self.world, center_color=YELLOW, center_line=L_CONT, inner_line=L_CONT,
+                       side_line=L_SIDE)
+        ok = adverse_road(road, self.net, self.world, center_color=YELLOW, center_line=L_CONT, inner_line=L_CONT,
+                          side_line=L_SIDE) and ok
+        self.add_socket(Socket(road, neg_road(road)))
+        self.buildings = []       # (lane, position, heading): TollGateBuilding on every second lane of both roads
+        for r in (road, neg_road(road)):
+            for idx, lane in enumerate(self.net.lanes(r)):
+                lane.speed_limit = self.SPEED_LIMIT
+                if idx % 2 == 1:
+                    self.buildings.append((lane, lane.position(lane.length / 2, 0), lane.heading_at(0)))
+        return ok
+
+
 # BLOCK_TYPE_DISTRIBUTION_V2 (component/algorithm/blocks_prob_dist.py:24-43), in its dict order
 BLOCK_DIST = [("Curve", Curve, 0.3), ("Straight", Straight, 0.1), ("InRampOnStraight", InRamp, 0.1),
               ("OutRampOnStraight", OutRamp, 0.1), ("StdInterSection", InterSection, 0.15),
               ("StdTInterSection", TInterSection, 0.15), ("Roundabout", Roundabout, 0.1), ("InFork", None, 0.0),
-              ("OutFork", None, 0.0), ("Merge", None, 0.0), ("Split", None, 0.0), ("ParkingLot", None, 0.0),
-              ("TollGate", None, 0.0), ("Bidirection", None, 0.0)]
+              ("OutFork", None, 0.0), ("Merge", Merge, 0.0), ("Split", Split, 0.0), ("ParkingLot", None, 0.0),
+              ("TollGate", TollGate, 0.0), ("Bidirection", Bidirection, 0.0)]
 BY_ID = {cls.ID: cls for _, cls, _ in BLOCK_DIST if cls is not None}
 MIN_LANES, MAX_LANES = 1, 5
 
@@ -1035,7 +1204,7 @@ class BIG:
 
     def _construct(self, b):
         ok = b.construct()
-        n = max(len(self.world.lanes(s.positive)) for s in b.sockets.values())
+        n = max(len(s.positive_lanes(self.world)) for s in b.sockets.values())
         if n < MIN_LANES or n > MAX_LANES:
             ok = False
         return ok
@@ -1104,9 +1273,33 @@ def build_fixed(kind, lane_num=2, lane_width=3.5, exit_length=60):
         blk.std = False
         blk.u_turn = lane_num > 1
         blk.construct()
+    elif kind in ("bottleneck", "bidirection", "tollgate"):
+        return _build_chain(big, kind, lane_num, exit_length)
     else:
         raise NotImplementedError("multi-agent map %r is not restated" % kind)
     big.blocks.append(blk)
+    return to_tables(big) + (big, )
+
+
+def _build_chain(big, kind, lane_num, exit_length, neck_lane_num=1, neck_length=20, toll_lane_num=8, toll_length=10):
+    """MABottleneckMap / MABidirectionMap / MATollGateMap (envs/marl_envs/marl_bottleneck.py:27-66,
+    marl_bidirection.py:27-77, marl_tollgate.py:103-150): fixed block chains, every block with seed 1"""
+    def add(cls, extra):
+        blk = cls(len(big.blocks), big.blocks[-1].get_socket(0), big.world, 1)
+        blk.construct(extra)
+        big.blocks.append(blk)
+    d = lane_num - neck_lane_num
+    if kind == "bottleneck":      # first block with bottle_lane_num lanes -> Merge -> Split
+        add(Merge, dict(lane_num=d, length=neck_length))
+        add(Split, dict(length=exit_length, lane_num=d))
+    elif kind == "bidirection":   # -> Merge -> Bidirection -> Split
+        add(Merge, dict(lane_num=d, length=3))
+        add(Bidirection, None)
+        add(Split, dict(length=exit_length, lane_num=d))
+    else:                         # tollgate: -> Split -> TollGate -> Merge, bottle length 35
+        add(Split, dict(length=2, lane_num=toll_lane_num - lane_num, bottle_len=35))
+        add(TollGate, dict(length=toll_length))
+        add(Merge, dict(lane_num=toll_lane_num - lane_num, length=exit_length, bottle_len=35))
     return to_tables(big) + (big, )
 
 

@@ -28,10 +28,23 @@ def export_multi_agent(args):
     from metadrive.manager.spawn_manager import SpawnManager
     if args.env == "ma_roundabout":
         from metadrive.envs.marl_envs.marl_inout_roundabout import MultiAgentRoundaboutEnv as cls
-    else:
+    elif args.env == "ma_intersection":
         from metadrive.envs.marl_envs.marl_intersection import MultiAgentIntersectionEnv as cls
+    elif args.env == "ma_bottleneck":
+        from metadrive.envs.marl_envs.marl_bottleneck import MultiAgentBottleneckEnv as cls
+    elif args.env == "ma_bidirection":
+        from metadrive.envs.marl_envs.marl_bidirection import MultiAgentBidirectionEnv as cls
+    elif args.env == "ma_tollgate":
+        from metadrive.envs.marl_envs.marl_tollgate import MultiAgentTollgateEnv as cls
+    else:
+        from metadrive.envs.marl_envs.marl_parking_lot import MultiAgentParkingLotEnv as cls
     env = cls(dict(log_level=50))
-    env.reset()
+    try:
+        env.reset()
+    except KeyError as e:
+        # MultiAgentBidirectionEnv.reward_function reads config["use_lateral"], a key no config defines
+        # (envs/marl_envs/marl_bidirection.py:113): the reference's env cannot finish reset(); its MAP is built by then
+        print("reset() of the reference raised", repr(e)[:60], "- exporting the map it built")
     m, mi = rx.export_map(env.current_map)
     roads = list(env.config["spawn_roads"])
     v = next(iter(env.agents.values()))
@@ -60,7 +73,8 @@ def export_multi_agent(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--env", default="metadrive", choices=["metadrive", "safe", "ma_roundabout", "ma_intersection"])
+    ap.add_argument("--env", default="metadrive", choices=["metadrive", "safe", "ma_roundabout", "ma_intersection", "ma_bottleneck", "ma_bidirection", "ma_tollgate",
+                             "ma_parkinglot"])
     ap.add_argument("--n", type=int, default=1000)
     ap.add_argument("--start", type=int, default=0)
     ap.add_argument("--density", type=float, default=None)

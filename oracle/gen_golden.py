@@ -223,6 +223,12 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         spawn_roads = list(env.config["spawn_roads"])
         road_nodes = np.array([[mi.nodes[r.start_node], mi.nodes[r.end_node]] for r in spawn_roads], np.int32)
         dest_nodes = np.array([mi.nodes[(-r).end_node] for r in spawn_roads], np.int32)
+        # envs without a destination draw (the default SpawnManager.update_destination_for, spawn_manager.py:224-228):
+        # auto_assign_task sends every agent to the far end of the map = one destination per spawn road
+        fixed_dest = type(eng.spawn_manager).update_destination_for is \
+            __import__("metadrive.manager.spawn_manager", fromlist=["SpawnManager"]).SpawnManager.update_destination_for
+        if fixed_dest:
+            dest_nodes = dest_nodes[::-1].reshape(-1, 1).copy()
         sm = eng.spawn_manager
         place_keys = list(sm.safe_spawn_places.keys())
         place_lane = [tuple(sm.safe_spawn_places[k]["config"]["spawn_lane_index"]) for k in place_keys]
@@ -287,7 +293,13 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
                 seat_name[j] = v.name
                 keys = first_query[0]
                 pk = place_keys[place_lane.index(tuple(v.config["spawn_lane_index"]))]
-                draws[t] = [keys.index(pk), int(np.nonzero(dest_nodes == mi.nodes[v.config["destination"]])[0][0]), len(keys)]
+                if fixed_dest:
+                    road = [tuple(r) for r in road_nodes.tolist()].index(
+                        (mi.nodes[v.config["spawn_lane_index"][0]], mi.nodes[v.config["spawn_lane_index"][1]]))
+                    assert mi.nodes[v.navigation.checkpoints[-1]] == dest_nodes[road, 0]
+                    draws[t] = [keys.index(pk), 0, len(keys)]
+                else:
+                    draws[t] = [keys.index(pk), int(np.nonzero(dest_nodes == mi.nodes[v.config["destination"]])[0][0]), len(keys)]
                 ck = v.navigation.checkpoints
                 routes_new[t, :len(ck)] = [mi.nodes[c] for c in ck]
                 newborn[t, j] = True
@@ -309,10 +321,15 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         obs = np.stack(obs).astype(np.float32)
         if obs_stride > 1:  # keep the fixture small: full observations for every obs_stride-th seat only
             keep = np.zeros(n_seats, bool); keep[::obs_stride] = True
-            obs[:, ~keep, 19:] = -1.0
+            obs[:, ~keep, od - int(env.config["vehicle_config"]["lidar"]["num_lasers"]):] = -1.0
         conf = {k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))}
         conf["n_lasers"] = int(env.config["vehicle_config"]["lidar"]["num_lasers"])
         conf["lidar_dist"] = float(env.config["vehicle_config"]["lidar"]["distance"])
+        conf["n_side_lasers"] = int(env.config["vehicle_config"]["side_detector"]["num_lasers"])
+        conf["side_dist"] = float(env.config["vehicle_config"]["side_detector"]["distance"])
+        conf["n_lane_lasers"] = int(env.config["vehicle_config"]["lane_line_detector"]["num_lasers"])
+        conf["lane_dist"] = float(env.config["vehicle_config"]["lane_line_detector"]["distance"])
+        conf["ignore_road_sign"] = int("cross_yellow_line_done" in env.config)
         out = dict(
             tag=tag, seed=int(env.current_seed), lane_num=env.config["map_config"]["lane_num"],
             map_lane_f=m["lane_f"], map_lane_i=m["lane_i"], map_road_i=m["road_i"], map_meta=m["meta"],
@@ -425,7 +442,7 @@ def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
 ALL_TAGS = ["cfg1_S_straight", "cfg1_S_random", "cfg1_S_discrete", "cfg2_pg3_seed3", "cfg2_pg3_seed7", "cfg2_pg3_seed11_dense",
             "cfg2_SCO_nolimit", "cfg2_pg3_seed11_others4", "cfg2_pg3_seed3_detectors", "cfg4_safe_seed2", "cfg4_safe_seed5",
             "cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg3_ma_roundabout", "cfg3_ma_roundabout_respawn",
-            "cfg3_ma_intersection_respawn", "cfg5_ped_X"]
+            "cfg3_ma_intersection_respawn", "cfg3_ma_bottleneck_respawn", "cfg5_ped_X"]
 
 
 def main():
@@ -531,6 +548,18 @@ def main():
         path = os.path.join(args.out, "cfg3_ma_intersection_respawn.npz")
         np.savez_compressed(path, **out)
         print("cfg3_ma_intersection_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
+              "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
+    # MultiAgentBottleneckEnv (envs/marl_envs/marl_bottleneck.py): Merge / Split blocks, agents born at both ends without a
+    # destination draw, 4-ray side / lane-line detectors in the observation, reward without the positive_road sign
+    if args.only == "cfg3_ma_bottleneck_respawn":
+        from metadrive.envs.marl_envs.marl_bottleneck import MultiAgentBottleneckEnv
+        lid = dict(vehicle_config=dict(lidar=dict(num_lasers=240, distance=50, num_others=0)))
+        cfgb = dict(num_agents=8, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, **lid)
+        out = run_episode_ma(MultiAgentBottleneckEnv, cfgb, None, "cfg3_ma_bottleneck_respawn", steps=300,
+                             noise=args.ma_noise, seed=9, obs_stride=3)
+        path = os.path.join(args.out, "cfg3_ma_bottleneck_respawn.npz")
+        np.savez_compressed(path, **out)
+        print("cfg3_ma_bottleneck_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
               "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     # BASELINE config 5 (composed): X map, respawn-mode IDM traffic, 16 crossing pedestrians; crashes do not end the
     # episode here so that the trace keeps running through pedestrian / vehicle contacts

@@ -57,7 +57,10 @@ def golden_world_ma(g, replicas=1, **cfg_kw):
     kw.update(horizon=int(conf.get("horizon", 1000)), delay_done=int(conf.get("delay_done", 25)),
               allow_respawn=int(bool(conf.get("allow_respawn", True))), n_lasers=int(conf["n_lasers"]),
               lidar_dist=float(conf["lidar_dist"]), ma_places=len(tables["places"]), ma_dests=tables["n_dests"],
-              ma_roads=tables["n_roads"], tape_len=len(tape) // replicas)
+              ma_roads=tables["n_roads"], tape_len=len(tape) // replicas,
+              n_side_lasers=int(conf.get("n_side_lasers", 0)), side_dist=float(conf.get("side_dist", 50.0)),
+              n_lane_lasers=int(conf.get("n_lane_lasers", 0)), lane_dist=float(conf.get("lane_dist", 20.0)),
+              ignore_road_sign=int(conf.get("ignore_road_sign", 0)))
     kw.update(cfg_kw)
     cfg = make_config(replicas, S, NA, 0, **kw)
     return arrays, cfg, geo

@@ -236,6 +236,29 @@ def test_ma_roundabout_respawn_and_horizon():
         env.close()
 
 
+def test_ma_bottleneck_env_surface():
+    """envs/marl_envs/marl_bottleneck.py: 20 agents born at both ends of the I -> Merge -> Split map, 4-ray side / lane-line
+    detectors in the observation (4 + 6 + 4 + 10 state floats), every agent routed to the far end (no destination draw),
+    respawn at both spawn roads; driving straight on ends on the merging lanes' solid lines or in a queue."""
+    from metadrive_ped_b200 import MultiAgentBottleneckEnv
+    env = MultiAgentBottleneckEnv({"horizon": 80})
+    try:
+        obs, info = env.reset()
+        assert len(obs) == 20 and obs["agent0"].shape == (24 + 72, ) and env.observation_space.contains(obs)
+        seen, r_sum = set(obs), 0.0
+        for step in range(160):
+            o, r, tm, tc, i = _ma_act(env, {k: [0.0, 0.6] for k in env.agents})
+            seen |= set(o)
+            r_sum += sum(r.values())
+            if not env.agents:
+                break
+        assert not env.agents and len(seen) > 20 and r_sum != 0.0
+        with pytest.raises(NotImplementedError):
+            MultiAgentBottleneckEnv({"cross_yellow_line_done": False}).reset()
+    finally:
+        env.close()
+
+
 def test_batched_multi_agent_env_autoreset():
     import torch
     from metadrive_ped_b200 import BatchedMultiAgentEnv

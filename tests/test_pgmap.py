@@ -156,9 +156,11 @@ def test_golden_fixtures_regenerate_identically(tag, tmp_path):
             np.testing.assert_array_equal(old[k], new[k], err_msg=k)
 
 
-@pytest.mark.parametrize("asset", ["ma_roundabout.npz", "ma_intersection.npz"])
+@pytest.mark.parametrize("asset", ["ma_roundabout.npz", "ma_intersection.npz", "ma_bottleneck.npz", "ma_tollgate.npz",
+                                   "ma_bidirection.npz"])
 def test_generated_multi_agent_maps_equal_the_exported_assets(asset):
-    """MARoundaboutMap / MAIntersectionMap (exit length 60, two lanes, U-turns on the intersection) and the spawn roads,
+    """MARoundaboutMap / MAIntersectionMap (exit length 60, two lanes, U-turns on the intersection), MABottleneckMap (I -> Merge
+    -> Split, 4 lanes into 1) and MATollGateMap (I -> Split -> TollGate -> Merge, 3 lanes into 8) and the spawn roads,
     destination nodes, slot constants and static_default vehicle of the multi-agent envs, generated vs exported."""
     from metadrive_ped_b200.ma import MultiAgentLibrary
     gen, ref = MultiAgentLibrary(asset), MultiAgentLibrary(asset, from_asset=True)
