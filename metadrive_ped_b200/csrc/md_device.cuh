@@ -627,13 +627,20 @@ __device__ __forceinline__ void latch_before_step(const float* S, float* C, int*
 }
 
 // ------------------------------------------------------------------------------------------------ map views
+// Grid records (built by the library at md_load_scene from the tables above, private to it): what a grid walk needs about
+// an item sits NEXT TO the item, indexed like lgrid_items / grid_items, so that a team of lanes fetches the records of all
+// its items in one round trip instead of chasing item id -> table row once per item.
+//   lrec[2k], lrec[2k+1] : lane id (int bits), hull AABB xmin ymin xmax | ymax, hull offset (int bits), hull points (int bits), lane type
+//   irec[2k], irec[2k+1] : the 8 floats of the line_f / quad_f row of grid item k
+struct MapAccel { const float4* lrec; const float4* irec; };
 struct MapView {
     const float* lane_f; const int* lane_i; const float* lane_bb; const int* road_i; const float* hull;
     const float* lines; const float* quads; const int* gs; const int* gi; const int* lgs; const int* lgi;
+    const float4* lrec; const float4* irec;
     int n_lanes, n_roads, n_lines, nx, ny;
     float gx0, gy0, cell;
 };
-__device__ __forceinline__ MapView map_view(const MdArrays& A, int map) {
+__device__ __forceinline__ MapView map_view(const MdArrays& A, int map, const MapAccel* X = nullptr) {
     const int* d = A.map_desc + (size_t)map * MAPD;
     const float* df = A.map_descf + (size_t)map * MAPDF;
     MapView m;
@@ -648,6 +655,8 @@ __device__ __forceinline__ MapView map_view(const MdArrays& A, int map) {
     m.gi = A.grid_items + d[MD_ITEM_OFF];
     m.lgs = A.lgrid_start + d[MD_LGRID_OFF];
     m.lgi = A.lgrid_items + d[MD_LITEM_OFF];
+    m.lrec = X != nullptr ? X->lrec + 2 * (size_t)d[MD_LITEM_OFF] : nullptr;
+    m.irec = X != nullptr ? X->irec + 2 * (size_t)d[MD_ITEM_OFF] : nullptr;
     m.n_lanes = d[MD_N_LANES]; m.n_roads = d[MD_N_ROADS]; m.n_lines = d[MD_N_LINES];
     m.nx = d[MD_GRID_NX]; m.ny = d[MD_GRID_NY];
     m.gx0 = df[0]; m.gy0 = df[1]; m.cell = df[2];

@@ -30,7 +30,7 @@
 #define PRE_REGS 64
 #endif
 #ifndef DYN_REGS
-#define DYN_REGS 96
+#define DYN_REGS 80
 #endif
 #ifndef POST_REGS
 #define POST_REGS 128
@@ -49,6 +49,27 @@
 
 // ray direction tables (cos, sin per laser) live in global memory, one set per handle: every lane reads a different entry
 // (constant memory would serialise that), and two handles with different laser counts must not share them
+
+// Debug builds only (make EXTRA=-DMD_PHASE_CLK, scripts/phase_clk.py): thread 0 of every CTA stamps clock64() at the phase
+// boundaries of the step kernels into a device table [kernel][CTA][16]; entry 15 is the globaltimer at CTA start.
+#ifdef MD_PHASE_CLK
+__device__ unsigned long long* g_phase_clk = nullptr;
+#define CLK_CTAS 4096
+__device__ __forceinline__ void clk_mark(int kern, int phase) {
+    if (g_phase_clk != nullptr && threadIdx.x == 0 && blockIdx.x < CLK_CTAS) {
+        unsigned long long* row = g_phase_clk + ((size_t)kern * CLK_CTAS + blockIdx.x) * 16;
+        row[phase] = (unsigned long long)clock64();
+        if (phase == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); row[15] = t;
+                          unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); row[14] = sm; }
+        if (phase >= 13) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); row[12] = t; }
+    }
+}
+extern "C" int md_debug_phase_clk(unsigned long long* dev_table) {
+    return cudaMemcpyToSymbol(g_phase_clk, &dev_table, sizeof(dev_table)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define clk_mark(kern, phase)
+#endif
 
 enum {
     MODE_AGENT_PRE = 1, MODE_TRIGGER = 2, MODE_IDM = 4, MODE_DYN = 8, MODE_CONTACTS = 16, MODE_POST = 32,
@@ -429,10 +450,9 @@ __device__ __forceinline__ void loc_scan_init(LocScan& s) {
 }
 // one candidate lane of the grid cell under the vehicle (ray_localization, utils/pg/utils.py:151-203, answered by AABB ->
 // point-in-convex-hull; lane choice of node_network_navigation.py:219-241)
-__device__ __forceinline__ void loc_candidate(const MapView& m, const LocCtx& c, int l, LocScan& s) {
+// ... after the AABB test: `hull_off` / `hull_n` = the lane's convex hull in m.hull
+__device__ __forceinline__ void loc_candidate_in_bb(const MapView& m, const LocCtx& c, int l, int hull_off, int hull_n, LocScan& s) {
     const float px = c.px, py = c.py;
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(m.lane_bb) + l);
-    if (px < bb.x || py < bb.y || px > bb.z || py > bb.w) return;
     const float* Ll = m.lane_f + l * LANE_F;
     if (Ll[LF_TYPE] != 0.0f) {  // hull_shortcut's radial rejection, before paying for the arc coordinates (atan2)
         const float ro = Ll[LF_P0 + 2] + 0.5f * Ll[LF_WIDTH];
@@ -443,8 +463,7 @@ __device__ __forceinline__ void loc_candidate(const MapView& m, const LocCtx& c,
     lane_local(Ll, px, py, lon, lat);
     const int sc = hull_shortcut(Ll, px, py, lon, lat);
     if (sc < 0) return;
-    if (sc == 0 &&
-        !point_in_hull(Ll, m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], px, py)) return;
+    if (sc == 0 && !point_in_hull(Ll, m.hull + 2 * hull_off, hull_n, px, py)) return;
     s.on_lane = 1;
     float lh = lane_heading_at(Ll, lon);
     float cosang = md_cosf(lh) * c.hx + md_sinf(lh) * c.hy;
@@ -456,6 +475,12 @@ __device__ __forceinline__ void loc_candidate(const MapView& m, const LocCtx& c,
     if (l >= c.cur_first && l < c.cur_first + c.cur_n && dist < s.d_cur) { s.d_cur = dist; s.best_cur = l; s.lon_cur = lon; s.lat_cur = lat; }
     if (c.next_road >= 0 && l >= c.nx_first && l < c.nx_first + c.nx_n && dist < s.d_next) { s.d_next = dist; s.best_next = l; s.lon_next = lon; s.lat_next = lat; }
 }
+__device__ __forceinline__ void loc_candidate(const MapView& m, const LocCtx& c, int l, LocScan& s) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(m.lane_bb) + l);
+    if (c.px < bb.x || c.py < bb.y || c.px > bb.z || c.py > bb.w) return;
+    loc_candidate_in_bb(m, c, l, m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], s);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ LocCtx loc_ctx(const MapView& m, const float* S, const int* I, const int* __restrict__ rroad) {
     LocCtx c;
     c.px = S[VS_POS]; c.py = S[VS_POS + 1];
@@ -918,20 +943,24 @@ __host__ __device__ inline size_t pre_base_bytes(int S, int O, int epb) {   // N
     size_t b = (sizeof(Nb) + 2 * sizeof(int)) * (size_t)S * epb + sizeof(float) * OBJ_F * (size_t)O * epb + 32;
     return (b + 15) & ~(size_t)15;
 }
+// the teams' tables are sized for 2-lane teams (threads / 2 of them): a CTA with more active vehicles than 4-lane teams
+// halves the team size instead of dropping to one thread per vehicle (which made that CTA the kernel's tail)
 __host__ __device__ inline int pre_team_size(int S, int O, int threads) {
-    return sizeof(float2) * (size_t)(S + O) * (threads / PRE_TEAM) <= PRE_TEAM_SCRATCH ? PRE_TEAM : 1;
+    return sizeof(float2) * (size_t)(S + O) * (threads / 2) <= PRE_TEAM_SCRATCH ? PRE_TEAM : 1;
 }
 __host__ __device__ inline size_t pre_smem_bytes(int S, int O, int epb, int threads) {
     const int T = pre_team_size(S, O, threads);
-    return pre_base_bytes(S, O, epb) + (T > 1 ? sizeof(float2) * (size_t)(S + O) * (threads / T) : 0);
+    return pre_base_bytes(S, O, epb) + (T > 1 ? sizeof(float2) * (size_t)(S + O) * (threads / 2) : 0);
 }
 __global__ void __maxnreg__(PRE_REGS)
 k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ actions, float* __restrict__ idm_out,
-      float4* __restrict__ veh_act, int use_teams, uint32_t* __restrict__ pass_ctr, uint32_t d_bank, uint32_t d_noise) {
+      float4* __restrict__ veh_act, int use_teams, uint32_t* __restrict__ pass_ctr, uint32_t d_bank, uint32_t d_noise,
+      unsigned int* __restrict__ work_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // the first kernel of a step advances the view's pass counters (scenario draws, observation passes); they live in
     // device memory so that a whole step is a fixed launch sequence (CUDA-graph replayable).  Nobody reads them in k_pre.
     if (pass_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { pass_ctr[0] += d_bank; pass_ctr[1] += d_noise; }
+    if (work_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *work_count = 0u;   // k_dyn's list of this step starts empty
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     const int n_rows = epb * S, env0 = blockIdx.x * epb;
     Nb* nb_all = reinterpret_cast<Nb*>(smem_raw);
@@ -939,6 +968,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
     int* list = reinterpret_cast<int*>(smem_raw + sizeof(Nb) * (size_t)n_rows + sizeof(float) * OBJ_F * (size_t)O * epb);
     int* n_list = list + n_rows;
     if (threadIdx.x == 0) *n_list = 0;
+    clk_mark(0, 0);
     __syncthreads();
     const float4 idle = make_float4(0.0f, 0.0f, 2.0f, 0.0f);  // what vehicle.reset() leaves (base_vehicle.py:376): brake 2
     // ---- phase 1
@@ -994,6 +1024,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         if (env < cfg.n_envs) obj_all[k] = A.obj_f[(size_t)env0 * O * OBJ_F + k];
     }
     __syncthreads();
+    clk_mark(0, 1);
     // ---- PGTrafficManager.before_step: trigger (manager/traffic_manager.py:74-88), one thread per env
     for (int le = threadIdx.x; le < epb; le += blockDim.x) {
         const int env = env0 + le;
@@ -1019,6 +1050,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         if (mode & MODE_AGENT_PRE) A.env_i[env * ENV_I + EI_STEP] += 1;
     }
     __syncthreads();
+    clk_mark(0, 2);
     // ---- phase 2: IDM decisions against the pre-step world (policy/idm_policy.py:235-267), one thread per active vehicle
     if (!(mode & (MODE_IDM | MODE_IDM_OUT))) return;
     // The listed vehicles that are active (triggered) are compacted once more, and a team of PRE_TEAM lanes runs each
@@ -1033,8 +1065,16 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         if (nb_all[list[j]].active) alist[atomicAdd(n_alist, 1)] = list[j];
     __syncthreads();
     const int n_act = *n_alist;
+    clk_mark(0, 3);
     // teams only while one round covers the CTA's active vehicles (each round is a full IDM chain) and the tables fit
-    const int T = (use_teams && n_act * PRE_TEAM <= (int)blockDim.x) ? pre_team_size(S, O, blockDim.x) : 1;
+    int T = use_teams ? pre_team_size(S, O, blockDim.x) : 1;
+    while (T > 1 && n_act * T > (int)blockDim.x) T >>= 1;
+#ifdef MD_PHASE_CLK
+    if (g_phase_clk != nullptr && threadIdx.x == 0 && blockIdx.x < CLK_CTAS) {
+        g_phase_clk[((size_t)0 * CLK_CTAS + blockIdx.x) * 16 + 10] = (unsigned long long)n_act;
+        g_phase_clk[((size_t)0 * CLK_CTAS + blockIdx.x) * 16 + 11] = (unsigned long long)T;
+    }
+#endif
     const int sub = threadIdx.x & (T - 1), team = threadIdx.x / T, n_teams = blockDim.x / T;
     const unsigned team_mask = T > 1 ? (((1u << T) - 1u) << ((threadIdx.x & 31) & ~(T - 1))) : 0u;
     float2* scratch = reinterpret_cast<float2*>(smem_raw + pre_base_bytes(S, O, epb)) + (size_t)team * (S + O);
@@ -1072,6 +1112,10 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         o4[0] = make_float4(D[0], D[1], D[2], D[3]);
         o4[1] = make_float4(D[4], D[5], D[6], D[7]);
     }
+#ifdef MD_PHASE_CLK
+    __syncthreads();
+    clk_mark(0, 13);
+#endif
 }
 
 // ---- k_dyn: engine.step = n_sub x doPhysics + contact-added callback (engine/base_engine.py:417-445) --------------
@@ -1111,211 +1155,257 @@ __device__ MD_RESP_INL void contact_response(const Nb* nb, const CBody* cd, cons
     }
 }
 
+// smem of k_dyn beyond step_smem_bytes: CBody rows | list | 4 counters | alive count per env | (16-aligned) contact words
+__host__ __device__ inline size_t dyn_list_bytes(int S, int epb) { return sizeof(int) * ((size_t)epb * S + 4 + epb); }
 __global__ void __maxnreg__(DYN_REGS)
 k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ veh_act, const float* __restrict__ ext_act3,
-      int n_sub, uint4* __restrict__ contact_tab) {
+      int n_sub, uint4* __restrict__ contact_tab, int* __restrict__ work_list, unsigned int* __restrict__ work_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // Two identities per thread.  H ("housekeeping", thread t <-> slot row t of the CTA's envs) sweeps the rows, stages and
-    // maintains the objects.  The vehicle identity comes from a compacted list of the alive vehicles, so that the warps
-    // that integrate are dense (a third to a half of the slot rows of a PG scene are empty or not alive).
-    const StepGeom H = step_geom(cfg, epb, smem_raw);
-    const int S = H.S, O = H.O;
+    // A CTA owns `epb` envs but runs only about as many threads as those envs hold ALIVE vehicles (a third to a half of the
+    // slot rows of a PG scene are empty or not alive, and idle threads would still pin 96 registers each): housekeeping -
+    // sweeping the slot rows, staging and maintaining the objects - strides over the rows, and every thread takes its
+    // vehicle from a compacted list of the alive ones.  The envs are handled in passes: a pass takes as many consecutive
+    // envs as have, together, at most blockDim.x alive vehicles (normally all of them: one pass; the host sizes the CTA from
+    // the scene's alive counts).  Contacts never cross envs, so the passes are independent.
+    const int S = cfg.slots_per_env, O = cfg.objs_per_env, ofs = (O + 3) & ~3;
+    const int W = blockDim.x, tid = threadIdx.x;
+    const int env0 = blockIdx.x * epb, n_env = min(epb, cfg.n_envs - env0), n_rows = n_env * S;
+    Nb* nb_all = reinterpret_cast<Nb*>(smem_raw);
+    float* obj_all = reinterpret_cast<float*>(smem_raw + sizeof(Nb) * (size_t)epb * S);
+    int* first_all = reinterpret_cast<int*>(smem_raw + sizeof(Nb) * (size_t)epb * S + sizeof(float) * OBJ_F * (size_t)O * epb);
     CBody* cd_all = reinterpret_cast<CBody*>(smem_raw + step_smem_bytes(S, O, epb));
     int* list = reinterpret_cast<int*>(smem_raw + step_smem_bytes(S, O, epb) + sizeof(CBody) * (size_t)epb * S);
     int* n_list = list + epb * S;
+    int* env_cnt = n_list + 4;
     // contact export (md_enable_contacts): two words per slot row in shared memory, ORed by the row's own vehicle thread
     unsigned long long* touch_all = reinterpret_cast<unsigned long long*>(
-        smem_raw + ((step_smem_bytes(S, O, epb) + sizeof(CBody) * (size_t)epb * S + sizeof(int) * ((size_t)epb * S + 4) + 15) & ~(size_t)15));
-    if (threadIdx.x == 0) { n_list[0] = 0; n_list[1] = 0; }
-    if (contact_tab != nullptr && H.work) { touch_all[2 * (H.le * S + H.slot)] = 0ull; touch_all[2 * (H.le * S + H.slot) + 1] = 0ull; }
+        smem_raw + ((step_smem_bytes(S, O, epb) + sizeof(CBody) * (size_t)epb * S + dyn_list_bytes(S, epb) + 15) & ~(size_t)15));
+    const bool contacts = (mode & MODE_CONTACTS) != 0;
+    clk_mark(1, 0);
+    for (int le = tid; le < epb; le += W) env_cnt[le] = 0;
     __syncthreads();
-    if (H.work) {
+    for (int row = tid; row < n_rows; row += W) {
+        const int le = row / S;
+        const int4 i0 = *reinterpret_cast<const int4*>(A.veh_i + ((size_t)env0 * S + row) * VEH_I);  // kind, alive, active, trigger
+        nb_all[row].alive = i0.y; nb_all[row].active = i0.z;
+        if (i0.y) atomicAdd(&env_cnt[le], 1);
+        if (contact_tab != nullptr) { touch_all[2 * row] = 0ull; touch_all[2 * row + 1] = 0ull; }
+    }
+    if (contacts)   // stage the object rows of the CTA's envs (contiguous in global memory)
+        for (int k = tid; k < n_env * O * OBJ_F; k += W) obj_all[k] = A.obj_f[(size_t)env0 * O * OBJ_F + k];
+    __syncthreads();
+    clk_mark(1, 1);
+    for (int le0 = 0; le0 < n_env;) {
+        int le1 = le0, n_pass = 0;
+        while (le1 < n_env && n_pass + env_cnt[le1] <= W) { n_pass += env_cnt[le1]; le1++; }
+        if (le1 == le0) le1 = le0 + 1;   // cannot happen (an env holds at most S <= blockDim.x vehicles); never spin
+        const int row0 = le0 * S, row1 = le1 * S;
+        if (tid == 0) { n_list[0] = 0; n_list[1] = 0; }
+        __syncthreads();
         // the list is filled from both ends: driven vehicles (agents, triggered traffic) from the front, parked ones (the
         // untriggered traffic of later blocks: brakes on, four wheels down - the majority in a PG scene) from the back, so
         // that a warp integrates vehicles on the same control-flow path
-        const int4 i0 = *reinterpret_cast<const int4*>(A.veh_i + (size_t)H.g * VEH_I);  // kind, alive, active, trigger
-        H.nb[H.slot].alive = i0.y;
-        if (i0.y) {
-            if (i0.z) list[atomicAdd(&n_list[0], 1)] = H.le * S + H.slot;
-            else list[epb * S - 1 - atomicAdd(&n_list[1], 1)] = H.le * S + H.slot;
-        }
-    }
-    __syncthreads();
-    StepGeom G = H;
-    const int n_front = n_list[0], n_back = n_list[1];
-    G.work = (int)threadIdx.x < n_front + n_back;
-    if (G.work) {
-        const int v = (int)threadIdx.x < n_front ? list[threadIdx.x] : list[epb * S - 1 - ((int)threadIdx.x - n_front)];
-        G.le = v / S; G.slot = v - G.le * S;
-        G.env = blockIdx.x * epb + G.le; G.g = G.env * S + G.slot;
-        G.nb = H.nb + ((ptrdiff_t)G.le - H.le) * S;
-        G.sobj = H.sobj + ((ptrdiff_t)G.le - H.le) * O * OBJ_F;
-        G.obj_first = H.obj_first + ((ptrdiff_t)G.le - H.le) * ((O + 3) & ~3);
-    }
-    const int slot = G.slot, g = G.g;
-    CBody* cd = cd_all + (size_t)G.le * S;
-    float P[VEH_P], St[VEH_S];
-    int alive = 0, is_static = 1, flags = 0;
-    Actuation act;
-    act.steer_rad = 0.0f; act.engine = 0.0f; act.brake = 2.0f;
-    if (G.work) {
-        const int* I = A.veh_i + (size_t)g * VEH_I;
-        alive = 1; is_static = I[VI_STATIC]; flags = I[VI_FLAGS];
-        load16(P, A.veh_p + (size_t)g * VEH_P);
-        load16(St, A.veh_s + (size_t)g * VEH_S);
-        if (mode & MODE_EXT_ACT) {
-            act.steer_rad = ext_act3[3 * (size_t)g]; act.engine = ext_act3[3 * (size_t)g + 1]; act.brake = ext_act3[3 * (size_t)g + 2];
-        } else {
-            float4 a = veh_act[g];
-            act.steer_rad = a.x; act.engine = a.y; act.brake = a.z;
-        }
-    }
-    const bool contacts = (mode & MODE_CONTACTS) != 0;
-    if (contacts) stage_objects(H, A.obj_f);
-    Body B;
-    B.pos = f3(St[VS_POS], St[VS_POS + 1], St[VS_POS + 2]);
-    B.q[0] = St[VS_QUAT]; B.q[1] = St[VS_QUAT + 1]; B.q[2] = St[VS_QUAT + 2]; B.q[3] = St[VS_QUAT + 3];
-    B.v = f3(St[VS_VEL], St[VS_VEL + 1], St[VS_VEL + 2]);
-    B.w = f3(St[VS_ANGVEL], St[VS_ANGVEL + 1], St[VS_ANGVEL + 2]);
-    const bool moves = G.work && alive && !is_static;
-    // Contact candidates of this step (the broad phase): bit k of (cand_lo, cand_hi) = body k (vehicle slot k < S, object
-    // k - S) can come within touching distance during the n_sub sub-steps: centre distance at the start of the step <=
-    // the two bounding radii + 1.5 x the distance both can travel + 0.5 m.  "Can travel" uses the speed of the env's
-    // fastest body for both sides: an inelastic contact impulse hands a hit body at most the speed of the one that hit
-    // it.  Every truly overlapping pair is a candidate (accelerations change a speed by < 1 m/s within a step), so the
-    // exact SAT below sees the same pairs as a full scan.
-    unsigned long long cand_lo = 0ull, cand_hi = 0ull;
-    int block_any = 0, block_obj = 0;
-    if (contacts) {
-        if (G.work && alive) {
-            const Rect r0 = vehicle_rect(P, St);
-            G.nb[slot].r = r0;
-            G.nb[slot].vx = sqrtf(r0.hu * r0.hu + r0.hv * r0.hv);                                  // bounding radius
-            G.nb[slot].vy = sqrtf(B.v.x * B.v.x + B.v.y * B.v.y + B.v.z * B.v.z);                  // speed
-        }
-        __syncthreads();
-        bool has_obj = false;
-        if (G.work && alive) {
-            const float T = 1.5f * cfg.dt * (float)n_sub;
-            const Rect r0 = G.nb[slot].r;
-            float vmax = 0.0f;
-#ifndef MD_CAND_OWN_SPEED
-            for (int k = 0; k < S; k++) if (G.nb[k].alive) vmax = fmaxf(vmax, G.nb[k].vy);
-            const float my_rad = G.nb[slot].vx + 0.5f, my_speed = vmax;
-#else
-            const float my_rad = G.nb[slot].vx + 0.5f, my_speed = G.nb[slot].vy;
-#endif
-            for (int k = 0; k < S; k++) {
-                if (k == slot || !G.nb[k].alive) continue;
-                const float dx = G.nb[k].r.cx - r0.cx, dy = G.nb[k].r.cy - r0.cy;
-#ifndef MD_CAND_OWN_SPEED
-                const float reach = my_rad + G.nb[k].vx + (my_speed + vmax) * T;
-#else
-                const float reach = my_rad + G.nb[k].vx + (my_speed + G.nb[k].vy) * T;
-#endif
-                if (dx * dx + dy * dy <= reach * reach) { if (k < 64) cand_lo |= 1ull << k; else cand_hi |= 1ull << (k - 64); }
+        for (int row = row0 + tid; row < row1; row += W)
+            if (nb_all[row].alive) {
+                if (nb_all[row].active) list[atomicAdd(&n_list[0], 1)] = row;
+                else list[epb * S - 1 - atomicAdd(&n_list[1], 1)] = row;
             }
-            for (int k = 0; k < O; k++) {
-                const float* Ob = G.sobj + k * OBJ_F;
-                if (Ob[OB_KIND] < 0.0f) continue;
-                const float orad = Ob[OB_KIND] == 2.0f ? sqrtf(Ob[OB_A] * Ob[OB_A] + Ob[OB_B] * Ob[OB_B]) : Ob[OB_A];
-                const float ospeed = Ob[OB_KIND] == 3.0f ? sqrtf(Ob[OB_VX] * Ob[OB_VX] + Ob[OB_VY] * Ob[OB_VY]) : 0.0f;
-                const float dx = Ob[OB_X] - r0.cx, dy = Ob[OB_Y] - r0.cy;
-                const float reach = my_rad + orad + (my_speed + ospeed) * T;
-                if (dx * dx + dy * dy <= reach * reach) {
-                    const int b = S + k;
-                    if (b < 64) cand_lo |= 1ull << b; else cand_hi |= 1ull << (b - 64);
-                    has_obj = true;
+        __syncthreads();
+        const int n_front = n_list[0], n_back = n_list[1];
+        const bool work = tid < n_front + n_back;
+        int le = le0, slot = 0;
+        if (work) {
+            const int v = tid < n_front ? list[tid] : list[epb * S - 1 - (tid - n_front)];
+            le = v / S; slot = v - le * S;
+        }
+        const int g = (env0 + le) * S + slot;
+        Nb* nb = nb_all + (size_t)le * S;
+        float* sobj = obj_all + (size_t)le * O * OBJ_F;
+        int* obj_first = first_all + (size_t)le * ofs;
+        CBody* cd = cd_all + (size_t)le * S;
+        clk_mark(1, 2);
+        float P[VEH_P], St[VEH_S];
+        int is_static = 1, flags = 0;
+        Actuation act;
+        act.steer_rad = 0.0f; act.engine = 0.0f; act.brake = 2.0f;
+        if (work) {
+            const int* I = A.veh_i + (size_t)g * VEH_I;
+            is_static = I[VI_STATIC]; flags = I[VI_FLAGS];
+            load16(P, A.veh_p + (size_t)g * VEH_P);
+            load16(St, A.veh_s + (size_t)g * VEH_S);
+            if (mode & MODE_EXT_ACT) {
+                act.steer_rad = ext_act3[3 * (size_t)g]; act.engine = ext_act3[3 * (size_t)g + 1]; act.brake = ext_act3[3 * (size_t)g + 2];
+            } else {
+                float4 a = veh_act[g];
+                act.steer_rad = a.x; act.engine = a.y; act.brake = a.z;
+            }
+        }
+        Body B;
+        B.pos = f3(St[VS_POS], St[VS_POS + 1], St[VS_POS + 2]);
+        B.q[0] = St[VS_QUAT]; B.q[1] = St[VS_QUAT + 1]; B.q[2] = St[VS_QUAT + 2]; B.q[3] = St[VS_QUAT + 3];
+        B.v = f3(St[VS_VEL], St[VS_VEL + 1], St[VS_VEL + 2]);
+        B.w = f3(St[VS_ANGVEL], St[VS_ANGVEL + 1], St[VS_ANGVEL + 2]);
+        const bool moves = work && !is_static;
+        // Contact candidates of this step (the broad phase): bit k of (cand_lo, cand_hi) = body k (vehicle slot k < S, object
+        // k - S) can come within touching distance during the n_sub sub-steps: centre distance at the start of the step <=
+        // the two bounding radii + 1.5 x the distance both can travel + 0.5 m.  "Can travel" uses the speed of the env's
+        // fastest body for both sides: an inelastic contact impulse hands a hit body at most the speed of the one that hit
+        // it.  Every truly overlapping pair is a candidate (accelerations change a speed by < 1 m/s within a step), so the
+        // exact SAT below sees the same pairs as a full scan.
+        unsigned long long cand_lo = 0ull, cand_hi = 0ull;
+        int block_any = 0, block_obj = 0;
+        if (contacts) {
+            if (work) {
+                const Rect r0 = vehicle_rect(P, St);
+                nb[slot].r = r0;
+                nb[slot].vx = sqrtf(r0.hu * r0.hu + r0.hv * r0.hv);                                  // bounding radius
+                nb[slot].vy = sqrtf(B.v.x * B.v.x + B.v.y * B.v.y + B.v.z * B.v.z);                  // speed
+            }
+            __syncthreads();
+            bool has_obj = false;
+            if (work) {
+                const float T = 1.5f * cfg.dt * (float)n_sub;
+                const Rect r0 = nb[slot].r;
+                float vmax = 0.0f;
+#ifndef MD_CAND_OWN_SPEED
+                for (int k = 0; k < S; k++) if (nb[k].alive) vmax = fmaxf(vmax, nb[k].vy);
+                const float my_rad = nb[slot].vx + 0.5f, my_speed = vmax;
+#else
+                const float my_rad = nb[slot].vx + 0.5f, my_speed = nb[slot].vy;
+#endif
+                for (int k = 0; k < S; k++) {
+                    if (k == slot || !nb[k].alive) continue;
+                    const float dx = nb[k].r.cx - r0.cx, dy = nb[k].r.cy - r0.cy;
+#ifndef MD_CAND_OWN_SPEED
+                    const float reach = my_rad + nb[k].vx + (my_speed + vmax) * T;
+#else
+                    const float reach = my_rad + nb[k].vx + (my_speed + nb[k].vy) * T;
+#endif
+                    if (dx * dx + dy * dy <= reach * reach) { if (k < 64) cand_lo |= 1ull << k; else cand_hi |= 1ull << (k - 64); }
+                }
+                for (int k = 0; k < O; k++) {
+                    const float* Ob = sobj + k * OBJ_F;
+                    if (Ob[OB_KIND] < 0.0f) continue;
+                    const float orad = Ob[OB_KIND] == 2.0f ? sqrtf(Ob[OB_A] * Ob[OB_A] + Ob[OB_B] * Ob[OB_B]) : Ob[OB_A];
+                    const float ospeed = Ob[OB_KIND] == 3.0f ? sqrtf(Ob[OB_VX] * Ob[OB_VX] + Ob[OB_VY] * Ob[OB_VY]) : 0.0f;
+                    const float dx = Ob[OB_X] - r0.cx, dy = Ob[OB_Y] - r0.cy;
+                    const float reach = my_rad + orad + (my_speed + ospeed) * T;
+                    if (dx * dx + dy * dy <= reach * reach) {
+                        const int b = S + k;
+                        if (b < 64) cand_lo |= 1ull << b; else cand_hi |= 1ull << (b - 64);
+                        has_obj = true;
+                    }
                 }
             }
+            block_any = __syncthreads_or((cand_lo | cand_hi) != 0ull);
+            block_obj = __syncthreads_or(has_obj);
         }
-        block_any = __syncthreads_or((cand_lo | cand_hi) != 0ull);
-        block_obj = __syncthreads_or(has_obj);
-    }
-    SteerCS scs;
-    scs.cs = md_cosf(act.steer_rad); scs.sn = md_sinf(act.steer_rad);
-    for (int rep = 0; rep < n_sub; rep++) {
-        if (moves) {
-            vehicle_substep(P, B, act, scs, cfg.dt);
-            St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y; St[VS_POS + 2] = B.pos.z;
-            St[VS_QUAT] = B.q[0]; St[VS_QUAT + 1] = B.q[1]; St[VS_QUAT + 2] = B.q[2]; St[VS_QUAT + 3] = B.q[3];
-        }
-        if (contacts && block_any) {  // a CTA without candidate pairs has no contact this step: no exchange, no barriers
-            __syncthreads();  // everyone finished reading the previous footprints
-            if (G.work) {  // snapshot of the post-move state: the contact flags and the response both read it
-                G.nb[slot].r = vehicle_rect(P, St);
-                CBody c;
-                c.ox = B.pos.x; c.oy = B.pos.y; c.vx = B.v.x; c.vy = B.v.y; c.w = B.w.z; c.pad = 0.0f;
-                c.im = moves ? 1.0f / P[VP_MASS] : 0.0f;
-                c.ii = moves ? 1.0f / (P[VP_MASS] / 12.0f * (P[VP_WIDTH] * P[VP_WIDTH] + P[VP_LENGTH] * P[VP_LENGTH])) : 0.0f;
-                cd[slot] = c;
+        clk_mark(1, 3);
+        SteerCS scs;
+        scs.cs = md_cosf(act.steer_rad); scs.sn = md_sinf(act.steer_rad);
+        const int ko0 = le0 * O, ko1 = le1 * O;   // the pass's object rows, and their (padded) COST_ONCE claim words
+        for (int rep = 0; rep < n_sub; rep++) {
+            if (moves) {
+                vehicle_substep(P, B, act, scs, cfg.dt);
+                St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y; St[VS_POS + 2] = B.pos.z;
+                St[VS_QUAT] = B.q[0]; St[VS_QUAT + 1] = B.q[1]; St[VS_QUAT + 2] = B.q[2]; St[VS_QUAT + 3] = B.q[3];
             }
-            if (H.work)
-                for (int k = H.slot; k < O; k += S) {  // kinematic movers (traffic_participants/pedestrian.py:67-95)
-                    H.obj_first[k] = 0x7fffffff;
-                    float* Ob = H.sobj + k * OBJ_F;
+            if (contacts && block_any) {  // a pass without candidate pairs has no contact this step: no exchange, no barriers
+                __syncthreads();  // everyone finished reading the previous footprints
+                if (work) {  // snapshot of the post-move state: the contact flags and the response both read it
+                    nb[slot].r = vehicle_rect(P, St);
+                    CBody c;
+                    c.ox = B.pos.x; c.oy = B.pos.y; c.vx = B.v.x; c.vy = B.v.y; c.w = B.w.z; c.pad = 0.0f;
+                    c.im = moves ? 1.0f / P[VP_MASS] : 0.0f;
+                    c.ii = moves ? 1.0f / (P[VP_MASS] / 12.0f * (P[VP_WIDTH] * P[VP_WIDTH] + P[VP_LENGTH] * P[VP_LENGTH])) : 0.0f;
+                    cd[slot] = c;
+                }
+                for (int k = ko0 + tid; k < ko1; k += W) {  // kinematic movers (traffic_participants/pedestrian.py:67-95)
+                    first_all[(k / O) * ofs + k % O] = 0x7fffffff;
+                    float* Ob = obj_all + (size_t)k * OBJ_F;
                     if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
                 }
-            __syncthreads();
-            if (cand_lo | cand_hi) {
-                const int f = contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, true, false,
-                                           contact_tab != nullptr ? touch_all + 2 * (G.le * S + slot) : nullptr);
-                flags |= f & ~FL_TOUCH;
+                __syncthreads();
+                if (cand_lo | cand_hi) {
+                    const int f = contact_pass(nb, sobj, S, slot, nb[slot].r, cand_lo, cand_hi, obj_first, true, false,
+                                               contact_tab != nullptr ? touch_all + 2 * (le * S + slot) : nullptr);
+                    flags |= f & ~FL_TOUCH;
 #ifndef MD_NO_RESPONSE
-                if (moves && (f & FL_TOUCH)) {  // something overlaps: push apart (registers only;
-                    float d[5];                                           // the snapshot stays as it is for the others)
-                    contact_response(G.nb, cd, G.sobj, S, slot, cand_lo, cand_hi, d);
-                    B.v.x += d[0]; B.v.y += d[1]; B.w.z += d[2];
-                    B.pos.x += d[3]; B.pos.y += d[4];
-                    St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y;
-                }
+                    if (moves && (f & FL_TOUCH)) {  // something overlaps: push apart (registers only;
+                        float d[5];                                           // the snapshot stays as it is for the others)
+                        contact_response(nb, cd, sobj, S, slot, cand_lo, cand_hi, d);
+                        B.v.x += d[0]; B.v.y += d[1]; B.w.z += d[2];
+                        B.pos.x += d[3]; B.pos.y += d[4];
+                        St[VS_POS] = B.pos.x; St[VS_POS + 1] = B.pos.y;
+                    }
 #endif
-            }
-            if (block_obj) {  // COST_ONCE needs the claims of every vehicle before anyone reads them
-                __syncthreads();
-                if (cand_lo | cand_hi)
-                    flags |= contact_pass(G.nb, G.sobj, S, slot, G.nb[slot].r, cand_lo, cand_hi, G.obj_first, false, true) & ~FL_TOUCH;
-                __syncthreads();
-                if (H.work)
-                    for (int k = H.slot; k < O; k += S)
-                        if (H.obj_first[k] != 0x7fffffff) H.sobj[k * OBJ_F + OB_CRASHED] = 1.0f;
-            }
-        } else if (contacts && H.work) {
-            for (int k = H.slot; k < O; k += S) {  // nobody looks: the pedestrians still walk, in the same increments
-                float* Ob = H.sobj + k * OBJ_F;
-                if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
+                }
+                if (block_obj) {  // COST_ONCE needs the claims of every vehicle before anyone reads them
+                    __syncthreads();
+                    if (cand_lo | cand_hi)
+                        flags |= contact_pass(nb, sobj, S, slot, nb[slot].r, cand_lo, cand_hi, obj_first, false, true) & ~FL_TOUCH;
+                    __syncthreads();
+                    for (int k = ko0 + tid; k < ko1; k += W)
+                        if (first_all[(k / O) * ofs + k % O] != 0x7fffffff) obj_all[(size_t)k * OBJ_F + OB_CRASHED] = 1.0f;
+                }
+            } else if (contacts) {
+                for (int k = ko0 + tid; k < ko1; k += W) {  // nobody looks: the pedestrians still walk, in the same increments
+                    float* Ob = obj_all + (size_t)k * OBJ_F;
+                    if (Ob[OB_KIND] == 3.0f) { Ob[OB_X] += Ob[OB_VX] * cfg.dt; Ob[OB_Y] += Ob[OB_VY] * cfg.dt; }
+                }
             }
         }
-    }
-    if (G.work && alive) {
-        if (moves) {
-            St[VS_VEL] = B.v.x; St[VS_VEL + 1] = B.v.y; St[VS_VEL + 2] = B.v.z;
-            St[VS_ANGVEL] = B.w.x; St[VS_ANGVEL + 1] = B.w.y; St[VS_ANGVEL + 2] = B.w.z;
-            store16(A.veh_s + (size_t)g * VEH_S, St);
+#ifdef MD_PHASE_CLK
+        __syncthreads();
+        clk_mark(1, 4);
+#endif
+        if (work) {
+            if (moves) {
+                St[VS_VEL] = B.v.x; St[VS_VEL + 1] = B.v.y; St[VS_VEL + 2] = B.v.z;
+                St[VS_ANGVEL] = B.w.x; St[VS_ANGVEL + 1] = B.w.y; St[VS_ANGVEL + 2] = B.w.z;
+                store16(A.veh_s + (size_t)g * VEH_S, St);
+            }
+            A.veh_i[(size_t)g * VEH_I + VI_FLAGS] = flags;
         }
-        A.veh_i[(size_t)g * VEH_I + VI_FLAGS] = flags;
+        if (work_list != nullptr) {
+            // the vehicles engine.after_step will have work for (alive and active), appended to the step's global work list:
+            // one atomic per warp.  k_scan runs a warp per entry; the order of the entries is irrelevant.
+            const bool emit = work && tid < n_front;
+            const unsigned em = __ballot_sync(0xffffffffu, emit);
+            if (em) {
+                const int lane = tid & 31, leader = __ffs(em) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(work_count, (unsigned)__popc(em));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (emit) work_list[base + __popc(em & ((1u << lane) - 1u))] = g;
+            }
+        }
+        le0 = le1;
+        if (le0 < n_env) __syncthreads();   // the next pass reuses the list and its counters
     }
     if (contact_tab != nullptr) {   // one 16-byte row per slot: the bodies touched during this step (zero for empty slots)
         __syncthreads();
-        if (H.work) {
-            const unsigned long long a = touch_all[2 * (H.le * S + H.slot)], b = touch_all[2 * (H.le * S + H.slot) + 1];
-            contact_tab[H.g] = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
+        for (int row = tid; row < n_rows; row += W) {
+            const unsigned long long a = touch_all[2 * row], b = touch_all[2 * row + 1];
+            contact_tab[(size_t)env0 * S + row] = make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
         }
     }
     if (contacts && O > 0) {
         __syncthreads();
-        if (H.work)
-            for (int k = H.slot; k < O; k += S) {  // pedestrians turn around at the ends of their crossing (peds.py)
-                float* Ob = H.sobj + k * OBJ_F;
-                if (Ob[OB_KIND] != 3.0f || Ob[OB_B] <= 0.0f) continue;
-                const float speed = sqrtf(Ob[OB_VX] * Ob[OB_VX] + Ob[OB_VY] * Ob[OB_VY]);
-                Ob[OB_HEADING] -= speed * (cfg.dt * (float)n_sub);
-                if (Ob[OB_HEADING] <= 0.0f) { Ob[OB_VX] = -Ob[OB_VX]; Ob[OB_VY] = -Ob[OB_VY]; Ob[OB_HEADING] += Ob[OB_B]; }
-            }
+        for (int k = tid; k < n_env * O; k += W) {  // pedestrians turn around at the ends of their crossing (peds.py)
+            float* Ob = obj_all + (size_t)k * OBJ_F;
+            if (Ob[OB_KIND] != 3.0f || Ob[OB_B] <= 0.0f) continue;
+            const float speed = sqrtf(Ob[OB_VX] * Ob[OB_VX] + Ob[OB_VY] * Ob[OB_VY]);
+            Ob[OB_HEADING] -= speed * (cfg.dt * (float)n_sub);
+            if (Ob[OB_HEADING] <= 0.0f) { Ob[OB_VX] = -Ob[OB_VX]; Ob[OB_VY] = -Ob[OB_VY]; Ob[OB_HEADING] += Ob[OB_B]; }
+        }
         __syncthreads();
-        if (H.work)
-            for (int k = H.slot; k < O * OBJ_F; k += S) A.obj_f[(size_t)H.env * O * OBJ_F + k] = H.sobj[k];
+        for (int k = tid; k < n_env * O * OBJ_F; k += W) A.obj_f[(size_t)env0 * O * OBJ_F + k] = obj_all[k];
     }
+#ifdef MD_PHASE_CLK
+    __syncthreads();
+    clk_mark(1, 13);
+#endif
 }
 
 // ---- env.reset state restore of one slot row (snapshot -> live arrays) -----------------------------------------
@@ -1546,12 +1636,152 @@ __device__ __forceinline__ void after_step_vehicle(const MapView& m, const float
     C[VC_ENERGY] += step_energy;
 }
 
+// ---- k_scan: the two table-walking scans of a vehicle's after_step - candidate lanes of update_localization, line /
+// sidewalk items of _state_check - with a WARP per vehicle of the step's work list (k_dyn appends the alive + active
+// vehicles).  A GPU holds only ~30 k such vehicles at BASELINE cfg2: as teams inside k_post's CTAs (128 registers per
+// thread, 4 CTAs per SM) they took two rounds of 4-lane teams, 50 of k_post's 100 us; here every vehicle gets 32 lanes at
+// once, the grid is balanced over the SMs whatever the envs hold, and the register budget is the scans' own.
+#define SCAN_WARPS 8
+// TS lanes per vehicle (a warp holds 32 / TS vehicles).  The loads are ordered so that the independent chains of a vehicle
+// overlap: (state, checkpoints, map id) -> (map tables' offsets, route roads) -> (cell ranges of BOTH scans, road rows) ->
+// (grid records of the candidates AND of the first items) -> lane rows of the surviving candidates.
+template <int TS>
+__global__ void __launch_bounds__(SCAN_WARPS * 32, 4)
+k_scan(MdConfig cfg, MdArrays A, MapAccel X, const int* __restrict__ work_list, const unsigned int* __restrict__ work_count,
+       LocScan* __restrict__ scan_tab) {
+    const int lane = threadIdx.x & 31, tl = threadIdx.x & (TS - 1), tbase = lane & ~(TS - 1), S = cfg.slots_per_env;
+    const unsigned tmask = TS == 32 ? 0xffffffffu : (((1u << TS) - 1u) << tbase);
+    clk_mark(3, 0);
+    const int n = (int)*work_count, n_teams = gridDim.x * (SCAN_WARPS * 32 / TS);
+    for (int j = (blockIdx.x * SCAN_WARPS * 32 + threadIdx.x) / TS; j < n; j += n_teams) {
+#ifdef MD_PHASE_CLK
+        const bool first = j < n_teams;
+#endif
+        const int g = __ldg(work_list + j), env = g / S;
+        const float* St = A.veh_s + (size_t)g * VEH_S;
+        float P4[4], Sv[VEH_S];
+        load16(Sv, St);
+        const float4 p0 = *reinterpret_cast<const float4*>(A.veh_p + (size_t)g * VEH_P);
+        P4[0] = p0.x; P4[1] = p0.y; P4[2] = p0.z; P4[3] = p0.w;  // type, length, width, height
+        const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP], &X);
+        const LocCtx c = loc_ctx(m, Sv, A.veh_i + (size_t)g * VEH_I, A.veh_rroad + (size_t)g * ROUTE_MAX);
+        const Rect r = vehicle_rect(P4, Sv);
+        // cell ranges: the lane grid cell under the centre, the static grid cells under the bounding circle (first four)
+        int k0, k1;
+        loc_cell(m, c.px, c.py, k0, k1);
+        const float rad = sqrtf(r.hu * r.hu + r.hv * r.hv);
+        int x0 = (int)floorf((r.cx - rad - m.gx0) / m.cell), x1 = (int)floorf((r.cx + rad - m.gx0) / m.cell);
+        int y0 = (int)floorf((r.cy - rad - m.gy0) / m.cell), y1 = (int)floorf((r.cy + rad - m.gy0) / m.cell);
+        x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, m.nx - 1); y1 = min(y1, m.ny - 1);
+        const int nxc = x1 - x0 + 1, nc = nxc > 0 && y1 >= y0 ? nxc * (y1 - y0 + 1) : 0;
+        int cs[4], cn[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            cs[q] = 0; cn[q] = 0;
+            if (q < nc) {
+                const int cell = (y0 + q / nxc) * m.nx + x0 + q % nxc;
+                cs[q] = __ldg(m.gs + cell); cn[q] = __ldg(m.gs + cell + 1) - cs[q];
+            }
+        }
+        LocScan sc;
+        loc_scan_init(sc);
+        int flags = 0;
+#ifdef MD_PHASE_CLK
+        if (first && cn[0] >= 0 && k1 >= 0) clk_mark(3, 1);
+#endif
+        // ---- candidate lanes (ascending; a survivor per lane)
+        for (int kb = k0; kb < k1; kb += TS) {
+            const int kk = kb + tl;
+            float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b = a;
+            bool in = false;
+            if (kk < k1) {
+                a = __ldg(m.lrec + 2 * kk); b = __ldg(m.lrec + 2 * kk + 1);
+                in = !(c.px < a.y || c.py < a.z || c.px > a.w || c.py > b.x);
+            }
+            const unsigned surv = (__ballot_sync(tmask, in) & tmask) >> tbase;
+            const int src = (int)__fns(surv, 0, tl + 1);          // team lane holding the (tl + 1)-th survivor, or -1
+            const int sl = src >= 0 && src < TS ? src : 0;
+            const int l = __float_as_int(__shfl_sync(tmask, a.x, sl, TS));
+            const int ho = __float_as_int(__shfl_sync(tmask, b.y, sl, TS)), hn = __float_as_int(__shfl_sync(tmask, b.z, sl, TS));
+            if (tl < __popc(surv)) loc_candidate_in_bb(m, c, l, ho, hn, sc);
+        }
+#ifdef MD_PHASE_CLK
+        if (first && sc.d_any >= 0.0f) clk_mark(3, 2);
+#endif
+        // ---- line / sidewalk items of the cells, four cells at a time, their item ranges concatenated
+        for (int cb = 0; cb < nc; cb += 4) {
+            if (cb > 0) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int ci = cb + q;
+                    cs[q] = 0; cn[q] = 0;
+                    if (ci < nc) {
+                        const int cell = (y0 + ci / nxc) * m.nx + x0 + ci % nxc;
+                        cs[q] = __ldg(m.gs + cell); cn[q] = __ldg(m.gs + cell + 1) - cs[q];
+                    }
+                }
+            }
+            const int p1 = cn[0], p2 = p1 + cn[1], p3 = p2 + cn[2], tot = p3 + cn[3];
+#pragma unroll 1
+            for (int i = tl; i < tot; i += TS) {
+                const int k = i < p1 ? cs[0] + i : (i < p2 ? cs[1] + (i - p1) : (i < p3 ? cs[2] + (i - p2) : cs[3] + (i - p3)));
+                const int it = __ldg(m.gi + k);
+                const float4 h = __ldg(m.irec + 2 * k), u = __ldg(m.irec + 2 * k + 1);
+                if (it < m.n_lines) {
+                    const int kind = (int)h.w;
+                    const int bit = kind == 0 ? FL_ON_WHITE : (kind == 1 ? FL_ON_YELLOW : FL_ON_BROKEN);
+                    if (flags & bit) continue;
+                    const float dx = h.x - r.cx, dy = h.y - r.cy, rr = rad + h.z + LINE_HALF_W + 0.01f;
+                    if (dx * dx + dy * dy > rr * rr) continue;
+                    Rect lr;
+                    lr.cx = h.x; lr.cy = h.y; lr.ux = u.x; lr.uy = u.y; lr.hu = h.z; lr.hv = LINE_HALF_W;
+                    if (rect_rect(r, lr)) flags |= bit;
+                } else {
+                    if (flags & FL_CRASH_SIDEWALK) continue;
+                    float qd[8] = {h.x, h.y, h.z, h.w, u.x, u.y, u.z, u.w};
+                    if (rect_quad(r, qd)) flags |= FL_CRASH_SIDEWALK;
+                }
+            }
+        }
+        sc.static_flags = flags;
+#ifdef MD_PHASE_CLK
+        if (first && flags >= 0) clk_mark(3, 3);
+#endif
+#define TEAM_MIN(D, L, LON, LAT)                                                                         \
+        {                                                                                                \
+            const float od_ = __shfl_xor_sync(tmask, D, off, TS), olon_ = __shfl_xor_sync(tmask, LON, off, TS), \
+                        olat_ = __shfl_xor_sync(tmask, LAT, off, TS);                                    \
+            const int ol_ = __shfl_xor_sync(tmask, L, off, TS);                                          \
+            if (od_ < D || (od_ == D && ol_ >= 0 && (L < 0 || ol_ < L))) { D = od_; L = ol_; LON = olon_; LAT = olat_; } \
+        }
+#pragma unroll
+        for (int off = TS >> 1; off > 0; off >>= 1) {
+            TEAM_MIN(sc.d_any, sc.best_any, sc.lon_any, sc.lat_any)
+            TEAM_MIN(sc.d_cur, sc.best_cur, sc.lon_cur, sc.lat_cur)
+            TEAM_MIN(sc.d_next, sc.best_next, sc.lon_next, sc.lat_next)
+            sc.on_lane |= __shfl_xor_sync(tmask, sc.on_lane, off, TS);
+            sc.static_flags |= __shfl_xor_sync(tmask, sc.static_flags, off, TS);
+        }
+#undef TEAM_MIN
+        if (tl == 0) scan_tab[g] = sc;
+#ifdef MD_PHASE_CLK
+        if (first) clk_mark(3, 4);
+#endif
+    }
+#ifdef MD_PHASE_CLK
+    __syncthreads();
+    clk_mark(3, 13);
+#endif
+}
+
 __global__ void __maxnreg__(POST_REGS)
 k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restrict__ body_tab,
-       const uint8_t* __restrict__ env_mask, uint8_t* __restrict__ done_mask, Snapshot snap, int team_pref) {
+       const uint8_t* __restrict__ env_mask, uint8_t* __restrict__ done_mask, Snapshot snap, int team_pref, MapAccel X,
+       const LocScan* __restrict__ scan_tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     const int n_rows = epb * S, env0 = blockIdx.x * epb;
+    clk_mark(2, 0);
     if (mode & MODE_RESTORE) {
         // env.reset of the masked envs, part 1: snapshot -> live arrays (what k_restore does, fused in so that an
         // auto-reset costs one launch).  CTAs without a finished env leave at once.
@@ -1574,6 +1804,7 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
     for (int le = threadIdx.x; le < epb; le += blockDim.x)
         ctr_base[le] = env0 + le < cfg.n_envs ? A.env_i[(env0 + le) * ENV_I + EI_RNG] : 0;
     __syncthreads();
+    clk_mark(2, 1);
     // ---- phase 1: footprints + work list (row v = env_local * S + slot, the order of the global rows)
     for (int v = threadIdx.x; v < n_rows; v += blockDim.x) {
         const int le = v / S, slot = v - le * S, env = env0 + le;
@@ -1605,6 +1836,7 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         if (env < cfg.n_envs) obj_all[k] = A.obj_f[(size_t)env0 * O * OBJ_F + k];
     }
     __syncthreads();
+    clk_mark(2, 2);
     // ---- phase 2a: the three scans of a vehicle's after_step that walk tables - candidate lanes of update_localization,
     // line / sidewalk items of _state_check, the env's bodies for the post-step contacts - spread over a team of 2 - 4
     // lanes per vehicle.  A GPU holds only ~200 active vehicles per SM at BASELINE cfg2: one thread per vehicle leaves 6
@@ -1624,17 +1856,28 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         for (int j = team; j < n_work; j += n_teams) {
             const int v = list[j], le = v / S, slot = v - le * S, env = env0 + le;
             const size_t g = (size_t)env * S + slot;
-            const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+            if (scan_tab != nullptr) {
+                // k_scan already ran the candidate and static scans of this vehicle: the team adds the post-step contacts
+                int cf = fp_contacts_team(fp_all + (size_t)le * S, obj_all + (size_t)le * O * OBJ_F, S, O, slot, fp_all[v].r, sub, T);
+                for (int off = T >> 1; off > 0; off >>= 1) cf |= __shfl_xor_sync(team_mask, cf, off);
+                if (sub == 0) { LocScan sc = scan_tab[g]; sc.contact_flags = cf; scan[j] = sc; }
+                continue;
+            }
+            const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP], &X);
             const LocCtx c = loc_ctx(m, A.veh_s + g * VEH_S, A.veh_i + g * VEH_I, A.veh_rroad + g * ROUTE_MAX);
             LocScan sc;
             loc_scan_init(sc);
             int k0, k1;
             loc_cell(m, c.px, c.py, k0, k1);
+            if (j == team) clk_mark(2, 4);
             for (int kk = k0 + sub; kk < k1; kk += T) loc_candidate(m, c, m.lgi[kk], sc);
+            if (j == team) clk_mark(2, 5);
             const Rect r = fp_all[v].r;
             sc.static_flags = state_check_static_team(m, r, sub, T);
+            if (j == team) clk_mark(2, 6);
             sc.contact_flags = fp_contacts_team(fp_all + (size_t)le * S, obj_all + (size_t)le * O * OBJ_F, S, O, slot, r, sub, T);
             __syncwarp(team_mask);
+            if (j == team) clk_mark(2, 7);
 #define TEAM_MIN(D, L, LON, LAT)                                                                         \
             {                                                                                            \
                 const float od_ = __shfl_xor_sync(team_mask, D, off), olon_ = __shfl_xor_sync(team_mask, LON, off), \
@@ -1655,6 +1898,7 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         }
     }
     __syncthreads();
+    clk_mark(2, 3);
     // ---- phase 2: one thread per vehicle with work
     for (int j = threadIdx.x; j < n_work; j += blockDim.x) {
         const int v = list[j], le = v / S, slot = v - le * S, env = env0 + le;
@@ -1712,6 +1956,10 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         write_body_row(body_tab + g * BODY_ROW, P, St, alive_row);
     }
     // ---- phase 3: respawn / hybrid traffic (manager/traffic_manager.py:112-121)
+#ifdef MD_PHASE_CLK
+    __syncthreads();
+    clk_mark(2, 13);
+#endif
     if (!((mode & MODE_REMOVE) && cfg.traffic_mode != 0)) return;
     __syncthreads();
     for (int j = threadIdx.x; j < n_work; j += blockDim.x) {
@@ -2356,6 +2604,9 @@ struct View {
     uint8_t* mask;
     int* lidar_list;             // multi-agent lidar passes: the observing seats, compacted (k_lidar_list)
     unsigned int* lidar_count;
+    int* work_list;              // the step's work list: slot rows (view-relative) of the alive + active vehicles (k_dyn -> k_scan)
+    unsigned int* work_count;
+    LocScan* scan_tab;           // k_scan's result per slot row (read by k_post)
     uint32_t* pass;              // device: [0] scenario-draw passes so far (the counter of the draw hash (seed, env, pass)),
                                  // [1] observation passes so far (the counter of the lidar noise hash)
 };
@@ -2416,6 +2667,9 @@ struct md_sim {
     std::vector<HostGroup> groups;
     int compact;            // multi-agent: only valid observation rows travel to the host
     int64_t launches;
+    int* work_list; unsigned int* work_count; LocScan* scan_tab;   // k_dyn -> k_scan -> k_post (see View)
+    MapAccel accel;         // grid records derived from the map tables at md_load_scene
+    float dyn_alive;        // the scene's alive vehicles per env: sizes k_dyn's CTAs (0 = one thread per slot row)
     md_sim* bank;           // scenario bank (md_attach_bank): finished envs restart as a scenario drawn from it
     uint32_t bank_seed;
     bool bank_ever;         // a bank was attached at some point: envs may hold drawn scenarios, restores must be `full`
@@ -2496,6 +2750,9 @@ static View make_view(const md_sim* sim, int env0, int n, int count_slot) {
     v.lidar_list = sim->lidar_list ? sim->lidar_list + na0 : nullptr;
     v.lidar_count = sim->lidar_count ? sim->lidar_count + count_slot : nullptr;
     v.pass = sim->d_pass + 2 * count_slot;
+    v.work_list = sim->work_list + nv0;
+    v.work_count = sim->work_count + count_slot;
+    v.scan_tab = sim->scan_tab + nv0;
     return v;
 }
 
@@ -2580,6 +2837,8 @@ extern "C" void md_destroy(md_sim* sim) {
         for (int i = 0; i < N_SNAP; i++) { cudaFree(sim->snap_bufs[i]); cudaFree(sim->post_bufs[i]); }
         cudaFree(sim->post_body); cudaFree(sim->post_obs);
         cudaFree(sim->body_tab); cudaFree(sim->veh_act); cudaFree(sim->mask);
+        cudaFree((void*)sim->accel.lrec); cudaFree((void*)sim->accel.irec);
+        cudaFree(sim->work_list); cudaFree(sim->work_count); cudaFree(sim->scan_tab);
         cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_mask);
         cudaFree(sim->d_actions); cudaFree(sim->d_obs); cudaFree(sim->d_mask_in);
     }
@@ -2599,6 +2858,39 @@ extern "C" int md_snapshot(md_sim* sim) {
 }
 
 extern "C" int md_host_groups(md_sim* sim, int n_groups);
+
+// grid records (MapAccel, md_device.cuh): one 32-byte record per lgrid_items / grid_items entry, same indexing
+static int build_accel(md_sim* sim, const MdArrays* host) {
+    const int64_t M = sim->rows[0], n_l = sim->rows[22], n_i = sim->rows[10];
+    std::vector<float> lrec((size_t)(n_l ? n_l : 1) * 8, 0.0f), irec((size_t)(n_i ? n_i : 1) * 8, 0.0f);
+    auto bits = [](int v) { float f; memcpy(&f, &v, 4); return f; };
+    for (int64_t mp = 0; mp < M; mp++) {
+        const int* d = host->map_desc + mp * MAPD;
+        const int cells = d[MD_GRID_NX] * d[MD_GRID_NY];
+        const int nl = host->lgrid_start[d[MD_LGRID_OFF] + cells], ni = host->grid_start[d[MD_GRID_OFF] + cells];
+        for (int k = 0; k < nl; k++) {
+            const int l = host->lgrid_items[d[MD_LITEM_OFF] + k];
+            const float* bb = host->lane_bb + (size_t)(d[MD_LANE_OFF] + l) * 4;
+            const int* li = host->lane_i + (size_t)(d[MD_LANE_OFF] + l) * LANE_I;
+            float* o = lrec.data() + (size_t)(d[MD_LITEM_OFF] + k) * 8;
+            o[0] = bits(l); o[1] = bb[0]; o[2] = bb[1]; o[3] = bb[2]; o[4] = bb[3];
+            o[5] = bits(li[LI_HULL_OFF]); o[6] = bits(li[LI_HULL_N]);
+            o[7] = host->lane_f[(size_t)(d[MD_LANE_OFF] + l) * LANE_F + LF_TYPE];
+        }
+        for (int k = 0; k < ni; k++) {
+            const int it = host->grid_items[d[MD_ITEM_OFF] + k];
+            const float* src = it < d[MD_N_LINES] ? host->line_f + (size_t)(d[MD_LINE_OFF] + it) * LINE_F
+                                                  : host->quad_f + (size_t)(d[MD_QUAD_OFF] + it - d[MD_N_LINES]) * QUAD_F;
+            memcpy(irec.data() + (size_t)(d[MD_ITEM_OFF] + k) * 8, src, 32);
+        }
+    }
+    void *dl = nullptr, *di = nullptr;
+    CK(cudaMalloc(&dl, lrec.size() * 4)); CK(cudaMalloc(&di, irec.size() * 4));
+    CK(cudaMemcpy(dl, lrec.data(), lrec.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(di, irec.data(), irec.size() * 4, cudaMemcpyHostToDevice));
+    sim->accel.lrec = (const float4*)dl; sim->accel.irec = (const float4*)di;
+    return 0;
+}
 
 extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* rows) {
     if (!sim || !host || !rows) return -2;
@@ -2635,12 +2927,24 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
         CK(cudaMalloc(&sim->lidar_count, sizeof(unsigned int) * (1 + MAX_HOST_GROUPS)));
         CK(cudaMemset(sim->lidar_count, 0, sizeof(unsigned int) * (1 + MAX_HOST_GROUPS)));
     }
+    CK(cudaMalloc(&sim->work_list, sizeof(int) * (size_t)NV));
+    CK(cudaMalloc(&sim->work_count, sizeof(unsigned int) * (1 + MAX_HOST_GROUPS)));
+    CK(cudaMemset(sim->work_count, 0, sizeof(unsigned int) * (1 + MAX_HOST_GROUPS)));
+    CK(cudaMalloc(&sim->scan_tab, sizeof(LocScan) * (size_t)NV));
     CK(cudaMalloc(&sim->d_pass, sizeof(uint32_t) * 2 * (1 + MAX_HOST_GROUPS)));
     CK(cudaMemset(sim->d_pass, 0, sizeof(uint32_t) * 2 * (1 + MAX_HOST_GROUPS)));
     CK(cudaMallocHost(&sim->h_actions, NA * 2 * 4)); CK(cudaMallocHost(&sim->h_obs, NA * od * 4));
     CK(cudaMallocHost(&sim->h_mask, (size_t)c.n_envs));
     CK(cudaMalloc(&sim->d_actions, NA * 2 * 4)); CK(cudaMalloc(&sim->d_obs, NA * od * 4));
     CK(cudaMalloc(&sim->d_mask_in, (size_t)c.n_envs));
+    if (build_accel(sim, host)) return -1;
+    {   // k_dyn runs about as many threads per CTA as its envs hold alive vehicles: 1.25 x the scene's mean (envs with more
+        // take a second pass inside the kernel)
+        const int* hi = host->veh_i;
+        double alive = 0.0;
+        for (int64_t g = 0; g < NV; g++) alive += hi[g * VEH_I + VI_ALIVE] != 0;
+        sim->dyn_alive = (float)(alive / (double)c.n_envs);
+    }
     sim->loaded = true;
     sim->all = make_view(sim, 0, c.n_envs, 0);
     if (opt_in_smem(sim)) return -4;
@@ -2698,9 +3002,18 @@ static StepLaunch step_launch(const MdConfig& c, int epb_pref) {
 static int epb_pre() { static int v = env_int("MD_EPB_PRE", PRE_EPB); return v; }
 static int epb_post() { static int v = env_int("MD_EPB_POST", POST_EPB); return v; }
 static int epb_dyn() { static int v = env_int("MD_EPB_DYN", DYN_EPB); return v; }
-static StepLaunch dyn_launch(const MdConfig& c) {  // k_dyn appends the compacted list of alive vehicles to the shared tables
+// k_dyn appends the compacted list of alive vehicles to the shared tables and runs `threads_pref` threads per CTA: about as
+// many as its envs hold alive vehicles (md_load_scene sizes it from the scene; MD_DYN_THREADS overrides; 0 = one per slot row)
+static StepLaunch dyn_launch(const MdConfig& c, float alive_per_env) {
     StepLaunch L = step_launch(c, epb_dyn());
-    L.smem += sizeof(CBody) * (size_t)L.epb * c.slots_per_env + sizeof(int) * ((size_t)L.epb * c.slots_per_env + 4);
+    static const int forced = env_int("MD_DYN_THREADS", -1);
+    int t = forced >= 0 ? forced : (int)(1.25f * alive_per_env * (float)L.epb + 0.999f);
+    if (t > 0) {
+        if (t < c.slots_per_env) t = c.slots_per_env;   // a pass holds at least one whole env
+        t = (t + 31) & ~31;
+        if (t < L.threads) L.threads = t;
+    }
+    L.smem += sizeof(CBody) * (size_t)L.epb * c.slots_per_env + dyn_list_bytes(c.slots_per_env, L.epb);
     L.smem = ((L.smem + 15) & ~(size_t)15) + 16 * (size_t)L.epb * c.slots_per_env;   // contact export words
     return L;
 }
@@ -2729,10 +3042,33 @@ template <typename K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+// The step kernels are occupancy-bound by registers, with 10 - 40 KB of shared memory per CTA: ask for the shared-memory
+// carve-out that lets the register-limited number of CTAs be resident (the driver's default split left k_dyn at 6 CTAs per
+// SM where the registers allow 7, i.e. a second wave for 13 % of the CTAs).  MD_DEBUG_OCC=1 prints the resulting occupancy.
+template <typename K>
+static cudaError_t prefer_carveout(K kernel, const char* name, const StepLaunch& L, int regs) {
+    const int threads = (L.threads + 31) & ~31;
+    int target = 65536 / (threads * regs);
+    if (target > 2048 / threads) target = 2048 / threads;
+    if (target > 32) target = 32;
+    if (target < 1) target = 1;
+    const size_t need = (size_t)target * (L.smem + 1024);
+    int pct = (int)((100 * need + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    static const int dbg = env_int("MD_DEBUG_OCC", 0);
+    if (dbg && e == cudaSuccess) {
+        int n = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, L.threads, L.smem);
+        fprintf(stderr, "[mdstep] %s: %d blocks x %d threads, %zu B smem, carve-out %d %% -> %d CTAs / SM (register target %d)\n",
+                name, L.blocks, L.threads, L.smem, pct, n, target);
+    }
+    return e;
+}
 // dynamic shared memory above the 48 KB default needs an opt-in per kernel
 static int opt_in_smem(md_sim* sim) {
     const size_t floor48 = 48 * 1024;
-    StepLaunch D = dyn_launch(sim->cfg), A = pre_launch(sim->cfg), B = post_launch(sim->cfg);
+    StepLaunch D = dyn_launch(sim->cfg, sim->dyn_alive), A = pre_launch(sim->cfg), B = post_launch(sim->cfg);
     if (A.smem > 200 * 1024 || B.smem > 200 * 1024 || D.smem > 200 * 1024) {
         sim->err = "slots/objects per env need more than 200 KB of shared memory per CTA";
         return -4;
@@ -2740,6 +3076,9 @@ static int opt_in_smem(md_sim* sim) {
     CK(allow_smem(k_dyn, D.smem > floor48 ? D.smem : floor48));
     CK(allow_smem(k_pre, A.smem > floor48 ? A.smem : floor48));
     CK(allow_smem(k_post, B.smem > floor48 ? B.smem : floor48));
+    CK(prefer_carveout(k_dyn, "k_dyn", D, DYN_REGS));
+    CK(prefer_carveout(k_pre, "k_pre", A, PRE_REGS));
+    CK(prefer_carveout(k_post, "k_post", B, POST_REGS));
     size_t lb = lidar_smem_per_warp(sim->cfg.slots_per_env, sim->cfg.objs_per_env, sim->cfg.n_lasers) * LIDAR_WARPS;
     if (lb > floor48) CK(allow_smem(k_lidar, lb));
     return 0;
@@ -2750,23 +3089,26 @@ static int launch_pre(md_sim* sim, const View& v, int mode, const float* actions
     StepLaunch L = pre_launch(v.cfg);
     static const int use_teams = env_int("MD_PRE_TEAM", 1);
     k_pre<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, actions, idm_out, v.veh_act, use_teams,
-                                               (d_bank | d_noise) ? v.pass : nullptr, d_bank, d_noise);
+                                               (d_bank | d_noise) ? v.pass : nullptr, d_bank, d_noise,
+                                               (mode & MODE_AGENT_PRE) ? v.work_count : nullptr);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_dyn(md_sim* sim, const View& v, int mode, const float* ext_act3, int n_sub, cudaStream_t st) {
-    StepLaunch L = dyn_launch(v.cfg);
+static int launch_dyn(md_sim* sim, const View& v, int mode, const float* ext_act3, int n_sub, cudaStream_t st, bool emit_list = false) {
+    StepLaunch L = dyn_launch(v.cfg, sim->dyn_alive);
     k_dyn<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, v.veh_act, ext_act3, n_sub,
-                                               (mode & MODE_CONTACTS) ? v.contact_tab : nullptr);
+                                               (mode & MODE_CONTACTS) ? v.contact_tab : nullptr,
+                                               emit_list ? v.work_list : nullptr, v.work_count);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_post(md_sim* sim, const View& v, int mode, StepOut out, const uint8_t* mask, cudaStream_t st) {
+static int launch_post(md_sim* sim, const View& v, int mode, StepOut out, const uint8_t* mask, cudaStream_t st, bool scanned = false) {
     StepLaunch L = post_launch(v.cfg);
     static const int team_pref = env_int("MD_POST_TEAM", 0);   // 0 = adaptive, 1 = off, 2 / 4 / 8 / 16 / 32 lanes per vehicle
-    k_post<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, out, v.body_tab, mask, v.mask, v.snap, team_pref);
+    k_post<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, out, v.body_tab, mask, v.mask, v.snap, team_pref, sim->accel,
+                                                scanned ? v.scan_tab : nullptr);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -2873,9 +3215,20 @@ static int step_impl(md_sim* sim, View& v, const float* actions_dev, StepOut out
     const uint32_t d_bank = (fused_reset && sim->post_valid && sim->bank) ? 1u : 0u;
     if (launch_pre(sim, v, MODE_AGENT_PRE | MODE_TRIGGER | MODE_IDM, actions_dev, nullptr, st, d_bank, 2u)) return -1;
     if (prof) CK(cudaEventRecord(ev[1], st));
-    if (launch_dyn(sim, v, MODE_DYN | MODE_CONTACTS, nullptr, v.cfg.decision_repeat, st)) return -1;
+    static const int use_scan = env_int("MD_SCAN", 1);   // 0: the scans run as teams inside k_post (tuning / fallback)
+    if (launch_dyn(sim, v, MODE_DYN | MODE_CONTACTS, nullptr, v.cfg.decision_repeat, st, use_scan != 0)) return -1;
     if (prof) CK(cudaEventRecord(ev[2], st));
-    if (launch_post(sim, v, MODE_POST | MODE_OUT | MODE_REMOVE | (fused_reset ? MODE_MARK_DONE : 0), out, nullptr, st)) return -1;
+    if (use_scan) {
+        // a persistent grid: 4 CTAs of 8 warps per SM are resident at 64 registers per thread, and each team strides over
+        // the list.  MD_SCAN_TEAM = 8 / 16 / 32 lanes per vehicle (measured), MD_SCAN_CTAS overrides the grid.
+        static const int scan_ctas = env_int("MD_SCAN_CTAS", 148 * 4), scan_team = env_int("MD_SCAN_TEAM", 8);
+        if (scan_team == 32) k_scan<32><<<scan_ctas, SCAN_WARPS * 32, 0, st>>>(v.cfg, v.dev, sim->accel, v.work_list, v.work_count, v.scan_tab);
+        else if (scan_team == 16) k_scan<16><<<scan_ctas, SCAN_WARPS * 32, 0, st>>>(v.cfg, v.dev, sim->accel, v.work_list, v.work_count, v.scan_tab);
+        else k_scan<8><<<scan_ctas, SCAN_WARPS * 32, 0, st>>>(v.cfg, v.dev, sim->accel, v.work_list, v.work_count, v.scan_tab);
+        sim->launches++;
+        CK(cudaGetLastError());
+    }
+    if (launch_post(sim, v, MODE_POST | MODE_OUT | MODE_REMOVE | (fused_reset ? MODE_MARK_DONE : 0), out, nullptr, st, use_scan != 0)) return -1;
     if (prof) CK(cudaEventRecord(ev[3], st));
     if (fused_reset && sim->post_valid && sim->bank) {
         if (launch_restore_bank(sim, v, out.obs, v.mask, st)) return -1;
