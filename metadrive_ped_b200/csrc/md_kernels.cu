@@ -23,6 +23,27 @@
 #include "../../include/mdstep.h"
 #include "md_device.cuh"
 
+// Debug builds only (make EXTRA=-DMD_PHASE_CLK, scripts/phase_clk.py): thread 0 of every CTA stamps clock64() at the phase
+// boundaries of the step kernels into a device table [kernel][CTA][16]; entry 15 is the globaltimer at CTA start.
+#ifdef MD_PHASE_CLK
+__device__ unsigned long long* g_phase_clk = nullptr;
+#define CLK_CTAS 4096
+__device__ __forceinline__ void clk_mark(int kern, int phase) {
+    if (g_phase_clk != nullptr && threadIdx.x == 0 && blockIdx.x < CLK_CTAS) {
+        unsigned long long* row = g_phase_clk + ((size_t)kern * CLK_CTAS + blockIdx.x) * 16;
+        row[phase] = (unsigned long long)clock64();
+        if (phase == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); row[15] = t;
+                          unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); row[14] = sm; }
+        if (phase >= 13) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); row[12] = t; }
+    }
+}
+extern "C" int md_debug_phase_clk(unsigned long long* dev_table) {
+    return cudaMemcpyToSymbol(g_phase_clk, &dev_table, sizeof(dev_table)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define clk_mark(kern, phase)
+#endif
+
 #define STEP_THREADS 128
 // register caps per kernel (__maxnreg__): the block size is a run-time choice (envs per CTA x slots per env), so the
 // occupancy is steered through the register budget instead of __launch_bounds__
@@ -49,27 +70,6 @@
 
 // ray direction tables (cos, sin per laser) live in global memory, one set per handle: every lane reads a different entry
 // (constant memory would serialise that), and two handles with different laser counts must not share them
-
-// Debug builds only (make EXTRA=-DMD_PHASE_CLK, scripts/phase_clk.py): thread 0 of every CTA stamps clock64() at the phase
-// boundaries of the step kernels into a device table [kernel][CTA][16]; entry 15 is the globaltimer at CTA start.
-#ifdef MD_PHASE_CLK
-__device__ unsigned long long* g_phase_clk = nullptr;
-#define CLK_CTAS 4096
-__device__ __forceinline__ void clk_mark(int kern, int phase) {
-    if (g_phase_clk != nullptr && threadIdx.x == 0 && blockIdx.x < CLK_CTAS) {
-        unsigned long long* row = g_phase_clk + ((size_t)kern * CLK_CTAS + blockIdx.x) * 16;
-        row[phase] = (unsigned long long)clock64();
-        if (phase == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); row[15] = t;
-                          unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); row[14] = sm; }
-        if (phase >= 13) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); row[12] = t; }
-    }
-}
-extern "C" int md_debug_phase_clk(unsigned long long* dev_table) {
-    return cudaMemcpyToSymbol(g_phase_clk, &dev_table, sizeof(dev_table)) == cudaSuccess ? 0 : -1;
-}
-#else
-#define clk_mark(kern, phase)
-#endif
 
 enum {
     MODE_AGENT_PRE = 1, MODE_TRIGGER = 2, MODE_IDM = 4, MODE_DYN = 8, MODE_CONTACTS = 16, MODE_POST = 32,
@@ -169,13 +169,15 @@ __device__ void find_front_back(const MapView& m, const NbrView& nv, unsigned lo
     }
 }
 
-// find_front_back with the expensive part - lane coordinates of every surrounding object on the three lanes, and whether
-// its lane continues / precedes them - spread over the T lanes of a sub-warp team (the search is 60 % of k_pre).  The
-// object loop of the reference is ORDER dependent (an object on a successor lane only counts until one on the lane itself
-// was found), so the team only fills a table (`scratch`, one float4 per neighbour index), and every lane then runs the
-// ordered fold over it redundantly - all lanes of the team end with the same, exact result.
-//   scratch[k] = (code, lane_local longitude on this lane / on its own lane): code bit 0 same lane, bit 1 this lane is the
-//   previous of its lane, bit 2 its lane is the previous of this lane
+// find_front_back with the expensive part - the lane coordinates of every surrounding object and whether its lane is one
+// of the three lanes, continues or precedes them - spread over the T lanes of a sub-warp team (the search is 60 % of
+// k_pre).  The object loop of the reference is ORDER dependent (an object on a successor lane only counts until one on
+// the lane itself was found), so the team only fills a table (`scratch`, one float2 per neighbour index), and every lane
+// then runs the ordered folds over it redundantly - all lanes of the team end with the same, exact result.
+// An object's longitude is taken on ITS OWN lane whichever of the three lanes is being searched (on the lane itself the
+// two coincide), so the table is filled ONCE for the three searches: one lane-row fetch and one lane_local per object.
+//   scratch[k] = (codes, longitude of object k on its own lane); codes = 3 bits per searched lane i (<< 3 i): bit 0 the
+//   object is on lane i, bit 1 lane i is the previous of its lane, bit 2 its lane is the previous of lane i
 __device__ void find_front_back_team(const MapView& m, const NbrView& nv, unsigned long long valid_lo, unsigned long long valid_hi,
                                      int lane, float px, float py, float max_d, bool use_ref, int ref_first, int ref_n,
                                      FrontBack& out, int sub, int T, unsigned team_mask, float2* scratch) {
@@ -185,61 +187,77 @@ __device__ void find_front_back_team(const MapView& m, const NbrView& nv, unsign
         if (idx > 0) lanes[0] = ref_first + idx - 1;
         if (idx + 1 < ref_n) lanes[2] = ref_first + idx + 1;
     }
+    float cur_long[3], left_long[3], sx[3], sy[3], ex[3], ey[3];
+#pragma unroll
     for (int i = 0; i < 3; i++) {
         out.fobj[i] = out.bobj[i] = OBJ_NONE;
         out.exists[i] = lanes[i] >= 0;
         out.fdist[i] = out.bdist[i] = max_d;
+        cur_long[i] = left_long[i] = sx[i] = sy[i] = ex[i] = ey[i] = 0.0f;
         if (lanes[i] < 0) continue;
         const float* Li = m.lane_f + lanes[i] * LANE_F;
-        float cur_long, lat;
-        lane_local(Li, px, py, cur_long, lat);
-        float left_long = Li[LF_LENGTH] - cur_long;
-        // the table: the ord-th valid neighbour belongs to lane ord % T of the team
-        int ord = 0;
-        for (int half = 0; half < 2; half++)
-            for (unsigned long long mk = half ? valid_hi : valid_lo; mk; mk &= mk - 1, ord++) {
-                if ((ord & (T - 1)) != sub) continue;
-                const int k = __ffsll((long long)mk) - 1 + 64 * half;
-                float ox, oy, ovx, ovy; int olane; bool ped;
-                nv.get(k, ox, oy, ovx, ovy, olane, ped);
-                float2 rec = make_float2(0.0f, 0.0f);
-                if (olane >= 0) {
-                    const float* Lo = m.lane_f + olane * LANE_F;
-                    float lon, lt;
-                    if (olane == lanes[i]) { lane_local(Li, ox, oy, lon, lt); rec.x = 1.0f; rec.y = lon; }
-                    else {
-                        const int code = (lane_is_previous_of(Li, Lo) ? 2 : 0) | (lane_is_previous_of(Lo, Li) ? 4 : 0);
-                        if (code) { lane_local(Lo, ox, oy, lon, lt); rec.y = lon; }
-                        rec.x = (float)code;
+        float lat;
+        lane_local(Li, px, py, cur_long[i], lat);
+        left_long[i] = Li[LF_LENGTH] - cur_long[i];
+        sx[i] = Li[LF_SX]; sy[i] = Li[LF_SY]; ex[i] = Li[LF_EX]; ey[i] = Li[LF_EY];
+    }
+    // the table: the ord-th valid neighbour belongs to lane ord % T of the team
+    int ord = 0;
+    for (int half = 0; half < 2; half++)
+        for (unsigned long long mk = half ? valid_hi : valid_lo; mk; mk &= mk - 1, ord++) {
+            if ((ord & (T - 1)) != sub) continue;
+            const int k = __ffsll((long long)mk) - 1 + 64 * half;
+            float ox, oy, ovx, ovy; int olane; bool ped;
+            nv.get(k, ox, oy, ovx, ovy, olane, ped);
+            float2 rec = make_float2(0.0f, 0.0f);
+            if (olane >= 0) {
+                const float* Lo = m.lane_f + olane * LANE_F;
+                const float osx = Lo[LF_SX], osy = Lo[LF_SY], oex = Lo[LF_EX], oey = Lo[LF_EY];
+                int codes = 0;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    if (lanes[i] < 0) continue;
+                    int c;
+                    if (olane == lanes[i]) c = 1;
+                    else {   // lane_is_previous_of(Li, Lo), lane_is_previous_of(Lo, Li)
+                        const float ax = ex[i] - osx, ay = ey[i] - osy, bx = oex - sx[i], by = oey - sy[i];
+                        c = (sqrtf(ax * ax + ay * ay) < 0.1f ? 2 : 0) | (sqrtf(bx * bx + by * by) < 0.1f ? 4 : 0);
                     }
+                    codes |= c << (3 * i);
                 }
-                scratch[k] = rec;
+                if (codes) { float lon, lt; lane_local(Lo, ox, oy, lon, lt); rec.y = lon; }
+                rec.x = (float)codes;
             }
-        __syncwarp(team_mask);
-        // the ordered fold (policy/idm_policy.py:100-131), identical on every lane
+            scratch[k] = rec;
+        }
+    __syncwarp(team_mask);
+    // the ordered folds (policy/idm_policy.py:100-131), identical on every lane
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (lanes[i] < 0) continue;
         bool ffound = false, bfound = false;
         for (int half = 0; half < 2; half++)
             for (unsigned long long mk = half ? valid_hi : valid_lo; mk; mk &= mk - 1) {
                 const int k = __ffsll((long long)mk) - 1 + 64 * half;
                 const float2 rec = scratch[k];
-                const int code = (int)rec.x;
+                const int code = ((int)rec.x >> (3 * i)) & 7;
                 float lon = rec.y;
                 if (code & 1) {
-                    lon -= cur_long;
+                    lon -= cur_long[i];
                     if (out.fdist[i] > lon && lon > 0.0f) { out.fdist[i] = lon; out.fobj[i] = k; ffound = true; }
                     if (lon < 0.0f && fabsf(lon) < out.bdist[i]) { out.bdist[i] = fabsf(lon); out.bobj[i] = k; bfound = true; }
                 } else if (!ffound && (code & 2)) {
-                    lon += left_long;
+                    lon += left_long[i];
                     if (out.fdist[i] > lon && lon > 0.0f) { out.fdist[i] = lon; out.fobj[i] = k; }
                 } else if (!bfound && (code & 4)) {
                     float ox, oy, ovx, ovy; int olane; bool ped;
                     nv.get(k, ox, oy, ovx, ovy, olane, ped);
-                    lon = m.lane_f[olane * LANE_F + LF_LENGTH] - lon + cur_long;
+                    lon = m.lane_f[olane * LANE_F + LF_LENGTH] - lon + cur_long[i];
                     if (out.bdist[i] > lon) { out.bdist[i] = lon; out.bobj[i] = k; }
                 }
             }
-        __syncwarp(team_mask);  // the table is rewritten for the next lane
     }
+    __syncwarp(team_mask);  // the table is rewritten by the team's next vehicle
 }
 
 __device__ __forceinline__ float pid(float kp, float ki, float kd, float& p_err, float& i_err, float err) {
@@ -323,6 +341,7 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
         success = true;
     } else success = true;
     I[VI_ROUTING_LANE] = rt;
+    if (threadIdx.x == 0) clk_mark(0, 4);
 
     // Lidar.get_surrounding_objects(r = 50) (component/sensors/lidar.py:170-186): membership bitmask
     unsigned long long vlo = 0ull, vhi = 0ull;
@@ -336,6 +355,7 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
             if (Ob[OB_KIND] == 3.0f || Ob[OB_LANE] < 0.0f) has_ped = true;  // no `.lane` -> except path (:254-259)
         }
     }
+    if (threadIdx.x == 0) clk_mark(0, 5);
     int front = OBJ_NONE;
     float front_dist = 0.0f;
     int steer_lane = rt;
@@ -402,6 +422,7 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
         else find_front_back(m, nv, vlo, vhi, rt, px, py, 30.0f, false, 0, 0, fb);
         front = fb.fobj[1]; front_dist = fb.fdist[1]; steer_lane = rt;
     }
+    if (threadIdx.x == 0) clk_mark(0, 6);
     // steering_control (:293-301)
     const float* Ls = m.lane_f + steer_lane * LANE_F;
     float lon, lat;
@@ -428,6 +449,7 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
     }
     out_a0 = steering;
     out_a1 = acc;
+    if (threadIdx.x == 0) clk_mark(0, 7);
 #undef IN_CUR
 }
 
@@ -960,7 +982,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
     // the first kernel of a step advances the view's pass counters (scenario draws, observation passes); they live in
     // device memory so that a whole step is a fixed launch sequence (CUDA-graph replayable).  Nobody reads them in k_pre.
     if (pass_ctr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { pass_ctr[0] += d_bank; pass_ctr[1] += d_noise; }
-    if (work_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *work_count = 0u;   // k_dyn's list of this step starts empty
+    if (work_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { work_count[0] = 0u; work_count[1] = 0u; }   // k_dyn's list of this step starts empty; [1] = k_scan's cursor
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     const int n_rows = epb * S, env0 = blockIdx.x * epb;
     Nb* nb_all = reinterpret_cast<Nb*>(smem_raw);
@@ -1645,18 +1667,27 @@ __device__ __forceinline__ void after_step_vehicle(const MapView& m, const float
 // TS lanes per vehicle (a warp holds 32 / TS vehicles).  The loads are ordered so that the independent chains of a vehicle
 // overlap: (state, checkpoints, map id) -> (map tables' offsets, route roads) -> (cell ranges of BOTH scans, road rows) ->
 // (grid records of the candidates AND of the first items) -> lane rows of the surviving candidates.
-template <int TS>
-__global__ void __launch_bounds__(SCAN_WARPS * 32, 4)
-k_scan(MdConfig cfg, MdArrays A, MapAccel X, const int* __restrict__ work_list, const unsigned int* __restrict__ work_count,
+template <int TS, int MB>
+__global__ void __launch_bounds__(SCAN_WARPS * 32, MB)
+k_scan(MdConfig cfg, MdArrays A, MapAccel X, const int* __restrict__ work_list, unsigned int* __restrict__ work_count,
        LocScan* __restrict__ scan_tab) {
     const int lane = threadIdx.x & 31, tl = threadIdx.x & (TS - 1), tbase = lane & ~(TS - 1), S = cfg.slots_per_env;
     const unsigned tmask = TS == 32 ? 0xffffffffu : (((1u << TS) - 1u) << tbase);
     clk_mark(3, 0);
-    const int n = (int)*work_count, n_teams = gridDim.x * (SCAN_WARPS * 32 / TS);
-    for (int j = (blockIdx.x * SCAN_WARPS * 32 + threadIdx.x) / TS; j < n; j += n_teams) {
+    // The vehicles differ a lot in cost (a cell of an intersection holds several times the lanes and line boxes of a cell of
+    // a straight road), so the warps do not stride over the list: each fetches its next 32 / TS vehicles from a cursor
+    // (one atomic per warp and fetch - a few thousand per launch).
+    const int n = (int)work_count[0];
 #ifdef MD_PHASE_CLK
-        const bool first = j < n_teams;
+    bool first = true;
 #endif
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&work_count[1], 32u / TS);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((int)base >= n) break;
+        const int j = (int)base + lane / TS;
+        if (j >= n) continue;   // the whole team skips: the masks below only name this team's lanes
         const int g = __ldg(work_list + j), env = g / S;
         const float* St = A.veh_s + (size_t)g * VEH_S;
         float P4[4], Sv[VEH_S];
@@ -1766,6 +1797,7 @@ k_scan(MdConfig cfg, MdArrays A, MapAccel X, const int* __restrict__ work_list, 
         if (tl == 0) scan_tab[g] = sc;
 #ifdef MD_PHASE_CLK
         if (first) clk_mark(3, 4);
+        first = false;
 #endif
     }
 #ifdef MD_PHASE_CLK
@@ -2751,7 +2783,7 @@ static View make_view(const md_sim* sim, int env0, int n, int count_slot) {
     v.lidar_count = sim->lidar_count ? sim->lidar_count + count_slot : nullptr;
     v.pass = sim->d_pass + 2 * count_slot;
     v.work_list = sim->work_list + nv0;
-    v.work_count = sim->work_count + count_slot;
+    v.work_count = sim->work_count + 2 * count_slot;   // [0] entries, [1] k_scan's cursor
     v.scan_tab = sim->scan_tab + nv0;
     return v;
 }
@@ -2928,8 +2960,8 @@ extern "C" int md_load_scene(md_sim* sim, const MdArrays* host, const int64_t* r
         CK(cudaMemset(sim->lidar_count, 0, sizeof(unsigned int) * (1 + MAX_HOST_GROUPS)));
     }
     CK(cudaMalloc(&sim->work_list, sizeof(int) * (size_t)NV));
-    CK(cudaMalloc(&sim->work_count, sizeof(unsigned int) * (1 + MAX_HOST_GROUPS)));
-    CK(cudaMemset(sim->work_count, 0, sizeof(unsigned int) * (1 + MAX_HOST_GROUPS)));
+    CK(cudaMalloc(&sim->work_count, sizeof(unsigned int) * 2 * (1 + MAX_HOST_GROUPS)));
+    CK(cudaMemset(sim->work_count, 0, sizeof(unsigned int) * 2 * (1 + MAX_HOST_GROUPS)));
     CK(cudaMalloc(&sim->scan_tab, sizeof(LocScan) * (size_t)NV));
     CK(cudaMalloc(&sim->d_pass, sizeof(uint32_t) * 2 * (1 + MAX_HOST_GROUPS)));
     CK(cudaMemset(sim->d_pass, 0, sizeof(uint32_t) * 2 * (1 + MAX_HOST_GROUPS)));
@@ -3221,10 +3253,12 @@ static int step_impl(md_sim* sim, View& v, const float* actions_dev, StepOut out
     if (use_scan) {
         // a persistent grid: 4 CTAs of 8 warps per SM are resident at 64 registers per thread, and each team strides over
         // the list.  MD_SCAN_TEAM = 8 / 16 / 32 lanes per vehicle (measured), MD_SCAN_CTAS overrides the grid.
-        static const int scan_ctas = env_int("MD_SCAN_CTAS", 148 * 4), scan_team = env_int("MD_SCAN_TEAM", 8);
-        if (scan_team == 32) k_scan<32><<<scan_ctas, SCAN_WARPS * 32, 0, st>>>(v.cfg, v.dev, sim->accel, v.work_list, v.work_count, v.scan_tab);
-        else if (scan_team == 16) k_scan<16><<<scan_ctas, SCAN_WARPS * 32, 0, st>>>(v.cfg, v.dev, sim->accel, v.work_list, v.work_count, v.scan_tab);
-        else k_scan<8><<<scan_ctas, SCAN_WARPS * 32, 0, st>>>(v.cfg, v.dev, sim->accel, v.work_list, v.work_count, v.scan_tab);
+        static const int scan_mb = env_int("MD_SCAN_MB", 4), scan_team = env_int("MD_SCAN_TEAM", 8);
+        static const int scan_ctas = env_int("MD_SCAN_CTAS", 148 * scan_mb);
+#define SCAN_LAUNCH(TS, MB) k_scan<TS, MB><<<scan_ctas, SCAN_WARPS * 32, 0, st>>>(v.cfg, v.dev, sim->accel, v.work_list, v.work_count, v.scan_tab)
+        if (scan_mb == 6) { if (scan_team == 4) SCAN_LAUNCH(4, 6); else if (scan_team == 16) SCAN_LAUNCH(16, 6); else SCAN_LAUNCH(8, 6); }
+        else { if (scan_team == 4) SCAN_LAUNCH(4, 4); else if (scan_team == 16) SCAN_LAUNCH(16, 4); else if (scan_team == 32) SCAN_LAUNCH(32, 4); else SCAN_LAUNCH(8, 4); }
+#undef SCAN_LAUNCH
         sim->launches++;
         CK(cudaGetLastError());
     }

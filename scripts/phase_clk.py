@@ -41,7 +41,7 @@ tab = torch.zeros((4, CTAS, 16), dtype=torch.int64, device=dev)
 h = mdlib.load()
 h.md_debug_phase_clk.argtypes = [C.c_void_p]
 assert h.md_debug_phase_clk(C.c_void_p(tab.data_ptr())) == 0
-NAMES = {0: ("k_pre", ["phase1 sweep", "trigger", "compact", "idm", ]), 1: ("k_dyn", ["list", "remap", "load", "broad", "substeps", "store"]),
+NAMES = {0: ("k_pre", ["phase1 sweep", "trigger", "compact", "idm: rows+map+routing lane", "idm: neighbour mask", "idm: front/back + lane change", "idm: steering+acc", "idm: actuate+store, other rounds"]), 1: ("k_dyn", ["list", "remap", "load", "broad", "substeps", "store"]),
          3: ("k_scan", ["prelude (first item)", "candidates", "items", "reduce+store", "later items"]),
          2: ("k_post", ["restore", "phase1", "2a r0: map_view+loc_ctx+cell", "2a r0: candidates", "2a r0: static", "2a r0: contacts", "2a later rounds+shfl", "phase2"])}
 acc = {}
@@ -58,7 +58,7 @@ for rep in range(5):
         rows = t[k]
         used = rows[:, 0] != 0
         r = rows[used]
-        marks = [0, 1, 2, 3, 4, 13] if k in (1, 3) else ([0, 1, 2, 3, 13] if k == 0 else [0, 1, 2, 4, 5, 6, 7, 3, 13])
+        marks = [0, 1, 2, 3, 4, 13] if k in (1, 3) else ([0, 1, 2, 3, 4, 5, 6, 7, 13] if k == 0 else [0, 1, 2, 4, 5, 6, 7, 3, 13])
         if k == 2:
             if (r[:, 7] != 0).any():
                 r = r[r[:, 7] != 0]
