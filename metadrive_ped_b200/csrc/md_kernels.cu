@@ -502,7 +502,6 @@ __device__ __forceinline__ void loc_candidate(const MapView& m, const LocCtx& c,
     if (c.px < bb.x || c.py < bb.y || c.px > bb.z || c.py > bb.w) return;
     loc_candidate_in_bb(m, c, l, m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], s);
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ LocCtx loc_ctx(const MapView& m, const float* S, const int* I, const int* __restrict__ rroad) {
     LocCtx c;
     c.px = S[VS_POS]; c.py = S[VS_POS + 1];
