@@ -326,6 +326,24 @@ def measure(args, workload, rank, local_rank, world, K, warmup, full):
         if world > 1:
             dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
         e2e[name] = (world * E * n_ag * Ke * live_frac / float(dt_e.item()), rows / Ke)
+    # what the host link gives while every rank copies at once: a pinned 64 MiB device-to-host copy, all ranks started together.
+    # (On the 8-GPU boxes of this pool the GPUs share the host's PCIe / memory fabric: the per-GPU rate with 8 ranks active is a
+    # fraction of the rate of a GPU copying alone, and it caps e2e - see d2h_probe_gbs_per_gpu next to d2h_achieved_gbs_per_gpu.)
+    probe_gbs = None
+    if full:
+        pd = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        ph = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        ph.copy_(pd, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ph.copy_(pd, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        dt_p = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_p, op=dist.ReduceOp.MAX)
+        probe_gbs = 10 * (64 << 20) / float(dt_p.item()) / 1e9
+        del pd, ph
     obs_rows = e2e["pipelined"][1]     # observation rows copied per step (multi-agent: only the FL_VALID seats travel)
     h2d = A * 2 * 4
     d2h = int(obs_rows * sim.obs_dim * 4 + A * (4 + 4 + 1 + 1 + 4 + 8 * 4))
@@ -352,6 +370,11 @@ def measure(args, workload, rank, local_rank, world, K, warmup, full):
                         "H2D and its results D2H every step; a group's next actions are sent after its results were received" % G}
         if "sync" in e2e:
             e2e_d["sync_call_value"] = e2e["sync"][0]
+        if probe_gbs is not None:
+            steps_per_s = e2e["pipelined"][0] / (world * E * n_ag * live_frac)
+            e2e_d["d2h_achieved_gbs_per_gpu"] = d2h * steps_per_s / 1e9
+            e2e_d["d2h_probe_gbs_per_gpu"] = probe_gbs
+            e2e_d["d2h_probe"] = "64 MiB pinned device-to-host copies, all %d ranks copying at once (slowest rank)" % world
         line = {"metric": "agent_steps_per_sec_240beam_lidar", "value": value, "unit": "agent-steps/s", "n_gpus": world,
                 "steps": K, "warmup": warmup, "ms_per_step": 1e3 * total_s / K, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -422,7 +445,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short cfg3 / cfg4 / cfg5 entries")
     ap.add_argument("--no-resample", action="store_true", help="finished envs replay their own scenario instead of drawing a new one")
-    ap.add_argument("--host-groups", type=int, default=4, help="host groups of the e2e leg (md_host_groups)")
+    ap.add_argument("--host-groups", type=int, default=2, help="host groups of the e2e leg (md_host_groups)")
     ap.add_argument("--burnin", type=int, default=150,
                     help="untimed setup steps (with auto-reset) so that envs sit at mixed episode phases")
     args = ap.parse_args()

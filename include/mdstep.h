@@ -136,7 +136,7 @@ int md_get_contacts(md_sim* sim, uint32_t* host_dst, size_t bytes);
 int md_snapshot(md_sim* sim);
 /* per-stage device timing of the next max_steps md_step / md_step_autoreset calls: six cudaEvents per call recorded on
  * the launch stream (no synchronisation added).  md_profile_end (after the caller synchronised) fills ms[5*i + k] with
- * the milliseconds of stage k (0 k_pre, 1 k_dyn, 2 k_post, 3 fused reset, 4 k_lidar) of recorded step i and returns
+ * the milliseconds of stage k (0 k_pre, 1 k_dyn, 2 k_scan + k_post, 3 fused reset, 4 k_lidar) of recorded step i and returns
  * how many steps. */
 int md_profile_begin(md_sim* sim, int max_steps);
 int md_profile_end(md_sim* sim, float* ms, int cap);

@@ -3252,11 +3252,10 @@ static int step_impl(md_sim* sim, View& v, const float* actions_dev, StepOut out
     if (use_scan) {
         // a persistent grid: 4 CTAs of 8 warps per SM are resident at 64 registers per thread, and each team strides over
         // the list.  MD_SCAN_TEAM = 8 / 16 / 32 lanes per vehicle (measured), MD_SCAN_CTAS overrides the grid.
-        static const int scan_mb = env_int("MD_SCAN_MB", 4), scan_team = env_int("MD_SCAN_TEAM", 8);
-        static const int scan_ctas = env_int("MD_SCAN_CTAS", 148 * scan_mb);
-#define SCAN_LAUNCH(TS, MB) k_scan<TS, MB><<<scan_ctas, SCAN_WARPS * 32, 0, st>>>(v.cfg, v.dev, sim->accel, v.work_list, v.work_count, v.scan_tab)
-        if (scan_mb == 6) { if (scan_team == 4) SCAN_LAUNCH(4, 6); else if (scan_team == 16) SCAN_LAUNCH(16, 6); else SCAN_LAUNCH(8, 6); }
-        else { if (scan_team == 4) SCAN_LAUNCH(4, 4); else if (scan_team == 16) SCAN_LAUNCH(16, 4); else if (scan_team == 32) SCAN_LAUNCH(32, 4); else SCAN_LAUNCH(8, 4); }
+        static const int scan_team = env_int("MD_SCAN_TEAM", 8), scan_ctas = env_int("MD_SCAN_CTAS", 148 * 4);
+#define SCAN_LAUNCH(TS) k_scan<TS, 4><<<scan_ctas, SCAN_WARPS * 32, 0, st>>>(v.cfg, v.dev, sim->accel, v.work_list, v.work_count, v.scan_tab)
+        // (6 CTAs per SM = 40 registers spill and are no faster; 4 / 16 / 32 lanes per vehicle are within 3 us of 8, 32 is slower)
+        if (scan_team == 4) SCAN_LAUNCH(4); else if (scan_team == 16) SCAN_LAUNCH(16); else if (scan_team == 32) SCAN_LAUNCH(32); else SCAN_LAUNCH(8);
 #undef SCAN_LAUNCH
         sim->launches++;
         CK(cudaGetLastError());

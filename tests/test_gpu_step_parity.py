@@ -155,6 +155,75 @@ def test_lidar_kernel_bit_exact_hits(tag, oracle_lib):
     sim.close()
 
 
+def test_lidar_degenerate_cases(oracle_lib):
+    """SURVEY 7.2's degenerate cases of Lidar.perceive, md_lidar against the oracle (hit ids exact, fractions 1e-4 relative) on a
+    SafeMetaDriveEnv scene (vehicles, cones, warning tripods) with a NON-INTEGER perceive distance: the ego inside another
+    vehicle's box (every ray of the angular mask on), a body whose near face is exactly the perceive distance away (miss =
+    1.0 vs. hit just below 1.0), rays parallel to a neighbour's long side at a hand's width, and a pitched ego whose rays -
+    cast at z = 1.2 m (sensors/lidar.py:19) - graze the top faces of the cylinders (cone 1.0 m, warning 1.2 m)."""
+    from metadrive_ped_b200.sim import BatchedSim
+    from oracle.oracle import OracleSim
+    import torch
+    g = load_golden("cfg4_safe_seed5")
+    D = 37.3
+    arrays, cfg, _ = golden_world(g, replicas=32, lidar_dist=D)
+    sim, orc = BatchedSim(arrays, cfg), OracleSim(arrays, cfg)
+    sim.reset(); orc.reset_observe()
+    S, O = cfg.slots_per_env, cfg.objs_per_env
+    vs, obj = orc.a["veh_s"].copy(), orc.a["obj_f"].copy()
+    vp = orc.a["veh_p"]
+    rng = np.random.RandomState(7)
+    n_veh = g["veh_f"].shape[1]
+    warn = [k for k in range(O) if obj[k, 0] == 1.0]
+    cyl = [k for k in range(O) if obj[k, 0] in (0.0, 1.0)]
+    assert n_veh >= 3 and warn and cyl, "the fixture must hold traffic, cones and a warning tripod"
+
+    def yaw_quat(yaw, pitch=0.0):   # chassis +Y is the nose: yaw about z, then a small pitch about the body x axis
+        qz = np.array([np.cos(yaw / 2), 0.0, 0.0, np.sin(yaw / 2)])
+        qx = np.array([np.cos(pitch / 2), np.sin(pitch / 2), 0.0, 0.0])
+        w1, x1, y1, z1 = qz; w2, x2, y2, z2 = qx
+        return np.array([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                         w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2])
+
+    for e in range(cfg.n_envs):
+        ego, case = e * S, e % 4
+        k = 1 + rng.randint(n_veh - 1)
+        other = vs[e * S + k]
+        oyaw = 2.0 * np.arctan2(other[6], other[3])
+        if case == 0:      # inside the other vehicle's box (centres up to 0.3 m apart), any heading
+            vs[ego, 0:2] = other[0:2] + rng.uniform(-0.3, 0.3, 2)
+            vs[ego, 3:7] = yaw_quat(rng.uniform(-np.pi, np.pi))
+        elif case == 1:    # the near face of a cylinder exactly D ahead (to within float rounding, either side of it)
+            o = obj[e * O + cyl[rng.randint(len(cyl))]]
+            ang = rng.uniform(-np.pi, np.pi)
+            dist = D + o[4] + (rng.randint(3) - 1) * 1e-5
+            vs[ego, 0:2] = o[1:3] - dist * np.array([np.cos(ang), np.sin(ang)])
+            vs[ego, 3:7] = yaw_quat(ang - np.pi / 2)
+        elif case == 2:    # alongside the other vehicle, headings exactly parallel, 5 cm between the flanks
+            W_o, W_e = vp[e * S + k, 2], vp[ego, 2]
+            side = np.array([np.cos(oyaw), np.sin(oyaw)])          # the body x axis = to the right of the nose
+            vs[ego, 0:2] = other[0:2] + side * (0.5 * (W_o + W_e) + 0.05) * (1 if e % 8 < 4 else -1)
+            vs[ego, 3:7] = yaw_quat(oyaw)
+        else:              # 4 m from a warning tripod, pitched so that the z = 1.2 m rays rise / sink through its top face
+            o = obj[e * O + warn[rng.randint(len(warn))]]
+            ang = rng.uniform(-np.pi, np.pi)
+            vs[ego, 0:2] = o[1:3] - 4.0 * np.array([np.cos(ang), np.sin(ang)])
+            vs[ego, 3:7] = yaw_quat(ang - np.pi / 2, pitch=rng.uniform(-0.03, 0.03))
+    orc.a["veh_s"][:] = vs
+    sim.set_state("veh_s", vs)
+    frac_o, hit_o = orc.lidar()
+    frac_g, hit_g = sim.lidar()
+    frac_g, hit_g = frac_g.cpu().numpy(), hit_g.cpu().numpy()
+    np.testing.assert_array_equal(hit_g, hit_o)
+    np.testing.assert_allclose(frac_g, frac_o, rtol=1e-4, atol=1e-6)
+    np.testing.assert_array_equal(frac_g, frac_o)                       # in fact bit-identical
+    assert ((hit_o < 0) == (frac_o == 1.0)).all(), "a miss reads exactly 1.0, a hit less"
+    inside = frac_o[0::4]
+    assert (inside.min(1) < 0.05).all(), "inside a box: the enclosing body is seen at point-blank range"
+    assert (hit_o[2::4] >= 0).sum() > 100 and (hit_o[3::4] >= 0).any() and (hit_o[1::4] >= 0).any()
+    sim.close()
+
+
 def test_isolated_stage_entry_points(oracle_lib):
     """md_idm / md_dynamics / md_after_step (per-kernel entry points for parity tests and ncu captures of a kernel
     in isolation) against the oracle's isolated stages, bit for bit, in the middle of an episode with triggered traffic."""
