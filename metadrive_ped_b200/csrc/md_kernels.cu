@@ -1500,15 +1500,13 @@ struct BankView {
     const float* body; const float* obs; const float* veh_p; const int* env_trigger;
     int n;
 };
+struct FusedBank { BankView B; uint32_t seed; const uint32_t* pass_ctr; int on; };   // k_post's fused auto-reset (bank draws)
 __global__ void k_bump(uint32_t* __restrict__ pass_ctr, uint32_t d_bank, uint32_t d_noise) { pass_ctr[0] += d_bank; pass_ctr[1] += d_noise; }
-__global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, uint32_t seed, const uint32_t* __restrict__ pass_ctr,
-                               float* __restrict__ body_tab, float* __restrict__ obs, const uint8_t* __restrict__ env_mask) {
-    const uint32_t pass = pass_ctr[0];
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// one slot row (plus its share of the env-level rows) of a finished env <- the scenario drawn for it
+__device__ __forceinline__ void restore_bank_row(const MdConfig& cfg, const MdArrays& A, const BankView& B, uint32_t seed, uint32_t pass,
+                                                 float* __restrict__ body_tab, float* __restrict__ obs, int env, int slot) {
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
-    if (g >= (long long)cfg.n_envs * S) return;
-    const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
-    if (env_mask != nullptr && env_mask[env] == 0) return;
+    const long long g = (long long)env * S + slot;
     // the draw: a counter hash of (seed, env, reset pass) - every thread of the env computes the same scenario
     uint32_t x = seed * 0x9E3779B9u + (uint32_t)(env + cfg.env_base) * 0x85EBCA6Bu + pass * 0xC2B2AE35u + 0x165667B1u;
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
@@ -1567,6 +1565,15 @@ __global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, uint32_t se
         const int ag = k / OBS_STATE(cfg), col = k - ag * OBS_STATE(cfg);
         obs[((size_t)env * NA + ag) * (size_t)OBS_DIM(cfg) + col] = B.obs[((size_t)scn * NA + ag) * OBS_STATE(cfg) + col];
     }
+}
+__global__ void k_restore_bank(MdConfig cfg, MdArrays A, BankView B, uint32_t seed, const uint32_t* __restrict__ pass_ctr,
+                               float* __restrict__ body_tab, float* __restrict__ obs, const uint8_t* __restrict__ env_mask) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int S = cfg.slots_per_env;
+    if (g >= (long long)cfg.n_envs * S) return;
+    const int env = (int)(g / S), slot = (int)(g - (long long)env * S);
+    if (env_mask != nullptr && env_mask[env] == 0) return;
+    restore_bank_row(cfg, A, B, seed, pass_ctr[0], body_tab, obs, env, slot);
 }
 __global__ void k_restore(MdConfig cfg, MdArrays A, Snapshot snap, const uint8_t* __restrict__ env_mask, int full) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1808,7 +1815,7 @@ k_scan(MdConfig cfg, MdArrays A, MapAccel X, const int* __restrict__ work_list, 
 __global__ void __maxnreg__(POST_REGS)
 k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restrict__ body_tab,
        const uint8_t* __restrict__ env_mask, uint8_t* __restrict__ done_mask, Snapshot snap, int team_pref, MapAccel X,
-       const LocScan* __restrict__ scan_tab) {
+       const LocScan* __restrict__ scan_tab, FusedBank FB) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     const int n_rows = epb * S, env0 = blockIdx.x * epb;
@@ -1986,11 +1993,23 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[g * NAVI_DIM + k] = navi[k];
         write_body_row(body_tab + g * BODY_ROW, P, St, alive_row);
     }
-    // ---- phase 3: respawn / hybrid traffic (manager/traffic_manager.py:112-121)
 #ifdef MD_PHASE_CLK
     __syncthreads();
     clk_mark(2, 13);
 #endif
+    // ---- auto-reset of the envs that finished in this step, fused in (single agent, scenario bank attached): the CTA owns
+    // its envs' rows, every read of this step is behind the barrier, so the rows of the drawn scenarios can be copied in
+    // right here instead of by a launch of their own (k_restore_bank: 12 us for a copy of ~1 % of the envs)
+    if (FB.on) {
+        __syncthreads();
+        const uint32_t pass = FB.pass_ctr[0];
+        for (int v = threadIdx.x; v < n_rows; v += blockDim.x) {
+            const int le = v / S, env = env0 + le;
+            if (env < cfg.n_envs && done_mask[env]) restore_bank_row(cfg, A, FB.B, FB.seed, pass, body_tab, out.obs, env, v - le * S);
+        }
+        return;   // trigger-mode worlds only (md_attach_bank): no phase 3
+    }
+    // ---- phase 3: respawn / hybrid traffic (manager/traffic_manager.py:112-121)
     if (!((mode & MODE_REMOVE) && cfg.traffic_mode != 0)) return;
     __syncthreads();
     for (int j = threadIdx.x; j < n_work; j += blockDim.x) {
@@ -3069,8 +3088,19 @@ static StepLaunch post_launch(const MdConfig& c) {  // k_post: epb envs per CTA,
     return L;
 }
 
+// The attribute belongs to the FUNCTION, not to a handle: it is only ever raised, so that a handle with a small scene loaded
+// later does not take away the opt-in an earlier, still live handle with a larger scene launches with ("invalid argument"
+// on the next launch of the earlier handle - seen with the single-env wrappers, which keep several handles alive).
 template <typename K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
+    static std::vector<std::pair<const void*, size_t>> high;
+    for (auto& h : high)
+        if (h.first == (const void*)kernel) {
+            if (bytes <= h.second) return cudaSuccess;
+            h.second = bytes;
+            return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        }
+    high.push_back({(const void*)kernel, bytes});
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 // The step kernels are occupancy-bound by registers, with 10 - 40 KB of shared memory per CTA: ask for the shared-memory
@@ -3135,11 +3165,21 @@ static int launch_dyn(md_sim* sim, const View& v, int mode, const float* ext_act
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_post(md_sim* sim, const View& v, int mode, StepOut out, const uint8_t* mask, cudaStream_t st, bool scanned = false) {
+static BankView bank_view(const md_sim* bk) {
+    BankView B;
+    B.post = bk->all.post; B.body = bk->post_body; B.obs = bk->post_obs; B.veh_p = bk->dev.veh_p;
+    B.env_trigger = bk->dev.env_trigger; B.n = bk->cfg.n_envs;
+    return B;
+}
+static int launch_post(md_sim* sim, const View& v, int mode, StepOut out, const uint8_t* mask, cudaStream_t st, bool scanned = false,
+                       bool fuse_bank = false) {
     StepLaunch L = post_launch(v.cfg);
     static const int team_pref = env_int("MD_POST_TEAM", 0);   // 0 = adaptive, 1 = off, 2 / 4 / 8 / 16 / 32 lanes per vehicle
+    FusedBank FB;
+    memset(&FB, 0, sizeof(FB));
+    if (fuse_bank) { FB.B = bank_view(sim->bank); FB.seed = sim->bank_seed; FB.pass_ctr = v.pass; FB.on = 1; }
     k_post<<<L.blocks, L.threads, L.smem, st>>>(v.cfg, v.dev, mode, L.epb, out, v.body_tab, mask, v.mask, v.snap, team_pref, sim->accel,
-                                                scanned ? v.scan_tab : nullptr);
+                                                scanned ? v.scan_tab : nullptr, FB);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -3156,9 +3196,7 @@ static int launch_restore_bank(md_sim* sim, View& v, float* obs, const uint8_t* 
     const MdConfig& c = v.cfg;
     const md_sim* bk = sim->bank;
     const long long nv = (long long)c.n_envs * c.slots_per_env;
-    BankView B;
-    B.post = bk->all.post; B.body = bk->post_body; B.obs = bk->post_obs; B.veh_p = bk->dev.veh_p;
-    B.env_trigger = bk->dev.env_trigger; B.n = bk->cfg.n_envs;
+    const BankView B = bank_view(bk);
     k_restore_bank<<<(int)((nv + 255) / 256), 256, 0, st>>>(c, v.dev, B, sim->bank_seed, v.pass, v.body_tab, obs, mask);
     sim->launches++;
     CK(cudaGetLastError());
@@ -3260,10 +3298,14 @@ static int step_impl(md_sim* sim, View& v, const float* actions_dev, StepOut out
         sim->launches++;
         CK(cudaGetLastError());
     }
-    if (launch_post(sim, v, MODE_POST | MODE_OUT | MODE_REMOVE | (fused_reset ? MODE_MARK_DONE : 0), out, nullptr, st, use_scan != 0)) return -1;
+    // with a bank attached the finished envs are restored by k_post itself (MD_FUSE_BANK=0: by a k_restore_bank launch)
+    static const int fuse_bank_pref = env_int("MD_FUSE_BANK", 1);
+    const bool bank_reset = fused_reset && sim->post_valid && sim->bank;
+    const bool fuse_bank = bank_reset && fuse_bank_pref && !v.cfg.is_multi_agent && out.obs != nullptr;
+    if (launch_post(sim, v, MODE_POST | MODE_OUT | MODE_REMOVE | (fused_reset ? MODE_MARK_DONE : 0), out, nullptr, st, use_scan != 0, fuse_bank)) return -1;
     if (prof) CK(cudaEventRecord(ev[3], st));
-    if (fused_reset && sim->post_valid && sim->bank) {
-        if (launch_restore_bank(sim, v, out.obs, v.mask, st)) return -1;
+    if (bank_reset) {
+        if (!fuse_bank && launch_restore_bank(sim, v, out.obs, v.mask, st)) return -1;
     } else if (fused_reset && sim->post_valid) {
         const long long nv = (long long)v.cfg.n_envs * v.cfg.slots_per_env;
         k_restore_post<<<(int)((nv + 255) / 256), 256, 0, st>>>(v.cfg, v.dev, v.post, v.post_body, v.post_obs, v.body_tab, out.obs, v.mask);

@@ -108,6 +108,23 @@ def test_drop_in_details():
     o.close()
 
 
+def test_handles_of_different_size_coexist():
+    """Kernel attributes (the dynamic shared-memory opt-in) belong to the function, not to a handle: loading a small scene
+    must not take it away from a live handle with a large one (a k_pre launch of the large handle failed with "invalid
+    argument" after a smaller scene had been loaded - seen through the single-env wrappers' handle cache)."""
+    from metadrive_ped_b200 import MetaDriveEnv, SafeMetaDriveEnv
+    big = SafeMetaDriveEnv(dict(accident_prob=1.0, map=7, traffic_density=0.3, num_scenarios=4))
+    big.reset(seed=1)
+    small = MetaDriveEnv(dict(map="S", traffic_density=0.0))
+    small.reset(seed=0)
+    for _ in range(3):
+        big.step([0.0, 0.5])
+        small.step([0.0, 0.5])
+    big.reset(seed=2)
+    big.step([0.0, 0.5])
+    big.close(); small.close()
+
+
 def test_config_errors_match_reference():
     from metadrive_ped_b200 import MetaDriveEnv, SafeMetaDriveEnv
     with pytest.raises(KeyError):
