@@ -41,7 +41,7 @@ tab = torch.zeros((4, CTAS, 16), dtype=torch.int64, device=dev)
 h = mdlib.load()
 h.md_debug_phase_clk.argtypes = [C.c_void_p]
 assert h.md_debug_phase_clk(C.c_void_p(tab.data_ptr())) == 0
-NAMES = {0: ("k_pre", ["phase1 sweep", "trigger", "compact", "idm: rows+map+routing lane", "idm: neighbour mask", "idm: front/back + lane change", "idm: steering+acc", "idm: actuate+store, other rounds"]), 1: ("k_dyn", ["list", "remap", "load", "broad", "substeps", "store"]),
+NAMES = {0: ("k_pre", ["phase1 sweep", "trigger", "compact", "idm: rows+map+routing lane", "idm: neighbour mask", "idm: front/back + lane change", "idm: steering+acc", "idm: actuate+store, other rounds"]), 1: ("k_dyn", ["row sweep + object staging", "pass list", "row loads + broad phase", "5 sub-steps", "store + work list"]),
          3: ("k_scan", ["prelude (first item)", "candidates", "items", "reduce+store", "later items"]),
          2: ("k_post", ["restore", "phase1", "2a r0: map_view+loc_ctx+cell", "2a r0: candidates", "2a r0: static", "2a r0: contacts", "2a later rounds+shfl", "phase2"])}
 acc = {}
