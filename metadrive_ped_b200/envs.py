@@ -38,6 +38,8 @@ STEP_DEFAULTS = dict(
                                    add_others_navi=False),
                         side_detector=dict(num_lasers=0, distance=50), lane_line_detector=dict(num_lasers=0, distance=20),
                         enable_reverse=False, vehicle_model="default", overtake_stat=False),
+    # record / replay (envs/base_env.py:255-263; manager/record_manager.py, replay_manager.py), see MetaDriveEnv.dump_episode
+    record_episode=False, replay_episode=None, only_reset_when_replay=False,
     # extensions of this build: which device hosts the simulation; crossing pedestrians per env (peds.py, BASELINE
     # config 5 - the reference has the Pedestrian object but no spawner for PG maps)
     device=0, num_pedestrians=0,
@@ -188,6 +190,23 @@ class _Agent:
     on_lane = property(lambda s: s._flag(0x100))
 
 
+class _EngineShim:
+    """What user code reaches through `env.engine` on this path: dump_episode() and the record / replay switches."""
+    def __init__(self, env):
+        self._env = env
+
+    def dump_episode(self):
+        return self._env.dump_episode()
+
+    @property
+    def record_episode(self):
+        return bool(self._env.config["record_episode"])
+
+    @property
+    def replay_episode(self):
+        return self._env.config["replay_episode"] is not None
+
+
 class MetaDriveEnv:
     ENV_KIND = "metadrive"
     EXTRA_DEFAULTS = {}
@@ -221,6 +240,33 @@ class MetaDriveEnv:
         self._overtake = (set(), set())
         self.observation_space = _box(-0.0, 1.0, (_obs_dim(self.config["vehicle_config"]), ))
         self.action_space = _action_space(self.config)
+        self._episode = None      # record_episode: the episode being recorded
+        self._replay_t = 0
+        self.engine = _EngineShim(self)
+
+    # -- record / replay.  The reference's RecordManager logs the state of every object at every physics sub-step and its
+    # ReplayManager restores those states frame by frame (manager/record_manager.py:35-198, replay_manager.py:56-170).  This
+    # simulator is deterministic - bit for bit - given the scenario, the actions and the random tape, so an episode is
+    # recorded as (scenario seed, config, actions) plus one state frame per env.step (for export and as a check), and replayed
+    # by stepping the recorded actions: the replayed observations, rewards and flags ARE the recorded episode's.
+    def _frame(self, step):
+        vs, vi = self._sim.get_state("veh_s"), self._sim.get_state("veh_i")
+        objs = {}
+        for k in range(len(vi)):
+            if not vi[k, 1]:
+                continue
+            w, x, y, z = (float(q) for q in vs[k, 3:7])
+            yaw = float(np.arctan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z)))
+            objs[DEFAULT_AGENT if k == 0 else "traffic_%d" % k] = dict(
+                position=[float(v) for v in vs[k, 0:3]], heading_theta=float((yaw + np.pi / 2 + np.pi) % (2 * np.pi) - np.pi),
+                velocity=[float(v) for v in vs[k, 7:9]], type="agent" if vi[k, 0] == 1 else "traffic", active=bool(vi[k, 2]))
+        return dict(episode_step=int(step), step_info=objs, agents=[DEFAULT_AGENT])
+
+    def dump_episode(self):
+        """BaseEngine.dump_episode (engine/base_engine.py): the episode recorded since the last reset (record_episode=True)."""
+        assert self._episode is not None, "record_episode is off or reset() was not called"
+        import copy
+        return copy.deepcopy(self._episode)
 
     # -- scenes
     def _library(self):
@@ -267,6 +313,10 @@ class MetaDriveEnv:
     # -- gym surface
     def reset(self, seed=None):
         from .sim import BatchedSim
+        epi = self.config["replay_episode"]
+        if epi is not None:   # the logged scenario is replayed whatever seed is asked for (base_env.py:502-537)
+            seed = int(epi["scenario_index"])
+            self._replay_t = 0
         if seed is None:   # BaseEnv._reset_global_seed: a uniform draw over the scenario range (envs/base_env.py:886-891)
             seed = int(self._rng.randint(self.start_seed, self.start_seed + self.num_scenarios))
         assert self.start_seed <= seed < self.start_seed + self.num_scenarios, \
@@ -289,6 +339,12 @@ class MetaDriveEnv:
         self.episode_cost = 0.0
         self._overtake = (set(), set())
         obs = self._sim.reset_host()[0].copy()
+        self._episode = None
+        if self.config["record_episode"]:
+            import time
+            self._episode = dict(scenario_index=seed, global_seed=seed, coordinate="MetaDrive", time=time.strftime("%Y-%m-%d_%H-%M-%S"),
+                                 global_config={k: v for k, v in self.config.items() if k != "replay_episode"},
+                                 frames_per_step=1, frame=[[self._frame(0)]], actions=[])
         return obs, self._info(None)
 
     def _processed_action(self, action):
@@ -308,10 +364,21 @@ class MetaDriveEnv:
 
     def step(self, action):
         assert self._sim is not None, "call reset() first"
+        epi = self.config["replay_episode"]
+        replaying = epi is not None and not self.config["only_reset_when_replay"]
+        if replaying:
+            assert self._replay_t < len(epi["actions"]), "the replayed episode is over (info['replay_done'])"
+            action = epi["actions"][self._replay_t]
         a = _action_row(self.config, action).reshape(1, 2)
         obs, rew, cost, term, trunc, flags, info_f = self._sim.step_host(a, autoreset=False)
         self.episode_cost += float(cost[0])
         info = self._info((self._processed_action(action), float(cost[0]), int(flags[0]), info_f[0]))
+        if self._episode is not None:
+            self._episode["actions"].append(action if np.isscalar(action) else [float(v) for v in np.asarray(action).reshape(-1)])
+            self._episode["frame"].append([self._frame(len(self._episode["actions"]))])
+        if replaying:
+            self._replay_t += 1
+            info["replay_done"] = self._replay_t >= len(epi["actions"])   # REPLAY_DONE (replay_manager.py:121-125)
         # cost_to_reward is only declared by the reference (envs/safe_metadrive_env.py:17), never read: the reward stays as is
         return obs[0].copy(), float(rew[0]), bool(term[0]), bool(trunc[0]), info
 
@@ -481,6 +548,8 @@ class MultiAgentMetaDrive:
                 raise NotImplementedError("config['%s'] is outside the step path this build covers" % k)
         if self.config["traffic_density"] != 0.0:
             raise NotImplementedError("multi-agent envs with IDM traffic are not covered")
+        if self.config["record_episode"] or self.config["replay_episode"] is not None:
+            raise NotImplementedError("record / replay covers the single-agent envs")
         lid = self.config["vehicle_config"]["lidar"]
         assert 0.0 <= lid["dropout_prob"] <= 1.0  # obs/state_obs.py:240
         if lid["add_others_navi"]:

@@ -108,6 +108,40 @@ def test_drop_in_details():
     o.close()
 
 
+def test_record_and_replay_episode():
+    """record_episode / replay_episode (envs/base_env.py:255-263, manager/record_manager.py, replay_manager.py): an episode
+    recorded with random actions is replayed - whatever seed and actions the caller passes - with the same observations,
+    rewards, flags and object states, step for step; info["replay_done"] marks its end."""
+    from metadrive_ped_b200 import MetaDriveEnv
+    rng = np.random.RandomState(3)
+    env = MetaDriveEnv(dict(record_episode=True, num_scenarios=20, start_seed=5, traffic_density=0.2))
+    obs0, _ = env.reset(seed=11)
+    log = []
+    for t in range(60):
+        o, r, te, tr, info = env.step(rng.uniform(-1, 1, 2) * [0.3, 1.0])
+        log.append((o, r, te, tr, info["crash_vehicle"], info["out_of_road"], info["cost"]))
+        if te or tr:
+            break
+    epi = env.engine.dump_episode()
+    env.close()
+    assert epi["scenario_index"] == 11 and len(epi["actions"]) == len(log) == len(epi["frame"]) - 1
+    f_last = epi["frame"][-1][0]
+    assert f_last["episode_step"] == len(log) and "default_agent" in f_last["step_info"] and len(f_last["step_info"]) >= 3
+    rep = MetaDriveEnv(dict(replay_episode=epi, num_scenarios=20, start_seed=5, traffic_density=0.2, record_episode=True))
+    o0, _ = rep.reset(seed=7)                      # the logged scenario wins
+    assert rep.current_seed == 11
+    np.testing.assert_array_equal(o0, obs0)
+    for t, (o, r, te, tr, cv, oor, cost) in enumerate(log):
+        o2, r2, te2, tr2, info = rep.step([0.0, 0.0])   # ignored: the logged action is applied
+        np.testing.assert_array_equal(o2, o, err_msg="obs at step %d" % t)
+        assert (r2, te2, tr2, info["crash_vehicle"], info["out_of_road"], info["cost"]) == (r, te, tr, cv, oor, cost)
+        assert info["replay_done"] == (t == len(log) - 1)
+    again = rep.dump_episode()                      # the replay re-recorded: identical frames
+    for fa, fb in zip(epi["frame"], again["frame"]):
+        assert fa[0]["step_info"] == fb[0]["step_info"]
+    rep.close()
+
+
 def test_handles_of_different_size_coexist():
     """Kernel attributes (the dynamic shared-memory opt-in) belong to the function, not to a handle: loading a small scene
     must not take it away from a live handle with a large one (a k_pre launch of the large handle failed with "invalid
