@@ -2719,6 +2719,8 @@ struct md_sim {
     int64_t launches;
     int* work_list; unsigned int* work_count; LocScan* scan_tab;   // k_dyn -> k_scan -> k_post (see View)
     MapAccel accel;         // grid records derived from the map tables at md_load_scene
+    // md_step_autoreset as a CUDA graph (device-resident path): captured once per set of caller pointers on an internal stream
+    cudaGraphExec_t dg_exec; uint64_t dg_key[12]; int dg_launches; cudaStream_t dg_stream;
     float dyn_alive;        // the scene's alive vehicles per env: sizes k_dyn's CTAs (0 = one thread per slot row)
     md_sim* bank;           // scenario bank (md_attach_bank): finished envs restart as a scenario drawn from it
     uint32_t bank_seed;
@@ -2889,6 +2891,8 @@ extern "C" void md_destroy(md_sim* sim) {
         cudaFree(sim->body_tab); cudaFree(sim->veh_act); cudaFree(sim->mask);
         cudaFree((void*)sim->accel.lrec); cudaFree((void*)sim->accel.irec);
         cudaFree(sim->work_list); cudaFree(sim->work_count); cudaFree(sim->scan_tab);
+        if (sim->dg_exec) cudaGraphExecDestroy(sim->dg_exec);
+        if (sim->dg_stream) cudaStreamDestroy(sim->dg_stream);
         cudaFreeHost(sim->h_actions); cudaFreeHost(sim->h_obs); cudaFreeHost(sim->h_mask);
         cudaFree(sim->d_actions); cudaFree(sim->d_obs); cudaFree(sim->d_mask_in);
     }
@@ -3363,6 +3367,36 @@ extern "C" int md_step_autoreset(md_sim* sim, const float* actions_dev, float* o
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));
     StepOut out = {obs_dev, reward_dev, cost_dev, terminated_dev, truncated_dev, info_flags_dev, info_f_dev};
+    // The launch sequence of a step is fixed (counters live on the device, nothing synchronises or allocates): replay it as a
+    // CUDA graph unless the per-stage profiling events are being recorded.  The graph is captured on an internal stream (the
+    // caller's may be the legacy default stream, which cannot be captured) and re-captured when a caller pointer or anything
+    // that shapes the sequence changes.  MD_DEV_GRAPH=0 launches kernel by kernel.
+    static const int use_graph = env_int("MD_DEV_GRAPH", 1);
+    if (use_graph && !(sim->prof_n < sim->prof_cap)) {
+        const uint64_t key[12] = {(uint64_t)(uintptr_t)actions_dev, (uint64_t)(uintptr_t)obs_dev, (uint64_t)(uintptr_t)reward_dev,
+                                  (uint64_t)(uintptr_t)cost_dev, (uint64_t)(uintptr_t)terminated_dev, (uint64_t)(uintptr_t)truncated_dev,
+                                  (uint64_t)(uintptr_t)info_flags_dev, (uint64_t)(uintptr_t)info_f_dev, (uint64_t)(uintptr_t)sim->bank,
+                                  (uint64_t)(uintptr_t)sim->all.contact_tab, (uint64_t)sim->bank_seed, sim->post_valid ? 1ull : 0ull};
+        if (sim->dg_exec == nullptr || memcmp(key, sim->dg_key, sizeof(key)) != 0) {
+            if (sim->dg_exec) { cudaGraphExecDestroy(sim->dg_exec); sim->dg_exec = nullptr; }
+            if (!sim->dg_stream) CK(cudaStreamCreateWithFlags(&sim->dg_stream, cudaStreamNonBlocking));
+            const int64_t l0 = sim->launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(sim->dg_stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = step_autoreset_impl(sim, sim->all, actions_dev, out, sim->dg_stream, false);
+            const cudaError_t ce = cudaStreamEndCapture(sim->dg_stream, &graph);
+            sim->dg_launches = (int)(sim->launches - l0);
+            sim->launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            CK(ce);
+            CK(cudaGraphInstantiate(&sim->dg_exec, graph, 0));
+            CK(cudaGraphDestroy(graph));
+            memcpy(sim->dg_key, key, sizeof(key));
+        }
+        CK(cudaGraphLaunch(sim->dg_exec, (cudaStream_t)stream));
+        sim->launches += sim->dg_launches;
+        return 0;
+    }
     return step_autoreset_impl(sim, sim->all, actions_dev, out, (cudaStream_t)stream, true);
 }
 
