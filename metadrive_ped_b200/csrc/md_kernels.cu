@@ -1401,6 +1401,12 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
                 if (emit) work_list[base + __popc(em & ((1u << lane) - 1u))] = g;
             }
         }
+#ifdef MD_PHASE_CLK
+        if (g_phase_clk != nullptr && tid == 0 && blockIdx.x < CLK_CTAS) {
+            unsigned long long* row = g_phase_clk + ((size_t)1 * CLK_CTAS + blockIdx.x) * 16;
+            row[8] += 1ull; row[9] += (unsigned long long)block_any; row[10] += (unsigned long long)(n_front + n_back); row[11] += (unsigned long long)n_front;
+        }
+#endif
         le0 = le1;
         if (le0 < n_env) __syncthreads();   // the next pass reuses the list and its counters
     }

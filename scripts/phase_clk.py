@@ -76,6 +76,13 @@ for lo, hi in ((0, 32), (32, 48), (48, 64), (64, 80), (80, 200)):
     sel = (r[:, 10] >= lo) & (r[:, 10] < hi)
     if sel.any():
         print("   n_act in [%d, %d): %d CTAs, duration mean %.1f max %.1f us" % (lo, hi, sel.sum(), dur[sel].mean(), dur[sel].max()))
+r = t[1][t[1][:, 0] != 0]
+dur = (r[:, 13] - r[:, 0]) / 1965.0
+print("k_dyn (last rep): passes", {int(v): int((r[:, 8] == v).sum()) for v in np.unique(r[:, 8])}, "CTAs with contact candidates", int((r[:, 9] > 0).sum()),
+      "alive per CTA percentiles", np.percentile(r[:, 10], [10, 50, 90, 100]))
+for label, sel in (("1 pass, no candidates", (r[:, 8] == 1) & (r[:, 9] == 0)), ("1 pass, candidates", (r[:, 8] == 1) & (r[:, 9] > 0)), ("2+ passes", r[:, 8] > 1)):
+    if sel.any():
+        print("   %-24s %4d CTAs, duration mean %.1f p90 %.1f max %.1f us; active %.1f alive %.1f" % (label, sel.sum(), dur[sel].mean(), np.percentile(dur[sel], 90), dur[sel].max(), r[sel, 11].mean(), r[sel, 10].mean()))
 for k, (name, phases) in NAMES.items():
     m = np.mean([a[0] for a in acc[k]], 0) / 1965.0   # cycles -> us at 1965 MHz
     tot = np.mean([a[1] for a in acc[k]], 0) / 1965.0
