@@ -347,13 +347,22 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
     unsigned long long vlo = 0ull, vhi = 0ull;
     bool has_ped = false;
     const int n = nv.count();
-    for (int k = 0; k < n; k++) {
+    for (int k = sub; k < n; k += T) {   // the membership tests are strided over the team's lanes and ORed below
         if (!nv.valid(k)) continue;
         if (k < 64) vlo |= 1ull << k; else vhi |= 1ull << (k - 64);
         if (k >= nv.S) {
             const float* Ob = nv.obj + (k - nv.S) * OBJ_F;
             if (Ob[OB_KIND] == 3.0f || Ob[OB_LANE] < 0.0f) has_ped = true;  // no `.lane` -> except path (:254-259)
         }
+    }
+    if (T > 1) {
+        int ped = has_ped ? 1 : 0;
+        for (int off = T >> 1; off > 0; off >>= 1) {
+            vlo |= __shfl_xor_sync(team_mask, vlo, off);
+            if (n > 64) vhi |= __shfl_xor_sync(team_mask, vhi, off);
+            ped |= __shfl_xor_sync(team_mask, ped, off);
+        }
+        has_ped = ped != 0;
     }
     if (threadIdx.x == 0) clk_mark(0, 5);
     int front = OBJ_NONE;
