@@ -2736,6 +2736,7 @@ struct md_sim {
     MapAccel accel;         // grid records derived from the map tables at md_load_scene
     // md_step_autoreset as a CUDA graph (device-resident path): captured once per set of caller pointers on an internal stream
     cudaGraphExec_t dg_exec; uint64_t dg_key[12]; int dg_launches; cudaStream_t dg_stream;
+    int dg_misses, dg_hits;  // consecutive re-captures / replays: a caller that passes new buffers every step gets plain launches
     float dyn_alive;        // the scene's alive vehicles per env: sizes k_dyn's CTAs (0 = one thread per slot row)
     md_sim* bank;           // scenario bank (md_attach_bank): finished envs restart as a scenario drawn from it
     uint32_t bank_seed;
@@ -3387,12 +3388,15 @@ extern "C" int md_step_autoreset(md_sim* sim, const float* actions_dev, float* o
     // caller's may be the legacy default stream, which cannot be captured) and re-captured when a caller pointer or anything
     // that shapes the sequence changes.  MD_DEV_GRAPH=0 launches kernel by kernel.
     static const int use_graph = env_int("MD_DEV_GRAPH", 1);
-    if (use_graph && !(sim->prof_n < sim->prof_cap)) {
+    if (use_graph && !(sim->prof_n < sim->prof_cap) && sim->dg_misses < 4) {
         const uint64_t key[12] = {(uint64_t)(uintptr_t)actions_dev, (uint64_t)(uintptr_t)obs_dev, (uint64_t)(uintptr_t)reward_dev,
                                   (uint64_t)(uintptr_t)cost_dev, (uint64_t)(uintptr_t)terminated_dev, (uint64_t)(uintptr_t)truncated_dev,
                                   (uint64_t)(uintptr_t)info_flags_dev, (uint64_t)(uintptr_t)info_f_dev, (uint64_t)(uintptr_t)sim->bank,
                                   (uint64_t)(uintptr_t)sim->all.contact_tab, (uint64_t)sim->bank_seed, sim->post_valid ? 1ull : 0ull};
         if (sim->dg_exec == nullptr || memcmp(key, sim->dg_key, sizeof(key)) != 0) {
+            // a capture costs ~100 us: worth it only if the same buffers come back.  Four re-captures without a replay in
+            // between (a caller that allocates its action tensor anew every step) switch the handle to plain launches.
+            if (sim->dg_exec) { sim->dg_misses = sim->dg_hits > 0 ? 1 : sim->dg_misses + 1; sim->dg_hits = 0; }
             if (sim->dg_exec) { cudaGraphExecDestroy(sim->dg_exec); sim->dg_exec = nullptr; }
             if (!sim->dg_stream) CK(cudaStreamCreateWithFlags(&sim->dg_stream, cudaStreamNonBlocking));
             const int64_t l0 = sim->launches;
@@ -3408,6 +3412,7 @@ extern "C" int md_step_autoreset(md_sim* sim, const float* actions_dev, float* o
             CK(cudaGraphDestroy(graph));
             memcpy(sim->dg_key, key, sizeof(key));
         }
+        else sim->dg_hits++;
         CK(cudaGraphLaunch(sim->dg_exec, (cudaStream_t)stream));
         sim->launches += sim->dg_launches;
         return 0;
