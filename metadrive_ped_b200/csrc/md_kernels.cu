@@ -95,6 +95,9 @@ struct __align__(16) Nb {
     int lane, alive, active, kind;
 };
 
+// entries of an IDM team's neighbour table (see pre_team_size)
+#define PRE_NB_CAP 32
+__host__ __device__ inline int pre_nb_cap(int S, int O) { return S + O < PRE_NB_CAP ? S + O : PRE_NB_CAP; }
 struct FrontBack { int fobj[3], bobj[3]; float fdist[3], bdist[3]; bool exists[3]; };
 #define OBJ_NONE (-1)
 
@@ -176,7 +179,7 @@ __device__ void find_front_back(const MapView& m, const NbrView& nv, unsigned lo
 // then runs the ordered folds over it redundantly - all lanes of the team end with the same, exact result.
 // An object's longitude is taken on ITS OWN lane whichever of the three lanes is being searched (on the lane itself the
 // two coincide), so the table is filled ONCE for the three searches: one lane-row fetch and one lane_local per object.
-//   scratch[k] = (codes, longitude of object k on its own lane); codes = 3 bits per searched lane i (<< 3 i): bit 0 the
+//   scratch[ord] = (codes, longitude on its own lane) of the ord-th valid neighbour; codes = 3 bits per searched lane i (<< 3 i): bit 0 the
 //   object is on lane i, bit 1 lane i is the previous of its lane, bit 2 its lane is the previous of lane i
 __device__ void find_front_back_team(const MapView& m, const NbrView& nv, unsigned long long valid_lo, unsigned long long valid_hi,
                                      int lane, float px, float py, float max_d, bool use_ref, int ref_first, int ref_n,
@@ -228,7 +231,7 @@ __device__ void find_front_back_team(const MapView& m, const NbrView& nv, unsign
                 if (codes) { float lon, lt; lane_local(Lo, ox, oy, lon, lt); rec.y = lon; }
                 rec.x = (float)codes;
             }
-            scratch[k] = rec;
+            scratch[ord] = rec;
         }
     __syncwarp(team_mask);
     // the ordered folds (policy/idm_policy.py:100-131), identical on every lane
@@ -236,10 +239,11 @@ __device__ void find_front_back_team(const MapView& m, const NbrView& nv, unsign
     for (int i = 0; i < 3; i++) {
         if (lanes[i] < 0) continue;
         bool ffound = false, bfound = false;
+        int o2 = 0;
         for (int half = 0; half < 2; half++)
-            for (unsigned long long mk = half ? valid_hi : valid_lo; mk; mk &= mk - 1) {
+            for (unsigned long long mk = half ? valid_hi : valid_lo; mk; mk &= mk - 1, o2++) {
                 const int k = __ffsll((long long)mk) - 1 + 64 * half;
-                const float2 rec = scratch[k];
+                const float2 rec = scratch[o2];
                 const int code = ((int)rec.x >> (3 * i)) & 7;
                 float lon = rec.y;
                 if (code & 1) {
@@ -365,6 +369,8 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
         has_ped = ped != 0;
     }
     if (threadIdx.x == 0) clk_mark(0, 5);
+    // the team's table holds PRE_NB_CAP neighbours; with more in range every lane runs the serial search (same result)
+    const bool team_ok = T > 1 && __popcll(vlo) + __popcll(vhi) <= pre_nb_cap(nv.S, nv.O);
     int front = OBJ_NONE;
     float front_dist = 0.0f;
     int steer_lane = rt;
@@ -372,7 +378,7 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
     if (has_ped) {
         front = OBJ_NONE; front_dist = 5.0f; steer_lane = rt;
     } else if (success && cfg.enable_idm_lane_change) {
-        if (T > 1) find_front_back_team(m, nv, vlo, vhi, rt, px, py, 30.0f, true, cur_first, cur_n, fb, sub, T, team_mask, scratch);
+        if (team_ok) find_front_back_team(m, nv, vlo, vhi, rt, px, py, 30.0f, true, cur_first, cur_n, fb, sub, T, team_mask, scratch);
         else find_front_back(m, nv, vlo, vhi, rt, px, py, 30.0f, true, cur_first, cur_n, fb);
         int next_n = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_N] : 0;
         int next_first = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_FIRST] : -1;
@@ -427,7 +433,7 @@ __device__ void idm_act(const MdConfig& cfg, const MapView& m, const NbrView& nv
             }
         }
     } else {
-        if (T > 1) find_front_back_team(m, nv, vlo, vhi, rt, px, py, 30.0f, false, 0, 0, fb, sub, T, team_mask, scratch);
+        if (team_ok) find_front_back_team(m, nv, vlo, vhi, rt, px, py, 30.0f, false, 0, 0, fb, sub, T, team_mask, scratch);
         else find_front_back(m, nv, vlo, vhi, rt, px, py, 30.0f, false, 0, 0, fb);
         front = fb.fobj[1]; front_dist = fb.fdist[1]; steer_lane = rt;
     }
@@ -969,18 +975,25 @@ __device__ __forceinline__ void stage_objects(const StepGeom& G, const float* __
 #endif
 #define PRE_TEAM 4                    // lanes per vehicle in the IDM phase
 #define PRE_TEAM_SCRATCH (32 * 1024)  // the teams' tables (one float2 per neighbour index and team) must fit this
+// k_pre stages the envs' object rows in shared memory only while they are few: a SafeMetaDriveEnv CTA (16 envs x 60 obstacles)
+// would carry 46 KB of them and fit twice per SM - a second wave for half the CTAs - where the IDM reads a handful of fields
+// per object, which the read-only cache serves as well
+__host__ __device__ inline bool pre_stage_objs(int O, int epb) { return sizeof(float) * OBJ_F * (size_t)O * epb <= 16 * 1024; }
 __host__ __device__ inline size_t pre_base_bytes(int S, int O, int epb) {   // Nb rows | objects | list | counters | active list
-    size_t b = (sizeof(Nb) + 2 * sizeof(int)) * (size_t)S * epb + sizeof(float) * OBJ_F * (size_t)O * epb + 32;
+    size_t b = (sizeof(Nb) + 2 * sizeof(int)) * (size_t)S * epb + (pre_stage_objs(O, epb) ? sizeof(float) * OBJ_F * (size_t)O * epb : 0) + 32;
     return (b + 15) & ~(size_t)15;
 }
 // the teams' tables are sized for 2-lane teams (threads / 2 of them): a CTA with more active vehicles than 4-lane teams
 // halves the team size instead of dropping to one thread per vehicle (which made that CTA the kernel's tail)
+// A team's table has one entry per VALID neighbour (the bodies within 50 m), in their order - not one per slot / object of
+// the env: a SafeMetaDriveEnv scene holds 60 obstacles and a pedestrian scene 16 more bodies, of which a vehicle sees a few.
+// PRE_NB_CAP entries per team; a vehicle with more valid neighbours runs the search on one lane (idm_act).
 __host__ __device__ inline int pre_team_size(int S, int O, int threads) {
-    return sizeof(float2) * (size_t)(S + O) * (threads / 2) <= PRE_TEAM_SCRATCH ? PRE_TEAM : 1;
+    return sizeof(float2) * (size_t)pre_nb_cap(S, O) * (threads / 2) <= PRE_TEAM_SCRATCH ? PRE_TEAM : 1;
 }
 __host__ __device__ inline size_t pre_smem_bytes(int S, int O, int epb, int threads) {
     const int T = pre_team_size(S, O, threads);
-    return pre_base_bytes(S, O, epb) + (T > 1 ? sizeof(float2) * (size_t)(S + O) * (threads / 2) : 0);
+    return pre_base_bytes(S, O, epb) + (T > 1 ? sizeof(float2) * (size_t)pre_nb_cap(S, O) * (threads / 2) : 0);
 }
 __global__ void __maxnreg__(PRE_REGS)
 k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ actions, float* __restrict__ idm_out,
@@ -994,8 +1007,9 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
     const int S = cfg.slots_per_env, O = cfg.objs_per_env, NA = cfg.agents_per_env;
     const int n_rows = epb * S, env0 = blockIdx.x * epb;
     Nb* nb_all = reinterpret_cast<Nb*>(smem_raw);
+    const bool stage_objs = pre_stage_objs(O, epb);
     float* obj_all = reinterpret_cast<float*>(smem_raw + sizeof(Nb) * (size_t)n_rows);
-    int* list = reinterpret_cast<int*>(smem_raw + sizeof(Nb) * (size_t)n_rows + sizeof(float) * OBJ_F * (size_t)O * epb);
+    int* list = reinterpret_cast<int*>(smem_raw + sizeof(Nb) * (size_t)n_rows + (stage_objs ? sizeof(float) * OBJ_F * (size_t)O * epb : 0));
     int* n_list = list + n_rows;
     if (threadIdx.x == 0) *n_list = 0;
     clk_mark(0, 0);
@@ -1049,10 +1063,11 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         } else veh_act[g] = idle;
         if (dirty_i) store16i(A.veh_i + g * VEH_I, I);
     }
-    for (int k = threadIdx.x; k < epb * O * OBJ_F; k += blockDim.x) {
-        const int env = env0 + k / (O * OBJ_F);
-        if (env < cfg.n_envs) obj_all[k] = A.obj_f[(size_t)env0 * O * OBJ_F + k];
-    }
+    if (stage_objs)
+        for (int k = threadIdx.x; k < epb * O * OBJ_F; k += blockDim.x) {
+            const int env = env0 + k / (O * OBJ_F);
+            if (env < cfg.n_envs) obj_all[k] = A.obj_f[(size_t)env0 * O * OBJ_F + k];
+        }
     __syncthreads();
     clk_mark(0, 1);
     // ---- PGTrafficManager.before_step: trigger (manager/traffic_manager.py:74-88), one thread per env
@@ -1107,7 +1122,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
 #endif
     const int sub = threadIdx.x & (T - 1), team = threadIdx.x / T, n_teams = blockDim.x / T;
     const unsigned team_mask = T > 1 ? (((1u << T) - 1u) << ((threadIdx.x & 31) & ~(T - 1))) : 0u;
-    float2* scratch = reinterpret_cast<float2*>(smem_raw + pre_base_bytes(S, O, epb)) + (size_t)team * (S + O);
+    float2* scratch = reinterpret_cast<float2*>(smem_raw + pre_base_bytes(S, O, epb)) + (size_t)team * pre_nb_cap(S, O);
     for (int j = team; j < n_act; j += n_teams) {
         const int v = alist[j];
         const int le = v / S, slot = v - le * S, env = env0 + le;
@@ -1124,7 +1139,8 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         I[VI_ACTIVE] = 1;  // possibly triggered just now
         const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
         NbrView nv;
-        nv.nb = nb_all + (size_t)le * S; nv.obj = obj_all + (size_t)le * O * OBJ_F; nv.S = S; nv.O = O; nv.self = slot;
+        nv.nb = nb_all + (size_t)le * S; nv.S = S; nv.O = O; nv.self = slot;
+        nv.obj = stage_objs ? obj_all + (size_t)le * O * OBJ_F : A.obj_f + (size_t)env * O * OBJ_F;
         nv.px = St[VS_POS]; nv.py = St[VS_POS + 1];
         float a0, a1;
         idm_act(cfg, m, nv, (int)g + cfg.env_base * S, St, I, D, A.veh_rroad + g * ROUTE_MAX, a0, a1, sub, T, team_mask, scratch);
