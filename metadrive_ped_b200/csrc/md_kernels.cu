@@ -1015,9 +1015,14 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
     clk_mark(0, 0);
     __syncthreads();
     const float4 idle = make_float4(0.0f, 0.0f, 2.0f, 0.0f);  // what vehicle.reset() leaves (base_vehicle.py:376): brake 2
-    // ---- phase 1
-    for (int v = threadIdx.x; v < n_rows; v += blockDim.x) {
-        const int le = v / S, slot = v - le * S, env = env0 + le;
+    // ---- phase 1.  The rows are visited agents first (they take the long path: latches, actuation, two more rows), so that
+    // the threads' first pass holds all of them and a second pass only short traffic rows.
+    const int n_agent_rows = epb * NA;
+    for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
+        int le, slot;
+        if (i < n_agent_rows) { le = i / NA; slot = i - le * NA; }
+        else { const int j = i - n_agent_rows; le = j / (S - NA); slot = NA + (j - le * (S - NA)); }
+        const int v = le * S + slot, env = env0 + le;
         Nb& n = nb_all[v];
         n.alive = 0; n.active = 0; n.kind = 0; n.lane = -1;
         if (env >= cfg.n_envs) continue;
