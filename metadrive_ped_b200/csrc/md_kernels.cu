@@ -983,6 +983,9 @@ __host__ __device__ inline size_t pre_base_bytes(int S, int O, int epb) {   // N
     size_t b = (sizeof(Nb) + 2 * sizeof(int)) * (size_t)S * epb + (pre_stage_objs(O, epb) ? sizeof(float) * OBJ_F * (size_t)O * epb : 0) + 32;
     return (b + 15) & ~(size_t)15;
 }
+// ... followed by one MapView per env (the map's table pointers, read by every IDM team of the env: without it each team
+// chases env row -> map descriptor -> tables itself, two dependent round trips) and then the teams' neighbour tables
+__host__ __device__ inline size_t pre_views_bytes(int epb) { return (sizeof(MapView) * (size_t)epb + 15) & ~(size_t)15; }
 // the teams' tables are sized for 2-lane teams (threads / 2 of them): a CTA with more active vehicles than 4-lane teams
 // halves the team size instead of dropping to one thread per vehicle (which made that CTA the kernel's tail)
 // A team's table has one entry per VALID neighbour (the bodies within 50 m), in their order - not one per slot / object of
@@ -993,7 +996,7 @@ __host__ __device__ inline int pre_team_size(int S, int O, int threads) {
 }
 __host__ __device__ inline size_t pre_smem_bytes(int S, int O, int epb, int threads) {
     const int T = pre_team_size(S, O, threads);
-    return pre_base_bytes(S, O, epb) + (T > 1 ? sizeof(float2) * (size_t)pre_nb_cap(S, O) * (threads / 2) : 0);
+    return pre_base_bytes(S, O, epb) + pre_views_bytes(epb) + (T > 1 ? sizeof(float2) * (size_t)pre_nb_cap(S, O) * (threads / 2) : 0);
 }
 __global__ void __maxnreg__(PRE_REGS)
 k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ actions, float* __restrict__ idm_out,
@@ -1017,6 +1020,9 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
     const float4 idle = make_float4(0.0f, 0.0f, 2.0f, 0.0f);  // what vehicle.reset() leaves (base_vehicle.py:376): brake 2
     // ---- phase 1.  The rows are visited agents first (they take the long path: latches, actuation, two more rows), so that
     // the threads' first pass holds all of them and a second pass only short traffic rows.
+    MapView* mv_all = reinterpret_cast<MapView*>(smem_raw + pre_base_bytes(S, O, epb));
+    if ((int)threadIdx.x < epb && env0 + (int)threadIdx.x < cfg.n_envs)
+        mv_all[threadIdx.x] = map_view(A, A.env_i[(env0 + threadIdx.x) * ENV_I + EI_MAP]);
     const int n_agent_rows = epb * NA;
     for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
         int le, slot;
@@ -1083,7 +1089,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         if ((mode & MODE_TRIGGER) && cfg.traffic_mode != 1) {
             int nt = A.env_i[env * ENV_I + EI_NEXT_TRIGGER];
             if (nt > 0) {
-                const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+                const MapView& m = mv_all[le];
                 const int n_blocks = A.env_i[env * ENV_I + EI_N_BLOCKS];
                 for (int s = 0; s < NA && nt > 0; s++) {
                     if (!nb[s].active || nb[s].kind != 1) continue;
@@ -1127,7 +1133,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
 #endif
     const int sub = threadIdx.x & (T - 1), team = threadIdx.x / T, n_teams = blockDim.x / T;
     const unsigned team_mask = T > 1 ? (((1u << T) - 1u) << ((threadIdx.x & 31) & ~(T - 1))) : 0u;
-    float2* scratch = reinterpret_cast<float2*>(smem_raw + pre_base_bytes(S, O, epb)) + (size_t)team * pre_nb_cap(S, O);
+    float2* scratch = reinterpret_cast<float2*>(smem_raw + pre_base_bytes(S, O, epb) + pre_views_bytes(epb)) + (size_t)team * pre_nb_cap(S, O);
     for (int j = team; j < n_act; j += n_teams) {
         const int v = alist[j];
         const int le = v / S, slot = v - le * S, env = env0 + le;
@@ -1142,7 +1148,7 @@ k_pre(MdConfig cfg, MdArrays A, int mode, int epb, const float* __restrict__ act
         const float4 d0 = d4[0], d1 = d4[1];
         D[0] = d0.x; D[1] = d0.y; D[2] = d0.z; D[3] = d0.w; D[4] = d1.x; D[5] = d1.y; D[6] = d1.z; D[7] = d1.w;
         I[VI_ACTIVE] = 1;  // possibly triggered just now
-        const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+        const MapView m = mv_all[le];
         NbrView nv;
         nv.nb = nb_all + (size_t)le * S; nv.S = S; nv.O = O; nv.self = slot;
         nv.obj = stage_objs ? obj_all + (size_t)le * O * OBJ_F : A.obj_f + (size_t)env * O * OBJ_F;
