@@ -1999,7 +1999,9 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         const int env_step = A.env_i[env * ENV_I + EI_STEP];
         const int* rroad = A.veh_rroad + g * ROUTE_MAX;
         if (mode & MODE_CLEAR_FLAGS) I[VI_FLAGS] = FL_ON_LANE;
+        if (j == 0 && St[0] > -1e30f && C[0] > -1e30f && I[0] > -1000 && navi[0] > -1e30f) clk_mark(2, 8);
         after_step_vehicle(m, St, C, I, A.veh_route + g * ROUTE_MAX, rroad, navi, fp, sobj, S, O, slot, fp[slot].r, use_teams ? scan + j : nullptr);
+        if (j == 0 && I[VI_FLAGS] > -1 && C[VC_ENERGY] > -1e30f) clk_mark(2, 9);
         if ((mode & MODE_RESET) && !I[VI_ACTIVE]) I[VI_FLAGS] = FL_ON_LANE;  // reset() ends with _init_step_info
         // traffic_manager.after_step: off-lane traffic leaves the world (manager/traffic_manager.py:94-111); in respawn /
         // hybrid mode phase 3 brings it back as a new vehicle
@@ -2025,6 +2027,12 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
                 }
             }
         }
+#ifdef MD_PHASE_CLK
+        if (j == 0) {
+            clk_mark(2, 10);
+            if (g_phase_clk != nullptr && blockIdx.x < CLK_CTAS) g_phase_clk[((size_t)2 * CLK_CTAS + blockIdx.x) * 16 + 14] = is_agent ? 1ull : 0ull;
+        }
+#endif
         if ((mode & MODE_MARK_DONE) && is_agent && slot == 0) {
             const size_t a = (size_t)env * NA;
             done_mask[env] = (out.term[a] || out.trunc[a]) ? 1 : 0;
@@ -2034,6 +2042,7 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
 #pragma unroll
         for (int k = 0; k < NAVI_DIM; k++) A.veh_navi[g * NAVI_DIM + k] = navi[k];
         write_body_row(body_tab + g * BODY_ROW, P, St, alive_row);
+        if (j == 0) clk_mark(2, 11);
     }
 #ifdef MD_PHASE_CLK
     __syncthreads();

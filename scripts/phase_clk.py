@@ -76,6 +76,14 @@ for lo, hi in ((0, 32), (32, 48), (48, 64), (64, 80), (80, 200)):
     sel = (r[:, 10] >= lo) & (r[:, 10] < hi)
     if sel.any():
         print("   n_act in [%d, %d): %d CTAs, duration mean %.1f max %.1f us" % (lo, hi, sel.sum(), dur[sel].mean(), dur[sel].max()))
+r = t[2][t[2][:, 8] != 0]
+if len(r):
+    for role, sel in (("agent", r[:, 14] == 1), ("traffic", r[:, 14] == 0)):
+        if sel.any():
+            q = r[sel]
+            print("k_post phase 2, thread 0's vehicle = %s (%d CTAs): rows loaded %.1f us after the phase began, after_step %.1f, outputs %.1f, stores %.1f" % (
+                role, sel.sum(), ((q[:, 8] - q[:, 3]) / 1965.0).mean(), ((q[:, 9] - q[:, 8]) / 1965.0).mean(), ((q[:, 10] - q[:, 9]) / 1965.0).mean(),
+                ((q[:, 11] - q[:, 10]) / 1965.0).mean()))
 r = t[1][t[1][:, 0] != 0]
 dur = (r[:, 13] - r[:, 0]) / 1965.0
 print("k_dyn (last rep): passes", {int(v): int((r[:, 8] == v).sum()) for v in np.unique(r[:, 8])}, "CTAs with contact candidates", int((r[:, 9] > 0).sum()),
