@@ -783,17 +783,23 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
     float speed_kmh = sqrtf(S[VS_VEL] * S[VS_VEL] + S[VS_VEL + 1] * S[VS_VEL + 1]) * 3.6f;
     int flags = I[VI_FLAGS];
     int c0 = I[VI_CKPT0], n_ck = I[VI_ROUTE_LEN];
-    int cur_road = rroad[c0];
-    int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+    // the two road chains (current road, final road of the route) are independent: their loads are issued side by side, so
+    // that the thread waits for one round trip per level instead of walking one chain after the other
+    const int cur_road = rroad[c0];
+    const int final_road = rroad[n_ck - 2];
+    const int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+    const int final_lane = m.road_i[final_road * ROAD_I + RI_FIRST] + m.road_i[final_road * ROAD_I + RI_N] - 1;
+    const int road_neg = m.road_i[cur_road * ROAD_I + RI_NEG];
     int lane = I[VI_LANE];
     float lane_w = m.lane_f[lane * LANE_F + LF_WIDTH];
+    const float fl_len = m.lane_f[final_lane * LANE_F + LF_LENGTH];
     if (write_scalars) {
         I[VI_EP_LEN] += 1;
         int rl = lane;
         float positive = 1.0f;
         if (!(lane >= cur_first && lane < cur_first + cur_n)) {
             rl = cur_first;
-            positive = (m.road_i[cur_road * ROAD_I + RI_NEG] && !cfg.ignore_road_sign) ? -1.0f : 1.0f;
+            positive = (road_neg && !cfg.ignore_road_sign) ? -1.0f : 1.0f;
         }
         float long_last, long_now, lat_now, tmp;
         lane_local(m.lane_f + rl * LANE_F, C[VC_LAST_X], C[VC_LAST_Y], long_last, tmp);
@@ -803,11 +809,8 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         rew += cfg.driving_reward * (long_now - long_last) * lateral_factor * positive;
         rew += cfg.speed_reward * (speed_kmh / P[VP_MAX_SPEED]) * positive;
         float step_reward = rew;
-        int final_road = rroad[n_ck - 2];
-        int final_lane = m.road_i[final_road * ROAD_I + RI_FIRST] + m.road_i[final_road * ROAD_I + RI_N] - 1;
         float fl_long, fl_lat;
         lane_local(m.lane_f + final_lane * LANE_F, px, py, fl_long, fl_lat);
-        float fl_len = m.lane_f[final_lane * LANE_F + LF_LENGTH];
         bool arrive = (fl_len - 5.0f < fl_long && fl_long < fl_len + 5.0f) &&
                       (lane_w / 2.0f >= fl_lat && fl_lat >= (0.5f - (float)cur_n) * lane_w);
         bool outr = !(flags & FL_ON_LANE);
