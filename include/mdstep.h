@@ -66,7 +66,10 @@ int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward
 int md_autoreset(md_sim* sim, const uint8_t* terminated_dev, const uint8_t* truncated_dev, float* obs_dev, void* stream);
 /* md_step + md_autoreset in one call.  Single-agent worlds take a fused path: k_post marks the finished envs, one more
  * launch restores and re-localises them, and the lidar observes the post-reset world once (the reward / cost / done /
- * info outputs keep the finished step's values, the observation rows of finished envs hold the reset observation). */
+ * info outputs keep the finished step's values, the observation rows of finished envs hold the reset observation).
+ * The launch sequence of a step is fixed (every counter lives on the device), so the call replays it as a CUDA graph while
+ * the caller passes the same buffers (captured on an internal stream, launched into `stream`, which may be the legacy
+ * default stream); buffers that change every step switch the handle back to plain launches.  MD_DEV_GRAPH=0 disables it. */
 int md_step_autoreset(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,
                       uint8_t* terminated_dev, uint8_t* truncated_dev, int32_t* info_flags_dev, float* info_f_dev, void* stream);
 
