@@ -324,6 +324,9 @@ def populate(big, seed, traffic_density=0.1, traffic_mode="trigger", accident_pr
     sp = Spawner(big, seed, lane_num, lane_width)
     if random_traffic:   # PGTrafficManager.seed skips the re-seeding (traffic_manager.py:323-325): an unseeded stream
         sp.traffic_rng = np.random.RandomState()
+    for blk in big.blocks:   # the map is built first: every TollGateBuilding a TollGate block spawns takes a seed from the
+        for _ in getattr(blk, "buildings", ()):   # engine's stream (pgblock/tollgate.py:64-76, engine/base_engine.py:123-135)
+            sp.engine_seed()
     sp.accidents(accident_prob, include_breakdown)
     n_obj_vehicles = len(sp.static)
     sp.ego(random_spawn_lane, random_agent_model, agent_model)

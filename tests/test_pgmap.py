@@ -52,6 +52,30 @@ def test_generator_reproduces_the_reference_libraries(name, spec, kw, n):
         assert seen_blocks == set("ISCrRXTO"), seen_blocks
 
 
+@pytest.mark.parametrize("name,spec", [("lib_yY.npz", "yY"), ("lib_SyYC.npz", "SyYC"), ("lib_StollC.npz", "S$C")])
+def test_generator_reproduces_maps_with_bottleneck_and_tollgate_blocks(name, spec):
+    """Merge ("y"), Split ("Y") and TollGate ("$") blocks inside BIG-generated maps (map="SyYC" ...): 8 scenarios each exported
+    from the reference (oracle/gen_assets.py --map).  Lane tables bit for bit; rosters identical - which, for the tollgate map,
+    requires the seed every TollGateBuilding draws from the engine's stream when the block is built."""
+    lib = ScenarioLibrary(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "libs", name))
+    for i in range(len(lib)):
+        seed = int(lib.seeds[i])
+        lane_f, lane_i, road_i, meta, _ = lib._map_args(i)
+        g_f, g_i, g_r, g_meta, big = pgmap.generate(seed, spec)
+        assert "".join(b["id"] for b in meta["blocks"]) == "".join(b.ID for b in big.blocks) == "I" + spec
+        np.testing.assert_array_equal(lane_f, g_f)
+        np.testing.assert_array_equal(lane_i, g_i)
+        np.testing.assert_array_equal(road_i, g_r)
+        ref = lib.scenario(i, 0)
+        got = pgspawn.populate(big, seed, traffic_density=0.1, traffic_mode="trigger", accident_prob=0.0)
+        for field in ("veh_static", "routes", "veh_int", "idm"):
+            np.testing.assert_array_equal(getattr(ref, field), getattr(got, field), err_msg="%s of seed %d" % (field, seed))
+        np.testing.assert_allclose(ref.veh_dyn, got.veh_dyn, rtol=0, atol=1e-12)
+    if "$" in spec:
+        with pytest.raises(NotImplementedError):
+            GeneratedLibrary(0, 1, map=spec)
+
+
 def test_generated_world_equals_exported_world():
     """What the device receives: scene.pack over generated scenarios == scene.pack over the exported ones, every array."""
     gen = GeneratedLibrary(0, 16)
