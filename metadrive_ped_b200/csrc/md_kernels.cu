@@ -3110,11 +3110,10 @@ static StepLaunch step_launch(const MdConfig& c, int epb_pref) {
 }
 static int epb_pre() { static int v = env_int("MD_EPB_PRE", PRE_EPB); return v; }
 static int epb_post() { static int v = env_int("MD_EPB_POST", POST_EPB); return v; }
-static int epb_dyn() { static int v = env_int("MD_EPB_DYN", DYN_EPB); return v; }
 // k_dyn appends the compacted list of alive vehicles to the shared tables and runs `threads_pref` threads per CTA: about as
 // many as its envs hold alive vehicles (md_load_scene sizes it from the scene; MD_DYN_THREADS overrides; 0 = one per slot row)
-static StepLaunch dyn_launch(const MdConfig& c, float alive_per_env) {
-    StepLaunch L = step_launch(c, epb_dyn());
+static StepLaunch dyn_launch_epb(const MdConfig& c, float alive_per_env, int epb) {
+    StepLaunch L = step_launch(c, epb);
     static const int forced = env_int("MD_DYN_THREADS", -1);
     int t = forced >= 0 ? forced : (int)(1.25f * alive_per_env * (float)L.epb + 0.999f);
     if (t > 0) {
@@ -3125,6 +3124,21 @@ static StepLaunch dyn_launch(const MdConfig& c, float alive_per_env) {
     L.smem += sizeof(CBody) * (size_t)L.epb * c.slots_per_env + dyn_list_bytes(c.slots_per_env, L.epb);
     L.smem = ((L.smem + 15) & ~(size_t)15) + 16 * (size_t)L.epb * c.slots_per_env;   // contact export words
     return L;
+}
+// envs per CTA of k_dyn: 16 when such CTAs (6 warps at BASELINE cfg2) still fit the SMs in ONE wave - fewer half-empty warps
+// and barriers than 8-env CTAs of 3 warps (0.095 -> 0.090 ms at cfg2) - else 8 (scenes with many objects are limited by
+// shared memory, multi-agent scenes by registers: measured slower with 16).  MD_EPB_DYN overrides.
+static StepLaunch dyn_launch(const MdConfig& c, float alive_per_env) {
+    static const int forced = env_int("MD_EPB_DYN", 0);
+    if (forced > 0) return dyn_launch_epb(c, alive_per_env, forced);
+    const StepLaunch L16 = dyn_launch_epb(c, alive_per_env, 2 * DYN_EPB);
+    if (L16.epb == 2 * DYN_EPB && L16.threads <= 192 && L16.smem <= 48 * 1024) {
+        const int by_regs = 65536 / (L16.threads * DYN_REGS), by_smem = (int)((228 * 1024) / (L16.smem + 1024));
+        const int per_sm = by_regs < by_smem ? by_regs : by_smem;
+        static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+        if (L16.blocks <= sms * per_sm) return L16;
+    }
+    return dyn_launch_epb(c, alive_per_env, DYN_EPB);
 }
 static StepLaunch pre_launch(const MdConfig& c) {  // k_pre: epb envs per CTA, a fixed number of worker threads
     StepLaunch L;
