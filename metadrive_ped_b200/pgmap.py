@@ -366,7 +366,7 @@ def crosses(net, lane, factor=0, ignored=None):
 
 
 # ---------------------------------------------------------------------------------------------- road construction
-def bend_then_straight(prev, follow_len, radius, angle, clockwise=True, width=3.5, line_types=None, speed_limit=20):
+def bend_then_straight(prev, follow_len, radius, angle, clockwise=True, width=3.5, line_types=(L_BROKEN, L_BROKEN), speed_limit=20):
     """create_bend_straight (create_pg_block_utils.py:19-48)"""
     sign = 1 if clockwise else -1
     center = prev.position(prev.length, sign * radius)
@@ -473,6 +473,22 @@ def adverse_road(road, block_net, world_net, ignore=None, center_line=None, side
                    inner_line=inner_line, center_line=center_line, center_color=center_color, kind=kind)
     block_net.lanes(road)[0].line_colors = (center_color, GREY)
     return ok
+
+
+def two_way_road(road, block_net, world_net, new_road, center_line=None, side_line=None, inner_line=None):
+    """CreateTwoWayRoad (create_pg_block_utils.py:284-349): a road in the reverse direction lying ON `road` (named `new_road`)"""
+    lanes = block_net.lanes(road)
+    ref = lanes[-1]
+    num = len(lanes)
+    w = ref.width_at(0)
+    if isinstance(ref, SLane):
+        sym = SLane(ref.position(lanes[-1].length, -(num - 1) * w), ref.position(0, -(num - 1) * w), w, lanes[-1].line_types,
+                    ref.speed_limit)
+    else:
+        cw = not ref.clockwise
+        radius = ref.radius + (num - 1) * w if not cw else ref.radius - (num - 1) * w
+        sym = CLane(ref.center, radius, ref.end_phase, ref.angle, cw, w, ref.line_types, ref.speed_limit)
+    return road_from(sym, num, new_road, block_net, world_net, side_line=side_line, inner_line=inner_line, center_line=center_line)
 
 
 def wave_lanes(prev, lateral, wave_len, last_len, width, toward_left=True):
@@ -1132,11 +1148,105 @@ class TollGate(Block):
         return ok
 
 
+class ParkingLot(Block):
+    """pgblock/parking_lot.py: a one-lane two-way street with `one_side_vehicle_number` parking spaces on either side; every
+    space is reached by a right-angle bend from either direction and left by one towards either direction"""
+    ID = "P"
+    SPACE = {"one_side_vehicle_number": disc(2, 10), "radius": const(4), "length": const(8)}
+    ANGLE = np.deg2rad(90)
+    SOCKET_LENGTH = 4
+
+    def plug(self):
+        c = self.cfg
+        assert self.n_pos == 1, "Lane number of previous block must be 1 in each direction"
+        self.parking_spawn_roads, self.dest_roads = [], []
+        self.space_len, self.space_w = c["length"], self.lane_width
+        n, radius = int(c["one_side_vehicle_number"]), c["radius"]
+        kw = dict(center_line=L_BROKEN, inner_line=L_BROKEN)
+        main = extend_straight(self.pos_lanes[0], 2 * radius + (n - 1) * self.space_w, [L_BROKEN, L_NONE])
+        road = (self.pre_socket.positive[1], self.node(0, 0))
+        ok = road_from(main, self.n_pos, road, self.net, self.world, side_line=L_NONE, center_color=GREY, **kw)
+        ok = adverse_road(road, self.net, self.world, side_line=L_NONE, center_color=GREY, **kw) and ok
+        out_lane = extend_straight(main, self.SOCKET_LENGTH, [L_BROKEN, L_NONE])
+        out_road = (self.node(0, 0), self.node(0, 1))
+        ok = road_from(out_lane, self.n_pos, out_road, self.net, self.world, side_line=L_SIDE, **kw) and ok
+        ok = adverse_road(out_road, self.net, self.world, side_line=L_SIDE, **kw) and ok
+        self.add_socket(self.socket_from(out_road))
+        mine, pre = self.get_socket(0), self.pre_socket
+        rev = lambda s: Socket(s.negative, s.positive)
+        for i in range(n):
+            ok = self._space(rev(mine), rev(pre), i + 1, radius, i * self.space_w, (n - i - 1) * self.space_w) and ok
+        for i in range(n):
+            ok = self._space(pre, mine, n + i + 1, radius, i * self.space_w, (n - i - 1) * self.space_w) and ok
+        return ok
+
+    def _from_world(self, sock):
+        pre = self.pre_socket
+        return (sock.positive, sock.negative) in ((pre.positive, pre.negative), (pre.negative, pre.positive))
+
+    def _space(self, in_socket, out_socket, part, radius, dist_in, dist_out):
+        """_add_one_parking_space (parking_lot.py:115-332)"""
+        ok = True
+        none = dict(center_line=L_NONE, inner_line=L_NONE, side_line=L_NONE)
+        node = lambda k: self.node(part, k)
+        one = lambda lane, road, **k: road_from(lane, self.n_pos, road, self.net, self.world, **k)
+        net = self.world if self._from_world(in_socket) else self.net
+        in_lane = net.lanes(in_socket.positive)[0]
+        start = in_socket.positive[1]
+        if dist_in > 1e-3:
+            in_lane = extend_straight(in_lane, dist_in, [L_NONE, L_NONE])
+            one(in_lane, (in_socket.positive[1], node(0)), **none)
+            start = node(0)
+        side = L_SIDE if dist_in < 1e-3 else L_NONE
+        bend, straight = bend_then_straight(in_lane, self.space_len, radius, self.ANGLE, True, self.space_w)
+        bend_ok = one(bend, (start, node(1)), center_line=L_NONE, inner_line=L_NONE, side_line=side)
+        if dist_in < 1e-3:
+            ok = ok and bend_ok
+        straight_road = (node(1), node(2))
+        self.dest_roads.append(straight_road)
+        ok = ok and one(straight, straight_road, center_line=L_CONT, inner_line=L_NONE, side_line=side, center_color=GREY)
+        # the way in from the other direction
+        neg = out_socket.negative
+        net = self.world if self._from_world(out_socket) else self.net
+        neg_lane = net.lanes(neg)[0]
+        start = neg[1]
+        if dist_out > 1e-3:
+            neg_lane = extend_straight(neg_lane, dist_out, [L_NONE, L_NONE])
+            one(neg_lane, (neg[1], node(3)), **none)
+            start = node(3)
+        bend, straight = bend_then_straight(neg_lane, self.lane_width, radius, self.ANGLE, False, self.space_w)
+        one(bend, (start, node(4)), **none)
+        one(straight, (node(4), node(1)), **none)
+        # the space under a second road name, in the reverse direction: (1, 2) = (5, 6)
+        parking_road = (node(5), node(6))
+        self.parking_spawn_roads.append(parking_road)
+        two_way_road((node(1), node(2)), self.net, self.world, parking_road, center_line=L_NONE, inner_line=L_NONE,
+                     side_line=L_SIDE if dist_out < 1e-3 else L_NONE)
+        parking_lane = self.net.lanes(parking_road)[0]
+        # the way out, first direction
+        bend, straight = bend_then_straight(parking_lane, 0.1 if dist_out < 1e-3 else dist_out, radius, self.ANGLE, True,
+                                            parking_lane.width)
+        bend_ok = one(bend, (node(6), node(7) if dist_out > 1e-3 else out_socket.positive[0]), center_line=L_NONE,
+                      inner_line=L_NONE, side_line=L_SIDE if dist_out < 1e-3 else L_NONE)
+        if dist_out < 1e-3:
+            ok = ok and bend_ok
+        if dist_out > 1e-3:
+            ok = ok and one(straight, (node(7), out_socket.positive[0]), **none)
+        # the way out, other direction
+        ext = extend_straight(parking_lane, self.lane_width, [L_NONE, L_NONE])
+        one(ext, (node(6), node(8)), **none)
+        bend, straight = bend_then_straight(ext, 0.1 if dist_in < 1e-3 else dist_in, radius, self.ANGLE, False, parking_lane.width)
+        one(bend, (node(8), node(9) if dist_in > 1e-3 else in_socket.negative[0]), **none)
+        if dist_in > 1e-3:
+            one(straight, (node(9), in_socket.negative[0]), **none)
+        return ok
+
+
 # BLOCK_TYPE_DISTRIBUTION_V2 (component/algorithm/blocks_prob_dist.py:24-43), in its dict order
 BLOCK_DIST = [("Curve", Curve, 0.3), ("Straight", Straight, 0.1), ("InRampOnStraight", InRamp, 0.1),
               ("OutRampOnStraight", OutRamp, 0.1), ("StdInterSection", InterSection, 0.15),
               ("StdTInterSection", TInterSection, 0.15), ("Roundabout", Roundabout, 0.1), ("InFork", None, 0.0),
-              ("OutFork", None, 0.0), ("Merge", Merge, 0.0), ("Split", Split, 0.0), ("ParkingLot", None, 0.0),
+              ("OutFork", None, 0.0), ("Merge", Merge, 0.0), ("Split", Split, 0.0), ("ParkingLot", ParkingLot, 0.0),
               ("TollGate", TollGate, 0.0), ("Bidirection", Bidirection, 0.0)]
 BY_ID = {cls.ID: cls for _, cls, _ in BLOCK_DIST if cls is not None}
 MIN_LANES, MAX_LANES = 1, 5
@@ -1273,7 +1383,7 @@ def build_fixed(kind, lane_num=2, lane_width=3.5, exit_length=60):
         blk.std = False
         blk.u_turn = lane_num > 1
         blk.construct()
-    elif kind in ("bottleneck", "bidirection", "tollgate"):
+    elif kind in ("bottleneck", "bidirection", "tollgate", "parkinglot"):
         return _build_chain(big, kind, lane_num, exit_length)
     else:
         raise NotImplementedError("multi-agent map %r is not restated" % kind)
@@ -1296,6 +1406,12 @@ def _build_chain(big, kind, lane_num, exit_length, neck_lane_num=1, neck_length=
         add(Merge, dict(lane_num=d, length=3))
         add(Bidirection, None)
         add(Split, dict(length=exit_length, lane_num=d))
+    elif kind == "parkinglot":    # MAParkingLotMap (marl_parking_lot.py:144-184): -> ParkingLot (4 spaces a side) -> T intersection
+        add(ParkingLot, dict(one_side_vehicle_number=4))
+        t = TInterSection(len(big.blocks), big.blocks[-1].get_socket(0), big.world, 1)
+        t.EXIT_LEN = 10
+        t.construct(dict(t_type=1, change_lane_num=0))
+        big.blocks.append(t)
     else:                         # tollgate: -> Split -> TollGate -> Merge, bottle length 35
         add(Split, dict(length=2, lane_num=toll_lane_num - lane_num, bottle_len=35))
         add(TollGate, dict(length=toll_length))

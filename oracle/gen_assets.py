@@ -63,7 +63,8 @@ def export_multi_agent(args):
     out = dict(
         lane_f=m["lane_f"], lane_i=m["lane_i"], road_i=m["road_i"], meta=m["meta"], config=json.dumps(conf),
         spawn_roads=np.array([[mi.nodes[r.start_node], mi.nodes[r.end_node]] for r in roads], np.int32),
-        dest_nodes=np.array([mi.nodes[(-r).end_node] for r in roads], np.int32),
+        # (the parking lot's spawn roads include its parking spaces, whose "negative road" is not a road of the map: -1)
+        dest_nodes=np.array([mi.nodes.get((-r).end_node, -1) for r in roads], np.int32),
         veh_static=rx.vehicle_static(v).astype(np.float32),
     )
     env.close()

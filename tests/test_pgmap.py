@@ -76,6 +76,21 @@ def test_generator_reproduces_maps_with_bottleneck_and_tollgate_blocks(name, spe
             GeneratedLibrary(0, 1, map=spec)
 
 
+def test_generator_reproduces_the_parking_lot_map():
+    """MAParkingLotMap (envs/marl_envs/marl_parking_lot.py:144-184): first block (one lane, 20 m) -> ParkingLot (4 spaces a
+    side, pgblock/parking_lot.py) -> T intersection; 106 lanes, bit for bit against the reference's export.  (The map only:
+    the env's parking-space spawn manager is not restated.)"""
+    import json
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "libs", "ma_parkinglot.npz"))
+    conf, meta = json.loads(str(d["config"])), json.loads(str(d["meta"]))
+    lane_f, lane_i, road_i, g_meta, big = pgmap.build_fixed("parkinglot", conf["lane_num"], 3.5, conf["exit_length"])
+    assert [b.ID for b in big.blocks] == ["I", "P", "T"] and g_meta["nodes"] == meta["nodes"]
+    np.testing.assert_array_equal(lane_f, d["lane_f"])
+    np.testing.assert_array_equal(lane_i, d["lane_i"])
+    np.testing.assert_array_equal(road_i, d["road_i"])
+    assert len(big.blocks[1].dest_roads) == 8 and len(big.blocks[1].parking_spawn_roads) == 8
+
+
 def test_generated_world_equals_exported_world():
     """What the device receives: scene.pack over generated scenarios == scene.pack over the exported ones, every array."""
     gen = GeneratedLibrary(0, 16)
@@ -97,8 +112,9 @@ def test_block_sequences_and_parameters():
         assert len(big.blocks) == n_blocks
         if isinstance(spec, str):
             assert "".join(b.ID for b in big.blocks[1:]) == spec
-    with pytest.raises(NotImplementedError):
-        pgmap.generate(0, "SP")                                                    # parking lot: not restated
+    with pytest.raises(AssertionError):
+        pgmap.generate(0, "SP")                                                    # a parking lot needs a one-lane road before it
+    assert [b.ID for b in pgmap.generate(0, "SP", lane_num=1)[4].blocks] == ["I", "S", "P"]
     # traffic density scales the roster (traffic_manager.py:236-238); the same seed keeps the same map
     _, _, _, _, big = pgmap.generate(11, 3)
     n = [len(pgspawn.populate(pgmap.generate(11, 3)[4], 11, d).veh_static) for d in (0.0, 0.1, 0.3)]
