@@ -220,7 +220,8 @@ typedef struct MdConfig {
     float success_reward, out_of_road_penalty, crash_vehicle_penalty, crash_object_penalty;
     float driving_reward, speed_reward;
     float crash_vehicle_cost, crash_object_cost, out_of_road_cost;
-    int use_lateral_reward, out_of_route_done, on_continuous_line_done;
+    int use_lateral_reward, out_of_route_done, on_continuous_line_done;   /* on_continuous_line_done: 1 = yellow / white solid line or sidewalk ends the episode;
+                                                                            2 = white solid line or sidewalk only (MultiAgentBottleneckEnv with cross_yellow_line_done=False) */
     int crash_vehicle_done, crash_object_done, crash_human_done, truncate_as_terminate;
     int enable_idm_lane_change, is_multi_agent, delay_done, allow_respawn;
     /* multi-agent respawn tables (manager/spawn_manager.py:117-217): safe places per env, destinations, spawn roads */

@@ -516,9 +516,7 @@ def _ma_cfg_kw(c):
     if "cross_yellow_line_done" in c:
         # MultiAgentBottleneckEnv._is_out_of_road / reward_function (envs/marl_envs/marl_bottleneck.py:89-135): white solid
         # line | off the lanes | sidewalk, plus the yellow solid line when cross_yellow_line_done; no positive_road sign
-        if not c["cross_yellow_line_done"]:
-            raise NotImplementedError("cross_yellow_line_done=False is not covered")
-        kw.update(out_of_route_done=0, on_continuous_line_done=1, ignore_road_sign=1)
+        kw.update(out_of_route_done=0, on_continuous_line_done=1 if c["cross_yellow_line_done"] else 2, ignore_road_sign=1)
     return kw
 
 

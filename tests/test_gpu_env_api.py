@@ -353,8 +353,10 @@ def test_ma_bottleneck_env_surface():
             if not env.agents:
                 break
         assert not env.agents and len(seen) > 20 and r_sum != 0.0
-        with pytest.raises(NotImplementedError):
-            MultiAgentBottleneckEnv({"cross_yellow_line_done": False}).reset()
+        lax = MultiAgentBottleneckEnv({"cross_yellow_line_done": False, "num_agents": 4})   # the yellow solid line may be crossed
+        lax.reset()
+        lax.step({k: [0.0, 0.5] for k in lax.agents})
+        lax.close()
     finally:
         env.close()
 
