@@ -121,6 +121,14 @@
 #define VC_EP_REWARD 11
 #define VC_STEP_ENERGY 12
 #define VC_TOTAL_COST 13
+/* MultiAgentTollgateEnv only (cfg.toll_env; envs/marl_envs/marl_tollgate.py:39-105): small integers kept as floats.
+ *   VC_TOLL_A = 16 * in_toll_time + 8 * has_exit + 4 * violation + last_block, where in_toll_time is
+ *               TollGateObservation's counter (:82-95), last_block StayTimeManager.last_block reduced to what its rules read
+ *               (0 not recorded yet, 1 the toll block, 2 any other block), has_exit / violation what `exit_time` means
+ *               to done_function (:261-266): both times recorded and exit - entry < min_pass_steps
+ *   VC_TOLL_ENTRY = entry_time + 1 (0 = none) */
+#define VC_TOLL_A 14
+#define VC_TOLL_ENTRY 15
 /* veh_i [NV, 16] */
 #define VEH_I 16
 #define VI_KIND 0        /* 0 empty, 1 agent, 2 traffic */
@@ -173,7 +181,9 @@
 
 /* ---- per-object arrays: obj_f [NO, 12] --------------------------------------------------------- */
 #define OBJ_F 12
-#define OB_KIND 0    /* -1 empty, 0 cone, 1 warning, 2 barrier, 3 pedestrian */
+#define OB_KIND 0    /* -1 empty, 0 cone, 1 warning, 2 barrier, 3 pedestrian, 4 building (TollGateBuilding: a static box like
+                      * the barrier, crash_building instead of crash_object, no COST_ONCE latch; buildings/tollgate_building.py) */
+#define OB_IS_BOX(kind) ((kind) == 2.0f || (kind) == 4.0f)
 #define OB_X 1
 #define OB_Y 2
 #define OB_HEADING 3
@@ -206,11 +216,14 @@
 #define OBS_LANE(cfg) ((cfg).n_lane_lasers > 0 ? (cfg).n_lane_lasers : 1)
 #define OBS_EGO(cfg) (OBS_SIDE(cfg) + 6 + OBS_LANE(cfg))
 #define OBS_NAVI 10
-#define OBS_STATE(cfg) (OBS_EGO(cfg) + OBS_NAVI)
+/* TollGateStateObservation (marl_tollgate.py:65-76) drops the navigation block; TollGateObservation (:79-105) appends
+ * [in the toll block, stayed longer than min_pass_steps] after the lidar floats */
+#define OBS_STATE(cfg) (OBS_EGO(cfg) + ((cfg).toll_env ? 0 : OBS_NAVI))
+#define OBS_TOLL(cfg) ((cfg).toll_env ? 2 : 0)
 #define MAX_DET_LASERS 128
 #define DET_HEIGHT 0.2f      /* DistanceDetector.DEFAULT_HEIGHT (sensors/distance_detector.py:92) */
 #define OBS_OTHERS(cfg) (4 * (cfg).num_others)                       /* component/sensors/lidar.py:93-138 */
-#define OBS_DIM(cfg) (OBS_STATE(cfg) + OBS_OTHERS(cfg) + (cfg).n_lasers)
+#define OBS_DIM(cfg) (OBS_STATE(cfg) + OBS_OTHERS(cfg) + (cfg).n_lasers + OBS_TOLL(cfg))
 
 /* ---- configuration passed by value through the C ABI ------------------------------------------- */
 typedef struct MdConfig {
@@ -221,7 +234,9 @@ typedef struct MdConfig {
     float driving_reward, speed_reward;
     float crash_vehicle_cost, crash_object_cost, out_of_road_cost;
     int use_lateral_reward, out_of_route_done, on_continuous_line_done;   /* on_continuous_line_done: 1 = yellow / white solid line or sidewalk ends the episode;
-                                                                            2 = white solid line or sidewalk only (MultiAgentBottleneckEnv with cross_yellow_line_done=False) */
+                                                                            2 = white solid line or sidewalk only (MultiAgentBottleneckEnv with cross_yellow_line_done=False);
+                                                                            3 = sidewalk or yellow solid line, 4 = sidewalk only, and leaving the lanes does NOT count
+                                                                            (MultiAgentTollgateEnv._is_out_of_road, marl_tollgate.py:239-245) */
     int crash_vehicle_done, crash_object_done, crash_human_done, truncate_as_terminate;
     int enable_idm_lane_change, is_multi_agent, delay_done, allow_respawn;
     /* multi-agent respawn tables (manager/spawn_manager.py:117-217): safe places per env, destinations, spawn roads */
@@ -248,6 +263,12 @@ typedef struct MdConfig {
     /* MultiAgentBottleneckEnv / MultiAgentTollgateEnv.reward_function (envs/marl_envs/marl_bottleneck.py:89-127) drop the
      * `positive_road` sign MetaDriveEnv.reward_function applies off the reference lanes (envs/metadrive_env.py:249-266) */
     int ignore_road_sign;
+    /* MultiAgentTollgateEnv (envs/marl_envs/marl_tollgate.py): toll_env = 1 switches on its observation (no navigation block,
+     * two toll floats at the end), its reward (inside the toll block: -overspeed_penalty * speed / max_speed when faster than the
+     * lanes' limit, no speed reward), its done_function (crash_done reads crash_vehicle only; leaving the toll block less than
+     * min_pass_steps after entering it ends the episode as out_of_road) and the stay-time bookkeeping behind it */
+    int toll_env, min_pass_steps;
+    float overspeed_penalty;
 } MdConfig;
 
 /* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */

@@ -3,6 +3,7 @@
 Only the step path lives here (include/mdstep.h is the boundary): hand-written sm_100a kernels in csrc/, the ctypes
 binding (lib, sim), host-side scene tables (scene, library) and the drop-in env classes (envs)."""
 from .envs import (BatchedMetaDriveEnv, BatchedMultiAgentEnv, MetaDriveEnv, MultiAgentBottleneckEnv,  # noqa: F401
-                   MultiAgentIntersectionEnv, MultiAgentMetaDrive, MultiAgentRoundaboutEnv, SafeMetaDriveEnv)
+                   MultiAgentIntersectionEnv, MultiAgentMetaDrive, MultiAgentRoundaboutEnv, MultiAgentTollgateEnv,
+                   SafeMetaDriveEnv)
 
 __version__ = "0.1.0"

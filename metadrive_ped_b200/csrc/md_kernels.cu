@@ -112,7 +112,7 @@ struct NbrView {
         }
         const float* Ob = obj + (k - S) * OBJ_F;
         if (Ob[OB_KIND] < 0.0f) return false;
-        if (Ob[OB_KIND] == 2.0f) { Rect r = object_rect(Ob); return rect_circle(r, px, py, 50.0f); }
+        if (OB_IS_BOX(Ob[OB_KIND])) { Rect r = object_rect(Ob); return rect_circle(r, px, py, 50.0f); }
         float dx = Ob[OB_X] - px, dy = Ob[OB_Y] - py, rr = 50.0f + Ob[OB_A];
         return dx * dx + dy * dy <= rr * rr;
     }
@@ -721,10 +721,11 @@ __device__ __forceinline__ int dynamic_contacts(const Nb* nb, float* obj, int S,
         const float* Ob = obj + k * OBJ_F;
         if (Ob[OB_KIND] < 0.0f) continue;
         bool hit;
-        if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
+        if (OB_IS_BOX(Ob[OB_KIND])) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
         else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
         if (!hit) continue;
         if (Ob[OB_KIND] == 3.0f) flags |= FL_CRASH_HUMAN;
+        else if (Ob[OB_KIND] == 4.0f) flags |= FL_CRASH_BUILDING;   // collision_callback.py:39-41, base_vehicle.py:737-738
         else if (latch) {
             if (Ob[OB_CRASHED] == 0.0f) {
                 if (claim_pass) atomicMin(&obj_first[k], slot);          // COST_ONCE: lowest slot takes the flag
@@ -756,12 +757,13 @@ __device__ __forceinline__ int contact_pass(const Nb* nb, float* obj, int S, int
             const int ko = k - S;
             const float* Ob = obj + ko * OBJ_F;
             bool hit;
-            if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
+            if (OB_IS_BOX(Ob[OB_KIND])) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
             else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
             if (!hit) continue;
             if (touch && claim_pass) touch[half] |= 1ull << (k & 63);
             if (Ob[OB_KIND] == 3.0f) { flags |= FL_CRASH_HUMAN; continue; }
             flags |= FL_TOUCH;   // a solid obstacle overlaps, whether or not its COST_ONCE flag is still to be had
+            if (Ob[OB_KIND] == 4.0f) { flags |= FL_CRASH_BUILDING; continue; }   // a toll booth: no COST_ONCE latch
             if (Ob[OB_CRASHED] == 0.0f) {
                 if (claim_pass) atomicMin(&obj_first[ko], slot);          // COST_ONCE: lowest slot takes the flag
                 else if (obj_first[ko] == slot) flags |= FL_CRASH_OBJECT;
@@ -775,7 +777,10 @@ __device__ __forceinline__ int contact_pass(const Nb* nb, float* obj, int S, int
 // (envs/metadrive_env.py:128-279, envs/base_env.py:586-623, obs/state_obs.py:64-151)
 __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_step, const float* P, const float* S, float* C,
                               int* I, const int* __restrict__ rroad, const float* navi, size_t a, const StepOut& out,
-                              bool write_scalars) {
+                              int pass) {
+    // pass: bit 0 = a step (reward / cost / done are written; the tollgate env's done_function reads the stay times),
+    //       bit 1 = the tollgate env's StayTimeManager.record runs after the observation (a step or a newborn agent; not reset)
+    const bool write_scalars = (pass & 1) != 0;
     float px = S[VS_POS], py = S[VS_POS + 1];
     M3 R = quat_to_m3(S[VS_QUAT], S[VS_QUAT + 1], S[VS_QUAT + 2], S[VS_QUAT + 3]);
     float hx, hy;
@@ -793,6 +798,8 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
     int lane = I[VI_LANE];
     float lane_w = m.lane_f[lane * LANE_F + LF_WIDTH];
     const float fl_len = m.lane_f[final_lane * LANE_F + LF_LENGTH];
+    const int cur_block = m.road_i[cur_road * ROAD_I + RI_BLOCK];
+    const bool toll_now = cfg.toll_env && cur_block == '$';
     if (write_scalars) {
         I[VI_EP_LEN] += 1;
         int rl = lane;
@@ -807,7 +814,14 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         float lateral_factor = cfg.use_lateral_reward ? clipf(1.0f - 2.0f * fabsf(lat_now) / lane_w, 0.0f, 1.0f) : 1.0f;
         float rew = 0.0f;
         rew += cfg.driving_reward * (long_now - long_last) * lateral_factor * positive;
-        rew += cfg.speed_reward * (speed_kmh / P[VP_MAX_SPEED]) * positive;
+        // MultiAgentTollgateEnv.reward_function (marl_tollgate.py:217-226): inside the toll block a vehicle faster than its
+        // lane's speed limit (pgblock/tollgate.py:19,68: 3, compared with km/h - base_vehicle.py:910-911) is paid the overspeed
+        // penalty INSTEAD of the driving reward, and nobody gets a speed reward there
+        if (toll_now) {
+            const bool lane_toll = m.road_i[m.lane_i[lane * LANE_I + LI_ROAD] * ROAD_I + RI_BLOCK] == '$';
+            if ((lane_toll ? 3.0f : 1000.0f) < speed_kmh) rew = -cfg.overspeed_penalty * speed_kmh / P[VP_MAX_SPEED];
+        } else
+            rew += cfg.speed_reward * (speed_kmh / P[VP_MAX_SPEED]) * positive;
         float step_reward = rew;
         float fl_long, fl_lat;
         lane_local(m.lane_f + final_lane * LANE_F, px, py, fl_long, fl_lat);
@@ -816,6 +830,8 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         bool outr = !(flags & FL_ON_LANE);
         if (cfg.out_of_route_done) outr = outr || (flags & FL_OUT_OF_ROUTE);
         else if (cfg.on_continuous_line_done == 2) outr = outr || (flags & (FL_ON_WHITE | FL_CRASH_SIDEWALK));   // bottleneck env, yellow line allowed
+        else if (cfg.on_continuous_line_done >= 3)   // marl_tollgate.py:239-245: leaving the lanes is not out of road there
+            outr = (flags & (cfg.on_continuous_line_done == 3 ? (FL_ON_YELLOW | FL_CRASH_SIDEWALK) : FL_CRASH_SIDEWALK)) != 0;
         else if (cfg.on_continuous_line_done) outr = outr || (flags & (FL_ON_YELLOW | FL_ON_WHITE | FL_CRASH_SIDEWALK));
         if (arrive) rew = cfg.success_reward;
         else if (outr) rew = -cfg.out_of_road_penalty;
@@ -823,7 +839,7 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         else if (flags & FL_CRASH_OBJECT) rew = -cfg.crash_object_penalty;
         C[VC_EP_REWARD] += rew;
         bool max_step = cfg.horizon > 0 && I[VI_EP_LEN] >= cfg.horizon;
-        bool done = false;
+        bool done = false, stay_violation = false;
         if (arrive) done = true;
         if (outr) done = true;
         if ((flags & FL_CRASH_VEHICLE) && cfg.crash_vehicle_done) done = true;
@@ -832,9 +848,12 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         if ((flags & FL_CRASH_HUMAN) && cfg.crash_human_done) done = true;
         if (max_step && cfg.truncate_as_terminate) done = true;
         if (cfg.is_multi_agent && !max_step) {  // MultiAgentMetaDrive.done_function (multi_agent_metadrive.py:114-128)
-            const int crash = flags & (FL_CRASH_VEHICLE | FL_CRASH_OBJECT | FL_CRASH_BUILDING | FL_CRASH_SIDEWALK | FL_CRASH_HUMAN);
+            int crash = flags & (FL_CRASH_VEHICLE | FL_CRASH_OBJECT | FL_CRASH_BUILDING | FL_CRASH_SIDEWALK | FL_CRASH_HUMAN);
+            if (cfg.toll_env) crash = flags & FL_CRASH_VEHICLE;   // marl_tollgate.py:250 reads crash_vehicle only
             if (crash && !cfg.ma_crash_done && !(arrive || outr)) done = false;
             if (outr && !cfg.ma_out_of_road_done && !arrive) done = false;
+            // marl_tollgate.py:261-266: through the toll block in less than min_pass_steps - as recorded up to the previous step
+            if (cfg.toll_env && (((int)C[VC_TOLL_A] >> 2) & 1)) { done = true; stay_violation = true; }
         }
         float c = 0.0f;
         if (outr) c = cfg.out_of_road_cost;
@@ -849,7 +868,7 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         if (done) I[VI_DONE] = 1;
         out.reward[a] = rew; out.cost[a] = c;
         out.term[a] = (uint8_t)(I[VI_DONE] != 0); out.trunc[a] = (uint8_t)trunc;
-        out.info_flags[a] = flags | (outr ? FL_OUT_OF_ROAD : 0) | (arrive ? FL_ARRIVE : 0) | (max_step ? FL_MAX_STEP : 0);
+        out.info_flags[a] = flags | ((outr || stay_violation) ? FL_OUT_OF_ROAD : 0) | (arrive ? FL_ARRIVE : 0) | (max_step ? FL_MAX_STEP : 0);
         float4* inf = reinterpret_cast<float4*>(out.info_f + a * 8);
         inf[0] = make_float4(sqrtf(S[VS_VEL] * S[VS_VEL] + S[VS_VEL + 1] * S[VS_VEL + 1]), S[VS_STEER], S[VS_THROTTLE], C[VC_STEP_ENERGY]);
         inf[1] = make_float4(C[VC_ENERGY], step_reward, C[VC_EP_REWARD], (float)I[VI_EP_LEN]);
@@ -889,8 +908,33 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
         lane_local(m.lane_f + lane * LANE_F, px, py, lon, lat);
         o[sd + 6] = clipf((lat * 2.0f / 4.5f + 1.0f) / 2.0f, 0.0f, 1.0f);
     }
+    if (!cfg.toll_env) {
 #pragma unroll
-    for (int k = 0; k < NAVI_DIM; k++) o[OBS_EGO(cfg) + k] = navi[k];
+        for (int k = 0; k < NAVI_DIM; k++) o[OBS_EGO(cfg) + k] = navi[k];
+        return;
+    }
+    // TollGateObservation.observe (marl_tollgate.py:92-105): the counter runs while the current road is the toll block
+    const int a_ = (int)C[VC_TOLL_A];
+    int in_toll = a_ >> 4, has_exit = (a_ >> 3) & 1, viol = (a_ >> 2) & 1, last = a_ & 3;
+    in_toll += toll_now ? 1 : 0;
+    float* to = o + OBS_DIM(cfg) - 2;
+    to[0] = toll_now ? 1.0f : 0.0f;
+    to[1] = (toll_now && in_toll > cfg.min_pass_steps) ? 1.0f : 0.0f;
+    if (pass & 2) {
+        // StayTimeManager.record (marl_tollgate.py:50-62), after the step: entry when the block changes to the toll block, exit
+        // when it changes from the toll block to Merge / Split
+        if (last != 0) {
+            if (toll_now && last != 1) {
+                C[VC_TOLL_ENTRY] = (float)(env_step + 1);
+                if (has_exit) viol = cfg.min_pass_steps > 0;   // exit - entry < 0 from here on
+            } else if (!toll_now && last == 1 && (cur_block == 'y' || cur_block == 'Y')) {
+                has_exit = 1;
+                viol = C[VC_TOLL_ENTRY] > 0.0f && (env_step - ((int)C[VC_TOLL_ENTRY] - 1)) < cfg.min_pass_steps;
+            }
+        }
+        last = toll_now ? 1 : 2;
+    }
+    C[VC_TOLL_A] = (float)(16 * in_toll + 8 * has_exit + 4 * viol + last);
 }
 
 __device__ __forceinline__ void load16(float* dst, const float* src) {
@@ -1209,7 +1253,7 @@ __device__ MD_RESP_INL void contact_response(const Nb* nb, const CBody* cd, cons
             CBody ob;
             ob.ox = Ob[OB_X]; ob.oy = Ob[OB_Y]; ob.vx = 0.0f; ob.vy = 0.0f; ob.w = 0.0f; ob.im = 0.0f; ob.ii = 0.0f;
             bool hit;
-            if (Ob[OB_KIND] == 2.0f) { const Rect ro = object_rect(Ob); hit = rr_contact(mr, ro, nx, ny, depth, px, py); }
+            if (OB_IS_BOX(Ob[OB_KIND])) { const Rect ro = object_rect(Ob); hit = rr_contact(mr, ro, nx, ny, depth, px, py); }
             else hit = rc_contact(mr, Ob[OB_X], Ob[OB_Y], Ob[OB_A], nx, ny, depth, px, py);
             if (hit) pair_impulse(me, ob, nx, ny, depth, px, py, false, d);
         }
@@ -1347,7 +1391,7 @@ k_dyn(MdConfig cfg, MdArrays A, int mode, int epb, const float4* __restrict__ ve
                 for (int k = 0; k < O; k++) {
                     const float* Ob = sobj + k * OBJ_F;
                     if (Ob[OB_KIND] < 0.0f) continue;
-                    const float orad = Ob[OB_KIND] == 2.0f ? sqrtf(Ob[OB_A] * Ob[OB_A] + Ob[OB_B] * Ob[OB_B]) : Ob[OB_A];
+                    const float orad = OB_IS_BOX(Ob[OB_KIND]) ? sqrtf(Ob[OB_A] * Ob[OB_A] + Ob[OB_B] * Ob[OB_B]) : Ob[OB_A];
                     const float ospeed = Ob[OB_KIND] == 3.0f ? sqrtf(Ob[OB_VX] * Ob[OB_VX] + Ob[OB_VY] * Ob[OB_VY]) : 0.0f;
                     const float dx = Ob[OB_X] - r0.cx, dy = Ob[OB_Y] - r0.cy;
                     const float reach = my_rad + orad + (my_speed + ospeed) * T;
@@ -1533,6 +1577,8 @@ __global__ void k_restore_post(MdConfig cfg, MdArrays A, Snapshot post, const fl
     if (slot < cfg.agents_per_env) {
         const size_t a = (size_t)env * cfg.agents_per_env + slot;
         for (int k = 0; k < OBS_STATE(cfg); k++) obs[a * (size_t)OBS_DIM(cfg) + k] = post_obs[a * OBS_STATE(cfg) + k];
+        // the tollgate env's two toll floats: no spawn road lies inside the toll block, so a reset observation carries [0, 0]
+        for (int k = 0; k < OBS_TOLL(cfg); k++) obs[(a + 1) * (size_t)OBS_DIM(cfg) - 1 - k] = 0.0f;
     }
 }
 // ---- scenario resampling at reset (BaseEnv.reset(seed=None) -> _reset_global_seed draws a scenario, envs/base_env.py:
@@ -1657,9 +1703,9 @@ __device__ __forceinline__ int fp_contacts(const Fp* fp, const float* obj, int S
         const float* Ob = obj + k * OBJ_F;
         if (Ob[OB_KIND] < 0.0f) continue;
         bool hit;
-        if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
+        if (OB_IS_BOX(Ob[OB_KIND])) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
         else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
-        if (hit) flags |= Ob[OB_KIND] == 3.0f ? FL_CRASH_HUMAN : FL_CRASH_OBJECT;
+        if (hit) flags |= Ob[OB_KIND] == 3.0f ? FL_CRASH_HUMAN : (Ob[OB_KIND] == 4.0f ? FL_CRASH_BUILDING : FL_CRASH_OBJECT);
     }
     return flags;
 }
@@ -1673,9 +1719,9 @@ __device__ __forceinline__ int fp_contacts_team(const Fp* fp, const float* obj, 
         const float* Ob = obj + k * OBJ_F;
         if (Ob[OB_KIND] < 0.0f) continue;
         bool hit;
-        if (Ob[OB_KIND] == 2.0f) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
+        if (OB_IS_BOX(Ob[OB_KIND])) { Rect ro = object_rect(Ob); hit = rect_rect(r, ro); }
         else hit = rect_circle(r, Ob[OB_X], Ob[OB_Y], Ob[OB_A]);
-        if (hit) flags |= Ob[OB_KIND] == 3.0f ? FL_CRASH_HUMAN : FL_CRASH_OBJECT;
+        if (hit) flags |= Ob[OB_KIND] == 3.0f ? FL_CRASH_HUMAN : (Ob[OB_KIND] == 4.0f ? FL_CRASH_BUILDING : FL_CRASH_OBJECT);
     }
     return flags;
 }
@@ -2018,7 +2064,7 @@ k_post(MdConfig cfg, MdArrays A, int mode, int epb, StepOut out, float* __restri
         const int alive_row = I[VI_ALIVE];
         if ((mode & (MODE_OUT | MODE_RESET)) && is_agent && I[VI_ACTIVE] && slot < NA) {
             const size_t a = (size_t)env * NA + slot;
-            agent_outputs(cfg, m, env_step, P, St, C, I, rroad, navi, a, out, (mode & MODE_OUT) != 0);
+            agent_outputs(cfg, m, env_step, P, St, C, I, rroad, navi, a, out, (mode & MODE_OUT) ? 3 : 0);
             if ((mode & MODE_OUT) && cfg.is_multi_agent) {
                 // MultiAgentMetaDrive._after_vehicle_done -> agent_manager._finish (multi_agent_metadrive.py:153-166,
                 // agent_manager.py:115-128): success leaves at once, everything else becomes a static wreck
@@ -2257,7 +2303,7 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     }
     for (int k = lane; k < O; k += 32) {
         const float* ob = sobj + OBJ_F * k;
-        float r = ob[OB_KIND] == 2.0f ? sqrtf(ob[OB_A] * ob[OB_A] + ob[OB_B] * ob[OB_B]) : ob[OB_A];
+        float r = OB_IS_BOX(ob[OB_KIND]) ? sqrtf(ob[OB_A] * ob[OB_A] + ob[OB_B] * ob[OB_B]) : ob[OB_A];
         srad[S + k] = ob[OB_KIND] >= 0.0f ? r * 1.001f + 1e-3f : -1.0f;
     }
     __syncwarp();
@@ -2418,7 +2464,7 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
             t = ray_obb(o, d, f3(b[0], b[1], b[2]), R, f3(b[3], b[4], b[5]));
         } else {
             const float* ob = sobj + OBJ_F * (k - S);
-            if (ob[OB_KIND] == 2.0f) {
+            if (OB_IS_BOX(ob[OB_KIND])) {
                 const float ch = md_cosf(ob[OB_HEADING]), sh = md_sinf(ob[OB_HEADING]);
                 M3 R;
                 R.m[0][0] = ch; R.m[0][1] = -sh; R.m[0][2] = 0.0f; R.m[1][0] = sh; R.m[1][1] = ch; R.m[1][2] = 0.0f;
@@ -2636,7 +2682,7 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
     const MapView m = map_view(A, E[EI_MAP]);
     after_step_vehicle(m, St, C, I, vr, vrr, navi, nb, A.obj_f + (size_t)env * O * OBJ_F, S, O, seat, nb[seat].r);
     const size_t a = (size_t)env * NA + seat;
-    agent_outputs(cfg, m, E[EI_STEP], P, St, C, I, vrr, navi, a, out, false);
+    agent_outputs(cfg, m, E[EI_STEP], P, St, C, I, vrr, navi, a, out, 2);
     // a newborn agent: reward 0, not done, first observation (multi_agent_metadrive.py:137-144)
     out.reward[a] = 0.0f; out.cost[a] = 0.0f; out.term[a] = 0; out.trunc[a] = 0;
     out.info_flags[a] = (I[VI_FLAGS] & 0x3ff) | FL_VALID | FL_NEWBORN;

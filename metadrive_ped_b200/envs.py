@@ -145,6 +145,14 @@ def _merge(default, user, path=""):
     return out
 
 
+def _merge_new(default, user):
+    """Config.update(..., allow_add_new_key=True): what the reference's env classes use to extend the defaults"""
+    out = dict(default)
+    for k, v in (user or {}).items():
+        out[k] = _merge_new(default[k], v) if isinstance(default.get(k), dict) and isinstance(v, dict) else v
+    return out
+
+
 def _obs_dim(vc):
     """LidarStateObservation.observation_space (obs/state_obs.py:30-62, 172-183): side block (2 distances or the side
     detector's rays) + 6 + lane block (1 offset or the lane-line detector's rays) + navi 10 + others 4k + lidar N."""
@@ -517,6 +525,11 @@ def _ma_cfg_kw(c):
         # MultiAgentBottleneckEnv._is_out_of_road / reward_function (envs/marl_envs/marl_bottleneck.py:89-135): white solid
         # line | off the lanes | sidewalk, plus the yellow solid line when cross_yellow_line_done; no positive_road sign
         kw.update(out_of_route_done=0, on_continuous_line_done=1 if c["cross_yellow_line_done"] else 2, ignore_road_sign=1)
+    if "overspeed_penalty" in c:
+        # MultiAgentTollgateEnv (envs/marl_envs/marl_tollgate.py:185-266): out of road = sidewalk (+ yellow solid line), the toll
+        # block's overspeed penalty, the stay-time rule, TollGateObservation
+        kw.update(on_continuous_line_done=3 if c["cross_yellow_line_done"] else 4, toll_env=1,
+                  min_pass_steps=int(c["vehicle_config"]["min_pass_steps"]), overspeed_penalty=float(c["overspeed_penalty"]))
     return kw
 
 
@@ -534,9 +547,7 @@ class MultiAgentMetaDrive:
         d = _merge(STEP_DEFAULTS, {k: v for k, v in MA_DEFAULTS.items() if k in STEP_DEFAULTS})
         d.update({k: v for k, v in MA_DEFAULTS.items() if k not in STEP_DEFAULTS})
         d["vehicle_config"] = _merge(STEP_DEFAULTS["vehicle_config"], MA_DEFAULTS["vehicle_config"])
-        d.update({k: v for k, v in cls.ENV_DEFAULTS.items() if k != "vehicle_config"})
-        d["vehicle_config"] = _merge(d["vehicle_config"], cls.ENV_DEFAULTS.get("vehicle_config", {}))
-        return d
+        return _merge_new(d, cls.ENV_DEFAULTS)
 
     def __init__(self, config=None):
         from .ma import MultiAgentLibrary
@@ -558,7 +569,10 @@ class MultiAgentMetaDrive:
             self.num_agents = self._lib.max_capacity
         assert 0 < self.num_agents <= self._lib.max_capacity, \
             "Too many agents! We only accept {} agents, but you have {} agents!".format(self._lib.max_capacity, self.num_agents)
-        self._obs_box = _box(-0.0, 1.0, (_obs_dim(self.config["vehicle_config"]), ))
+        od = _obs_dim(self.config["vehicle_config"])
+        if "overspeed_penalty" in self.config:   # TollGateObservation.observation_space (marl_tollgate.py:85-93): no navi, + 2
+            od += 2 - 10
+        self._obs_box = _box(-0.0, 1.0, (od, ))
         self._act_box = _action_space(self.config)
         self._seat_id = ["agent%d" % k for k in range(self.num_agents)] + [None]
         self._active = set(self._seat_id[:self.num_agents])
@@ -658,6 +672,19 @@ class MultiAgentBottleneckEnv(MultiAgentMetaDrive):
     ENV_DEFAULTS = dict(num_agents=20, cross_yellow_line_done=True,
                         vehicle_config=dict(side_detector=dict(num_lasers=4, distance=50),
                                             lane_line_detector=dict(num_lasers=4, distance=20)))
+
+
+class MultiAgentTollgateEnv(MultiAgentMetaDrive):
+    """envs/marl_envs/marl_tollgate.py:15-36, 167-277: 3 lanes split into 8 toll lanes and merge again (I -> Split -> TollGate ->
+    Merge), a booth (static box: crash_building, lidar-visible) on every second toll lane; agents are born at both ends and
+    must stay in the toll block for at least min_pass_steps (else the step after they leave ends their episode as
+    out_of_road) at no more than the lanes' speed limit (else the overspeed penalty replaces the driving reward);
+    TollGateObservation = ego state without the navigation block + lidar + [in the toll block, stayed long enough]"""
+    ASSET = "ma_tollgate.npz"
+    ENV_DEFAULTS = dict(num_agents=40, cross_yellow_line_done=True, speed_reward=0.0, overspeed_penalty=0.5,
+                        vehicle_config=dict(min_pass_steps=30, side_detector=dict(num_lasers=72, distance=20),
+                                            lane_line_detector=dict(num_lasers=4, distance=20),
+                                            lidar=dict(num_lasers=72, distance=20)))
 
 
 class BatchedMultiAgentEnv:

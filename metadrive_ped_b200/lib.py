@@ -17,7 +17,7 @@ EXPORTS = [
     "md_host_views", "md_attach_bank", "md_sizeof_config", "md_sizeof_arrays", "md_host_groups", "md_host_group_count",
     "md_host_group_views", "md_host_send", "md_host_recv", "md_host_compact", "md_fp32_peak", "md_enable_contacts", "md_get_contacts",
 ]
-ABI_VERSION = 5  # include/mdstep.h MD_ABI_VERSION
+ABI_VERSION = 6  # include/mdstep.h MD_ABI_VERSION
 
 
 class MdStepError(RuntimeError):

@@ -111,8 +111,7 @@ MA_MAPS = {
     # envs/marl_envs/marl_bottleneck.py:10-25: first road + the negative of Split's socket road
     "bottleneck": dict(env="ma_bottleneck", num_agents=20, spawn_nodes=[(2, 0, 0, 1)], lane_num=4, exit_length=60.0,
                        fixed_dest=True),
-    # envs/marl_envs/marl_tollgate.py:15-36: first road + the negative of the closing Merge's socket road (map only: the env's
-    # toll observation / stay-time rules are not on the device)
+    # envs/marl_envs/marl_tollgate.py:15-36: first road + the negative of the closing Merge's socket road
     "tollgate": dict(env="ma_tollgate", num_agents=40, spawn_nodes=[(3, 0, 0, 1)], lane_num=3, exit_length=70.0,
                      fixed_dest=True),
     # envs/marl_envs/marl_bidirection.py:10-25 (map only: the reference's env raises KeyError('use_lateral') in its
@@ -144,7 +143,11 @@ def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None):
     conf = dict(env=m["env"], num_agents=m["num_agents"], lane_num=lane_num, exit_length=float(exit_length), entrance_length=10.0,
                 respawn_longitude=RESPAWN_REGION_LONGITUDE, respawn_lateral=RESPAWN_REGION_LATERAL, max_vehicle_length=10.0,
                 max_vehicle_width=2.5, disable_u_turn=False, fixed_dest=bool(m.get("fixed_dest", False)))
-    return dict(lane_f=lane_f, lane_i=lane_i, road_i=road_i, meta=json.dumps(meta), config=json.dumps(conf),
+    # static bodies the map itself brings: the toll booths (scene.Scenario.objects rows: kind 4 = building, x, y, heading,
+    # half extent across the heading, half extent along it - the barrier's column order -, height BUILDING_HEIGHT = 5, lane id)
+    objects = np.array([[4.0, b[1], b[2], b[3], b[5], b[4], 5.0, b[0]] for blk in meta["blocks"]
+                        for b in blk.get("buildings", [])], np.float64).reshape(-1, 8)
+    return dict(lane_f=lane_f, lane_i=lane_i, road_i=road_i, meta=json.dumps(meta), config=json.dumps(conf), objects=objects,
                 spawn_roads=np.array([[node[a], node[b]] for a, b in roads], np.int32),
                 dest_nodes=np.array([node[pgmap.neg_road(r)[1]] for r in roads], np.int32),
                 veh_static=np.asarray(static, np.float32))
@@ -173,6 +176,7 @@ class MultiAgentLibrary:
         self.spawn_roads = np.asarray(d["spawn_roads"], np.int32)
         self.dest_nodes = np.asarray(d["dest_nodes"], np.int32)
         self.veh_static = np.asarray(d["veh_static"], np.float32)
+        self.objects = np.asarray(d["objects"], np.float64) if "objects" in d else np.zeros((0, 8))
         if self.conf.get("fixed_dest") or self.conf["env"] in ("ma_bottleneck", "ma_tollgate", "ma_bidirection"):
             # destination of spawn road k = the far end of the map = the end node of the OTHER spawn road's negative
             self.dest_nodes = self.dest_nodes[::-1].reshape(-1, 1)
@@ -219,7 +223,7 @@ class MultiAgentLibrary:
             veh_int[k] = [1, -1, lane, 0, 1 if n_ck > 2 else 0, 1]
         static = np.tile(self.veh_static, (num_agents, 1))
         idm = np.tile(np.array([[0.0, 30.0]], np.float32), (num_agents, 1))
-        return sc.Scenario(0, static, veh_dyn, routes, veh_int, idm, np.zeros((0, 8)), 0)
+        return sc.Scenario(0, static, veh_dyn, routes, veh_int, idm, self.objects, 0)
 
     def build_world(self, n_envs, num_agents, seed=0, **cfg_kw):
         """(arrays, cfg) for n_envs independent multi-agent envs: num_agents + 1 seats each (the spare seat keeps a
@@ -229,8 +233,9 @@ class MultiAgentLibrary:
         NA = num_agents + 1
         S = ((NA + 3) // 4) * 4
         tape = make_tape(n_envs, seed=seed + 1)
-        arrays = sc.pack([self.geo], scen, S, NA, 0, ma_tables={0: self.tables}, ma_tables_tape=tape)
+        O = len(self.objects)
+        arrays = sc.pack([self.geo], scen, S, NA, O, ma_tables={0: self.tables}, ma_tables_tape=tape)
         kw = dict(is_multi_agent=1, ma_places=len(self.tables["places"]), ma_dests=self.tables["n_dests"],
                   ma_roads=self.tables["n_roads"], tape_len=TAPE_LEN)
         kw.update(cfg_kw)
-        return arrays, make_config(n_envs, S, NA, 0, **kw)
+        return arrays, make_config(n_envs, S, NA, O, **kw)

@@ -1361,6 +1361,11 @@ def to_tables(big):
             respawn_roads=[roads.get(r, -1) for r in blk.respawn_roads],
             sockets=[[roads.get(s.positive, -1), roads.get(s.negative, -1) if s.negative is not None else -1]
                      for s in blk.sockets.values()]))
+        if getattr(blk, "buildings", None):
+            # TollGateBuilding (component/buildings/tollgate_building.py:7-26): a static box BUILDING_LENGTH = 10 long and one
+            # lane wide, centred on the lane: [lane id, x, y, heading, half length, half width]
+            blocks[-1]["buildings"] = [[lid(lane), float(pos[0]), float(pos[1]), float(heading), 5.0, lane.width / 2.0]
+                                       for lane, pos, heading in blk.buildings]
     meta = dict(nodes=list(nodes.keys()), blocks=blocks)
     return lane_f, lane_i, road_i, meta
 

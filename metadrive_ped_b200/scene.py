@@ -469,6 +469,7 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
             ob = obj_f[e * O:e * O + m]
             ob[:, 0:7] = sc.objects[:, 0:7]
             ob[:, 7] = sc.objects[:, 6] / 2  # shapes are centred at height/2 (base_static_object.py:24)
+            ob[sc.objects[:, 0] == 4, 7] = 0.0  # a TollGateBuilding is put back to z = 0 (buildings/tollgate_building.py:25)
             ob[:, 8] = sc.objects[:, 7]
             if sc.objects.shape[1] >= 10:
                 ob[:, 10:12] = sc.objects[:, 8:10]

