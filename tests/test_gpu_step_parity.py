@@ -60,9 +60,19 @@ def test_multi_agent_step_matches_oracle_and_golden(tag, oracle_lib):
         np.testing.assert_array_equal(sim.reward.cpu().numpy(), orc.reward)
         np.testing.assert_array_equal(og[valid], orc.obs[valid], err_msg="observations at step %d" % t)
         # env 0 against the reference's own trace
+        before = vs_g.copy()
         check_ma_step(g, t, (vs_g, sim.get_state("veh_i")),
                       (og, sim.reward.cpu().numpy(), sim.cost.cpu().numpy(), sim.terminated.cpu().numpy(),
                        sim.truncated.cpu().numpy(), fl), tag)
+        if not np.array_equal(before, vs_g):
+            # check_ma_step re-synchronised a wreck to the trace (the head-on toll-booth hit, documented there): the same rows go
+            # into every replica of both simulations, which stay bit-identical to each other
+            S = cfg.slots_per_env
+            for k in np.nonzero((before != vs_g).any(axis=1))[0]:
+                for e in range(1, cfg.n_envs):
+                    vs_g[e * S + k] = vs_g[k]
+            orc.a["veh_s"][:] = vs_g
+            sim.set_state("veh_s", vs_g)
     assert grazes[0] <= max(2, 1e-4 * grazes[1])
     sim.close()
 
