@@ -109,6 +109,11 @@ int md_host_compact(md_sim* sim, int compact);
 /* Lidar.perceive (component/sensors/lidar.py:49-73; sensors/distance_detector.py:27-85): frac_dev [A,n_lasers] in
  * [0,1]; hit_dev [A,n_lasers] = hit vehicle slot, slots_per_env + object index, or -1 */
 int md_lidar(md_sim* sim, float* frac_dev, int32_t* hit_dev, void* stream);
+/* TopDownObservation.observe (obs/top_down_obs.py:98-200, 221-229; obs/top_down_obs_impl.py:19-97, 203-250, 266-428 - the
+ * observation of envs/top_down_env.py:7-31 TopDownSingleFrameMetaDriveEnv): img_dev [A, resolution, resolution, 3] float32 RGB
+ * in [0, 1], the window of +-max_distance metres around every agent turned so that it looks up: lane lines, the ego GREEN,
+ * every other vehicle BLUE; an empty seat's image is black.  Reads the current state, changes nothing. */
+int md_topdown(md_sim* sim, float* img_dev, int resolution, float max_distance, void* stream);
 /* n_sub x BulletWorld.doPhysics(dt,1,dt) for every vehicle with given actuation act3_dev [NV,3] = steering rad,
  * engine force, brake (component/vehicle/base_vehicle.py:447-484; engine/core/engine_core.py:350-352) */
 int md_dynamics(md_sim* sim, const float* act3_dev, int n_sub, void* stream);

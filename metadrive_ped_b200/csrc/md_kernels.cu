@@ -3616,6 +3616,136 @@ extern "C" int md_profile_end(md_sim* sim, float* ms, int cap) {
     return n;
 }
 
+// ---- TopDownObservation (obs/top_down_obs.py:98-200; obs/top_down_obs_impl.py:19-97, 203-250, 266-428): the ego-centred
+// bird's-eye RGB image of TopDownSingleFrameMetaDriveEnv (envs/top_down_env.py:7-31), [A, res, res, 3] in [0, 1].  The scene the
+// reference paints with pygame - lane lines (35, 35, 35) 0.3 m wide, the ego GREEN, every other vehicle BLUE (headings under 2
+// degrees snapped to 0), the window of +-max_distance turned so that the ego looks up, its left on the image's right - is
+// evaluated analytically at the centre of every output pixel (oracle/md_oracle.c: mdo_topdown states the rules; pygame is not
+// on this image, its rasteriser is not pinned).  One CTA per 16 x 16 pixel tile of one agent: the vehicles' rectangles and the
+// line segments near the tile (through the static grid) are staged in shared memory once, then every thread shades its pixel.
+#define TD_TILE 16
+#define TD_MAX_LINES 768
+#define TD_LINE_HW 0.15f
+#define TD_SNAP_TAN 0.03492077f
+__device__ __forceinline__ Rect td_snap(Rect r) {
+    if (r.ux > 0.0f && fabsf(r.uy) <= TD_SNAP_TAN * r.ux) { r.ux = 1.0f; r.uy = 0.0f; }
+    return r;
+}
+__device__ __forceinline__ bool td_inside(const Rect& r, float x, float y) {
+    const float dx = x - r.cx, dy = y - r.cy;
+    return fabsf(dx * r.ux + dy * r.uy) <= r.hu && fabsf(dy * r.ux - dx * r.uy) <= r.hv;
+}
+__device__ __forceinline__ float td_cover(float cx, float cy, float half, float ux, float uy, float x, float y, float px) {
+    const float dx = x - cx, dy = y - cy;
+    const float al = fabsf(dx * ux + dy * uy), pe = fabsf(dy * ux - dx * uy);
+    const float cp = clipf((TD_LINE_HW + 0.5f * px - pe) / px, 0.0f, 1.0f);
+    const float ca = clipf((half + 0.5f * px - al) / px, 0.0f, 1.0f);
+    return cp * ca;
+}
+__global__ void __launch_bounds__(TD_TILE * TD_TILE)
+k_topdown(MdConfig cfg, MdArrays A, float* __restrict__ img, int res, float max_distance) {
+    __shared__ Rect s_other[128];
+    __shared__ int s_alive[128];
+    __shared__ Rect s_ego;
+    __shared__ float s_line[TD_MAX_LINES * 5];
+    __shared__ int s_n;
+    const int S = cfg.slots_per_env, NA = cfg.agents_per_env;
+    const int a = blockIdx.x, env = a / NA, slot = a - env * NA;
+    const int tiles = (res + TD_TILE - 1) / TD_TILE;
+    const int ty = blockIdx.y / tiles, tx = blockIdx.y - ty * tiles;
+    const int r = ty * TD_TILE + threadIdx.x / TD_TILE, c = tx * TD_TILE + (threadIdx.x & (TD_TILE - 1));
+    const bool in_img = r < res && c < res;
+    float* o = img + ((size_t)a * res * res + (size_t)r * res + c) * 3;
+    const size_t g0 = (size_t)env * S;
+    if (!A.veh_i[(g0 + slot) * VEH_I + VI_ALIVE]) {   // an empty seat: a black image
+        if (in_img) { o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f; }
+        return;
+    }
+    for (int k = threadIdx.x; k < S; k += blockDim.x) {
+        const size_t g = g0 + k;
+        const int alive = A.veh_i[g * VEH_I + VI_ALIVE];
+        s_alive[k] = alive && k != slot;
+        if (alive) {
+            float P[VEH_P], St[VEH_S];
+            load16(P, A.veh_p + g * VEH_P);
+            load16(St, A.veh_s + g * VEH_S);
+            const Rect rr = vehicle_rect(P, St);
+            if (k == slot) s_ego = rr;
+            else s_other[k] = td_snap(rr);
+        }
+    }
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const Rect ego = s_ego;
+    const float px = 2.0f * max_distance / (float)res;
+    const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+    // the tile's centre and the radius that holds every pixel centre of it plus a line's reach (half width + one pixel)
+    const float uc = ((float)(tx * TD_TILE) + 0.5f * TD_TILE - 0.5f * (float)res) * px;
+    const float vc = (0.5f * (float)res - ((float)(ty * TD_TILE) + 0.5f * TD_TILE)) * px;
+    const float tcx = ego.cx + (vc * ego.ux - uc * ego.uy), tcy = ego.cy + (vc * ego.uy + uc * ego.ux);
+    const float reach = 0.70710678f * TD_TILE * px + TD_LINE_HW + px;
+    int x0 = (int)floorf((tcx - reach - m.gx0) / m.cell), x1 = (int)floorf((tcx + reach - m.gx0) / m.cell);
+    int y0 = (int)floorf((tcy - reach - m.gy0) / m.cell), y1 = (int)floorf((tcy + reach - m.gy0) / m.cell);
+    x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, m.nx - 1); y1 = min(y1, m.ny - 1);
+    for (int cy = y0; cy <= y1; cy++)
+        for (int cx = x0; cx <= x1; cx++) {
+            const int cell = cy * m.nx + cx;
+            for (int k = m.gs[cell] + threadIdx.x; k < m.gs[cell + 1]; k += blockDim.x) {
+                const int it = m.gi[k];
+                if (it >= m.n_lines) continue;
+                const float* Ln = m.lines + (size_t)it * LINE_F;
+                const float dx = Ln[LN_CX] - tcx, dy = Ln[LN_CY] - tcy, rr = reach + Ln[LN_HALF];
+                if (dx * dx + dy * dy > rr * rr) continue;
+                const int j = atomicAdd(&s_n, 1);
+                if (j < TD_MAX_LINES) {
+                    s_line[5 * j] = Ln[LN_CX]; s_line[5 * j + 1] = Ln[LN_CY]; s_line[5 * j + 2] = Ln[LN_HALF];
+                    s_line[5 * j + 3] = Ln[LN_UX]; s_line[5 * j + 4] = Ln[LN_UY];
+                }
+            }
+        }
+    __syncthreads();
+    if (!in_img) return;
+    const float u = ((float)c + 0.5f - 0.5f * (float)res) * px, v = (0.5f * (float)res - ((float)r + 0.5f)) * px;
+    const float x = ego.cx + (v * ego.ux - u * ego.uy), y = ego.cy + (v * ego.uy + u * ego.ux);
+    bool hit = false;
+    for (int k = 0; k < S && !hit; k++) hit = s_alive[k] && td_inside(s_other[k], x, y);
+    if (hit) { o[0] = 100.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 1.0f; return; }
+    if (td_inside(td_snap(ego), x, y)) { o[0] = 50.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 0.0f; return; }
+    float best = 0.0f;
+    const int n = s_n;
+    if (n <= TD_MAX_LINES) {
+        for (int k = 0; k < n; k++)
+            best = fmaxf(best, td_cover(s_line[5 * k], s_line[5 * k + 1], s_line[5 * k + 2], s_line[5 * k + 3], s_line[5 * k + 4], x, y, px));
+    } else {   // more segments around the tile than the staging area holds: walk the grid cells directly
+        for (int cy = y0; cy <= y1; cy++)
+            for (int cx = x0; cx <= x1; cx++) {
+                const int cell = cy * m.nx + cx;
+                for (int k = m.gs[cell]; k < m.gs[cell + 1]; k++) {
+                    const int it = m.gi[k];
+                    if (it >= m.n_lines) continue;
+                    const float* Ln = m.lines + (size_t)it * LINE_F;
+                    best = fmaxf(best, td_cover(Ln[LN_CX], Ln[LN_CY], Ln[LN_HALF], Ln[LN_UX], Ln[LN_UY], x, y, px));
+                }
+            }
+    }
+    o[0] = o[1] = o[2] = best * (35.0f / 255.0f);
+}
+
+extern "C" int md_topdown(md_sim* sim, float* img_dev, int resolution, float max_distance, void* stream) {
+    if (!sim || !sim->loaded) return -2;
+    if (img_dev == nullptr || resolution <= 0 || !(max_distance > 0.0f) || sim->cfg.slots_per_env > 128) {
+        sim->err = "md_topdown: needs an output buffer, resolution > 0, max_distance > 0 and at most 128 slots per env";
+        return -3;
+    }
+    CK(cudaSetDevice(sim->device));
+    const int tiles = (resolution + TD_TILE - 1) / TD_TILE;
+    dim3 grid((unsigned)(sim->cfg.n_envs * sim->cfg.agents_per_env), (unsigned)(tiles * tiles));
+    k_topdown<<<grid, TD_TILE * TD_TILE, 0, (cudaStream_t)stream>>>(sim->cfg, sim->dev, img_dev, resolution, max_distance);
+    sim->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int md_lidar(md_sim* sim, float* frac_dev, int32_t* hit_dev, void* stream) {
     if (!sim || !sim->loaded) return -2;
     CK(cudaSetDevice(sim->device));

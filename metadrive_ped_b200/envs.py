@@ -459,6 +459,31 @@ class SafeMetaDriveEnv(MetaDriveEnv):
         return info
 
 
+class TopDownSingleFrameMetaDriveEnv(MetaDriveEnv):
+    """envs/top_down_env.py:7-31: MetaDriveEnv whose observation is TopDownObservation (obs/top_down_obs.py) - the ego-centred
+    bird's-eye RGB image [resolution_size, resolution_size, 3] of the +-distance metres around the ego (float32 in [0, 1] with
+    norm_pixel, else uint8), rendered on the device by md_topdown.  frame_stack / post_stack / frame_skip are the keys of the
+    stacked multi-channel variant (TopDownMetaDrive) and are accepted but unused here, as in the reference's class."""
+    EXTRA_DEFAULTS = dict(frame_skip=5, frame_stack=3, post_stack=5, norm_pixel=True, resolution_size=84, distance=30)
+
+    def __init__(self, config=None):
+        super().__init__(config)
+        n = int(self.config["resolution_size"])
+        self.observation_space = _box(-0.0, 1.0, (n, n, 3)) if self.config["norm_pixel"] else Box(0, 255, (n, n, 3), np.uint8)
+
+    def _image(self):
+        img = self._sim.topdown(int(self.config["resolution_size"]), float(self.config["distance"]))[0].cpu().numpy()
+        return img if self.config["norm_pixel"] else (img * 255.0).astype(np.uint8)
+
+    def reset(self, seed=None):
+        _, info = super().reset(seed)
+        return self._image(), info
+
+    def step(self, action):
+        _, r, te, tr, info = super().step(action)
+        return self._image(), r, te, tr, info
+
+
 class BatchedMetaDriveEnv:
     """E independent MetaDriveEnv instances stepped per call, device tensors in and out (the fast path the Gym dict
     surface cannot offer at 10^6+ steps/s).  Finished envs reset in place on device."""

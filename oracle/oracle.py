@@ -114,6 +114,12 @@ class OracleSim:
         lib().mdo_lidar(C.byref(self.cfg), C.byref(self.A), _p(self.ray_cs), _p(frac), _p(hit))
         return frac, hit
 
+    def topdown(self, resolution=84, max_distance=30.0):
+        """[n_agents, res, res, 3] RGB in [0, 1]: the ego-centred bird's-eye image (mdo_topdown)"""
+        img = np.zeros((self.n_agents, resolution, resolution, 3), np.float32)
+        lib().mdo_topdown(C.byref(self.cfg), C.byref(self.A), _p(img), C.c_int(resolution), C.c_float(max_distance))
+        return img
+
     def dynamics(self, act3, n_sub):
         act3 = np.ascontiguousarray(act3, np.float32)
         lib().mdo_dynamics(C.byref(self.cfg), C.byref(self.A), _p(act3), C.c_int(n_sub))
