@@ -3621,8 +3621,9 @@ extern "C" int md_profile_end(md_sim* sim, float* ms, int cap) {
 // reference paints with pygame - lane lines (35, 35, 35) 0.3 m wide, the ego GREEN, every other vehicle BLUE (headings under 2
 // degrees snapped to 0), the window of +-max_distance turned so that the ego looks up, its left on the image's right - is
 // evaluated analytically at the centre of every output pixel (oracle/md_oracle.c: mdo_topdown states the rules; pygame is not
-// on this image, its rasteriser is not pinned).  One CTA per 16 x 16 pixel tile of one agent: the vehicles' rectangles and the
-// line segments near the tile (through the static grid) are staged in shared memory once, then every thread shades its pixel.
+// on this image, its rasteriser is not pinned).  One CTA per row of 16 x 16 pixel tiles of one agent: the vehicles' rectangles
+// are staged in shared memory once, the line segments near each tile (through the static grid) once per tile, then every thread
+// shades its pixel.
 #define TD_TILE 16
 #define TD_MAX_LINES 768
 #define TD_LINE_HW 0.15f
@@ -3635,36 +3636,39 @@ __device__ __forceinline__ bool td_inside(const Rect& r, float x, float y) {
     const float dx = x - r.cx, dy = y - r.cy;
     return fabsf(dx * r.ux + dy * r.uy) <= r.hu && fabsf(dy * r.ux - dx * r.uy) <= r.hv;
 }
-__device__ __forceinline__ float td_cover(float cx, float cy, float half, float ux, float uy, float x, float y, float px) {
+// box-filtered coverage of the pixel (side px, centre (x, y)) by a segment's 2 * TD_LINE_HW wide box: the product of the
+// overlaps across and along the segment, each as a fraction of a pixel.  Most segments near a tile miss a given pixel across:
+// that test comes first and costs five operations.
+__device__ __forceinline__ float td_cover(float cx, float cy, float half, float ux, float uy, float x, float y, float px, float inv_px) {
     const float dx = x - cx, dy = y - cy;
-    const float al = fabsf(dx * ux + dy * uy), pe = fabsf(dy * ux - dx * uy);
-    const float cp = clipf((TD_LINE_HW + 0.5f * px - pe) / px, 0.0f, 1.0f);
-    const float ca = clipf((half + 0.5f * px - al) / px, 0.0f, 1.0f);
-    return cp * ca;
+    const float tp = (TD_LINE_HW + 0.5f * px) - fabsf(dy * ux - dx * uy);
+    if (tp <= 0.0f) return 0.0f;
+    const float ta = (half + 0.5f * px) - fabsf(dx * ux + dy * uy);
+    if (ta <= 0.0f) return 0.0f;
+    return fminf(tp * inv_px, 1.0f) * fminf(ta * inv_px, 1.0f);
 }
 __global__ void __launch_bounds__(TD_TILE * TD_TILE)
-k_topdown(MdConfig cfg, MdArrays A, float* __restrict__ img, int res, float max_distance) {
+k_topdown(MdConfig cfg, MdArrays A, MapAccel X, float* __restrict__ img, int res, float max_distance) {
     __shared__ Rect s_other[128];
-    __shared__ int s_alive[128];
+    __shared__ int s_base[128], s_alive[128];
     __shared__ Rect s_ego;
     __shared__ float s_line[TD_MAX_LINES * 5];
     __shared__ int s_n;
     const int S = cfg.slots_per_env, NA = cfg.agents_per_env;
     const int a = blockIdx.x, env = a / NA, slot = a - env * NA;
-    const int tiles = (res + TD_TILE - 1) / TD_TILE;
-    const int ty = blockIdx.y / tiles, tx = blockIdx.y - ty * tiles;
-    const int r = ty * TD_TILE + threadIdx.x / TD_TILE, c = tx * TD_TILE + (threadIdx.x & (TD_TILE - 1));
-    const bool in_img = r < res && c < res;
-    float* o = img + ((size_t)a * res * res + (size_t)r * res + c) * 3;
+    const int tiles = (res + TD_TILE - 1) / TD_TILE, ty = blockIdx.y;   // one CTA per ROW of tiles: the agent's set-up is paid once
+    const int r = ty * TD_TILE + threadIdx.x / TD_TILE;
     const size_t g0 = (size_t)env * S;
+    float* row = img + ((size_t)a * res * res + (size_t)r * res) * 3;
     if (!A.veh_i[(g0 + slot) * VEH_I + VI_ALIVE]) {   // an empty seat: a black image
-        if (in_img) { o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f; }
+        if (r < res)
+            for (int c = threadIdx.x & (TD_TILE - 1); c < res; c += TD_TILE) { row[3 * c] = 0.0f; row[3 * c + 1] = 0.0f; row[3 * c + 2] = 0.0f; }
         return;
     }
     for (int k = threadIdx.x; k < S; k += blockDim.x) {
         const size_t g = g0 + k;
         const int alive = A.veh_i[g * VEH_I + VI_ALIVE];
-        s_alive[k] = alive && k != slot;
+        s_base[k] = alive && k != slot;
         if (alive) {
             float P[VEH_P], St[VEH_S];
             load16(P, A.veh_p + g * VEH_P);
@@ -3674,61 +3678,82 @@ k_topdown(MdConfig cfg, MdArrays A, float* __restrict__ img, int res, float max_
             else s_other[k] = td_snap(rr);
         }
     }
-    if (threadIdx.x == 0) s_n = 0;
+    const float px = 2.0f * max_distance / (float)res, inv_px = 1.0f / px;
+    const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP], &X);
     __syncthreads();
-    const Rect ego = s_ego;
-    const float px = 2.0f * max_distance / (float)res;
-    const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
-    // the tile's centre and the radius that holds every pixel centre of it plus a line's reach (half width + one pixel)
-    const float uc = ((float)(tx * TD_TILE) + 0.5f * TD_TILE - 0.5f * (float)res) * px;
+    const Rect ego = s_ego, ego_box = td_snap(ego);
     const float vc = (0.5f * (float)res - ((float)(ty * TD_TILE) + 0.5f * TD_TILE)) * px;
-    const float tcx = ego.cx + (vc * ego.ux - uc * ego.uy), tcy = ego.cy + (vc * ego.uy + uc * ego.ux);
+    const float v = (0.5f * (float)res - ((float)r + 0.5f)) * px;
+    // a tile's radius: every pixel centre of it, plus a line's reach (half width + one pixel)
     const float reach = 0.70710678f * TD_TILE * px + TD_LINE_HW + px;
-    int x0 = (int)floorf((tcx - reach - m.gx0) / m.cell), x1 = (int)floorf((tcx + reach - m.gx0) / m.cell);
-    int y0 = (int)floorf((tcy - reach - m.gy0) / m.cell), y1 = (int)floorf((tcy + reach - m.gy0) / m.cell);
-    x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, m.nx - 1); y1 = min(y1, m.ny - 1);
-    for (int cy = y0; cy <= y1; cy++)
-        for (int cx = x0; cx <= x1; cx++) {
-            const int cell = cy * m.nx + cx;
-            for (int k = m.gs[cell] + threadIdx.x; k < m.gs[cell + 1]; k += blockDim.x) {
-                const int it = m.gi[k];
+    for (int tx = 0; tx < tiles; tx++) {
+        const float uc = ((float)(tx * TD_TILE) + 0.5f * TD_TILE - 0.5f * (float)res) * px;
+        const float tcx = ego.cx + (vc * ego.ux - uc * ego.uy), tcy = ego.cy + (vc * ego.uy + uc * ego.ux);
+        if (threadIdx.x == 0) s_n = 0;
+        for (int k = threadIdx.x; k < S; k += blockDim.x) {   // vehicles that cannot reach into this tile are dropped here
+            int near = s_base[k];
+            if (near) {
+                const Rect& q = s_other[k];
+                const float dx = q.cx - tcx, dy = q.cy - tcy, rr = 0.70710678f * TD_TILE * px + q.hu + q.hv;
+                near = dx * dx + dy * dy <= rr * rr;
+            }
+            s_alive[k] = near;
+        }
+        __syncthreads();
+        int x0 = (int)floorf((tcx - reach - m.gx0) / m.cell), x1 = (int)floorf((tcx + reach - m.gx0) / m.cell);
+        int y0 = (int)floorf((tcy - reach - m.gy0) / m.cell), y1 = (int)floorf((tcy + reach - m.gy0) / m.cell);
+        x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, m.nx - 1); y1 = min(y1, m.ny - 1);
+        // one warp per grid cell under the tile, its lanes over the cell's items; the item's row sits next to the item in the
+        // grid records (MapAccel), so a lane waits for the cell's range and then for ONE round of loads
+        const int ncx = x1 - x0 + 1, n_cells = ncx * (y1 - y0 + 1);
+        for (int ci = threadIdx.x >> 5; ci < n_cells; ci += (TD_TILE * TD_TILE) >> 5) {
+            const int cell = (y0 + ci / ncx) * m.nx + x0 + ci % ncx;
+            const int k1 = m.gs[cell + 1];
+            for (int k = m.gs[cell] + (threadIdx.x & 31); k < k1; k += 32) {
+                const int it = __ldg(m.gi + k);
+                const float4 h = __ldg(m.irec + 2 * k), d = __ldg(m.irec + 2 * k + 1);   // cx cy half kind | ux uy . .
                 if (it >= m.n_lines) continue;
-                const float* Ln = m.lines + (size_t)it * LINE_F;
-                const float dx = Ln[LN_CX] - tcx, dy = Ln[LN_CY] - tcy, rr = reach + Ln[LN_HALF];
+                const float dx = h.x - tcx, dy = h.y - tcy, rr = reach + h.z;
                 if (dx * dx + dy * dy > rr * rr) continue;
                 const int j = atomicAdd(&s_n, 1);
                 if (j < TD_MAX_LINES) {
-                    s_line[5 * j] = Ln[LN_CX]; s_line[5 * j + 1] = Ln[LN_CY]; s_line[5 * j + 2] = Ln[LN_HALF];
-                    s_line[5 * j + 3] = Ln[LN_UX]; s_line[5 * j + 4] = Ln[LN_UY];
+                    s_line[5 * j] = h.x; s_line[5 * j + 1] = h.y; s_line[5 * j + 2] = h.z; s_line[5 * j + 3] = d.x; s_line[5 * j + 4] = d.y;
                 }
             }
         }
-    __syncthreads();
-    if (!in_img) return;
-    const float u = ((float)c + 0.5f - 0.5f * (float)res) * px, v = (0.5f * (float)res - ((float)r + 0.5f)) * px;
-    const float x = ego.cx + (v * ego.ux - u * ego.uy), y = ego.cy + (v * ego.uy + u * ego.ux);
-    bool hit = false;
-    for (int k = 0; k < S && !hit; k++) hit = s_alive[k] && td_inside(s_other[k], x, y);
-    if (hit) { o[0] = 100.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 1.0f; return; }
-    if (td_inside(td_snap(ego), x, y)) { o[0] = 50.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 0.0f; return; }
-    float best = 0.0f;
-    const int n = s_n;
-    if (n <= TD_MAX_LINES) {
-        for (int k = 0; k < n; k++)
-            best = fmaxf(best, td_cover(s_line[5 * k], s_line[5 * k + 1], s_line[5 * k + 2], s_line[5 * k + 3], s_line[5 * k + 4], x, y, px));
-    } else {   // more segments around the tile than the staging area holds: walk the grid cells directly
-        for (int cy = y0; cy <= y1; cy++)
-            for (int cx = x0; cx <= x1; cx++) {
-                const int cell = cy * m.nx + cx;
-                for (int k = m.gs[cell]; k < m.gs[cell + 1]; k++) {
-                    const int it = m.gi[k];
-                    if (it >= m.n_lines) continue;
-                    const float* Ln = m.lines + (size_t)it * LINE_F;
-                    best = fmaxf(best, td_cover(Ln[LN_CX], Ln[LN_CY], Ln[LN_HALF], Ln[LN_UX], Ln[LN_UY], x, y, px));
+        __syncthreads();
+        const int c = tx * TD_TILE + (threadIdx.x & (TD_TILE - 1));
+        if (r < res && c < res) {
+            float* o = row + 3 * c;
+            const float u = ((float)c + 0.5f - 0.5f * (float)res) * px;
+            const float x = ego.cx + (v * ego.ux - u * ego.uy), y = ego.cy + (v * ego.uy + u * ego.ux);
+            bool hit = false;
+            for (int k = 0; k < S && !hit; k++) hit = s_alive[k] && td_inside(s_other[k], x, y);
+            if (hit) { o[0] = 100.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 1.0f; }                      // ObjectGraphics.BLUE
+            else if (td_inside(ego_box, x, y)) { o[0] = 50.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 0.0f; }   // GREEN
+            else {
+                float best = 0.0f;
+                const int n = s_n;
+                if (n <= TD_MAX_LINES) {
+                    for (int k = 0; k < n; k++)
+                        best = fmaxf(best, td_cover(s_line[5 * k], s_line[5 * k + 1], s_line[5 * k + 2], s_line[5 * k + 3], s_line[5 * k + 4], x, y, px, inv_px));
+                } else {   // more segments around the tile than the staging area holds: walk the grid cells directly
+                    for (int cy = y0; cy <= y1; cy++)
+                        for (int cx = x0; cx <= x1; cx++) {
+                            const int cell = cy * m.nx + cx;
+                            for (int k = m.gs[cell]; k < m.gs[cell + 1]; k++) {
+                                const int it = m.gi[k];
+                                if (it >= m.n_lines) continue;
+                                const float* Ln = m.lines + (size_t)it * LINE_F;
+                                best = fmaxf(best, td_cover(Ln[LN_CX], Ln[LN_CY], Ln[LN_HALF], Ln[LN_UX], Ln[LN_UY], x, y, px, inv_px));
+                            }
+                        }
                 }
+                o[0] = o[1] = o[2] = best * (35.0f / 255.0f);   // WorldSurface.LANE_LINE_COLOR
             }
+        }
+        __syncthreads();   // the next tile restages s_line / s_alive
     }
-    o[0] = o[1] = o[2] = best * (35.0f / 255.0f);
 }
 
 extern "C" int md_topdown(md_sim* sim, float* img_dev, int resolution, float max_distance, void* stream) {
@@ -3739,8 +3764,8 @@ extern "C" int md_topdown(md_sim* sim, float* img_dev, int resolution, float max
     }
     CK(cudaSetDevice(sim->device));
     const int tiles = (resolution + TD_TILE - 1) / TD_TILE;
-    dim3 grid((unsigned)(sim->cfg.n_envs * sim->cfg.agents_per_env), (unsigned)(tiles * tiles));
-    k_topdown<<<grid, TD_TILE * TD_TILE, 0, (cudaStream_t)stream>>>(sim->cfg, sim->dev, img_dev, resolution, max_distance);
+    dim3 grid((unsigned)(sim->cfg.n_envs * sim->cfg.agents_per_env), (unsigned)tiles);
+    k_topdown<<<grid, TD_TILE * TD_TILE, 0, (cudaStream_t)stream>>>(sim->cfg, sim->dev, sim->accel, img_dev, resolution, max_distance);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
