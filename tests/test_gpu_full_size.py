@@ -17,6 +17,13 @@ MUTABLE = ("env_i", "veh_s", "veh_c", "veh_i", "veh_idm", "veh_navi", "obj_f", "
 
 def _world(workload, n_envs=None):
     import bench
+    if workload == "toll":
+        # MultiAgentTollgateEnv at its default 40 agents (envs/marl_envs/marl_tollgate.py:15-36), 48 envs: booths, the toll
+        # observation, overspeed penalties and the stay-time rule under random driving
+        from metadrive_ped_b200.envs import MultiAgentTollgateEnv, _ma_cfg_kw
+        from metadrive_ped_b200.ma import MultiAgentLibrary
+        c = MultiAgentTollgateEnv.default_config()
+        return MultiAgentLibrary(MultiAgentTollgateEnv.ASSET).build_world(n_envs or 48, c["num_agents"], seed=3, **_ma_cfg_kw(c))
     n = n_envs or bench.WORKLOADS[workload]["envs"]
     _, arrays, cfg = bench.build_world(n, 0, workload)
     return arrays, cfg
@@ -30,6 +37,15 @@ def _actions(rng, cfg, multi):
     """Every agent its own action sequence: throttle mostly forward, steering = a per-agent bias + noise, so that within
     a few dozen steps agents leave the road, hit traffic / cones / pedestrians, and (multi-agent) arrive and respawn."""
     n = cfg.n_envs * cfg.agents_per_env
+    if cfg.toll_env:
+        # the tollgate map is one straight road: nearly straight driving at every agent's own pace brings most of them to the toll
+        # block (some into a booth, most through it too fast, a slow few staying long enough), a weaving tenth off the lanes
+        a = np.zeros((n, 2), np.float32)
+        weave = np.random.RandomState(12).uniform(0, 1, n) < 0.1
+        a[:, 0] = np.where(weave, 0.15, 0.01) * rng.uniform(-1.0, 1.0, n)
+        pace = np.random.RandomState(13).uniform(0.05, 1.0, n)
+        a[:, 1] = pace * rng.uniform(0.2, 1.0, n)
+        return a.astype(np.float32)
     bias = np.random.RandomState(11).uniform(-0.25, 0.25, n)
     a = rng.uniform(-1.0, 1.0, (n, 2)).astype(np.float32)
     a[:, 0] = (0.3 * a[:, 0] + bias).astype(np.float32)
@@ -37,13 +53,13 @@ def _actions(rng, cfg, multi):
     return a
 
 
-@pytest.mark.parametrize("workload,steps", [("cfg2", 60), ("cfg4", 40), ("cfg5", 40), ("cfg3", 25)])
+@pytest.mark.parametrize("workload,steps", [("cfg2", 60), ("cfg4", 40), ("cfg5", 40), ("cfg3", 25), ("toll", 150)])
 def test_full_size_step_matches_oracle(workload, steps, oracle_lib):
     import torch
     from metadrive_ped_b200.sim import BatchedSim
     from oracle.oracle import OracleSim, set_threads
     set_threads()
-    multi = workload == "cfg3"
+    multi = workload in ("cfg3", "toll")
     arrays, cfg = _world(workload)
     E, S, NA, O = cfg.n_envs, cfg.slots_per_env, cfg.agents_per_env, cfg.objs_per_env
     sim, orc = BatchedSim(arrays, cfg), OracleSim(arrays, cfg)
