@@ -114,6 +114,11 @@ int md_lidar(md_sim* sim, float* frac_dev, int32_t* hit_dev, void* stream);
  * in [0, 1], the window of +-max_distance metres around every agent turned so that it looks up: lane lines, the ego GREEN,
  * every other vehicle BLUE; an empty seat's image is black.  Reads the current state, changes nothing. */
 int md_topdown(md_sim* sim, float* img_dev, int resolution, float max_distance, void* stream);
+/* The per-frame grey channels TopDownMultiChannel stacks (obs/top_down_obs_multi_channel.py:101-146, 148-205, 216-270 - the
+ * observation of envs/top_down_env.py:34-48 TopDownMetaDrive): img_dev [A, resolution, resolution, 2] float32 =
+ * [road_network: lane lines over the drivable area of the lanes of the agent's route, doubled and clipped as observe() does;
+ *  traffic_flow: the other vehicles].  The stacking over time (past frames, past positions) is host logic, as in the reference. */
+int md_topdown_channels(md_sim* sim, float* img_dev, int resolution, float max_distance, void* stream);
 /* n_sub x BulletWorld.doPhysics(dt,1,dt) for every vehicle with given actuation act3_dev [NV,3] = steering rad,
  * engine force, brake (component/vehicle/base_vehicle.py:447-484; engine/core/engine_core.py:350-352) */
 int md_dynamics(md_sim* sim, const float* act3_dev, int n_sub, void* stream);

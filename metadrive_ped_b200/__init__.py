@@ -4,6 +4,6 @@ Only the step path lives here (include/mdstep.h is the boundary): hand-written s
 binding (lib, sim), host-side scene tables (scene, library) and the drop-in env classes (envs)."""
 from .envs import (BatchedMetaDriveEnv, BatchedMultiAgentEnv, MetaDriveEnv, MultiAgentBottleneckEnv,  # noqa: F401
                    MultiAgentIntersectionEnv, MultiAgentMetaDrive, MultiAgentRoundaboutEnv, MultiAgentTollgateEnv,
-                   SafeMetaDriveEnv, TopDownSingleFrameMetaDriveEnv)
+                   SafeMetaDriveEnv, TopDownMetaDrive, TopDownSingleFrameMetaDriveEnv)
 
 __version__ = "0.1.0"

@@ -3647,6 +3647,11 @@ __device__ __forceinline__ float td_cover(float cx, float cy, float half, float 
     if (ta <= 0.0f) return 0.0f;
     return fminf(tp * inv_px, 1.0f) * fminf(ta * inv_px, 1.0f);
 }
+// CH = 3: the RGB image of TopDownObservation.  CH = 2: the two per-frame grey channels TopDownMultiChannel stacks
+// (obs/top_down_obs_multi_channel.py:101-146, 235-270): [road_network = lane lines (35) over the drivable area of the route's
+// lanes (64), doubled and clipped as observe() does; traffic_flow = the other vehicles in the grey of ObjectGraphics.BLUE]
+#define TD_MAX_ROUTE_LANES 160
+template <int CH>
 __global__ void __launch_bounds__(TD_TILE * TD_TILE)
 k_topdown(MdConfig cfg, MdArrays A, MapAccel X, float* __restrict__ img, int res, float max_distance) {
     __shared__ Rect s_other[128];
@@ -3654,17 +3659,22 @@ k_topdown(MdConfig cfg, MdArrays A, MapAccel X, float* __restrict__ img, int res
     __shared__ Rect s_ego;
     __shared__ float s_line[TD_MAX_LINES * 5];
     __shared__ int s_n;
+    __shared__ int s_rl[CH == 2 ? TD_MAX_ROUTE_LANES : 1], s_rl_on[CH == 2 ? TD_MAX_ROUTE_LANES : 1];
+    __shared__ float4 s_rl_bb[CH == 2 ? TD_MAX_ROUTE_LANES : 1];
+    __shared__ int s_nrl;
     const int S = cfg.slots_per_env, NA = cfg.agents_per_env;
     const int a = blockIdx.x, env = a / NA, slot = a - env * NA;
     const int tiles = (res + TD_TILE - 1) / TD_TILE, ty = blockIdx.y;   // one CTA per ROW of tiles: the agent's set-up is paid once
     const int r = ty * TD_TILE + threadIdx.x / TD_TILE;
     const size_t g0 = (size_t)env * S;
-    float* row = img + ((size_t)a * res * res + (size_t)r * res) * 3;
+    float* row = img + ((size_t)a * res * res + (size_t)r * res) * CH;
     if (!A.veh_i[(g0 + slot) * VEH_I + VI_ALIVE]) {   // an empty seat: a black image
         if (r < res)
-            for (int c = threadIdx.x & (TD_TILE - 1); c < res; c += TD_TILE) { row[3 * c] = 0.0f; row[3 * c + 1] = 0.0f; row[3 * c + 2] = 0.0f; }
+            for (int c = threadIdx.x & (TD_TILE - 1); c < res; c += TD_TILE)
+                for (int k = 0; k < CH; k++) row[CH * c + k] = 0.0f;
         return;
     }
+    if (threadIdx.x == 0) s_nrl = 0;
     for (int k = threadIdx.x; k < S; k += blockDim.x) {
         const size_t g = g0 + k;
         const int alive = A.veh_i[g * VEH_I + VI_ALIVE];
@@ -3681,6 +3691,22 @@ k_topdown(MdConfig cfg, MdArrays A, MapAccel X, float* __restrict__ img, int res
     const float px = 2.0f * max_distance / (float)res, inv_px = 1.0f / px;
     const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP], &X);
     __syncthreads();
+    if (CH == 2) {   // the lanes of the route's roads (draw_navigation_node, top_down_obs_multi_channel.py:272-277) and their boxes
+        const int n_seg = A.veh_i[(g0 + slot) * VEH_I + VI_ROUTE_LEN] - 1;
+        const int* rroad = A.veh_rroad + (g0 + slot) * ROUTE_MAX;
+        for (int k = threadIdx.x; k < n_seg; k += blockDim.x) {
+            const int rd = rroad[k];
+            if (rd < 0) continue;
+            const int first = m.road_i[rd * ROAD_I + RI_FIRST], nl = m.road_i[rd * ROAD_I + RI_N];
+            const int j0 = atomicAdd(&s_nrl, nl);
+            for (int j = 0; j < nl && j0 + j < TD_MAX_ROUTE_LANES; j++) {
+                s_rl[j0 + j] = first + j;
+                s_rl_bb[j0 + j] = __ldg(reinterpret_cast<const float4*>(m.lane_bb) + first + j);
+            }
+        }
+        __syncthreads();
+    }
+    const int n_rl = CH == 2 ? min(s_nrl, TD_MAX_ROUTE_LANES) : 0;
     const Rect ego = s_ego, ego_box = td_snap(ego);
     const float vc = (0.5f * (float)res - ((float)(ty * TD_TILE) + 0.5f * TD_TILE)) * px;
     const float v = (0.5f * (float)res - ((float)r + 0.5f)) * px;
@@ -3699,6 +3725,12 @@ k_topdown(MdConfig cfg, MdArrays A, MapAccel X, float* __restrict__ img, int res
             }
             s_alive[k] = near;
         }
+        if (CH == 2)   // route lanes whose box comes near this tile
+            for (int k = threadIdx.x; k < n_rl; k += blockDim.x) {
+                const float4 bb = s_rl_bb[k];
+                const float R = 0.70710678f * TD_TILE * px;
+                s_rl_on[k] = !(tcx + R < bb.x || tcx - R > bb.z || tcy + R < bb.y || tcy - R > bb.w);
+            }
         __syncthreads();
         int x0 = (int)floorf((tcx - reach - m.gx0) / m.cell), x1 = (int)floorf((tcx + reach - m.gx0) / m.cell);
         int y0 = (int)floorf((tcy - reach - m.gy0) / m.cell), y1 = (int)floorf((tcy + reach - m.gy0) / m.cell);
@@ -3724,15 +3756,14 @@ k_topdown(MdConfig cfg, MdArrays A, MapAccel X, float* __restrict__ img, int res
         __syncthreads();
         const int c = tx * TD_TILE + (threadIdx.x & (TD_TILE - 1));
         if (r < res && c < res) {
-            float* o = row + 3 * c;
+            float* o = row + CH * c;
             const float u = ((float)c + 0.5f - 0.5f * (float)res) * px;
             const float x = ego.cx + (v * ego.ux - u * ego.uy), y = ego.cy + (v * ego.uy + u * ego.ux);
             bool hit = false;
             for (int k = 0; k < S && !hit; k++) hit = s_alive[k] && td_inside(s_other[k], x, y);
-            if (hit) { o[0] = 100.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 1.0f; }                      // ObjectGraphics.BLUE
-            else if (td_inside(ego_box, x, y)) { o[0] = 50.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 0.0f; }   // GREEN
-            else {
-                float best = 0.0f;
+            const bool on_ego = CH == 3 && !hit && td_inside(ego_box, x, y);
+            float best = 0.0f;
+            if (CH == 2 || (!hit && !on_ego)) {
                 const int n = s_n;
                 if (n <= TD_MAX_LINES) {
                     for (int k = 0; k < n; k++)
@@ -3749,14 +3780,31 @@ k_topdown(MdConfig cfg, MdArrays A, MapAccel X, float* __restrict__ img, int res
                             }
                         }
                 }
-                o[0] = o[1] = o[2] = best * (35.0f / 255.0f);   // WorldSurface.LANE_LINE_COLOR
+            }
+            if (CH == 3) {
+                if (hit) { o[0] = 100.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 1.0f; }           // ObjectGraphics.BLUE
+                else if (on_ego) { o[0] = 50.0f / 255.0f; o[1] = 200.0f / 255.0f; o[2] = 0.0f; }   // GREEN
+                else o[0] = o[1] = o[2] = best * (35.0f / 255.0f);                                 // WorldSurface.LANE_LINE_COLOR
+            } else {
+                bool area = false;
+                for (int k = 0; k < n_rl && !area; k++) {
+                    if (!s_rl_on[k]) continue;
+                    const float4 bb = s_rl_bb[k];
+                    if (x < bb.x || y < bb.y || x > bb.z || y > bb.w) continue;
+                    const int l = s_rl[k];
+                    area = point_in_hull(m.lane_f + l * LANE_F, m.hull + 2 * m.lane_i[l * LANE_I + LI_HULL_OFF], m.lane_i[l * LANE_I + LI_HULL_N], x, y);
+                }
+                // the line is painted over the area; observe() doubles the road channel and clips it
+                const float road = best * (35.0f / 255.0f) + (1.0f - best) * (area ? 64.0f / 255.0f : 0.0f);
+                o[0] = fminf(road * 2.0f, 1.0f);
+                o[1] = hit ? 176.37f / 255.0f : 0.0f;   // 0.299 * 100 + 0.587 * 200 + 0.114 * 255 (_transform, :216-227)
             }
         }
         __syncthreads();   // the next tile restages s_line / s_alive
     }
 }
 
-extern "C" int md_topdown(md_sim* sim, float* img_dev, int resolution, float max_distance, void* stream) {
+static int topdown_impl(md_sim* sim, float* img_dev, int resolution, float max_distance, void* stream, int channels) {
     if (!sim || !sim->loaded) return -2;
     if (img_dev == nullptr || resolution <= 0 || !(max_distance > 0.0f) || sim->cfg.slots_per_env > 128) {
         sim->err = "md_topdown: needs an output buffer, resolution > 0, max_distance > 0 and at most 128 slots per env";
@@ -3765,10 +3813,19 @@ extern "C" int md_topdown(md_sim* sim, float* img_dev, int resolution, float max
     CK(cudaSetDevice(sim->device));
     const int tiles = (resolution + TD_TILE - 1) / TD_TILE;
     dim3 grid((unsigned)(sim->cfg.n_envs * sim->cfg.agents_per_env), (unsigned)tiles);
-    k_topdown<<<grid, TD_TILE * TD_TILE, 0, (cudaStream_t)stream>>>(sim->cfg, sim->dev, sim->accel, img_dev, resolution, max_distance);
+    if (channels == 3)
+        k_topdown<3><<<grid, TD_TILE * TD_TILE, 0, (cudaStream_t)stream>>>(sim->cfg, sim->dev, sim->accel, img_dev, resolution, max_distance);
+    else
+        k_topdown<2><<<grid, TD_TILE * TD_TILE, 0, (cudaStream_t)stream>>>(sim->cfg, sim->dev, sim->accel, img_dev, resolution, max_distance);
     sim->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+extern "C" int md_topdown(md_sim* sim, float* img_dev, int resolution, float max_distance, void* stream) {
+    return topdown_impl(sim, img_dev, resolution, max_distance, stream, 3);
+}
+extern "C" int md_topdown_channels(md_sim* sim, float* img_dev, int resolution, float max_distance, void* stream) {
+    return topdown_impl(sim, img_dev, resolution, max_distance, stream, 2);
 }
 
 extern "C" int md_lidar(md_sim* sim, float* frac_dev, int32_t* hit_dev, void* stream) {

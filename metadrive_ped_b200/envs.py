@@ -14,6 +14,8 @@ scenario libraries exported from the reference are its goldens (tests/test_pgmap
 A config outside what is restated raises, it is never silently approximated.  Rendering / image observation / manual
 control keys raise NotImplementedError.
 """
+import math
+
 import numpy as np
 
 from .abi import TRAFFIC_MODES
@@ -482,6 +484,70 @@ class TopDownSingleFrameMetaDriveEnv(MetaDriveEnv):
     def step(self, action):
         _, r, te, tr, info = super().step(action)
         return self._image(), r, te, tr, info
+
+
+class TopDownStack:
+    """The stacking TopDownMultiChannel does over time (obs/top_down_obs_multi_channel.py:44-60 the two deques, :163-182 the past
+    positions, :229-270 observe, :283-290 _get_stack_indices), host logic as in the reference.  observe() takes this step's
+    [road_network, traffic_flow] frames (md_topdown_channels) and returns [res, res, 2 + frame_stack]:
+    road_network | past positions | traffic now, frame_skip steps ago, 2 * frame_skip steps ago ..."""
+    def __init__(self, resolution, max_distance, frame_stack=5, post_stack=5, frame_skip=5):
+        from collections import deque
+        self.res, self.frame_skip, self.num_stacks = int(resolution), int(frame_skip), 2 + int(frame_stack)
+        self.traffic = deque([], maxlen=(frame_stack - 1) * frame_skip + 1)
+        self.past_pos = deque([], maxlen=(post_stack - 1) * frame_skip + 1)
+        self.scaling = resolution / max_distance   # the reference scales the past positions by resolution / distance (:57),
+        self.fill = True                           # twice the image's resolution / (2 * distance): kept
+
+    def reset(self):
+        self.fill = True   # the past positions are NOT cleared here: the reference clears them inside the first observe (:236-242)
+
+    def indices(self, length):
+        return [length - 1 - i * self.frame_skip for i in range(int(math.ceil(length / self.frame_skip)))]
+
+    def observe(self, road, traffic, position, heading_theta):
+        n = self.res
+        heading = heading_theta if abs(heading_theta) > 2 * np.pi / 180 else 0.0
+        self.past_pos.append(np.asarray(position, np.float64).copy())
+        past = np.zeros((n, n), np.float32)
+        for k in self.indices(len(self.past_pos)):
+            d = (self.past_pos[k] - self.past_pos[-1]) * self.scaling
+            fwd, left = d[0] * np.cos(heading) + d[1] * np.sin(heading), -d[0] * np.sin(heading) + d[1] * np.cos(heading)
+            # Vector2(dy, dx).rotate(deg(heading) + 90), swapped back and moved to the centre (:167-179): the canvas' x = left
+            # of the ego, y = behind it; Surface.fill((x, y), (1, 1)) truncates towards zero and clips to the surface
+            x, y = int(np.clip(left + n / 2, -n, n)), int(np.clip(-fwd + n / 2, -n, n))
+            if 0 <= x < n and 0 <= y < n:
+                past[y, x] = 1.0
+        if self.fill:
+            self.past_pos.clear()
+            self.traffic.clear()
+            for _ in range(self.traffic.maxlen):
+                self.traffic.append(traffic)
+            self.fill = False
+        self.traffic.append(traffic)
+        img = [road, past] + [self.traffic[i] for i in self.indices(len(self.traffic))]
+        return np.clip(np.stack(img, axis=2), 0.0, 1.0).astype(np.float32)
+
+
+class TopDownMetaDrive(TopDownSingleFrameMetaDriveEnv):
+    """envs/top_down_env.py:34-48: the stacked multi-channel bird's-eye observation (TopDownMultiChannel), [resolution_size,
+    resolution_size, 2 + frame_stack] float32 in [0, 1]; the two per-frame channels come from md_topdown_channels, TopDownStack
+    keeps the history"""
+    def __init__(self, config=None):
+        super().__init__(config)
+        c = self.config
+        assert c["norm_pixel"], "the stacked observation is built in [0, 1] (clip_rgb), as TopDownMetaDrive's default"
+        n = int(c["resolution_size"])
+        self._stack = TopDownStack(n, float(c["distance"]), c["frame_stack"], c["post_stack"], c["frame_skip"])
+        self.observation_space = _box(-0.0, 1.0, (n, n, self._stack.num_stacks))
+
+    def _image(self):
+        ch = self._sim.topdown(int(self.config["resolution_size"]), float(self.config["distance"]), channels=2)[0].cpu().numpy()
+        return self._stack.observe(ch[..., 0], ch[..., 1], self.agent.position, self.agent.heading_theta)
+
+    def reset(self, seed=None):
+        self._stack.reset()
+        return super().reset(seed)
 
 
 class BatchedMetaDriveEnv:

@@ -16,7 +16,7 @@ EXPORTS = [
     "md_get_state", "md_set_state", "md_snapshot", "md_launch_count", "md_profile_begin", "md_profile_end",
     "md_host_views", "md_attach_bank", "md_sizeof_config", "md_sizeof_arrays", "md_host_groups", "md_host_group_count",
     "md_host_group_views", "md_host_send", "md_host_recv", "md_host_compact", "md_fp32_peak", "md_enable_contacts", "md_get_contacts",
-    "md_topdown",
+    "md_topdown", "md_topdown_channels",
 ]
 ABI_VERSION = 6  # include/mdstep.h MD_ABI_VERSION
 
@@ -70,6 +70,7 @@ def load():
     lib.md_lidar.argtypes = [vp, vp, vp, vp]
     lib.md_dynamics.argtypes = [vp, vp, ip, vp]
     lib.md_topdown.argtypes = [vp, vp, ip, C.c_float, vp]
+    lib.md_topdown_channels.argtypes = [vp, vp, ip, C.c_float, vp]
     lib.md_after_step.argtypes = [vp, vp]
     lib.md_idm.argtypes = [vp, vp, vp]
     lib.md_get_state.argtypes = [vp, C.c_char_p, vp, C.c_size_t]

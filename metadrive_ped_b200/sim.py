@@ -184,14 +184,17 @@ class BatchedSim:
         self._check(self.lib.md_lidar(self.h, self._ptr(frac), self._ptr(hit), self._stream()))
         return frac, hit
 
-    def topdown(self, resolution=84, max_distance=30.0, out=None):
+    def topdown(self, resolution=84, max_distance=30.0, out=None, channels=3):
         """TopDownObservation (obs/top_down_obs.py): [n_agents, resolution, resolution, 3] float32 RGB in [0, 1], the window of
-        +-max_distance metres around every agent, turned so that it looks up (md_topdown)"""
+        +-max_distance metres around every agent, turned so that it looks up (md_topdown); channels=2: the per-frame
+        [road_network, traffic_flow] grey channels TopDownMultiChannel stacks (md_topdown_channels)"""
         t = self.torch
+        assert channels in (2, 3)
         if out is None:
-            out = t.empty((self.n_agents, resolution, resolution, 3), dtype=t.float32, device=self.tdev)
-        assert out.is_contiguous() and tuple(out.shape) == (self.n_agents, resolution, resolution, 3)
-        self._check(self.lib.md_topdown(self.h, self._ptr(out), int(resolution), float(max_distance), self._stream()))
+            out = t.empty((self.n_agents, resolution, resolution, channels), dtype=t.float32, device=self.tdev)
+        assert out.is_contiguous() and tuple(out.shape) == (self.n_agents, resolution, resolution, channels)
+        fn = self.lib.md_topdown if channels == 3 else self.lib.md_topdown_channels
+        self._check(fn(self.h, self._ptr(out), int(resolution), float(max_distance), self._stream()))
         return out
 
     def dynamics(self, act3, n_sub):

@@ -114,10 +114,11 @@ class OracleSim:
         lib().mdo_lidar(C.byref(self.cfg), C.byref(self.A), _p(self.ray_cs), _p(frac), _p(hit))
         return frac, hit
 
-    def topdown(self, resolution=84, max_distance=30.0):
-        """[n_agents, res, res, 3] RGB in [0, 1]: the ego-centred bird's-eye image (mdo_topdown)"""
-        img = np.zeros((self.n_agents, resolution, resolution, 3), np.float32)
-        lib().mdo_topdown(C.byref(self.cfg), C.byref(self.A), _p(img), C.c_int(resolution), C.c_float(max_distance))
+    def topdown(self, resolution=84, max_distance=30.0, channels=3):
+        """[n_agents, res, res, 3] RGB in [0, 1]: the ego-centred bird's-eye image (mdo_topdown); channels=2: the per-frame
+        [road_network, traffic_flow] grey channels of the stacked observation"""
+        img = np.zeros((self.n_agents, resolution, resolution, channels), np.float32)
+        lib().mdo_topdown(C.byref(self.cfg), C.byref(self.A), _p(img), C.c_int(resolution), C.c_float(max_distance), C.c_int(channels))
         return img
 
     def dynamics(self, act3, n_sub):
