@@ -3620,7 +3620,7 @@ extern "C" int md_profile_end(md_sim* sim, float* ms, int cap) {
 // bird's-eye RGB image of TopDownSingleFrameMetaDriveEnv (envs/top_down_env.py:7-31), [A, res, res, 3] in [0, 1].  The scene the
 // reference paints with pygame - lane lines (35, 35, 35) 0.3 m wide, the ego GREEN, every other vehicle BLUE (headings under 2
 // degrees snapped to 0), the window of +-max_distance turned so that the ego looks up, its left on the image's right - is
-// evaluated analytically at the centre of every output pixel (oracle/md_oracle.c: mdo_topdown states the rules; pygame is not
+// evaluated analytically at the centre of every output pixel (the CPU restatement mdo_topdown under oracle/ states the rules; pygame is not
 // on this image, its rasteriser is not pinned).  One CTA per row of 16 x 16 pixel tiles of one agent: the vehicles' rectangles
 // are staged in shared memory once, the line segments near each tile (through the static grid) once per tile, then every thread
 // shades its pixel.

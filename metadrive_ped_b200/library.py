@@ -157,13 +157,12 @@ class GeneratedLibrary(ScenarioLibrary):
             if k not in c:
                 raise KeyError(k)
             c[k] = v
-        if isinstance(c["map"], str) and any(b in c["map"] for b in "$BP"):
-            # the generator builds these blocks (pgmap.TollGate / Bidirection / ParkingLot, bit-identical lane tables), but a
-            # TollGate's booths (TollGateBuilding: crash_building, lidar-visible) are not bodies of the device world, and a
-            # Bidirection block's two roads / a parking space's two road names share one lane - no reference trace pins the step
-            # path on such scenes
-            raise NotImplementedError("maps with TollGate ('$'), Bidirection ('B') or ParkingLot ('P') blocks can be generated "
-                                      "(pgmap.generate) but not stepped: toll booths / shared lanes are not in the device world")
+        if isinstance(c["map"], str) and any(b in c["map"] for b in "BP"):
+            # the generator builds these blocks (pgmap.Bidirection / ParkingLot, bit-identical lane tables), but a Bidirection
+            # block's two roads / a parking space's two road names share one lane - no reference trace pins the step path on such
+            # scenes.  TollGate blocks ('$') are stepped: their booths are static boxes of the device world (object kind 4).
+            raise NotImplementedError("maps with Bidirection ('B') or ParkingLot ('P') blocks can be generated "
+                                      "(pgmap.generate) but not stepped: their shared lanes are not in the device world")
         self.gen = c
         self.path = "<generated>"
         self.seeds = np.arange(start_seed, start_seed + num_scenarios, dtype=np.int32)

@@ -339,4 +339,11 @@ def populate(big, seed, traffic_density=0.1, traffic_mode="trigger", accident_pr
         order = list(range(n_obj_vehicles, len(sp.static))) + list(range(n_obj_vehicles))
         for name in ("static", "dyn", "routes", "ints", "idm"):
             setattr(sp, name, [getattr(sp, name)[k] for k in order])
+    # the toll booths close the object table (oracle/ref_export.Roster.objects_table): kind 4, half extent across the heading,
+    # half extent along it (BUILDING_LENGTH / 2), BUILDING_HEIGHT (component/buildings/tollgate_building.py:7-26)
+    idx = None
+    for blk in big.blocks:
+        for lane, pos, heading in getattr(blk, "buildings", ()):
+            idx = idx or MapIndex(big)
+            sp.objects.append([4.0, float(pos[0]), float(pos[1]), float(heading), lane.width / 2.0, 5.0, 5.0, idx.lane_id(lane)])
     return sp.scenario(map_id)

@@ -45,6 +45,18 @@ def roster_arrays(env, mi, roster):
                 objects=roster.objects_table())
 
 
+def idm_timers(env, roster):
+    """overtake_timer of every roster vehicle's IDM policy (-1: no such policy).  The reference redraws it from the policy's own
+    RandomState when a lateral lane change completes (policy/idm_policy.py:285-288); this build draws from a counter hash
+    instead (DESIGN.md "Deliberate differences"), so the replay tests inject the trace's draw where the timer was reset."""
+    out = np.full(len(roster.vehicles), -1.0)
+    for k, v in enumerate(roster.vehicles):
+        pol = env.engine.get_policy(v.name)
+        if pol is not None and hasattr(pol, "overtake_timer"):
+            out[k] = pol.overtake_timer
+    return out
+
+
 class Recorders:
     """What the reference decides per step, besides the state: for every Lidar.perceive call the object each ray hit
     (sensors/distance_detector.py:27-85: `detected_objects` holds one result per hitting ray, in ray order) and the body
@@ -85,6 +97,7 @@ class Recorders:
             if v is obj:
                 return k
         kept = [o for o in roster.objects if type(o).__name__ in ("TrafficCone", "TrafficWarning", "TrafficBarrier")]
+        kept += list(getattr(roster, "buildings", []))   # the toll booths close the object table (Roster.objects_table)
         for j, o in enumerate(kept):
             if o is obj:
                 return 1000 + j
@@ -122,7 +135,7 @@ def _pad_pairs(per_step):
     return out
 
 
-def run_episode(env_cls, config, seed, actions, tag):
+def run_episode(env_cls, config, seed, actions, tag, closed_loop=None):
     from oracle import ref_export as rx
     rec = Recorders()
     env = env_cls(config)
@@ -135,7 +148,12 @@ def run_episode(env_cls, config, seed, actions, tag):
         n_lasers = int(env.config["vehicle_config"]["lidar"]["num_lasers"])
         hits, pairs = [rec.ego_hits(roster, n_lasers)], []
         fs, is_, obs, rew, cost, term, trunc, infos = [f0], [i0], [obs0], [], [], [], [], []
-        for a in actions:
+        timers = [idm_timers(env, roster)]
+        actions = np.array(actions, np.float64)
+        for t in range(len(actions)):
+            if closed_loop:   # the lane-follow driver of the multi-agent traces, seeded by the tag's seed
+                actions[t] = _lane_follow_action(env.agent, closed_loop, 0.02, fast=55, slow=20)
+            a = actions[t]
             rec.clear()
             if config.get("discrete_action"):  # Discrete: the index travels in column 0; MultiDiscrete: both columns
                 o, r, te, tr, info = env.step([int(a[0]), int(a[1])] if config.get("use_multi_discrete") else int(a[0]))
@@ -146,6 +164,7 @@ def run_episode(env_cls, config, seed, actions, tag):
             f, i = rx.record_world(env, roster)
             fs.append(f)
             is_.append(i)
+            timers.append(idm_timers(env, roster))
             obs.append(o)
             rew.append(r)
             cost.append(info["cost"])
@@ -162,7 +181,7 @@ def run_episode(env_cls, config, seed, actions, tag):
             actions=np.asarray(actions[:T], np.float64), veh_f=np.stack(fs), veh_i=np.stack(is_),
             obs=np.stack(obs).astype(np.float32), reward=np.asarray(rew, np.float64), cost=np.asarray(cost, np.float64),
             terminated=np.asarray(term, bool), truncated=np.asarray(trunc, bool), info=np.asarray(infos, np.float64),
-            lidar_hit=np.stack(hits), contact_pairs=_pad_pairs(pairs),
+            lidar_hit=np.stack(hits), contact_pairs=_pad_pairs(pairs), idm_timer=np.stack(timers),
             config=json.dumps(dict({k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))},
                                    num_others=int(env.config["vehicle_config"]["lidar"]["num_others"]),
                                    n_side_lasers=int(env.config["vehicle_config"]["side_detector"]["num_lasers"]),
@@ -479,7 +498,7 @@ def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
 
 ALL_TAGS = ["cfg1_S_straight", "cfg1_S_random", "cfg1_S_discrete", "cfg2_pg3_seed3", "cfg2_pg3_seed7", "cfg2_pg3_seed11_dense",
             "cfg2_SCO_nolimit", "cfg2_pg3_seed11_others4", "cfg2_pg3_seed3_detectors", "cfg4_safe_seed2", "cfg4_safe_seed5",
-            "cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg3_ma_roundabout", "cfg3_ma_roundabout_respawn",
+            "cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg2_StollC_seed0", "cfg3_ma_roundabout", "cfg3_ma_roundabout_respawn",
             "cfg3_ma_intersection_respawn", "cfg3_ma_bottleneck_respawn", "cfg3_ma_tollgate_respawn", "cfg5_ped_X"]
 
 
@@ -550,6 +569,10 @@ def main():
         # seed 8 into a traffic vehicle (step ~81), and both keep going (crash_*_done=False, safe_metadrive_env.py:15-16)
         ("cfg4_safe_seed40_cones", SafeMetaDriveEnv, dict(num_scenarios=100, start_seed=0, log_level=50), 40, smooth_long),
         ("cfg4_safe_seed8_bump", SafeMetaDriveEnv, dict(num_scenarios=100, start_seed=0, log_level=50), 8, smooth_long),
+        # a TollGate block inside a BIG map (map="S$C"): toll booths (TollGateBuilding: static boxes, crash_building, lidar-
+        # visible, obstacles on their lane to the IDM traffic) in a single-agent env
+        ("cfg2_StollC_seed0", MetaDriveEnv, dict(map="S$C", traffic_density=0.2, num_scenarios=20, start_seed=0, log_level=50), 0,
+         np.zeros((230, 2))),   # closed loop: the lane-follow driver (see the loop below)
     ]
     # BASELINE config 3: MultiAgentRoundaboutEnv with 240-beam lidar
     #   cfg3_ma_roundabout          40 agents, random actions, respawn off (crash / out-of-road / wreck bookkeeping)
@@ -640,7 +663,7 @@ def main():
     for tag, cls, cfg, seed, acts in cases:
         if not match(tag):
             continue
-        out = run_episode(cls, cfg, seed, acts, tag)
+        out = run_episode(cls, cfg, seed, acts, tag, closed_loop=np.random.RandomState(31) if tag == "cfg2_StollC_seed0" else None)
         path = os.path.join(args.out, tag + ".npz")
         np.savez_compressed(path, **out)
         print(tag, "steps", len(out["reward"]), "vehicles", out["veh_f"].shape[1], "objects",

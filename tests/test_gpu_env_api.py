@@ -172,8 +172,9 @@ def test_graph_replay_equals_plain_launches():
 
 
 def test_env_runs_maps_with_bottleneck_blocks():
-    """map strings with Merge / Split blocks ("SyYC", pgblock/bottleneck.py) generate and step; TollGate / Bidirection blocks
-    are generated but refused by the env (toll booths and shared lanes are not in the device world)."""
+    """map strings with Merge / Split blocks ("SyYC", pgblock/bottleneck.py) and TollGate blocks ("S$C", pgblock/tollgate.py: booths as
+    static boxes) generate and step; Bidirection / ParkingLot blocks are generated but refused by the env (their shared lanes are
+    not in the device world)."""
     from metadrive_ped_b200 import MetaDriveEnv
     env = MetaDriveEnv(dict(map="SyYC", traffic_density=0.2, num_scenarios=8))
     for seed in (0, 3):
@@ -187,8 +188,19 @@ def test_env_runs_maps_with_bottleneck_blocks():
                 break
         assert dist > 5.0, "the ego makes progress along the route"
     env.close()
+    # a TollGate block inside the map: the booths are bodies of the world (the middle lane of three ends in one)
+    env = MetaDriveEnv(dict(map="S$C", traffic_density=0.0, num_scenarios=4))
+    obs, _ = env.reset(seed=1)   # the agent manager's draw puts seed 1's ego on the middle lane (y = 3.5)
+    hit = False
+    for _ in range(300):
+        obs, r, te, tr, info = env.step([0.0, 0.5])
+        if te or tr:
+            hit = info["crash_building"]
+            break
+    assert hit, "driving straight on along the middle lane ends in the toll booth"
+    env.close()
     with pytest.raises(NotImplementedError):
-        MetaDriveEnv(dict(map="S$C")).reset(seed=0)
+        MetaDriveEnv(dict(map="SBC")).reset(seed=0)
 
 
 def test_handles_of_different_size_coexist():

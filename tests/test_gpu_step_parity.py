@@ -100,6 +100,13 @@ def test_step_matches_oracle_and_golden(tag, oracle_lib):
             for e in ev:
                 orc.a["veh_p"].reshape(cfg.n_envs, S, -1)[:, int(events[e, 1])] = g["respawn_static"][e]
             sim.set_state("veh_p", orc.a["veh_p"])
+        if "idm_timer" in g:  # the reference's overtake-timer redraws go into both simulations (tests/test_oracle_golden.py)
+            redrawn = [k for k in np.nonzero(g["idm_timer"][t + 1] < g["idm_timer"][t])[0] if g["veh_i"][t + 1][k, 0] == 1]
+            if redrawn:
+                np.testing.assert_array_equal(sim.get_state("veh_idm"), orc.a["veh_idm"])
+                for k in redrawn:
+                    orc.a["veh_idm"].reshape(cfg.n_envs, S, -1)[:, k, 0] = g["idm_timer"][t + 1][k]
+                sim.set_state("veh_idm", orc.a["veh_idm"])
         if "ped_state" in g:
             np.testing.assert_array_equal(sim.get_state("obj_f"), orc.a["obj_f"])
         vi_g, vi_o = sim.get_state("veh_i"), orc.a["veh_i"]

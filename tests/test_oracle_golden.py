@@ -205,6 +205,12 @@ def test_oracle_replays_reference_trace(tag, oracle_lib):
             # respawn-mode traffic: the reference samples fresh engine / brake forces for the new vehicle; this build
             # keeps the slot's parameters (documented), so the test injects the reference's for the rest of the replay
             sim.a["veh_p"][int(events[e, 1])] = g["respawn_static"][e]
+        if "idm_timer" in g:
+            # a completed lateral lane change redraws the IDM's overtake timer: the reference from the policy's RandomState
+            # (idm_policy.py:285-288), this build from a counter hash (documented) - the replay takes the trace's draw
+            for k in np.nonzero(g["idm_timer"][t + 1] < g["idm_timer"][t])[0]:
+                if g["veh_i"][t + 1][k, 0] == 1:
+                    sim.a["veh_idm"][k, 0] = g["idm_timer"][t + 1][k]
         if "ped_state" in g:  # pedestrians: positions and turn-arounds of the crossing model
             np.testing.assert_allclose(sim.a["obj_f"][:, 1:3], g["ped_state"][t + 1][:, 0:2], atol=2e-3, rtol=0)
             np.testing.assert_allclose(sim.a["obj_f"][:, 10:12], g["ped_state"][t + 1][:, 2:4], atol=1e-5, rtol=0)

@@ -71,9 +71,13 @@ def test_generator_reproduces_maps_with_bottleneck_and_tollgate_blocks(name, spe
         for field in ("veh_static", "routes", "veh_int", "idm"):
             np.testing.assert_array_equal(getattr(ref, field), getattr(got, field), err_msg="%s of seed %d" % (field, seed))
         np.testing.assert_allclose(ref.veh_dyn, got.veh_dyn, rtol=0, atol=1e-12)
-    if "$" in spec:
+    if "$" in spec:   # the booths close the object table: one on every second lane of both toll roads
+        lib = GeneratedLibrary(0, 2, map=spec)
+        arrays, cfg = lib.build_world([0, 1])
+        booths = arrays["obj_f"][arrays["obj_f"][:, 0] == 4.0]
+        assert cfg.objs_per_env >= 2 and len(booths) == 4 and (booths[:, 5] == 5.0).all() and (booths[:, 7] == 0.0).all()
         with pytest.raises(NotImplementedError):
-            GeneratedLibrary(0, 1, map=spec)
+            GeneratedLibrary(0, 1, map="SBC")
 
 
 def test_generator_reproduces_the_parking_lot_map():
