@@ -222,7 +222,8 @@
 #define OBS_TOLL(cfg) ((cfg).toll_env ? 2 : 0)
 #define MAX_DET_LASERS 128
 #define DET_HEIGHT 0.2f      /* DistanceDetector.DEFAULT_HEIGHT (sensors/distance_detector.py:92) */
-#define OBS_OTHERS(cfg) (4 * (cfg).num_others)                       /* component/sensors/lidar.py:93-138 */
+#define OBS_OTHER_W(cfg) ((cfg).add_others_navi ? 8 : 4)                  /* floats per neighbour (component/sensors/lidar.py:93-138) */
+#define OBS_OTHERS(cfg) (OBS_OTHER_W(cfg) * (cfg).num_others)
 #define OBS_DIM(cfg) (OBS_STATE(cfg) + OBS_OTHERS(cfg) + (cfg).n_lasers + OBS_TOLL(cfg))
 
 /* ---- configuration passed by value through the C ABI ------------------------------------------- */
@@ -243,7 +244,7 @@ typedef struct MdConfig {
     int ma_places, ma_dests, ma_roads, tape_len;
     /* MultiAgentMetaDrive.done_function overrides (envs/marl_envs/multi_agent_metadrive.py:114-128) */
     int ma_crash_done, ma_out_of_road_done;
-    int num_others; /* lidar.num_others: the k nearest vehicles, 4 floats each, between the state and the lidar floats */
+    int num_others; /* lidar.num_others: the k nearest vehicles, 4 floats each (8 with add_others_navi), between the state and the lidar floats */
     /* side_detector / lane_line_detector (vehicle_config; 0 lasers = off, the reference's default) */
     int n_side_lasers, n_lane_lasers;
     float side_dist, lane_dist;
@@ -269,6 +270,9 @@ typedef struct MdConfig {
      * min_pass_steps after entering it ends the episode as out_of_road) and the stay-time bookkeeping behind it */
     int toll_env, min_pass_steps;
     float overspeed_penalty;
+    /* lidar.add_others_navi (component/sensors/lidar.py:120-129): every neighbour of the num_others block carries 4 more floats,
+     * ITS two navigation checkpoints (BaseNavigation.get_checkpoints, base_navigation.py:145-152) in the observer's frame */
+    int add_others_navi;
 } MdConfig;
 
 /* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */

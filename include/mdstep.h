@@ -25,7 +25,7 @@ extern "C" {
 
 typedef struct md_sim md_sim;
 
-#define MD_ABI_VERSION 6
+#define MD_ABI_VERSION 7
 int md_abi_version(void);
 /* sizeof(MdConfig) / sizeof(MdArrays) the library was built with: the loader compares them with its own mirror */
 int md_sizeof_config(void);
@@ -54,7 +54,7 @@ int md_reset(md_sim* sim, const uint8_t* env_mask_dev, float* obs_dev, void* str
 /* env.step(): replaces BaseEnv.step = _step_simulator + _get_step_return (envs/base_env.py:426-463, 586-623):
  * engine.before_step (agent actuation, trigger, IDM), decision_repeat x doPhysics + contact callback,
  * engine.after_step (localisation, state check), reward / cost / done, LidarStateObservation.observe.
- * actions_dev [A,2]; obs_dev [A, OBS_DIM(cfg)] (19 + 4*num_others + n_lasers by default); reward/cost [A] f32; terminated/truncated [A] u8;
+ * actions_dev [A,2]; obs_dev [A, OBS_DIM(cfg)] (19 + 4*num_others (8* with add_others_navi) + n_lasers by default); reward/cost [A] f32; terminated/truncated [A] u8;
  * info_flags [A] i32 (FL_* bits); info_f [A,8] f32 = velocity, steering, acceleration, step_energy, episode_energy,
  * step_reward, episode_reward, episode_length. */
 int md_step(md_sim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, float* cost_dev,

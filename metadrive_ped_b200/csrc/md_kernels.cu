@@ -2238,6 +2238,53 @@ __device__ __forceinline__ float lidar_noise(const MdConfig& cfg, float frac, ui
 // Multi-agent passes: the seats that observe (FL_VALID / FL_NEWBORN) are a fraction of all seats (wrecks, empty seats,
 // nothing new in the respawn pass).  With a warp per SEAT every CTA of k_lidar lived as long as its one or two live warps -
 // 18 waves of mostly empty CTAs; the observing seats are therefore compacted first and k_lidar takes a warp per ENTRY.
+// lidar.add_others_navi (component/sensors/lidar.py:120-129): the two navigation checkpoints of every neighbour of the num_others
+// block (BaseNavigation.get_checkpoints, base_navigation.py:145-152: the ends of the first lane of ITS current road and of its next
+// road - the current one again on the final road - shifted by later_middle = (lanes of the current road / 2 - 0.5) x width of the
+// lane it is on) through Lidar._project_to_vehicle_system (:85-91): the offset from the observer, cut to the perceive distance, in
+// the observer's frame.  A kernel of its own, launched after k_lidar only when the key is on (k_lidar left the neighbour's slot in
+// the first of the four floats), so that the ray casting keeps its registers: one thread per (observer, neighbour).
+__global__ void k_others_navi(MdConfig cfg, MdArrays A, const float* __restrict__ body_tab, float* __restrict__ out, int out_stride,
+                              int out_off, const uint8_t* __restrict__ env_mask, const int* __restrict__ agent_flags, int need_flag) {
+    const int S = cfg.slots_per_env, NA = cfg.agents_per_env, K = cfg.num_others;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)cfg.n_envs * NA * K) return;
+    const long long a = t / K;
+    const int n = (int)(t - a * K);
+    const int env = (int)(a / NA), slot = (int)(a - (long long)env * NA);
+    if (env_mask != nullptr && env_mask[env] == 0) return;
+    if (agent_flags != nullptr) { if (!(agent_flags[a] & need_flag)) return; }   // the observers of k_lidar, by the same rule
+    else if (!A.veh_i[(size_t)(env * S + slot) * VEH_I + VI_ACTIVE]) return;
+    float* o4 = out + (size_t)a * out_stride + out_off + 8 * n + 4;
+    const int k = __float_as_int(o4[0]);
+    if (k < 0) { o4[0] = o4[1] = o4[2] = o4[3] = 0.0f; return; }
+    const float* eb = body_tab + ((size_t)env * S + slot) * BODY_ROW;
+    const float ox = eb[16], oy = eb[17];
+    const MapView m = map_view(A, A.env_i[env * ENV_I + EI_MAP]);
+    const size_t g = (size_t)env * S + k;
+    const int* Ig = A.veh_i + g * VEH_I;
+    const int* route = A.veh_route + g * ROUTE_MAX;
+    const int c0 = Ig[VI_CKPT0], c1 = Ig[VI_CKPT1];
+    const int cur_road = find_road(m, route[c0], route[c0 + 1]);
+    const int next_road = c1 != c0 ? find_road(m, route[c1], route[c1 + 1]) : -1;
+    const int cur_first = m.road_i[cur_road * ROAD_I + RI_FIRST], cur_n = m.road_i[cur_road * ROAD_I + RI_N];
+    const int nx_first = next_road >= 0 ? m.road_i[next_road * ROAD_I + RI_FIRST] : cur_first;
+    const int lane = Ig[VI_LANE] >= 0 ? Ig[VI_LANE] : cur_first;
+    const float later_middle = ((float)cur_n / 2.0f - 0.5f) * m.lane_f[lane * LANE_F + LF_WIDTH];
+    const float D = cfg.lidar_dist;
+    for (int j = 0; j < 2; j++) {
+        const float* L = m.lane_f + (j == 0 ? cur_first : nx_first) * LANE_F;
+        float ckx, cky;
+        lane_position(L, L[LF_LENGTH], later_middle, ckx, cky);
+        float cx = ckx - ox, cy = cky - oy;
+        const float dn = sqrtf(cx * cx + cy * cy);
+        if (dn > D) { cx = cx / dn * D; cy = cy / dn * D; }
+        const float in_heading = cx * eb[7] + cy * eb[10];
+        const float in_rhs = -(cx * eb[6] + cy * eb[9]);
+        o4[2 * j] = clipf((in_heading / D + 1.0f) / 2.0f, 0.0f, 1.0f);
+        o4[2 * j + 1] = clipf((in_rhs / D + 1.0f) / 2.0f, 0.0f, 1.0f);
+    }
+}
 __global__ void k_lidar_list(long long n_agents, const int* __restrict__ agent_flags, int need_flag, int* __restrict__ list,
                              unsigned int* __restrict__ count) {
     const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2318,7 +2365,8 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
     }
     const F3 o = f3(eb[16], eb[17], LIDAR_HEIGHT);
     const int K = out_off >= 0 ? cfg.num_others : 0;
-    float* orow = out + (size_t)a * out_stride + (out_off >= 0 ? out_off + 4 * K : 0);
+    const int KW = OBS_OTHER_W(cfg);
+    float* orow = out + (size_t)a * out_stride + (out_off >= 0 ? out_off + KW * K : 0);
     if (K > 0) {
         // Lidar.get_surrounding_vehicles_info (component/sensors/lidar.py:93-138): the K nearest vehicles of the broad
         // phase set (bodies overlapping the disc of radius int(distance)), by centre distance.  Lane l holds the
@@ -2371,7 +2419,8 @@ k_lidar(MdConfig cfg, const float* __restrict__ body_tab, const float* __restric
                     v.z = clipf((vf / max_speed + 1.0f) / 2.0f, 0.0f, 1.0f);
                     v.w = clipf((vr / max_speed + 1.0f) / 2.0f, 0.0f, 1.0f);
                 }
-                orow_k[4 * n] = v.x; orow_k[4 * n + 1] = v.y; orow_k[4 * n + 2] = v.z; orow_k[4 * n + 3] = v.w;
+                orow_k[KW * n] = v.x; orow_k[KW * n + 1] = v.y; orow_k[KW * n + 2] = v.z; orow_k[KW * n + 3] = v.w;
+                if (KW == 8) orow_k[8 * n + 4] = __int_as_float(bd < 3.0e38f ? bk : -1);   // the neighbour's slot, for k_others_navi
             }
         }
     }
@@ -3340,6 +3389,12 @@ static int launch_lidar(md_sim* sim, const View& v, uint32_t noise_off, float* o
                                                     v.lidar_count);
     sim->launches++;
     CK(cudaGetLastError());
+    if (off >= 0 && c.add_others_navi && c.num_others > 0) {   // the neighbours' checkpoints, next to their four floats
+        const long long nt = na * c.num_others;
+        k_others_navi<<<(int)((nt + 127) / 128), 128, 0, st>>>(c, v.dev, v.body_tab, out, stride, off, mask, agent_flags, need_flag);
+        sim->launches++;
+        CK(cudaGetLastError());
+    }
     if (off >= 0 && (c.n_side_lasers > 0 || c.n_lane_lasers > 0)) {  // the detector blocks of the same observation rows
         k_linedet<<<blocks, LIDAR_WARPS * 32, 0, st>>>(c, v.dev, v.body_tab, out, mask, agent_flags, need_flag,
                                                        sim->ray_tab + 2 * MAX_LASERS, sim->ray_tab + 2 * MAX_LASERS + 2 * MAX_DET_LASERS);
@@ -3533,7 +3588,7 @@ extern "C" int md_attach_bank(md_sim* sim, md_sim* bank, int seed) {
     const MdConfig &a = sim->cfg, &b = bank->cfg;
     if (bank->device != sim->device || a.slots_per_env != b.slots_per_env || a.objs_per_env != b.objs_per_env ||
         a.agents_per_env != b.agents_per_env || a.n_lasers != b.n_lasers || a.n_side_lasers != b.n_side_lasers ||
-        a.n_lane_lasers != b.n_lane_lasers || a.num_others != b.num_others) {
+        a.n_lane_lasers != b.n_lane_lasers || a.num_others != b.num_others || a.add_others_navi != b.add_others_navi) {
         sim->err = "scenario bank: device, slots / objects / agents per env and the observation layout must match";
         return -2;
     }

@@ -157,10 +157,10 @@ def _merge_new(default, user):
 
 def _obs_dim(vc):
     """LidarStateObservation.observation_space (obs/state_obs.py:30-62, 172-183): side block (2 distances or the side
-    detector's rays) + 6 + lane block (1 offset or the lane-line detector's rays) + navi 10 + others 4k + lidar N."""
+    detector's rays) + 6 + lane block (1 offset or the lane-line detector's rays) + navi 10 + others 4k (8k with add_others_navi) + lidar N."""
     side = vc["side_detector"]["num_lasers"] or 2
     lane = vc["lane_line_detector"]["num_lasers"] or 1
-    return side + 6 + lane + 10 + 4 * vc["lidar"]["num_others"] + vc["lidar"]["num_lasers"]
+    return side + 6 + lane + 10 + (8 if vc["lidar"]["add_others_navi"] else 4) * vc["lidar"]["num_others"] + vc["lidar"]["num_lasers"]
 
 
 class _Agent:
@@ -236,8 +236,6 @@ class MetaDriveEnv:
             raise NotImplementedError("static_traffic_object=False (loose cones that can be pushed) is not covered")
         lid = self.config["vehicle_config"]["lidar"]
         assert 0.0 <= lid["dropout_prob"] <= 1.0  # obs/state_obs.py:240
-        if lid["add_others_navi"]:
-            raise NotImplementedError("lidar add_others_navi is not covered yet")
         self.start_seed = self.start_index = self.config["start_seed"]
         self.num_scenarios = self.env_num = self.config["num_scenarios"]
         self._lib = None
@@ -299,6 +297,7 @@ class MetaDriveEnv:
         return dict(
             n_lasers=c["vehicle_config"]["lidar"]["num_lasers"], lidar_dist=float(c["vehicle_config"]["lidar"]["distance"]),
             num_others=int(c["vehicle_config"]["lidar"]["num_others"]),
+            add_others_navi=int(bool(c["vehicle_config"]["lidar"]["add_others_navi"])),
             lidar_gaussian_noise=float(c["vehicle_config"]["lidar"]["gaussian_noise"]),
             lidar_dropout_prob=float(c["vehicle_config"]["lidar"]["dropout_prob"]),
             noise_seed=int(c.get("start_seed", 0) or 0),
@@ -652,8 +651,6 @@ class MultiAgentMetaDrive:
             raise NotImplementedError("record / replay covers the single-agent envs")
         lid = self.config["vehicle_config"]["lidar"]
         assert 0.0 <= lid["dropout_prob"] <= 1.0  # obs/state_obs.py:240
-        if lid["add_others_navi"]:
-            raise NotImplementedError("lidar add_others_navi is not covered yet")
         self._lib = MultiAgentLibrary(self.ASSET)
         self.num_agents = self.config["num_agents"]
         if self.num_agents == -1:

@@ -37,7 +37,7 @@ class BatchedSim:
         self.n_agents = cfg.n_envs * cfg.agents_per_env
         # include/md_layout.h OBS_STATE / OBS_DIM: the tollgate env drops the 10 navigation floats and appends 2 toll floats
         self.state_dim = (cfg.n_side_lasers or 2) + 6 + (cfg.n_lane_lasers or 1) + (0 if cfg.toll_env else 10)
-        self.obs_dim = self.state_dim + 4 * cfg.num_others + cfg.n_lasers + (2 if cfg.toll_env else 0)
+        self.obs_dim = self.state_dim + (8 if cfg.add_others_navi else 4) * cfg.num_others + cfg.n_lasers + (2 if cfg.toll_env else 0)
         na = self.n_agents
         kw = dict(device=self.tdev)
         self.obs = torch.zeros((na, self.obs_dim), dtype=torch.float32, **kw)

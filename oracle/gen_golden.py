@@ -184,6 +184,7 @@ def run_episode(env_cls, config, seed, actions, tag, closed_loop=None):
             lidar_hit=np.stack(hits), contact_pairs=_pad_pairs(pairs), idm_timer=np.stack(timers),
             config=json.dumps(dict({k: v for k, v in config.items() if isinstance(v, (int, float, str, bool))},
                                    num_others=int(env.config["vehicle_config"]["lidar"]["num_others"]),
+                                   **(dict(add_others_navi=1) if env.config["vehicle_config"]["lidar"]["add_others_navi"] else {}),
                                    n_side_lasers=int(env.config["vehicle_config"]["side_detector"]["num_lasers"]),
                                    side_dist=float(env.config["vehicle_config"]["side_detector"]["distance"]),
                                    n_lane_lasers=int(env.config["vehicle_config"]["lane_line_detector"]["num_lasers"]),
@@ -497,7 +498,7 @@ def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
 
 
 ALL_TAGS = ["cfg1_S_straight", "cfg1_S_random", "cfg1_S_discrete", "cfg2_pg3_seed3", "cfg2_pg3_seed7", "cfg2_pg3_seed11_dense",
-            "cfg2_SCO_nolimit", "cfg2_pg3_seed11_others4", "cfg2_pg3_seed3_detectors", "cfg4_safe_seed2", "cfg4_safe_seed5",
+            "cfg2_SCO_nolimit", "cfg2_pg3_seed11_others4", "cfg2_pg3_seed3_others_navi", "cfg2_pg3_seed3_detectors", "cfg4_safe_seed2", "cfg4_safe_seed5",
             "cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg2_StollC_seed0", "cfg3_ma_roundabout", "cfg3_ma_roundabout_respawn",
             "cfg3_ma_intersection_respawn", "cfg3_ma_bottleneck_respawn", "cfg3_ma_tollgate_respawn", "cfg5_ped_X"]
 
@@ -557,6 +558,10 @@ def main():
         ("cfg2_pg3_seed11_others4", MetaDriveEnv,
          dict(map=3, traffic_density=0.3, num_scenarios=20, start_seed=0, log_level=50,
               vehicle_config=dict(lidar=dict(num_others=4))), 11, smooth),
+        # ... with add_others_navi (lidar.py:120-129): every neighbour's two checkpoints in the ego frame follow its 4 floats
+        ("cfg2_pg3_seed3_others_navi", MetaDriveEnv,
+         dict(map=3, traffic_density=0.1, num_scenarios=20, start_seed=0, log_level=50,
+              vehicle_config=dict(lidar=dict(num_others=4, add_others_navi=True))), 3, smooth),
         # side / lane-line detectors on (sensors/distance_detector.py:194-209): their rays replace the 2 + 1 floats
         ("cfg2_pg3_seed3_detectors", MetaDriveEnv,
          dict(map=3, traffic_density=0.1, num_scenarios=20, start_seed=0, log_level=50,

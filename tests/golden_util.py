@@ -109,6 +109,7 @@ def golden_world(g, replicas=1, slots=None, objs=None, **cfg_kw):
     if "horizon" in conf and conf["horizon"]:
         kw["horizon"] = int(conf["horizon"])
     kw["num_others"] = int(conf.get("num_others", 0))
+    kw["add_others_navi"] = int(conf.get("add_others_navi", 0))
     kw.update(n_side_lasers=int(conf.get("n_side_lasers", 0)), side_dist=float(conf.get("side_dist", 50.0)),
               n_lane_lasers=int(conf.get("n_lane_lasers", 0)), lane_dist=float(conf.get("lane_dist", 20.0)))
     if isinstance(conf.get("discrete_action"), int) and not isinstance(conf.get("discrete_action"), bool):

@@ -289,19 +289,26 @@ def _ma_act(env, action):
     return obs, reward, terminated, truncated, info
 
 
-@pytest.mark.parametrize("num_agents,num_others", [(1, 8), (1, 0), (4, 8), (4, 0), (8, 0)])
-def test_ma_roundabout_env_surface(num_agents, num_others):
-    """metadrive/tests/test_env/test_ma_roundabout_env.py:80-103: spaces, key bookkeeping, no done at step 0."""
+@pytest.mark.parametrize("num_agents,num_others,navi", [(1, 8, False), (1, 0, False), (4, 8, False), (4, 0, False), (8, 0, False),
+                                                        (4, 4, True), (1, 4, True)])
+def test_ma_roundabout_env_surface(num_agents, num_others, navi):
+    """metadrive/tests/test_env/test_ma_roundabout_env.py:80-103: spaces, key bookkeeping, no done at step 0 - also with the
+    neighbours' checkpoints in the others block (lidar.add_others_navi: 8 floats per neighbour, sensors/lidar.py:120-129)."""
     from metadrive_ped_b200 import MultiAgentRoundaboutEnv
     env = MultiAgentRoundaboutEnv({"num_agents": num_agents, "delay_done": 0,
-                                   "vehicle_config": {"lidar": {"num_others": num_others}}})
+                                   "vehicle_config": {"lidar": {"num_others": num_others, "add_others_navi": navi}}})
+    W = 8 if navi else 4
     try:
         obs, info = env.reset()
         assert set(obs.keys()) == {"agent%d" % k for k in range(num_agents)} == set(env.agents.keys())
         assert env.observation_space.contains(obs)
-        assert obs["agent0"].shape == (19 + 4 * num_others + 72, )  # multi-agent default lidar: 72 lasers, 40 m
+        assert obs["agent0"].shape == (19 + W * num_others + 72, )  # multi-agent default lidar: 72 lasers, 40 m
         if num_others and num_agents > 1:
-            assert any(o[19:19 + 4 * num_others].any() for o in obs.values()), "neighbours show up in the others block"
+            assert any(o[19:19 + W * num_others].any() for o in obs.values()), "neighbours show up in the others block"
+        if navi:
+            for o in obs.values():   # a neighbour brings its checkpoints; an empty entry is eight zeros
+                blk = o[19:19 + 8 * num_others].reshape(num_others, 8)
+                assert (blk[:, :4].any(1) == blk[:, 4:].any(1)).all()
         for step in range(100):
             act = {k: [1, 1] for k in env.agents.keys()}
             o, r, tm, tc, i = _ma_act(env, act)

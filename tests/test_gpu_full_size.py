@@ -108,7 +108,7 @@ def test_full_size_step_matches_oracle(workload, steps, oracle_lib):
         np.testing.assert_allclose(vs_g[m_veh, 3:7], vs_o[m_veh, 3:7], atol=1e-3, rtol=0)
         np.testing.assert_allclose(rg[m_ag], orc.reward[m_ag], atol=1e-3, rtol=0)
         valid = m_ag & (((fl_o & 0x2000) != 0) if multi else True)
-        sd = sim.state_dim + 4 * cfg.num_others
+        sd = sim.state_dim + (8 if cfg.add_others_navi else 4) * cfg.num_others
         np.testing.assert_allclose(og[valid][:, :sd], oo[valid][:, :sd], atol=1e-3, rtol=0)
         bad = ~np.isclose(og[valid][:, sd:], oo[valid][:, sd:], atol=2e-4, rtol=1e-4)
         n_rays += bad.size

@@ -193,7 +193,7 @@ def test_oracle_replays_reference_trace(tag, oracle_lib):
         ray_cols[(ns or 2) + 6:(ns or 2) + 6 + nl] = True
     np.testing.assert_allclose(obs0[0, :SD], g["obs"][0][:SD], atol=2e-5, rtol=0)
     np.testing.assert_allclose(obs0[0, SD:], g["obs"][0][SD:], atol=1e-5, rtol=1e-4)
-    K4 = 4 * cfg.num_others  # lidar.num_others block between the state and the lidar floats
+    K4 = (8 if cfg.add_others_navi else 4) * cfg.num_others  # lidar.num_others block between the state and the lidar floats
     assert obs0.shape[1] == SD + K4 + cfg.n_lasers == g["obs"].shape[1]
     T, n = len(g["reward"]), g["veh_f"].shape[1]
     skip = KNIFE_EDGES.get(tag, {})
