@@ -384,6 +384,9 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         conf["n_lane_lasers"] = int(env.config["vehicle_config"]["lane_line_detector"]["num_lasers"])
         conf["lane_dist"] = float(env.config["vehicle_config"]["lane_line_detector"]["distance"])
         conf["ignore_road_sign"] = int("cross_yellow_line_done" in env.config)
+        if env.config["vehicle_config"]["lidar"]["num_others"]:   # the others block sits between the state and the lidar floats
+            conf.update(num_others=int(env.config["vehicle_config"]["lidar"]["num_others"]),
+                        add_others_navi=int(bool(env.config["vehicle_config"]["lidar"]["add_others_navi"])))
         if hasattr(env, "stay_time_manager"):   # MultiAgentTollgateEnv (envs/marl_envs/marl_tollgate.py:15-36, 239-245)
             conf.update(toll_env=1, min_pass_steps=int(env.config["vehicle_config"]["min_pass_steps"]),
                         overspeed_penalty=float(env.config["overspeed_penalty"]), speed_reward=float(env.config["speed_reward"]),
@@ -500,7 +503,7 @@ def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
 ALL_TAGS = ["cfg1_S_straight", "cfg1_S_random", "cfg1_S_discrete", "cfg2_pg3_seed3", "cfg2_pg3_seed7", "cfg2_pg3_seed11_dense",
             "cfg2_SCO_nolimit", "cfg2_pg3_seed11_others4", "cfg2_pg3_seed3_others_navi", "cfg2_pg3_seed3_detectors", "cfg4_safe_seed2", "cfg4_safe_seed5",
             "cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg2_StollC_seed0", "cfg3_ma_roundabout", "cfg3_ma_roundabout_respawn",
-            "cfg3_ma_intersection_respawn", "cfg3_ma_bottleneck_respawn", "cfg3_ma_tollgate_respawn", "cfg5_ped_X"]
+            "cfg3_ma_intersection_respawn", "cfg3_ma_intersection_others_navi", "cfg3_ma_bottleneck_respawn", "cfg3_ma_tollgate_respawn", "cfg5_ped_X"]
 
 
 def main():
@@ -614,6 +617,18 @@ def main():
         path = os.path.join(args.out, "cfg3_ma_intersection_respawn.npz")
         np.savez_compressed(path, **out)
         print("cfg3_ma_intersection_respawn steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
+              "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
+    # ... with the others block of the cooperative-MARL configs: the 4 nearest AGENTS and their checkpoints (lidar.num_others = 4,
+    # add_others_navi, sensors/lidar.py:93-138) in front of the multi-agent default lidar (72 lasers, 40 m)
+    if args.only == "cfg3_ma_intersection_others_navi":
+        from metadrive.envs.marl_envs.marl_intersection import MultiAgentIntersectionEnv
+        lid = dict(vehicle_config=dict(lidar=dict(num_lasers=72, distance=40, num_others=4, add_others_navi=True)))
+        cfgi = dict(num_agents=8, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, **lid)
+        out = run_episode_ma(MultiAgentIntersectionEnv, cfgi, None, "cfg3_ma_intersection_others_navi", steps=220,
+                             noise=args.ma_noise, seed=13, obs_stride=2)
+        path = os.path.join(args.out, "cfg3_ma_intersection_others_navi.npz")
+        np.savez_compressed(path, **out)
+        print("cfg3_ma_intersection_others_navi steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
               "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     # MultiAgentBottleneckEnv (envs/marl_envs/marl_bottleneck.py): Merge / Split blocks, agents born at both ends without a
     # destination draw, 4-ray side / lane-line detectors in the observation, reward without the positive_road sign

@@ -62,7 +62,7 @@ def golden_world_ma(g, replicas=1, **cfg_kw):
               n_side_lasers=int(conf.get("n_side_lasers", 0)), side_dist=float(conf.get("side_dist", 50.0)),
               n_lane_lasers=int(conf.get("n_lane_lasers", 0)), lane_dist=float(conf.get("lane_dist", 20.0)),
               ignore_road_sign=int(conf.get("ignore_road_sign", 0)))
-    for k in ("toll_env", "min_pass_steps", "on_continuous_line_done", "out_of_route_done"):
+    for k in ("toll_env", "min_pass_steps", "on_continuous_line_done", "out_of_route_done", "num_others", "add_others_navi"):
         if k in conf:
             kw[k] = int(conf[k])
     for k in ("overspeed_penalty", "speed_reward"):
