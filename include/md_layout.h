@@ -237,7 +237,8 @@ typedef struct MdConfig {
     int use_lateral_reward, out_of_route_done, on_continuous_line_done;   /* on_continuous_line_done: 1 = yellow / white solid line or sidewalk ends the episode;
                                                                             2 = white solid line or sidewalk only (MultiAgentBottleneckEnv with cross_yellow_line_done=False);
                                                                             3 = sidewalk or yellow solid line, 4 = sidewalk only, and leaving the lanes does NOT count
-                                                                            (MultiAgentTollgateEnv._is_out_of_road, marl_tollgate.py:239-245) */
+                                                                            (MultiAgentTollgateEnv._is_out_of_road, marl_tollgate.py:239-245);
+                                                                            5 = off the lanes, yellow solid line or sidewalk (MultiAgentParkingLotEnv, marl_parking_lot.py:252-256) */
     int crash_vehicle_done, crash_object_done, crash_human_done, truncate_as_terminate;
     int enable_idm_lane_change, is_multi_agent, delay_done, allow_respawn;
     /* multi-agent respawn tables (manager/spawn_manager.py:117-217): safe places per env, destinations, spawn roads */

@@ -829,6 +829,7 @@ __device__ void agent_outputs(const MdConfig& cfg, const MapView& m, int env_ste
                       (lane_w / 2.0f >= fl_lat && fl_lat >= (0.5f - (float)cur_n) * lane_w);
         bool outr = !(flags & FL_ON_LANE);
         if (cfg.out_of_route_done) outr = outr || (flags & FL_OUT_OF_ROUTE);
+        else if (cfg.on_continuous_line_done == 5) outr = outr || (flags & (FL_ON_YELLOW | FL_CRASH_SIDEWALK));   // parking-lot env: white lines may be crossed
         else if (cfg.on_continuous_line_done == 2) outr = outr || (flags & (FL_ON_WHITE | FL_CRASH_SIDEWALK));   // bottleneck env, yellow line allowed
         else if (cfg.on_continuous_line_done >= 3)   // marl_tollgate.py:239-245: leaving the lanes is not out of road there
             outr = (flags & (cfg.on_continuous_line_done == 3 ? (FL_ON_YELLOW | FL_CRASH_SIDEWALK) : FL_CRASH_SIDEWALK)) != 0;

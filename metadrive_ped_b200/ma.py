@@ -72,6 +72,8 @@ def build_ma_tables(geo: "sc.MapGeometry", spawn_roads, dest_nodes):
     routes = np.full((R * D, sc.ROUTE_MAX), -1, np.int32)
     for ri in range(R):
         for d in range(D):
+            if dest_nodes[ri, d] < 0:     # a shorter list, -1 padded (parking lot: 8 spaces for some roads, 3 exits for the others)
+                continue
             p = route_for(geo.road_i, spawn_roads[ri], dest_nodes[ri, d])
             assert 2 <= len(p) <= sc.ROUTE_MAX, (ri, d, p)
             routes[ri * D + d, :len(p)] = p

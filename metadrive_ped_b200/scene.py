@@ -271,7 +271,11 @@ def build_map_geometry(mt: MapTable, map_region_size=1024.0) -> MapGeometry:
                 lane_f[l, 15] = n - run
                 lane_f[l, 14] = ro * math.cos(0.5 * POLYGON_SAMPLE_RATE / r) - 0.01
         hulls.append(np.concatenate([hull, hull[:1]]))  # stored closed: edge i = (v[i], v[i+1]), n edges, n+1 rows
-        lane_bb[l] = [hull[:, 0].min(), hull[:, 1].min(), hull[:, 0].max(), hull[:, 1].max()]
+        # the hull test counts a point up to 1e-3 m^2 / edge length outside an edge as inside (md_device.cuh
+        # point_in_hull, the stand-in for Bullet's hull margin): the box must not cut that band off
+        edges = np.linalg.norm(np.diff(np.concatenate([hull, hull[:1]]), axis=0), axis=1)
+        pad = min(0.05, 1e-3 / max(float(edges.min()), 1e-3))
+        lane_bb[l] = [hull[:, 0].min() - pad, hull[:, 1].min() - pad, hull[:, 0].max() + pad, hull[:, 1].max() + pad]
         lane_i[l] = [ri[0], ri[1], ri[2], ri[3], hull_off, len(hull), ri[4], ri[5]]
         hull_off += len(hull) + 1
         # lane lines (pg_block.py:248-255, 334-361): left border only for lane 0 of a positive road

@@ -201,17 +201,35 @@ def run_episode(env_cls, config, seed, actions, tag, closed_loop=None):
         env.close()
 
 
-def _lane_follow_action(v, rs, noise, fast=32, slow=16):
+def _lane_follow_action(v, rs, noise, fast=32, slow=16, ahead=2.0, kh=2.5, kl=0.5):
     """Test-side driver for multi-agent traces: steer along the localised lane (slower on tight arcs), plus noise."""
     lane = v.navigation.current_lane
     lon, lat = lane.local_coordinates(v.position)
-    err = lane.heading_theta_at(lon + 2.0) - v.heading_theta
+    err = lane.heading_theta_at(lon + ahead) - v.heading_theta
     err = (err + np.pi) % (2 * np.pi) - np.pi
-    steer = 2.5 * err + 0.5 * lat + noise * rs.uniform(-1, 1)
+    steer = kh * err + kl * lat + noise * rs.uniform(-1, 1)
     tight = getattr(lane, "radius", 1e9) < 20
     target = slow if tight else fast
     thr = (0.6 if v.speed_km_h < target else (-0.3 if v.speed_km_h > target + 6 else 0.0)) + noise * rs.uniform(-1, 1)
     return [float(np.clip(steer, -1, 1)), float(np.clip(thr, -1, 1))]
+
+
+def _parking_action(name, v, rs):
+    """Test-side driver for the parking-lot trace: slow lane following; the agents pull out one after the other (agent k waits
+    100 k steps) and brake for an agent in front of them, so that some of them reach their parking space / the far end of a road."""
+    if v.engine.episode_step < int(os.environ.get("PK_WAIT", 100)) * int(name[5:]):
+        return [0.0, 0.0]
+    a = _lane_follow_action(v, rs, 0.02, fast=float(os.environ.get("PK_FAST", 9)), slow=float(os.environ.get("PK_SLOW", 4)),
+                            ahead=float(os.environ.get("PK_AHEAD", 1.0)), kh=float(os.environ.get("PK_KH", 4.0)), kl=float(os.environ.get("PK_KL", 1.0)))
+    hx, hy = np.cos(v.heading_theta), np.sin(v.heading_theta)
+    for u in v.engine.agent_manager.active_agents.values():
+        if u is v:
+            continue
+        dx, dy = u.position[0] - v.position[0], u.position[1] - v.position[1]
+        ahead, side = dx * hx + dy * hy, -dx * hy + dy * hx
+        if 0 < ahead < 8 and abs(side) < 2.5:
+            a[1] = -1.0 if v.speed_km_h > 1.0 else 0.0
+    return a
 
 
 def _toll_action(v, rs, noise, patient, waited, toll_x):
@@ -272,14 +290,41 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         seat_name = [v.name for v in seat_vehicle[:n]] + [None]  # engine recycles vehicle objects under new names
         spawn_roads = list(env.config["spawn_roads"])
         road_nodes = np.array([[mi.nodes[r.start_node], mi.nodes[r.end_node]] for r in spawn_roads], np.int32)
-        dest_nodes = np.array([mi.nodes[(-r).end_node] for r in spawn_roads], np.int32)
+        dest_nodes = np.array([mi.nodes.get((-r).end_node, -1) for r in spawn_roads], np.int32)
         # envs without a destination draw (the default SpawnManager.update_destination_for, spawn_manager.py:224-228):
         # auto_assign_task sends every agent to the far end of the map = one destination per spawn road
         fixed_dest = type(eng.spawn_manager).update_destination_for is \
             __import__("metadrive.manager.spawn_manager", fromlist=["SpawnManager"]).SpawnManager.update_destination_for
+        sm = eng.spawn_manager
+        parking = hasattr(sm, "parking_space_available")
         if fixed_dest:
             dest_nodes = dest_nodes[::-1].reshape(-1, 1).copy()
-        sm = eng.spawn_manager
+        park_log = []
+        if parking:
+            # MultiAgentParkingLotEnv (envs/marl_envs/marl_parking_lot.py:47-90): an agent born on one of the roads into the lot
+            # is sent to a parking space nobody else is heading for (drawn among the AVAILABLE ones), an agent born in a
+            # parking space to the far end of one of those roads.  One destination list per spawn road, -1 padded.
+            in_roads = list(env.config["in_spawn_roads"])
+            spaces = list(env.current_map.parking_space)
+            dest_nodes = np.full((len(spawn_roads), max(len(spaces), len(in_roads))), -1, np.int32)
+            for ri, r in enumerate(spawn_roads):
+                if r in in_roads:
+                    dest_nodes[ri, :len(spaces)] = [mi.nodes[s.end_node] for s in spaces]
+                else:
+                    dest_nodes[ri, :len(in_roads)] = [mi.nodes[(-q).end_node] for q in in_roads]
+            orig_gps = sm.get_parking_space
+
+            def logging_gps(v_id):   # the spaces that were available, in list order, and the one that was drawn
+                before = sorted(spaces.index(s) for s in sm.parking_space_available)
+                got = orig_gps(v_id)
+                park_log.append((before, spaces.index(got)))
+                return got
+
+            sm.get_parking_space = logging_gps
+            name_seat = {k: j for j, k in enumerate(names)}
+            parking_taken = np.full(n_seats, -1, np.int32)   # reset-time assignment: seat -> parking space it is heading for
+            for vid, s in sm.v_dest_pair.items():
+                parking_taken[name_seat[vid]] = spaces.index(s)
         place_keys = list(sm.safe_spawn_places.keys())
         place_lane = [tuple(sm.safe_spawn_places[k]["config"]["spawn_lane_index"]) for k in place_keys]
         first_query = []
@@ -346,7 +391,16 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
                 seat_name[j] = v.name
                 keys = first_query[0]
                 pk = place_keys[place_lane.index(tuple(v.config["spawn_lane_index"]))]
-                if fixed_dest:
+                if parking:
+                    road = [tuple(r) for r in road_nodes.tolist()].index(
+                        (mi.nodes[v.config["spawn_lane_index"][0]], mi.nodes[v.config["spawn_lane_index"][1]]))
+                    d_abs = int(np.nonzero(dest_nodes[road] == mi.nodes[v.config["destination"]])[0][0])
+                    if spawn_roads[road] in in_roads:   # rank of the drawn space among the available ones
+                        before, got = park_log[-1]
+                        assert got == d_abs
+                        d_abs = before.index(got)
+                    draws[t] = [keys.index(pk), d_abs, len(keys)]
+                elif fixed_dest:
                     road = [tuple(r) for r in road_nodes.tolist()].index(
                         (mi.nodes[v.config["spawn_lane_index"][0]], mi.nodes[v.config["spawn_lane_index"][1]]))
                     assert mi.nodes[v.navigation.checkpoints[-1]] == dest_nodes[road, 0]
@@ -384,6 +438,9 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         conf["n_lane_lasers"] = int(env.config["vehicle_config"]["lane_line_detector"]["num_lasers"])
         conf["lane_dist"] = float(env.config["vehicle_config"]["lane_line_detector"]["distance"])
         conf["ignore_road_sign"] = int("cross_yellow_line_done" in env.config)
+        if parking:   # marl_parking_lot.py:252-256: yellow solid line, off the lanes or sidewalk = out of road (white lines may be crossed)
+            conf.update(parking_spaces=len(spaces), parking_in_roads=len(in_roads), on_continuous_line_done=5,
+                        enable_reverse=int(bool(env.config["vehicle_config"]["enable_reverse"])))
         if env.config["vehicle_config"]["lidar"]["num_others"]:   # the others block sits between the state and the lidar floats
             conf.update(num_others=int(env.config["vehicle_config"]["lidar"]["num_others"]),
                         add_others_navi=int(bool(env.config["vehicle_config"]["lidar"]["add_others_navi"])))
@@ -400,6 +457,8 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
             ma_spawn_roads=road_nodes, ma_dest_nodes=dest_nodes, ma_alive_seats=np.array([n], np.int32),
             config=json.dumps(conf), **{"init_" + k: v for k, v in init.items()},
         )
+        if parking:
+            out["ma_parking_taken"] = parking_taken
         out["ref_lines"] = rx.export_static_bodies(env.engine)["lines"]
         return out
     finally:
@@ -630,6 +689,24 @@ def main():
         np.savez_compressed(path, **out)
         print("cfg3_ma_intersection_others_navi steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
               "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
+    # MultiAgentParkingLotEnv (envs/marl_envs/marl_parking_lot.py): agents born in parking spaces drive out, agents born on the
+    # roads into the lot drive into a free space (enable_reverse on; white lines may be crossed).
+    # Respawn is off: the reference's override (_respawn_single_vehicle, marl_parking_lot.py:230-236) calls vehicle.reset() WITHOUT the
+    # drawn place's config, so every newborn lands on the first road's default pose (5, 0) with no destination - there is no
+    # behaviour worth pinning there (DESIGN.md "Deliberate differences").
+    if args.only == "cfg3_ma_parkinglot":
+        from metadrive.envs.marl_envs.marl_parking_lot import MultiAgentParkingLotEnv
+        lid = dict(vehicle_config=dict(lidar=dict(num_lasers=72, distance=40, num_others=0)))
+        cfgp = dict(num_agents=7, allow_respawn=False, log_level=50, delay_done=25, horizon=1000, **lid)
+        rs_p = np.random.RandomState(17)   # a slow lane-follow driver: the lot's arcs are a car length wide
+        out = run_episode_ma(MultiAgentParkingLotEnv, cfgp, None, "cfg3_ma_parkinglot", steps=args.ma_steps if args.ma_steps != 450 else 800,
+                             noise=args.ma_noise, seed=17, obs_stride=2,
+                             driver=lambda k, v: _parking_action(k, v, rs_p))
+        path = os.path.join(args.out, "cfg3_ma_parkinglot.npz")
+        np.savez_compressed(path, **out)
+        print("cfg3_ma_parkinglot steps", len(out["reward"]), "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()),
+              "out of road", int(((out["info_flags"] & 0x400) != 0).sum()), "crashes", int(((out["info_flags"] & 0x1) != 0).sum()),
+              "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     # MultiAgentBottleneckEnv (envs/marl_envs/marl_bottleneck.py): Merge / Split blocks, agents born at both ends without a
     # destination draw, 4-ray side / lane-line detectors in the observation, reward without the positive_road sign
     if args.only == "cfg3_ma_bottleneck_respawn":
