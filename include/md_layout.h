@@ -128,6 +128,7 @@
  *               to done_function (:261-266): both times recorded and exit - entry < min_pass_steps
  *   VC_TOLL_ENTRY = entry_time + 1 (0 = none) */
 #define VC_TOLL_A 14
+#define VC_PARK 14       /* parking-lot env (never a toll env): 1 + the parking space this agent is heading for, 0 = none */
 #define VC_TOLL_ENTRY 15
 /* veh_i [NV, 16] */
 #define VEH_I 16
@@ -274,6 +275,12 @@ typedef struct MdConfig {
     /* lidar.add_others_navi (component/sensors/lidar.py:120-129): every neighbour of the num_others block carries 4 more floats,
      * ITS two navigation checkpoints (BaseNavigation.get_checkpoints, base_navigation.py:145-152) in the observer's frame */
     int add_others_navi;
+    /* MultiAgentParkingLotEnv (envs/marl_envs/marl_parking_lot.py:47-142): parking_spaces > 0 switches on ParkingLotSpawnManager's
+     * respawn rules.  The spawn roads 0 .. parking_in_roads-1 lead INTO the lot: an agent born there is sent to a parking space no
+     * active agent is heading for (destination d of its road = space d; VC_PARK of the agent = d + 1), and such a place is no
+     * respawn place while no space is free; the other spawn roads are the spaces themselves, whose agents are sent to the far end of
+     * one of the roads into the lot (destinations 0 .. parking_in_roads-1 of their road) */
+    int parking_spaces, parking_in_roads;
 } MdConfig;
 
 /* ---- all arrays of one simulation, as plain pointers (host for the oracle, device for the library) */

@@ -25,7 +25,7 @@ extern "C" {
 
 typedef struct md_sim md_sim;
 
-#define MD_ABI_VERSION 7
+#define MD_ABI_VERSION 8
 int md_abi_version(void);
 /* sizeof(MdConfig) / sizeof(MdArrays) the library was built with: the loader compares them with its own mirror */
 int md_sizeof_config(void);

@@ -3,7 +3,8 @@
 Only the step path lives here (include/mdstep.h is the boundary): hand-written sm_100a kernels in csrc/, the ctypes
 binding (lib, sim), host-side scene tables (scene, library) and the drop-in env classes (envs)."""
 from .envs import (BatchedMetaDriveEnv, BatchedMultiAgentEnv, MetaDriveEnv, MultiAgentBottleneckEnv,  # noqa: F401
-                   MultiAgentIntersectionEnv, MultiAgentMetaDrive, MultiAgentRoundaboutEnv, MultiAgentTollgateEnv,
+                   MultiAgentIntersectionEnv, MultiAgentMetaDrive, MultiAgentParkingLotEnv, MultiAgentRoundaboutEnv,
+                   MultiAgentTollgateEnv,
                    SafeMetaDriveEnv, TopDownMetaDrive, TopDownSingleFrameMetaDriveEnv)
 
 __version__ = "0.1.0"

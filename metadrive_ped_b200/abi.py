@@ -23,6 +23,7 @@ class MdConfig(C.Structure):
         ("lidar_gaussian_noise", C.c_float), ("lidar_dropout_prob", C.c_float), ("noise_seed", C.c_int),
         ("env_base", C.c_int), ("ignore_road_sign", C.c_int),
         ("toll_env", C.c_int), ("min_pass_steps", C.c_int), ("overspeed_penalty", C.c_float), ("add_others_navi", C.c_int),
+        ("parking_spaces", C.c_int), ("parking_in_roads", C.c_int),
     ]
 
 
@@ -40,7 +41,7 @@ def make_config(n_envs, slots_per_env, agents_per_env=1, objs_per_env=0, **kw):
         is_multi_agent=0, delay_done=0, allow_respawn=0, ma_places=0, ma_dests=0, ma_roads=0, tape_len=1,
         ma_crash_done=1, ma_out_of_road_done=1, num_others=0, n_side_lasers=0, n_lane_lasers=0, side_dist=50.0, lane_dist=20.0, discrete_action=0,
         discrete_steering_dim=5, discrete_throttle_dim=5, lidar_gaussian_noise=0.0, lidar_dropout_prob=0.0, noise_seed=0, env_base=0, ignore_road_sign=0,
-        toll_env=0, min_pass_steps=30, overspeed_penalty=0.5, add_others_navi=0,
+        toll_env=0, min_pass_steps=30, overspeed_penalty=0.5, add_others_navi=0, parking_spaces=0, parking_in_roads=0,
     )
     for k, v in kw.items():
         if k not in d:

@@ -2647,6 +2647,7 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
     if (env >= cfg.n_envs) return;
     Fp* nb = reinterpret_cast<Fp*>(smem_raw) + (size_t)warp * S;
     int n_alive = 0, seat = 0x7fffffff;
+    unsigned park_taken = 0u;   // parking-lot env: the spaces ACTIVE agents are heading for (marl_parking_lot.py:61-76)
     for (int s0 = 0; s0 < S; s0 += 32) {
         const int s = s0 + lane;
         int alive = 0, free_seat = 0;
@@ -2654,6 +2655,10 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
             const size_t g = (size_t)env * S + s;
             const int* I = A.veh_i + g * VEH_I;
             alive = I[VI_ALIVE];
+            if (cfg.parking_spaces > 0 && s < NA && I[VI_ACTIVE]) {
+                const int sp = (int)A.veh_c[g * VEH_C + VC_PARK];
+                if (sp > 0) park_taken |= 1u << (sp - 1);
+            }
             nb[s].alive = alive;
             if (alive) {
                 float P[VEH_P], St[VEH_S];
@@ -2669,6 +2674,14 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
         if (fm && seat == 0x7fffffff) seat = s0 + __ffs(fm) - 1;
     }
     __syncwarp();
+    unsigned park_free = 0u;
+    int n_park_free = 0;
+    if (cfg.parking_spaces > 0) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) park_taken |= __shfl_xor_sync(0xffffffffu, park_taken, off);
+        park_free = ((1u << cfg.parking_spaces) - 1u) & ~park_taken;
+        n_park_free = __popc(park_free);
+    }
     int* E = A.env_i + (size_t)env * ENV_I;
     const bool allowed = cfg.allow_respawn && !(cfg.horizon > 0 && E[EI_STEP] >= cfg.horizon) &&
                          seat != 0x7fffffff && n_alive < NA - 1;
@@ -2683,9 +2696,10 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
             const float4 a = Pl[0], b = Pl[1];
             Rect pr;
             pr.cx = a.x; pr.cy = a.y; pr.ux = b.y; pr.uy = b.z; pr.hu = 4.0f; pr.hv = 1.5f;
-            clear = true;
-            for (int k = 0; k < S; k++)
-                if (nb[k].alive && rect_rect(pr, nb[k].r)) { clear = false; break; }
+            // parking-lot env: no free space, no agent from outside (get_available_respawn_places, marl_parking_lot.py:103-105)
+            clear = !(cfg.parking_spaces > 0 && (int)b.w < cfg.parking_in_roads && n_park_free == 0);
+            for (int k = 0; k < S && clear; k++)
+                if (nb[k].alive && rect_rect(pr, nb[k].r)) clear = false;
         }
         clear_mask |= (unsigned long long)__ballot_sync(0xffffffffu, clear) << p0;
     }
@@ -2693,7 +2707,7 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
     const int n_clear = __popcll(clear_mask);
     const uint32_t ctr = (uint32_t)E[EI_RNG];
     int pick = (int)(tape_draw(cfg, A.env_tape, env, ctr, 0) % (uint32_t)n_clear);
-    const int dsel = (int)(tape_draw(cfg, A.env_tape, env, ctr, 1) % (uint32_t)cfg.ma_dests);
+    int dsel = (int)(tape_draw(cfg, A.env_tape, env, ctr, 1) % (uint32_t)cfg.ma_dests);
     E[EI_RNG] = (int)(ctr + 1u);
     int p = 0;
     for (unsigned long long mk = clear_mask;; mk &= mk - 1) {  // the pick-th clear place
@@ -2701,6 +2715,16 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
         if (pick-- == 0) break;
     }
     const float* Pl = A.ma_place_f + ((size_t)env * cfg.ma_places + p) * 8;
+    int park = 0;
+    if (cfg.parking_spaces > 0) {   // update_destination_for (marl_parking_lot.py:80-88)
+        if ((int)Pl[7] < cfg.parking_in_roads) {   // from outside: the r-th free space
+            int r = (int)(tape_draw(cfg, A.env_tape, env, ctr, 1) % (uint32_t)n_park_free);
+            unsigned mk = park_free;
+            while (r-- > 0) mk &= mk - 1u;
+            dsel = __ffs((int)mk) - 1;
+            park = dsel + 1;
+        } else dsel = (int)(tape_draw(cfg, A.env_tape, env, ctr, 1) % (uint32_t)cfg.parking_in_roads);   // from a space: one of the ways out
+    }
     const size_t g = (size_t)env * S + seat;
     float P[VEH_P], St[VEH_S], C[VEH_C], navi[NAVI_DIM];
     int I[VEH_I];
@@ -2716,6 +2740,7 @@ k_respawn(MdConfig cfg, MdArrays A, StepOut out, float* __restrict__ body_tab) {
     for (int k = 0; k < NAVI_DIM; k++) navi[k] = 0.0f;
     St[VS_POS] = Pl[0]; St[VS_POS + 1] = Pl[1]; St[VS_POS + 2] = 0.5f * P[VP_HEIGHT];
     St[VS_QUAT] = Pl[2]; St[VS_QUAT + 3] = Pl[3];
+    C[VC_PARK] = (float)park;
     const int rsel = (int)Pl[7] * cfg.ma_dests + dsel;
     const int* rt = A.ma_route + ((size_t)env * cfg.ma_roads * cfg.ma_dests + rsel) * ROUTE_MAX;
     const int* rr = A.ma_rroad + ((size_t)env * cfg.ma_roads * cfg.ma_dests + rsel) * ROUTE_MAX;

@@ -615,6 +615,10 @@ def _ma_cfg_kw(c):
         # MultiAgentBottleneckEnv._is_out_of_road / reward_function (envs/marl_envs/marl_bottleneck.py:89-135): white solid
         # line | off the lanes | sidewalk, plus the yellow solid line when cross_yellow_line_done; no positive_road sign
         kw.update(out_of_route_done=0, on_continuous_line_done=1 if c["cross_yellow_line_done"] else 2, ignore_road_sign=1)
+    if "parking_space_num" in c:
+        # MultiAgentParkingLotEnv._is_out_of_road (envs/marl_envs/marl_parking_lot.py:252-256): yellow solid line | off the lanes |
+        # sidewalk - the white lines of the lot may be crossed
+        kw.update(on_continuous_line_done=5)
     if "overspeed_penalty" in c:
         # MultiAgentTollgateEnv (envs/marl_envs/marl_tollgate.py:185-266): out of road = sidewalk (+ yellow solid line), the toll
         # block's overspeed penalty, the stay-time rule, TollGateObservation
@@ -773,6 +777,24 @@ class MultiAgentTollgateEnv(MultiAgentMetaDrive):
                         vehicle_config=dict(min_pass_steps=30, side_detector=dict(num_lasers=72, distance=20),
                                             lane_line_detector=dict(num_lasers=4, distance=20),
                                             lidar=dict(num_lasers=72, distance=20)))
+
+
+class MultiAgentParkingLotEnv(MultiAgentMetaDrive):
+    """envs/marl_envs/marl_parking_lot.py:22-43, 47-142, 199-260: a one-lane street with four parking spaces on either side between
+    the first block and a T intersection.  Agents are born in the parking spaces (they pull out and leave by one of the three roads)
+    and on the three roads into the lot (each is sent to a parking space nobody else is heading for); vehicles can reverse
+    (enable_reverse), white lines may be crossed.  Respawn follows ParkingLotSpawnManager's rules - no newcomer from outside while
+    every space is spoken for, a space is free again once its agent is done - on the device (`MdConfig.parking_spaces`).  The
+    reference's own `_respawn_single_vehicle` override drops the drawn place (it calls `vehicle.reset()` without the config, :235),
+    so its newborns all land on the first road's default pose without a destination; this build respawns them where the spawn
+    manager put them (DESIGN.md "Deliberate differences")."""
+    ASSET = "ma_parkinglot.npz"
+    ENV_DEFAULTS = dict(num_agents=10, parking_space_num=8, vehicle_config=dict(enable_reverse=True))
+
+    def __init__(self, config=None):
+        super().__init__(config)
+        if self.config["parking_space_num"] != 8:
+            raise NotImplementedError("the parking lot is generated with the env's default of 8 spaces")
 
 
 class BatchedMultiAgentEnv:

@@ -18,7 +18,7 @@ EXPORTS = [
     "md_host_group_views", "md_host_send", "md_host_recv", "md_host_compact", "md_fp32_peak", "md_enable_contacts", "md_get_contacts",
     "md_topdown", "md_topdown_channels",
 ]
-ABI_VERSION = 7  # include/mdstep.h MD_ABI_VERSION
+ABI_VERSION = 8  # include/mdstep.h MD_ABI_VERSION
 
 
 class MdStepError(RuntimeError):

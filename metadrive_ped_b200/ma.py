@@ -120,8 +120,14 @@ MA_MAPS = {
     # reward_function, :113, at the first step, so there is no behaviour to pin)
     "bidirection": dict(env="ma_bidirection", num_agents=20, spawn_nodes=[(3, 0, 0, 1)], lane_num=4, exit_length=60.0,
                         fixed_dest=True),
+    # envs/marl_envs/marl_parking_lot.py:22-43, 144-184: first block -> ParkingLot (4 spaces a side) -> T intersection (exits 10 m), one
+    # lane each way.  Spawn roads = the three roads INTO the lot (first road, the negatives of the T's two far exits) + the eight
+    # parking spaces under their second road name (ParkingLot.node(1, i, 5) -> (1, i, 6), :207-211).  An agent born on a road into the
+    # lot is sent to a parking space nobody else is heading for, one born in a space to the far end of one of the three roads (:80-88).
+    "parkinglot": dict(env="ma_parkinglot", num_agents=10, spawn_nodes=[(2, 0, 0, 1), (2, 2, 0, 1)], lane_num=1, exit_length=20.0,
+                       parking=True),
 }
-ASSET_KIND = {"ma_roundabout.npz": "roundabout", "ma_intersection.npz": "intersection", "ma_bottleneck.npz": "bottleneck",
+ASSET_KIND = {"ma_parkinglot.npz": "parkinglot", "ma_roundabout.npz": "roundabout", "ma_intersection.npz": "intersection", "ma_bottleneck.npz": "bottleneck",
               "ma_tollgate.npz": "tollgate", "ma_bidirection.npz": "bidirection"}
 
 
@@ -149,9 +155,20 @@ def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None):
     # half extent across the heading, half extent along it - the barrier's column order -, height BUILDING_HEIGHT = 5, lane id)
     objects = np.array([[4.0, b[1], b[2], b[3], b[5], b[4], 5.0, b[0]] for blk in meta["blocks"]
                         for b in blk.get("buildings", [])], np.float64).reshape(-1, 8)
+    if m.get("parking"):
+        lot = big.blocks[1]
+        n_in, spaces = len(roads), [node[r[1]] for r in lot.dest_roads]
+        exits = [node[pgmap.neg_road(r)[1]] for r in roads]
+        roads = roads + list(lot.parking_spawn_roads)
+        dest = np.full((len(roads), max(len(spaces), n_in)), -1, np.int32)   # one destination list per spawn road, -1 padded
+        dest[:n_in, :len(spaces)] = spaces
+        dest[n_in:, :n_in] = exits
+        conf.update(parking_spaces=len(spaces), parking_in_roads=n_in)
+        static[15] = 1.0   # vehicle_config enable_reverse (marl_parking_lot.py:38)
+    else:
+        dest = np.array([node[pgmap.neg_road(r)[1]] for r in roads], np.int32)
     return dict(lane_f=lane_f, lane_i=lane_i, road_i=road_i, meta=json.dumps(meta), config=json.dumps(conf), objects=objects,
-                spawn_roads=np.array([[node[a], node[b]] for a, b in roads], np.int32),
-                dest_nodes=np.array([node[pgmap.neg_road(r)[1]] for r in roads], np.int32),
+                spawn_roads=np.array([[node[a], node[b]] for a, b in roads], np.int32), dest_nodes=dest,
                 veh_static=np.asarray(static, np.float32))
 
 
@@ -203,12 +220,14 @@ class MultiAgentLibrary:
             "Too many agents! We only accept {} agents, but you have {} agents!".format(self.max_capacity, num_agents)
         pick = rng.choice(len(self.slots), num_agents, replace=False)
         D = self.tables["n_dests"]
+        n_in, free = int(c.get("parking_in_roads", 0)), list(range(int(c.get("parking_spaces", 0))))
         dl = (c["respawn_longitude"] - c["max_vehicle_length"]) / 2
         dw = (c["respawn_lateral"] - c["max_vehicle_width"]) / 2
         H = float(self.veh_static[3])
         veh_dyn = np.zeros((num_agents, 14), np.float64)
         routes = np.full((num_agents, sc.ROUTE_MAX), -1, np.int32)
         veh_int = np.zeros((num_agents, 6), np.int32)
+        parking = np.full(num_agents, -1, np.int32)
         for k, si in enumerate(pick):
             lane, lon, ri = self.slots[int(si)]
             lon = lon + rng.uniform(-dl, dl) if dl > 0 else lon + rng.uniform(dl, -dl)
@@ -218,14 +237,21 @@ class MultiAgentLibrary:
             yaw = sc.lane_heading_at(row, lon) - math.pi / 2
             veh_dyn[k, 0:3] = [x, y, H / 2]
             veh_dyn[k, 3:7] = [math.cos(yaw / 2), 0.0, 0.0, math.sin(yaw / 2)]
-            d = int(rng.integers(0, D))
+            if not n_in:
+                d = int(rng.integers(0, D))
+            elif ri < n_in:    # ParkingLotSpawnManager.get_parking_space (marl_parking_lot.py:61-71): a space nobody is heading for
+                assert len(free) > 0, "more agents on the roads into the lot than parking spaces"
+                d = free.pop(int(rng.integers(0, len(free))))
+                parking[k] = d
+            else:              # update_destination_for (:80-88): the far end of one of the roads into the lot
+                d = int(rng.integers(0, n_in))
             rt = self.tables["routes"][ri * D + d]
             routes[k] = rt
             n_ck = int((rt >= 0).sum())
             veh_int[k] = [1, -1, lane, 0, 1 if n_ck > 2 else 0, 1]
         static = np.tile(self.veh_static, (num_agents, 1))
         idm = np.tile(np.array([[0.0, 30.0]], np.float32), (num_agents, 1))
-        return sc.Scenario(0, static, veh_dyn, routes, veh_int, idm, self.objects, 0)
+        return sc.Scenario(0, static, veh_dyn, routes, veh_int, idm, self.objects, 0, parking if n_in else None)
 
     def build_world(self, n_envs, num_agents, seed=0, **cfg_kw):
         """(arrays, cfg) for n_envs independent multi-agent envs: num_agents + 1 seats each (the spare seat keeps a
@@ -238,6 +264,7 @@ class MultiAgentLibrary:
         O = len(self.objects)
         arrays = sc.pack([self.geo], scen, S, NA, O, ma_tables={0: self.tables}, ma_tables_tape=tape)
         kw = dict(is_multi_agent=1, ma_places=len(self.tables["places"]), ma_dests=self.tables["n_dests"],
-                  ma_roads=self.tables["n_roads"], tape_len=TAPE_LEN)
+                  ma_roads=self.tables["n_roads"], tape_len=TAPE_LEN, parking_spaces=int(self.conf.get("parking_spaces", 0)),
+                  parking_in_roads=int(self.conf.get("parking_in_roads", 0)))
         kw.update(cfg_kw)
         return arrays, make_config(n_envs, S, NA, O, **kw)

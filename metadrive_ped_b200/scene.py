@@ -15,7 +15,7 @@ Host-side numpy in float64, rounded to float32 at the end.
 import json
 import math
 from dataclasses import dataclass, field
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 
@@ -365,6 +365,7 @@ class Scenario:
     idm: np.ndarray
     objects: np.ndarray
     seed: int = 0
+    parking: Optional[np.ndarray] = None   # parking-lot env: [n] the parking space every vehicle is heading for, -1 = none
 
 
 def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int, agents_per_env: int,
@@ -466,6 +467,8 @@ def pack(maps: List[MapGeometry], scenarios: List[Scenario], slots_per_env: int,
         veh_idm[sl, 0] = sc.idm[:, 0]
         veh_idm[sl, 1] = sc.idm[:, 1]
         veh_c[sl, 0:2] = sc.veh_dyn[:, 0:2]
+        if sc.parking is not None:
+            veh_c[sl, 14] = np.asarray(sc.parking, np.float32) + 1.0    # VC_PARK (include/md_layout.h)
         m = len(sc.objects)
         if m > O:
             raise ValueError("an env holds %d objects but objs_per_env is %d" % (m, O))

@@ -46,7 +46,8 @@ def golden_world_ma(g, replicas=1, **cfg_kw):
     geo = sc.build_map_geometry(mt)
     n = int(g["ma_alive_seats"][0])
     scen = sc.Scenario(0, g["init_veh_static"][:n], g["init_veh_dyn"][:n], g["init_routes"][:n], g["init_veh_int"][:n],
-                       g["init_idm"][:n], g["init_objects"], int(g["seed"]))
+                       g["init_idm"][:n], g["init_objects"], int(g["seed"]),
+                       g["ma_parking_taken"][:n] if "ma_parking_taken" in g else None)
     NA = n + 1
     S = ((NA + 3) // 4) * 4
     tables = ma.build_ma_tables(geo, g["ma_spawn_roads"], g["ma_dest_nodes"])
@@ -62,7 +63,8 @@ def golden_world_ma(g, replicas=1, **cfg_kw):
               n_side_lasers=int(conf.get("n_side_lasers", 0)), side_dist=float(conf.get("side_dist", 50.0)),
               n_lane_lasers=int(conf.get("n_lane_lasers", 0)), lane_dist=float(conf.get("lane_dist", 20.0)),
               ignore_road_sign=int(conf.get("ignore_road_sign", 0)))
-    for k in ("toll_env", "min_pass_steps", "on_continuous_line_done", "out_of_route_done", "num_others", "add_others_navi"):
+    for k in ("toll_env", "min_pass_steps", "on_continuous_line_done", "out_of_route_done", "num_others", "add_others_navi",
+              "parking_spaces", "parking_in_roads"):
         if k in conf:
             kw[k] = int(conf[k])
     for k in ("overspeed_penalty", "speed_reward"):

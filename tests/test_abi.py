@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(h, n), n
     assert set(names) == set(mdlib.EXPORTS)
     h.md_abi_version.restype = ctypes.c_int
-    assert h.md_abi_version() == 7
+    assert h.md_abi_version() == 8
 
 
 def test_config_struct_matches_header():

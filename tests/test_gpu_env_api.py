@@ -596,3 +596,27 @@ def test_enable_reverse():
         env.close()
     assert out[False][0] > 0.0 and abs(out[False][1]) < 0.5          # braked to a stop ahead of where braking began
     assert out[True][0] < out[False][0] - 3.0 and out[True][1] > 1.0  # rolled back past it, still moving (speed is unsigned)
+
+
+def test_ma_parking_lot_env_surface():
+    """MultiAgentParkingLotEnv (envs/marl_envs/marl_parking_lot.py): 10 agents among 8 parking spaces + 3 roads into the lot, dict
+    surface, vehicles that can reverse, finished agents replaced by newborns with fresh ids."""
+    from metadrive_ped_b200 import MultiAgentParkingLotEnv
+    env = MultiAgentParkingLotEnv({"delay_done": 5})
+    try:
+        obs, info = env.reset()
+        assert len(obs) == 10 and env.observation_space.contains(obs) and obs["agent0"].shape == (19 + 72, )
+        assert env.config["vehicle_config"]["enable_reverse"]
+        seen, finished = set(obs), 0
+        rng = np.random.RandomState(0)
+        for step in range(250):
+            act = {k: [rng.uniform(-0.5, 0.5), 0.4] for k in env.agents.keys()}
+            o, r, tm, tc, i = _ma_act(env, act)
+            finished += sum(bool(v) for k, v in tm.items() if k != "__all__")
+            seen |= set(o)
+            if tm["__all__"]:
+                break
+        assert finished >= 3 and len(seen) > 10, "agents finish (crash / leave the lot) and newborns take over"
+        assert INFO_KEYS <= set(next(iter(i.values())))
+    finally:
+        env.close()

@@ -24,6 +24,15 @@ def _world(workload, n_envs=None):
         from metadrive_ped_b200.ma import MultiAgentLibrary
         c = MultiAgentTollgateEnv.default_config()
         return MultiAgentLibrary(MultiAgentTollgateEnv.ASSET).build_world(n_envs or 48, c["num_agents"], seed=3, **_ma_cfg_kw(c))
+    if workload == "park":
+        # MultiAgentParkingLotEnv at its default 10 agents (envs/marl_envs/marl_parking_lot.py:22-43), 64 envs: pulling out of the
+        # spaces, reversing, ParkingLotSpawnManager's respawn rules under random driving
+        from metadrive_ped_b200.envs import MultiAgentParkingLotEnv, _apply_vehicle_config, _ma_cfg_kw
+        from metadrive_ped_b200.ma import MultiAgentLibrary
+        c = MultiAgentParkingLotEnv.default_config()
+        arrays, cfg = MultiAgentLibrary(MultiAgentParkingLotEnv.ASSET).build_world(n_envs or 64, c["num_agents"], seed=5, **_ma_cfg_kw(c))
+        _apply_vehicle_config(arrays, c)
+        return arrays, cfg
     n = n_envs or bench.WORKLOADS[workload]["envs"]
     _, arrays, cfg = bench.build_world(n, 0, workload)
     return arrays, cfg
@@ -46,6 +55,12 @@ def _actions(rng, cfg, multi):
         pace = np.random.RandomState(13).uniform(0.05, 1.0, n)
         a[:, 1] = pace * rng.uniform(0.2, 1.0, n)
         return a.astype(np.float32)
+    if cfg.parking_spaces:
+        # a parking lot: gentle throttle, now and then the brake / reverse gear, every agent with its own steering bias
+        a = np.zeros((n, 2), np.float32)
+        a[:, 0] = np.random.RandomState(14).uniform(-0.6, 0.6, n) + 0.3 * rng.uniform(-1.0, 1.0, n)
+        a[:, 1] = np.where(rng.uniform(0, 1, n) < 0.15, -0.6, 0.35) * rng.uniform(0.3, 1.0, n)
+        return a.astype(np.float32)
     bias = np.random.RandomState(11).uniform(-0.25, 0.25, n)
     a = rng.uniform(-1.0, 1.0, (n, 2)).astype(np.float32)
     a[:, 0] = (0.3 * a[:, 0] + bias).astype(np.float32)
@@ -53,13 +68,13 @@ def _actions(rng, cfg, multi):
     return a
 
 
-@pytest.mark.parametrize("workload,steps", [("cfg2", 60), ("cfg4", 40), ("cfg5", 40), ("cfg3", 25), ("toll", 150)])
+@pytest.mark.parametrize("workload,steps", [("cfg2", 60), ("cfg4", 40), ("cfg5", 40), ("cfg3", 25), ("toll", 150), ("park", 400)])
 def test_full_size_step_matches_oracle(workload, steps, oracle_lib):
     import torch
     from metadrive_ped_b200.sim import BatchedSim
     from oracle.oracle import OracleSim, set_threads
     set_threads()
-    multi = workload in ("cfg3", "toll")
+    multi = workload in ("cfg3", "toll", "park")
     arrays, cfg = _world(workload)
     E, S, NA, O = cfg.n_envs, cfg.slots_per_env, cfg.agents_per_env, cfg.objs_per_env
     sim, orc = BatchedSim(arrays, cfg), OracleSim(arrays, cfg)
@@ -72,7 +87,7 @@ def test_full_size_step_matches_oracle(workload, steps, oracle_lib):
     rows = {"env_i": 1, "obj_f": O}
     ok = np.ones(E, bool)  # envs still in lock-step
     rng = np.random.RandomState(7)
-    n_done = n_rays = n_bad_rays = n_float = n_float_diff = 0
+    n_done = n_rays = n_bad_rays = n_float = n_float_diff = n_newborn = 0
     for t in range(steps):
         a = _actions(rng, cfg, multi)
         sim.step(torch.from_numpy(a).cuda(), autoreset=not multi)
@@ -96,6 +111,9 @@ def test_full_size_step_matches_oracle(workload, steps, oracle_lib):
         per_env = lambda x: x.reshape(E, -1)
         same &= (per_env(fl_g) == per_env(fl_o)).all(1) & (per_env(te_g) == per_env(orc.term)).all(1)
         same &= (per_env(tr_g) == per_env(orc.trunc)).all(1)
+        if workload == "park":   # who is heading for which parking space (VC_PARK)
+            same &= (sim.get_state("veh_c").reshape(E, S, -1)[:, :, 14] == orc.a["veh_c"].reshape(E, S, -1)[:, :, 14]).all(1)
+            n_newborn += int(((fl_o & 0x4000) != 0).sum())
         ok &= same
         assert ok.all(), "%d of %d envs differ in their integer state at step %d" % ((~ok).sum(), E, t)
         m_env = ok
@@ -117,6 +135,8 @@ def test_full_size_step_matches_oracle(workload, steps, oracle_lib):
     assert n_bad_rays == 0 and n_float_diff == 0, (n_bad_rays, n_rays, n_float_diff, n_float)
     if not multi:
         assert n_done > 0, "the run must exercise the fused auto-reset"
+    if workload == "park":
+        assert n_newborn >= E, "the run must exercise the parking lot's respawn rules (%d respawns)" % n_newborn
     print("%s: %d envs x %d steps, %d resets, %d floats (state + observations) compared, all bit-identical"
           % (workload, E, steps, n_done, n_float))
     sim.close()
