@@ -699,7 +699,7 @@ def main():
         lid = dict(vehicle_config=dict(lidar=dict(num_lasers=72, distance=40, num_others=0)))
         cfgp = dict(num_agents=7, allow_respawn=False, log_level=50, delay_done=25, horizon=1000, **lid)
         rs_p = np.random.RandomState(17)   # a slow lane-follow driver: the lot's arcs are a car length wide
-        out = run_episode_ma(MultiAgentParkingLotEnv, cfgp, None, "cfg3_ma_parkinglot", steps=args.ma_steps if args.ma_steps != 450 else 800,
+        out = run_episode_ma(MultiAgentParkingLotEnv, cfgp, None, "cfg3_ma_parkinglot", steps=args.ma_steps if args.ma_steps != 450 else 1000,
                              noise=args.ma_noise, seed=17, obs_stride=2,
                              driver=lambda k, v: _parking_action(k, v, rs_p))
         path = os.path.join(args.out, "cfg3_ma_parkinglot.npz")
