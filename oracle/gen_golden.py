@@ -694,6 +694,8 @@ def main():
     # Respawn is off: the reference's override (_respawn_single_vehicle, marl_parking_lot.py:230-236) calls vehicle.reset() WITHOUT the
     # drawn place's config, so every newborn lands on the first road's default pose (5, 0) with no destination - there is no
     # behaviour worth pinning there (DESIGN.md "Deliberate differences").
+    # (ParkingLotSpawnManager indexes list(set) of Road objects, marl_parking_lot.py:66-67: the fixture is what PYTHONHASHSEED=0 gives,
+    # which main() sets for every tag's process)
     if args.only == "cfg3_ma_parkinglot":
         from metadrive.envs.marl_envs.marl_parking_lot import MultiAgentParkingLotEnv
         lid = dict(vehicle_config=dict(lidar=dict(num_lasers=72, distance=40, num_others=0)))
