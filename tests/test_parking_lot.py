@@ -1,8 +1,6 @@
 """MultiAgentParkingLotEnv (envs/marl_envs/marl_parking_lot.py) on the host: the generated library against the reference trace
 `cfg3_ma_parkinglot`, and ParkingLotSpawnManager's respawn rules as the CPU oracle restates them (the CUDA path is compared with
 the oracle bit for bit in tests/test_gpu_full_size.py::test_full_size_step_matches_oracle[park])."""
-import json
-
 import numpy as np
 
 from tests.golden_util import load_golden
