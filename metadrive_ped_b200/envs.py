@@ -649,8 +649,8 @@ class MultiAgentMetaDrive:
         for k in UNSUPPORTED_TRUE:
             if self.config[k]:
                 raise NotImplementedError("config['%s'] is outside the step path this build covers" % k)
-        if self.config["traffic_density"] != 0.0:
-            raise NotImplementedError("multi-agent envs with IDM traffic are not covered")
+        if abs(self.config["traffic_density"]) >= 1e-2 and self.config["traffic_mode"] != "trigger":
+            raise NotImplementedError("multi-agent envs with respawn / hybrid IDM traffic are not covered (trigger mode is)")
         if self.config["record_episode"] or self.config["replay_episode"] is not None:
             raise NotImplementedError("record / replay covers the single-agent envs")
         lid = self.config["vehicle_config"]["lidar"]
@@ -679,7 +679,9 @@ class MultiAgentMetaDrive:
             self._sim.close()
         rs = (seed if seed is not None else self.config["start_seed"]) * 1000003 + self._episode
         self._episode += 1
-        arrays, cfg = self._lib.build_world(1, self.num_agents, seed=rs, **_ma_cfg_kw(self.config))
+        arrays, cfg = self._lib.build_world(1, self.num_agents, seed=rs, traffic_density=self.config["traffic_density"],
+                                            traffic_seed=seed if seed is not None else self.config["start_seed"],
+                                            **_ma_cfg_kw(self.config))
         _apply_vehicle_config(arrays, self.config)
         self._sim = BatchedSim(arrays, cfg, device=self.config["device"])
         self._seat_id = ["agent%d" % k for k in range(self.num_agents)] + [None]
@@ -807,7 +809,10 @@ class BatchedMultiAgentEnv:
         c = _merge(env_cls.default_config(), config)
         lib = MultiAgentLibrary(env_cls.ASSET)
         n = c["num_agents"] if c["num_agents"] != -1 else lib.max_capacity
-        arrays, cfg = lib.build_world(num_envs, n, seed=seed, **_ma_cfg_kw(c))
+        if abs(c["traffic_density"]) >= 1e-2 and c["traffic_mode"] != "trigger":
+            raise NotImplementedError("multi-agent envs with respawn / hybrid IDM traffic are not covered (trigger mode is)")
+        arrays, cfg = lib.build_world(num_envs, n, seed=seed, traffic_density=c["traffic_density"], traffic_seed=c["start_seed"],
+                                      **_ma_cfg_kw(c))
         _apply_vehicle_config(arrays, c)
         self.sim = BatchedSim(arrays, cfg, device=c["device"])
         self.num_envs, self.seats = num_envs, n + 1

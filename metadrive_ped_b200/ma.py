@@ -169,7 +169,7 @@ def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None):
         dest = np.array([node[pgmap.neg_road(r)[1]] for r in roads], np.int32)
     return dict(lane_f=lane_f, lane_i=lane_i, road_i=road_i, meta=json.dumps(meta), config=json.dumps(conf), objects=objects,
                 spawn_roads=np.array([[node[a], node[b]] for a, b in roads], np.int32), dest_nodes=dest,
-                veh_static=np.asarray(static, np.float32))
+                veh_static=np.asarray(static, np.float32), big=big)
 
 
 class MultiAgentLibrary:
@@ -181,8 +181,10 @@ class MultiAgentLibrary:
     (`_randomize_position_in_slot`, :211-217) and a random destination per agent (marl_inout_roundabout.py:138-143).
     The reference draws these from an unseeded generator; here the caller passes the generator."""
     def __init__(self, name, from_asset=False):
+        self.big = None   # the generated map's blocks and lanes (IDM traffic is populated over them); an exported asset has none
         if not from_asset and ASSET_KIND.get(name, name) in MA_MAPS:
             d = generated_source(ASSET_KIND.get(name, name))
+            self.big = d["big"]
         else:
             path = name if os.path.exists(name) else os.path.join(ASSET_DIR, name)
             d = np.load(path, allow_pickle=False)
@@ -214,7 +216,24 @@ class MultiAgentLibrary:
     def max_capacity(self):
         return len(self.slots)
 
-    def scenario(self, rng, num_agents):
+    def traffic(self, num_agents, density, seed):
+        """PGTrafficManager.reset in a multi-agent env (manager/traffic_manager.py:54-72, 211-277; trigger mode): the vehicles of
+        every block after the first, parked until an agent enters the block's trigger road.  The manager's streams are seeded
+        with the env's seed; every agent spawned before took one seed from the engine's stream (engine/base_engine.py:123-135),
+        which decides the traffic vehicles' sampled parameters.  Rows in roster order, pinned on `cfg3_ma_roundabout_traffic`."""
+        from . import pgspawn
+        if self.big is None:
+            raise NotImplementedError("IDM traffic needs the generated map (exported assets hold lane tables only)")
+        sp = pgspawn.Spawner(self.big, int(seed), int(self.conf["lane_num"]), 3.5)
+        for _ in range(num_agents):
+            sp.engine_seed()
+        sp.traffic_trigger(float(density))
+        n = len(sp.static)
+        return (np.array(sp.static, np.float64).reshape(n, 16), np.array(sp.dyn, np.float64).reshape(n, 14),
+                np.array(sp.routes, np.int32).reshape(n, sc.ROUTE_MAX), np.array(sp.ints, np.int32).reshape(n, 6),
+                np.array(sp.idm, np.float32).reshape(n, 2))
+
+    def scenario(self, rng, num_agents, traffic_density=0.0, traffic_seed=0):
         c = self.conf
         assert 0 < num_agents <= self.max_capacity, \
             "Too many agents! We only accept {} agents, but you have {} agents!".format(self.max_capacity, num_agents)
@@ -251,15 +270,21 @@ class MultiAgentLibrary:
             veh_int[k] = [1, -1, lane, 0, 1 if n_ck > 2 else 0, 1]
         static = np.tile(self.veh_static, (num_agents, 1))
         idm = np.tile(np.array([[0.0, 30.0]], np.float32), (num_agents, 1))
-        return sc.Scenario(0, static, veh_dyn, routes, veh_int, idm, self.objects, 0, parking if n_in else None)
+        if abs(traffic_density) >= 1e-2:   # traffic_manager.py:62
+            t_static, t_dyn, t_routes, t_int, t_idm = self.traffic(num_agents, traffic_density, traffic_seed)
+            static, veh_dyn = np.concatenate([static, t_static]), np.concatenate([veh_dyn, t_dyn])
+            routes, veh_int, idm = np.concatenate([routes, t_routes]), np.concatenate([veh_int, t_int]), np.concatenate([idm, t_idm])
+            parking = np.concatenate([parking, np.full(len(t_static), -1, np.int32)])
+        return sc.Scenario(0, static, veh_dyn, routes, veh_int, idm, self.objects, int(traffic_seed), parking if n_in else None)
 
-    def build_world(self, n_envs, num_agents, seed=0, **cfg_kw):
+    def build_world(self, n_envs, num_agents, seed=0, traffic_density=0.0, traffic_seed=0, **cfg_kw):
         """(arrays, cfg) for n_envs independent multi-agent envs: num_agents + 1 seats each (the spare seat keeps a
-        finished agent's last transition and a newborn's first observation on different rows)."""
+        finished agent's last transition and a newborn's first observation on different rows), then the env's IDM traffic
+        (traffic_density > 0; env e draws it with the seed traffic_seed + e)."""
         rng = np.random.default_rng(seed)
-        scen = [self.scenario(rng, num_agents) for _ in range(n_envs)]
+        scen = [self.scenario(rng, num_agents, traffic_density, traffic_seed + e) for e in range(n_envs)]
         NA = num_agents + 1
-        S = ((NA + 3) // 4) * 4
+        S = ((NA + max(len(s.veh_static) for s in scen) - num_agents + 3) // 4) * 4
         tape = make_tape(n_envs, seed=seed + 1)
         O = len(self.objects)
         arrays = sc.pack([self.geo], scen, S, NA, O, ma_tables={0: self.tables}, ma_tables_tape=tape)

@@ -346,6 +346,9 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
                 else:
                     f, i = rx.record_vehicle(v, roster, env)
                     fs.append(f); is_.append(i)
+            for v in roster.traffic:   # IDM traffic of a multi-agent env (traffic_density > 0): rows after the seats, roster order
+                f, i = rx.record_vehicle(v, roster, env)
+                fs.append(f); is_.append(i)
             return np.stack(fs), np.stack(is_)
 
         f0, i0 = world()
@@ -438,6 +441,8 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         conf["n_lane_lasers"] = int(env.config["vehicle_config"]["lane_line_detector"]["num_lasers"])
         conf["lane_dist"] = float(env.config["vehicle_config"]["lane_line_detector"]["distance"])
         conf["ignore_road_sign"] = int("cross_yellow_line_done" in env.config)
+        if roster.traffic:
+            conf["n_traffic"] = len(roster.traffic)
         if parking:   # marl_parking_lot.py:252-256: yellow solid line, off the lanes or sidewalk = out of road (white lines may be crossed)
             conf.update(parking_spaces=len(spaces), parking_in_roads=len(in_roads), on_continuous_line_done=5,
                         enable_reverse=int(bool(env.config["vehicle_config"]["enable_reverse"])))
@@ -562,7 +567,7 @@ def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
 ALL_TAGS = ["cfg1_S_straight", "cfg1_S_random", "cfg1_S_discrete", "cfg2_pg3_seed3", "cfg2_pg3_seed7", "cfg2_pg3_seed11_dense",
             "cfg2_SCO_nolimit", "cfg2_pg3_seed11_others4", "cfg2_pg3_seed3_others_navi", "cfg2_pg3_seed3_detectors", "cfg4_safe_seed2", "cfg4_safe_seed5",
             "cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg2_StollC_seed0", "cfg3_ma_roundabout", "cfg3_ma_roundabout_respawn",
-            "cfg3_ma_intersection_respawn", "cfg3_ma_intersection_others_navi", "cfg3_ma_parkinglot", "cfg3_ma_bottleneck_respawn", "cfg3_ma_tollgate_respawn", "cfg5_ped_X"]
+            "cfg3_ma_intersection_respawn", "cfg3_ma_intersection_others_navi", "cfg3_ma_parkinglot", "cfg3_ma_roundabout_traffic", "cfg3_ma_bottleneck_respawn", "cfg3_ma_tollgate_respawn", "cfg5_ped_X"]
 
 
 def main():
@@ -708,6 +713,19 @@ def main():
         np.savez_compressed(path, **out)
         print("cfg3_ma_parkinglot steps", len(out["reward"]), "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()),
               "out of road", int(((out["info_flags"] & 0x400) != 0).sum()), "crashes", int(((out["info_flags"] & 0x1) != 0).sum()),
+              "->", os.path.getsize(path) // 1024, "KiB", flush=True)
+    # a multi-agent env with IDM traffic (traffic_density > 0, trigger mode: the block's vehicles start when ANY agent enters the
+    # trigger road, manager/traffic_manager.py:74-92)
+    if args.only == "cfg3_ma_roundabout_traffic":
+        from metadrive.envs.marl_envs.marl_inout_roundabout import MultiAgentRoundaboutEnv
+        lid = dict(vehicle_config=dict(lidar=dict(num_lasers=72, distance=40, num_others=0)))
+        cfgt = dict(num_agents=8, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, traffic_density=0.15, **lid)
+        out = run_episode_ma(MultiAgentRoundaboutEnv, cfgt, None, "cfg3_ma_roundabout_traffic", steps=300,
+                             noise=args.ma_noise, seed=21, obs_stride=2)
+        path = os.path.join(args.out, "cfg3_ma_roundabout_traffic.npz")
+        np.savez_compressed(path, **out)
+        print("cfg3_ma_roundabout_traffic steps", len(out["reward"]), "traffic", out["veh_f"].shape[1] - int(out["ma_alive_seats"][0]) - 1,
+              "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()), "crashes", int(((out["info_flags"] & 0x1) != 0).sum()),
               "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     # MultiAgentBottleneckEnv (envs/marl_envs/marl_bottleneck.py): Merge / Split blocks, agents born at both ends without a
     # destination draw, 4-ray side / lane-line detectors in the observation, reward without the positive_road sign

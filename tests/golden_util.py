@@ -45,11 +45,13 @@ def golden_world_ma(g, replicas=1, **cfg_kw):
                      np.asarray(g["map_road_i"], np.int32), json.loads(str(g["map_meta"])), int(g["lane_num"]))
     geo = sc.build_map_geometry(mt)
     n = int(g["ma_alive_seats"][0])
-    scen = sc.Scenario(0, g["init_veh_static"][:n], g["init_veh_dyn"][:n], g["init_routes"][:n], g["init_veh_int"][:n],
-                       g["init_idm"][:n], g["init_objects"], int(g["seed"]),
+    n_tr = int(json.loads(str(g["config"])).get("n_traffic", 0))   # IDM traffic of the env: roster rows after the agents
+    m = n + n_tr
+    scen = sc.Scenario(0, g["init_veh_static"][:m], g["init_veh_dyn"][:m], g["init_routes"][:m], g["init_veh_int"][:m],
+                       g["init_idm"][:m], g["init_objects"], int(g["seed"]),
                        g["ma_parking_taken"][:n] if "ma_parking_taken" in g else None)
     NA = n + 1
-    S = ((NA + 3) // 4) * 4
+    S = ((NA + n_tr + 3) // 4) * 4
     tables = ma.build_ma_tables(geo, g["ma_spawn_roads"], g["ma_dest_nodes"])
     tape = np.tile(ma_tape_from_trace(g), (replicas, 1))
     O = len(g["init_objects"])   # static bodies of the map itself (toll booths)

@@ -620,3 +620,26 @@ def test_ma_parking_lot_env_surface():
         assert INFO_KEYS <= set(next(iter(i.values())))
     finally:
         env.close()
+
+
+def test_ma_env_with_idm_traffic():
+    """A multi-agent env with traffic_density > 0 (trigger mode): the IDM vehicles of the roundabout block wait until an agent drives
+    onto the block's trigger road, then drive; respawn / hybrid traffic modes are refused."""
+    from metadrive_ped_b200 import MultiAgentRoundaboutEnv
+    env = MultiAgentRoundaboutEnv({"num_agents": 8, "traffic_density": 0.15, "delay_done": 5})
+    try:
+        obs, info = env.reset(seed=0)
+        assert len(obs) == 8 and env.observation_space.contains(obs)
+        vi = env._sim.get_state("veh_i")
+        traffic = vi[:, 0] == 2
+        assert traffic.sum() == 9 and not vi[traffic, 2].any(), "the reference's nine vehicles for seed 0, parked"
+        for step in range(200):
+            o, r, tm, tc, i = _ma_act(env, {k: [0.0, 0.6] for k in env.agents.keys()})
+            if tm["__all__"]:
+                break
+        vi = env._sim.get_state("veh_i")
+        assert vi[traffic, 2].any(), "an agent on the trigger road started the block's traffic"
+    finally:
+        env.close()
+    with pytest.raises(NotImplementedError):
+        MultiAgentRoundaboutEnv({"num_agents": 8, "traffic_density": 0.15, "traffic_mode": "respawn"})

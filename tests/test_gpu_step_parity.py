@@ -32,7 +32,7 @@ MULTI = [t for t in list_golden() if t.startswith("cfg3")]
 def test_multi_agent_step_matches_oracle_and_golden(tag, oracle_lib):
     """BASELINE config 3 (MultiAgentRoundaboutEnv): the CUDA step incl. wrecks, arrivals and on-device respawn against
     the oracle (integer state, seat flags, routes bit-exact) and against the reference trace (tests/test_oracle_golden)."""
-    from tests.test_oracle_golden import check_ma_step, grazes
+    from tests.test_oracle_golden import check_ma_step, grazes, ma_timer_redraws
     g, cfg, sim, orc, torch = _make(tag, replicas=2)
     NA = cfg.agents_per_env
     obs_g = sim.reset().cpu().numpy()
@@ -64,6 +64,12 @@ def test_multi_agent_step_matches_oracle_and_golden(tag, oracle_lib):
         check_ma_step(g, t, (vs_g, sim.get_state("veh_i")),
                       (og, sim.reward.cpu().numpy(), sim.cost.cpu().numpy(), sim.terminated.cpu().numpy(),
                        sim.truncated.cpu().numpy(), fl), tag)
+        redrawn = ma_timer_redraws(g, t)
+        if redrawn:   # IDM traffic of the env: the reference's overtake-timer redraws go into both simulations
+            np.testing.assert_array_equal(sim.get_state("veh_idm"), orc.a["veh_idm"])
+            for k, v in redrawn:
+                orc.a["veh_idm"].reshape(cfg.n_envs, cfg.slots_per_env, -1)[:, k, 0] = v
+            sim.set_state("veh_idm", orc.a["veh_idm"])
         if not np.array_equal(before, vs_g):
             # check_ma_step re-synchronised a wreck to the trace (the head-on toll-booth hit, documented there): the same rows go
             # into every replica of both simulations, which stay bit-identical to each other

@@ -1,0 +1,49 @@
+"""Multi-agent envs with IDM traffic (traffic_density > 0, trigger mode) on the host: the traffic roster the library generates
+against the reference trace `cfg3_ma_roundabout_traffic`, and the trigger rule on the CPU oracle."""
+import json
+
+import numpy as np
+
+from tests.golden_util import load_golden
+
+
+def test_generated_traffic_roster_equals_the_reference_trace():
+    """PGTrafficManager.reset behind 8 agents on the roundabout map, seed 0, density 0.15: classes, sampled engine / brake forces
+    (the engine's seed stream after 8 agent spawns), poses, routes, trigger blocks and overtake timers of all 9 vehicles."""
+    from metadrive_ped_b200.ma import MultiAgentLibrary
+    lib, g = MultiAgentLibrary("ma_roundabout.npz"), load_golden("cfg3_ma_roundabout_traffic")
+    n = int(g["ma_alive_seats"][0])
+    np.testing.assert_array_equal(lib.table.lane_f, g["map_lane_f"])
+    ref_blocks = json.loads(str(g["map_meta"]))["blocks"]
+    assert [b["trigger_road"] for b in lib.table.meta["blocks"]] == [b["trigger_road"] for b in ref_blocks]
+    static, dyn, routes, ints, idm = lib.traffic(n, 0.15, 0)
+    assert len(static) == len(g["init_veh_static"]) - n == 9
+    np.testing.assert_allclose(static, g["init_veh_static"][n:], rtol=1e-7)
+    np.testing.assert_allclose(dyn, g["init_veh_dyn"][n:], rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(routes, g["init_routes"][n:])
+    np.testing.assert_array_equal(ints, g["init_veh_int"][n:])
+    np.testing.assert_array_equal(idm, g["init_idm"][n:])
+
+
+def test_traffic_starts_when_an_agent_enters_the_trigger_road(oracle_lib):
+    from metadrive_ped_b200.envs import MultiAgentRoundaboutEnv, _apply_vehicle_config, _ma_cfg_kw
+    from metadrive_ped_b200.ma import MultiAgentLibrary
+    from oracle.oracle import OracleSim
+    c = MultiAgentRoundaboutEnv.default_config()
+    c["traffic_density"] = 0.15
+    arrays, cfg = MultiAgentLibrary("ma_roundabout.npz").build_world(3, 8, seed=4, traffic_density=0.15, traffic_seed=0, **_ma_cfg_kw(c))
+    _apply_vehicle_config(arrays, c)
+    E, S, NA = cfg.n_envs, cfg.slots_per_env, cfg.agents_per_env
+    assert NA == 9 and S >= NA + 9 and cfg.traffic_mode == 0
+    sim = OracleSim(arrays, cfg)
+    sim.reset_observe()
+    vi = sim.a["veh_i"].reshape(E, S, -1)
+    traffic = vi[:, :, 0] == 2
+    assert traffic[:, NA:].sum(1).min() >= 5 and not vi[traffic][:, 2].any(), "traffic waits (alive, not active) after reset"
+    started = np.zeros(E, bool)
+    for t in range(250):
+        a = np.tile(np.array([[0.0, 0.6]], np.float32), (E * NA, 1))
+        sim.step(a)
+        vi = sim.a["veh_i"].reshape(E, S, -1)
+        started |= (vi[:, :, 2][traffic.reshape(E, S)].reshape(E, -1) != 0).any(1)
+    assert started.all(), "every env's traffic was triggered by an agent driving onto the trigger road"

@@ -65,15 +65,31 @@ def _n_lasers(g):
     return _NL[key]
 
 
+def ma_timer_redraws(g, t):
+    """Traffic rows (slot, value) whose IDM overtake timer the reference redrew during step t (a completed lateral lane change,
+    idm_policy.py:285-288, from the policy's own RandomState; this build draws from a counter hash - documented): the replays take
+    the trace's value (veh_f column 32 = overtake_timer)."""
+    n_seats = int(g["ma_alive_seats"][0]) + 1
+    a, b = g["veh_f"][t], g["veh_f"][t + 1]
+    return [(k, float(b[k, 32])) for k in range(n_seats, b.shape[0])
+            if g["veh_i"][t + 1][k, 0] == 1 and g["veh_i"][t][k, 0] == 1 and b[k, 32] < a[k, 32]]
+
+
 def check_ma_step(g, t, sim_state, out, tag, pose_tol=1e-2, obs_tol=2e-4):
     """One multi-agent step of an implementation (`sim_state` = veh_s, veh_i; `out` = obs, reward, cost, term, trunc,
     info_flags) against the reference trace: seat bookkeeping exact, poses / rewards / observations within tolerance."""
     vs, vi = sim_state
     obs, rew, cost, term, trunc, fl = out
-    n_seats = g["veh_f"].shape[1]
+    n_seats = int(g["ma_alive_seats"][0]) + 1
     ref_f, ref_i = g["veh_f"][t + 1], g["veh_i"][t + 1]
-    np.testing.assert_array_equal(vi[:n_seats, 1], ref_i[:, 0], err_msg="alive @%d" % t)
-    np.testing.assert_array_equal(vi[:n_seats, 2], ref_i[:, 1], err_msg="active @%d" % t)
+    n_tr = ref_f.shape[0] - n_seats   # IDM traffic rows follow the seats (slot = seats + j)
+    np.testing.assert_array_equal(vi[:n_seats + n_tr, 1], ref_i[:, 0], err_msg="alive @%d" % t)
+    np.testing.assert_array_equal(vi[:n_seats + n_tr, 2], ref_i[:, 1], err_msg="active @%d" % t)
+    for k in range(n_seats, n_seats + n_tr):
+        if ref_i[k, 0] == 1:
+            assert np.abs(vs[k, 0:3] - ref_f[k, 0:3]).max() < pose_tol, ("traffic", tag, t, k)
+            if ref_i[k, 1]:
+                assert vi[k, 4] == ref_i[k, 2], ("traffic lane", tag, t, k)
     valid = g["valid"][t]
     np.testing.assert_array_equal((fl[:n_seats] & 0x2000) != 0, valid, err_msg="valid seats @%d" % t)
     np.testing.assert_array_equal((fl[:n_seats] & 0x4000) != 0, g["newborn"][t], err_msg="newborn seats @%d" % t)
@@ -150,7 +166,6 @@ def test_oracle_replays_multi_agent_trace(tag, oracle_lib):
     g = load_golden(tag)
     arrays, cfg, _ = golden_world(g)
     sim = OracleSim(arrays, cfg)
-    n_seats = g["veh_f"].shape[1]
     obs0 = sim.reset_observe().copy()
     n0 = int(g["ma_alive_seats"][0])
     SD, ray_cols, _ = _state_layout(g, obs0.shape[1])
@@ -161,6 +176,8 @@ def test_oracle_replays_multi_agent_trace(tag, oracle_lib):
     for t in range(T):
         obs, r, te, tr = sim.step(g["actions"][t].astype(np.float32))
         check_ma_step(g, t, (sim.a["veh_s"], sim.a["veh_i"]), (obs, r, sim.cost, te, tr, sim.info_flags), tag)
+        for k, v in ma_timer_redraws(g, t):
+            sim.a["veh_idm"][k, 0] = v
         if g["respawn_draws"][t, 0] >= 0:  # the respawned agent got the reference's route
             k = int(np.nonzero(g["newborn"][t])[0][0])
             np.testing.assert_array_equal(sim.a["veh_route"][k], g["respawn_routes"][t])
