@@ -24,6 +24,16 @@ def _world(workload, n_envs=None):
         from metadrive_ped_b200.ma import MultiAgentLibrary
         c = MultiAgentTollgateEnv.default_config()
         return MultiAgentLibrary(MultiAgentTollgateEnv.ASSET).build_world(n_envs or 48, c["num_agents"], seed=3, **_ma_cfg_kw(c))
+    if workload == "matr":
+        # a multi-agent env with IDM traffic: 12 agents on the roundabout, trigger-mode traffic of density 0.15 (another draw per env)
+        from metadrive_ped_b200.envs import MultiAgentRoundaboutEnv, _apply_vehicle_config, _ma_cfg_kw
+        from metadrive_ped_b200.ma import MultiAgentLibrary
+        c = MultiAgentRoundaboutEnv.default_config()
+        c["traffic_density"] = 0.15
+        arrays, cfg = MultiAgentLibrary(MultiAgentRoundaboutEnv.ASSET).build_world(n_envs or 48, 12, seed=7, traffic_density=0.15,
+                                                                                  traffic_seed=0, **_ma_cfg_kw(c))
+        _apply_vehicle_config(arrays, c)
+        return arrays, cfg
     if workload == "park":
         # MultiAgentParkingLotEnv at its default 10 agents (envs/marl_envs/marl_parking_lot.py:22-43), 64 envs: pulling out of the
         # spaces, reversing, ParkingLotSpawnManager's respawn rules under random driving
@@ -68,13 +78,13 @@ def _actions(rng, cfg, multi):
     return a
 
 
-@pytest.mark.parametrize("workload,steps", [("cfg2", 60), ("cfg4", 40), ("cfg5", 40), ("cfg3", 25), ("toll", 150), ("park", 400)])
+@pytest.mark.parametrize("workload,steps", [("cfg2", 60), ("cfg4", 40), ("cfg5", 40), ("cfg3", 25), ("toll", 150), ("park", 400), ("matr", 200)])
 def test_full_size_step_matches_oracle(workload, steps, oracle_lib):
     import torch
     from metadrive_ped_b200.sim import BatchedSim
     from oracle.oracle import OracleSim, set_threads
     set_threads()
-    multi = workload in ("cfg3", "toll", "park")
+    multi = workload in ("cfg3", "toll", "park", "matr")
     arrays, cfg = _world(workload)
     E, S, NA, O = cfg.n_envs, cfg.slots_per_env, cfg.agents_per_env, cfg.objs_per_env
     sim, orc = BatchedSim(arrays, cfg), OracleSim(arrays, cfg)
@@ -135,6 +145,9 @@ def test_full_size_step_matches_oracle(workload, steps, oracle_lib):
     assert n_bad_rays == 0 and n_float_diff == 0, (n_bad_rays, n_rays, n_float_diff, n_float)
     if not multi:
         assert n_done > 0, "the run must exercise the fused auto-reset"
+    if workload == "matr":
+        tr = orc.a["veh_i"].reshape(E, S, -1)[:, NA:]
+        assert ((tr[:, :, 0] == 2) & (tr[:, :, 2] != 0)).any(1).mean() > 0.5, "the traffic must have been triggered in most envs"
     if workload == "park":
         assert n_newborn >= E, "the run must exercise the parking lot's respawn rules (%d respawns)" % n_newborn
     print("%s: %d envs x %d steps, %d resets, %d floats (state + observations) compared, all bit-identical"
