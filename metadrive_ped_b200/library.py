@@ -158,11 +158,13 @@ class GeneratedLibrary(ScenarioLibrary):
                 raise KeyError(k)
             c[k] = v
         if isinstance(c["map"], str) and any(b in c["map"] for b in "BP"):
-            # the generator builds these blocks (pgmap.Bidirection / ParkingLot, bit-identical lane tables), but a Bidirection
-            # block's two roads / a parking space's two road names share one lane - no reference trace pins the step path on such
-            # scenes.  TollGate blocks ('$') are stepped: their booths are static boxes of the device world (object kind 4).
-            raise NotImplementedError("maps with Bidirection ('B') or ParkingLot ('P') blocks can be generated "
-                                      "(pgmap.generate) but not stepped: their shared lanes are not in the device world")
+            # the generator builds these blocks (pgmap.Bidirection / ParkingLot, bit-identical lane tables) and the step path localises
+            # on their shared lanes (the parking-lot env does), but the reference itself cannot drive them inside a BIG map: "SPC" fails
+            # an assertion while the map is built, and the Bidirection block of "SBC" puts ONE lane for both directions on the yellow
+            # centre line behind three lanes a side, without a Merge in front - no trace to pin.  TollGate blocks ('$') are stepped:
+            # their booths are static boxes of the device world (object kind 4).
+            raise NotImplementedError("maps with Bidirection ('B') or ParkingLot ('P') blocks can be generated (pgmap.generate) "
+                                      "but not stepped: the reference cannot drive them inside a procedurally generated map")
         self.gen = c
         self.path = "<generated>"
         self.seeds = np.arange(start_seed, start_seed + num_scenarios, dtype=np.int32)
