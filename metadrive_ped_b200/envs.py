@@ -643,8 +643,12 @@ class MultiAgentMetaDrive:
         d["vehicle_config"] = _merge(STEP_DEFAULTS["vehicle_config"], MA_DEFAULTS["vehicle_config"])
         return _merge_new(d, cls.ENV_DEFAULTS)
 
-    def __init__(self, config=None):
+    @classmethod
+    def _make_library(cls, config):
         from .ma import MultiAgentLibrary
+        return MultiAgentLibrary(cls.ASSET)
+
+    def __init__(self, config=None):
         self.config = _merge(self.default_config(), config)
         for k in UNSUPPORTED_TRUE:
             if self.config[k]:
@@ -655,7 +659,7 @@ class MultiAgentMetaDrive:
             raise NotImplementedError("record / replay covers the single-agent envs")
         lid = self.config["vehicle_config"]["lidar"]
         assert 0.0 <= lid["dropout_prob"] <= 1.0  # obs/state_obs.py:240
-        self._lib = MultiAgentLibrary(self.ASSET)
+        self._lib = self._make_library(self.config)
         self.num_agents = self.config["num_agents"]
         if self.num_agents == -1:
             self.num_agents = self._lib.max_capacity
@@ -793,10 +797,15 @@ class MultiAgentParkingLotEnv(MultiAgentMetaDrive):
     ASSET = "ma_parkinglot.npz"
     ENV_DEFAULTS = dict(num_agents=10, parking_space_num=8, vehicle_config=dict(enable_reverse=True))
 
-    def __init__(self, config=None):
-        super().__init__(config)
-        if self.config["parking_space_num"] != 8:
-            raise NotImplementedError("the parking lot is generated with the env's default of 8 spaces")
+    @classmethod
+    def _make_library(cls, config):
+        from .ma import MultiAgentLibrary
+        n = int(config["parking_space_num"])
+        assert n % 2 == 0, "number of parking spaces must be multiples of 2"      # marl_parking_lot.py:213-214
+        assert n >= 4, "minimal number of parking space is 4"
+        if n > 30:
+            raise NotImplementedError("at most 30 parking spaces (who is heading for which space is a 32-bit set on the device)")
+        return MultiAgentLibrary(cls.ASSET, parking_space_num=n)
 
 
 class BatchedMultiAgentEnv:
@@ -804,10 +813,9 @@ class BatchedMultiAgentEnv:
     reward / terminated / truncated [E*seats], info flags (FL_VALID marks the seats that produced a transition this step,
     FL_NEWBORN the seats respawned this step).  seats = num_agents + 1.  Finished envs reset in place on device."""
     def __init__(self, num_envs, config=None, env_cls=MultiAgentRoundaboutEnv, seed=0):
-        from .ma import MultiAgentLibrary
         from .sim import BatchedSim
         c = _merge(env_cls.default_config(), config)
-        lib = MultiAgentLibrary(env_cls.ASSET)
+        lib = env_cls._make_library(c)
         n = c["num_agents"] if c["num_agents"] != -1 else lib.max_capacity
         if abs(c["traffic_density"]) >= 1e-2 and c["traffic_mode"] != "trigger":
             raise NotImplementedError("multi-agent envs with respawn / hybrid IDM traffic are not covered (trigger mode is)")

@@ -131,7 +131,7 @@ ASSET_KIND = {"ma_parkinglot.npz": "parkinglot", "ma_roundabout.npz": "roundabou
               "ma_tollgate.npz": "tollgate", "ma_bidirection.npz": "bidirection"}
 
 
-def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None):
+def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None, parking_space_num=8):
     """What an exported multi-agent asset holds, generated: lane tables, spawn roads (the first block's second road and the
     three roads ENTERING the block, i.e. the negatives of its exits), destination nodes, the static_default vehicle row
     (component/pg_space.py:227-234, vehicle_type.py:35-36) and SpawnManager's slot constants (spawn_manager.py:25-35)."""
@@ -139,7 +139,7 @@ def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None):
     m = MA_MAPS[kind]
     lane_num = m["lane_num"] if lane_num is None else lane_num
     exit_length = m["exit_length"] if exit_length is None else exit_length
-    lane_f, lane_i, road_i, meta, big = pgmap.build_fixed(kind, lane_num, lane_width, exit_length)
+    lane_f, lane_i, road_i, meta, big = pgmap.build_fixed(kind, lane_num, lane_width, exit_length, parking_space_num)
     node = {n: k for k, n in enumerate(meta["nodes"])}
     roads = [(">>", ">>>")]
     for bi, part, a, b in m["spawn_nodes"]:
@@ -180,10 +180,10 @@ class MultiAgentLibrary:
     (spawn road x lane x longitudinal slot) drawn without replacement, a random offset inside the slot
     (`_randomize_position_in_slot`, :211-217) and a random destination per agent (marl_inout_roundabout.py:138-143).
     The reference draws these from an unseeded generator; here the caller passes the generator."""
-    def __init__(self, name, from_asset=False):
+    def __init__(self, name, from_asset=False, parking_space_num=8):
         self.big = None   # the generated map's blocks and lanes (IDM traffic is populated over them); an exported asset has none
         if not from_asset and ASSET_KIND.get(name, name) in MA_MAPS:
-            d = generated_source(ASSET_KIND.get(name, name))
+            d = generated_source(ASSET_KIND.get(name, name), parking_space_num=parking_space_num)
             self.big = d["big"]
         else:
             path = name if os.path.exists(name) else os.path.join(ASSET_DIR, name)

@@ -1370,7 +1370,7 @@ def to_tables(big):
     return lane_f, lane_i, road_i, meta
 
 
-def build_fixed(kind, lane_num=2, lane_width=3.5, exit_length=60):
+def build_fixed(kind, lane_num=2, lane_width=3.5, exit_length=60, parking_space_num=8):
     """The fixed maps of the multi-agent envs (envs/marl_envs/marl_inout_roundabout.py:27-60, marl_intersection.py:27-71):
     a first block and ONE block built from a given configuration with block seed 1."""
     big = BIG.__new__(BIG)
@@ -1389,14 +1389,15 @@ def build_fixed(kind, lane_num=2, lane_width=3.5, exit_length=60):
         blk.u_turn = lane_num > 1
         blk.construct()
     elif kind in ("bottleneck", "bidirection", "tollgate", "parkinglot"):
-        return _build_chain(big, kind, lane_num, exit_length)
+        return _build_chain(big, kind, lane_num, exit_length, parking_space_num=parking_space_num)
     else:
         raise NotImplementedError("multi-agent map %r is not restated" % kind)
     big.blocks.append(blk)
     return to_tables(big) + (big, )
 
 
-def _build_chain(big, kind, lane_num, exit_length, neck_lane_num=1, neck_length=20, toll_lane_num=8, toll_length=10):
+def _build_chain(big, kind, lane_num, exit_length, neck_lane_num=1, neck_length=20, toll_lane_num=8, toll_length=10,
+                 parking_space_num=8):
     """MABottleneckMap / MABidirectionMap / MATollGateMap (envs/marl_envs/marl_bottleneck.py:27-66,
     marl_bidirection.py:27-77, marl_tollgate.py:103-150): fixed block chains, every block with seed 1"""
     def add(cls, extra):
@@ -1411,8 +1412,8 @@ def _build_chain(big, kind, lane_num, exit_length, neck_lane_num=1, neck_length=
         add(Merge, dict(lane_num=d, length=3))
         add(Bidirection, None)
         add(Split, dict(length=exit_length, lane_num=d))
-    elif kind == "parkinglot":    # MAParkingLotMap (marl_parking_lot.py:144-184): -> ParkingLot (4 spaces a side) -> T intersection
-        add(ParkingLot, dict(one_side_vehicle_number=4))
+    elif kind == "parkinglot":    # MAParkingLotMap (marl_parking_lot.py:144-184): -> ParkingLot (parking_space_num / 2 spaces a side) -> T
+        add(ParkingLot, dict(one_side_vehicle_number=int(parking_space_num / 2)))
         t = TInterSection(len(big.blocks), big.blocks[-1].get_socket(0), big.world, 1)
         t.EXIT_LEN = 10
         t.construct(dict(t_type=1, change_lane_num=0))

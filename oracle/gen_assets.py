@@ -38,7 +38,8 @@ def export_multi_agent(args):
         from metadrive.envs.marl_envs.marl_tollgate import MultiAgentTollgateEnv as cls
     else:
         from metadrive.envs.marl_envs.marl_parking_lot import MultiAgentParkingLotEnv as cls
-    env = cls(dict(log_level=50))
+    env = cls(dict(log_level=50, **(dict(parking_space_num=args.parking_spaces, num_agents=min(10, 3 + args.parking_spaces))
+                                  if args.parking_spaces else {})))
     try:
         env.reset()
     except KeyError as e:
@@ -78,6 +79,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--env", default="metadrive", choices=["metadrive", "safe", "ma_roundabout", "ma_intersection", "ma_bottleneck", "ma_bidirection", "ma_tollgate",
                              "ma_parkinglot"])
+    ap.add_argument("--parking-spaces", type=int, default=0, help="ma_parkinglot: parking_space_num (default: the env's 8)")
     ap.add_argument("--n", type=int, default=1000)
     ap.add_argument("--start", type=int, default=0)
     ap.add_argument("--density", type=float, default=None)

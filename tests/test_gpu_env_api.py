@@ -620,6 +620,14 @@ def test_ma_parking_lot_env_surface():
         assert INFO_KEYS <= set(next(iter(i.values())))
     finally:
         env.close()
+    env = MultiAgentParkingLotEnv({"parking_space_num": 12, "num_agents": -1, "delay_done": 5})   # a bigger lot, filled up
+    try:
+        obs, info = env.reset()
+        assert len(obs) == 15
+        for step in range(60):
+            o, r, tm, tc, i = _ma_act(env, {k: [0.0, 0.3] for k in env.agents.keys()})
+    finally:
+        env.close()
 
 
 def test_ma_env_with_idm_traffic():

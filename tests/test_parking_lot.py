@@ -78,3 +78,39 @@ def test_respawn_rules_of_the_spawn_manager(oracle_lib):
                     assert vc[e, s, 14] == 0 and dest in exits
                     n_out += 1
     assert n_in >= 3 and n_out >= 3, (n_in, n_out)
+
+
+def test_other_numbers_of_parking_spaces(oracle_lib):
+    """parking_space_num = 4 and 12 (marl_parking_lot.py:211-219): capacity 3 + N, the respawn rules hold on the oracle; odd or
+    fewer than 4 spaces fail the reference's assertions."""
+    import pytest
+    from metadrive_ped_b200.envs import MultiAgentParkingLotEnv, _apply_vehicle_config, _ma_cfg_kw
+    from oracle.oracle import OracleSim
+    for n_spaces, n_agents in ((4, 6), (12, 12)):
+        c = MultiAgentParkingLotEnv.default_config()
+        c.update(parking_space_num=n_spaces, num_agents=n_agents)
+        lib = MultiAgentParkingLotEnv._make_library(c)
+        assert lib.max_capacity == 3 + n_spaces
+        arrays, cfg = lib.build_world(3, n_agents, seed=1, **_ma_cfg_kw(c))
+        _apply_vehicle_config(arrays, c)
+        assert cfg.parking_spaces == n_spaces and cfg.ma_dests == max(n_spaces, 3)
+        sim = OracleSim(arrays, cfg)
+        sim.reset_observe()
+        E, S, NA = cfg.n_envs, cfg.slots_per_env, cfg.agents_per_env
+        rng = np.random.RandomState(5)
+        bias = rng.uniform(-0.6, 0.6, E * NA)
+        born = 0
+        for t in range(300):
+            a = np.zeros((E * NA, 2), np.float32)
+            a[:, 0] = bias + 0.3 * rng.uniform(-1, 1, E * NA)
+            a[:, 1] = 0.35 * rng.uniform(0.3, 1.0, E * NA)
+            sim.step(a)
+            vi, vc = sim.a["veh_i"].reshape(E, S, -1), sim.a["veh_c"].reshape(E, S, -1)
+            for e in range(E):
+                goal = [int(vc[e, s, 14]) for s in range(NA) if vi[e, s, 2] and vc[e, s, 14] > 0]
+                assert len(goal) == len(set(goal)) and all(1 <= x <= n_spaces for x in goal)
+            born += int(((sim.info_flags & 0x4000) != 0).sum())
+        assert born >= 3
+    for bad in (5, 2):
+        with pytest.raises(AssertionError):
+            MultiAgentParkingLotEnv._make_library(dict(parking_space_num=bad))

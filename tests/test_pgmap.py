@@ -80,19 +80,25 @@ def test_generator_reproduces_maps_with_bottleneck_and_tollgate_blocks(name, spe
             GeneratedLibrary(0, 1, map="SBC")
 
 
-def test_generator_reproduces_the_parking_lot_map():
-    """MAParkingLotMap (envs/marl_envs/marl_parking_lot.py:144-184): first block (one lane, 20 m) -> ParkingLot (4 spaces a
-    side, pgblock/parking_lot.py) -> T intersection; 106 lanes, bit for bit against the reference's export.  (The map only:
-    the env's parking-space spawn manager is not restated.)"""
+@pytest.mark.parametrize("spaces,asset", [(8, "ma_parkinglot.npz"), (4, "ma_parkinglot_4.npz"), (12, "ma_parkinglot_12.npz")])
+def test_generator_reproduces_the_parking_lot_map(spaces, asset):
+    """MAParkingLotMap (envs/marl_envs/marl_parking_lot.py:144-184): first block (one lane, 20 m) -> ParkingLot (parking_space_num
+    / 2 spaces a side, pgblock/parking_lot.py) -> T intersection; 106 lanes with the env's 8 spaces; lane tables, node names and the
+    env's spawn roads (3 ways in + the spaces) bit for bit against the reference's exports (oracle/gen_assets.py --env ma_parkinglot
+    [--parking-spaces N])."""
     import json
-    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "libs", "ma_parkinglot.npz"))
+    from metadrive_ped_b200.ma import MultiAgentLibrary
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "libs", asset))
     conf, meta = json.loads(str(d["config"])), json.loads(str(d["meta"]))
-    lane_f, lane_i, road_i, g_meta, big = pgmap.build_fixed("parkinglot", conf["lane_num"], 3.5, conf["exit_length"])
+    lane_f, lane_i, road_i, g_meta, big = pgmap.build_fixed("parkinglot", conf["lane_num"], 3.5, conf["exit_length"], spaces)
     assert [b.ID for b in big.blocks] == ["I", "P", "T"] and g_meta["nodes"] == meta["nodes"]
     np.testing.assert_array_equal(lane_f, d["lane_f"])
     np.testing.assert_array_equal(lane_i, d["lane_i"])
     np.testing.assert_array_equal(road_i, d["road_i"])
-    assert len(big.blocks[1].dest_roads) == 8 and len(big.blocks[1].parking_spawn_roads) == 8
+    assert len(big.blocks[1].dest_roads) == spaces and len(big.blocks[1].parking_spawn_roads) == spaces
+    lib = MultiAgentLibrary("parkinglot", parking_space_num=spaces)
+    np.testing.assert_array_equal(lib.spawn_roads, d["spawn_roads"])
+    assert lib.max_capacity == 3 + spaces and lib.conf["parking_spaces"] == spaces
 
 
 def test_generated_world_equals_exported_world():
