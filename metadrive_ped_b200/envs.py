@@ -655,8 +655,6 @@ class MultiAgentMetaDrive:
                 raise NotImplementedError("config['%s'] is outside the step path this build covers" % k)
         if abs(self.config["traffic_density"]) >= 1e-2 and self.config["traffic_mode"] != "trigger":
             raise NotImplementedError("multi-agent envs with respawn / hybrid IDM traffic are not covered (trigger mode is)")
-        if self.config["record_episode"] or self.config["replay_episode"] is not None:
-            raise NotImplementedError("record / replay covers the single-agent envs")
         lid = self.config["vehicle_config"]["lidar"]
         assert 0.0 <= lid["dropout_prob"] <= 1.0  # obs/state_obs.py:240
         self._lib = self._make_library(self.config)
@@ -674,6 +672,7 @@ class MultiAgentMetaDrive:
         self._active = set(self._seat_id[:self.num_agents])
         self._sim = None
         self._episode = 0
+        self._record, self._replay_t = None, 0
         self.current_seed = self.config["start_seed"]
 
     # -- gym surface
@@ -682,10 +681,14 @@ class MultiAgentMetaDrive:
         if self._sim is not None:
             self._sim.close()
         rs = (seed if seed is not None else self.config["start_seed"]) * 1000003 + self._episode
+        traffic_seed = seed if seed is not None else self.config["start_seed"]
+        epi = self.config["replay_episode"]
+        if epi is not None:   # the logged episode is replayed whatever seed is asked for (envs/base_env.py:502-537): same spawn
+            rs, traffic_seed = int(epi["world_seed"]), int(epi["scenario_index"])   # draws, same respawn tape, same traffic
+            self._replay_t = 0
         self._episode += 1
         arrays, cfg = self._lib.build_world(1, self.num_agents, seed=rs, traffic_density=self.config["traffic_density"],
-                                            traffic_seed=seed if seed is not None else self.config["start_seed"],
-                                            **_ma_cfg_kw(self.config))
+                                            traffic_seed=traffic_seed, **_ma_cfg_kw(self.config))
         _apply_vehicle_config(arrays, self.config)
         self._sim = BatchedSim(arrays, cfg, device=self.config["device"])
         self._seat_id = ["agent%d" % k for k in range(self.num_agents)] + [None]
@@ -693,6 +696,15 @@ class MultiAgentMetaDrive:
         self._active = set(self._seat_id[:self.num_agents])
         obs = self._sim.reset_host()
         self.episode_step = 0
+        self._record = None
+        if self.config["record_episode"]:
+            # record / replay the way the single-agent envs do it (MetaDriveEnv.dump_episode): the simulation is deterministic bit for
+            # bit, so an episode is the seeds of its world + the actions per agent id + one state frame per env.step
+            import time
+            self._record = dict(scenario_index=int(traffic_seed), global_seed=int(traffic_seed), world_seed=int(rs), coordinate="MetaDrive",
+                                time=time.strftime("%Y-%m-%d_%H-%M-%S"),
+                                global_config={k: v for k, v in self.config.items() if k != "replay_episode"},
+                                frames_per_step=1, frame=[[self._frame(0)]], actions=[])
         return ({self._seat_id[k]: obs[k].copy() for k in range(self.num_agents)},
                 {self._seat_id[k]: self._info(None) for k in range(self.num_agents)})
 
@@ -708,8 +720,35 @@ class MultiAgentMetaDrive:
     def action_space(self):
         return DictSpace({k: self._act_box for k in self.agents})
 
+    def _frame(self, step):
+        """One frame of a recorded episode: every body of the world under its agent id (traffic: its slot)."""
+        vs, vi = self._sim.get_state("veh_s"), self._sim.get_state("veh_i")
+        objs = {}
+        for k in range(len(vi)):
+            if not vi[k, 1]:
+                continue
+            name = self._seat_id[k] if k <= self.num_agents and vi[k, 0] == 1 else "traffic_%d" % k
+            objs[str(name)] = dict(position=[float(v) for v in vs[k, 0:3]], quaternion=[float(v) for v in vs[k, 3:7]],
+                                   velocity=[float(v) for v in vs[k, 7:9]], type="agent" if vi[k, 0] == 1 else "traffic",
+                                   active=bool(vi[k, 2]))
+        return dict(episode_step=int(step), step_info=objs, agents=sorted(self._active))
+
+    def dump_episode(self):
+        assert getattr(self, "_record", None) is not None, "record_episode is off or reset() was not called"
+        import copy
+        return copy.deepcopy(self._record)
+
+    @property
+    def engine(self):
+        return _EngineShim(self)
+
     def step(self, actions):
         assert self._sim is not None, "call reset() first"
+        epi = self.config["replay_episode"]
+        replaying = epi is not None and not self.config["only_reset_when_replay"]
+        if replaying:
+            assert self._replay_t < len(epi["actions"]), "the replayed episode is over (info['replay_done'])"
+            actions = epi["actions"][self._replay_t]
         NA = self.num_agents + 1
         a = np.zeros((NA, 2), np.float32)
         acting = {}
@@ -741,6 +780,14 @@ class MultiAgentMetaDrive:
                 self._active.discard(aid)
         tc["__all__"] = all(tc.values())
         tm["__all__"] = all(tm.values())
+        if self._record is not None:
+            self._record["actions"].append({aid: (actions[aid] if np.isscalar(actions[aid]) else
+                                                  [float(v) for v in np.asarray(actions[aid]).reshape(-1)]) for aid in acting.values()})
+            self._record["frame"].append([self._frame(len(self._record["actions"]))])
+        if replaying:
+            self._replay_t += 1
+            for aid in info:
+                info[aid]["replay_done"] = self._replay_t >= len(epi["actions"])   # REPLAY_DONE (replay_manager.py:121-125)
         return o, r, tm, tc, info
 
     _info = MetaDriveEnv._info

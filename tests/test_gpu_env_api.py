@@ -651,3 +651,33 @@ def test_ma_env_with_idm_traffic():
         env.close()
     with pytest.raises(NotImplementedError):
         MultiAgentRoundaboutEnv({"num_agents": 8, "traffic_density": 0.15, "traffic_mode": "respawn"})
+
+
+def test_ma_record_and_replay_episode():
+    """record_episode / replay_episode on a multi-agent env: a recorded episode (random actions, crashes, respawns under fresh agent
+    ids) is replayed - whatever the caller passes - with the same agent ids, observations, rewards and done flags step for step."""
+    from metadrive_ped_b200 import MultiAgentIntersectionEnv
+    rng = np.random.RandomState(2)
+    cfg = {"num_agents": 8, "delay_done": 5, "traffic_density": 0.1}
+    env = MultiAgentIntersectionEnv(dict(cfg, record_episode=True))
+    obs0, _ = env.reset(seed=0)
+    log = []
+    for t in range(120):
+        o, r, tm, tc, info = env.step({k: rng.uniform(-1, 1, 2) * [0.4, 1.0] for k in env.agents.keys()})
+        log.append((o, r, tm, tc))
+        if tm["__all__"]:
+            break
+    epi = env.engine.dump_episode()
+    env.close()
+    assert len(epi["actions"]) == len(log) == len(epi["frame"]) - 1
+    assert any(len(set(o) - set(obs0)) for o, _, _, _ in log), "the episode holds respawned agents"
+    rep = MultiAgentIntersectionEnv(dict(cfg, replay_episode=epi))
+    o0, _ = rep.reset(seed=3)
+    assert set(o0) == set(obs0) and all(np.array_equal(o0[k], obs0[k]) for k in obs0)
+    for t, (o, r, tm, tc) in enumerate(log):
+        o2, r2, tm2, tc2, info = rep.step({k: [0.0, 0.0] for k in rep.agents.keys()})   # ignored: the logged actions are applied
+        assert set(o2) == set(o) and r2 == r and tm2 == tm and tc2 == tc, "step %d" % t
+        for k in o:
+            np.testing.assert_array_equal(o2[k], o[k], err_msg="obs of %s at step %d" % (k, t))
+        assert all(i["replay_done"] == (t == len(log) - 1) for i in info.values())
+    rep.close()
