@@ -644,9 +644,14 @@ class MultiAgentMetaDrive:
         return _merge_new(d, cls.ENV_DEFAULTS)
 
     @classmethod
-    def _make_library(cls, config):
+    def _make_library(cls, config, **kw):
+        """The env's fixed map, generated from config["map_config"] the way the reference's MA*Map classes read it (lane_num,
+        lane_width, exit_length; bottleneck: bottle_lane_num / neck_lane_num / neck_length; tollgate: toll_lane_num / toll_length)."""
         from .ma import MultiAgentLibrary
-        return MultiAgentLibrary(cls.ASSET)
+        mc = config["map_config"]
+        chain = {k: mc[k] for k in ("neck_lane_num", "neck_length", "toll_lane_num", "toll_length") if k in mc}
+        return MultiAgentLibrary(cls.ASSET, lane_num=int(mc.get("bottle_lane_num", mc["lane_num"])), lane_width=float(mc["lane_width"]),
+                                 exit_length=float(mc["exit_length"]), **chain, **kw)
 
     def __init__(self, config=None):
         self.config = _merge(self.default_config(), config)
@@ -801,13 +806,13 @@ class MultiAgentMetaDrive:
 class MultiAgentRoundaboutEnv(MultiAgentMetaDrive):
     """envs/marl_envs/marl_inout_roundabout.py:12-24, 145-153"""
     ASSET = "ma_roundabout.npz"
-    ENV_DEFAULTS = dict(num_agents=40)
+    ENV_DEFAULTS = dict(num_agents=40, map_config=dict(exit_length=60, lane_num=2))
 
 
 class MultiAgentIntersectionEnv(MultiAgentMetaDrive):
     """envs/marl_envs/marl_intersection.py:12-25, 98-108"""
     ASSET = "ma_intersection.npz"
-    ENV_DEFAULTS = dict(num_agents=30)
+    ENV_DEFAULTS = dict(num_agents=30, map_config=dict(exit_length=60, lane_num=2))
 
 
 class MultiAgentBottleneckEnv(MultiAgentMetaDrive):
@@ -815,6 +820,7 @@ class MultiAgentBottleneckEnv(MultiAgentMetaDrive):
     are born at both ends and drive to the other end (no destination draw), 4-ray side / lane-line detectors"""
     ASSET = "ma_bottleneck.npz"
     ENV_DEFAULTS = dict(num_agents=20, cross_yellow_line_done=True,
+                        map_config=dict(exit_length=60, lane_num=4, bottle_lane_num=4, neck_lane_num=1, neck_length=20),
                         vehicle_config=dict(side_detector=dict(num_lasers=4, distance=50),
                                             lane_line_detector=dict(num_lasers=4, distance=20)))
 
@@ -827,6 +833,7 @@ class MultiAgentTollgateEnv(MultiAgentMetaDrive):
     TollGateObservation = ego state without the navigation block + lidar + [in the toll block, stayed long enough]"""
     ASSET = "ma_tollgate.npz"
     ENV_DEFAULTS = dict(num_agents=40, cross_yellow_line_done=True, speed_reward=0.0, overspeed_penalty=0.5,
+                        map_config=dict(exit_length=70, lane_num=3, toll_lane_num=8, toll_length=10),
                         vehicle_config=dict(min_pass_steps=30, side_detector=dict(num_lasers=72, distance=20),
                                             lane_line_detector=dict(num_lasers=4, distance=20),
                                             lidar=dict(num_lasers=72, distance=20)))
@@ -842,7 +849,8 @@ class MultiAgentParkingLotEnv(MultiAgentMetaDrive):
     so its newborns all land on the first road's default pose without a destination; this build respawns them where the spawn
     manager put them (DESIGN.md "Deliberate differences")."""
     ASSET = "ma_parkinglot.npz"
-    ENV_DEFAULTS = dict(num_agents=10, parking_space_num=8, vehicle_config=dict(enable_reverse=True))
+    ENV_DEFAULTS = dict(num_agents=10, parking_space_num=8, map_config=dict(exit_length=20, lane_num=1),
+                        vehicle_config=dict(enable_reverse=True))
 
     @classmethod
     def _make_library(cls, config):
@@ -852,7 +860,7 @@ class MultiAgentParkingLotEnv(MultiAgentMetaDrive):
         assert n >= 4, "minimal number of parking space is 4"
         if n > 30:
             raise NotImplementedError("at most 30 parking spaces (who is heading for which space is a 32-bit set on the device)")
-        return MultiAgentLibrary(cls.ASSET, parking_space_num=n)
+        return super()._make_library(config, parking_space_num=n)
 
 
 class BatchedMultiAgentEnv:

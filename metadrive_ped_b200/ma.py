@@ -131,7 +131,7 @@ ASSET_KIND = {"ma_parkinglot.npz": "parkinglot", "ma_roundabout.npz": "roundabou
               "ma_tollgate.npz": "tollgate", "ma_bidirection.npz": "bidirection"}
 
 
-def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None, parking_space_num=8):
+def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None, parking_space_num=8, **chain_kw):
     """What an exported multi-agent asset holds, generated: lane tables, spawn roads (the first block's second road and the
     three roads ENTERING the block, i.e. the negatives of its exits), destination nodes, the static_default vehicle row
     (component/pg_space.py:227-234, vehicle_type.py:35-36) and SpawnManager's slot constants (spawn_manager.py:25-35)."""
@@ -139,7 +139,7 @@ def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None, park
     m = MA_MAPS[kind]
     lane_num = m["lane_num"] if lane_num is None else lane_num
     exit_length = m["exit_length"] if exit_length is None else exit_length
-    lane_f, lane_i, road_i, meta, big = pgmap.build_fixed(kind, lane_num, lane_width, exit_length, parking_space_num)
+    lane_f, lane_i, road_i, meta, big = pgmap.build_fixed(kind, lane_num, lane_width, exit_length, parking_space_num, **chain_kw)
     node = {n: k for k, n in enumerate(meta["nodes"])}
     roads = [(">>", ">>>")]
     for bi, part, a, b in m["spawn_nodes"]:
@@ -148,9 +148,11 @@ def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None, park
     d = pgspawn.DIMS["static_default"]
     static = [pgspawn.VEHICLE_TYPES.index("static_default"), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], 800, 150, 40,
               0.9, 80, 0.0]
-    conf = dict(env=m["env"], num_agents=m["num_agents"], lane_num=lane_num, exit_length=float(exit_length), entrance_length=10.0,
+    conf = dict(env=m["env"], num_agents=m["num_agents"], lane_num=lane_num, lane_width=float(lane_width), exit_length=float(exit_length),
+                entrance_length=10.0,
                 respawn_longitude=RESPAWN_REGION_LONGITUDE, respawn_lateral=RESPAWN_REGION_LATERAL, max_vehicle_length=10.0,
-                max_vehicle_width=2.5, disable_u_turn=False, fixed_dest=bool(m.get("fixed_dest", False)))
+                max_vehicle_width=2.5, disable_u_turn=bool(kind == "intersection" and lane_num < 2),   # marl_intersection.py:103
+                fixed_dest=bool(m.get("fixed_dest", False)))
     # static bodies the map itself brings: the toll booths (scene.Scenario.objects rows: kind 4 = building, x, y, heading,
     # half extent across the heading, half extent along it - the barrier's column order -, height BUILDING_HEIGHT = 5, lane id)
     objects = np.array([[4.0, b[1], b[2], b[3], b[5], b[4], 5.0, b[0]] for blk in meta["blocks"]
@@ -180,10 +182,10 @@ class MultiAgentLibrary:
     (spawn road x lane x longitudinal slot) drawn without replacement, a random offset inside the slot
     (`_randomize_position_in_slot`, :211-217) and a random destination per agent (marl_inout_roundabout.py:138-143).
     The reference draws these from an unseeded generator; here the caller passes the generator."""
-    def __init__(self, name, from_asset=False, parking_space_num=8):
+    def __init__(self, name, from_asset=False, parking_space_num=8, lane_num=None, lane_width=3.5, exit_length=None, **chain_kw):
         self.big = None   # the generated map's blocks and lanes (IDM traffic is populated over them); an exported asset has none
         if not from_asset and ASSET_KIND.get(name, name) in MA_MAPS:
-            d = generated_source(ASSET_KIND.get(name, name), parking_space_num=parking_space_num)
+            d = generated_source(ASSET_KIND.get(name, name), lane_num, lane_width, exit_length, parking_space_num, **chain_kw)
             self.big = d["big"]
         else:
             path = name if os.path.exists(name) else os.path.join(ASSET_DIR, name)
@@ -224,7 +226,7 @@ class MultiAgentLibrary:
         from . import pgspawn
         if self.big is None:
             raise NotImplementedError("IDM traffic needs the generated map (exported assets hold lane tables only)")
-        sp = pgspawn.Spawner(self.big, int(seed), int(self.conf["lane_num"]), 3.5)
+        sp = pgspawn.Spawner(self.big, int(seed), int(self.conf["lane_num"]), float(self.conf.get("lane_width", 3.5)))
         for _ in range(num_agents):
             sp.engine_seed()
         sp.traffic_trigger(float(density))

@@ -1370,7 +1370,7 @@ def to_tables(big):
     return lane_f, lane_i, road_i, meta
 
 
-def build_fixed(kind, lane_num=2, lane_width=3.5, exit_length=60, parking_space_num=8):
+def build_fixed(kind, lane_num=2, lane_width=3.5, exit_length=60, parking_space_num=8, **chain_kw):
     """The fixed maps of the multi-agent envs (envs/marl_envs/marl_inout_roundabout.py:27-60, marl_intersection.py:27-71):
     a first block and ONE block built from a given configuration with block seed 1."""
     big = BIG.__new__(BIG)
@@ -1389,7 +1389,7 @@ def build_fixed(kind, lane_num=2, lane_width=3.5, exit_length=60, parking_space_
         blk.u_turn = lane_num > 1
         blk.construct()
     elif kind in ("bottleneck", "bidirection", "tollgate", "parkinglot"):
-        return _build_chain(big, kind, lane_num, exit_length, parking_space_num=parking_space_num)
+        return _build_chain(big, kind, lane_num, exit_length, parking_space_num=parking_space_num, **chain_kw)
     else:
         raise NotImplementedError("multi-agent map %r is not restated" % kind)
     big.blocks.append(blk)

@@ -38,8 +38,10 @@ def export_multi_agent(args):
         from metadrive.envs.marl_envs.marl_tollgate import MultiAgentTollgateEnv as cls
     else:
         from metadrive.envs.marl_envs.marl_parking_lot import MultiAgentParkingLotEnv as cls
-    env = cls(dict(log_level=50, **(dict(parking_space_num=args.parking_spaces, num_agents=min(10, 3 + args.parking_spaces))
-                                  if args.parking_spaces else {})))
+    extra = dict(parking_space_num=args.parking_spaces, num_agents=min(10, 3 + args.parking_spaces)) if args.parking_spaces else {}
+    if args.map_config:   # a non-default map of the env (lane_num, exit_length, neck_length, toll_lane_num ...)
+        extra.update(map_config=json.loads(args.map_config), num_agents=4)
+    env = cls(dict(log_level=50, **extra))
     try:
         env.reset()
     except KeyError as e:
@@ -52,6 +54,7 @@ def export_multi_agent(args):
     conf = dict(
         env=args.env, num_agents=int(env.config["num_agents"]), lane_num=int(env.config["map_config"]["lane_num"]),
         exit_length=float(env.config["map_config"]["exit_length"]), entrance_length=float(FirstPGBlock.ENTRANCE_LENGTH),
+        map_config={k: v for k, v in dict(env.config["map_config"]).items() if isinstance(v, (int, float))},
         respawn_longitude=float(SpawnManager.RESPAWN_REGION_LONGITUDE), respawn_lateral=float(SpawnManager.RESPAWN_REGION_LATERAL),
         max_vehicle_length=float(SpawnManager.MAX_VEHICLE_LENGTH), max_vehicle_width=float(SpawnManager.MAX_VEHICLE_WIDTH),
         disable_u_turn=bool(getattr(env.engine.spawn_manager, "disable_u_turn", False)),
@@ -80,6 +83,7 @@ def main():
     ap.add_argument("--env", default="metadrive", choices=["metadrive", "safe", "ma_roundabout", "ma_intersection", "ma_bottleneck", "ma_bidirection", "ma_tollgate",
                              "ma_parkinglot"])
     ap.add_argument("--parking-spaces", type=int, default=0, help="ma_parkinglot: parking_space_num (default: the env's 8)")
+    ap.add_argument("--map-config", default=None, help="multi-agent envs: JSON of map_config overrides")
     ap.add_argument("--n", type=int, default=1000)
     ap.add_argument("--start", type=int, default=0)
     ap.add_argument("--density", type=float, default=None)

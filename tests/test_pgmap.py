@@ -227,3 +227,28 @@ def test_generated_multi_agent_maps_equal_the_exported_assets(asset):
     b, cb = ref.build_world(3, 8, seed=5)
     for k in a:
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+@pytest.mark.parametrize("env_name,asset", [("MultiAgentRoundaboutEnv", "ma_roundabout_3lanes.npz"),
+                                            ("MultiAgentIntersectionEnv", "ma_intersection_3lanes.npz"),
+                                            ("MultiAgentBottleneckEnv", "ma_bottleneck_neck30.npz"),
+                                            ("MultiAgentTollgateEnv", "ma_tollgate_6lanes.npz")])
+def test_multi_agent_envs_honour_map_config(env_name, asset):
+    """config["map_config"] of the multi-agent envs (lane_num / exit_length; bottleneck: neck_length ...; tollgate: toll_lane_num /
+    toll_length), read the way the reference's MA*Map classes read it: the map and spawn roads the env generates for a NON-default
+    map_config against the reference's export of the same config (oracle/gen_assets.py --env ma_* --map-config JSON)."""
+    import json
+    import metadrive_ped_b200.envs as E
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "libs", asset))
+    ref_mc = json.loads(str(d["config"]))["map_config"]
+    cls = getattr(E, env_name)
+    default_mc = cls.default_config()["map_config"]
+    override = {k: v for k, v in ref_mc.items() if default_mc.get(k) != v}
+    assert override, "the golden must hold a non-default map"
+    assert all(k in default_mc for k in override), "the env declares the reference's map_config keys"
+    lib = cls._make_library(E._merge(cls.default_config(), dict(map_config=override)))
+    np.testing.assert_array_equal(lib.table.lane_f, d["lane_f"])
+    np.testing.assert_array_equal(lib.table.lane_i, d["lane_i"])
+    np.testing.assert_array_equal(lib.table.road_i, d["road_i"])
+    np.testing.assert_array_equal(lib.spawn_roads, d["spawn_roads"])
+    assert lib.table.meta["nodes"] == json.loads(str(d["meta"]))["nodes"]
