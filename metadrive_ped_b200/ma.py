@@ -191,13 +191,17 @@ class MultiAgentLibrary:
             path = name if os.path.exists(name) else os.path.join(ASSET_DIR, name)
             d = np.load(path, allow_pickle=False)
         self.conf = json.loads(str(d["config"]))
-        if self.conf.get("disable_u_turn"):
-            raise NotImplementedError("destination draws without U-turns are not covered")
         self.table = sc.MapTable(np.asarray(d["lane_f"], np.float64), np.asarray(d["lane_i"], np.int32),
                                  np.asarray(d["road_i"], np.int32), json.loads(str(d["meta"])), int(self.conf["lane_num"]))
         self.geo = sc.build_map_geometry(self.table)
         self.spawn_roads = np.asarray(d["spawn_roads"], np.int32)
         self.dest_nodes = np.asarray(d["dest_nodes"], np.int32)
+        if self.conf.get("disable_u_turn") and self.dest_nodes.ndim == 1:
+            # MAIntersectionSpawnManager.update_destination_for on a one-lane intersection (marl_intersection.py:76-82, 103): the
+            # agent's own spawn road is no destination - one destination list per spawn road, without its own entry, so that the
+            # uniform draw over the list (reset-time scenario and k_respawn alike) is the reference's draw
+            R_ = len(self.dest_nodes)
+            self.dest_nodes = np.array([[self.dest_nodes[j] for j in range(R_) if j != i] for i in range(R_)], np.int32)
         self.veh_static = np.asarray(d["veh_static"], np.float32)
         self.objects = np.asarray(d["objects"], np.float64) if "objects" in d else np.zeros((0, 8))
         if self.conf.get("fixed_dest") or self.conf["env"] in ("ma_bottleneck", "ma_tollgate", "ma_bidirection"):

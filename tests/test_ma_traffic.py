@@ -47,3 +47,43 @@ def test_traffic_starts_when_an_agent_enters_the_trigger_road(oracle_lib):
         vi = sim.a["veh_i"].reshape(E, S, -1)
         started |= (vi[:, :, 2][traffic.reshape(E, S)].reshape(E, -1) != 0).any(1)
     assert started.all(), "every env's traffic was triggered by an agent driving onto the trigger road"
+
+
+def test_one_lane_intersection_draws_no_u_turn_destinations(oracle_lib):
+    """MultiAgentIntersectionEnv with map_config lane_num = 1: the reference's spawn manager never sends an agent back out of the
+    road it was born on (marl_intersection.py:76-82, 103).  Reset-time draws and on-device respawn draws (CPU oracle)."""
+    import metadrive_ped_b200.envs as E
+    from oracle.oracle import OracleSim
+    cls = E.MultiAgentIntersectionEnv
+    c = E._merge(cls.default_config(), dict(map_config=dict(lane_num=1), num_agents=8, delay_done=3))
+    lib = cls._make_library(c)
+    assert lib.conf["disable_u_turn"] and lib.dest_nodes.shape == (4, 3)
+    full = E.MultiAgentIntersectionEnv._make_library(E._merge(cls.default_config(), {})).dest_nodes   # 2 lanes: U-turns allowed
+    assert full.ndim == 1 and len(full) == 4
+    arrays, cfg = lib.build_world(4, 8, seed=3, **E._ma_cfg_kw(c))
+    assert cfg.ma_dests == 3
+    sim = OracleSim(arrays, cfg)
+    sim.reset_observe()
+    En, S, NA = cfg.n_envs, cfg.slots_per_env, cfg.agents_per_env
+    lane_road = {lane: ri for lane, _, ri in lib.slots}
+    all_dest = [int(x) for x in np.unique(lib.dest_nodes)]
+    forbidden = {ri: [d for d in all_dest if d not in [int(x) for x in lib.dest_nodes[ri]]] for ri in range(4)}
+    assert all(len(v) == 1 for v in forbidden.values())
+
+    def check(rows_i, rows_rt):
+        n = 0
+        for I, rt in zip(rows_i, rows_rt):
+            if I[0] == 1 and I[1]:
+                dest = int(rt[rt >= 0][-1])
+                assert dest != forbidden[lane_road[int(I[13])]][0], "an agent was sent back out of its own road"
+                n += 1
+        return n
+    assert check(sim.a["veh_i"], sim.a["veh_route"]) == 4 * 8
+    rng = np.random.RandomState(0)
+    born = 0
+    for t in range(250):
+        a = np.stack([rng.uniform(-0.5, 0.5, En * NA), rng.uniform(0.2, 1.0, En * NA)], 1).astype(np.float32)
+        sim.step(a)
+        check(sim.a["veh_i"], sim.a["veh_route"])
+        born += int(((sim.info_flags & 0x4000) != 0).sum())
+    assert born >= 8
