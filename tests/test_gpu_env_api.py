@@ -681,3 +681,28 @@ def test_ma_record_and_replay_episode():
             np.testing.assert_array_equal(o2[k], o[k], err_msg="obs of %s at step %d" % (k, t))
         assert all(i["replay_done"] == (t == len(log) - 1) for i in info.values())
     rep.close()
+
+
+def test_ma_envs_with_custom_map_config():
+    """map_config overrides of the multi-agent envs reach the generated map: a three-lane roundabout holds more spawn slots, a
+    one-lane intersection (no U-turn destinations) and a six-booth toll plaza step with respawns."""
+    from metadrive_ped_b200 import MultiAgentIntersectionEnv, MultiAgentRoundaboutEnv, MultiAgentTollgateEnv
+    env = MultiAgentRoundaboutEnv({"num_agents": -1, "map_config": {"lane_num": 3, "exit_length": 50}})
+    try:
+        obs, _ = env.reset()
+        assert len(obs) == 60 and env.config["map_config"]["lane_num"] == 3
+    finally:
+        env.close()
+    for cls, mc in ((MultiAgentIntersectionEnv, {"lane_num": 1}), (MultiAgentTollgateEnv, {"toll_lane_num": 6, "toll_length": 14})):
+        env = cls({"num_agents": 6, "delay_done": 3, "map_config": mc})
+        try:
+            obs, _ = env.reset()
+            seen = set(obs)
+            for step in range(150):
+                o, r, tm, tc, i = _ma_act(env, {k: [0.1, 0.8] for k in env.agents.keys()})
+                seen |= set(o)
+                if tm["__all__"]:
+                    break
+            assert len(seen) > 6, "newborns took over"
+        finally:
+            env.close()
