@@ -217,10 +217,9 @@ def _lane_follow_action(v, rs, noise, fast=32, slow=16, ahead=2.0, kh=2.5, kl=0.
 def _parking_action(name, v, rs):
     """Test-side driver for the parking-lot trace: slow lane following; the agents pull out one after the other (agent k waits
     100 k steps) and brake for an agent in front of them, so that some of them reach their parking space / the far end of a road."""
-    if v.engine.episode_step < int(os.environ.get("PK_WAIT", 100)) * int(name[5:]):
+    if v.engine.episode_step < 100 * int(name[5:]):
         return [0.0, 0.0]
-    a = _lane_follow_action(v, rs, 0.02, fast=float(os.environ.get("PK_FAST", 9)), slow=float(os.environ.get("PK_SLOW", 4)),
-                            ahead=float(os.environ.get("PK_AHEAD", 1.0)), kh=float(os.environ.get("PK_KH", 4.0)), kl=float(os.environ.get("PK_KL", 1.0)))
+    a = _lane_follow_action(v, rs, 0.02, fast=9.0, slow=4.0, ahead=1.0, kh=4.0, kl=1.0)
     hx, hy = np.cos(v.heading_theta), np.sin(v.heading_theta)
     for u in v.engine.agent_manager.active_agents.values():
         if u is v:
