@@ -186,16 +186,17 @@ def test_generator_reproduces_the_golden_episodes_scenes(tag):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/metadrive"), reason="needs the reference checkout (build container only)")
-@pytest.mark.parametrize("tag", ["cfg1_S_straight", "cfg4_safe_seed2"])
+@pytest.mark.parametrize("tag", ["cfg1_S_straight", "cfg4_safe_seed2", "cfg3_ma_intersection_others_navi"])
 def test_golden_fixtures_regenerate_identically(tag, tmp_path):
     """The committed recipe reproduces the committed fixtures: oracle/gen_golden.py runs ONE FRESH PROCESS PER TAG (the
-    reference leaks map constants through class attributes across env instances, see its main()), multi-agent episodes
-    are seeded.  Two small tags are regenerated here and compared array by array."""
+    reference leaks map constants through class attributes across env instances, see its main()) with PYTHONHASHSEED=0, multi-agent
+    episodes are seeded.  Two small single-agent tags and a multi-agent one (8 agents, respawns) are regenerated here and compared
+    array by array."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.check_call([sys.executable, "-m", "oracle.gen_golden", "--only", tag, "--exact", "--out", str(tmp_path)], cwd=root,
-                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=dict(os.environ, PYTHONHASHSEED="0"))
     new = np.load(os.path.join(str(tmp_path), tag + ".npz"))
     old = np.load(os.path.join(root, "tests", "golden", tag + ".npz"))
     assert sorted(new.files) == sorted(old.files)
