@@ -648,6 +648,9 @@ class MultiAgentMetaDrive:
         """The env's fixed map, generated from config["map_config"] the way the reference's MA*Map classes read it (lane_num,
         lane_width, exit_length; bottleneck: bottle_lane_num / neck_lane_num / neck_length; tollgate: toll_lane_num / toll_length)."""
         from .ma import MultiAgentLibrary
+        if cls.ASSET is None:
+            raise NotImplementedError("MultiAgentMetaDrive itself (agents on a BIG-generated map) is not covered: use one of the "
+                                      "multi-agent envs with a map of their own (roundabout, intersection, bottleneck, tollgate, parking lot)")
         mc = config["map_config"]
         chain = {k: mc[k] for k in ("neck_lane_num", "neck_length", "toll_lane_num", "toll_length") if k in mc}
         return MultiAgentLibrary(cls.ASSET, lane_num=int(mc.get("bottle_lane_num", mc["lane_num"])), lane_width=float(mc["lane_width"]),
