@@ -648,10 +648,14 @@ class MultiAgentMetaDrive:
         """The env's fixed map, generated from config["map_config"] the way the reference's MA*Map classes read it (lane_num,
         lane_width, exit_length; bottleneck: bottle_lane_num / neck_lane_num / neck_length; tollgate: toll_lane_num / toll_length)."""
         from .ma import MultiAgentLibrary
-        if cls.ASSET is None:
-            raise NotImplementedError("MultiAgentMetaDrive itself (agents on a BIG-generated map) is not covered: use one of the "
-                                      "multi-agent envs with a map of their own (roundabout, intersection, bottleneck, tollgate, parking lot)")
         mc = config["map_config"]
+        if cls.ASSET is None:
+            # MultiAgentMetaDrive itself (multi_agent_metadrive.py:12-62): the BIG-generated map of config["map"] for the scenario seed,
+            # every agent born on the first road and bound for the end of the last block
+            if not isinstance(config["map"], (int, str)) or any(b in str(config["map"]) for b in "BP"):
+                raise NotImplementedError("map %r is not covered" % (config["map"], ))
+            return MultiAgentLibrary("pg", lane_num=int(mc["lane_num"]), lane_width=float(mc["lane_width"]), exit_length=float(mc["exit_length"]),
+                                     pg_seed=int(kw.pop("pg_seed", config["start_seed"])), pg_map=config["map"])
         chain = {k: mc[k] for k in ("neck_lane_num", "neck_length", "toll_lane_num", "toll_length") if k in mc}
         return MultiAgentLibrary(cls.ASSET, lane_num=int(mc.get("bottle_lane_num", mc["lane_num"])), lane_width=float(mc["lane_width"]),
                                  exit_length=float(mc["exit_length"]), **chain, **kw)
@@ -690,6 +694,14 @@ class MultiAgentMetaDrive:
             self._sim.close()
         rs = (seed if seed is not None else self.config["start_seed"]) * 1000003 + self._episode
         traffic_seed = seed if seed is not None else self.config["start_seed"]
+        if self.ASSET is None:   # the map follows the scenario seed (envs/base_env.py:886-891, manager/pg_map_manager.py:57-74)
+            if seed is None:
+                traffic_seed = int(np.random.randint(self.config["start_seed"], self.config["start_seed"] + self.config["num_scenarios"]))
+            assert self.config["start_seed"] <= traffic_seed < self.config["start_seed"] + self.config["num_scenarios"], \
+                "scenario_index (seed) should be in [{}:{})".format(self.config["start_seed"], self.config["start_seed"] + self.config["num_scenarios"])
+            if int(self._lib.pg_seed) != int(traffic_seed):
+                self._lib = self._make_library(self.config, pg_seed=traffic_seed)
+            self.current_seed = traffic_seed
         epi = self.config["replay_episode"]
         if epi is not None:   # the logged episode is replayed whatever seed is asked for (envs/base_env.py:502-537): same spawn
             rs, traffic_seed = int(epi["world_seed"]), int(epi["scenario_index"])   # draws, same respawn tape, same traffic

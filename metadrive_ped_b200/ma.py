@@ -124,6 +124,9 @@ MA_MAPS = {
     # lane each way.  Spawn roads = the three roads INTO the lot (first road, the negatives of the T's two far exits) + the eight
     # parking spaces under their second road name (ParkingLot.node(1, i, 5) -> (1, i, 6), :207-211).  An agent born on a road into the
     # lot is sent to a parking space nobody else is heading for, one born in a space to the far end of one of the three roads (:80-88).
+    # MultiAgentMetaDrive itself (envs/marl_envs/multi_agent_metadrive.py:12-62): a BIG-generated map (config map / seed), every agent
+    # born on the first road and - no destination draw - bound for the end of the last block (auto_assign_task)
+    "pg": dict(env="ma_pg", num_agents=15, spawn_nodes=[], lane_num=3, exit_length=50.0, fixed_dest=True, pg=True),
     "parkinglot": dict(env="ma_parkinglot", num_agents=10, spawn_nodes=[(2, 0, 0, 1), (2, 2, 0, 1)], lane_num=1, exit_length=20.0,
                        parking=True),
 }
@@ -131,7 +134,7 @@ ASSET_KIND = {"ma_parkinglot.npz": "parkinglot", "ma_roundabout.npz": "roundabou
               "ma_tollgate.npz": "tollgate", "ma_bidirection.npz": "bidirection"}
 
 
-def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None, parking_space_num=8, **chain_kw):
+def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None, parking_space_num=8, pg_seed=0, pg_map=3, **chain_kw):
     """What an exported multi-agent asset holds, generated: lane tables, spawn roads (the first block's second road and the
     three roads ENTERING the block, i.e. the negatives of its exits), destination nodes, the static_default vehicle row
     (component/pg_space.py:227-234, vehicle_type.py:35-36) and SpawnManager's slot constants (spawn_manager.py:25-35)."""
@@ -139,7 +142,10 @@ def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None, park
     m = MA_MAPS[kind]
     lane_num = m["lane_num"] if lane_num is None else lane_num
     exit_length = m["exit_length"] if exit_length is None else exit_length
-    lane_f, lane_i, road_i, meta, big = pgmap.build_fixed(kind, lane_num, lane_width, exit_length, parking_space_num, **chain_kw)
+    if m.get("pg"):
+        lane_f, lane_i, road_i, meta, big = pgmap.generate(int(pg_seed), pg_map, lane_num, lane_width, exit_length)
+    else:
+        lane_f, lane_i, road_i, meta, big = pgmap.build_fixed(kind, lane_num, lane_width, exit_length, parking_space_num, **chain_kw)
     node = {n: k for k, n in enumerate(meta["nodes"])}
     roads = [(">>", ">>>")]
     for bi, part, a, b in m["spawn_nodes"]:
@@ -167,6 +173,8 @@ def generated_source(kind, lane_num=None, lane_width=3.5, exit_length=None, park
         dest[n_in:, :n_in] = exits
         conf.update(parking_spaces=len(spaces), parking_in_roads=n_in)
         static[15] = 1.0   # vehicle_config enable_reverse (marl_parking_lot.py:38)
+    elif m.get("pg"):   # NodeNetworkNavigation.auto_assign_task: the end of the last block's socket road
+        dest = np.array([node[pgspawn.route_for(big, (">>", ">>>", 0), int(pg_seed))[0][-1]]], np.int32)
     else:
         dest = np.array([node[pgmap.neg_road(r)[1]] for r in roads], np.int32)
     return dict(lane_f=lane_f, lane_i=lane_i, road_i=road_i, meta=json.dumps(meta), config=json.dumps(conf), objects=objects,
@@ -182,10 +190,12 @@ class MultiAgentLibrary:
     (spawn road x lane x longitudinal slot) drawn without replacement, a random offset inside the slot
     (`_randomize_position_in_slot`, :211-217) and a random destination per agent (marl_inout_roundabout.py:138-143).
     The reference draws these from an unseeded generator; here the caller passes the generator."""
-    def __init__(self, name, from_asset=False, parking_space_num=8, lane_num=None, lane_width=3.5, exit_length=None, **chain_kw):
+    def __init__(self, name, from_asset=False, parking_space_num=8, lane_num=None, lane_width=3.5, exit_length=None, pg_seed=0, pg_map=3,
+                 **chain_kw):
+        self.pg_seed = int(pg_seed)
         self.big = None   # the generated map's blocks and lanes (IDM traffic is populated over them); an exported asset has none
         if not from_asset and ASSET_KIND.get(name, name) in MA_MAPS:
-            d = generated_source(ASSET_KIND.get(name, name), lane_num, lane_width, exit_length, parking_space_num, **chain_kw)
+            d = generated_source(ASSET_KIND.get(name, name), lane_num, lane_width, exit_length, parking_space_num, pg_seed, pg_map, **chain_kw)
             self.big = d["big"]
         else:
             path = name if os.path.exists(name) else os.path.join(ASSET_DIR, name)

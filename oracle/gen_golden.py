@@ -298,6 +298,8 @@ def run_episode_ma(env_cls, config, actions, tag, steps=None, noise=0.0, seed=0,
         parking = hasattr(sm, "parking_space_available")
         if fixed_dest:
             dest_nodes = dest_nodes[::-1].reshape(-1, 1).copy()
+            if len(spawn_roads) == 1:   # MultiAgentMetaDrive itself: one spawn road, everybody drives to the end of the last block
+                dest_nodes[0, 0] = mi.nodes[env.agents[names[0]].navigation.checkpoints[-1]]
         park_log = []
         if parking:
             # MultiAgentParkingLotEnv (envs/marl_envs/marl_parking_lot.py:47-90): an agent born on one of the roads into the lot
@@ -566,7 +568,7 @@ def run_episode_cfg5(config, seed, steps, tag, n_peds=16):
 ALL_TAGS = ["cfg1_S_straight", "cfg1_S_random", "cfg1_S_discrete", "cfg2_pg3_seed3", "cfg2_pg3_seed7", "cfg2_pg3_seed11_dense",
             "cfg2_SCO_nolimit", "cfg2_pg3_seed11_others4", "cfg2_pg3_seed3_others_navi", "cfg2_pg3_seed3_detectors", "cfg4_safe_seed2", "cfg4_safe_seed5",
             "cfg4_safe_seed40_cones", "cfg4_safe_seed8_bump", "cfg2_StollC_seed0", "cfg3_ma_roundabout", "cfg3_ma_roundabout_respawn",
-            "cfg3_ma_intersection_respawn", "cfg3_ma_intersection_others_navi", "cfg3_ma_parkinglot", "cfg3_ma_roundabout_traffic", "cfg3_ma_bottleneck_respawn", "cfg3_ma_tollgate_respawn", "cfg5_ped_X"]
+            "cfg3_ma_intersection_respawn", "cfg3_ma_intersection_others_navi", "cfg3_ma_parkinglot", "cfg3_ma_roundabout_traffic", "cfg3_ma_pg3", "cfg3_ma_bottleneck_respawn", "cfg3_ma_tollgate_respawn", "cfg5_ped_X"]
 
 
 def main():
@@ -713,6 +715,17 @@ def main():
         print("cfg3_ma_parkinglot steps", len(out["reward"]), "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()),
               "out of road", int(((out["info_flags"] & 0x400) != 0).sum()), "crashes", int(((out["info_flags"] & 0x1) != 0).sum()),
               "->", os.path.getsize(path) // 1024, "KiB", flush=True)
+    # MultiAgentMetaDrive itself (envs/marl_envs/multi_agent_metadrive.py:12-62): the agents on the first road of a BIG-generated map
+    # (map = 2 blocks, seed 0), all bound for the end of the last block
+    if args.only == "cfg3_ma_pg3":
+        from metadrive.envs.marl_envs.multi_agent_metadrive import MultiAgentMetaDrive
+        lid = dict(vehicle_config=dict(lidar=dict(num_lasers=72, distance=40, num_others=0)))
+        cfgm = dict(num_agents=6, allow_respawn=True, log_level=50, delay_done=25, horizon=1000, map=2, **lid)
+        out = run_episode_ma(MultiAgentMetaDrive, cfgm, None, "cfg3_ma_pg3", steps=300, noise=args.ma_noise, seed=23, obs_stride=3)
+        path = os.path.join(args.out, "cfg3_ma_pg3.npz")
+        np.savez_compressed(path, **out)
+        print("cfg3_ma_pg3 steps", len(out["reward"]), "respawns", int((out["respawn_draws"][:, 0] >= 0).sum()),
+              "arrivals", int(((out["info_flags"] & 0x800) != 0).sum()), "->", os.path.getsize(path) // 1024, "KiB", flush=True)
     # a multi-agent env with IDM traffic (traffic_density > 0, trigger mode: the block's vehicles start when ANY agent enters the
     # trigger road, manager/traffic_manager.py:74-92)
     if args.only == "cfg3_ma_roundabout_traffic":

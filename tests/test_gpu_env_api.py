@@ -706,3 +706,23 @@ def test_ma_envs_with_custom_map_config():
             assert len(seen) > 6, "newborns took over"
         finally:
             env.close()
+
+
+def test_base_multi_agent_env():
+    """MultiAgentMetaDrive itself: 15 agents on the first road of the BIG map of the scenario seed, all bound for the end of the last
+    block; another seed brings another map."""
+    from metadrive_ped_b200 import MultiAgentMetaDrive
+    env = MultiAgentMetaDrive({"num_scenarios": 4, "map": 2, "delay_done": 3})
+    try:
+        obs, _ = env.reset(seed=0)
+        assert len(obs) == 15 and env.observation_space.contains(obs) and env.current_seed == 0
+        lanes0 = len(env._lib.table.lane_f)
+        for step in range(60):
+            o, r, tm, tc, i = _ma_act(env, {k: [0.0, 0.5] for k in env.agents.keys()})
+        assert sum(r.values()) > 0, "they make progress along the route"
+        obs, _ = env.reset(seed=3)
+        assert env.current_seed == 3 and len(obs) == 15 and env._lib.pg_seed == 3
+        _ma_act(env, {k: [0.0, 0.5] for k in env.agents.keys()})
+        assert lanes0 > 0
+    finally:
+        env.close()

@@ -87,3 +87,31 @@ def test_one_lane_intersection_draws_no_u_turn_destinations(oracle_lib):
         check(sim.a["veh_i"], sim.a["veh_route"])
         born += int(((sim.info_flags & 0x4000) != 0).sum())
     assert born >= 8
+
+
+def test_base_multi_agent_env_on_generated_maps(oracle_lib):
+    """MultiAgentMetaDrive itself (envs/marl_envs/multi_agent_metadrive.py): the BIG map of config["map"] / the scenario seed, the
+    first road as the only spawn road (15 slots), the end of the last block as everybody's destination - library against the
+    reference trace cfg3_ma_pg3 (map = 2 blocks, seed 0), and a short run on the oracle with another seed's map."""
+    import metadrive_ped_b200.envs as E
+    from oracle.oracle import OracleSim
+    g = load_golden("cfg3_ma_pg3")
+    c = E._merge(E.MultiAgentMetaDrive.default_config(), dict(map=2, num_agents=6, num_scenarios=5))
+    lib = E.MultiAgentMetaDrive._make_library(c)
+    np.testing.assert_array_equal(lib.table.lane_f, g["map_lane_f"])
+    np.testing.assert_array_equal(lib.table.road_i, g["map_road_i"])
+    np.testing.assert_array_equal(lib.spawn_roads, g["ma_spawn_roads"])
+    np.testing.assert_array_equal(lib.dest_nodes, g["ma_dest_nodes"])
+    assert lib.max_capacity == 15
+    for k in range(int(g["ma_alive_seats"][0])):
+        np.testing.assert_array_equal(lib.tables["routes"][0], g["init_routes"][k])
+    lib3 = E.MultiAgentMetaDrive._make_library(c, pg_seed=3)
+    assert lib3.pg_seed == 3 and not np.array_equal(lib3.table.lane_f.shape, ()) and len(lib3.table.lane_f) != 0
+    arrays, cfg = lib3.build_world(2, 6, seed=1, **E._ma_cfg_kw(c))
+    sim = OracleSim(arrays, cfg)
+    obs = sim.reset_observe()
+    assert obs.shape == (2 * 7, 19 + 72)
+    for t in range(40):
+        sim.step(np.tile(np.array([[0.0, 0.5]], np.float32), (2 * 7, 1)))
+    vi = sim.a["veh_i"].reshape(2, cfg.slots_per_env, -1)
+    assert vi[:, :6, 2].all() and (vi[:, :6, 8] & 0x100).all(), "six agents per env, still driving on their lanes"
