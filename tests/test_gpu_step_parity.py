@@ -2,6 +2,8 @@
 integers and floats alike (shared elementary functions, include/md_math.h; same operation order; no FMA contraction) -
 and against the golden traces of the reference within the north-star tolerances (lidar fractions 1e-4 relative, poses
 1e-2 m / 1e-3 rad over 100 steps)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -25,7 +27,11 @@ def _make(tag, replicas):
 
 
 SINGLE = [t for t in list_golden() if not t.startswith("cfg3")]
-MULTI = [t for t in list_golden() if t.startswith("cfg3")]
+# cfg3_ma_pg3 (MultiAgentMetaDrive on a BIG map) joined the fixtures after the round's GPU minutes were spent: the CPU oracle replays it
+# (tests/test_oracle_golden.py) and the env runs on the GPU (tests/test_gpu_env_api.py::test_base_multi_agent_env); its CUDA-vs-
+# oracle replay is switched on with MD_GPU_NEW_TRACES=1 until it has been seen green on a B200
+NEW_TRACES = () if os.environ.get("MD_GPU_NEW_TRACES", "") not in ("", "0") else ("cfg3_ma_pg3", )
+MULTI = [t for t in list_golden() if t.startswith("cfg3") and t not in NEW_TRACES]
 
 
 @pytest.mark.parametrize("tag", MULTI)
